@@ -1,0 +1,176 @@
+/* libvcpenc — C ABI of the B200-native H.264 encoder that replaces the `ffmpeg` child
+ * process of the VCP consumer.
+ *
+ * Reference interfaces replaced (all paths relative to /root/reference):
+ *   vcpenc_transcode      <- runFFmpegWithTimeout(ctx,input,output,ffmpegArgs,timeout)
+ *                            cmd/consumer.go:370-394 (argv built at :376-380)
+ *   vcpenc_verify         <- verifyOutputFile(path)           cmd/consumer.go:396-419
+ *   vcpenc_parse_args     <- the option grammar of the preset strings
+ *                            internal/config/config.go:44-52 after strings.Fields (:378)
+ *   vcpenc_device_count   <- CUDA_VISIBLE_DEVICES convention  install.sh:279-297
+ *   vcpenc_encode_frames, vcpenc_session_...: the in-memory core underneath (no reference
+ *                            analogue; the reference hides this inside the ffmpeg process)
+ *
+ * Rules: plain pointers and sizes only; thread-safe and re-entrant; never aborts the
+ * process; every failure is a non-zero return plus a message in `err`.  There is no CPU
+ * fallback: with no usable CUDA device every encode entry point fails with
+ * VCPENC_E_NODEVICE.
+ */
+#ifndef VCPENC_H
+#define VCPENC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* error classes (return values) */
+#define VCPENC_OK 0
+#define VCPENC_E_ARGS 1        /* malformed / unsupported option tokens            */
+#define VCPENC_E_IO 2          /* cannot read input / write output                 */
+#define VCPENC_E_FORMAT 3      /* input container or pixel format not understood   */
+#define VCPENC_E_NODEVICE 4    /* no CUDA device (there is no CPU fallback)        */
+#define VCPENC_E_CUDA 5        /* CUDA runtime error                               */
+#define VCPENC_E_CANCELLED 6   /* *cancel became non-zero  ("任务被取消")           */
+#define VCPENC_E_TIMEOUT 7     /* timeout_ms elapsed       ("编码超时")             */
+#define VCPENC_E_NOTENCODE 8   /* preset is not a video encode (-c copy, -vn): the
+                                  caller should hand the task to a stock ffmpeg    */
+#define VCPENC_E_AUDIO 9       /* input has audio that would need encoding         */
+#define VCPENC_E_VERIFY 10     /* verify: no valid video stream ("无有效视频流")     */
+#define VCPENC_E_OVERFLOW 11   /* output buffer too small                          */
+#define VCPENC_E_INTERNAL 12
+
+/* codecs */
+#define VCPENC_CODEC_H264 0
+#define VCPENC_CODEC_HEVC 1
+
+/* rate-control modes */
+#define VCPENC_RC_CQP 0        /* constant QP (also what -crf maps to)             */
+#define VCPENC_RC_ABR 1        /* -b:v target, per-GOP budget                      */
+
+/* input pixel formats accepted by the colour-convert kernel (K1) */
+#define VCPENC_FMT_YUV420P 0
+#define VCPENC_FMT_NV12 1
+#define VCPENC_FMT_RGB24 2
+#define VCPENC_FMT_YUV444P 3
+#define VCPENC_FMT_YUV422P 4
+#define VCPENC_FMT_BGR24 5
+
+typedef struct vcpenc_params {
+    int32_t width, height;     /* luma size of the OUTPUT picture (display size)    */
+    int32_t fps_num, fps_den;
+    int32_t codec;             /* VCPENC_CODEC_*                                    */
+    int32_t gop;               /* closed-GOP length in frames (-g), IDR period      */
+    int32_t rc_mode;           /* VCPENC_RC_*                                       */
+    int32_t qp_i, qp_p;        /* CQP values / ABR starting point                   */
+    int32_t bitrate;           /* bits per second for ABR (-b:v)                    */
+    int32_t maxrate, bufsize;  /* -maxrate / -bufsize (bits, bits)                  */
+    int32_t slices;            /* slices per picture (-slices)                      */
+    int32_t deblock_idc;       /* disable_deblocking_filter_idc: 0 on, 1 off, 2 on
+                                  but not across slice edges                        */
+    int32_t entropy;           /* 0 CAVLC (-coder 0), 1 CABAC (-coder 1)            */
+    int32_t in_fmt;            /* VCPENC_FMT_* of the frames handed in              */
+    int32_t in_width, in_height; /* size of the frames handed in (0 = same as out)  */
+    int32_t faststart;         /* -movflags +faststart: moov before mdat            */
+    int32_t effort;            /* from -preset / -tune: 0 fast .. 2 slow            */
+    int32_t reserved[12];
+} vcpenc_params;
+
+/* per coded picture, filled by the encode calls */
+typedef struct vcpenc_frame_info {
+    uint64_t offset;           /* byte offset of the access unit in the output      */
+    uint32_t size;             /* bytes (Annex-B, incl. start codes, SPS/PPS on IDR) */
+    uint8_t  is_idr;
+    uint8_t  qp;
+    uint8_t  pad[2];
+} vcpenc_frame_info;
+
+/* per-kernel device timing, accumulated while profiling is enabled on a session */
+#define VCPENC_K_CSC 0         /* K1 colour convert / pad / half-res pyramid        */
+#define VCPENC_K_ME_PRE 1      /* K2a motion search pre-pass on originals           */
+#define VCPENC_K_ME_REFINE 2   /* K2b full/half/quarter-pel refine on recon         */
+#define VCPENC_K_P_RECON 3     /* K3 inter predict + T/Q/IQ/IT + recon              */
+#define VCPENC_K_I_RECON 4     /* K3 intra predict + T/Q/IQ/IT + recon (wavefront)  */
+#define VCPENC_K_MBINFO 5      /* mv prediction / skip / boundary strengths         */
+#define VCPENC_K_DEBLOCK 6     /* K4 in-loop deblocking (wavefront)                 */
+#define VCPENC_K_PAD 7         /* border extension of the reconstructed picture     */
+#define VCPENC_K_CAVLC_COUNT 8 /* K5 pass 1: bits per macroblock                    */
+#define VCPENC_K_CAVLC_SCAN 9  /* K5 pass 2: per-slice prefix sums + slice headers  */
+#define VCPENC_K_CAVLC_WRITE 10/* K5 pass 3: bit-exact placement into the RBSP      */
+#define VCPENC_K_RC 11         /* rate-control update                               */
+#define VCPENC_K_COUNT 12
+
+typedef struct vcpenc_kernel_stat {
+    double   ms;               /* summed CUDA-event time                            */
+    uint64_t launches;
+} vcpenc_kernel_stat;
+
+/* ---- the two calls the consumer makes -------------------------------------------- */
+
+/* Transcode `input` to `output` as the argv `ffmpeg -hide_banner -loglevel warning -y -i
+ * input <argv...> output` would.  argv == strings.Fields(task.FFmpegArgs).  `cancel` is
+ * polled at least once per GOP batch and replaces the SIGKILL that exec.CommandContext
+ * delivers; timeout_ms <= 0 means none.  The callee creates/truncates `output`; on
+ * failure the caller removes it (cmd/consumer.go:264). */
+int vcpenc_transcode(const char* input, const char* output, int argc, const char* const* argv,
+                     int timeout_ms, volatile int* cancel, char* err, size_t errlen);
+
+/* ffprobe-equivalent acceptance check: file exists, size > 0, container parses and has a
+ * video stream.  0 = ok. */
+int vcpenc_verify(const char* path, char* err, size_t errlen);
+
+/* ---- supporting entry points ---------------------------------------------------------- */
+
+int vcpenc_device_count(void);           /* honours CUDA_VISIBLE_DEVICES; 0 if none    */
+const char* vcpenc_version(void);
+void vcpenc_default_params(vcpenc_params* p);
+
+/* Parse preset tokens into params (codec, rc, gop, ...).  Returns VCPENC_E_NOTENCODE for
+ * `-c copy` / `-vn`, VCPENC_E_ARGS for unknown tokens. Host-only, needs no GPU. */
+int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_params* p, char* err,
+                      size_t errlen);
+
+/* Encode `nframes` frames held in HOST memory (tightly packed, p->in_fmt) on `device`;
+ * GOPs are independent, so a caller may shard a clip by calling this once per GOP range.
+ * Output: Annex-B byte stream in `out` (SPS/PPS in front of every IDR), one
+ * vcpenc_frame_info per frame.  `recon` (optional, may be NULL) receives the encoder's
+ * reconstructed pictures, yuv420p, display size — what a conformant decoder must output. */
+int vcpenc_encode_frames(const vcpenc_params* p, int device, const uint8_t* frames,
+                         int nframes, uint8_t* out, size_t out_cap, size_t* out_len,
+                         vcpenc_frame_info* info, uint8_t* recon, volatile int* cancel,
+                         char* err, size_t errlen);
+
+/* Session API: keeps frames resident in HBM so the encode can be timed on the device. */
+typedef struct vcpenc_session vcpenc_session;
+int vcpenc_session_create(const vcpenc_params* p, int device, int max_frames,
+                          vcpenc_session** out, char* err, size_t errlen);
+/* copy host frames to the device and run K1 (convert, pad, pyramid) */
+int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes, char* err,
+                          size_t errlen);
+/* run K2..K5 over the resident frames; bitstream stays on the device.  If `ms` is given
+ * it receives the CUDA-event time of the whole pass (events recorded on the launching
+ * stream). */
+int vcpenc_session_encode(vcpenc_session* s, float* ms, char* err, size_t errlen);
+/* fetch the bitstream (and optionally recon) of the last encode */
+int vcpenc_session_download(vcpenc_session* s, uint8_t* out, size_t out_cap, size_t* out_len,
+                            vcpenc_frame_info* info, uint8_t* recon, char* err, size_t errlen);
+/* per-kernel CUDA-event timing: enable, then encode, then read VCPENC_K_COUNT stats */
+int vcpenc_session_profile(vcpenc_session* s, int enable);
+int vcpenc_session_kernel_stats(vcpenc_session* s, vcpenc_kernel_stat* stats /*[K_COUNT]*/);
+/* debug/parity taps: motion vectors (int16 x,y per MB per frame, quarter-pel) and MB types */
+int vcpenc_session_debug_mbs(vcpenc_session* s, int16_t* mv_prepass, int16_t* mv_final,
+                             uint8_t* mb_type, uint8_t* cbp);
+void vcpenc_session_destroy(vcpenc_session* s);
+
+/* Wrap an Annex-B stream produced above into an MP4 file (avc1/avcC, moov-first when
+ * faststart).  Host-only. */
+int vcpenc_mux_mp4(const vcpenc_params* p, const uint8_t* annexb, size_t len,
+                   const vcpenc_frame_info* info, int nframes, const char* path, char* err,
+                   size_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCPENC_H */

@@ -1,0 +1,1118 @@
+/* oracle/h264_oracle.c — CPU restatement of the hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this file's shared object.  It is never linked into libvcpenc and is not a
+ * fallback of the product.
+ *
+ * What it restates.  The reference's hot path is `runFFmpegWithTimeout`
+ * (/root/reference/cmd/consumer.go:370-394), which spawns a system `ffmpeg`; the codec
+ * arithmetic is therefore in a third-party binary that is absent from /root/reference and
+ * from this image (unpinned version, /root/reference/install.sh:90-99; encoders libx264 /
+ * h264_nvenc selected by internal/config/config.go:45-50).  There is no reference source
+ * file to follow and the reference holds no test or golden vector for this path:
+ *
+ *     PARITY UNPINNED against the reference's own encoder output.
+ *
+ * The oracle instead restates the *published* algorithm — ITU-T H.264 (intra 16x16 /
+ * P_L0_16x16 / P_Skip prediction, 4x4 integer transform, quantisation, CAVLC, in-loop
+ * deblocking, Annex-B) — as a scalar, sequential, macroblock-raster-order encoder, and is
+ * pinned by the arbiter the north-star names: the FFmpeg h264 decoder (bundled libavcodec)
+ * must decode its stream to exactly the reconstruction it reports (tests/test_oracle.py).
+ * The CUDA path must then emit the same bytes as this oracle on the same input.
+ *
+ * Encoder-side (non-normative) decisions follow video_codec_pipeline_b200/csrc/vcp_algo.h.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define VCP_TAB static const
+#include "../video_codec_pipeline_b200/csrc/h264_tables.h"
+#include "../video_codec_pipeline_b200/csrc/vcp_algo.h"
+#include "../include/vcpenc.h"
+
+/* ------------------------------------------------------------------------------------ */
+/* bit writer                                                                            */
+typedef struct {
+    uint8_t* buf;
+    size_t cap, pos; /* bytes */
+    uint32_t cur;    /* bits accumulated */
+    int nbits;
+    int overflow;
+} BW;
+
+static void bw_init(BW* b, uint8_t* buf, size_t cap) {
+    b->buf = buf; b->cap = cap; b->pos = 0; b->cur = 0; b->nbits = 0; b->overflow = 0;
+}
+static void bw_put(BW* b, int n, uint32_t v) { /* n <= 24 */
+    while (n > 0) {
+        int take = n > 8 ? 8 : n;
+        uint32_t part = (v >> (n - take)) & ((1u << take) - 1);
+        b->cur = (b->cur << take) | part;
+        b->nbits += take;
+        n -= take;
+        while (b->nbits >= 8) {
+            uint8_t byte = (uint8_t)(b->cur >> (b->nbits - 8));
+            if (b->pos < b->cap) b->buf[b->pos++] = byte; else b->overflow = 1;
+            b->nbits -= 8;
+        }
+    }
+}
+static void bw_put32(BW* b, uint32_t v) { bw_put(b, 16, v >> 16); bw_put(b, 16, v & 0xffff); }
+static void bw_ue(BW* b, unsigned k) {
+    unsigned x = k + 1; int n = 0;
+    while ((x >> n) > 1) n++;
+    bw_put(b, n, 0);
+    bw_put(b, n + 1, x);
+}
+static void bw_se(BW* b, int v) { bw_ue(b, v <= 0 ? (unsigned)(-2 * v) : (unsigned)(2 * v - 1)); }
+static void bw_trailing(BW* b) {
+    bw_put(b, 1, 1);
+    if (b->nbits) bw_put(b, 8 - b->nbits, 0);
+}
+static size_t bw_bits(const BW* b) { return b->pos * 8 + b->nbits; }
+
+/* NAL unit: start code + header + emulation-prevented payload */
+static size_t nal_write(uint8_t* out, size_t cap, int ref_idc, int type, const uint8_t* rbsp, size_t n) {
+    size_t o = 0; int zeros = 0;
+    if (cap < 5) return 0;
+    out[o++] = 0; out[o++] = 0; out[o++] = 0; out[o++] = 1;
+    out[o++] = (uint8_t)((ref_idc << 5) | type);
+    for (size_t i = 0; i < n; i++) {
+        if (zeros >= 2 && rbsp[i] <= 3) { if (o >= cap) return 0; out[o++] = 3; zeros = 0; }
+        if (o >= cap) return 0;
+        out[o++] = rbsp[i];
+        zeros = rbsp[i] == 0 ? zeros + 1 : 0;
+    }
+    return o;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* frames                                                                                */
+typedef struct {
+    int w, h;         /* coded luma size */
+    int ys, cs;       /* strides */
+    uint8_t *ybuf, *ubuf, *vbuf;
+    uint8_t *y, *u, *v; /* pixel (0,0) */
+} Frame;
+
+static int frame_alloc(Frame* f, int w, int h) {
+    f->w = w; f->h = h;
+    f->ys = w + 2 * VCP_PAD; f->cs = w / 2 + 2 * VCP_PADC;
+    f->ybuf = (uint8_t*)malloc((size_t)f->ys * (h + 2 * VCP_PAD));
+    f->ubuf = (uint8_t*)malloc((size_t)f->cs * (h / 2 + 2 * VCP_PADC));
+    f->vbuf = (uint8_t*)malloc((size_t)f->cs * (h / 2 + 2 * VCP_PADC));
+    if (!f->ybuf || !f->ubuf || !f->vbuf) return -1;
+    f->y = f->ybuf + (size_t)VCP_PAD * f->ys + VCP_PAD;
+    f->u = f->ubuf + (size_t)VCP_PADC * f->cs + VCP_PADC;
+    f->v = f->vbuf + (size_t)VCP_PADC * f->cs + VCP_PADC;
+    return 0;
+}
+static void frame_free(Frame* f) { free(f->ybuf); free(f->ubuf); free(f->vbuf); }
+
+static void plane_pad(uint8_t* p, int stride, int w, int h, int pad) {
+    for (int y = 0; y < h; y++) {
+        uint8_t* r = p + (size_t)y * stride;
+        memset(r - pad, r[0], pad);
+        memset(r + w, r[w - 1], pad);
+    }
+    for (int y = 1; y <= pad; y++) {
+        memcpy(p - (size_t)y * stride - pad, p - pad, w + 2 * pad);
+        memcpy(p + (size_t)(h - 1 + y) * stride - pad, p + (size_t)(h - 1) * stride - pad, w + 2 * pad);
+    }
+}
+static void frame_pad(Frame* f) {
+    plane_pad(f->y, f->ys, f->w, f->h, VCP_PAD);
+    plane_pad(f->u, f->cs, f->w / 2, f->h / 2, VCP_PADC);
+    plane_pad(f->v, f->cs, f->w / 2, f->h / 2, VCP_PADC);
+}
+
+/* K1 restated: load a display-size yuv420p picture into the coded-size padded frame
+ * (replicating the last column/row up to the macroblock grid, then the border). */
+static void plane_load(uint8_t* dst, int ds, int cw, int ch, const uint8_t* src, int sw, int sh) {
+    for (int y = 0; y < ch; y++) {
+        const uint8_t* s = src + (size_t)(y < sh ? y : sh - 1) * sw;
+        uint8_t* d = dst + (size_t)y * ds;
+        memcpy(d, s, sw);
+        for (int x = sw; x < cw; x++) d[x] = s[sw - 1];
+    }
+}
+static void frame_load_yuv420p(Frame* f, const uint8_t* src, int w, int h) {
+    int cw = (w + 1) / 2, chh = (h + 1) / 2;
+    plane_load(f->y, f->ys, f->w, f->h, src, w, h);
+    plane_load(f->u, f->cs, f->w / 2, f->h / 2, src + (size_t)w * h, cw, chh);
+    plane_load(f->v, f->cs, f->w / 2, f->h / 2, src + (size_t)w * h + (size_t)cw * chh, cw, chh);
+    frame_pad(f);
+}
+
+/* half-resolution luma with border VCP_PAD1, computed from the padded full-res plane */
+typedef struct { int w, h, s; uint8_t* buf; uint8_t* p; } Half;
+static int half_alloc(Half* hf, int w, int h) {
+    hf->w = w / 2; hf->h = h / 2; hf->s = hf->w + 2 * VCP_PAD1;
+    hf->buf = (uint8_t*)malloc((size_t)hf->s * (hf->h + 2 * VCP_PAD1));
+    if (!hf->buf) return -1;
+    hf->p = hf->buf + (size_t)VCP_PAD1 * hf->s + VCP_PAD1;
+    return 0;
+}
+static void half_build(Half* hf, const Frame* f) {
+    for (int y = -VCP_PAD1; y < hf->h + VCP_PAD1; y++)
+        for (int x = -VCP_PAD1; x < hf->w + VCP_PAD1; x++) {
+            const uint8_t* s = f->y + (size_t)(2 * y) * f->ys + 2 * x;
+            hf->p[(size_t)y * hf->s + x] = (uint8_t)((s[0] + s[1] + s[f->ys] + s[f->ys + 1] + 2) >> 2);
+        }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* per-macroblock record                                                                  */
+typedef struct {
+    uint8_t type;        /* VCP_MB_* */
+    uint8_t i16_mode, chroma_mode;
+    uint8_t cbp;         /* luma bits 0..3 | chroma << 4 */
+    int16_t mv[2];       /* quarter-pel */
+    int16_t mvd[2];
+    uint8_t nnz_y[16];   /* raster (y*4+x) total_coeff of each luma 4x4 (AC only for I16) */
+    uint8_t nnz_c[2][4]; /* raster (y*2+x), AC */
+    int16_t lv[VCP_LV_STRIDE];
+} MB;
+
+/* ------------------------------------------------------------------------------------ */
+/* transform / quant                                                                      */
+static void fdct4(const int d[16], int w[16]) {
+    int t[16];
+    for (int i = 0; i < 4; i++) {
+        int a0 = d[4 * i] + d[4 * i + 3], a1 = d[4 * i + 1] + d[4 * i + 2];
+        int a2 = d[4 * i + 1] - d[4 * i + 2], a3 = d[4 * i] - d[4 * i + 3];
+        t[4 * i] = a0 + a1; t[4 * i + 1] = 2 * a3 + a2; t[4 * i + 2] = a0 - a1; t[4 * i + 3] = a3 - 2 * a2;
+    }
+    for (int i = 0; i < 4; i++) {
+        int a0 = t[i] + t[12 + i], a1 = t[4 + i] + t[8 + i];
+        int a2 = t[4 + i] - t[8 + i], a3 = t[i] - t[12 + i];
+        w[i] = a0 + a1; w[4 + i] = 2 * a3 + a2; w[8 + i] = a0 - a1; w[12 + i] = a3 - 2 * a2;
+    }
+}
+/* inverse: input dequantised coefficients (raster), output residual (raster) */
+static void idct4(const int c[16], int r[16]) {
+    int t[16];
+    for (int i = 0; i < 4; i++) {
+        int e0 = c[4 * i] + c[4 * i + 2], e1 = c[4 * i] - c[4 * i + 2];
+        int e2 = (c[4 * i + 1] >> 1) - c[4 * i + 3], e3 = c[4 * i + 1] + (c[4 * i + 3] >> 1);
+        t[4 * i] = e0 + e3; t[4 * i + 1] = e1 + e2; t[4 * i + 2] = e1 - e2; t[4 * i + 3] = e0 - e3;
+    }
+    for (int i = 0; i < 4; i++) {
+        int e0 = t[i] + t[8 + i], e1 = t[i] - t[8 + i];
+        int e2 = (t[4 + i] >> 1) - t[12 + i], e3 = t[4 + i] + (t[12 + i] >> 1);
+        r[i] = (e0 + e3 + 32) >> 6; r[4 + i] = (e1 + e2 + 32) >> 6;
+        r[8 + i] = (e1 - e2 + 32) >> 6; r[12 + i] = (e0 - e3 + 32) >> 6;
+    }
+}
+static int quant1(int w, int mf, int f, int qbits) {
+    int a = w < 0 ? -w : w;
+    int l = (int)(((int64_t)a * mf + f) >> qbits);
+    if (l > 2047) l = 2047;
+    return w < 0 ? -l : l;
+}
+/* quantise 4x4 (raster w) into zig-zag levels; returns number of non-zeros among
+ * scan positions [first..15] */
+static int quant4x4(const int w[16], int qp, int intra, int first, int16_t lv[16]) {
+    int qbits = 15 + qp / 6, f = (1 << qbits) / (intra ? 3 : 6), nz = 0;
+    for (int k = first; k < 16; k++) {
+        int i = vcp_zigzag4x4[k];
+        int l = quant1(w[i], vcp_quant_mf[qp % 6][vcp_coef_class[i]], f, qbits);
+        lv[k] = (int16_t)l;
+        nz += l != 0;
+    }
+    return nz;
+}
+static void dequant4x4(const int16_t lv[16], int qp, int first, int c[16]) {
+    for (int k = first; k < 16; k++) {
+        int i = vcp_zigzag4x4[k];
+        c[i] = (lv[k] * vcp_dequant_v[qp % 6][vcp_coef_class[i]]) << (qp / 6);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* inter prediction                                                                       */
+static inline int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
+static inline int hb1(const uint8_t* r, int s, int x, int y) { /* horizontal half between x,x+1 */
+    const uint8_t* p = r + (size_t)y * s + x; (void)s;
+    return tap6(p[-2], p[-1], p[0], p[1], p[2], p[3]);
+}
+static inline int hv1(const uint8_t* r, int s, int x, int y) { /* vertical half between y,y+1 */
+    const uint8_t* p = r + (size_t)y * s + x;
+    return tap6(p[-2 * s], p[-s], p[0], p[s], p[2 * s], p[3 * s]);
+}
+static inline int hj1(const uint8_t* r, int s, int x, int y) {
+    return tap6(hb1(r, s, x, y - 2), hb1(r, s, x, y - 1), hb1(r, s, x, y), hb1(r, s, x, y + 1),
+                hb1(r, s, x, y + 2), hb1(r, s, x, y + 3));
+}
+#define C5(v) vcp_clip255(((v) + 16) >> 5)
+#define C10(v) vcp_clip255(((v) + 512) >> 10)
+/* luma sample at quarter-pel position (8.4.2.2.1) */
+static int luma_qpel(const uint8_t* r, int s, int ix, int iy, int fx, int fy) {
+    int G = r[(size_t)iy * s + ix];
+    switch (fy * 4 + fx) {
+    case 0: return G;
+    case 1: return (G + C5(hb1(r, s, ix, iy)) + 1) >> 1;
+    case 2: return C5(hb1(r, s, ix, iy));
+    case 3: return (r[(size_t)iy * s + ix + 1] + C5(hb1(r, s, ix, iy)) + 1) >> 1;
+    case 4: return (G + C5(hv1(r, s, ix, iy)) + 1) >> 1;
+    case 5: return (C5(hb1(r, s, ix, iy)) + C5(hv1(r, s, ix, iy)) + 1) >> 1;
+    case 6: return (C5(hb1(r, s, ix, iy)) + C10(hj1(r, s, ix, iy)) + 1) >> 1;
+    case 7: return (C5(hb1(r, s, ix, iy)) + C5(hv1(r, s, ix + 1, iy)) + 1) >> 1;
+    case 8: return C5(hv1(r, s, ix, iy));
+    case 9: return (C5(hv1(r, s, ix, iy)) + C10(hj1(r, s, ix, iy)) + 1) >> 1;
+    case 10: return C10(hj1(r, s, ix, iy));
+    case 11: return (C10(hj1(r, s, ix, iy)) + C5(hv1(r, s, ix + 1, iy)) + 1) >> 1;
+    case 12: return (r[(size_t)(iy + 1) * s + ix] + C5(hv1(r, s, ix, iy)) + 1) >> 1;
+    case 13: return (C5(hv1(r, s, ix, iy)) + C5(hb1(r, s, ix, iy + 1)) + 1) >> 1;
+    case 14: return (C10(hj1(r, s, ix, iy)) + C5(hb1(r, s, ix, iy + 1)) + 1) >> 1;
+    default: return (C5(hv1(r, s, ix + 1, iy)) + C5(hb1(r, s, ix, iy + 1)) + 1) >> 1;
+    }
+}
+static void mc_luma16(const Frame* ref, int px, int py, int mvx, int mvy, uint8_t dst[256]) {
+    int ix = px + (mvx >> 2), iy = py + (mvy >> 2), fx = mvx & 3, fy = mvy & 3;
+    for (int y = 0; y < 16; y++)
+        for (int x = 0; x < 16; x++)
+            dst[y * 16 + x] = (uint8_t)luma_qpel(ref->y, ref->ys, ix + x, iy + y, fx, fy);
+}
+static void mc_chroma8(const uint8_t* r, int s, int px, int py, int mvx, int mvy, uint8_t dst[64]) {
+    int ix = px + (mvx >> 3), iy = py + (mvy >> 3), dx = mvx & 7, dy = mvy & 7;
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++) {
+            const uint8_t* p = r + (size_t)(iy + y) * s + ix + x;
+            dst[y * 8 + x] = (uint8_t)(((8 - dx) * (8 - dy) * p[0] + dx * (8 - dy) * p[1] +
+                                        (8 - dx) * dy * p[s] + dx * dy * p[s + 1] + 32) >> 6);
+        }
+}
+static int sad16(const uint8_t* a, int as, const uint8_t* b, int bs) {
+    int s = 0;
+    for (int y = 0; y < 16; y++)
+        for (int x = 0; x < 16; x++) s += abs(a[y * as + x] - b[y * bs + x]);
+    return s;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* encoder context                                                                        */
+typedef struct {
+    vcpenc_params p;
+    int mbw, mbh, nmb;
+    int cw, ch; /* coded size */
+    Frame cur, prev_orig, recon[2];
+    Half hcur, hprev;
+    MB* mbs;
+    int16_t* mvfp; /* pre-pass full-pel mv per MB (x,y) */
+    uint8_t* rbsp; size_t rbsp_cap;
+} Enc;
+
+static int slice_first_row(const Enc* e, int s) { return (int)((int64_t)s * e->mbh / e->p.slices); }
+static int slice_of_row(const Enc* e, int row) {
+    int s = (int)(((int64_t)row * e->p.slices) / e->mbh);
+    while (s + 1 < e->p.slices && slice_first_row(e, s + 1) <= row) s++;
+    while (s > 0 && slice_first_row(e, s) > row) s--;
+    return s;
+}
+
+/* ---- K2a: motion search pre-pass on originals ---------------------------------------- */
+static void me_prepass(Enc* e) {
+    const Half *hc = &e->hcur, *hp = &e->hprev;
+    for (int my = 0; my < e->mbh; my++)
+        for (int mx = 0; mx < e->mbw; mx++) {
+            /* L1 */
+            uint32_t best = 0xffffffffu;
+            const uint8_t* c = hc->p + (size_t)(8 * my) * hc->s + 8 * mx;
+            int idx = 0;
+            for (int dy = -VCP_ME_R1; dy <= VCP_ME_R1; dy++)
+                for (int dx = -VCP_ME_R1; dx <= VCP_ME_R1; dx++, idx++) {
+                    const uint8_t* r = hp->p + (size_t)(8 * my + dy) * hp->s + 8 * mx + dx;
+                    int sad = 0;
+                    for (int y = 0; y < 8; y++)
+                        for (int x = 0; x < 8; x++) sad += abs(c[y * hc->s + x] - r[y * hp->s + x]);
+                    uint32_t key = ((uint32_t)(sad + VCP_ME_L1_PEN * (abs(dx) + abs(dy))) << 16) | (uint32_t)idx;
+                    if (key < best) best = key;
+                }
+            int bi = (int)(best & 0xffff), W = 2 * VCP_ME_R1 + 1;
+            int cx = 2 * (bi % W - VCP_ME_R1), cy = 2 * (bi / W - VCP_ME_R1);
+            /* L0 */
+            best = 0xffffffffu; idx = 0;
+            const uint8_t* c0 = e->cur.y + (size_t)(16 * my) * e->cur.ys + 16 * mx;
+            for (int dy = -2; dy <= 2; dy++)
+                for (int dx = -2; dx <= 2; dx++, idx++) {
+                    int mvx = cx + dx, mvy = cy + dy;
+                    const uint8_t* r = e->prev_orig.y + (size_t)(16 * my + mvy) * e->prev_orig.ys + 16 * mx + mvx;
+                    int sad = sad16(c0, e->cur.ys, r, e->prev_orig.ys);
+                    uint32_t key = ((uint32_t)(sad + VCP_ME_L0_PEN * (abs(mvx) + abs(mvy))) << 8) | (uint32_t)idx;
+                    if (key < best) best = key;
+                }
+            bi = (int)(best & 0xff);
+            e->mvfp[2 * (my * e->mbw + mx)] = (int16_t)(cx + bi % 5 - 2);
+            e->mvfp[2 * (my * e->mbw + mx) + 1] = (int16_t)(cy + bi / 5 - 2);
+        }
+}
+
+/* predictor estimate for the refine cost: median of the neighbours' PRE-PASS vectors */
+static void pmv_estimate(const Enc* e, int mx, int my, int* px, int* py) {
+    int row0 = slice_first_row(e, slice_of_row(e, my));
+    int aA = mx > 0, aB = my > row0, aC = aB && mx + 1 < e->mbw, aD = aB && mx > 0;
+    int ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
+    const int16_t* m = e->mvfp;
+    int i = my * e->mbw + mx;
+    if (aA) { ax = 4 * m[2 * (i - 1)]; ay = 4 * m[2 * (i - 1) + 1]; }
+    if (aB) { bx = 4 * m[2 * (i - e->mbw)]; by = 4 * m[2 * (i - e->mbw) + 1]; }
+    if (aC) { cx = 4 * m[2 * (i - e->mbw + 1)]; cy = 4 * m[2 * (i - e->mbw + 1) + 1]; }
+    else if (aD) { cx = 4 * m[2 * (i - e->mbw - 1)]; cy = 4 * m[2 * (i - e->mbw - 1) + 1]; }
+    if (!aB && aA) { *px = ax; *py = ay; return; }
+    *px = vcp_median3(ax, bx, cx); *py = vcp_median3(ay, by, cy);
+}
+
+/* ---- K2b: refine on the reconstructed reference ------------------------------------------ */
+static void me_refine_mb(Enc* e, const Frame* ref, int mx, int my, int qp, int16_t mv[2]) {
+    int lam = vcp_lambda(qp), pmx, pmy;
+    pmv_estimate(e, mx, my, &pmx, &pmy);
+    int i = my * e->mbw + mx, px = 16 * mx, py = 16 * my;
+    const uint8_t* c = e->cur.y + (size_t)py * e->cur.ys + px;
+    int fx = e->mvfp[2 * i], fy = e->mvfp[2 * i + 1];
+    /* full-pel candidates */
+    int cand[11][2], n = 0;
+    cand[n][0] = fx; cand[n][1] = fy; n++;
+    for (int dy = -1; dy <= 1; dy++)
+        for (int dx = -1; dx <= 1; dx++) {
+            if (!dx && !dy) continue;
+            cand[n][0] = fx + dx; cand[n][1] = fy + dy; n++;
+        }
+    cand[n][0] = 0; cand[n][1] = 0; n++;
+    cand[n][0] = vcp_clip3(-VCP_MV_FP_MAX, VCP_MV_FP_MAX, (pmx + 2) >> 2);
+    cand[n][1] = vcp_clip3(-VCP_MV_FP_MAX, VCP_MV_FP_MAX, (pmy + 2) >> 2); n++;
+    uint32_t best = 0xffffffffu;
+    for (int k = 0; k < n; k++) {
+        int vx = cand[k][0], vy = cand[k][1];
+        const uint8_t* r = ref->y + (size_t)(py + vy) * ref->ys + px + vx;
+        int cost = sad16(c, e->cur.ys, r, ref->ys) + lam * (vcp_se_len(4 * vx - pmx) + vcp_se_len(4 * vy - pmy));
+        uint32_t key = ((uint32_t)cost << 4) | (uint32_t)k;
+        if (key < best) best = key;
+    }
+    int bx = 4 * cand[best & 15][0], by = 4 * cand[best & 15][1];
+    uint32_t bcost = best >> 4;
+    /* half-pel then quarter-pel: 8 neighbours each, raster order, strict improvement */
+    for (int step = 2; step >= 1; step--) {
+        uint32_t sb = (bcost << 4) | 0; /* centre keeps priority (index 0) */
+        int k = 1, cx = bx, cy = by;
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                if (!dx && !dy) continue;
+                int vx = cx + dx * step, vy = cy + dy * step;
+                uint8_t pred[256];
+                mc_luma16(ref, px, py, vx, vy, pred);
+                int cost = sad16(c, e->cur.ys, pred, 16) + lam * (vcp_se_len(vx - pmx) + vcp_se_len(vy - pmy));
+                uint32_t key = ((uint32_t)cost << 4) | (uint32_t)k;
+                if (key < sb) { sb = key; bx = vx; by = vy; }
+                k++;
+            }
+        bcost = sb >> 4;
+    }
+    mv[0] = (int16_t)bx; mv[1] = (int16_t)by;
+}
+
+/* ---- K3 (inter): predict, transform, quantise, reconstruct ------------------------------- */
+static void chroma_dc_fwd_quant(int dc[4], int qpc, int intra, int16_t lv[4], int deq[4]) {
+    /* 2x2 Hadamard, quantise (8.5.11.2 inverse restated forward), dequantise */
+    int h[4] = {dc[0] + dc[1] + dc[2] + dc[3], dc[0] - dc[1] + dc[2] - dc[3],
+                dc[0] + dc[1] - dc[2] - dc[3], dc[0] - dc[1] - dc[2] + dc[3]};
+    int qbits = 15 + qpc / 6, f = (1 << qbits) / (intra ? 3 : 6);
+    int mf = vcp_quant_mf[qpc % 6][0];
+    for (int i = 0; i < 4; i++) lv[i] = (int16_t)quant1(h[i], mf, 2 * f, qbits + 1);
+    int c[4] = {lv[0], lv[1], lv[2], lv[3]};
+    int g[4] = {c[0] + c[1] + c[2] + c[3], c[0] - c[1] + c[2] - c[3],
+                c[0] + c[1] - c[2] - c[3], c[0] - c[1] - c[2] + c[3]};
+    int ls = 16 * vcp_dequant_v[qpc % 6][0];
+    for (int i = 0; i < 4; i++) deq[i] = ((g[i] * ls) << (qpc / 6)) >> 5;
+}
+
+/* chroma of one MB (both planes): residual from pred, levels out, recon in place */
+static void encode_chroma(Enc* e, MB* mb, Frame* rec, int mx, int my, int qp, int intra,
+                          const uint8_t predu[64], const uint8_t predv[64]) {
+    int qpc = vcp_chroma_qp[vcp_clip3(0, 51, qp)];
+    int any_ac = 0, any_dc = 0;
+    int coef[2][4][16];
+    for (int pl = 0; pl < 2; pl++) {
+        const uint8_t* src = (pl ? e->cur.v : e->cur.u) + (size_t)(8 * my) * e->cur.cs + 8 * mx;
+        const uint8_t* pred = pl ? predv : predu;
+        int dc[4];
+        for (int b = 0; b < 4; b++) {
+            int bx = (b & 1) * 4, by = (b >> 1) * 4, d[16], w[16];
+            for (int y = 0; y < 4; y++)
+                for (int x = 0; x < 4; x++)
+                    d[y * 4 + x] = src[(by + y) * e->cur.cs + bx + x] - pred[(by + y) * 8 + bx + x];
+            fdct4(d, w);
+            dc[b] = w[0];
+            int16_t* lv = mb->lv + VCP_LV_CHROMA_AC + (pl * 4 + b) * 16;
+            lv[0] = 0;
+            int nz = quant4x4(w, qpc, intra, 1, lv);
+            mb->nnz_c[pl][b] = (uint8_t)nz;
+            any_ac |= nz;
+            coef[pl][b][0] = 0;
+            dequant4x4(lv, qpc, 1, coef[pl][b]);
+        }
+        int deq[4];
+        int16_t* dl = mb->lv + VCP_LV_CHROMA_DC + pl * 4;
+        chroma_dc_fwd_quant(dc, qpc, intra, dl, deq);
+        for (int b = 0; b < 4; b++) { coef[pl][b][0] = deq[b]; any_dc |= dl[b] != 0; }
+    }
+    int cbpc = any_ac ? 2 : (any_dc ? 1 : 0);
+    mb->cbp = (uint8_t)((mb->cbp & 15) | (cbpc << 4));
+    if (!any_ac) memset(mb->nnz_c, 0, sizeof mb->nnz_c);
+    for (int pl = 0; pl < 2; pl++) {
+        uint8_t* dst = (pl ? rec->v : rec->u) + (size_t)(8 * my) * rec->cs + 8 * mx;
+        const uint8_t* pred = pl ? predv : predu;
+        for (int b = 0; b < 4; b++) {
+            int bx = (b & 1) * 4, by = (b >> 1) * 4, r[16];
+            idct4(coef[pl][b], r);
+            for (int y = 0; y < 4; y++)
+                for (int x = 0; x < 4; x++)
+                    dst[(by + y) * rec->cs + bx + x] = (uint8_t)vcp_clip255(pred[(by + y) * 8 + bx + x] + r[y * 4 + x]);
+        }
+    }
+}
+
+static void encode_p_mb(Enc* e, const Frame* ref, Frame* rec, int mx, int my, int qp) {
+    MB* mb = &e->mbs[my * e->mbw + mx];
+    memset(mb->lv, 0, sizeof mb->lv);
+    mb->type = VCP_MB_P16; mb->cbp = 0;
+    uint8_t pred[256], pu[64], pv[64];
+    mc_luma16(ref, 16 * mx, 16 * my, mb->mv[0], mb->mv[1], pred);
+    mc_chroma8(ref->u, ref->cs, 8 * mx, 8 * my, mb->mv[0], mb->mv[1], pu);
+    mc_chroma8(ref->v, ref->cs, 8 * mx, 8 * my, mb->mv[0], mb->mv[1], pv);
+    const uint8_t* src = e->cur.y + (size_t)(16 * my) * e->cur.ys + 16 * mx;
+    uint8_t* dst = rec->y + (size_t)(16 * my) * rec->ys + 16 * mx;
+    for (int b = 0; b < 16; b++) {
+        int bx = vcp_blk_x[b] * 4, by = vcp_blk_y[b] * 4, d[16], w[16], c[16], r[16];
+        for (int y = 0; y < 4; y++)
+            for (int x = 0; x < 4; x++)
+                d[y * 4 + x] = src[(by + y) * e->cur.ys + bx + x] - pred[(by + y) * 16 + bx + x];
+        fdct4(d, w);
+        int16_t* lv = mb->lv + VCP_LV_LUMA + b * 16;
+        int nz = quant4x4(w, qp, 0, 0, lv);
+        mb->nnz_y[vcp_blk_y[b] * 4 + vcp_blk_x[b]] = (uint8_t)nz;
+        if (nz) mb->cbp |= (uint8_t)(1 << (b >> 2));
+        dequant4x4(lv, qp, 0, c);
+        idct4(c, r);
+        for (int y = 0; y < 4; y++)
+            for (int x = 0; x < 4; x++)
+                dst[(by + y) * rec->ys + bx + x] = (uint8_t)vcp_clip255(pred[(by + y) * 16 + bx + x] + r[y * 4 + x]);
+    }
+    encode_chroma(e, mb, rec, mx, my, qp, 0, pu, pv);
+}
+
+/* ---- motion vector prediction (8.4.1.3) and P_Skip (8.4.1.1) ------------------------------- */
+static void mv_neighbours(const Enc* e, int mx, int my, int avail[4], int mv[4][2], int ref[4]) {
+    /* 0:A left 1:B top 2:C top-right 3:D top-left; ref = 0 inter, -1 intra/unavailable */
+    int row0 = slice_first_row(e, slice_of_row(e, my));
+    int pos[4][2] = {{mx - 1, my}, {mx, my - 1}, {mx + 1, my - 1}, {mx - 1, my - 1}};
+    for (int k = 0; k < 4; k++) {
+        int x = pos[k][0], y = pos[k][1];
+        avail[k] = x >= 0 && x < e->mbw && y >= row0 && y <= my;
+        mv[k][0] = mv[k][1] = 0; ref[k] = -1;
+        if (avail[k]) {
+            const MB* n = &e->mbs[y * e->mbw + x];
+            if (n->type != VCP_MB_I16) { ref[k] = 0; mv[k][0] = n->mv[0]; mv[k][1] = n->mv[1]; }
+        }
+    }
+}
+static void mvp16(const Enc* e, int mx, int my, int* px, int* py) {
+    int av[4], mv[4][2], rf[4];
+    mv_neighbours(e, mx, my, av, mv, rf);
+    int c = av[2] ? 2 : 3;
+    if (!av[1] && !av[c] && av[0]) { *px = mv[0][0]; *py = mv[0][1]; return; }
+    int cnt = (rf[0] == 0) + (rf[1] == 0) + (rf[c] == 0);
+    if (cnt == 1) {
+        int k = rf[0] == 0 ? 0 : (rf[1] == 0 ? 1 : c);
+        *px = mv[k][0]; *py = mv[k][1]; return;
+    }
+    *px = vcp_median3(mv[0][0], mv[1][0], mv[c][0]);
+    *py = vcp_median3(mv[0][1], mv[1][1], mv[c][1]);
+}
+static void mv_pskip(const Enc* e, int mx, int my, int* px, int* py) {
+    int av[4], mv[4][2], rf[4];
+    mv_neighbours(e, mx, my, av, mv, rf);
+    if (!av[0] || !av[1] || (rf[0] == 0 && !mv[0][0] && !mv[0][1]) || (rf[1] == 0 && !mv[1][0] && !mv[1][1])) {
+        *px = *py = 0; return;
+    }
+    mvp16(e, mx, my, px, py);
+}
+
+/* ---- K3 (intra 16x16) -------------------------------------------------------------------- */
+static void pred_i16(const Frame* rec, int mx, int my, int mode, int aL, int aT, uint8_t p[256]) {
+    const uint8_t* o = rec->y + (size_t)(16 * my) * rec->ys + 16 * mx;
+    int s = rec->ys;
+    if (mode == 0) { for (int y = 0; y < 16; y++) memcpy(p + 16 * y, o - s, 16); }
+    else if (mode == 1) { for (int y = 0; y < 16; y++) memset(p + 16 * y, o[y * s - 1], 16); }
+    else if (mode == 2) {
+        int sum = 0, dc;
+        if (aT) for (int x = 0; x < 16; x++) sum += o[x - s];
+        if (aL) for (int y = 0; y < 16; y++) sum += o[y * s - 1];
+        dc = (aT && aL) ? (sum + 16) >> 5 : (aT || aL) ? (sum + 8) >> 4 : 128;
+        memset(p, dc, 256);
+    } else {
+        int H = 0, V = 0;
+        for (int i = 0; i < 8; i++) {
+            H += (i + 1) * (o[8 + i - s] - o[6 - i - s]);
+            V += (i + 1) * (o[(8 + i) * s - 1] - o[(6 - i) * s - 1]);
+        }
+        int a = 16 * (o[15 * s - 1] + o[15 - s]), b = (5 * H + 32) >> 6, c = (5 * V + 32) >> 6;
+        for (int y = 0; y < 16; y++)
+            for (int x = 0; x < 16; x++) p[y * 16 + x] = (uint8_t)vcp_clip255((a + b * (x - 7) + c * (y - 7) + 16) >> 5);
+    }
+}
+static void pred_c8(const uint8_t* plane, int s, int mx, int my, int mode, int aL, int aT, uint8_t p[64]) {
+    const uint8_t* o = plane + (size_t)(8 * my) * s + 8 * mx;
+    if (mode == 0) { /* DC, per 4x4 */
+        for (int b = 0; b < 4; b++) {
+            int bx = (b & 1) * 4, by = (b >> 1) * 4, st = 0, sl = 0, dc;
+            for (int i = 0; i < 4; i++) { if (aT) st += o[bx + i - s]; if (aL) sl += o[(by + i) * s - 1]; }
+            if (b == 0 || b == 3) dc = (aT && aL) ? (st + sl + 4) >> 3 : aT ? (st + 2) >> 2 : aL ? (sl + 2) >> 2 : 128;
+            else if (b == 1) dc = aT ? (st + 2) >> 2 : aL ? (sl + 2) >> 2 : 128;
+            else dc = aL ? (sl + 2) >> 2 : aT ? (st + 2) >> 2 : 128;
+            for (int y = 0; y < 4; y++) memset(p + (by + y) * 8 + bx, dc, 4);
+        }
+    } else if (mode == 1) { for (int y = 0; y < 8; y++) memset(p + 8 * y, o[y * s - 1], 8); }
+    else if (mode == 2) { for (int y = 0; y < 8; y++) memcpy(p + 8 * y, o - s, 8); }
+    else {
+        int H = 0, V = 0;
+        for (int i = 0; i < 4; i++) {
+            H += (i + 1) * (o[4 + i - s] - o[2 - i - s]);
+            V += (i + 1) * (o[(4 + i) * s - 1] - o[(2 - i) * s - 1]);
+        }
+        int a = 16 * (o[7 * s - 1] + o[7 - s]), b = (34 * H + 32) >> 6, c = (34 * V + 32) >> 6;
+        for (int y = 0; y < 8; y++)
+            for (int x = 0; x < 8; x++) p[y * 8 + x] = (uint8_t)vcp_clip255((a + b * (x - 3) + c * (y - 3) + 16) >> 5);
+    }
+}
+
+static void encode_i_mb(Enc* e, Frame* rec, int mx, int my, int qp) {
+    MB* mb = &e->mbs[my * e->mbw + mx];
+    memset(mb->lv, 0, sizeof mb->lv);
+    mb->type = VCP_MB_I16; mb->cbp = 0; mb->mv[0] = mb->mv[1] = 0; mb->mvd[0] = mb->mvd[1] = 0;
+    int row0 = slice_first_row(e, slice_of_row(e, my));
+    int aL = mx > 0, aT = my > row0;
+    const uint8_t* src = e->cur.y + (size_t)(16 * my) * e->cur.ys + 16 * mx;
+    /* luma mode: min SAD, ties to the lowest mode number */
+    uint8_t pred[256], best_pred[256];
+    uint32_t best = 0xffffffffu;
+    for (int mode = 0; mode < 4; mode++) {
+        if ((mode == 0 && !aT) || (mode == 1 && !aL) || (mode == 3 && !(aT && aL))) continue;
+        pred_i16(rec, mx, my, mode, aL, aT, pred);
+        uint32_t key = ((uint32_t)sad16(src, e->cur.ys, pred, 16) << 2) | (uint32_t)mode;
+        if (key < best) { best = key; memcpy(best_pred, pred, 256); }
+    }
+    mb->i16_mode = (uint8_t)(best & 3);
+    /* chroma mode: min SAD over both planes */
+    uint8_t pu[64], pv[64], bpu[64], bpv[64];
+    best = 0xffffffffu;
+    for (int mode = 0; mode < 4; mode++) {
+        if ((mode == 1 && !aL) || (mode == 2 && !aT) || (mode == 3 && !(aT && aL))) continue;
+        pred_c8(rec->u, rec->cs, mx, my, mode, aL, aT, pu);
+        pred_c8(rec->v, rec->cs, mx, my, mode, aL, aT, pv);
+        int sad = 0;
+        for (int y = 0; y < 8; y++)
+            for (int x = 0; x < 8; x++) {
+                sad += abs(e->cur.u[(size_t)(8 * my + y) * e->cur.cs + 8 * mx + x] - pu[y * 8 + x]);
+                sad += abs(e->cur.v[(size_t)(8 * my + y) * e->cur.cs + 8 * mx + x] - pv[y * 8 + x]);
+            }
+        uint32_t key = ((uint32_t)sad << 2) | (uint32_t)mode;
+        if (key < best) { best = key; memcpy(bpu, pu, 64); memcpy(bpv, pv, 64); }
+    }
+    mb->chroma_mode = (uint8_t)(best & 3);
+    /* luma residual: 16 4x4 core transforms, DCs through a 4x4 Hadamard */
+    int w[16][16], dcm[16]; /* dcm raster over 4x4 block grid */
+    int any_ac = 0;
+    for (int b = 0; b < 16; b++) {
+        int bx = vcp_blk_x[b] * 4, by = vcp_blk_y[b] * 4, d[16];
+        for (int y = 0; y < 4; y++)
+            for (int x = 0; x < 4; x++)
+                d[y * 4 + x] = src[(by + y) * e->cur.ys + bx + x] - best_pred[(by + y) * 16 + bx + x];
+        fdct4(d, w[b]);
+        dcm[vcp_blk_y[b] * 4 + vcp_blk_x[b]] = w[b][0];
+        int16_t* lv = mb->lv + VCP_LV_LUMA + b * 16;
+        lv[0] = 0;
+        int nz = quant4x4(w[b], qp, 1, 1, lv);
+        mb->nnz_y[vcp_blk_y[b] * 4 + vcp_blk_x[b]] = (uint8_t)nz;
+        any_ac |= nz;
+    }
+    if (any_ac) mb->cbp = 15; else memset(mb->nnz_y, 0, 16);
+    /* forward Hadamard of DCs (with /2), quantise */
+    int t[16], hd[16];
+    for (int i = 0; i < 4; i++) {
+        int a0 = dcm[4 * i] + dcm[4 * i + 3], a1 = dcm[4 * i + 1] + dcm[4 * i + 2];
+        int a2 = dcm[4 * i + 1] - dcm[4 * i + 2], a3 = dcm[4 * i] - dcm[4 * i + 3];
+        t[4 * i] = a0 + a1; t[4 * i + 1] = a3 + a2; t[4 * i + 2] = a0 - a1; t[4 * i + 3] = a3 - a2;
+    }
+    for (int i = 0; i < 4; i++) {
+        int a0 = t[i] + t[12 + i], a1 = t[4 + i] + t[8 + i];
+        int a2 = t[4 + i] - t[8 + i], a3 = t[i] - t[12 + i];
+        hd[i] = (a0 + a1) >> 1; hd[4 + i] = (a3 + a2) >> 1; hd[8 + i] = (a0 - a1) >> 1; hd[12 + i] = (a3 - a2) >> 1;
+    }
+    {
+        int qbits = 15 + qp / 6, f = (1 << qbits) / 3, mf = vcp_quant_mf[qp % 6][0];
+        int16_t* dl = mb->lv + VCP_LV_LUMA_DC;
+        int c[16], g[16];
+        for (int k = 0; k < 16; k++) {
+            dl[k] = (int16_t)quant1(hd[vcp_zigzag4x4[k]], mf, 2 * f, qbits + 1);
+            c[vcp_zigzag4x4[k]] = dl[k];
+        }
+        /* decoder side: inverse Hadamard then scale (8.5.10) */
+        for (int i = 0; i < 4; i++) {
+            int a0 = c[4 * i] + c[4 * i + 3], a1 = c[4 * i + 1] + c[4 * i + 2];
+            int a2 = c[4 * i + 1] - c[4 * i + 2], a3 = c[4 * i] - c[4 * i + 3];
+            t[4 * i] = a0 + a1; t[4 * i + 1] = a3 + a2; t[4 * i + 2] = a0 - a1; t[4 * i + 3] = a3 - a2;
+        }
+        for (int i = 0; i < 4; i++) {
+            int a0 = t[i] + t[12 + i], a1 = t[4 + i] + t[8 + i];
+            int a2 = t[4 + i] - t[8 + i], a3 = t[i] - t[12 + i];
+            g[i] = a0 + a1; g[4 + i] = a3 + a2; g[8 + i] = a0 - a1; g[12 + i] = a3 - a2;
+        }
+        int ls = 16 * vcp_dequant_v[qp % 6][0];
+        for (int i = 0; i < 16; i++)
+            dcm[i] = qp >= 36 ? (g[i] * ls) << (qp / 6 - 6)
+                              : (g[i] * ls + (1 << (5 - qp / 6))) >> (6 - qp / 6);
+    }
+    uint8_t* dst = rec->y + (size_t)(16 * my) * rec->ys + 16 * mx;
+    for (int b = 0; b < 16; b++) {
+        int bx = vcp_blk_x[b] * 4, by = vcp_blk_y[b] * 4, c[16], r[16];
+        int16_t* lv = mb->lv + VCP_LV_LUMA + b * 16;
+        if (!any_ac) memset(lv, 0, 32);
+        dequant4x4(lv, qp, 1, c);
+        c[0] = dcm[vcp_blk_y[b] * 4 + vcp_blk_x[b]];
+        idct4(c, r);
+        for (int y = 0; y < 4; y++)
+            for (int x = 0; x < 4; x++)
+                dst[(by + y) * rec->ys + bx + x] = (uint8_t)vcp_clip255(best_pred[(by + y) * 16 + bx + x] + r[y * 4 + x]);
+    }
+    encode_chroma(e, mb, rec, mx, my, qp, 1, bpu, bpv);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* K4: deblocking (8.7), macroblock raster order                                           */
+static int bs_of(const MB* p, const MB* q, int pblk, int qblk, int mbedge) {
+    if (p->type == VCP_MB_I16 || q->type == VCP_MB_I16) return mbedge ? 4 : 3;
+    if (p->nnz_y[pblk] || q->nnz_y[qblk]) return 2;
+    if (abs(p->mv[0] - q->mv[0]) >= 4 || abs(p->mv[1] - q->mv[1]) >= 4) return 1;
+    return 0;
+}
+static void filter_luma_line(uint8_t* pix, int xs, int bS, int alpha, int beta, int tc0) {
+    int p0 = pix[-xs], p1 = pix[-2 * xs], p2 = pix[-3 * xs], q0 = pix[0], q1 = pix[xs], q2 = pix[2 * xs];
+    if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
+    int ap = abs(p2 - p0), aq = abs(q2 - q0);
+    if (bS < 4) {
+        int tc = tc0 + (ap < beta) + (aq < beta);
+        int d = vcp_clip3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
+        pix[-xs] = (uint8_t)vcp_clip255(p0 + d);
+        pix[0] = (uint8_t)vcp_clip255(q0 - d);
+        if (ap < beta) pix[-2 * xs] = (uint8_t)(p1 + vcp_clip3(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - 2 * p1) >> 1));
+        if (aq < beta) pix[xs] = (uint8_t)(q1 + vcp_clip3(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - 2 * q1) >> 1));
+    } else {
+        int p3 = pix[-4 * xs], q3 = pix[3 * xs];
+        int small = abs(p0 - q0) < ((alpha >> 2) + 2);
+        if (ap < beta && small) {
+            pix[-xs] = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+            pix[-2 * xs] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
+            pix[-3 * xs] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+        } else pix[-xs] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+        if (aq < beta && small) {
+            pix[0] = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+            pix[xs] = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
+            pix[2 * xs] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
+        } else pix[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+    }
+}
+static void filter_chroma_line(uint8_t* pix, int xs, int bS, int alpha, int beta, int tc0) {
+    int p0 = pix[-xs], p1 = pix[-2 * xs], q0 = pix[0], q1 = pix[xs];
+    if (abs(p0 - q0) >= alpha || abs(p1 - p0) >= beta || abs(q1 - q0) >= beta) return;
+    if (bS < 4) {
+        int tc = tc0 + 1;
+        int d = vcp_clip3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
+        pix[-xs] = (uint8_t)vcp_clip255(p0 + d);
+        pix[0] = (uint8_t)vcp_clip255(q0 - d);
+    } else {
+        pix[-xs] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+        pix[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+    }
+}
+static void deblock_frame(Enc* e, Frame* f, int qp) {
+    if (e->p.deblock_idc == 1) return;
+    int qpc = vcp_chroma_qp[vcp_clip3(0, 51, qp)];
+    int aY = vcp_alpha_tab[qp], bY = vcp_beta_tab[qp], aC = vcp_alpha_tab[qpc], bC = vcp_beta_tab[qpc];
+    for (int my = 0; my < e->mbh; my++)
+        for (int mx = 0; mx < e->mbw; mx++) {
+            const MB* q = &e->mbs[my * e->mbw + mx];
+            int row0 = slice_first_row(e, slice_of_row(e, my));
+            int left_ok = mx > 0, top_ok = my > 0 && (e->p.deblock_idc != 2 || my > row0);
+            uint8_t* Y = f->y + (size_t)(16 * my) * f->ys + 16 * mx;
+            uint8_t* U = f->u + (size_t)(8 * my) * f->cs + 8 * mx;
+            uint8_t* V = f->v + (size_t)(8 * my) * f->cs + 8 * mx;
+            /* vertical edges */
+            for (int ed = 0; ed < 4; ed++) {
+                if (ed == 0 && !left_ok) continue;
+                const MB* p = ed == 0 ? q - 1 : q;
+                int bS[4];
+                for (int k = 0; k < 4; k++) bS[k] = bs_of(p, q, k * 4 + (ed == 0 ? 3 : ed - 1), k * 4 + ed, ed == 0);
+                for (int y = 0; y < 16; y++) {
+                    int b = bS[y >> 2];
+                    if (b) filter_luma_line(Y + (size_t)y * f->ys + 4 * ed, 1, b, aY, bY, b < 4 ? vcp_tc0_tab[qp][b - 1] : 0);
+                }
+                if (!(ed & 1)) for (int y = 0; y < 8; y++) {
+                    int b = bS[y >> 1];
+                    if (!b) continue;
+                    int t = b < 4 ? vcp_tc0_tab[qpc][b - 1] : 0;
+                    filter_chroma_line(U + (size_t)y * f->cs + 2 * ed, 1, b, aC, bC, t);
+                    filter_chroma_line(V + (size_t)y * f->cs + 2 * ed, 1, b, aC, bC, t);
+                }
+            }
+            /* horizontal edges */
+            for (int ed = 0; ed < 4; ed++) {
+                if (ed == 0 && !top_ok) continue;
+                const MB* p = ed == 0 ? q - e->mbw : q;
+                int bS[4];
+                for (int k = 0; k < 4; k++) bS[k] = bs_of(p, q, (ed == 0 ? 12 : 4 * (ed - 1)) + k, 4 * ed + k, ed == 0);
+                for (int x = 0; x < 16; x++) {
+                    int b = bS[x >> 2];
+                    if (b) filter_luma_line(Y + (size_t)(4 * ed) * f->ys + x, f->ys, b, aY, bY, b < 4 ? vcp_tc0_tab[qp][b - 1] : 0);
+                }
+                if (!(ed & 1)) for (int x = 0; x < 8; x++) {
+                    int b = bS[x >> 1];
+                    if (!b) continue;
+                    int t = b < 4 ? vcp_tc0_tab[qpc][b - 1] : 0;
+                    filter_chroma_line(U + (size_t)(2 * ed) * f->cs + x, f->cs, b, aC, bC, t);
+                    filter_chroma_line(V + (size_t)(2 * ed) * f->cs + x, f->cs, b, aC, bC, t);
+                }
+            }
+        }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* K5: CAVLC                                                                               */
+/* residual_block_cavlc (7.3.5.3.2 / 9.2) for coefficients c[0..n-1] in scan order */
+static int cavlc_block(BW* b, const int16_t* c, int n, int nC) {
+    int total = 0, t1 = 0, last = -1;
+    int lev[16], run[16];
+    /* gather non-zero coefficients from the high-frequency end */
+    int zeros = 0, total_zeros = 0;
+    for (int i = n - 1; i >= 0; i--) {
+        if (c[i]) {
+            if (total) run[total - 1] = zeros;
+            lev[total++] = c[i];
+            zeros = 0;
+            if (last < 0) last = i;
+        } else if (total) zeros++;
+    }
+    if (total) { run[total - 1] = zeros; total_zeros = last + 1 - total; }
+    for (int i = 0; i < total && i < 3; i++) { if (lev[i] == 1 || lev[i] == -1) t1++; else break; }
+    /* coeff_token */
+    if (nC == -1) bw_put(b, vcp_chroma_dc_coeff_token_len[4 * total + t1], vcp_chroma_dc_coeff_token_bits[4 * total + t1]);
+    else {
+        int tab = nC < 2 ? 0 : nC < 4 ? 1 : nC < 8 ? 2 : 3;
+        bw_put(b, vcp_coeff_token_len[tab][4 * total + t1], vcp_coeff_token_bits[tab][4 * total + t1]);
+    }
+    if (!total) return 0;
+    for (int i = 0; i < t1; i++) bw_put(b, 1, lev[i] < 0);
+    int suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
+    for (int i = t1; i < total; i++) {
+        int l = lev[i], code = l > 0 ? 2 * l - 2 : -2 * l - 1;
+        if (i == t1 && t1 < 3) code -= 2;
+        if (suffix_len == 0) {
+            if (code < 14) bw_put(b, code + 1, 1);
+            else if (code < 30) { bw_put(b, 15, 1); bw_put(b, 4, code - 14); }
+            else { bw_put(b, 16, 1); bw_put(b, 12, code - 30); }
+        } else {
+            int pre = code >> suffix_len;
+            if (pre < 15) { bw_put(b, pre + 1, 1); bw_put(b, suffix_len, code & ((1 << suffix_len) - 1)); }
+            else { bw_put(b, 16, 1); bw_put(b, 12, code - (15 << suffix_len)); }
+        }
+        if (suffix_len == 0) suffix_len = 1;
+        if (abs(l) > (3 << (suffix_len - 1)) && suffix_len < 6) suffix_len++;
+    }
+    if (total < n) {
+        if (n == 4) bw_put(b, vcp_chroma_dc_total_zeros_len[total - 1][total_zeros], vcp_chroma_dc_total_zeros_bits[total - 1][total_zeros]);
+        else bw_put(b, vcp_total_zeros_len[total - 1][total_zeros], vcp_total_zeros_bits[total - 1][total_zeros]);
+    }
+    int left = total_zeros;
+    for (int i = 0; i < total - 1 && left > 0; i++) {
+        int zl = left > 7 ? 7 : left;
+        bw_put(b, vcp_run_len[zl - 1][run[i]], vcp_run_bits[zl - 1][run[i]]);
+        left -= run[i];
+    }
+    return total;
+}
+
+/* nC for luma block at raster (bx,by) of MB (mx,my) */
+static int nnz_ctx(const Enc* e, int mx, int my, int bx, int by, int plane /*0 Y,1 Cb,2 Cr*/) {
+    int row0 = slice_first_row(e, slice_of_row(e, my));
+    int dim = plane ? 2 : 4;
+    int nA = -1, nB = -1;
+    const MB* m = &e->mbs[my * e->mbw + mx];
+    if (bx > 0) nA = plane ? m->nnz_c[plane - 1][by * 2 + bx - 1] : m->nnz_y[by * 4 + bx - 1];
+    else if (mx > 0) { const MB* l = m - 1; nA = plane ? l->nnz_c[plane - 1][by * 2 + 1] : l->nnz_y[by * 4 + 3]; }
+    if (by > 0) nB = plane ? m->nnz_c[plane - 1][(by - 1) * 2 + bx] : m->nnz_y[(by - 1) * 4 + bx];
+    else if (my > row0) { const MB* t = m - e->mbw; nB = plane ? t->nnz_c[plane - 1][(dim - 1) * 2 + bx] : t->nnz_y[12 + bx]; }
+    if (nA >= 0 && nB >= 0) return (nA + nB + 1) >> 1;
+    return nA >= 0 ? nA : nB >= 0 ? nB : 0;
+}
+
+static void cavlc_residual(BW* b, const Enc* e, const MB* mb, int mx, int my) {
+    if (mb->type == VCP_MB_I16) cavlc_block(b, mb->lv + VCP_LV_LUMA_DC, 16, nnz_ctx(e, mx, my, 0, 0, 0));
+    for (int blk = 0; blk < 16; blk++) {
+        if (!(mb->cbp & (1 << (blk >> 2)))) continue;
+        int nC = nnz_ctx(e, mx, my, vcp_blk_x[blk], vcp_blk_y[blk], 0);
+        const int16_t* lv = mb->lv + VCP_LV_LUMA + blk * 16;
+        if (mb->type == VCP_MB_I16) cavlc_block(b, lv + 1, 15, nC); else cavlc_block(b, lv, 16, nC);
+    }
+    int cc = mb->cbp >> 4;
+    if (cc) for (int pl = 0; pl < 2; pl++) cavlc_block(b, mb->lv + VCP_LV_CHROMA_DC + pl * 4, 4, -1);
+    if (cc & 2) for (int pl = 0; pl < 2; pl++)
+        for (int blk = 0; blk < 4; blk++)
+            cavlc_block(b, mb->lv + VCP_LV_CHROMA_AC + (pl * 4 + blk) * 16 + 1, 15, nnz_ctx(e, mx, my, blk & 1, blk >> 1, pl + 1));
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* headers                                                                                */
+static int level_idc_for(int mbw, int mbh, int fps_num, int fps_den) {
+    /* Table A-1: MaxMBPS, MaxFS */
+    static const struct { int idc; long mbps; long fs; } L[] = {
+        {10, 1485, 99}, {11, 3000, 396}, {12, 6000, 396}, {13, 11880, 396}, {20, 11880, 396},
+        {21, 19800, 792}, {22, 20250, 1620}, {30, 40500, 1620}, {31, 108000, 3600},
+        {32, 216000, 5120}, {40, 245760, 8192}, {42, 522240, 8704}, {50, 589824, 22080},
+        {51, 983040, 36864}, {52, 2073600, 36864}};
+    long fs = (long)mbw * mbh;
+    long mbps = (long)((double)fs * fps_num / (fps_den > 0 ? fps_den : 1) + 0.5);
+    for (unsigned i = 0; i < sizeof L / sizeof L[0]; i++)
+        if (fs <= L[i].fs && mbps <= L[i].mbps) return L[i].idc;
+    return 52;
+}
+static size_t write_sps(const Enc* e, uint8_t* out, size_t cap) {
+    uint8_t tmp[128]; BW b; bw_init(&b, tmp, sizeof tmp);
+    const vcpenc_params* p = &e->p;
+    bw_put(&b, 8, 66);              /* profile_idc: Baseline */
+    bw_put(&b, 8, 0xC0);            /* constraint_set0,1 (constrained baseline) */
+    bw_put(&b, 8, level_idc_for(e->mbw, e->mbh, p->fps_num, p->fps_den));
+    bw_ue(&b, 0);                   /* sps id */
+    bw_ue(&b, 4);                   /* log2_max_frame_num_minus4 -> 8 bits */
+    bw_ue(&b, 2);                   /* pic_order_cnt_type 2: output order == decode order */
+    bw_ue(&b, 1);                   /* max_num_ref_frames */
+    bw_put(&b, 1, 0);               /* gaps_in_frame_num_value_allowed */
+    bw_ue(&b, e->mbw - 1);
+    bw_ue(&b, e->mbh - 1);
+    bw_put(&b, 1, 1);               /* frame_mbs_only */
+    bw_put(&b, 1, 1);               /* direct_8x8_inference */
+    int cr = e->cw - p->width, cb = e->ch - p->height;
+    if (cr || cb) { bw_put(&b, 1, 1); bw_ue(&b, 0); bw_ue(&b, cr / 2); bw_ue(&b, 0); bw_ue(&b, cb / 2); }
+    else bw_put(&b, 1, 0);
+    bw_put(&b, 1, 1);               /* vui_parameters_present */
+    bw_put(&b, 1, 0);               /* aspect_ratio_info_present */
+    bw_put(&b, 1, 0);               /* overscan_info_present */
+    bw_put(&b, 1, 0);               /* video_signal_type_present */
+    bw_put(&b, 1, 0);               /* chroma_loc_info_present */
+    bw_put(&b, 1, 1);               /* timing_info_present */
+    bw_put32(&b, (uint32_t)p->fps_den);
+    bw_put32(&b, (uint32_t)p->fps_num * 2);
+    bw_put(&b, 1, 1);               /* fixed_frame_rate */
+    bw_put(&b, 1, 0);               /* nal_hrd */
+    bw_put(&b, 1, 0);               /* vcl_hrd */
+    bw_put(&b, 1, 0);               /* pic_struct_present */
+    bw_put(&b, 1, 1);               /* bitstream_restriction */
+    bw_put(&b, 1, 1);               /* motion_vectors_over_pic_boundaries */
+    bw_ue(&b, 0);                   /* max_bytes_per_pic_denom */
+    bw_ue(&b, 0);                   /* max_bits_per_mb_denom */
+    bw_ue(&b, 9);                   /* log2_max_mv_length_horizontal */
+    bw_ue(&b, 9);                   /* log2_max_mv_length_vertical */
+    bw_ue(&b, 0);                   /* max_num_reorder_frames */
+    bw_ue(&b, 1);                   /* max_dec_frame_buffering */
+    bw_trailing(&b);
+    return nal_write(out, cap, 3, 7, tmp, b.pos);
+}
+static size_t write_pps(const Enc* e, uint8_t* out, size_t cap) {
+    uint8_t tmp[64]; BW b; bw_init(&b, tmp, sizeof tmp);
+    bw_ue(&b, 0); bw_ue(&b, 0);
+    bw_put(&b, 1, 0);               /* entropy_coding_mode: CAVLC */
+    bw_put(&b, 1, 0);               /* bottom_field_pic_order_in_frame_present */
+    bw_ue(&b, 0);                   /* num_slice_groups_minus1 */
+    bw_ue(&b, 0); bw_ue(&b, 0);     /* num_ref_idx_l0/l1_default_active_minus1 */
+    bw_put(&b, 1, 0);               /* weighted_pred */
+    bw_put(&b, 2, 0);               /* weighted_bipred_idc */
+    bw_se(&b, 0);                   /* pic_init_qp_minus26 */
+    bw_se(&b, 0);                   /* pic_init_qs_minus26 */
+    bw_se(&b, 0);                   /* chroma_qp_index_offset */
+    bw_put(&b, 1, 1);               /* deblocking_filter_control_present */
+    bw_put(&b, 1, 0);               /* constrained_intra_pred */
+    bw_put(&b, 1, 0);               /* redundant_pic_cnt_present */
+    bw_trailing(&b);
+    (void)e;
+    return nal_write(out, cap, 3, 8, tmp, b.pos);
+}
+static void write_slice_header(const Enc* e, BW* b, int first_mb, int idr, int frame_num, int idr_id, int qp) {
+    bw_ue(b, (unsigned)first_mb);
+    bw_ue(b, idr ? 7 : 5);          /* slice_type: all slices of the picture are I / P */
+    bw_ue(b, 0);                    /* pps id */
+    bw_put(b, 8, (uint32_t)(frame_num & 255));
+    if (idr) bw_ue(b, (unsigned)idr_id);
+    if (!idr) {
+        bw_put(b, 1, 0);            /* num_ref_idx_active_override */
+        bw_put(b, 1, 0);            /* ref_pic_list_modification_flag_l0 */
+    }
+    if (idr) { bw_put(b, 1, 0); bw_put(b, 1, 0); } /* no_output_of_prior_pics, long_term_reference */
+    else bw_put(b, 1, 0);           /* adaptive_ref_pic_marking_mode */
+    bw_se(b, qp - 26);              /* slice_qp_delta */
+    bw_ue(b, (unsigned)e->p.deblock_idc);
+    if (e->p.deblock_idc != 1) { bw_se(b, 0); bw_se(b, 0); }
+}
+
+/* slice data for MB rows [r0,r1) */
+static void write_slice_data(Enc* e, BW* b, int r0, int r1, int idr) {
+    int skip_run = 0;
+    for (int my = r0; my < r1; my++)
+        for (int mx = 0; mx < e->mbw; mx++) {
+            const MB* mb = &e->mbs[my * e->mbw + mx];
+            if (!idr) {
+                if (mb->type == VCP_MB_PSKIP) { skip_run++; continue; }
+                bw_ue(b, (unsigned)skip_run); skip_run = 0;
+            }
+            if (mb->type == VCP_MB_I16) {
+                int t = 1 + mb->i16_mode + 4 * (mb->cbp >> 4) + ((mb->cbp & 15) ? 12 : 0);
+                bw_ue(b, (unsigned)(idr ? t : t + 5));
+                bw_ue(b, mb->chroma_mode);
+                bw_se(b, 0); /* mb_qp_delta */
+            } else {
+                bw_ue(b, 0); /* P_L0_16x16 */
+                bw_se(b, mb->mvd[0]); bw_se(b, mb->mvd[1]);
+                bw_ue(b, vcp_cbp_to_golomb_inter[mb->cbp]);
+                if (mb->cbp) bw_se(b, 0);
+            }
+            cavlc_residual(b, e, mb, mx, my);
+        }
+    if (skip_run) bw_ue(b, (unsigned)skip_run);
+    bw_trailing(b);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* public entry points (ctypes)                                                            */
+typedef struct orc_dump {
+    int16_t* mv_prepass; /* [nframes][nmb][2] full-pel * 4 */
+    int16_t* mv_final;   /* [nframes][nmb][2] quarter-pel */
+    uint8_t* mb_type;    /* [nframes][nmb] */
+    uint8_t* cbp;        /* [nframes][nmb] */
+} orc_dump;
+
+static void store_recon(const Enc* e, const Frame* f, uint8_t* dst) {
+    int w = e->p.width, h = e->p.height, cw = (w + 1) / 2, chh = (h + 1) / 2;
+    for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * w, f->y + (size_t)y * f->ys, w);
+    dst += (size_t)w * h;
+    for (int y = 0; y < chh; y++) memcpy(dst + (size_t)y * cw, f->u + (size_t)y * f->cs, cw);
+    dst += (size_t)cw * chh;
+    for (int y = 0; y < chh; y++) memcpy(dst + (size_t)y * cw, f->v + (size_t)y * f->cs, cw);
+}
+
+int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8_t* out, size_t out_cap,
+               size_t* out_len, vcpenc_frame_info* info, uint8_t* recon, orc_dump* dump) {
+    Enc E; Enc* e = &E;
+    memset(e, 0, sizeof *e);
+    e->p = *p;
+    if (p->width < 16 || p->height < 16 || (p->width & 1) || (p->height & 1) || p->gop < 1 || p->slices < 1) return VCPENC_E_ARGS;
+    if (p->entropy != 0 || p->codec != VCPENC_CODEC_H264 || p->in_fmt != VCPENC_FMT_YUV420P) return VCPENC_E_ARGS;
+    e->mbw = (p->width + 15) / 16; e->mbh = (p->height + 15) / 16; e->nmb = e->mbw * e->mbh;
+    if (p->slices > e->mbh) return VCPENC_E_ARGS;
+    e->cw = 16 * e->mbw; e->ch = 16 * e->mbh;
+    int rc = VCPENC_E_INTERNAL;
+    if (frame_alloc(&e->cur, e->cw, e->ch) || frame_alloc(&e->prev_orig, e->cw, e->ch) ||
+        frame_alloc(&e->recon[0], e->cw, e->ch) || frame_alloc(&e->recon[1], e->cw, e->ch) ||
+        half_alloc(&e->hcur, e->cw, e->ch) || half_alloc(&e->hprev, e->cw, e->ch)) goto done;
+    e->mbs = (MB*)calloc((size_t)e->nmb, sizeof(MB));
+    e->mvfp = (int16_t*)calloc((size_t)e->nmb * 2, sizeof(int16_t));
+    e->rbsp_cap = (size_t)e->nmb * 512 + 4096;
+    e->rbsp = (uint8_t*)malloc(e->rbsp_cap);
+    if (!e->mbs || !e->mvfp || !e->rbsp) goto done;
+
+    size_t fsz = (size_t)p->width * p->height + 2 * (size_t)((p->width + 1) / 2) * ((p->height + 1) / 2);
+    size_t o = 0;
+    int ri = 0, idr_count = 0;
+    for (int n = 0; n < nframes; n++) {
+        int t = n % p->gop, idr = t == 0;
+        int qp = idr ? p->qp_i : p->qp_p;
+        /* K1 */
+        { Frame tf = e->prev_orig; e->prev_orig = e->cur; e->cur = tf; Half th = e->hprev; e->hprev = e->hcur; e->hcur = th; }
+        frame_load_yuv420p(&e->cur, frames + (size_t)n * fsz, p->width, p->height);
+        half_build(&e->hcur, &e->cur);
+        Frame* rec = &e->recon[ri]; const Frame* ref = &e->recon[ri ^ 1];
+        if (idr) {
+            for (int my = 0; my < e->mbh; my++)
+                for (int mx = 0; mx < e->mbw; mx++) encode_i_mb(e, rec, mx, my, qp);
+            if (dump) {
+                if (dump->mv_prepass) memset(dump->mv_prepass + (size_t)n * e->nmb * 2, 0, (size_t)e->nmb * 4);
+            }
+        } else {
+            me_prepass(e);
+            for (int i = 0; i < e->nmb; i++) {
+                me_refine_mb(e, ref, i % e->mbw, i / e->mbw, qp, e->mbs[i].mv);
+                encode_p_mb(e, ref, rec, i % e->mbw, i / e->mbw, qp);
+            }
+            /* post-hoc: predictors, differences, skip */
+            for (int i = 0; i < e->nmb; i++) {
+                MB* mb = &e->mbs[i];
+                int sx, sy, px, py;
+                mv_pskip(e, i % e->mbw, i / e->mbw, &sx, &sy);
+                mvp16(e, i % e->mbw, i / e->mbw, &px, &py);
+                if (!mb->cbp && mb->mv[0] == sx && mb->mv[1] == sy) mb->type = VCP_MB_PSKIP;
+                mb->mvd[0] = (int16_t)(mb->mv[0] - px); mb->mvd[1] = (int16_t)(mb->mv[1] - py);
+            }
+            if (dump && dump->mv_prepass)
+                for (int i = 0; i < 2 * e->nmb; i++) dump->mv_prepass[(size_t)n * e->nmb * 2 + i] = (int16_t)(4 * e->mvfp[i]);
+        }
+        if (dump) for (int i = 0; i < e->nmb; i++) {
+            if (dump->mv_final) { dump->mv_final[((size_t)n * e->nmb + i) * 2] = e->mbs[i].mv[0]; dump->mv_final[((size_t)n * e->nmb + i) * 2 + 1] = e->mbs[i].mv[1]; }
+            if (dump->mb_type) dump->mb_type[(size_t)n * e->nmb + i] = e->mbs[i].type;
+            if (dump->cbp) dump->cbp[(size_t)n * e->nmb + i] = e->mbs[i].cbp;
+        }
+        /* K5 + NAL */
+        size_t au0 = o;
+        if (idr) {
+            size_t k = write_sps(e, out + o, out_cap - o); if (!k) { rc = VCPENC_E_OVERFLOW; goto done; } o += k;
+            k = write_pps(e, out + o, out_cap - o); if (!k) { rc = VCPENC_E_OVERFLOW; goto done; } o += k;
+        }
+        for (int s = 0; s < p->slices; s++) {
+            int r0 = slice_first_row(e, s), r1 = s + 1 < p->slices ? slice_first_row(e, s + 1) : e->mbh;
+            BW b; bw_init(&b, e->rbsp, e->rbsp_cap);
+            write_slice_header(e, &b, r0 * e->mbw, idr, t, idr_count & 1, qp);
+            write_slice_data(e, &b, r0, r1, idr);
+            if (b.overflow) { rc = VCPENC_E_OVERFLOW; goto done; }
+            size_t k = nal_write(out + o, out_cap - o, idr ? 3 : 2, idr ? 5 : 1, e->rbsp, b.pos);
+            if (!k) { rc = VCPENC_E_OVERFLOW; goto done; }
+            o += k;
+        }
+        if (idr) idr_count++;
+        if (info) { info[n].offset = au0; info[n].size = (uint32_t)(o - au0); info[n].is_idr = (uint8_t)idr; info[n].qp = (uint8_t)qp; }
+        /* K4 */
+        deblock_frame(e, rec, qp);
+        frame_pad(rec);
+        if (recon) store_recon(e, rec, recon + (size_t)n * fsz);
+        ri ^= 1;
+    }
+    *out_len = o;
+    rc = VCPENC_OK;
+done:
+    frame_free(&e->cur); frame_free(&e->prev_orig); frame_free(&e->recon[0]); frame_free(&e->recon[1]);
+    free(e->hcur.buf); free(e->hprev.buf); free(e->mbs); free(e->mvfp); free(e->rbsp);
+    return rc;
+}
+
+/* small known-answer taps for unit tests */
+void orc_fdct4(const int* d, int* w) { fdct4(d, w); }
+void orc_idct4(const int* c, int* r) { idct4(c, r); }
+int orc_quant4x4(const int* w, int qp, int intra, int first, int16_t* lv) { return quant4x4(w, qp, intra, first, lv); }
+void orc_dequant4x4(const int16_t* lv, int qp, int first, int* c) { memset(c, 0, 64); dequant4x4(lv, qp, first, c); }
+int orc_cavlc_block(const int16_t* c, int n, int nC, uint8_t* out, int cap) {
+    BW b; bw_init(&b, out, (size_t)cap);
+    cavlc_block(&b, c, n, nC);
+    int bits = (int)bw_bits(&b);
+    if (b.nbits) bw_put(&b, 8 - b.nbits, 0);
+    return bits;
+}
+int orc_ue_bits(unsigned k, uint8_t* out) { BW b; bw_init(&b, out, 8); bw_ue(&b, k); int n = (int)bw_bits(&b); if (b.nbits) bw_put(&b, 8 - b.nbits, 0); return n; }
+int orc_se_bits(int v, uint8_t* out) { BW b; bw_init(&b, out, 8); bw_se(&b, v); int n = (int)bw_bits(&b); if (b.nbits) bw_put(&b, 8 - b.nbits, 0); return n; }
+int orc_luma_qpel(const uint8_t* plane, int stride, int ix, int iy, int fx, int fy) { return luma_qpel(plane, stride, ix, iy, fx, fy); }
+int orc_lambda(int qp) { return vcp_lambda(qp); }
