@@ -75,7 +75,11 @@ typedef struct vcpenc_params {
     int32_t in_width, in_height; /* size of the frames handed in (0 = same as out)  */
     int32_t faststart;         /* -movflags +faststart: moov before mdat            */
     int32_t effort;            /* from -preset / -tune: 0 fast .. 2 slow            */
-    int32_t reserved[12];
+    int32_t debug;             /* 1: keep every reconstructed picture and per-MB
+                                  decisions resident for the parity taps            */
+    int32_t first_gop;         /* index of the first GOP handed in (sharded encodes):
+                                  keeps idr_pic_id alternating across shards        */
+    int32_t reserved[10];
 } vcpenc_params;
 
 /* per coded picture, filled by the encode calls */

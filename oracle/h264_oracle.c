@@ -1030,7 +1030,7 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
 
     size_t fsz = (size_t)p->width * p->height + 2 * (size_t)((p->width + 1) / 2) * ((p->height + 1) / 2);
     size_t o = 0;
-    int ri = 0, idr_count = 0;
+    int ri = 0, idr_count = p->first_gop;
     for (int n = 0; n < nframes; n++) {
         int t = n % p->gop, idr = t == 0;
         int qp = idr ? p->qp_i : p->qp_p;

@@ -1,0 +1,474 @@
+// Encoder core: session management, HBM allocation, GOP-batched stepping of the kernel chain.
+//
+// Execution model (DESIGN.md "Schedule"): closed GOPs are independent, so all GOPs resident on
+// the device advance in lock-step — step t runs each kernel once over frame t of every GOP.
+// The motion-search pre-pass runs once over all frames before the chain starts.  The only
+// serial dimension is t (a P-frame needs the previous reconstruction); everything else is
+// batch parallelism that fills the 148 SMs.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/vcpenc.h"
+#include "host_bits.h"
+#include "vcp_dev.cuh"
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            set_err(err, errlen, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return VCPENC_E_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+namespace {
+
+void set_err(char* err, size_t errlen, const char* fmt, ...) {
+    if (!err || !errlen) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err, errlen, fmt, ap);
+    va_end(ap);
+}
+
+size_t frame_bytes_of(const vcpenc_params& p) {
+    const size_t w = p.width, h = p.height;
+    return w * h + 2 * ((w + 1) / 2) * ((h + 1) / 2);
+}
+
+struct EventPair { cudaEvent_t a, b; int kind; };
+
+}  // namespace
+
+struct vcpenc_session {
+    vcpenc_params p{};
+    VcpGeom g{};
+    VcpBufs b{};
+    int device = 0;
+    int max_frames = 0, nframes = 0, ngop_max = 0, ring = 2;
+    int gop_base = 0;  // clip-level index of the first resident GOP
+    cudaStream_t st = nullptr, st_copy = nullptr;
+    std::vector<void*> allocs;
+    uint8_t* staging[2] = {nullptr, nullptr};
+    cudaEvent_t staging_free[2] = {nullptr, nullptr}, staging_ready[2] = {nullptr, nullptr};
+    int staging_frames = 0;
+    // debug taps
+    short2* dbg_mv = nullptr; uint8_t* dbg_type = nullptr; uint8_t* dbg_cbp = nullptr;
+    // host
+    std::vector<uint8_t> sps, pps;
+    std::vector<uint8_t> h_qp;
+    uint8_t* h_out = nullptr; size_t h_out_cap = 0;   // pinned
+    bool encoded = false;
+    // profiling
+    bool profile = false;
+    std::vector<EventPair> events; size_t events_used = 0;
+    vcpenc_kernel_stat stats[VCPENC_K_COUNT]{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(vcpenc_session* s, T** p, size_t count, char* err, size_t errlen) {
+    void* q = nullptr;
+    const size_t bytes = count * sizeof(T) + 256;  // slack: unaligned vector reads may touch a few bytes past the end
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) {
+        set_err(err, errlen, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return VCPENC_E_CUDA;
+    }
+    s->allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return VCPENC_OK;
+}
+
+int check_params(const vcpenc_params& p, char* err, size_t errlen) {
+    if (p.codec != VCPENC_CODEC_H264) { set_err(err, errlen, "codec %d not implemented (H.264 only)", p.codec); return VCPENC_E_ARGS; }
+    if (p.entropy != 0) { set_err(err, errlen, "CABAC not implemented yet (use -coder 0)"); return VCPENC_E_ARGS; }
+    if (p.width < 16 || p.height < 16 || (p.width & 1) || (p.height & 1)) { set_err(err, errlen, "unsupported picture size %dx%d", p.width, p.height); return VCPENC_E_ARGS; }
+    if (p.gop < 1 || p.slices < 1 || p.slices > (p.height + 15) / 16) { set_err(err, errlen, "bad gop/slices"); return VCPENC_E_ARGS; }
+    if (p.qp_i < 0 || p.qp_i > 51 || p.qp_p < 0 || p.qp_p > 51) { set_err(err, errlen, "qp out of range"); return VCPENC_E_ARGS; }
+    if (p.in_fmt != VCPENC_FMT_YUV420P) { set_err(err, errlen, "input pixel format %d not implemented", p.in_fmt); return VCPENC_E_FORMAT; }
+    if (p.deblock_idc < 0 || p.deblock_idc > 2) { set_err(err, errlen, "bad deblock_idc"); return VCPENC_E_ARGS; }
+    return VCPENC_OK;
+}
+
+struct Prof {
+    vcpenc_session* s; int kind; size_t idx; bool on;
+    Prof(vcpenc_session* s_, int kind_) : s(s_), kind(kind_), idx(0), on(s_->profile) {
+        if (!on) return;
+        if (s->events_used == s->events.size()) {
+            EventPair ep{};
+            cudaEventCreate(&ep.a); cudaEventCreate(&ep.b);
+            s->events.push_back(ep);
+        }
+        idx = s->events_used++;
+        s->events[idx].kind = kind;
+        cudaEventRecord(s->events[idx].a, s->st);
+    }
+    ~Prof() { if (on) cudaEventRecord(s->events[idx].b, s->st); }
+};
+
+void collect_profile(vcpenc_session* s) {
+    for (size_t i = 0; i < s->events_used; i++) {
+        float ms = 0;
+        cudaEventSynchronize(s->events[i].b);
+        cudaEventElapsedTime(&ms, s->events[i].a, s->events[i].b);
+        s->stats[s->events[i].kind].ms += ms;
+        s->stats[s->events[i].kind].launches++;
+    }
+    s->events_used = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vcpenc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* vcpenc_version(void) { return "vcpenc 0.1 (sm_100a, H.264 CAVLC I/P)"; }
+
+void vcpenc_default_params(vcpenc_params* p) {
+    memset(p, 0, sizeof *p);
+    p->fps_num = 30; p->fps_den = 1;
+    p->codec = VCPENC_CODEC_H264;
+    p->gop = 60;
+    p->rc_mode = VCPENC_RC_CQP;
+    p->qp_i = 24; p->qp_p = 26;
+    p->slices = 1;
+    p->deblock_idc = 0;
+    p->entropy = 0;
+    p->in_fmt = VCPENC_FMT_YUV420P;
+    p->effort = 1;
+}
+
+void vcpenc_session_destroy(vcpenc_session* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->st) cudaStreamSynchronize(s->st);
+    for (void* q : s->allocs) cudaFree(q);
+    for (auto& e : s->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (int i = 0; i < 2; i++) {
+        if (s->staging_free[i]) cudaEventDestroy(s->staging_free[i]);
+        if (s->staging_ready[i]) cudaEventDestroy(s->staging_ready[i]);
+    }
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->h_out) cudaFreeHost(s->h_out);
+    if (s->st) cudaStreamDestroy(s->st);
+    if (s->st_copy) cudaStreamDestroy(s->st_copy);
+    delete s;
+}
+
+int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, vcpenc_session** out,
+                          char* err, size_t errlen) {
+    if (!pp || !out || max_frames < 1) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
+    int rc = check_params(*pp, err, errlen);
+    if (rc) return rc;
+    const int ndev = vcpenc_device_count();
+    if (ndev <= 0) { set_err(err, errlen, "no CUDA device available (libvcpenc has no CPU fallback)"); return VCPENC_E_NODEVICE; }
+    if (device < 0 || device >= ndev) { set_err(err, errlen, "device %d out of range (%d visible)", device, ndev); return VCPENC_E_NODEVICE; }
+    CK(cudaSetDevice(device));
+    vcpenc_session* s = new vcpenc_session();
+    s->p = *pp; s->device = device; s->max_frames = max_frames; s->gop_base = pp->first_gop;
+    VcpGeom& g = s->g;
+    g.w = pp->width; g.h = pp->height;
+    g.mbw = (g.w + 15) / 16; g.mbh = (g.h + 15) / 16; g.nmb = g.mbw * g.mbh;
+    g.cw = 16 * g.mbw; g.ch = 16 * g.mbh;
+    g.ys = (g.cw + 2 * VCP_PAD + 127) & ~127;
+    g.cs = g.ys / 2; g.hs = g.ys / 2;
+    g.ysize = (size_t)g.ys * (g.ch + 2 * VCP_PAD);
+    g.csize = (size_t)g.cs * (g.ch / 2 + 2 * VCP_PADC);
+    g.hsize = (size_t)g.hs * (g.ch / 2 + 2 * VCP_PAD1);
+    g.yoff = VCP_PAD * g.ys + VCP_PAD;
+    g.coff = VCP_PADC * g.cs + VCP_PADC;
+    g.hoff = VCP_PAD1 * g.hs + VCP_PAD1;
+    g.slices = pp->slices; g.deblock_idc = pp->deblock_idc;
+    s->ngop_max = (max_frames + pp->gop - 1) / pp->gop;
+    s->ring = pp->debug ? std::min(pp->gop, max_frames) : std::min(2, std::min(pp->gop, max_frames));
+    if (s->ring < 1) s->ring = 1;
+
+#define TRY(x) do { rc = (x); if (rc) { vcpenc_session_destroy(s); return rc; } } while (0)
+#define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(err, errlen, "%s failed: %s", #call, cudaGetErrorString(e_)); vcpenc_session_destroy(s); return VCPENC_E_CUDA; } } while (0)
+    CKS(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    CKS(cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking));
+    CKS(cudaEventCreate(&s->ev0)); CKS(cudaEventCreate(&s->ev1));
+    VcpBufs& b = s->b;
+    const size_t N = max_frames, G = s->ngop_max, nmb = g.nmb;
+    TRY(dev_alloc(s, &b.src_y, N * g.ysize, err, errlen));
+    TRY(dev_alloc(s, &b.src_u, N * g.csize, err, errlen));
+    TRY(dev_alloc(s, &b.src_v, N * g.csize, err, errlen));
+    TRY(dev_alloc(s, &b.src_h, N * g.hsize, err, errlen));
+    TRY(dev_alloc(s, &b.rec_y, G * s->ring * g.ysize, err, errlen));
+    TRY(dev_alloc(s, &b.rec_u, G * s->ring * g.csize, err, errlen));
+    TRY(dev_alloc(s, &b.rec_v, G * s->ring * g.csize, err, errlen));
+    TRY(dev_alloc(s, &b.mvfp, N * nmb, err, errlen));
+    TRY(dev_alloc(s, &b.mv, G * nmb, err, errlen));
+    TRY(dev_alloc(s, &b.mvd, G * nmb, err, errlen));
+    TRY(dev_alloc(s, &b.mbtype, G * nmb, err, errlen));
+    TRY(dev_alloc(s, &b.cbp, G * nmb, err, errlen));
+    TRY(dev_alloc(s, &b.modes, G * nmb, err, errlen));
+    TRY(dev_alloc(s, &b.nnz, G * nmb * 24, err, errlen));
+    TRY(dev_alloc(s, &b.levels, G * nmb * VCP_LV_STRIDE, err, errlen));
+    TRY(dev_alloc(s, &b.mbbits, G * nmb, err, errlen));
+    TRY(dev_alloc(s, &b.mbbitoff, G * nmb, err, errlen));
+    TRY(dev_alloc(s, &b.skiprun, (size_t)1, err, errlen));
+    TRY(dev_alloc(s, &b.qp, N, err, errlen));
+    // raw slice payload: H.264 bounds a macroblock at 3200 bits; 512 B/MB leaves headroom
+    const int rows_per_slice = (g.mbh + g.slices - 1) / g.slices + 1;
+    b.rbsp_cap = ((size_t)rows_per_slice * g.mbw * 512 + 4096 + 15) & ~(size_t)15;
+    TRY(dev_alloc(s, &b.rbsp, G * g.slices * b.rbsp_cap, err, errlen));
+    TRY(dev_alloc(s, &b.slice_bits, G * g.slices, err, errlen));
+    b.out_cap = N * frame_bytes_of(*pp) + (1 << 20);
+    TRY(dev_alloc(s, &b.out, b.out_cap, err, errlen));
+    TRY(dev_alloc(s, &b.out_cursor, (size_t)1, err, errlen));
+    TRY(dev_alloc(s, &b.out_index, N * g.slices, err, errlen));
+    TRY(dev_alloc(s, &b.out_index_hi, N * g.slices, err, errlen));
+    TRY(dev_alloc(s, &b.frame_bits, N, err, errlen));
+    TRY(dev_alloc(s, &b.error_flag, (size_t)1, err, errlen));
+    if (pp->debug) {
+        TRY(dev_alloc(s, &s->dbg_mv, N * nmb, err, errlen));
+        TRY(dev_alloc(s, &s->dbg_type, N * nmb, err, errlen));
+        TRY(dev_alloc(s, &s->dbg_cbp, N * nmb, err, errlen));
+    }
+    // upload staging: two buffers of up to 16 frames
+    s->staging_frames = std::max(1, std::min(16, max_frames));
+    for (int i = 0; i < 2; i++) {
+        TRY(dev_alloc(s, &s->staging[i], (size_t)s->staging_frames * frame_bytes_of(*pp), err, errlen));
+        CKS(cudaEventCreateWithFlags(&s->staging_free[i], cudaEventDisableTiming));
+        CKS(cudaEventCreateWithFlags(&s->staging_ready[i], cudaEventDisableTiming));
+    }
+    // recon must never hold uninitialised borders when a vector reads them
+    CKS(cudaMemsetAsync(b.rec_y, 128, G * s->ring * g.ysize, s->st));
+    CKS(cudaMemsetAsync(b.rec_u, 128, G * s->ring * g.csize, s->st));
+    CKS(cudaMemsetAsync(b.rec_v, 128, G * s->ring * g.csize, s->st));
+    CKS(cudaMemsetAsync(b.mvfp, 0, N * nmb * sizeof(short2), s->st));
+    CKS(cudaStreamSynchronize(s->st));
+    s->sps = vcp::make_sps_nal(*pp);
+    s->pps = vcp::make_pps_nal(*pp);
+    *out = s;
+    return VCPENC_OK;
+#undef TRY
+#undef CKS
+}
+
+int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes, char* err, size_t errlen) {
+    if (!s || !frames || nframes < 1 || nframes > s->max_frames) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
+    CK(cudaSetDevice(s->device));
+    const size_t fb = frame_bytes_of(s->p);
+    s->nframes = nframes;
+    s->encoded = false;
+    s->h_qp.resize(nframes);
+    for (int n = 0; n < nframes; n++) s->h_qp[n] = (uint8_t)((n % s->p.gop) == 0 ? s->p.qp_i : s->p.qp_p);
+    CK(cudaMemcpyAsync(s->b.qp, s->h_qp.data(), nframes, cudaMemcpyHostToDevice, s->st));
+    int chunk = 0;
+    for (int n0 = 0; n0 < nframes; n0 += s->staging_frames, chunk++) {
+        const int k = chunk & 1;
+        const int cnt = std::min(s->staging_frames, nframes - n0);
+        if (chunk >= 2) CK(cudaStreamWaitEvent(s->st_copy, s->staging_free[k], 0));
+        CK(cudaMemcpyAsync(s->staging[k], frames + (size_t)n0 * fb, (size_t)cnt * fb, cudaMemcpyHostToDevice, s->st_copy));
+        CK(cudaEventRecord(s->staging_ready[k], s->st_copy));
+        CK(cudaStreamWaitEvent(s->st, s->staging_ready[k], 0));
+        {
+            Prof pr(s, VCPENC_K_CSC);
+            vcp_launch_k1_yuv420p(s->staging[k], fb, n0, cnt, s->g, s->b, s->st);
+        }
+        CK(cudaEventRecord(s->staging_free[k], s->st));
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s->st));
+    if (s->profile) collect_profile(s);
+    return VCPENC_OK;
+}
+
+static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
+    const VcpGeom& g = s->g;
+    const VcpBufs& b = s->b;
+    const int N = s->nframes, gop = s->p.gop;
+    CK(cudaMemsetAsync(b.out_cursor, 0, sizeof(unsigned long long), s->st));
+    CK(cudaMemsetAsync(b.error_flag, 0, sizeof(int), s->st));
+    CK(cudaMemsetAsync(b.frame_bits, 0, (size_t)N * sizeof(uint32_t), s->st));
+    {
+        Prof pr(s, VCPENC_K_ME_PRE);
+        vcp_launch_me_prepass(g, b, N, gop, s->st);
+    }
+    for (int t = 0; t < gop && t < N; t++) {
+        VcpStep sp;
+        sp.t = t; sp.gop = gop; sp.ring = s->ring; sp.nframes = N; sp.gop0 = s->gop_base;
+        sp.ngop = (N - t + gop - 1) / gop;
+        if (sp.ngop <= 0) break;
+        if (t == 0) {
+            Prof pr(s, VCPENC_K_I_RECON);
+            vcp_launch_i_recon(g, b, sp, s->st);
+        } else {
+            { Prof pr(s, VCPENC_K_ME_REFINE); vcp_launch_me_refine(g, b, sp, s->st); }
+            { Prof pr(s, VCPENC_K_P_RECON); vcp_launch_p_recon(g, b, sp, s->st); }
+            { Prof pr(s, VCPENC_K_MBINFO); vcp_launch_mbinfo(g, b, sp, s->st); }
+        }
+        { Prof pr(s, VCPENC_K_CAVLC_COUNT); vcp_launch_cavlc_count(g, b, sp, s->st); }
+        { Prof pr(s, VCPENC_K_CAVLC_SCAN); vcp_launch_cavlc_scan(g, b, sp, s->st); }
+        { Prof pr(s, VCPENC_K_CAVLC_WRITE); vcp_launch_cavlc_write(g, b, sp, s->st); vcp_launch_nal_pack(g, b, sp, s->st); }
+        { Prof pr(s, VCPENC_K_DEBLOCK); vcp_launch_deblock(g, b, sp, s->st); }
+        { Prof pr(s, VCPENC_K_PAD); vcp_launch_pad(g, b, sp, s->st); }
+        if (s->p.debug) {
+            for (int gi = 0; gi < sp.ngop; gi++) {
+                const size_t n = (size_t)gi * gop + t;
+                CK(cudaMemcpyAsync(s->dbg_mv + n * g.nmb, b.mv + (size_t)gi * g.nmb, g.nmb * sizeof(short2), cudaMemcpyDeviceToDevice, s->st));
+                CK(cudaMemcpyAsync(s->dbg_type + n * g.nmb, b.mbtype + (size_t)gi * g.nmb, g.nmb, cudaMemcpyDeviceToDevice, s->st));
+                CK(cudaMemcpyAsync(s->dbg_cbp + n * g.nmb, b.cbp + (size_t)gi * g.nmb, g.nmb, cudaMemcpyDeviceToDevice, s->st));
+            }
+        }
+    }
+    CK(cudaGetLastError());
+    return VCPENC_OK;
+}
+
+int vcpenc_session_encode(vcpenc_session* s, float* ms, char* err, size_t errlen) {
+    if (!s || s->nframes < 1) { set_err(err, errlen, "no frames uploaded"); return VCPENC_E_ARGS; }
+    CK(cudaSetDevice(s->device));
+    CK(cudaEventRecord(s->ev0, s->st));
+    int rc = run_encode(s, err, errlen);
+    if (rc) return rc;
+    CK(cudaEventRecord(s->ev1, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    if (ms) CK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+    if (s->profile) collect_profile(s);
+    int flag = 0;
+    CK(cudaMemcpy(&flag, s->b.error_flag, sizeof flag, cudaMemcpyDeviceToHost));
+    if (flag) { set_err(err, errlen, "bitstream buffer overflow on device (flag %d)", flag); return VCPENC_E_OVERFLOW; }
+    s->encoded = true;
+    return VCPENC_OK;
+}
+
+int vcpenc_session_download(vcpenc_session* s, uint8_t* out, size_t out_cap, size_t* out_len,
+                            vcpenc_frame_info* info, uint8_t* recon, char* err, size_t errlen) {
+    if (!s || !s->encoded || !out || !out_len) { set_err(err, errlen, "nothing encoded"); return VCPENC_E_ARGS; }
+    CK(cudaSetDevice(s->device));
+    const VcpGeom& g = s->g;
+    const int N = s->nframes, S = g.slices;
+    unsigned long long used = 0;
+    CK(cudaMemcpy(&used, s->b.out_cursor, sizeof used, cudaMemcpyDeviceToHost));
+    if (used > s->h_out_cap) {
+        if (s->h_out) cudaFreeHost(s->h_out);
+        s->h_out = nullptr; s->h_out_cap = 0;
+        const size_t cap = (size_t)used + (used >> 2) + 4096;
+        CK(cudaMallocHost(reinterpret_cast<void**>(&s->h_out), cap));
+        s->h_out_cap = cap;
+    }
+    std::vector<uint2> idx((size_t)N * S);
+    std::vector<uint32_t> idx_hi((size_t)N * S);
+    CK(cudaMemcpyAsync(s->h_out, s->b.out, (size_t)used, cudaMemcpyDeviceToHost, s->st));
+    CK(cudaMemcpyAsync(idx.data(), s->b.out_index, idx.size() * sizeof(uint2), cudaMemcpyDeviceToHost, s->st));
+    CK(cudaMemcpyAsync(idx_hi.data(), s->b.out_index_hi, idx_hi.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    static const uint8_t sc[4] = {0, 0, 0, 1};
+    size_t o = 0;
+    for (int n = 0; n < N; n++) {
+        const bool idr = (n % s->p.gop) == 0;
+        const size_t au0 = o;
+        size_t need = 0;
+        if (idr) need += 8 + s->sps.size() + s->pps.size();
+        for (int k = 0; k < S; k++) need += idx[(size_t)n * S + k].y;
+        if (o + need > out_cap) { set_err(err, errlen, "output buffer too small (%zu needed)", o + need); return VCPENC_E_OVERFLOW; }
+        if (idr) {
+            memcpy(out + o, sc, 4); o += 4; memcpy(out + o, s->sps.data(), s->sps.size()); o += s->sps.size();
+            memcpy(out + o, sc, 4); o += 4; memcpy(out + o, s->pps.data(), s->pps.size()); o += s->pps.size();
+        }
+        for (int k = 0; k < S; k++) {
+            const uint2 e = idx[(size_t)n * S + k];
+            const size_t off = ((size_t)idx_hi[(size_t)n * S + k] << 32) | e.x;
+            memcpy(out + o, s->h_out + off, e.y);
+            o += e.y;
+        }
+        if (info) {
+            info[n].offset = au0; info[n].size = (uint32_t)(o - au0);
+            info[n].is_idr = idr; info[n].qp = s->h_qp[n]; info[n].pad[0] = info[n].pad[1] = 0;
+        }
+    }
+    *out_len = o;
+    if (recon) {
+        if (!s->p.debug) { set_err(err, errlen, "recon download needs params.debug=1"); return VCPENC_E_ARGS; }
+        const size_t fb = frame_bytes_of(s->p);
+        const int w = g.w, h = g.h, cw = (w + 1) / 2, chh = (h + 1) / 2;
+        for (int n = 0; n < N; n++) {
+            const int gi = n / s->p.gop, t = n % s->p.gop;
+            const size_t slot = (size_t)gi * s->ring + (t % s->ring);
+            uint8_t* d = recon + (size_t)n * fb;
+            CK(cudaMemcpy2DAsync(d, w, s->b.rec_y + slot * g.ysize + g.yoff, g.ys, w, h, cudaMemcpyDeviceToHost, s->st));
+            CK(cudaMemcpy2DAsync(d + (size_t)w * h, cw, s->b.rec_u + slot * g.csize + g.coff, g.cs, cw, chh, cudaMemcpyDeviceToHost, s->st));
+            CK(cudaMemcpy2DAsync(d + (size_t)w * h + (size_t)cw * chh, cw, s->b.rec_v + slot * g.csize + g.coff, g.cs, cw, chh, cudaMemcpyDeviceToHost, s->st));
+        }
+        CK(cudaStreamSynchronize(s->st));
+    }
+    return VCPENC_OK;
+}
+
+int vcpenc_session_profile(vcpenc_session* s, int enable) {
+    if (!s) return VCPENC_E_ARGS;
+    s->profile = enable != 0;
+    if (enable) memset(s->stats, 0, sizeof s->stats);
+    return VCPENC_OK;
+}
+
+int vcpenc_session_kernel_stats(vcpenc_session* s, vcpenc_kernel_stat* stats) {
+    if (!s || !stats) return VCPENC_E_ARGS;
+    memcpy(stats, s->stats, sizeof s->stats);
+    return VCPENC_OK;
+}
+
+int vcpenc_session_debug_mbs(vcpenc_session* s, int16_t* mv_prepass, int16_t* mv_final, uint8_t* mb_type, uint8_t* cbp) {
+    if (!s || !s->p.debug || !s->encoded) return VCPENC_E_ARGS;
+    cudaSetDevice(s->device);
+    const size_t n = (size_t)s->nframes * s->g.nmb;
+    if (mv_prepass && cudaMemcpy(mv_prepass, s->b.mvfp, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return VCPENC_E_CUDA;
+    if (mv_final && cudaMemcpy(mv_final, s->dbg_mv, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return VCPENC_E_CUDA;
+    if (mb_type && cudaMemcpy(mb_type, s->dbg_type, n, cudaMemcpyDeviceToHost) != cudaSuccess) return VCPENC_E_CUDA;
+    if (cbp && cudaMemcpy(cbp, s->dbg_cbp, n, cudaMemcpyDeviceToHost) != cudaSuccess) return VCPENC_E_CUDA;
+    return VCPENC_OK;
+}
+
+int vcpenc_encode_frames(const vcpenc_params* p, int device, const uint8_t* frames, int nframes, uint8_t* out,
+                         size_t out_cap, size_t* out_len, vcpenc_frame_info* info, uint8_t* recon,
+                         volatile int* cancel, char* err, size_t errlen) {
+    if (!p || !frames || nframes < 1 || !out || !out_len) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
+    vcpenc_params q = *p;
+    if (recon) q.debug = 1;
+    // bound HBM use: process whole GOPs in chunks
+    const size_t per_frame = 5 * frame_bytes_of(q);
+    size_t budget_frames = (size_t)(48ull << 30) / std::max<size_t>(per_frame, 1);
+    int chunk = (int)std::min<size_t>(budget_frames, (size_t)nframes);
+    if (chunk < nframes) chunk = std::max(q.gop, chunk / q.gop * q.gop);
+    vcpenc_session* s = nullptr;
+    int rc = vcpenc_session_create(&q, device, std::min(chunk, nframes), &s, err, errlen);
+    if (rc) return rc;
+    const size_t fb = frame_bytes_of(q);
+    size_t o = 0;
+    for (int n0 = 0; n0 < nframes && !rc; n0 += chunk) {
+        if (cancel && *cancel) { set_err(err, errlen, "任务被取消"); rc = VCPENC_E_CANCELLED; break; }
+        const int cnt = std::min(chunk, nframes - n0);
+        s->gop_base = q.first_gop + n0 / q.gop;
+        rc = vcpenc_session_upload(s, frames + (size_t)n0 * fb, cnt, err, errlen);
+        if (!rc) rc = vcpenc_session_encode(s, nullptr, err, errlen);
+        size_t len = 0;
+        if (!rc) rc = vcpenc_session_download(s, out + o, out_cap - o, &len, info ? info + n0 : nullptr,
+                                               recon ? recon + (size_t)n0 * fb : nullptr, err, errlen);
+        if (!rc && info) for (int i = 0; i < cnt; i++) info[n0 + i].offset += o;
+        o += len;
+    }
+    vcpenc_session_destroy(s);
+    if (!rc) *out_len = o;
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+// K2 — integer motion estimation.
+//
+//  K2a  me_prepass_kernel : hierarchical full-pel search on the ORIGINAL frames.  It does not
+//        depend on any reconstruction, so one launch covers every P-frame of every GOP that
+//        is resident — this is where the bulk of the SAD work lives and it is off the
+//        frame-to-frame dependency chain.
+//          L1: half-res 8x8 block per macroblock, exhaustive +-12 (625 candidates), SAD via
+//              VABSDIFF4.U8.ACC (__vsadu4); lanes own a column offset dx, walk the 32
+//              reference rows once and feed 8 running accumulators (one per dy in flight).
+//          L0: full-res 16x16, +-2 around twice the L1 vector, warp-cooperative SAD +
+//              redux.sync reduction.
+//  K2b  me_refine_kernel  : inside the per-frame chain, against the RECONSTRUCTED reference:
+//        11 full-pel candidates, then 8 half-pel and 8 quarter-pel neighbours evaluated from
+//        half-pel planes (b, h, j of 8.4.2.2.1) built once per macroblock in shared memory.
+//
+// Replaces x264's `me=hex subme=7` / NVENC's ME inside the ffmpeg child
+// (/root/reference/cmd/consumer.go:376-382).  Decisions are bit-identical to
+// oracle/h264_oracle.c (me_prepass, me_refine_mb).
+#include "vcp_dev.cuh"
+#include "vcp_luma_interp.cuh"
+
+namespace {
+
+constexpr int ME_WARPS = 8;                       // macroblocks per CTA (one row segment)
+constexpr int L1_WIN_W = ME_WARPS * 8 + 2 * VCP_ME_R1;  // 88
+constexpr int L1_WIN_WA = 96;                     // allocated width (word slack for unaligned reads)
+constexpr int L1_WIN_H = 8 + 2 * VCP_ME_R1;       // 32
+
+__global__ void __launch_bounds__(ME_WARPS * 32) me_prepass_kernel(VcpGeom g, VcpBufs b, int nframes, int gop) {
+    __shared__ __align__(16) uint8_t win[L1_WIN_H][L1_WIN_WA];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.z;
+    if (n % gop == 0) return;  // IDR: no search
+    const int my = blockIdx.y, mx0 = blockIdx.x * ME_WARPS, mx = mx0 + warp;
+    const uint8_t* hc = b.src_h + (size_t)n * g.hsize + g.hoff;
+    const uint8_t* hp = b.src_h + (size_t)(n - 1) * g.hsize + g.hoff;
+    // stage the shared L1 window: rows 8my-12 .. 8my+19, cols 8mx0-12 .. 8mx0+75 (+ slack)
+    {
+        const uint8_t* base = hp + (ptrdiff_t)(8 * my - VCP_ME_R1) * g.hs + (8 * mx0 - VCP_ME_R1);
+        for (int i = threadIdx.x; i < L1_WIN_H * (L1_WIN_WA / 4); i += blockDim.x) {
+            int r = i / (L1_WIN_WA / 4), c = i % (L1_WIN_WA / 4);
+            reinterpret_cast<uint32_t*>(&win[r][0])[c] = ld_u32(base + (ptrdiff_t)r * g.hs + 4 * c);
+        }
+    }
+    __syncthreads();
+    if (mx >= g.mbw) return;
+
+    // ---- L1 -----------------------------------------------------------------------------
+    uint32_t cur[8][2];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const uint2 v = *reinterpret_cast<const uint2*>(hc + (size_t)(8 * my + r) * g.hs + 8 * mx);
+        cur[r][0] = v.x; cur[r][1] = v.y;
+    }
+    uint32_t best = 0xffffffffu;
+    if (lane < 2 * VCP_ME_R1 + 1) {
+        const int dx = lane - VCP_ME_R1;
+        const int col = 8 * warp + lane;  // window column of this lane's candidates
+        uint32_t acc[2 * VCP_ME_R1 + 1];
+#pragma unroll
+        for (int i = 0; i < 2 * VCP_ME_R1 + 1; i++) acc[i] = 0;
+#pragma unroll
+        for (int rr = 0; rr < L1_WIN_H; rr++) {
+            const uint2 ref = ld8_unaligned(&win[rr][col]);
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int di = rr - r;  // dy + R1
+                if (di >= 0 && di <= 2 * VCP_ME_R1)
+                    acc[di] = sad4(ref.y, cur[r][1], sad4(ref.x, cur[r][0], acc[di]));
+            }
+        }
+#pragma unroll
+        for (int di = 0; di < 2 * VCP_ME_R1 + 1; di++) {
+            const int dy = di - VCP_ME_R1;
+            const uint32_t cost = acc[di] + VCP_ME_L1_PEN * (vcp_iabs(dx) + vcp_iabs(dy));
+            const uint32_t key = (cost << 16) | (uint32_t)(di * (2 * VCP_ME_R1 + 1) + lane);
+            best = key < best ? key : best;
+        }
+    }
+    best = warp_min(best);
+    const int bi = (int)(best & 0xffff), W = 2 * VCP_ME_R1 + 1;
+    const int cx = 2 * (bi % W - VCP_ME_R1), cy = 2 * (bi / W - VCP_ME_R1);
+
+    // ---- L0: +-2 around (cx,cy) on the full-res originals -----------------------------------
+    const uint8_t* yc = b.src_y + (size_t)n * g.ysize + g.yoff;
+    const uint8_t* yp = b.src_y + (size_t)(n - 1) * g.ysize + g.yoff;
+    const int row = lane >> 1, hx = (lane & 1) * 8;
+    const uint2 c8 = *reinterpret_cast<const uint2*>(yc + (size_t)(16 * my + row) * g.ys + 16 * mx + hx);
+    best = 0xffffffffu;
+#pragma unroll 5
+    for (int idx = 0; idx < 25; idx++) {
+        const int mvx = cx + idx % 5 - 2, mvy = cy + idx / 5 - 2;
+        const uint2 r8 = ld8_unaligned(yp + (ptrdiff_t)(16 * my + row + mvy) * g.ys + 16 * mx + hx + mvx);
+        const int sad = warp_sum((int)sad4(r8.y, c8.y, sad4(r8.x, c8.x, 0)));
+        const uint32_t key = ((uint32_t)(sad + VCP_ME_L0_PEN * (vcp_iabs(mvx) + vcp_iabs(mvy))) << 8) | (uint32_t)idx;
+        best = key < best ? key : best;
+    }
+    if (lane == 0) {
+        const int k = (int)(best & 0xff);
+        b.mvfp[(size_t)n * g.nmb + my * g.mbw + mx] = make_short2((short)(cx + k % 5 - 2), (short)(cy + k / 5 - 2));
+    }
+}
+
+// predictor estimate from the neighbours' pre-pass vectors (oracle: pmv_estimate)
+__device__ __forceinline__ void pmv_estimate(const VcpGeom& g, const short2* __restrict__ mvfp, int mx, int my, int& px, int& py) {
+    const int row0 = vcp_slice_first_row(vcp_slice_of_row(my, g.slices, g.mbh), g.slices, g.mbh);
+    const bool aA = mx > 0, aB = my > row0, aC = aB && mx + 1 < g.mbw, aD = aB && mx > 0;
+    const int i = my * g.mbw + mx;
+    int ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
+    if (aA) { short2 v = mvfp[i - 1]; ax = 4 * v.x; ay = 4 * v.y; }
+    if (aB) { short2 v = mvfp[i - g.mbw]; bx = 4 * v.x; by = 4 * v.y; }
+    if (aC) { short2 v = mvfp[i - g.mbw + 1]; cx = 4 * v.x; cy = 4 * v.y; }
+    else if (aD) { short2 v = mvfp[i - g.mbw - 1]; cx = 4 * v.x; cy = 4 * v.y; }
+    if (!aB && aA) { px = ax; py = ay; return; }
+    px = vcp_median3(ax, bx, cx); py = vcp_median3(ay, by, cy);
+}
+
+constexpr int RF_WARPS = 4;
+
+__global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
+    __shared__ LumaPlanes planes[RF_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mbi = blockIdx.x * RF_WARPS + warp;
+    const int gi = blockIdx.y;
+    if (mbi >= g.nmb) return;
+    const int n = vcp_frame_of(s, gi);
+    const int mx = mbi % g.mbw, my = mbi / g.mbw;
+    const int qp = b.qp[n];
+    const int lam = vcp_lambda(qp);
+    const short2* mvfp = b.mvfp + (size_t)n * g.nmb;
+    int pmx, pmy;
+    pmv_estimate(g, mvfp, mx, my, pmx, pmy);
+    const uint8_t* yc = b.src_y + (size_t)n * g.ysize + g.yoff;
+    const uint8_t* yr = b.rec_y + (size_t)vcp_rec_slot(s, gi, s.t - 1) * g.ysize + g.yoff;
+    const int row = lane >> 1, hx = (lane & 1) * 8;
+    const int px = 16 * mx, py = 16 * my;
+    const uint2 c8 = *reinterpret_cast<const uint2*>(yc + (size_t)(py + row) * g.ys + px + hx);
+    const short2 f = mvfp[mbi];
+
+    // full-pel candidates
+    uint32_t best = 0xffffffffu;
+    int bvx = 0, bvy = 0;
+#pragma unroll 1
+    for (int k = 0; k < 11; k++) {
+        int vx, vy;
+        if (k == 0) { vx = f.x; vy = f.y; }
+        else if (k < 9) { const int q = k - 1 + (k > 4); vx = f.x + q % 3 - 1; vy = f.y + q / 3 - 1; }
+        else if (k == 9) { vx = 0; vy = 0; }
+        else {
+            vx = vcp_clip3(-VCP_MV_FP_MAX, VCP_MV_FP_MAX, (pmx + 2) >> 2);
+            vy = vcp_clip3(-VCP_MV_FP_MAX, VCP_MV_FP_MAX, (pmy + 2) >> 2);
+        }
+        const uint2 r8 = ld8_unaligned(yr + (ptrdiff_t)(py + row + vy) * g.ys + px + hx + vx);
+        const int sad = warp_sum((int)sad4(r8.y, c8.y, sad4(r8.x, c8.x, 0)));
+        const int cost = sad + lam * (vcp_se_len(4 * vx - pmx) + vcp_se_len(4 * vy - pmy));
+        const uint32_t key = ((uint32_t)cost << 4) | (uint32_t)k;
+        if (key < best) { best = key; bvx = vx; bvy = vy; }
+    }
+    uint32_t bcost = best >> 4;
+
+    // half-pel planes around the best full-pel position
+    LumaPlanes& P = planes[warp];
+    luma_planes_build(P, yr + (ptrdiff_t)(py + bvy) * g.ys + px + bvx, g.ys, lane, true, true, true);
+    __syncwarp();
+    int bx = 4 * bvx, by = 4 * bvy;
+    int ox = 0, oy = 0;  // offset of the running best relative to the plane centre, quarter-pel
+#pragma unroll 1
+    for (int step = 2; step >= 1; step--) {
+        uint32_t sb = bcost << 4;
+        int nox = ox, noy = oy;
+#pragma unroll 1
+        for (int k = 1; k <= 8; k++) {
+            const int q = k - 1 + (k > 4);
+            const int cxq = ox + (q % 3 - 1) * step, cyq = oy + (q / 3 - 1) * step;
+            const uint2 p8 = luma_planes_fetch8(P, cxq, cyq, row, hx);
+            const int sad = warp_sum((int)sad4(p8.y, c8.y, sad4(p8.x, c8.x, 0)));
+            const int cost = sad + lam * (vcp_se_len(4 * bvx + cxq - pmx) + vcp_se_len(4 * bvy + cyq - pmy));
+            const uint32_t key = ((uint32_t)cost << 4) | (uint32_t)k;
+            if (key < sb) { sb = key; nox = cxq; noy = cyq; }
+        }
+        bcost = sb >> 4; ox = nox; oy = noy;
+    }
+    bx += ox; by += oy;
+    if (lane == 0) b.mv[(size_t)gi * g.nmb + mbi] = make_short2((short)bx, (short)by);
+}
+
+}  // namespace
+
+void vcp_launch_me_prepass(const VcpGeom& g, const VcpBufs& b, int nframes, int gop, cudaStream_t st) {
+    if (nframes <= 0) return;
+    dim3 grid((g.mbw + ME_WARPS - 1) / ME_WARPS, g.mbh, nframes);
+    me_prepass_kernel<<<grid, ME_WARPS * 32, 0, st>>>(g, b, nframes, gop);
+}
+
+void vcp_launch_me_refine(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
+    dim3 grid((g.nmb + RF_WARPS - 1) / RF_WARPS, s.ngop);
+    me_refine_kernel<<<grid, RF_WARPS * 32, 0, st>>>(g, b, s);
+}

@@ -1,0 +1,411 @@
+// K3 — prediction, 4x4 integer transform, quantisation, dequantisation, inverse transform and
+// reconstruction (H.264 8.3, 8.4.2, 8.5).  One warp per macroblock; lanes 0-15 own the luma
+// 4x4 blocks (coding order), lanes 16-19 the Cb and 20-23 the Cr blocks.
+//
+//   p_recon_kernel : P_L0_16x16, fully parallel over the macroblocks of all resident GOPs.
+//   i_recon_kernel : Intra16x16, wavefront (anti-diagonal) inside one CTA per (frame, slice),
+//                    because intra prediction reads the reconstructed left/top neighbours.
+//
+// Replaces x264's dct/quant/predict inside the ffmpeg child
+// (/root/reference/cmd/consumer.go:376-382).  Bit-identical to oracle/h264_oracle.c
+// (encode_p_mb, encode_i_mb, encode_chroma); the FFmpeg decoder must reproduce `rec_*`.
+#include "vcp_dev.cuh"
+#include "vcp_luma_interp.cuh"
+#include "vcp_transform.cuh"
+
+namespace {
+
+// coding-order luma block index -> position
+__device__ __forceinline__ int blk_x4(int b) { return (b & 1) | ((b >> 1) & 2); }
+__device__ __forceinline__ int blk_y4(int b) { return ((b >> 1) & 1) | ((b >> 2) & 2); }
+__device__ __forceinline__ int blk_ras(int b) { return blk_y4(b) * 4 + blk_x4(b); }
+
+// ---- shared tail: chroma residual of lanes 16..23, writes levels / nnz / recon ---------------
+// pred4[r] = the lane's four predicted rows (packed 4 px); returns per-lane nz of the AC part
+struct __align__(16) McScratch {
+    LumaPlanes P;
+    uint8_t pred[16][16];
+};
+
+__device__ __forceinline__ void store_block_recon(uint8_t* dst, int stride, const uint32_t pred[4], const int r[16]) {
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+        *reinterpret_cast<uint32_t*>(dst + (size_t)y * stride) =
+            vcp_recon4(pred[y], r[4 * y], r[4 * y + 1], r[4 * y + 2], r[4 * y + 3]);
+}
+
+// Transform/quantise/reconstruct one macroblock given per-lane predictions.
+//  lanes 0..15 : luma block b=lane (pred rows in predw)
+//  lanes 16..23: chroma block (plane=(lane-16)>>2, blk=lane&3)
+// intra16: luma DC goes through the 4x4 Hadamard (dcbuf = 16 ints of shared scratch).
+__device__ __forceinline__ void mb_transform(const VcpGeom& g, const VcpBufs& b, int n, int slot, int gi, int mbi,
+                                             int mx, int my, int qp, bool intra16, const uint32_t predw[4],
+                                             int* dcbuf, int lane, uint32_t& cbp_out) {
+    const int qpc = vcp_chroma_qp[vcp_clip3(0, 51, qp)];
+    const bool is_luma = lane < 16, is_chroma = lane >= 16 && lane < 24;
+    const int pl = (lane - 16) >> 2, cb = lane & 3;
+    int bx = 0, by = 0;
+    const uint8_t* src = nullptr;
+    uint8_t* dst = nullptr;
+    int sstride = 0;
+    if (is_luma) {
+        bx = blk_x4(lane) * 4; by = blk_y4(lane) * 4;
+        src = b.src_y + (size_t)n * g.ysize + g.yoff + (size_t)(16 * my + by) * g.ys + 16 * mx + bx;
+        dst = b.rec_y + (size_t)slot * g.ysize + g.yoff + (size_t)(16 * my + by) * g.ys + 16 * mx + bx;
+        sstride = g.ys;
+    } else if (is_chroma) {
+        bx = (cb & 1) * 4; by = (cb >> 1) * 4;
+        const size_t o = g.coff + (size_t)(8 * my + by) * g.cs + 8 * mx + bx;
+        src = (pl ? b.src_v : b.src_u) + (size_t)n * g.csize + o;
+        dst = (pl ? b.rec_v : b.rec_u) + (size_t)slot * g.csize + o;
+        sstride = g.cs;
+    }
+    int w[16], c[16], lv[16], r[16];
+    int nz = 0;
+    if (is_luma || is_chroma) {
+        int d[16];
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            const uint32_t s4 = ld_u32(src + (size_t)y * sstride), p4 = predw[y];
+#pragma unroll
+            for (int x = 0; x < 4; x++) d[4 * y + x] = (int)((s4 >> (8 * x)) & 255) - (int)((p4 >> (8 * x)) & 255);
+        }
+        vcp_fdct4(d, w);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = 0;
+    }
+    const bool ac_only = is_chroma || (is_luma && intra16);
+    if (is_luma || is_chroma) nz = vcp_quant_dequant4x4(w, is_luma ? qp : qpc, intra16, ac_only ? 1 : 0, lv, c);
+
+    // chroma DC (lanes 16..23; all lanes execute the shuffles)
+    {
+        int deq = 0;
+        const int l = vcp_chroma_dc(is_chroma ? w[0] : 0, qpc, intra16, lane, deq);
+        if (is_chroma) {
+            c[0] = deq;
+            b.levels[((size_t)gi * g.nmb + mbi) * VCP_LV_STRIDE + VCP_LV_CHROMA_DC + pl * 4 + cb] = (int16_t)l;
+        }
+        const uint32_t dcnz = __ballot_sync(0xffffffffu, is_chroma && l != 0);
+        const uint32_t acnz = __ballot_sync(0xffffffffu, is_chroma && nz != 0);
+        const uint32_t cbpc = acnz ? 2u : (dcnz ? 1u : 0u);
+        cbp_out = cbpc << 4;
+        if (is_chroma && !acnz) nz = 0;
+    }
+    // luma DC for Intra16x16: 4x4 Hadamard over the 16 block DCs (8.5.10 restated forward)
+    if (intra16) {
+        const int ras = blk_ras(lane & 15);
+        // Hadamard sign H[r][c] (rows ++++, ++--, +--+, +-+-): bit r*4+c set => -1
+        constexpr uint32_t HS = 0xA6C0u;
+        const int hi = (lane >> 2) & 3, hj = lane & 3;
+        if (is_luma) dcbuf[ras] = w[0];
+        __syncwarp();
+        int lvl = 0;
+        if (is_luma) {
+            int sum = 0;
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int sg = (((HS >> (hi * 4 + a)) ^ (HS >> (hj * 4 + q))) & 1) ? -1 : 1;
+                    sum += sg * dcbuf[a * 4 + q];
+                }
+            const int qbits = 15 + qp / 6, f = (1 << qbits) / 3;
+            lvl = vcp_quant1(sum >> 1, vcp_quant_mf[qp % 6][0], 2 * f, qbits + 1);
+        }
+        __syncwarp();
+        if (is_luma) dcbuf[lane] = lvl;  // raster
+        __syncwarp();
+        int dq = 0;
+        if (is_luma) {
+            int sum = 0;
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int sg = (((HS >> (hi * 4 + a)) ^ (HS >> (hj * 4 + q))) & 1) ? -1 : 1;
+                    sum += sg * dcbuf[a * 4 + q];
+                }
+            const int ls = 16 * vcp_dequant_v[qp % 6][0];
+            dq = qp >= 36 ? (sum * ls) << (qp / 6 - 6) : (sum * ls + (1 << (5 - qp / 6))) >> (6 - qp / 6);
+            // zig-zag position of raster index `lane`
+            const int zpos = (int)((0xFEA9DB83C7426510ull >> (4 * lane)) & 15);
+            b.levels[((size_t)gi * g.nmb + mbi) * VCP_LV_STRIDE + VCP_LV_LUMA_DC + zpos] = (int16_t)lvl;
+        }
+        __syncwarp();
+        if (is_luma) dcbuf[16 + lane] = dq;  // raster dequantised DCs
+        __syncwarp();
+        if (is_luma) c[0] = dcbuf[16 + ras];
+    }
+    // coded block pattern (luma)
+    {
+        const uint32_t nzm = __ballot_sync(0xffffffffu, is_luma && nz != 0);
+        uint32_t cbpl;
+        if (intra16) { cbpl = nzm ? 15u : 0u; }
+        else cbpl = ((nzm & 0x000fu) ? 1u : 0u) | ((nzm & 0x00f0u) ? 2u : 0u) | ((nzm & 0x0f00u) ? 4u : 0u) | ((nzm & 0xf000u) ? 8u : 0u);
+        cbp_out |= cbpl;
+    }
+    // write levels, nnz, recon
+    if (is_luma || is_chroma) {
+        int16_t* lvp = b.levels + ((size_t)gi * g.nmb + mbi) * VCP_LV_STRIDE +
+                       (is_luma ? VCP_LV_LUMA + lane * 16 : VCP_LV_CHROMA_AC + (pl * 4 + cb) * 16);
+        vcp_store_levels16(lvp, lv);
+        const int ni = is_luma ? blk_y4(lane) * 4 + blk_x4(lane) : 16 + pl * 4 + cb;
+        b.nnz[((size_t)gi * g.nmb + mbi) * 24 + ni] = (uint8_t)nz;
+        vcp_idct4(c, r);
+        store_block_recon(dst, sstride, predw, r);
+    }
+}
+
+// ---- P macroblocks ---------------------------------------------------------------------------
+constexpr int PR_WARPS = 4;
+
+__global__ void __launch_bounds__(PR_WARPS * 32) p_recon_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
+    __shared__ McScratch scr[PR_WARPS];
+    __shared__ uint8_t cpred[PR_WARPS][2][8][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mbi = blockIdx.x * PR_WARPS + warp;
+    const int gi = blockIdx.y;
+    if (mbi >= g.nmb) return;
+    const int n = vcp_frame_of(s, gi);
+    const int slot = vcp_rec_slot(s, gi, s.t), rslot = vcp_rec_slot(s, gi, s.t - 1);
+    const int mx = mbi % g.mbw, my = mbi / g.mbw;
+    const int qp = b.qp[n];
+    const short2 mv = b.mv[(size_t)gi * g.nmb + mbi];
+
+    // luma prediction into shared memory
+    McScratch& S = scr[warp];
+    {
+        const int ix = mv.x >> 2, iy = mv.y >> 2, fx = mv.x & 3, fy = mv.y & 3;
+        bool nb, nh, nj;
+        luma_planes_needs(fx, fy, nb, nh, nj);
+        const uint8_t* yr = b.rec_y + (size_t)rslot * g.ysize + g.yoff;
+        luma_planes_build(S.P, yr + (ptrdiff_t)(16 * my + iy) * g.ys + 16 * mx + ix, g.ys, lane, nb, nh, nj);
+        const int row = lane >> 1, hx = (lane & 1) * 8;
+        const uint2 p8 = luma_planes_fetch8(S.P, fx, fy, row, hx);
+        *reinterpret_cast<uint2*>(&S.pred[row][hx]) = p8;
+    }
+    // chroma prediction: lane -> plane, row, 4 px
+    {
+        const int pl = lane >> 4, row = (lane >> 1) & 7, hx = (lane & 1) * 4;
+        const int ix = mv.x >> 3, iy = mv.y >> 3, dx = mv.x & 7, dy = mv.y & 7;
+        const uint8_t* cr = (pl ? b.rec_v : b.rec_u) + (size_t)rslot * g.csize + g.coff +
+                            (ptrdiff_t)(8 * my + iy + row) * g.cs + 8 * mx + ix + hx;
+        const uint2 r0 = ld8_unaligned(cr), r1 = ld8_unaligned(cr + g.cs);
+        uint32_t outw = 0;
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            const int A = (x < 4 ? (r0.x >> (8 * x)) : 0) & 255;
+            const int Bv = x < 3 ? (r0.x >> (8 * (x + 1))) & 255 : r0.y & 255;
+            const int Cc = (r1.x >> (8 * x)) & 255;
+            const int D = x < 3 ? (r1.x >> (8 * (x + 1))) & 255 : r1.y & 255;
+            const int v = ((8 - dx) * (8 - dy) * A + dx * (8 - dy) * Bv + (8 - dx) * dy * Cc + dx * dy * D + 32) >> 6;
+            outw |= (uint32_t)v << (8 * x);
+        }
+        *reinterpret_cast<uint32_t*>(&cpred[warp][pl][row][hx]) = outw;
+    }
+    __syncwarp();
+    uint32_t predw[4] = {0, 0, 0, 0};
+    if (lane < 16) {
+        const int bx = blk_x4(lane) * 4, by = blk_y4(lane) * 4;
+#pragma unroll
+        for (int y = 0; y < 4; y++) predw[y] = *reinterpret_cast<const uint32_t*>(&S.pred[by + y][bx]);
+    } else if (lane < 24) {
+        const int pl = (lane - 16) >> 2, cb = lane & 3, bx = (cb & 1) * 4, by = (cb >> 1) * 4;
+#pragma unroll
+        for (int y = 0; y < 4; y++) predw[y] = *reinterpret_cast<const uint32_t*>(&cpred[warp][pl][by + y][bx]);
+    }
+    uint32_t cbp;
+    mb_transform(g, b, n, slot, gi, mbi, mx, my, qp, false, predw, nullptr, lane, cbp);
+    if (lane == 0) {
+        b.cbp[(size_t)gi * g.nmb + mbi] = (uint8_t)cbp;
+        b.mbtype[(size_t)gi * g.nmb + mbi] = VCP_MB_P16;
+        b.modes[(size_t)gi * g.nmb + mbi] = 0;
+    }
+}
+
+// ---- Intra16x16 macroblocks (wavefront) ----------------------------------------------------------
+constexpr int IR_WARPS = 16;
+
+struct __align__(16) IScratch {
+    uint8_t top[24];   // [0..3] unused pad, top[4+x] x=-1..16 -> index x+4 (x=-1 at 3)
+    uint8_t left[16];
+    uint8_t ctop[2][12];  // index x+4, x=-1..7
+    uint8_t cleft[2][8];
+    uint8_t pred[16][16];
+    uint8_t cpred[2][8][8];
+    int dcbuf[32];
+};
+
+__device__ __forceinline__ uint32_t splat4(int v) { return (uint32_t)v * 0x01010101u; }
+
+__device__ void i16_encode_mb(const VcpGeom& g, const VcpBufs& b, IScratch& S, int n, int slot, int gi, int mx, int my,
+                              int row0, int qp, int lane) {
+    const int mbi = my * g.mbw + mx;
+    const bool aL = mx > 0, aT = my > row0;
+    uint8_t* ry = b.rec_y + (size_t)slot * g.ysize + g.yoff + (size_t)(16 * my) * g.ys + 16 * mx;
+    uint8_t* ru = b.rec_u + (size_t)slot * g.csize + g.coff + (size_t)(8 * my) * g.cs + 8 * mx;
+    uint8_t* rv = b.rec_v + (size_t)slot * g.csize + g.coff + (size_t)(8 * my) * g.cs + 8 * mx;
+    // neighbours (unfiltered reconstruction of this picture)
+    if (lane < 17) S.top[3 + lane] = (aT && (lane > 0 || aL)) ? ry[-(ptrdiff_t)g.ys + lane - 1] : 128;
+    if (lane < 16) S.left[lane] = aL ? ry[(ptrdiff_t)lane * g.ys - 1] : 128;
+    if (lane < 18) {
+        const int pl = lane / 9, x = lane % 9 - 1;
+        const uint8_t* rc = pl ? rv : ru;
+        S.ctop[pl][4 + x] = (aT && (x >= 0 || aL)) ? rc[-(ptrdiff_t)g.cs + x] : 128;
+    }
+    if (lane >= 16) {
+        const int pl = (lane - 16) >> 3, y = lane & 7;
+        S.cleft[pl][y] = aL ? (pl ? rv : ru)[(ptrdiff_t)y * g.cs - 1] : 128;
+    }
+    __syncwarp();
+    // ---- luma mode decision: lane owns row = lane>>1, 8 px at hx
+    const int row = lane >> 1, hx = (lane & 1) * 8;
+    const uint8_t* sy = b.src_y + (size_t)n * g.ysize + g.yoff + (size_t)(16 * my + row) * g.ys + 16 * mx + hx;
+    const uint2 c8 = *reinterpret_cast<const uint2*>(sy);
+    uint32_t best = 0xffffffffu;
+    uint2 bestp = make_uint2(0, 0);
+    // DC value
+    int dcv;
+    {
+        int st = 0, sl = 0;
+        for (int i = 0; i < 16; i++) { st += S.top[4 + i]; sl += S.left[i]; }
+        dcv = (aT && aL) ? (st + sl + 16) >> 5 : aT ? (st + 8) >> 4 : aL ? (sl + 8) >> 4 : 128;
+    }
+    // plane parameters
+    int pa = 0, pb = 0, pc = 0;
+    if (aT && aL) {
+        int H = 0, V = 0;
+        for (int i = 0; i < 8; i++) {
+            H += (i + 1) * (S.top[4 + 8 + i] - S.top[4 + 6 - i]);
+            const int lo = 6 - i;
+            V += (i + 1) * (S.left[8 + i] - (lo >= 0 ? S.left[lo] : S.top[3]));
+        }
+        pa = 16 * (S.left[15] + S.top[4 + 15]); pb = (5 * H + 32) >> 6; pc = (5 * V + 32) >> 6;
+    }
+#pragma unroll 1
+    for (int mode = 0; mode < 4; mode++) {
+        if ((mode == 0 && !aT) || (mode == 1 && !aL) || (mode == 3 && !(aT && aL))) continue;
+        uint2 p;
+        if (mode == 0) p = make_uint2(*reinterpret_cast<const uint32_t*>(&S.top[4 + hx]), *reinterpret_cast<const uint32_t*>(&S.top[8 + hx]));
+        else if (mode == 1) p = make_uint2(splat4(S.left[row]), splat4(S.left[row]));
+        else if (mode == 2) p = make_uint2(splat4(dcv), splat4(dcv));
+        else {
+            uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+            for (int x = 0; x < 8; x++) {
+                const uint32_t v = (uint32_t)vcp_clip255((pa + pb * (hx + x - 7) + pc * (row - 7) + 16) >> 5);
+                if (x < 4) w0 |= v << (8 * x); else w1 |= v << (8 * (x - 4));
+            }
+            p = make_uint2(w0, w1);
+        }
+        const int sad = warp_sum((int)sad4(p.y, c8.y, sad4(p.x, c8.x, 0)));
+        const uint32_t key = ((uint32_t)sad << 2) | (uint32_t)mode;
+        if (key < best) { best = key; bestp = p; }
+    }
+    const int i16mode = (int)(best & 3);
+    *reinterpret_cast<uint2*>(&S.pred[row][hx]) = bestp;
+
+    // ---- chroma mode decision: lane -> plane = lane>>4, row = (lane>>1)&7, 4 px at cx
+    const int cpl = lane >> 4, crow = (lane >> 1) & 7, cx = (lane & 1) * 4;
+    const uint8_t* sc = (cpl ? b.src_v : b.src_u) + (size_t)n * g.csize + g.coff + (size_t)(8 * my + crow) * g.cs + 8 * mx + cx;
+    const uint32_t cc4 = ld_u32(sc);
+    best = 0xffffffffu;
+    uint32_t bestc = 0;
+    // DC of this lane's 4x4 block
+    int cdc;
+    {
+        const int bxx = cx, byy = crow & 4;
+        int st = 0, sl = 0;
+        for (int i = 0; i < 4; i++) { st += S.ctop[cpl][4 + bxx + i]; sl += S.cleft[cpl][byy + i]; }
+        const int blk = (byy >> 2) * 2 + (bxx >> 2);
+        if (blk == 0 || blk == 3) cdc = (aT && aL) ? (st + sl + 4) >> 3 : aT ? (st + 2) >> 2 : aL ? (sl + 2) >> 2 : 128;
+        else if (blk == 1) cdc = aT ? (st + 2) >> 2 : aL ? (sl + 2) >> 2 : 128;
+        else cdc = aL ? (sl + 2) >> 2 : aT ? (st + 2) >> 2 : 128;
+    }
+    int ca = 0, cbb = 0, ccc = 0;
+    if (aT && aL) {
+        int H = 0, V = 0;
+        for (int i = 0; i < 4; i++) {
+            H += (i + 1) * (S.ctop[cpl][4 + 4 + i] - S.ctop[cpl][4 + 2 - i]);
+            const int lo = 2 - i;
+            V += (i + 1) * (S.cleft[cpl][4 + i] - (lo >= 0 ? S.cleft[cpl][lo] : S.ctop[cpl][3]));
+        }
+        ca = 16 * (S.cleft[cpl][7] + S.ctop[cpl][4 + 7]); cbb = (34 * H + 32) >> 6; ccc = (34 * V + 32) >> 6;
+    }
+#pragma unroll 1
+    for (int mode = 0; mode < 4; mode++) {
+        if ((mode == 1 && !aL) || (mode == 2 && !aT) || (mode == 3 && !(aT && aL))) continue;
+        uint32_t p;
+        if (mode == 0) p = splat4(cdc);
+        else if (mode == 1) p = splat4(S.cleft[cpl][crow]);
+        else if (mode == 2) p = *reinterpret_cast<const uint32_t*>(&S.ctop[cpl][4 + cx]);
+        else {
+            p = 0;
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+                p |= (uint32_t)vcp_clip255((ca + cbb * (cx + x - 3) + ccc * (crow - 3) + 16) >> 5) << (8 * x);
+        }
+        const int sad = warp_sum((int)sad4(p, cc4, 0));
+        const uint32_t key = ((uint32_t)sad << 2) | (uint32_t)mode;
+        if (key < best) { best = key; bestc = p; }
+    }
+    const int cmode = (int)(best & 3);
+    *reinterpret_cast<uint32_t*>(&S.cpred[cpl][crow][cx]) = bestc;
+    __syncwarp();
+
+    uint32_t predw[4] = {0, 0, 0, 0};
+    if (lane < 16) {
+        const int bx = blk_x4(lane) * 4, by = blk_y4(lane) * 4;
+#pragma unroll
+        for (int y = 0; y < 4; y++) predw[y] = *reinterpret_cast<const uint32_t*>(&S.pred[by + y][bx]);
+    } else if (lane < 24) {
+        const int pl = (lane - 16) >> 2, cb = lane & 3, bx = (cb & 1) * 4, by = (cb >> 1) * 4;
+#pragma unroll
+        for (int y = 0; y < 4; y++) predw[y] = *reinterpret_cast<const uint32_t*>(&S.cpred[pl][by + y][bx]);
+    }
+    uint32_t cbp;
+    mb_transform(g, b, n, slot, gi, mbi, mx, my, qp, true, predw, S.dcbuf, lane, cbp);
+    if (lane == 0) {
+        const size_t o = (size_t)gi * g.nmb + mbi;
+        b.cbp[o] = (uint8_t)cbp;
+        b.mbtype[o] = VCP_MB_I16;
+        b.modes[o] = (uint8_t)(i16mode | (cmode << 2));
+        b.mv[o] = make_short2(0, 0);
+        b.mvd[o] = make_short2(0, 0);
+    }
+}
+
+// grid: x = slice, y = GOP
+__global__ void __launch_bounds__(IR_WARPS * 32) i_recon_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
+    __shared__ IScratch scr[IR_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sl = blockIdx.x, gi = blockIdx.y;
+    const int n = vcp_frame_of(s, gi);
+    const int slot = vcp_rec_slot(s, gi, s.t);
+    const int qp = b.qp[n];
+    const int r0 = vcp_slice_first_row(sl, g.slices, g.mbh);
+    const int r1 = sl + 1 < g.slices ? vcp_slice_first_row(sl + 1, g.slices, g.mbh) : g.mbh;
+    const int rows = r1 - r0;
+    const int ndiag = g.mbw + rows - 1;
+    for (int d = 0; d < ndiag; d++) {
+        // macroblocks on this anti-diagonal: (mx, r0 + k) with mx = d - k
+        const int k0 = d - (g.mbw - 1) > 0 ? d - (g.mbw - 1) : 0;
+        const int k1 = d < rows - 1 ? d : rows - 1;
+        for (int k = k0 + warp; k <= k1; k += IR_WARPS)
+            i16_encode_mb(g, b, scr[warp], n, slot, gi, d - k, r0 + k, r0, qp, lane);
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+void vcp_launch_p_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
+    dim3 grid((g.nmb + PR_WARPS - 1) / PR_WARPS, s.ngop);
+    p_recon_kernel<<<grid, PR_WARPS * 32, 0, st>>>(g, b, s);
+}
+
+void vcp_launch_i_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
+    dim3 grid(g.slices, s.ngop);
+    i_recon_kernel<<<grid, IR_WARPS * 32, 0, st>>>(g, b, s);
+}
