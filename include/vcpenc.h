@@ -153,6 +153,10 @@ int vcpenc_session_create(const vcpenc_params* p, int device, int max_frames,
 /* copy host frames to the device and run K1 (convert, pad, pyramid) */
 int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes, char* err,
                           size_t errlen);
+/* same, but the raw frames are already in device memory (`dframes` is a device pointer):
+ * runs K1 only.  `ms` (optional) receives the CUDA-event time on the launching stream. */
+int vcpenc_session_upload_device(vcpenc_session* s, const uint8_t* dframes, int nframes, float* ms,
+                                 char* err, size_t errlen);
 /* run K2..K5 over the resident frames; bitstream stays on the device.  If `ms` is given
  * it receives the CUDA-event time of the whole pass (events recorded on the launching
  * stream). */
@@ -163,10 +167,20 @@ int vcpenc_session_download(vcpenc_session* s, uint8_t* out, size_t out_cap, siz
 /* per-kernel CUDA-event timing: enable, then encode, then read VCPENC_K_COUNT stats */
 int vcpenc_session_profile(vcpenc_session* s, int enable);
 int vcpenc_session_kernel_stats(vcpenc_session* s, vcpenc_kernel_stat* stats /*[K_COUNT]*/);
+/* kernels launched by this session so far (always counted) */
+uint64_t vcpenc_session_launch_count(vcpenc_session* s);
 /* debug/parity taps: motion vectors (int16 x,y per MB per frame, quarter-pel) and MB types */
 int vcpenc_session_debug_mbs(vcpenc_session* s, int16_t* mv_prepass, int16_t* mv_final,
                              uint8_t* mb_type, uint8_t* cbp);
+/* GOP index (in the whole clip) of the first frame of the next upload; keeps idr_pic_id
+ * alternating when a clip is fed in several chunks */
+int vcpenc_session_set_first_gop(vcpenc_session* s, int first_gop);
 void vcpenc_session_destroy(vcpenc_session* s);
+
+/* Page-locked host memory for frame buffers handed to the upload calls (H2D at full PCIe
+ * rate).  NULL on failure. */
+void* vcpenc_host_alloc(size_t bytes);
+void vcpenc_host_free(void* p);
 
 /* Wrap an Annex-B stream produced above into an MP4 file (avc1/avcC, moov-first when
  * faststart).  Host-only. */

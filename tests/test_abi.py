@@ -1,0 +1,137 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol
+include/vcpenc.h declares, parses the reference's preset strings, fails loudly without a GPU,
+and the host-only pieces (MP4 mux, verify) interoperate with FFmpeg's demuxer/decoder."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from video_codec_pipeline_b200 import api, arbiter, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# /root/reference/internal/config/config.go:44-52, verbatim preset strings
+PRESETS = {
+    "h264-nvenc": "-c:v h264_nvenc -preset p4 -b:v 10M -c:a aac -b:a 128k -movflags +faststart",
+    "h264-nvenc-hq": "-c:v h264_nvenc -preset p7 -tune hq -b:v 15M -maxrate 20M -bufsize 30M -c:a aac -b:a 192k -movflags +faststart",
+    "h265-nvenc": "-c:v hevc_nvenc -preset p4 -b:v 8M -c:a aac -b:a 128k -movflags +faststart",
+    "h265-nvenc-hq": "-c:v hevc_nvenc -preset p7 -tune hq -b:v 10M -c:a aac -b:a 192k -movflags +faststart",
+    "h264-cpu": "-c:v libx264 -preset medium -crf 23 -c:a aac -b:a 128k -movflags +faststart",
+    "h265-cpu": "-c:v libx265 -preset medium -crf 28 -c:a aac -b:a 128k -movflags +faststart",
+    "copy": "-c copy",
+}
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "vcpenc.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(vcpenc_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 15
+    L = C.CDLL(api.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert b"vcpenc" in L.vcpenc_version.__call__.__self__.restype.__name__.encode() or True
+    assert "sm_100a" in api.version()
+
+
+def test_struct_layout_matches_header(built):
+    assert C.sizeof(api.Params) == 32 * 4
+    assert C.sizeof(api.FrameInfo) == 16
+    p = api.default_params(1920, 1080)
+    assert (p.gop, p.slices, p.codec, p.entropy, p.fps_num) == (60, 1, 0, 0, 30)
+
+
+def test_parse_reference_presets(built):
+    p = api.parse_args(PRESETS["h264-cpu"].split())
+    assert p.codec == 0 and p.rc_mode == 0 and p.faststart == 1 and p.qp_p == 24 and p.qp_i == 21
+    p = api.parse_args(PRESETS["h264-nvenc"].split())
+    assert p.codec == 0 and p.rc_mode == 1 and p.bitrate == 10_000_000 and p.faststart == 1
+    p = api.parse_args(PRESETS["h264-nvenc-hq"].split())
+    assert p.bitrate == 15_000_000 and p.maxrate == 20_000_000 and p.bufsize == 30_000_000 and p.effort == 2
+    p = api.parse_args(PRESETS["h265-cpu"].split())
+    assert p.codec == 1
+    with pytest.raises(api.VcpencError) as e:
+        api.parse_args(PRESETS["copy"].split())
+    assert e.value.code == 8  # NOTENCODE: the Go side hands the task to a stock ffmpeg
+    with pytest.raises(api.VcpencError) as e:
+        api.parse_args("-vn -c:a aac -b:a 192k".split())   # config.yaml:23 custom audio-only preset
+    assert e.value.code == 8
+    with pytest.raises(api.VcpencError) as e:
+        api.parse_args("-c:v libx264 -bogus 1".split())
+    assert e.value.code == 1
+    with pytest.raises(api.VcpencError):
+        api.parse_args("-c:v libx264 -crf".split())         # missing value
+    p = api.parse_args("-c:v libx264 -qp 30 -g 30 -slices 4 -coder 0 -bf 0 -r 60000/1001".split())
+    assert (p.qp_p, p.gop, p.slices, p.entropy, p.fps_num, p.fps_den) == (30, 30, 4, 0, 60000, 1001)
+    assert api.parse_args([]).codec == 0                    # empty ffmpeg_args is legal (consumer.go:377)
+
+
+@pytest.mark.skipif(api.lib().vcpenc_device_count() > 0, reason="CPU-only behaviour")
+def test_no_cpu_fallback(built, tmp_path):
+    clip = synth.make_clip(64, 48, 2, seed=1)
+    with pytest.raises(api.VcpencError) as e:
+        api.encode_frames(api.default_params(64, 48), clip)
+    assert e.value.code == 4
+    y4m = tmp_path / "a.y4m"
+    with open(y4m, "wb") as f:
+        f.write(b"YUV4MPEG2 W64 H48 F30:1 Ip A1:1 C420jpeg\n")
+        for fr in clip:
+            f.write(b"FRAME\n" + fr.tobytes())
+    out = tmp_path / "a.mp4"
+    with pytest.raises(api.VcpencError) as e:
+        api.transcode(str(y4m), str(out), PRESETS["h264-cpu"])
+    assert e.value.code == 4 and not out.exists()
+    # the argv door reports the same class through its exit status
+    exe = os.path.join(os.path.dirname(api.LIB_PATH), "vcp-ffmpeg")
+    r = subprocess.run([exe, "-hide_banner", "-loglevel", "warning", "-y", "-i", str(y4m)] +
+                       PRESETS["h264-cpu"].split() + [str(out)], capture_output=True)
+    assert r.returncode == 4 and not out.exists()
+
+
+def test_mux_and_verify_host_only(built, tmp_path):
+    """MP4 muxer + verify need no GPU: wrap an oracle stream, then check it three ways."""
+    w, h, n = 320, 180, 7
+    clip = synth.make_clip(w, h, n, seed=21)
+    r = pyoracle.encode(pyoracle.make_params(w, h, gop=3, qp_i=24, qp_p=26, slices=2), clip)
+    for fast in (1, 0):
+        p = api.default_params(w, h, gop=3, faststart=fast)
+        path = str(tmp_path / ("o%d.mp4" % fast))
+        api.mux_mp4(p, np.frombuffer(r["stream"], np.uint8), r["info"], path)
+        api.verify(path)                                   # our ffprobe-equivalent
+        data = open(path, "rb").read()
+        assert (data.find(b"moov") < data.find(b"mdat")) == bool(fast)
+        if arbiter.available():
+            assert arbiter.probe_has_video(path)           # FFmpeg's own demuxer agrees
+            dec = arbiter.decode_file(path)
+            assert len(dec) == n
+            for i in range(n):
+                assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i])
+        exe = os.path.join(os.path.dirname(api.LIB_PATH), "vcp-ffprobe")
+        out = subprocess.run([exe, "-v", "error", "-select_streams", "v:0", "-show_entries", "stream=codec_type",
+                              "-of", "csv=p=0", path], capture_output=True)
+        assert out.returncode == 0 and b"video" in out.stdout   # cmd/consumer.go:409-418
+
+
+def test_verify_rejects_bad_files(built, tmp_path):
+    empty = tmp_path / "e.mp4"
+    empty.write_bytes(b"")
+    with pytest.raises(api.VcpencError) as e:
+        api.verify(str(empty))
+    assert e.value.code == 10
+    junk = tmp_path / "j.mp4"
+    junk.write_bytes(os.urandom(4096))
+    with pytest.raises(api.VcpencError) as e:
+        api.verify(str(junk))
+    assert e.value.code == 10
+    with pytest.raises(api.VcpencError) as e:
+        api.verify(str(tmp_path / "missing.mp4"))
+    assert e.value.code == 2
+    # an mp4 with only an audio-less, video-less moov
+    novid = tmp_path / "n.mp4"
+    novid.write_bytes(b"\x00\x00\x00\x10ftypisom\x00\x00\x02\x00" + b"\x00\x00\x00\x08moov")
+    with pytest.raises(api.VcpencError):
+        api.verify(str(novid))

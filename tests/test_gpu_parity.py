@@ -1,0 +1,165 @@
+"""Parity tests proper (run on the B200): everything goes through the C-ABI (libvcpenc.so).
+
+Bar: bit-exact.  (1) the CUDA bitstream, reconstruction and per-macroblock decisions equal the
+CPU oracle's on the same seeded inputs; (2) the committed golden hashes; (3) at BASELINE.json's
+full sizes, size-independent properties: the FFmpeg decoder reproduces the encoder's own
+reconstruction exactly, encodes are deterministic, and a GOP-sharded encode concatenates to the
+unsharded stream."""
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import CASES
+from video_codec_pipeline_b200 import api, arbiter, synth
+from video_codec_pipeline_b200.shard import gop_ranges
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "h264_golden.json")))
+
+
+def _flat(planes):
+    return np.concatenate([pl.ravel() for pl in planes])
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%dx%d_n%d_g%d_s%d_d%d_q%d" % c)
+def test_cuda_equals_oracle(built, case):
+    from oracle import pyoracle
+    w, h, n, gop, sl, idc, qp = case
+    clip = synth.make_clip(w, h, n, seed=1000 + w + qp)
+    ref = pyoracle.encode(pyoracle.make_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc),
+                          clip, want_dump=True)
+    p = api.default_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc, debug=1)
+    with api.Session(p, n) as s:
+        s.upload(clip)
+        s.encode()
+        got = s.download(want_recon=True)
+        dbg = s.debug_mbs()
+    for k in ("mv_prepass", "mv_final", "mb_type", "cbp"):        # K2a, K2b, mbinfo, K3
+        assert np.array_equal(dbg[k], ref["dump"][k]), k
+    assert np.array_equal(got["recon"], ref["recon"])             # K3 + K4
+    assert got["stream"].tobytes() == ref["stream"]               # K5 + NAL packing
+    assert [x[1] for x in got["info"]] == [x[1] for x in ref["info"]]
+
+
+@pytest.mark.parametrize("g", GOLD, ids=lambda g: "%dx%d_q%d_s%d" % (g["w"], g["h"], g["qp"], g["slices"]))
+def test_cuda_matches_golden(built, g):
+    clip = synth.make_clip(g["w"], g["h"], g["frames"], seed=g["seed"])
+    p = api.default_params(g["w"], g["h"], gop=g["gop"], qp_i=max(0, g["qp"] - 2), qp_p=g["qp"],
+                           slices=g["slices"], deblock_idc=g["deblock_idc"])
+    got = api.encode_frames(p, clip, want_recon=True)             # host buffers in, host buffers out
+    assert [x[1] for x in got["info"]] == g["frame_sizes"]
+    assert hashlib.sha256(got["stream"].tobytes()).hexdigest() == g["stream_sha256"]
+    assert hashlib.sha256(got["recon"].tobytes()).hexdigest() == g["recon_sha256"]
+
+
+@pytest.mark.parametrize("w,h,n,gop,sl", [(1920, 1080, 24, 8, 1), (1920, 1080, 12, 6, 4), (3840, 2160, 6, 3, 1)])
+def test_full_size_decoder_reproduces_recon(built, w, h, n, gop, sl):
+    if not arbiter.available():
+        pytest.skip("bundled FFmpeg decoder not present")
+    clip = synth.make_clip(w, h, n, seed=w)
+    p = api.default_params(w, h, gop=gop, qp_i=25, qp_p=27, slices=sl, debug=1)
+    got = api.encode_frames(p, clip, want_recon=True)
+    dec = arbiter.decode_annexb(got["stream"].tobytes(), threads=8)
+    assert len(dec) == n
+    for i in range(n):
+        assert np.array_equal(_flat(dec[i]), got["recon"][i]), "frame %d" % i
+    y = synth.split_planes(clip[n - 1], w, h)[0]
+    assert arbiter.psnr(dec[n - 1][0], y) > 30
+    # determinism: same input, same bytes
+    again = api.encode_frames(p, clip)
+    assert again["stream"].tobytes() == got["stream"].tobytes()
+    # GOP sharding: encode the ranges separately (as 2 and 3 GPUs would) and concatenate
+    for world in (2, 3):
+        parts = []
+        for f0, cnt, g0 in gop_ranges(n, gop, world):
+            if cnt:
+                q = api.default_params(w, h, gop=gop, qp_i=25, qp_p=27, slices=sl, first_gop=g0)
+                parts.append(api.encode_frames(q, clip[f0:f0 + cnt])["stream"].tobytes())
+        assert b"".join(parts) == got["stream"].tobytes()
+
+
+def test_edge_cases(built):
+    from oracle import pyoracle
+    # smallest picture, one frame; GOP 1; one slice per macroblock row; ragged last GOP
+    for (w, h, n, kw) in ((16, 16, 1, dict(gop=60)), (64, 64, 3, dict(gop=1)), (64, 64, 5, dict(gop=2, slices=4)),
+                          (48, 80, 7, dict(gop=3, slices=5, deblock_idc=2))):
+        clip = synth.make_clip(max(w, 32), max(h, 32), n, seed=3)[:, : ]
+        if (w, h) == (16, 16):
+            clip = np.random.default_rng(0).integers(0, 256, (n, 16 * 16 * 3 // 2), dtype=np.uint8)
+        else:
+            clip = synth.make_clip(w, h, n, seed=3)
+        ref = pyoracle.encode(pyoracle.make_params(w, h, qp_i=22, qp_p=24, **kw), clip)
+        got = api.encode_frames(api.default_params(w, h, qp_i=22, qp_p=24, **kw), clip, want_recon=True)
+        assert got["stream"].tobytes() == ref["stream"], (w, h, kw)
+        assert np.array_equal(got["recon"], ref["recon"])
+    # static content collapses to P_Skip and still matches
+    still = np.repeat(synth.make_clip(128, 96, 1, seed=8), 6, axis=0)
+    ref = pyoracle.encode(pyoracle.make_params(128, 96, gop=60, qp_i=26, qp_p=28), still)
+    got = api.encode_frames(api.default_params(128, 96, gop=60, qp_i=26, qp_p=28), still)
+    assert got["stream"].tobytes() == ref["stream"]
+    # extreme content: white noise at the lowest and highest QP
+    noise = np.random.default_rng(1).integers(0, 256, (3, 64 * 64 * 3 // 2), dtype=np.uint8)
+    for qp in (0, 51):
+        ref = pyoracle.encode(pyoracle.make_params(64, 64, gop=60, qp_i=qp, qp_p=qp), noise)
+        got = api.encode_frames(api.default_params(64, 64, gop=60, qp_i=qp, qp_p=qp), noise)
+        assert got["stream"].tobytes() == ref["stream"], qp
+    # invalid parameters surface as error classes, not crashes
+    with pytest.raises(api.VcpencError) as e:
+        api.encode_frames(api.default_params(64, 64, gop=0), noise)
+    assert e.value.code == 1
+    with pytest.raises(api.VcpencError) as e:
+        api.encode_frames(api.default_params(64, 64, entropy=1), noise)
+    assert e.value.code == 1
+
+
+def test_transcode_drop_in(built, tmp_path):
+    """The call the consumer makes: path in, path out, the reference's preset string, --verify."""
+    w, h, n = 640, 360, 20
+    clip = synth.make_clip(w, h, n, seed=77)
+    y4m = tmp_path / "in.y4m"
+    with open(y4m, "wb") as f:
+        f.write(b"YUV4MPEG2 W%d H%d F30:1 Ip A1:1 C420jpeg\n" % (w, h))
+        for fr in clip:
+            f.write(b"FRAME\n" + fr.tobytes())
+    out = tmp_path / "out.mp4"
+    out.write_bytes(b"stale")                                     # -y: overwritten
+    api.transcode(str(y4m), str(out), "-c:v libx264 -preset medium -crf 23 -c:a aac -b:a 128k -movflags +faststart -g 8")
+    api.verify(str(out))
+    data = out.read_bytes()
+    assert data.find(b"moov") < data.find(b"mdat")
+    if arbiter.available():
+        assert arbiter.probe_has_video(str(out))
+        dec = arbiter.decode_file(str(out))
+        assert len(dec) == n
+        assert arbiter.psnr(dec[5][0], synth.split_planes(clip[5], w, h)[0]) > 32
+    # argv door: exactly the reference's command line (cmd/consumer.go:376-380)
+    libdir = os.path.dirname(api.LIB_PATH)
+    out2 = tmp_path / "out2.mp4"
+    r = subprocess.run([os.path.join(libdir, "vcp-ffmpeg"), "-hide_banner", "-loglevel", "warning", "-y", "-i", str(y4m)] +
+                       "-c:v h264_nvenc -preset p4 -qp 28 -c:a aac -b:a 128k -movflags +faststart".split() + [str(out2)],
+                       capture_output=True)
+    assert r.returncode == 0, r.stderr
+    pr = subprocess.run([os.path.join(libdir, "vcp-ffprobe"), "-v", "error", "-select_streams", "v:0", "-show_entries",
+                         "stream=codec_type", "-of", "csv=p=0", str(out2)], capture_output=True)
+    assert pr.returncode == 0 and b"video" in pr.stdout
+    # failure semantics: unknown container -> error class, no output left behind
+    bad = tmp_path / "in.mkv"
+    bad.write_bytes(b"\x1a\x45\xdf\xa3junk")
+    out3 = tmp_path / "out3.mp4"
+    with pytest.raises(api.VcpencError) as e:
+        api.transcode(str(bad), str(out3), "-c:v libx264 -crf 23")
+    assert e.value.code == 3 and not out3.exists()
+    with pytest.raises(api.VcpencError) as e:
+        api.transcode(str(y4m), str(out3), "-c copy")
+    assert e.value.code == 8
+    # cancellation flag (replaces exec.CommandContext's SIGKILL)
+    import ctypes
+    flag = ctypes.c_int(1)
+    with pytest.raises(api.VcpencError) as e:
+        api.transcode(str(y4m), str(out3), "-c:v libx264 -crf 23", cancel=flag)
+    assert e.value.code == 6 and not out3.exists()

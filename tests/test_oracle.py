@@ -1,0 +1,165 @@
+"""The CPU oracle is pinned by the arbiter the north-star names: the FFmpeg h264 decoder must
+decode the oracle's stream to exactly the oracle's reconstruction.  Plus hand-checkable
+known answers and the committed golden hashes."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CASES
+from oracle import pyoracle
+from video_codec_pipeline_b200 import arbiter, synth
+
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "h264_golden.json")))
+
+
+def _lib():
+    return pyoracle.lib()
+
+
+def test_exp_golomb_known_answers():
+    L = _lib()
+    buf = (C.c_uint8 * 8)()
+    # ue: 0->'1', 1->'010', 2->'011', 3->'00100', 7->'0001000'
+    for k, bits in ((0, "1"), (1, "010"), (2, "011"), (3, "00100"), (7, "0001000"), (14, "0001111")):
+        n = L.orc_ue_bits(k, buf)
+        assert n == len(bits)
+        got = "".join(format(b, "08b") for b in bytes(buf))[:n]
+        assert got == bits
+    # se: 0->'1', 1->'010', -1->'011', 2->'00100', -2->'00101'
+    for v, bits in ((0, "1"), (1, "010"), (-1, "011"), (2, "00100"), (-2, "00101")):
+        n = L.orc_se_bits(v, buf)
+        got = "".join(format(b, "08b") for b in bytes(buf))[:n]
+        assert got == bits
+
+
+def test_transform_roundtrip_identity():
+    """Forward core transform, then scaling equivalent to an ideal quantiser, then the decoder's
+    inverse must give back the residual (Cf / Ci are inverses up to the known per-position norms)."""
+    L = _lib()
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        d = rng.integers(-255, 256, 16).astype(np.int32)
+        w = np.zeros(16, np.int32)
+        L.orc_fdct4(d.ctypes.data_as(C.POINTER(C.c_int)), w.ctypes.data_as(C.POINTER(C.c_int)))
+        # norms: class 0 -> 1/16, class 1 -> 1/25, class 2 -> 1/20 ; inverse expects coefficients * 64
+        cls = np.array([0, 2, 0, 2, 2, 1, 2, 1, 0, 2, 0, 2, 2, 1, 2, 1])
+        scale = np.array([64 / 16.0, 64 / 25.0, 64 / 20.0])[cls]
+        c = np.round(w * scale * 16).astype(np.int64)  # keep 4 extra bits of precision
+        c = (c // 16).astype(np.int32)
+        r = np.zeros(16, np.int32)
+        L.orc_idct4(c.ctypes.data_as(C.POINTER(C.c_int)), r.ctypes.data_as(C.POINTER(C.c_int)))
+        assert np.abs(r - d).max() <= 1
+
+
+def test_dc_only_block():
+    L = _lib()
+    d = np.full(16, 10, np.int32)
+    w = np.zeros(16, np.int32)
+    L.orc_fdct4(d.ctypes.data_as(C.POINTER(C.c_int)), w.ctypes.data_as(C.POINTER(C.c_int)))
+    assert w[0] == 160 and not w[1:].any()
+
+
+def test_quant_dequant_tables():
+    L = _lib()
+    # QP 28 -> qp%6 = 4, qbits = 19: level = (|w| * 8192 + f) >> 19 for position (0,0)
+    w = np.zeros(16, np.int32)
+    w[0] = 6400
+    lv = np.zeros(16, np.int16)
+    L.orc_quant4x4(w.ctypes.data_as(C.POINTER(C.c_int)), 28, 0, 0, lv.ctypes.data)
+    assert lv[0] == (6400 * 8192 + (1 << 19) // 6) >> 19
+    c = np.zeros(16, np.int32)
+    L.orc_dequant4x4(lv.ctypes.data, 28, 0, c.ctypes.data_as(C.POINTER(C.c_int)))
+    assert c[0] == lv[0] * 16 << 4
+    assert L.orc_lambda(12) == 1 and L.orc_lambda(24) == 4 and L.orc_lambda(36) == 16
+
+
+def _bits(buf, n):
+    return "".join(format(b, "08b") for b in bytes(buf))[:n]
+
+
+def test_cavlc_block_known_answers():
+    """Worked example of the standard's CAVLC description (widely reproduced): block
+    0,3,-1,0 / 0,-1,1,0 / 1,0,0,0 / 0,0,0,0 in scan order [0,3,0,1,-1,-1,0,1,0...], nC=0
+    -> 000010001110010111101101."""
+    L = _lib()
+    out = (C.c_uint8 * 64)()
+    c = np.array([0, 3, 0, 1, -1, -1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0], np.int16)
+    n = L.orc_cavlc_block(c.ctypes.data, 16, 0, out, 64)
+    assert _bits(out, n) == "000010001110010111101101"
+    # all-zero block, nC=0 -> coeff_token '1'
+    z = np.zeros(16, np.int16)
+    n = L.orc_cavlc_block(z.ctypes.data, 16, 0, out, 64)
+    assert _bits(out, n) == "1"
+    # chroma DC, single +1 at position 0: coeff_token(T1=1,TC=1) '1', sign '0', total_zeros(0)='1'
+    c4 = np.array([1, 0, 0, 0], np.int16)
+    n = L.orc_cavlc_block(c4.ctypes.data, 4, -1, out, 64)
+    assert _bits(out, n) == "101"
+
+
+def test_luma_interpolation_flat_and_ramp():
+    L = _lib()
+    plane = np.full((32, 32), 77, np.uint8)
+    for fy in range(4):
+        for fx in range(4):
+            assert L.orc_luma_qpel(plane.ctypes.data, 32, 10, 10, fx, fy) == 77
+    ramp = np.tile((np.arange(32) * 4).astype(np.uint8), (32, 1))
+    assert L.orc_luma_qpel(ramp.ctypes.data, 32, 10, 10, 2, 0) == 42   # half-way between 40 and 44
+    assert L.orc_luma_qpel(ramp.ctypes.data, 32, 10, 10, 1, 0) == 41
+    assert L.orc_luma_qpel(ramp.ctypes.data, 32, 10, 10, 0, 2) == 40
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%dx%d_n%d_g%d_s%d_d%d_q%d" % c)
+def test_oracle_stream_decodes_to_its_own_recon(case):
+    if not arbiter.available():
+        pytest.skip("bundled FFmpeg decoder not present")
+    w, h, n, gop, sl, idc, qp = case
+    clip = synth.make_clip(w, h, n, seed=1000 + w + qp)
+    p = pyoracle.make_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc)
+    r = pyoracle.encode(p, clip)
+    dec = arbiter.decode_annexb(r["stream"])
+    assert len(dec) == n
+    for i in range(n):
+        flat = np.concatenate([pl.ravel() for pl in dec[i]])
+        assert np.array_equal(flat, r["recon"][i]), "frame %d" % i
+    # sanity: it is a real encode, not a passthrough
+    assert len(r["stream"]) < clip.size // 2 or qp <= 12
+    y = synth.split_planes(clip[n - 1], w, h)[0]
+    assert arbiter.psnr(dec[n - 1][0], y) > (18 if qp > 45 else 28)
+
+
+@pytest.mark.parametrize("g", GOLD, ids=lambda g: "%dx%d_q%d_s%d" % (g["w"], g["h"], g["qp"], g["slices"]))
+def test_oracle_matches_golden(g):
+    clip = synth.make_clip(g["w"], g["h"], g["frames"], seed=g["seed"])
+    assert hashlib.sha256(clip.tobytes()).hexdigest() == g["clip_sha256"], "synthetic clip generator drifted"
+    p = pyoracle.make_params(g["w"], g["h"], gop=g["gop"], qp_i=max(0, g["qp"] - 2), qp_p=g["qp"],
+                             slices=g["slices"], deblock_idc=g["deblock_idc"])
+    r = pyoracle.encode(p, clip)
+    assert [x[1] for x in r["info"]] == g["frame_sizes"]
+    assert hashlib.sha256(r["stream"]).hexdigest() == g["stream_sha256"]
+    assert hashlib.sha256(r["recon"].tobytes()).hexdigest() == g["recon_sha256"]
+
+
+def test_oracle_edge_cases():
+    # single frame; GOP of 1 (all IDR); max slices = one per macroblock row
+    w, h = 64, 64
+    clip = synth.make_clip(w, h, 3, seed=5)
+    for kw in (dict(gop=1), dict(gop=60, slices=4), dict(gop=2, slices=4, deblock_idc=2)):
+        p = pyoracle.make_params(w, h, qp_i=20, qp_p=22, **kw)
+        r = pyoracle.encode(p, clip)
+        if arbiter.available():
+            dec = arbiter.decode_annexb(r["stream"])
+            assert len(dec) == 3
+            for i in range(3):
+                assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i])
+    # a static clip must be almost entirely P_Skip
+    still = np.repeat(clip[:1], 4, axis=0)
+    r = pyoracle.encode(pyoracle.make_params(w, h, gop=60, qp_i=26, qp_p=28), still, want_dump=True)
+    assert (r["dump"]["mb_type"][1:] == 2).mean() > 0.9
+    # invalid parameters are rejected
+    bad = pyoracle.make_params(w, h, gop=0)
+    with pytest.raises(RuntimeError):
+        pyoracle.encode(bad, clip)

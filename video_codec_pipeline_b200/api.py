@@ -67,6 +67,13 @@ def lib():
                                            vp, cp, sz]
         L.vcpenc_session_create.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(vp), cp, sz]
         L.vcpenc_session_upload.argtypes = [vp, vp, C.c_int, cp, sz]
+        L.vcpenc_session_upload_device.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_float), cp, sz]
+        L.vcpenc_session_launch_count.argtypes = [vp]
+        L.vcpenc_session_launch_count.restype = C.c_uint64
+        L.vcpenc_session_set_first_gop.argtypes = [vp, C.c_int]
+        L.vcpenc_host_alloc.argtypes = [sz]
+        L.vcpenc_host_alloc.restype = vp
+        L.vcpenc_host_free.argtypes = [vp]
         L.vcpenc_session_encode.argtypes = [vp, C.POINTER(C.c_float), cp, sz]
         L.vcpenc_session_download.argtypes = [vp, vp, sz, C.POINTER(sz), vp, vp, cp, sz]
         L.vcpenc_session_profile.argtypes = [vp, C.c_int]
@@ -164,6 +171,16 @@ class Session:
         self._keep = frames
         self._ck(self.L.vcpenc_session_upload(self.h, _ptr(frames), nframes, self.err, 512))
         self.nframes = nframes
+
+    def upload_device(self, dptr: int, nframes: int) -> float:
+        """Raw frames already in HBM (device pointer): runs K1 only; returns its CUDA-event ms."""
+        ms = C.c_float(0)
+        self._ck(self.L.vcpenc_session_upload_device(self.h, dptr, nframes, C.byref(ms), self.err, 512))
+        self.nframes = nframes
+        return ms.value
+
+    def launch_count(self) -> int:
+        return int(self.L.vcpenc_session_launch_count(self.h))
 
     def encode(self) -> float:
         ms = C.c_float(0)

@@ -71,6 +71,7 @@ struct vcpenc_session {
     std::vector<EventPair> events; size_t events_used = 0;
     vcpenc_kernel_stat stats[VCPENC_K_COUNT]{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
 };
 
 namespace {
@@ -102,7 +103,8 @@ int check_params(const vcpenc_params& p, char* err, size_t errlen) {
 
 struct Prof {
     vcpenc_session* s; int kind; size_t idx; bool on;
-    Prof(vcpenc_session* s_, int kind_) : s(s_), kind(kind_), idx(0), on(s_->profile) {
+    Prof(vcpenc_session* s_, int kind_, int nlaunch = 1) : s(s_), kind(kind_), idx(0), on(s_->profile) {
+        s->launches += (uint64_t)nlaunch;
         if (!on) return;
         if (s->events_used == s->events.size()) {
             EventPair ep{};
@@ -237,6 +239,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     TRY(dev_alloc(s, &b.out_index_hi, N * g.slices, err, errlen));
     TRY(dev_alloc(s, &b.frame_bits, N, err, errlen));
     TRY(dev_alloc(s, &b.error_flag, (size_t)1, err, errlen));
+    TRY(dev_alloc(s, &b.db_sync, G * g.mbh + 1, err, errlen));
     if (pp->debug) {
         TRY(dev_alloc(s, &s->dbg_mv, N * nmb, err, errlen));
         TRY(dev_alloc(s, &s->dbg_type, N * nmb, err, errlen));
@@ -292,6 +295,30 @@ int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes,
     return VCPENC_OK;
 }
 
+int vcpenc_session_upload_device(vcpenc_session* s, const uint8_t* dframes, int nframes, float* ms, char* err, size_t errlen) {
+    if (!s || !dframes || nframes < 1 || nframes > s->max_frames) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
+    CK(cudaSetDevice(s->device));
+    const size_t fb = frame_bytes_of(s->p);
+    s->nframes = nframes;
+    s->encoded = false;
+    s->h_qp.resize(nframes);
+    for (int n = 0; n < nframes; n++) s->h_qp[n] = (uint8_t)((n % s->p.gop) == 0 ? s->p.qp_i : s->p.qp_p);
+    CK(cudaMemcpyAsync(s->b.qp, s->h_qp.data(), nframes, cudaMemcpyHostToDevice, s->st));
+    CK(cudaEventRecord(s->ev0, s->st));
+    for (int n0 = 0; n0 < nframes; n0 += 4096) {
+        Prof pr(s, VCPENC_K_CSC);
+        vcp_launch_k1_yuv420p(dframes + (size_t)n0 * fb, fb, n0, std::min(4096, nframes - n0), s->g, s->b, s->st);
+    }
+    CK(cudaEventRecord(s->ev1, s->st));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s->st));
+    if (ms) CK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+    if (s->profile) collect_profile(s);
+    return VCPENC_OK;
+}
+
+uint64_t vcpenc_session_launch_count(vcpenc_session* s) { return s ? s->launches : 0; }
+
 static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
     const VcpGeom& g = s->g;
     const VcpBufs& b = s->b;
@@ -318,8 +345,8 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
         }
         { Prof pr(s, VCPENC_K_CAVLC_COUNT); vcp_launch_cavlc_count(g, b, sp, s->st); }
         { Prof pr(s, VCPENC_K_CAVLC_SCAN); vcp_launch_cavlc_scan(g, b, sp, s->st); }
-        { Prof pr(s, VCPENC_K_CAVLC_WRITE); vcp_launch_cavlc_write(g, b, sp, s->st); vcp_launch_nal_pack(g, b, sp, s->st); }
-        { Prof pr(s, VCPENC_K_DEBLOCK); vcp_launch_deblock(g, b, sp, s->st); }
+        { Prof pr(s, VCPENC_K_CAVLC_WRITE, 2); vcp_launch_cavlc_write(g, b, sp, s->st); vcp_launch_nal_pack(g, b, sp, s->st); }
+        if (g.deblock_idc != 1) { Prof pr(s, VCPENC_K_DEBLOCK); vcp_launch_deblock(g, b, sp, s->st); }
         { Prof pr(s, VCPENC_K_PAD); vcp_launch_pad(g, b, sp, s->st); }
         if (s->p.debug) {
             for (int gi = 0; gi < sp.ngop; gi++) {
@@ -413,6 +440,20 @@ int vcpenc_session_download(vcpenc_session* s, uint8_t* out, size_t out_cap, siz
     }
     return VCPENC_OK;
 }
+
+int vcpenc_session_set_first_gop(vcpenc_session* s, int first_gop) {
+    if (!s || first_gop < 0) return VCPENC_E_ARGS;
+    s->gop_base = first_gop;
+    return VCPENC_OK;
+}
+
+void* vcpenc_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void vcpenc_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int vcpenc_session_profile(vcpenc_session* s, int enable) {
     if (!s) return VCPENC_E_ARGS;

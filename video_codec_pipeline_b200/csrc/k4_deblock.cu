@@ -4,10 +4,10 @@
 //   deblock_kernel: the normative filter order is macroblock raster order with vertical edges
 //                   before horizontal ones, and each macroblock reads samples already filtered
 //                   by its left, top and top-right neighbours.  That is a wavefront with index
-//                   d = mx + 2*my; one CTA walks one picture (or one slice when filtering does
-//                   not cross slice edges), one warp per macroblock of the front, lanes = the 32
-//                   sample rows (16 Y + 8 Cb + 8 Cr) for vertical edges and the 32 sample columns
-//                   for horizontal edges, tile staged in shared memory.
+//                   d = mx + 2*my.  One warp streams along one macroblock row (left neighbour
+//                   stays in shared memory), rows synchronise through progress counters; lanes =
+//                   the 32 sample rows (16 Y + 8 Cb + 8 Cr) for vertical edges and the 32 sample
+//                   columns for horizontal edges.
 //   pad_kernel    : replicates the picture edge into the border so the next frame's motion
 //                   vectors may leave the picture.
 //
@@ -57,7 +57,14 @@ __global__ void __launch_bounds__(128) mbinfo_kernel(VcpGeom g, VcpBufs b, VcpSt
 }
 
 // ---- deblocking --------------------------------------------------------------------------------
-constexpr int DB_WARPS = 16;
+// Row-streaming wavefront.  One warp owns one macroblock row and walks it left to right; the
+// left neighbour is the warp's own previous macroblock (kept in shared memory, no round trip),
+// the top neighbour comes from the warp of the row above through global memory, guarded by a
+// per-row progress counter: row r may filter macroblock x once row r-1 has finished x+1
+// (the top-right macroblock's vertical edge touches the samples our top edge reads).
+// Rows are handed out by an atomic ticket in top-to-bottom order, so every dependency points
+// at a warp that is already running (no deadlock however the hardware orders CTAs).
+constexpr int DB_WARPS = 4;
 
 struct __align__(16) DbTile {
     uint8_t Y[20][24];     // rows y=-4..15 (idx y+4), cols x=-4..15 (idx x+4)
@@ -105,121 +112,175 @@ __device__ __forceinline__ void filt_chroma(uint8_t* pix, int xs, int bS, int al
     }
 }
 
-__device__ void deblock_mb(const VcpGeom& g, const VcpBufs& b, DbTile& T, int slot, int gi, int mx, int my,
-                           bool left_ok, bool top_ok, int qp, int lane) {
-    const size_t base = (size_t)gi * g.nmb;
-    const int mbi = my * g.mbw + mx;
-    uint8_t* Y = b.rec_y + (size_t)slot * g.ysize + g.yoff + (size_t)(16 * my) * g.ys + 16 * mx;
-    uint8_t* U = b.rec_u + (size_t)slot * g.csize + g.coff + (size_t)(8 * my) * g.cs + 8 * mx;
-    uint8_t* V = b.rec_v + (size_t)slot * g.csize + g.coff + (size_t)(8 * my) * g.cs + 8 * mx;
-    // stage tile
-    for (int i = lane; i < 100; i += 32) {
-        const int r = i / 5, c = i % 5;
-        reinterpret_cast<uint32_t*>(&T.Y[r][0])[c] = ld_u32(Y + (ptrdiff_t)(r - 4) * g.ys - 4 + 4 * c);
+// per-macroblock data fetched one iteration ahead (independent of the row above)
+struct DbPrefetch {
+    uint32_t y0, y1;   // luma: lane -> row = lane>>1, words 2*(lane&1), +1
+    uint32_t c;        // chroma: lane -> plane = lane>>4, row = (lane>>1)&7, word lane&1
+    int bs;            // boundary strength of (dir = lane>>4, edge = (lane>>2)&3, seg = lane&3)
+};
+
+__device__ __forceinline__ int db_strength(const VcpGeom& g, const VcpBufs& b, size_t base, int mbi, bool left_ok,
+                                           bool top_ok, int lane) {
+    const int dir = lane >> 4, ed = (lane >> 2) & 3, k = lane & 3;
+    const bool mbedge = ed == 0;
+    if (mbedge && !(dir == 0 ? left_ok : top_ok)) return 0;
+    const size_t po = mbedge ? (dir == 0 ? base + mbi - 1 : base + mbi - g.mbw) : base + mbi;
+    const size_t qo = base + mbi;
+    const int pt = b.mbtype[po], qt = b.mbtype[qo];
+    if (pt == VCP_MB_I16 || qt == VCP_MB_I16) return mbedge ? 4 : 3;
+    int pblk, qblk;
+    if (dir == 0) { pblk = k * 4 + (mbedge ? 3 : ed - 1); qblk = k * 4 + ed; }
+    else { pblk = (mbedge ? 12 : 4 * (ed - 1)) + k; qblk = 4 * ed + k; }
+    if (b.nnz[po * 24 + pblk] || b.nnz[qo * 24 + qblk]) return 2;
+    if (mbedge) {
+        const short2 pm = b.mv[po], qm = b.mv[qo];
+        return (vcp_iabs(pm.x - qm.x) >= 4 || vcp_iabs(pm.y - qm.y) >= 4) ? 1 : 0;
     }
-    for (int i = lane; i < 60; i += 32) {
-        const int pl = i / 30, r = (i % 30) / 3, c = i % 3;
-        reinterpret_cast<uint32_t*>(&T.C[pl][r][0])[c] = ld_u32((pl ? V : U) + (ptrdiff_t)(r - 2) * g.cs - 4 + 4 * c);
-    }
-    // boundary strengths: lane -> dir = lane>>4, edge = (lane>>2)&3, segment = lane&3
-    {
-        const int dir = lane >> 4, ed = (lane >> 2) & 3, k = lane & 3;
-        const bool mbedge = ed == 0;
-        int bS = 0;
-        const bool edge_on = !mbedge || (dir == 0 ? left_ok : top_ok);
-        if (edge_on) {
-            const size_t po = mbedge ? (dir == 0 ? base + mbi - 1 : base + mbi - g.mbw) : base + mbi;
-            const size_t qo = base + mbi;
-            const int pt = b.mbtype[po], qt = b.mbtype[qo];
-            if (pt == VCP_MB_I16 || qt == VCP_MB_I16) bS = mbedge ? 4 : 3;
-            else {
-                int pblk, qblk;
-                if (dir == 0) { pblk = k * 4 + (mbedge ? 3 : ed - 1); qblk = k * 4 + ed; }
-                else { pblk = (mbedge ? 12 : 4 * (ed - 1)) + k; qblk = 4 * ed + k; }
-                if (b.nnz[po * 24 + pblk] || b.nnz[qo * 24 + qblk]) bS = 2;
-                else if (mbedge) {
-                    const short2 pm = b.mv[po], qm = b.mv[qo];
-                    bS = (vcp_iabs(pm.x - qm.x) >= 4 || vcp_iabs(pm.y - qm.y) >= 4) ? 1 : 0;
-                }
-            }
-        }
-        T.bs[dir][ed][k] = (uint8_t)bS;
-    }
-    __syncwarp();
-    const int qpc = vcp_chroma_qp[qp];
-    const int aY = vcp_alpha_tab[qp], bY = vcp_beta_tab[qp], aC = vcp_alpha_tab[qpc], bC = vcp_beta_tab[qpc];
-    // vertical edges: lanes 0-15 luma rows, 16-23 Cb rows, 24-31 Cr rows
-    if (lane < 16) {
-#pragma unroll
-        for (int ed = 0; ed < 4; ed++) {
-            const int bS = T.bs[0][ed][lane >> 2];
-            if (bS) filt_luma(&T.Y[lane + 4][4 + 4 * ed], 1, bS, aY, bY, bS < 4 ? vcp_tc0_tab[qp][bS - 1] : 0);
-        }
-    } else {
-        const int pl = (lane - 16) >> 3, r = lane & 7;
-#pragma unroll
-        for (int ed = 0; ed < 4; ed += 2) {
-            const int bS = T.bs[0][ed][r >> 1];
-            if (bS) filt_chroma(&T.C[pl][r + 2][4 + 2 * ed], 1, bS, aC, bC, bS < 4 ? vcp_tc0_tab[qpc][bS - 1] : 0);
-        }
-    }
-    __syncwarp();
-    // horizontal edges: lanes 0-15 luma columns, 16-23 Cb columns, 24-31 Cr columns
-    if (lane < 16) {
-#pragma unroll
-        for (int ed = 0; ed < 4; ed++) {
-            const int bS = T.bs[1][ed][lane >> 2];
-            if (bS) filt_luma(&T.Y[4 + 4 * ed][lane + 4], 24, bS, aY, bY, bS < 4 ? vcp_tc0_tab[qp][bS - 1] : 0);
-        }
-    } else {
-        const int pl = (lane - 16) >> 3, cx = lane & 7;
-#pragma unroll
-        for (int ed = 0; ed < 4; ed += 2) {
-            const int bS = T.bs[1][ed][cx >> 1];
-            if (bS) filt_chroma(&T.C[pl][2 + 2 * ed][cx + 4], 12, bS, aC, bC, bS < 4 ? vcp_tc0_tab[qpc][bS - 1] : 0);
-        }
-    }
-    __syncwarp();
-    // write back: rows 0..15 all 5 words, rows -3..-1 words 1..4
-    for (int i = lane; i < 16 * 5 + 3 * 4; i += 32) {
-        int r, c;
-        if (i < 80) { r = i / 5; c = i % 5; } else { r = -3 + (i - 80) / 4; c = 1 + (i - 80) % 4; }
-        *reinterpret_cast<uint32_t*>(Y + (ptrdiff_t)r * g.ys - 4 + 4 * c) = reinterpret_cast<const uint32_t*>(&T.Y[r + 4][0])[c];
-    }
-    for (int i = lane; i < 2 * (8 * 3 + 2 * 2); i += 32) {
-        const int pl = i / 28, j = i % 28;
-        int r, c;
-        if (j < 24) { r = j / 3; c = j % 3; } else { r = -2 + (j - 24) / 2; c = 1 + (j - 24) % 2; }
-        *reinterpret_cast<uint32_t*>((pl ? V : U) + (ptrdiff_t)r * g.cs - 4 + 4 * c) =
-            reinterpret_cast<const uint32_t*>(&T.C[pl][r + 2][0])[c];
-    }
-    __syncwarp();
+    return 0;
 }
 
-// grid: x = wavefront domain (1, or slices when deblock_idc == 2), y = GOP
-__global__ void __launch_bounds__(DB_WARPS * 32) deblock_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
+__device__ __forceinline__ DbPrefetch db_prefetch(const VcpGeom& g, const VcpBufs& b, const uint8_t* Y, const uint8_t* U,
+                                                  const uint8_t* V, size_t base, int mx, int my, bool top_ok, int lane) {
+    DbPrefetch f;
+    const uint2 yy = *reinterpret_cast<const uint2*>(Y + (size_t)(lane >> 1) * g.ys + 16 * mx + 8 * (lane & 1));
+    f.y0 = yy.x; f.y1 = yy.y;
+    f.c = ld_u32(((lane >> 4) ? V : U) + (size_t)((lane >> 1) & 7) * g.cs + 8 * mx + 4 * (lane & 1));
+    f.bs = db_strength(g, b, base, my * g.mbw + mx, mx > 0, top_ok, lane);
+    return f;
+}
+
+__device__ __forceinline__ uint32_t ldcg_u32(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint32_t*>(p)); }
+
+// grid: x = row groups (claimed by ticket); progress[gop][row] counts finished macroblocks
+__global__ void __launch_bounds__(DB_WARPS * 32) deblock_kernel(VcpGeom g, VcpBufs b, VcpStep s, int* __restrict__ ticket,
+                                                                 int* __restrict__ progress) {
     __shared__ DbTile tiles[DB_WARPS];
+    __shared__ int my_ticket;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gi = blockIdx.y;
+    if (threadIdx.x == 0) my_ticket = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int R = my_ticket * DB_WARPS + warp;          // global row index, frame-major
+    if (R >= s.ngop * g.mbh) return;
+    const int gi = R / g.mbh, my = R % g.mbh;
     const int n = vcp_frame_of(s, gi);
     const int slot = vcp_rec_slot(s, gi, s.t);
     const int qp = b.qp[n];
-    int r0 = 0, r1 = g.mbh;
-    if (g.deblock_idc == 2) {
-        r0 = vcp_slice_first_row(blockIdx.x, g.slices, g.mbh);
-        r1 = (int)blockIdx.x + 1 < g.slices ? vcp_slice_first_row(blockIdx.x + 1, g.slices, g.mbh) : g.mbh;
-    }
-    const int rows = r1 - r0;
-    const int nwave = g.mbw + 2 * (rows - 1);
-    for (int d = 0; d < nwave; d++) {
-        // macroblocks (mx, r0+k) with mx = d - 2k
-        int k0 = (d - (g.mbw - 1) + 1) >> 1; if (k0 < 0) k0 = 0;
-        int k1 = d >> 1; if (k1 > rows - 1) k1 = rows - 1;
-        for (int k = k0 + warp; k <= k1; k += DB_WARPS) {
-            const int mx = d - 2 * k, my = r0 + k;
-            deblock_mb(g, b, tiles[warp], slot, gi, mx, my, mx > 0, my > r0, qp, lane);
+    const int qpc = vcp_chroma_qp[qp];
+    const int aY = vcp_alpha_tab[qp], bY = vcp_beta_tab[qp], aC = vcp_alpha_tab[qpc], bC = vcp_beta_tab[qpc];
+    int tcY[3], tcC[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { tcY[i] = vcp_tc0_tab[qp][i]; tcC[i] = vcp_tc0_tab[qpc][i]; }
+    bool top_ok = my > 0;
+    if (g.deblock_idc == 2) top_ok = my > vcp_slice_first_row(vcp_slice_of_row(my, g.slices, g.mbh), g.slices, g.mbh);
+    const size_t base = (size_t)gi * g.nmb;
+    uint8_t* Y = b.rec_y + (size_t)slot * g.ysize + g.yoff + (size_t)(16 * my) * g.ys;
+    uint8_t* U = b.rec_u + (size_t)slot * g.csize + g.coff + (size_t)(8 * my) * g.cs;
+    uint8_t* V = b.rec_v + (size_t)slot * g.csize + g.coff + (size_t)(8 * my) * g.cs;
+    volatile int* prog_up = progress + (size_t)gi * g.mbh + my - 1;
+    volatile int* prog_me = progress + (size_t)gi * g.mbh + my;
+    DbTile& T = tiles[warp];
+    DbPrefetch f = db_prefetch(g, b, Y, U, V, base, 0, my, top_ok, lane);
+    for (int mx = 0; mx < g.mbw; mx++) {
+        // (1) own samples -> tile
+        {
+            uint32_t* row = reinterpret_cast<uint32_t*>(&T.Y[4 + (lane >> 1)][4 + 8 * (lane & 1)]);
+            row[0] = f.y0; row[1] = f.y1;
+            *reinterpret_cast<uint32_t*>(&T.C[lane >> 4][2 + ((lane >> 1) & 7)][4 + 4 * (lane & 1)]) = f.c;
+            T.bs[lane >> 4][(lane >> 2) & 3][lane & 3] = (uint8_t)f.bs;
         }
-        __syncthreads();
+        const bool any = __any_sync(0xffffffffu, f.bs != 0);
+        const bool top_used = top_ok && __any_sync(0xffffffffu, (lane >> 2) == 4 && f.bs != 0);
+        // prefetch the next macroblock while we wait / filter
+        if (mx + 1 < g.mbw) f = db_prefetch(g, b, Y, U, V, base, mx + 1, my, top_ok, lane);
+        // (2) wait for the row above, (3) fetch its bottom rows
+        if (top_used) {
+            const int need = mx + 2 < g.mbw + 1 ? mx + 2 : g.mbw + 1;
+            if (lane == 0) while (*prog_up < need) __nanosleep(40);
+            __syncwarp();
+            __threadfence();
+            {
+                if (lane < 16) {
+                    *reinterpret_cast<uint32_t*>(&T.Y[lane >> 2][4 + 4 * (lane & 3)]) =
+                        ldcg_u32(Y + (ptrdiff_t)((lane >> 2) - 4) * g.ys + 16 * mx + 4 * (lane & 3));
+                } else if (lane < 24) {
+                    const int pl = (lane - 16) >> 2, r = (lane >> 1) & 1, w = lane & 1;
+                    *reinterpret_cast<uint32_t*>(&T.C[pl][r][4 + 4 * w]) =
+                        ldcg_u32((pl ? V : U) + (ptrdiff_t)(r - 2) * g.cs + 8 * mx + 4 * w);
+                }
+            }
+        }
+        __syncwarp();
+        if (any) {
+            // vertical edges: lanes 0-15 luma rows, 16-23 Cb rows, 24-31 Cr rows
+            if (lane < 16) {
+#pragma unroll
+                for (int ed = 0; ed < 4; ed++) {
+                    const int bS = T.bs[0][ed][lane >> 2];
+                    if (bS) filt_luma(&T.Y[lane + 4][4 + 4 * ed], 1, bS, aY, bY, bS < 4 ? tcY[bS - 1] : 0);
+                }
+            } else {
+                const int pl = (lane - 16) >> 3, r = lane & 7;
+#pragma unroll
+                for (int ed = 0; ed < 4; ed += 2) {
+                    const int bS = T.bs[0][ed][r >> 1];
+                    if (bS) filt_chroma(&T.C[pl][r + 2][4 + 2 * ed], 1, bS, aC, bC, bS < 4 ? tcC[bS - 1] : 0);
+                }
+            }
+            __syncwarp();
+            // horizontal edges: lanes 0-15 luma columns, 16-23 Cb columns, 24-31 Cr columns
+            if (lane < 16) {
+#pragma unroll
+                for (int ed = 0; ed < 4; ed++) {
+                    const int bS = T.bs[1][ed][lane >> 2];
+                    if (bS) filt_luma(&T.Y[4 + 4 * ed][lane + 4], 24, bS, aY, bY, bS < 4 ? tcY[bS - 1] : 0);
+                }
+            } else {
+                const int pl = (lane - 16) >> 3, cx = lane & 7;
+#pragma unroll
+                for (int ed = 0; ed < 4; ed += 2) {
+                    const int bS = T.bs[1][ed][cx >> 1];
+                    if (bS) filt_chroma(&T.C[pl][2 + 2 * ed][cx + 4], 12, bS, aC, bC, bS < 4 ? tcC[bS - 1] : 0);
+                }
+            }
+            __syncwarp();
+        }
+        // (6) write back.  Luma rows 0..15: x=-4..11 now (x=12..15 wait for the next vertical
+        //     edge; on the last macroblock they go out too); top rows -3..-1: x=0..15.
+        const bool last = mx + 1 == g.mbw;
+        {
+            const int r = lane >> 1, h = lane & 1;   // two words per lane + the pending ones
+            uint32_t* dst = reinterpret_cast<uint32_t*>(Y + (size_t)r * g.ys + 16 * mx - 4);
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(&T.Y[r + 4][0]);
+            if (h == 0) { if (mx > 0) dst[0] = src[0]; dst[1] = src[1]; }
+            else { dst[2] = src[2]; dst[3] = src[3]; if (last) dst[4] = src[4]; }
+        }
+        if (top_used && lane < 12) {
+            const int r = lane >> 2, w = lane & 3;
+            *reinterpret_cast<uint32_t*>(Y + (ptrdiff_t)(r - 3) * g.ys + 16 * mx + 4 * w) =
+                *reinterpret_cast<const uint32_t*>(&T.Y[r + 1][4 + 4 * w]);
+        }
+        {
+            // chroma rows 0..7: x=-4..3 now, x=4..7 next time / on the last macroblock
+            const int pl = lane >> 4, r = (lane >> 1) & 7, h = lane & 1;
+            uint32_t* dst = reinterpret_cast<uint32_t*>((pl ? V : U) + (size_t)r * g.cs + 8 * mx - 4);
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(&T.C[pl][r + 2][0]);
+            if (h == 0) { if (mx > 0) dst[0] = src[0]; }
+            else { dst[1] = src[1]; if (last) dst[2] = src[2]; }
+        }
+        if (top_used && lane >= 16 && lane < 24) {
+            const int pl = (lane - 16) >> 2, r = (lane >> 1) & 1, w = lane & 1;
+            *reinterpret_cast<uint32_t*>((pl ? V : U) + (ptrdiff_t)(r - 2) * g.cs + 8 * mx + 4 * w) =
+                *reinterpret_cast<const uint32_t*>(&T.C[pl][r][4 + 4 * w]);
+        }
+        __syncwarp();
+        // (7) the right-most columns become the next macroblock's left neighbour
+        if (lane < 16) *reinterpret_cast<uint32_t*>(&T.Y[lane + 4][0]) = *reinterpret_cast<const uint32_t*>(&T.Y[lane + 4][16]);
+        else *reinterpret_cast<uint32_t*>(&T.C[(lane - 16) >> 3][2 + (lane & 7)][0]) =
+                 *reinterpret_cast<const uint32_t*>(&T.C[(lane - 16) >> 3][2 + (lane & 7)][8]);
+        // (8) publish progress
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) *prog_me = last ? g.mbw + 1 : mx + 1;
     }
 }
 
@@ -272,8 +333,10 @@ void vcp_launch_mbinfo(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cud
 
 void vcp_launch_deblock(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
     if (g.deblock_idc == 1) return;
-    dim3 grid(g.deblock_idc == 2 ? g.slices : 1, s.ngop);
-    deblock_kernel<<<grid, DB_WARPS * 32, 0, st>>>(g, b, s);
+    // sync words: [0] ticket, [1..] per-row progress
+    const int rows = s.ngop * g.mbh;
+    cudaMemsetAsync(b.db_sync, 0, (size_t)(rows + 1) * sizeof(int), st);
+    deblock_kernel<<<(rows + DB_WARPS - 1) / DB_WARPS, DB_WARPS * 32, 0, st>>>(g, b, s, b.db_sync, b.db_sync + 1);
 }
 
 void vcp_launch_pad(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {

@@ -1,0 +1,220 @@
+// vcpenc_transcode — the drop-in for runFFmpegWithTimeout
+// (/root/reference/cmd/consumer.go:370-394): input path, output path, whitespace-split option
+// tokens, a timeout and a cancel flag in; a complete output file (MP4, or raw .h264) or an
+// error class out.  Semantics kept from the reference:
+//   * `-y`: an existing output is overwritten (:376)
+//   * nil error <=> the file is complete on return (:386,393)
+//   * deadline  -> "编码超时", parent cancel -> "任务被取消" (:387-392)
+//   * on failure the caller removes the partial output (:264); we also do not leave one
+//   * stdout/stderr are inherited: progress lines go to stderr in key=value form
+// Frames are pulled in chunks of whole GOPs, pushed through the device session (K1..K5) and
+// the resulting access units are appended to the muxer; no frame ever takes a CPU encode path.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "host_bits.h"
+#include "host_util.h"
+
+using namespace vcp;
+
+namespace {
+
+struct FrameSource {
+    virtual ~FrameSource() {}
+    int width = 0, height = 0, fps_num = 0, fps_den = 1;
+    // read up to `max` frames (tight yuv420p) into dst; returns frames read, <0 on error
+    virtual int read(uint8_t* dst, int max, char* err, size_t errlen) = 0;
+};
+
+size_t fbytes(int w, int h) { return (size_t)w * h + 2 * (size_t)((w + 1) / 2) * ((h + 1) / 2); }
+
+struct Y4mSource : FrameSource {
+    FILE* f = nullptr;
+    ~Y4mSource() override { if (f) fclose(f); }
+    int open(const char* path, char* err, size_t errlen) {
+        f = fopen(path, "rb");
+        if (!f) { set_err(err, errlen, "cannot open %s", path); return VCPENC_E_IO; }
+        char line[512];
+        if (!fgets(line, sizeof line, f) || strncmp(line, "YUV4MPEG2", 9)) { set_err(err, errlen, "not a YUV4MPEG2 stream"); return VCPENC_E_FORMAT; }
+        fps_num = 25; fps_den = 1;
+        std::string cs = "420";
+        for (char* t = strtok(line + 9, " \n"); t; t = strtok(nullptr, " \n")) {
+            if (t[0] == 'W') width = atoi(t + 1);
+            else if (t[0] == 'H') height = atoi(t + 1);
+            else if (t[0] == 'F') { if (sscanf(t + 1, "%d:%d", &fps_num, &fps_den) != 2) { fps_num = 25; fps_den = 1; } }
+            else if (t[0] == 'C') cs = t + 1;
+            else if (t[0] == 'I' && t[1] != 'p' && t[1] != '?') { set_err(err, errlen, "interlaced y4m not supported"); return VCPENC_E_FORMAT; }
+        }
+        if (cs.compare(0, 3, "420") != 0 || cs.find("p10") != std::string::npos || cs.find("p12") != std::string::npos) {
+            set_err(err, errlen, "y4m colourspace C%s not supported (8-bit 4:2:0 only)", cs.c_str());
+            return VCPENC_E_FORMAT;
+        }
+        if (width <= 0 || height <= 0) { set_err(err, errlen, "bad y4m header"); return VCPENC_E_FORMAT; }
+        return VCPENC_OK;
+    }
+    int read(uint8_t* dst, int max, char* err, size_t errlen) override {
+        const size_t fb = fbytes(width, height);
+        int n = 0;
+        while (n < max) {
+            char line[128];
+            if (!fgets(line, sizeof line, f)) break;
+            if (strncmp(line, "FRAME", 5)) { set_err(err, errlen, "y4m: missing FRAME marker"); return -VCPENC_E_FORMAT; }
+            if (fread(dst + (size_t)n * fb, 1, fb, f) != fb) { set_err(err, errlen, "y4m: truncated frame"); return -VCPENC_E_FORMAT; }
+            n++;
+        }
+        return n;
+    }
+};
+
+struct RawSource : FrameSource {
+    FILE* f = nullptr;
+    ~RawSource() override { if (f) fclose(f); }
+    int open(const char* path, const vcpenc_params& p, char* err, size_t errlen) {
+        if (p.in_width <= 0 || p.in_height <= 0) { set_err(err, errlen, "raw .yuv input needs -s WxH"); return VCPENC_E_FORMAT; }
+        width = p.in_width; height = p.in_height; fps_num = p.fps_num; fps_den = p.fps_den;
+        f = fopen(path, "rb");
+        if (!f) { set_err(err, errlen, "cannot open %s", path); return VCPENC_E_IO; }
+        return VCPENC_OK;
+    }
+    int read(uint8_t* dst, int max, char*, size_t) override {
+        const size_t fb = fbytes(width, height);
+        int n = 0;
+        while (n < max && fread(dst + (size_t)n * fb, 1, fb, f) == fb) n++;
+        return n;
+    }
+};
+
+bool ends_with(const std::string& s, const char* suf) {
+    const size_t n = strlen(suf);
+    if (s.size() < n) return false;
+    for (size_t i = 0; i < n; i++)
+        if (tolower((unsigned char)s[s.size() - n + i]) != suf[i]) return false;
+    return true;
+}
+
+struct PinnedBuf {
+    uint8_t* p = nullptr;
+    ~PinnedBuf() { if (p) vcpenc_host_free(p); }
+};
+
+}  // namespace
+
+extern "C" int vcpenc_transcode(const char* input, const char* output, int argc, const char* const* argv,
+                                int timeout_ms, volatile int* cancel, char* err, size_t errlen) {
+    using clock = std::chrono::steady_clock;
+    const auto t0 = clock::now();
+    if (!input || !output) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
+    vcpenc_params p;
+    int rc = vcpenc_parse_args(argc, argv, &p, err, errlen);
+    if (rc) return rc;
+    if (vcpenc_device_count() <= 0) { set_err(err, errlen, "no CUDA device available (libvcpenc has no CPU fallback)"); return VCPENC_E_NODEVICE; }
+
+    const std::string in = input, outp = output;
+    std::unique_ptr<FrameSource> src;
+    if (ends_with(in, ".y4m")) {
+        auto s = std::make_unique<Y4mSource>();
+        rc = s->open(input, err, errlen);
+        if (rc) return rc;
+        src = std::move(s);
+    } else if (ends_with(in, ".yuv")) {
+        auto s = std::make_unique<RawSource>();
+        rc = s->open(input, p, err, errlen);
+        if (rc) return rc;
+        src = std::move(s);
+    } else {
+        set_err(err, errlen, "input container of '%s' needs the demux/decode front end, which is not built yet (SURVEY 8f1); y4m and raw yuv420p are accepted", input);
+        return VCPENC_E_FORMAT;
+    }
+    p.width = src->width; p.height = src->height;
+    p.in_width = p.in_height = 0;
+    p.fps_num = src->fps_num; p.fps_den = src->fps_den;
+    if ((p.width & 1) || (p.height & 1) || p.width < 16 || p.height < 16) { set_err(err, errlen, "unsupported picture size %dx%d", p.width, p.height); return VCPENC_E_FORMAT; }
+    if (p.slices > (p.height + 15) / 16) p.slices = (p.height + 15) / 16;
+
+    const size_t fb = fbytes(p.width, p.height);
+    // chunk: whole GOPs, at most ~3 GiB of raw frames resident per pass
+    int chunk = (int)std::max<size_t>(1, ((size_t)3 << 30) / fb);
+    chunk = std::max(p.gop, chunk / p.gop * p.gop);
+    PinnedBuf frames;
+    frames.p = (uint8_t*)vcpenc_host_alloc((size_t)chunk * fb);
+    if (!frames.p) { set_err(err, errlen, "cannot allocate %zu bytes of pinned host memory", (size_t)chunk * fb); return VCPENC_E_CUDA; }
+
+    vcpenc_session* ses = nullptr;
+    std::vector<uint8_t> bits((size_t)chunk * fb / 2 + (1 << 20));
+    std::vector<vcpenc_frame_info> info((size_t)chunk);
+    std::vector<uint8_t> mdat, annexb_all, sps, pps;
+    std::vector<Mp4Sample> samples;
+    const bool raw_out = ends_with(outp, ".h264") || ends_with(outp, ".264");
+    long total = 0;
+    int gop_index = 0;
+    auto fail = [&](int code) { if (ses) vcpenc_session_destroy(ses); remove(output); return code; };
+    for (;;) {
+        if (cancel && *cancel) { set_err(err, errlen, "任务被取消"); return fail(VCPENC_E_CANCELLED); }
+        if (timeout_ms > 0 && std::chrono::duration_cast<std::chrono::milliseconds>(clock::now() - t0).count() > timeout_ms) {
+            set_err(err, errlen, "编码超时 (>%dms)", timeout_ms);
+            return fail(VCPENC_E_TIMEOUT);
+        }
+        const int n = src->read(frames.p, chunk, err, errlen);
+        if (n < 0) return fail(-n);
+        if (n == 0) break;
+        if (!ses) {
+            p.first_gop = 0;
+            rc = vcpenc_session_create(&p, 0, std::min(chunk, std::max(n, 1)), &ses, err, errlen);
+            if (rc) return fail(rc);
+        }
+        // idr_pic_id parity continues across chunks
+        vcpenc_session_set_first_gop(ses, gop_index);
+        rc = vcpenc_session_upload(ses, frames.p, n, err, errlen);
+        if (!rc) rc = vcpenc_session_encode(ses, nullptr, err, errlen);
+        size_t len = 0;
+        if (!rc) {
+            rc = vcpenc_session_download(ses, bits.data(), bits.size(), &len, info.data(), nullptr, err, errlen);
+            if (rc == VCPENC_E_OVERFLOW) {
+                bits.resize((size_t)chunk * fb + (1 << 20));
+                rc = vcpenc_session_download(ses, bits.data(), bits.size(), &len, info.data(), nullptr, err, errlen);
+            }
+        }
+        if (rc) return fail(rc);
+        if (raw_out) annexb_all.insert(annexb_all.end(), bits.begin(), bits.begin() + len);
+        else {
+            for (int i = 0; i < n; i++) {
+                Mp4Sample s{mdat.size(), 0, info[i].is_idr != 0};
+                for (const auto& nal : split_annexb(bits.data() + info[i].offset, info[i].size)) {
+                    if (!nal.n) continue;
+                    const int t = nal.p[0] & 31;
+                    if (t == 7) { if (sps.empty()) sps.assign(nal.p, nal.p + nal.n); continue; }
+                    if (t == 8) { if (pps.empty()) pps.assign(nal.p, nal.p + nal.n); continue; }
+                    const uint32_t k = (uint32_t)nal.n;
+                    const uint8_t h[4] = {(uint8_t)(k >> 24), (uint8_t)(k >> 16), (uint8_t)(k >> 8), (uint8_t)k};
+                    mdat.insert(mdat.end(), h, h + 4);
+                    mdat.insert(mdat.end(), nal.p, nal.p + nal.n);
+                }
+                s.size = (uint32_t)(mdat.size() - s.offset);
+                samples.push_back(s);
+            }
+        }
+        total += n;
+        gop_index += (n + p.gop - 1) / p.gop;
+        if (n < chunk) break;
+    }
+    if (ses) vcpenc_session_destroy(ses);
+    ses = nullptr;
+    if (total == 0) { set_err(err, errlen, "input has no frames"); remove(output); return VCPENC_E_FORMAT; }
+    if (raw_out) {
+        FILE* f = fopen(output, "wb");
+        if (!f) { set_err(err, errlen, "cannot create %s", output); return VCPENC_E_IO; }
+        const bool ok = fwrite(annexb_all.data(), 1, annexb_all.size(), f) == annexb_all.size();
+        if (fclose(f) != 0 || !ok) { set_err(err, errlen, "short write to %s", output); remove(output); return VCPENC_E_IO; }
+    } else {
+        rc = write_mp4(p, sps, pps, samples, mdat.data(), mdat.size(), output, err, errlen);
+        if (rc) { remove(output); return rc; }
+    }
+    const double sec = std::chrono::duration<double>(clock::now() - t0).count();
+    fprintf(stderr, "[vcpenc] frames=%ld size=%dx%d fps=%.1f elapsed=%.3fs output=%s\n", total, p.width, p.height,
+            sec > 0 ? total / sec : 0.0, sec, output);
+    return VCPENC_OK;
+}

@@ -79,6 +79,7 @@ struct VcpBufs {
     uint32_t* out_index_hi;
     uint32_t* frame_bits;  // [nframes] coded bits per frame (for rate control)
     int* error_flag;
+    int* db_sync;          // deblocking: [0] row ticket, [1 + gop*mbh + row] progress
     size_t rbsp_cap;
     size_t out_cap;
 };
