@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -55,6 +56,11 @@ struct vcpenc_session {
     int max_frames = 0, nframes = 0, ngop_max = 0, ring = 2;
     int gop_base = 0;  // clip-level index of the first resident GOP
     cudaStream_t st = nullptr, st_copy = nullptr;
+    static constexpr int kMaxGroups = 8;
+    cudaStream_t gst[kMaxGroups] = {};          // one stream per GOP group
+    cudaEvent_t gev[kMaxGroups] = {};
+    cudaEvent_t ev_pre = nullptr;
+    int ngroups = 4;
     std::vector<void*> allocs;
     uint8_t* staging[2] = {nullptr, nullptr};
     cudaEvent_t staging_free[2] = {nullptr, nullptr}, staging_ready[2] = {nullptr, nullptr};
@@ -103,7 +109,9 @@ int check_params(const vcpenc_params& p, char* err, size_t errlen) {
 
 struct Prof {
     vcpenc_session* s; int kind; size_t idx; bool on;
-    Prof(vcpenc_session* s_, int kind_, int nlaunch = 1) : s(s_), kind(kind_), idx(0), on(s_->profile) {
+    cudaStream_t stream;
+    Prof(vcpenc_session* s_, int kind_, int nlaunch = 1, cudaStream_t st_ = nullptr)
+        : s(s_), kind(kind_), idx(0), on(s_->profile), stream(st_ ? st_ : s_->st) {
         s->launches += (uint64_t)nlaunch;
         if (!on) return;
         if (s->events_used == s->events.size()) {
@@ -113,9 +121,9 @@ struct Prof {
         }
         idx = s->events_used++;
         s->events[idx].kind = kind;
-        cudaEventRecord(s->events[idx].a, s->st);
+        cudaEventRecord(s->events[idx].a, stream);
     }
-    ~Prof() { if (on) cudaEventRecord(s->events[idx].b, s->st); }
+    ~Prof() { if (on) cudaEventRecord(s->events[idx].b, stream); }
 };
 
 void collect_profile(vcpenc_session* s) {
@@ -168,6 +176,11 @@ void vcpenc_session_destroy(vcpenc_session* s) {
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->h_out) cudaFreeHost(s->h_out);
+    for (int i = 0; i < vcpenc_session::kMaxGroups; i++) {
+        if (s->gst[i]) cudaStreamDestroy(s->gst[i]);
+        if (s->gev[i]) cudaEventDestroy(s->gev[i]);
+    }
+    if (s->ev_pre) cudaEventDestroy(s->ev_pre);
     if (s->st) cudaStreamDestroy(s->st);
     if (s->st_copy) cudaStreamDestroy(s->st_copy);
     delete s;
@@ -206,6 +219,16 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     CKS(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
     CKS(cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking));
     CKS(cudaEventCreate(&s->ev0)); CKS(cudaEventCreate(&s->ev1));
+    CKS(cudaEventCreateWithFlags(&s->ev_pre, cudaEventDisableTiming));
+    {
+        const char* e = getenv("VCPENC_STREAMS");
+        int ng = e ? atoi(e) : 4;
+        s->ngroups = std::max(1, std::min(ng, (int)vcpenc_session::kMaxGroups));
+    }
+    for (int i = 0; i < s->ngroups; i++) {
+        CKS(cudaStreamCreateWithFlags(&s->gst[i], cudaStreamNonBlocking));
+        CKS(cudaEventCreateWithFlags(&s->gev[i], cudaEventDisableTiming));
+    }
     VcpBufs& b = s->b;
     const size_t N = max_frames, G = s->ngop_max, nmb = g.nmb;
     TRY(dev_alloc(s, &b.src_y, N * g.ysize, err, errlen));
@@ -239,7 +262,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     TRY(dev_alloc(s, &b.out_index_hi, N * g.slices, err, errlen));
     TRY(dev_alloc(s, &b.frame_bits, N, err, errlen));
     TRY(dev_alloc(s, &b.error_flag, (size_t)1, err, errlen));
-    TRY(dev_alloc(s, &b.db_sync, G * g.mbh + 1, err, errlen));
+    TRY(dev_alloc(s, &b.db_sync, G * (g.mbh + 1) + 1, err, errlen));
     if (pp->debug) {
         TRY(dev_alloc(s, &s->dbg_mv, N * nmb, err, errlen));
         TRY(dev_alloc(s, &s->dbg_type, N * nmb, err, errlen));
@@ -323,6 +346,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
     const VcpGeom& g = s->g;
     const VcpBufs& b = s->b;
     const int N = s->nframes, gop = s->p.gop;
+    const int ngop_total = (N + gop - 1) / gop;
     CK(cudaMemsetAsync(b.out_cursor, 0, sizeof(unsigned long long), s->st));
     CK(cudaMemsetAsync(b.error_flag, 0, sizeof(int), s->st));
     CK(cudaMemsetAsync(b.frame_bits, 0, (size_t)N * sizeof(uint32_t), s->st));
@@ -330,33 +354,51 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
         Prof pr(s, VCPENC_K_ME_PRE);
         vcp_launch_me_prepass(g, b, N, gop, s->st);
     }
+    // GOP groups advance on their own streams: the latency-bound wavefront kernels (intra
+    // recon, deblocking) of one group overlap the throughput-bound kernels of the others.
+    // Per-kernel profiling wants clean timings, so it runs everything on one stream.
+    const int ng = s->profile ? 1 : std::max(1, std::min(s->ngroups, ngop_total));
+    CK(cudaEventRecord(s->ev_pre, s->st));
+    for (int k = 0; k < ng; k++) CK(cudaStreamWaitEvent(s->gst[k], s->ev_pre, 0));
     for (int t = 0; t < gop && t < N; t++) {
-        VcpStep sp;
-        sp.t = t; sp.gop = gop; sp.ring = s->ring; sp.nframes = N; sp.gop0 = s->gop_base;
-        sp.ngop = (N - t + gop - 1) / gop;
-        if (sp.ngop <= 0) break;
-        if (t == 0) {
-            Prof pr(s, VCPENC_K_I_RECON);
-            vcp_launch_i_recon(g, b, sp, s->st);
-        } else {
-            { Prof pr(s, VCPENC_K_ME_REFINE); vcp_launch_me_refine(g, b, sp, s->st); }
-            { Prof pr(s, VCPENC_K_P_RECON); vcp_launch_p_recon(g, b, sp, s->st); }
-            { Prof pr(s, VCPENC_K_MBINFO); vcp_launch_mbinfo(g, b, sp, s->st); }
-        }
-        { Prof pr(s, VCPENC_K_CAVLC_COUNT); vcp_launch_cavlc_count(g, b, sp, s->st); }
-        { Prof pr(s, VCPENC_K_CAVLC_SCAN); vcp_launch_cavlc_scan(g, b, sp, s->st); }
-        { Prof pr(s, VCPENC_K_CAVLC_WRITE, 2); vcp_launch_cavlc_write(g, b, sp, s->st); vcp_launch_nal_pack(g, b, sp, s->st); }
-        if (g.deblock_idc != 1) { Prof pr(s, VCPENC_K_DEBLOCK); vcp_launch_deblock(g, b, sp, s->st); }
-        { Prof pr(s, VCPENC_K_PAD); vcp_launch_pad(g, b, sp, s->st); }
-        if (s->p.debug) {
-            for (int gi = 0; gi < sp.ngop; gi++) {
-                const size_t n = (size_t)gi * gop + t;
-                CK(cudaMemcpyAsync(s->dbg_mv + n * g.nmb, b.mv + (size_t)gi * g.nmb, g.nmb * sizeof(short2), cudaMemcpyDeviceToDevice, s->st));
-                CK(cudaMemcpyAsync(s->dbg_type + n * g.nmb, b.mbtype + (size_t)gi * g.nmb, g.nmb, cudaMemcpyDeviceToDevice, s->st));
-                CK(cudaMemcpyAsync(s->dbg_cbp + n * g.nmb, b.cbp + (size_t)gi * g.nmb, g.nmb, cudaMemcpyDeviceToDevice, s->st));
+        for (int k = 0; k < ng; k++) {
+            cudaStream_t st = s->profile ? s->st : s->gst[k];
+            VcpStep sp;
+            sp.t = t; sp.gop = gop; sp.ring = s->ring; sp.nframes = N; sp.gop0 = s->gop_base;
+            // GOPs of this group that own a frame at position t
+            const int gA = (int)((long long)ngop_total * k / ng), gB = (int)((long long)ngop_total * (k + 1) / ng);
+            const int active = (N - t + gop - 1) / gop;      // GOPs (from 0) that have frame t
+            sp.g0 = gA;
+            sp.ngop = std::min(gB, active) - gA;
+            if (sp.ngop <= 0) continue;
+            if (t == 0) {
+                Prof pr(s, VCPENC_K_I_RECON, 1, st);
+                vcp_launch_i_recon(g, b, sp, st);
+            } else {
+                { Prof pr(s, VCPENC_K_ME_REFINE, 1, st); vcp_launch_me_refine(g, b, sp, st); }
+                { Prof pr(s, VCPENC_K_P_RECON, 1, st); vcp_launch_p_recon(g, b, sp, st); }
+                { Prof pr(s, VCPENC_K_MBINFO, 1, st); vcp_launch_mbinfo(g, b, sp, st); }
+            }
+            { Prof pr(s, VCPENC_K_CAVLC_COUNT, 1, st); vcp_launch_cavlc_count(g, b, sp, st); }
+            { Prof pr(s, VCPENC_K_CAVLC_SCAN, 1, st); vcp_launch_cavlc_scan(g, b, sp, st); }
+            { Prof pr(s, VCPENC_K_CAVLC_WRITE, 2, st); vcp_launch_cavlc_write(g, b, sp, st); vcp_launch_nal_pack(g, b, sp, st); }
+            if (g.deblock_idc != 1) { Prof pr(s, VCPENC_K_DEBLOCK, 1, st); vcp_launch_deblock(g, b, sp, st); }
+            { Prof pr(s, VCPENC_K_PAD, 1, st); vcp_launch_pad(g, b, sp, st); }
+            if (s->p.debug) {
+                for (int gi = gA; gi < gA + sp.ngop; gi++) {
+                    const size_t n = (size_t)gi * gop + t;
+                    CK(cudaMemcpyAsync(s->dbg_mv + n * g.nmb, b.mv + (size_t)gi * g.nmb, g.nmb * sizeof(short2), cudaMemcpyDeviceToDevice, st));
+                    CK(cudaMemcpyAsync(s->dbg_type + n * g.nmb, b.mbtype + (size_t)gi * g.nmb, g.nmb, cudaMemcpyDeviceToDevice, st));
+                    CK(cudaMemcpyAsync(s->dbg_cbp + n * g.nmb, b.cbp + (size_t)gi * g.nmb, g.nmb, cudaMemcpyDeviceToDevice, st));
+                }
             }
         }
     }
+    if (!s->profile)
+        for (int k = 0; k < ng; k++) {
+            CK(cudaEventRecord(s->gev[k], s->gst[k]));
+            CK(cudaStreamWaitEvent(s->st, s->gev[k], 0));
+        }
     CK(cudaGetLastError());
     return VCPENC_OK;
 }

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
     __shared__ LumaPlanes planes[RF_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mbi = blockIdx.x * RF_WARPS + warp;
-    const int gi = blockIdx.y;
+    const int gi = blockIdx.y + s.g0;
     if (mbi >= g.nmb) return;
     const int n = vcp_frame_of(s, gi);
     const int mx = mbi % g.mbw, my = mbi / g.mbw;

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32) p_recon_kernel(VcpGeom g, VcpBu
     __shared__ uint8_t cpred[PR_WARPS][2][8][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mbi = blockIdx.x * PR_WARPS + warp;
-    const int gi = blockIdx.y;
+    const int gi = blockIdx.y + s.g0;
     if (mbi >= g.nmb) return;
     const int n = vcp_frame_of(s, gi);
     const int slot = vcp_rec_slot(s, gi, s.t), rslot = vcp_rec_slot(s, gi, s.t - 1);
@@ -380,7 +380,7 @@ __device__ void i16_encode_mb(const VcpGeom& g, const VcpBufs& b, IScratch& S, i
 __global__ void __launch_bounds__(IR_WARPS * 32) i_recon_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
     __shared__ IScratch scr[IR_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sl = blockIdx.x, gi = blockIdx.y;
+    const int sl = blockIdx.x, gi = blockIdx.y + s.g0;
     const int n = vcp_frame_of(s, gi);
     const int slot = vcp_rec_slot(s, gi, s.t);
     const int qp = b.qp[n];

@@ -23,7 +23,7 @@ namespace {
 // ---- mbinfo ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) mbinfo_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
     const int mbi = blockIdx.x * blockDim.x + threadIdx.x;
-    const int gi = blockIdx.y;
+    const int gi = blockIdx.y + s.g0;
     if (mbi >= g.nmb) return;
     const size_t base = (size_t)gi * g.nmb;
     const int mx = mbi % g.mbw, my = mbi / g.mbw;
@@ -64,7 +64,6 @@ __global__ void __launch_bounds__(128) mbinfo_kernel(VcpGeom g, VcpBufs b, VcpSt
 // (the top-right macroblock's vertical edge touches the samples our top edge reads).
 // Rows are handed out by an atomic ticket in top-to-bottom order, so every dependency points
 // at a warp that is already running (no deadlock however the hardware orders CTAs).
-constexpr int DB_WARPS = 4;
 
 struct __align__(16) DbTile {
     uint8_t Y[20][24];     // rows y=-4..15 (idx y+4), cols x=-4..15 (idx x+4)
@@ -72,183 +71,326 @@ struct __align__(16) DbTile {
     uint8_t bs[2][4][4];   // [dir][edge][segment]
 };
 
-__device__ __forceinline__ void filt_luma(uint8_t* pix, int xs, int bS, int alpha, int beta, int tc0) {
-    const int p0 = pix[-xs], p1 = pix[-2 * xs], p2 = pix[-3 * xs], q0 = pix[0], q1 = pix[xs], q2 = pix[2 * xs];
+// One luma line across an edge, in registers: v[0..7] = p3 p2 p1 p0 q0 q1 q2 q3.
+__device__ __forceinline__ void filt_luma_reg(int* v, int bS, int alpha, int beta, int tc0) {
+    const int p3 = v[0], p2 = v[1], p1 = v[2], p0 = v[3], q0 = v[4], q1 = v[5], q2 = v[6], q3 = v[7];
     if (vcp_iabs(p0 - q0) >= alpha || vcp_iabs(p1 - p0) >= beta || vcp_iabs(q1 - q0) >= beta) return;
     const int ap = vcp_iabs(p2 - p0), aq = vcp_iabs(q2 - q0);
     if (bS < 4) {
         const int tc = tc0 + (ap < beta) + (aq < beta);
         const int d = vcp_clip3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
-        pix[-xs] = (uint8_t)vcp_clip255(p0 + d);
-        pix[0] = (uint8_t)vcp_clip255(q0 - d);
-        if (ap < beta) pix[-2 * xs] = (uint8_t)(p1 + vcp_clip3(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - 2 * p1) >> 1));
-        if (aq < beta) pix[xs] = (uint8_t)(q1 + vcp_clip3(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - 2 * q1) >> 1));
+        v[3] = vcp_clip255(p0 + d);
+        v[4] = vcp_clip255(q0 - d);
+        if (ap < beta) v[2] = p1 + vcp_clip3(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - 2 * p1) >> 1);
+        if (aq < beta) v[5] = q1 + vcp_clip3(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - 2 * q1) >> 1);
     } else {
-        const int p3 = pix[-4 * xs], q3 = pix[3 * xs];
         const bool small = vcp_iabs(p0 - q0) < ((alpha >> 2) + 2);
         if (ap < beta && small) {
-            pix[-xs] = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
-            pix[-2 * xs] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
-            pix[-3 * xs] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
-        } else pix[-xs] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+            v[3] = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3;
+            v[2] = (p2 + p1 + p0 + q0 + 2) >> 2;
+            v[1] = (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3;
+        } else v[3] = (2 * p1 + p0 + q1 + 2) >> 2;
         if (aq < beta && small) {
-            pix[0] = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
-            pix[xs] = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
-            pix[2 * xs] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
-        } else pix[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+            v[4] = (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3;
+            v[5] = (p0 + q0 + q1 + q2 + 2) >> 2;
+            v[6] = (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3;
+        } else v[4] = (2 * q1 + q0 + p1 + 2) >> 2;
     }
 }
-__device__ __forceinline__ void filt_chroma(uint8_t* pix, int xs, int bS, int alpha, int beta, int tc0) {
-    const int p0 = pix[-xs], p1 = pix[-2 * xs], q0 = pix[0], q1 = pix[xs];
+// chroma: v[0..3] = p1 p0 q0 q1
+__device__ __forceinline__ void filt_chroma_reg(int* v, int bS, int alpha, int beta, int tc0) {
+    const int p1 = v[0], p0 = v[1], q0 = v[2], q1 = v[3];
     if (vcp_iabs(p0 - q0) >= alpha || vcp_iabs(p1 - p0) >= beta || vcp_iabs(q1 - q0) >= beta) return;
     if (bS < 4) {
         const int tc = tc0 + 1;
         const int d = vcp_clip3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
-        pix[-xs] = (uint8_t)vcp_clip255(p0 + d);
-        pix[0] = (uint8_t)vcp_clip255(q0 - d);
+        v[1] = vcp_clip255(p0 + d);
+        v[2] = vcp_clip255(q0 - d);
     } else {
-        pix[-xs] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
-        pix[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+        v[1] = (2 * p1 + p0 + q1 + 2) >> 2;
+        v[2] = (2 * q1 + q0 + p1 + 2) >> 2;
     }
 }
 
-// per-macroblock data fetched one iteration ahead (independent of the row above)
+// Everything one macroblock needs that does not depend on the row above, fetched one iteration
+// ahead as INDEPENDENT loads (a warp executes in order: a dependent chain would stall it).
 struct DbPrefetch {
     uint32_t y0, y1;   // luma: lane -> row = lane>>1, words 2*(lane&1), +1
     uint32_t c;        // chroma: lane -> plane = lane>>4, row = (lane>>1)&7, word lane&1
-    int bs;            // boundary strength of (dir = lane>>4, edge = (lane>>2)&3, seg = lane&3)
+    uint8_t pt, qt, pn, qn;   // types and nnz of the two 4x4 blocks across this lane's edge segment
+    short2 pm, qm;
 };
 
-__device__ __forceinline__ int db_strength(const VcpGeom& g, const VcpBufs& b, size_t base, int mbi, bool left_ok,
-                                           bool top_ok, int lane) {
+// per-lane addresses of the first macroblock of the row; advancing by one macroblock is a
+// constant stride, so the loop body carries no address arithmetic
+struct DbLaneAddr {
+    const uint8_t* y;     // luma: row lane>>1, 8 bytes at 8*(lane&1)
+    const uint8_t* c;     // chroma: plane lane>>4, row (lane>>1)&7, 4 bytes at 4*(lane&1)
+    const uint8_t* qt;    // mbtype of the current macroblock
+    const uint8_t* qn;    // nnz of the q-side block
+    const short2* qm;     // mv of the current macroblock
+    int p_mb_off;         // macroblock offset of the p side (0, -1 or -mbw)
+    int pn_off;           // nnz byte offset of the p-side block relative to qn
+    bool needs_left;      // the edge exists only when mx > 0
+    bool off;             // edge never filtered (top edge at a picture / slice boundary)
+};
+
+__device__ __forceinline__ DbLaneAddr db_lane_addr(const VcpGeom& g, const VcpBufs& b, const uint8_t* Y, const uint8_t* U,
+                                                   const uint8_t* V, size_t base, int my, bool top_ok, int lane) {
+    DbLaneAddr a;
+    a.y = Y + (size_t)(lane >> 1) * g.ys + 8 * (lane & 1);
+    a.c = ((lane >> 4) ? V : U) + (size_t)((lane >> 1) & 7) * g.cs + 4 * (lane & 1);
     const int dir = lane >> 4, ed = (lane >> 2) & 3, k = lane & 3;
     const bool mbedge = ed == 0;
-    if (mbedge && !(dir == 0 ? left_ok : top_ok)) return 0;
-    const size_t po = mbedge ? (dir == 0 ? base + mbi - 1 : base + mbi - g.mbw) : base + mbi;
-    const size_t qo = base + mbi;
-    const int pt = b.mbtype[po], qt = b.mbtype[qo];
-    if (pt == VCP_MB_I16 || qt == VCP_MB_I16) return mbedge ? 4 : 3;
     int pblk, qblk;
     if (dir == 0) { pblk = k * 4 + (mbedge ? 3 : ed - 1); qblk = k * 4 + ed; }
     else { pblk = (mbedge ? 12 : 4 * (ed - 1)) + k; qblk = 4 * ed + k; }
-    if (b.nnz[po * 24 + pblk] || b.nnz[qo * 24 + qblk]) return 2;
-    if (mbedge) {
-        const short2 pm = b.mv[po], qm = b.mv[qo];
-        return (vcp_iabs(pm.x - qm.x) >= 4 || vcp_iabs(pm.y - qm.y) >= 4) ? 1 : 0;
-    }
-    return 0;
+    const size_t qo = base + (size_t)my * g.mbw;
+    a.qt = b.mbtype + qo;
+    a.qn = b.nnz + qo * 24 + qblk;
+    a.qm = b.mv + qo;
+    a.needs_left = mbedge && dir == 0;
+    a.off = mbedge && dir == 1 && !top_ok;
+    a.p_mb_off = !mbedge || a.off ? 0 : (dir == 0 ? -1 : -g.mbw);
+    a.pn_off = a.p_mb_off * 24 + pblk - qblk;
+    return a;
 }
 
-__device__ __forceinline__ DbPrefetch db_prefetch(const VcpGeom& g, const VcpBufs& b, const uint8_t* Y, const uint8_t* U,
-                                                  const uint8_t* V, size_t base, int mx, int my, bool top_ok, int lane) {
+__device__ __forceinline__ DbPrefetch db_prefetch(const DbLaneAddr& a, int mx) {
     DbPrefetch f;
-    const uint2 yy = *reinterpret_cast<const uint2*>(Y + (size_t)(lane >> 1) * g.ys + 16 * mx + 8 * (lane & 1));
+    const uint2 yy = *reinterpret_cast<const uint2*>(a.y + 16 * mx);
     f.y0 = yy.x; f.y1 = yy.y;
-    f.c = ld_u32(((lane >> 4) ? V : U) + (size_t)((lane >> 1) & 7) * g.cs + 8 * mx + 4 * (lane & 1));
-    f.bs = db_strength(g, b, base, my * g.mbw + mx, mx > 0, top_ok, lane);
+    f.c = ld_u32(a.c + 8 * mx);
+    const bool dead = a.off || (a.needs_left && mx == 0);
+    const int po = dead ? 0 : a.p_mb_off;
+    f.qt = a.qt[mx]; f.pt = a.qt[mx + po];
+    f.qn = a.qn[24 * mx]; f.pn = a.qn[24 * mx + (dead ? 0 : a.pn_off)];
+    f.qm = a.qm[mx]; f.pm = a.qm[mx + po];
+    if (dead) f.pt = 0xff;   // marks "edge not filtered"
     return f;
 }
 
-__device__ __forceinline__ uint32_t ldcg_u32(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint32_t*>(p)); }
+__device__ __forceinline__ int db_strength(const DbPrefetch& f, int lane) {
+    const bool mbedge = ((lane >> 2) & 3) == 0;
+    if (f.pt == 0xff) return 0;
+    if (f.pt == VCP_MB_I16 || f.qt == VCP_MB_I16) return mbedge ? 4 : 3;
+    if (f.pn || f.qn) return 2;
+    if (mbedge && (vcp_iabs(f.pm.x - f.qm.x) >= 4 || vcp_iabs(f.pm.y - f.qm.y) >= 4)) return 1;
+    return 0;
+}
 
-// grid: x = row groups (claimed by ticket); progress[gop][row] counts finished macroblocks
-__global__ void __launch_bounds__(DB_WARPS * 32) deblock_kernel(VcpGeom g, VcpBufs b, VcpStep s, int* __restrict__ ticket,
-                                                                 int* __restrict__ progress) {
-    __shared__ DbTile tiles[DB_WARPS];
+// Inter-row hand-off.  __threadfence() is MEMBAR.SC.GPU + CCTL.IVALL on sm_100a (sequentially
+// consistent fence plus a full L1 invalidate, by every lane); the row-to-row link only needs
+// release/acquire at gpu scope, issued by ONE lane after a warp barrier (bar.warp.sync orders the
+// other lanes' stores before it), and the consumer reads the published samples with ld.cg (L2).
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(int* p, int v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t ldcg_u32(const uint8_t* p) { return __ldcg(reinterpret_cast<const uint32_t*>(p)); }
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
+    return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
+}
+
+// One CTA = one band of up to 16 consecutive macroblock rows of one picture (one warp per row).
+//   * rows inside a band hand their bottom samples to the row below through a small ring in
+//     SHARED memory guarded by cta-scope flags (no gpu-scope fence, ~100 cycles per hand-off);
+//   * only the first row of a band reads the previous band's samples from HBM (ld.cg) behind a
+//     gpu-scope progress counter, which the last row of a band publishes every DB_PUB macroblocks.
+// Bands are handed out by an atomic ticket in top-to-bottom order, so every dependency points at
+// a CTA that is already running.
+constexpr int DB_RING = 4;      // ring slots per row
+constexpr int DB_SLOT = 96;     // 4 luma rows x 16 + 2 planes x 2 chroma rows x 8
+constexpr int DB_PUB = 4;       // gpu-scope publish interval of a band's last row
+
+struct DbShared {
+    DbTile* tiles;                // [BH]
+    uint8_t* ring;                // [BH][DB_RING][DB_SLOT]
+    volatile int* done;           // [BH] macroblocks complete (samples final, written, stashed)
+    volatile int* taken;          // [BH] ring slots the row has finished reading from the row above
+};
+
+__global__ void __launch_bounds__(512) deblock_kernel(VcpGeom g, VcpBufs b, VcpStep s, int BH, int nbands,
+                                                        int* __restrict__ ticket, int* __restrict__ progress) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int my_ticket;
+    DbShared sh;
+    sh.tiles = reinterpret_cast<DbTile*>(smem_raw);
+    sh.ring = smem_raw + (size_t)BH * sizeof(DbTile);
+    sh.done = reinterpret_cast<volatile int*>(sh.ring + (size_t)BH * DB_RING * DB_SLOT);
+    sh.taken = sh.done + BH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) my_ticket = atomicAdd(ticket, 1);
+    if (threadIdx.x < 2 * BH) sh.done[threadIdx.x] = 0;   // done[] and taken[] are contiguous
     __syncthreads();
-    const int R = my_ticket * DB_WARPS + warp;          // global row index, frame-major
-    if (R >= s.ngop * g.mbh) return;
-    const int gi = R / g.mbh, my = R % g.mbh;
+    const int gi = s.g0 + my_ticket / nbands, band = my_ticket % nbands;
+    const int my = band * BH + warp;
+    if (my >= g.mbh || my_ticket >= s.ngop * nbands) return;
     const int n = vcp_frame_of(s, gi);
     const int slot = vcp_rec_slot(s, gi, s.t);
     const int qp = b.qp[n];
     const int qpc = vcp_chroma_qp[qp];
-    const int aY = vcp_alpha_tab[qp], bY = vcp_beta_tab[qp], aC = vcp_alpha_tab[qpc], bC = vcp_beta_tab[qpc];
-    int tcY[3], tcC[3];
+    const bool lum = lane < 16;
+    const int alpha = lum ? vcp_alpha_tab[qp] : vcp_alpha_tab[qpc], beta = lum ? vcp_beta_tab[qp] : vcp_beta_tab[qpc];
+    int tc[3];
 #pragma unroll
-    for (int i = 0; i < 3; i++) { tcY[i] = vcp_tc0_tab[qp][i]; tcC[i] = vcp_tc0_tab[qpc][i]; }
+    for (int i = 0; i < 3; i++) tc[i] = lum ? vcp_tc0_tab[qp][i] : vcp_tc0_tab[qpc][i];
     bool top_ok = my > 0;
     if (g.deblock_idc == 2) top_ok = my > vcp_slice_first_row(vcp_slice_of_row(my, g.slices, g.mbh), g.slices, g.mbh);
+    const bool top_smem = warp > 0;                                   // row above is in this CTA
+    const bool has_below = my + 1 < g.mbh;
+    const bool below_smem = has_below && warp + 1 < BH;               // consumer is in this CTA
+    const bool below_gmem = has_below && !below_smem;                 // consumer is the next band
     const size_t base = (size_t)gi * g.nmb;
     uint8_t* Y = b.rec_y + (size_t)slot * g.ysize + g.yoff + (size_t)(16 * my) * g.ys;
     uint8_t* U = b.rec_u + (size_t)slot * g.csize + g.coff + (size_t)(8 * my) * g.cs;
     uint8_t* V = b.rec_v + (size_t)slot * g.csize + g.coff + (size_t)(8 * my) * g.cs;
-    volatile int* prog_up = progress + (size_t)gi * g.mbh + my - 1;
-    volatile int* prog_me = progress + (size_t)gi * g.mbh + my;
-    DbTile& T = tiles[warp];
-    DbPrefetch f = db_prefetch(g, b, Y, U, V, base, 0, my, top_ok, lane);
+    const int* prog_up = progress + (size_t)gi * g.mbh + my - 1;
+    int* prog_me = progress + (size_t)gi * g.mbh + my;
+    DbTile& T = sh.tiles[warp];
+    uint8_t* ring_me = sh.ring + (size_t)warp * DB_RING * DB_SLOT;          // what I hand down
+    const uint8_t* ring_up = sh.ring + (size_t)(warp - 1) * DB_RING * DB_SLOT;  // what I receive
+    const DbLaneAddr la = db_lane_addr(g, b, Y, U, V, base, my, top_ok, lane);
+    DbPrefetch f = db_prefetch(la, 0);
+    int seen_up = 0;
     for (int mx = 0; mx < g.mbw; mx++) {
-        // (1) own samples -> tile
+        // (1) own samples and boundary strengths -> tile
+        const int mybs = db_strength(f, lane);
         {
             uint32_t* row = reinterpret_cast<uint32_t*>(&T.Y[4 + (lane >> 1)][4 + 8 * (lane & 1)]);
             row[0] = f.y0; row[1] = f.y1;
             *reinterpret_cast<uint32_t*>(&T.C[lane >> 4][2 + ((lane >> 1) & 7)][4 + 4 * (lane & 1)]) = f.c;
-            T.bs[lane >> 4][(lane >> 2) & 3][lane & 3] = (uint8_t)f.bs;
+            T.bs[lane >> 4][(lane >> 2) & 3][lane & 3] = (uint8_t)mybs;
         }
-        const bool any = __any_sync(0xffffffffu, f.bs != 0);
-        const bool top_used = top_ok && __any_sync(0xffffffffu, (lane >> 2) == 4 && f.bs != 0);
-        // prefetch the next macroblock while we wait / filter
-        if (mx + 1 < g.mbw) f = db_prefetch(g, b, Y, U, V, base, mx + 1, my, top_ok, lane);
-        // (2) wait for the row above, (3) fetch its bottom rows
+        const uint32_t nzmask = __ballot_sync(0xffffffffu, mybs != 0);
+        const bool top_used = (nzmask & 0x000f0000u) != 0;
+        if (mx + 1 < g.mbw) f = db_prefetch(la, mx + 1);
+        // (2) the row above must have finished macroblock mx (incl. the vertical edge of mx+1)
         if (top_used) {
-            const int need = mx + 2 < g.mbw + 1 ? mx + 2 : g.mbw + 1;
-            if (lane == 0) while (*prog_up < need) __nanosleep(40);
-            __syncwarp();
-            __threadfence();
-            {
-                if (lane < 16) {
-                    *reinterpret_cast<uint32_t*>(&T.Y[lane >> 2][4 + 4 * (lane & 3)]) =
-                        ldcg_u32(Y + (ptrdiff_t)((lane >> 2) - 4) * g.ys + 16 * mx + 4 * (lane & 3));
-                } else if (lane < 24) {
-                    const int pl = (lane - 16) >> 2, r = (lane >> 1) & 1, w = lane & 1;
-                    *reinterpret_cast<uint32_t*>(&T.C[pl][r][4 + 4 * w]) =
-                        ldcg_u32((pl ? V : U) + (ptrdiff_t)(r - 2) * g.cs + 8 * mx + 4 * w);
+            const int need = mx + 1;
+            if (seen_up < need) {
+                int v = 0;
+                if (lane == 0) {
+                    if (top_smem) { while ((v = sh.done[warp - 1]) < need) { } __threadfence_block(); }
+                    else { while ((v = ld_relaxed_gpu(prog_up)) < need) __nanosleep(20); fence_acq_rel_gpu(); }
                 }
+                seen_up = __shfl_sync(0xffffffffu, v, 0);
+            }
+            // (3) its bottom rows -> tile top rows
+            if (top_smem) {
+                const uint32_t* sl = reinterpret_cast<const uint32_t*>(ring_up + (mx % DB_RING) * DB_SLOT);
+                if (lane < 16) *reinterpret_cast<uint32_t*>(&T.Y[lane >> 2][4 + 4 * (lane & 3)]) = sl[lane];
+                else if (lane < 24) {
+                    const int pl = (lane - 16) >> 2, r = (lane >> 1) & 1, w = lane & 1;
+                    *reinterpret_cast<uint32_t*>(&T.C[pl][r][4 + 4 * w]) = sl[lane];
+                }
+            } else if (lane < 16) {
+                *reinterpret_cast<uint32_t*>(&T.Y[lane >> 2][4 + 4 * (lane & 3)]) =
+                    ldcg_u32(Y + (ptrdiff_t)((lane >> 2) - 4) * g.ys + 16 * mx + 4 * (lane & 3));
+            } else if (lane < 24) {
+                const int pl = (lane - 16) >> 2, r = (lane >> 1) & 1, w = lane & 1;
+                *reinterpret_cast<uint32_t*>(&T.C[pl][r][4 + 4 * w]) =
+                    ldcg_u32((pl ? V : U) + (ptrdiff_t)(r - 2) * g.cs + 8 * mx + 4 * w);
             }
         }
         __syncwarp();
-        if (any) {
-            // vertical edges: lanes 0-15 luma rows, 16-23 Cb rows, 24-31 Cr rows
-            if (lane < 16) {
+        if (top_smem && lane == 0) sh.taken[warp] = mx + 1;   // slot mx may be recycled by the row above
+        if (nzmask & 0x0000ffffu) {
+            // vertical edges, whole sample row in registers: lanes 0-15 luma rows, 16-31 chroma rows
+            if (lum) {
+                uint32_t* row = reinterpret_cast<uint32_t*>(&T.Y[lane + 4][0]);
+                int v[20];
+#pragma unroll
+                for (int w = 0; w < 5; w++) {
+                    const uint32_t x = row[w];
+                    v[4 * w] = x & 255; v[4 * w + 1] = (x >> 8) & 255; v[4 * w + 2] = (x >> 16) & 255; v[4 * w + 3] = x >> 24;
+                }
 #pragma unroll
                 for (int ed = 0; ed < 4; ed++) {
                     const int bS = T.bs[0][ed][lane >> 2];
-                    if (bS) filt_luma(&T.Y[lane + 4][4 + 4 * ed], 1, bS, aY, bY, bS < 4 ? tcY[bS - 1] : 0);
+                    if (bS) filt_luma_reg(&v[4 * ed], bS, alpha, beta, bS < 4 ? tc[bS - 1] : 0);
                 }
+#pragma unroll
+                for (int w = 0; w < 5; w++) row[w] = pack4(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3]);
             } else {
                 const int pl = (lane - 16) >> 3, r = lane & 7;
+                uint32_t* row = reinterpret_cast<uint32_t*>(&T.C[pl][r + 2][0]);
+                int v[12];
+#pragma unroll
+                for (int w = 0; w < 3; w++) {
+                    const uint32_t x = row[w];
+                    v[4 * w] = x & 255; v[4 * w + 1] = (x >> 8) & 255; v[4 * w + 2] = (x >> 16) & 255; v[4 * w + 3] = x >> 24;
+                }
 #pragma unroll
                 for (int ed = 0; ed < 4; ed += 2) {
                     const int bS = T.bs[0][ed][r >> 1];
-                    if (bS) filt_chroma(&T.C[pl][r + 2][4 + 2 * ed], 1, bS, aC, bC, bS < 4 ? tcC[bS - 1] : 0);
+                    if (bS) filt_chroma_reg(&v[2 + 2 * ed], bS, alpha, beta, bS < 4 ? tc[bS - 1] : 0);
                 }
+#pragma unroll
+                for (int w = 0; w < 3; w++) row[w] = pack4(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3]);
             }
-            __syncwarp();
-            // horizontal edges: lanes 0-15 luma columns, 16-23 Cb columns, 24-31 Cr columns
-            if (lane < 16) {
+        }
+        __syncwarp();
+        if (nzmask & 0xffff0000u) {
+            // horizontal edges, whole sample column in registers: lanes 0-15 luma, 16-31 chroma columns
+            if (lum) {
+                uint8_t* col = &T.Y[0][lane + 4];
+                int v[20];
+#pragma unroll
+                for (int r = 0; r < 20; r++) v[r] = col[24 * r];
 #pragma unroll
                 for (int ed = 0; ed < 4; ed++) {
                     const int bS = T.bs[1][ed][lane >> 2];
-                    if (bS) filt_luma(&T.Y[4 + 4 * ed][lane + 4], 24, bS, aY, bY, bS < 4 ? tcY[bS - 1] : 0);
+                    if (bS) filt_luma_reg(&v[4 * ed], bS, alpha, beta, bS < 4 ? tc[bS - 1] : 0);
                 }
+#pragma unroll
+                for (int r = 1; r < 19; r++) col[24 * r] = (uint8_t)v[r];
             } else {
                 const int pl = (lane - 16) >> 3, cx = lane & 7;
+                uint8_t* col = &T.C[pl][0][cx + 4];
+                int v[10];
+#pragma unroll
+                for (int r = 0; r < 10; r++) v[r] = col[12 * r];
 #pragma unroll
                 for (int ed = 0; ed < 4; ed += 2) {
                     const int bS = T.bs[1][ed][cx >> 1];
-                    if (bS) filt_chroma(&T.C[pl][2 + 2 * ed][cx + 4], 12, bS, aC, bC, bS < 4 ? tcC[bS - 1] : 0);
+                    if (bS) filt_chroma_reg(&v[2 * ed], bS, alpha, beta, bS < 4 ? tc[bS - 1] : 0);
                 }
+#pragma unroll
+                for (int r = 1; r < 9; r++) col[12 * r] = (uint8_t)v[r];
             }
-            __syncwarp();
         }
-        // (6) write back.  Luma rows 0..15: x=-4..11 now (x=12..15 wait for the next vertical
-        //     edge; on the last macroblock they go out too); top rows -3..-1: x=0..15.
+        __syncwarp();
         const bool last = mx + 1 == g.mbw;
+        // (4) hand-down ring: bottom 4 luma / 2 chroma rows.  Words 0..2 of macroblock mx are final
+        //     now; word 3 (x=12..15) of macroblock mx-1 became final with this vertical-edge pass.
+        if (below_smem) {
+            if (mx >= DB_RING && lane == 0) while (sh.taken[warp + 1] < mx - DB_RING + 1) { }
+            __syncwarp();
+            uint32_t* cur = reinterpret_cast<uint32_t*>(ring_me + (mx % DB_RING) * DB_SLOT);
+            uint32_t* prv = reinterpret_cast<uint32_t*>(ring_me + ((mx + DB_RING - 1) % DB_RING) * DB_SLOT);
+            if (lane < 16) {
+                const int r = lane >> 2, w = lane & 3;           // luma row 12+r, word w
+                const uint32_t* trow = reinterpret_cast<const uint32_t*>(&T.Y[16 + r][0]);
+                if (w < 3 || last) cur[lane] = trow[1 + w];
+                if (w == 3 && mx > 0) prv[lane] = trow[0];
+            } else if (lane < 24) {
+                const int pl = (lane - 16) >> 2, r = (lane >> 1) & 1, w = lane & 1;   // chroma row 6+r
+                const uint32_t* trow = reinterpret_cast<const uint32_t*>(&T.C[pl][8 + r][0]);
+                if (w == 0 || last) cur[lane] = trow[1 + w];
+                if (w == 1 && mx > 0) prv[lane] = trow[0];
+            }
+        }
+        // (5) write back.  Luma rows 0..15: x=-4..11 now (x=12..15 wait for the next vertical
+        //     edge; on the last macroblock they go out too); top rows -3..-1: x=0..15.
         {
-            const int r = lane >> 1, h = lane & 1;   // two words per lane + the pending ones
+            const int r = lane >> 1, h = lane & 1;
             uint32_t* dst = reinterpret_cast<uint32_t*>(Y + (size_t)r * g.ys + 16 * mx - 4);
             const uint32_t* src = reinterpret_cast<const uint32_t*>(&T.Y[r + 4][0]);
             if (h == 0) { if (mx > 0) dst[0] = src[0]; dst[1] = src[1]; }
@@ -260,7 +402,6 @@ __global__ void __launch_bounds__(DB_WARPS * 32) deblock_kernel(VcpGeom g, VcpBu
                 *reinterpret_cast<const uint32_t*>(&T.Y[r + 1][4 + 4 * w]);
         }
         {
-            // chroma rows 0..7: x=-4..3 now, x=4..7 next time / on the last macroblock
             const int pl = lane >> 4, r = (lane >> 1) & 7, h = lane & 1;
             uint32_t* dst = reinterpret_cast<uint32_t*>((pl ? V : U) + (size_t)r * g.cs + 8 * mx - 4);
             const uint32_t* src = reinterpret_cast<const uint32_t*>(&T.C[pl][r + 2][0]);
@@ -273,14 +414,19 @@ __global__ void __launch_bounds__(DB_WARPS * 32) deblock_kernel(VcpGeom g, VcpBu
                 *reinterpret_cast<const uint32_t*>(&T.C[pl][r][4 + 4 * w]);
         }
         __syncwarp();
+        // (6) publish: after this iteration's stores, macroblocks 0..mx-1 (all, on the last one) are
+        //     complete.  In-CTA consumers need only cta-scope ordering (their later stores to the
+        //     shared bottom rows must land after ours); the next band needs gpu scope.
+        const int complete = last ? g.mbw : mx;
+        if (below_smem && lane == 0) { __threadfence_block(); sh.done[warp] = complete; }
+        if (below_gmem && lane == 0 && (last || (mx % DB_PUB) == DB_PUB - 1)) {
+            fence_acq_rel_gpu();
+            st_relaxed_gpu(prog_me, complete);
+        }
         // (7) the right-most columns become the next macroblock's left neighbour
-        if (lane < 16) *reinterpret_cast<uint32_t*>(&T.Y[lane + 4][0]) = *reinterpret_cast<const uint32_t*>(&T.Y[lane + 4][16]);
+        if (lum) *reinterpret_cast<uint32_t*>(&T.Y[lane + 4][0]) = *reinterpret_cast<const uint32_t*>(&T.Y[lane + 4][16]);
         else *reinterpret_cast<uint32_t*>(&T.C[(lane - 16) >> 3][2 + (lane & 7)][0]) =
                  *reinterpret_cast<const uint32_t*>(&T.C[(lane - 16) >> 3][2 + (lane & 7)][8]);
-        // (8) publish progress
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) *prog_me = last ? g.mbw + 1 : mx + 1;
     }
 }
 
@@ -314,7 +460,7 @@ __device__ __forceinline__ void pad_plane(uint8_t* p, int stride, int w, int h, 
 }
 
 __global__ void __launch_bounds__(256) pad_kernel(VcpGeom g, VcpBufs b, VcpStep s, int ny, int nc) {
-    const int gi = blockIdx.y;
+    const int gi = blockIdx.y + s.g0;
     const int slot = vcp_rec_slot(s, gi, s.t);
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < ny) { pad_plane<16>(b.rec_y + (size_t)slot * g.ysize + g.yoff, g.ys, g.cw, g.ch, VCP_PAD, idx); return; }
@@ -333,10 +479,16 @@ void vcp_launch_mbinfo(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cud
 
 void vcp_launch_deblock(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
     if (g.deblock_idc == 1) return;
-    // sync words: [0] ticket, [1..] per-row progress
-    const int rows = s.ngop * g.mbh;
-    cudaMemsetAsync(b.db_sync, 0, (size_t)(rows + 1) * sizeof(int), st);
-    deblock_kernel<<<(rows + DB_WARPS - 1) / DB_WARPS, DB_WARPS * 32, 0, st>>>(g, b, s, b.db_sync, b.db_sync + 1);
+    // bands of up to 16 macroblock rows, one CTA each (512 threads: no register cap pressure)
+    const int nbands = (g.mbh + 15) / 16, BH = (g.mbh + nbands - 1) / nbands;
+    const size_t smem = (size_t)BH * (sizeof(DbTile) + DB_RING * DB_SLOT + 2 * sizeof(int));
+    // sync words: [0] ticket, [1..] per-row progress (each GOP group has its own region: groups
+    // run concurrently on different streams)
+    int* sync = b.db_sync + (size_t)s.g0 * (g.mbh + 1);
+    cudaMemsetAsync(sync, 0, (size_t)(s.ngop * g.mbh + 1) * sizeof(int), st);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(deblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr_set = true; }
+    deblock_kernel<<<s.ngop * nbands, BH * 32, smem, st>>>(g, b, s, BH, nbands, sync, sync + 1 - (size_t)s.g0 * g.mbh);
 }
 
 void vcp_launch_pad(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {

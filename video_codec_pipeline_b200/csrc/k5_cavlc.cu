@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(CV_WARPS * 32) cavlc_mb_kernel(VcpGeom g, VcpB
     __shared__ CvScratch scr[CV_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mbi = blockIdx.x * CV_WARPS + warp;
-    const int gi = blockIdx.y;
+    const int gi = blockIdx.y + s.g0;
     if (mbi >= g.nmb) return;
     if (WRITE) {
         int err = lane == 0 ? *b.error_flag : 0;
@@ -325,7 +325,7 @@ constexpr int SCAN_THREADS = 512;
 __global__ void __launch_bounds__(SCAN_THREADS) cavlc_scan_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
     __shared__ uint32_t wsum[33];
     __shared__ int last_nonskip;
-    const int sl = blockIdx.x, gi = blockIdx.y;
+    const int sl = blockIdx.x, gi = blockIdx.y + s.g0;
     const int n = vcp_frame_of(s, gi);
     const bool idr = s.t == 0;
     const int qp = b.qp[n];
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(PACK_THREADS) nal_pack_kernel(VcpGeom g, VcpBu
     __shared__ uint32_t wsum[33];
     __shared__ unsigned long long out_base;
     __shared__ int err_seen;
-    const int sl = blockIdx.x, gi = blockIdx.y;
+    const int sl = blockIdx.x, gi = blockIdx.y + s.g0;
     const int n = vcp_frame_of(s, gi);
     const bool idr = s.t == 0;
     if (threadIdx.x == 0) err_seen = *b.error_flag;

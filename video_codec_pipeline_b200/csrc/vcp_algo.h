@@ -41,19 +41,19 @@
 #define VCP_LV_CHROMA_AC 280    // 2 x 4 blocks x 16 (position 0 unused)
 #define VCP_LV_STRIDE 408       // int16 per macroblock
 
-// bit length of se(v)
-VCP_HD int vcp_se_len(int v) {
-    unsigned k = (v <= 0) ? (unsigned)(-2 * v) : (unsigned)(2 * v - 1);  // codeNum
-    unsigned x = k + 1;
-    int n = 0;
-    while (x > 1) { x >>= 1; n++; }
-    return 2 * n + 1;
-}
+// bit length of ue(k) / se(v): 2*floor(log2(codeNum+1)) + 1
 VCP_HD int vcp_ue_len(unsigned k) {
     unsigned x = k + 1;
+#if defined(__CUDA_ARCH__)
+    return 2 * (31 - __clz((int)x)) + 1;
+#else
     int n = 0;
     while (x > 1) { x >>= 1; n++; }
     return 2 * n + 1;
+#endif
+}
+VCP_HD int vcp_se_len(int v) {
+    return vcp_ue_len((v <= 0) ? (unsigned)(-2 * v) : (unsigned)(2 * v - 1));
 }
 
 // SAD-domain Lagrangian multiplier, ~ 2^((qp-12)/6)

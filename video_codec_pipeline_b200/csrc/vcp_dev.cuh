@@ -45,6 +45,7 @@ struct VcpStep {
     int ring;     // recon slots per GOP
     int nframes;  // total frames resident
     int gop0;     // index of the first resident GOP in the whole clip (idr_pic_id parity)
+    int g0;       // first GOP of the group this launch covers (groups run on separate streams)
 };
 __host__ __device__ __forceinline__ int vcp_frame_of(const VcpStep& s, int g) { return g * s.gop + s.t; }
 __host__ __device__ __forceinline__ int vcp_rec_slot(const VcpStep& s, int g, int t) { return g * s.ring + (t % s.ring); }
