@@ -392,6 +392,7 @@ static void me_refine_mb(Enc* e, const Frame* ref, int mx, int my, int qp, int16
     }
     int bx = 4 * cand[best & 15][0], by = 4 * cand[best & 15][1];
     uint32_t bcost = best >> 4;
+    if (bcost < VCP_SUBPEL_SKIP_COST) { mv[0] = (int16_t)bx; mv[1] = (int16_t)by; return; }
     /* half-pel then quarter-pel: 8 neighbours each, raster order, strict improvement */
     for (int step = 2; step >= 1; step--) {
         uint32_t sb = (bcost << 4) | 0; /* centre keeps priority (index 0) */

@@ -22,24 +22,31 @@
 namespace {
 
 constexpr int ME_WARPS = 8;                       // macroblocks per CTA (one row segment)
-constexpr int L1_WIN_W = ME_WARPS * 8 + 2 * VCP_ME_R1;  // 88
-constexpr int L1_WIN_WA = 96;                     // allocated width (word slack for unaligned reads)
+constexpr int L1_WIN_X0 = 16;                     // window starts 16 px left of the CTA's first block (16 B aligned)
+constexpr int L1_WIN_WA = 112;                    // 16 + 64 + 12 + slack for unaligned 12-byte reads, 7 x 16 B
 constexpr int L1_WIN_H = 8 + 2 * VCP_ME_R1;       // 32
+constexpr int L0_W = 28;                          // 16 + 4 candidates + slack, 7 words
+
+struct __align__(16) PrepassWarp {
+    uint8_t cur[16][16];
+    uint8_t ref[20][L0_W];
+};
 
 __global__ void __launch_bounds__(ME_WARPS * 32) me_prepass_kernel(VcpGeom g, VcpBufs b, int nframes, int gop) {
     __shared__ __align__(16) uint8_t win[L1_WIN_H][L1_WIN_WA];
+    __shared__ PrepassWarp pw[ME_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.z;
     if (n % gop == 0) return;  // IDR: no search
     const int my = blockIdx.y, mx0 = blockIdx.x * ME_WARPS, mx = mx0 + warp;
     const uint8_t* hc = b.src_h + (size_t)n * g.hsize + g.hoff;
     const uint8_t* hp = b.src_h + (size_t)(n - 1) * g.hsize + g.hoff;
-    // stage the shared L1 window: rows 8my-12 .. 8my+19, cols 8mx0-12 .. 8mx0+75 (+ slack)
+    // stage the shared L1 window with 16-byte loads: rows 8my-12 .. 8my+19, cols 8mx0-16 .. 8mx0+95
     {
-        const uint8_t* base = hp + (ptrdiff_t)(8 * my - VCP_ME_R1) * g.hs + (8 * mx0 - VCP_ME_R1);
-        for (int i = threadIdx.x; i < L1_WIN_H * (L1_WIN_WA / 4); i += blockDim.x) {
-            int r = i / (L1_WIN_WA / 4), c = i % (L1_WIN_WA / 4);
-            reinterpret_cast<uint32_t*>(&win[r][0])[c] = ld_u32(base + (ptrdiff_t)r * g.hs + 4 * c);
+        const uint8_t* base = hp + (ptrdiff_t)(8 * my - VCP_ME_R1) * g.hs + (8 * mx0 - L1_WIN_X0);
+        for (int i = threadIdx.x; i < L1_WIN_H * (L1_WIN_WA / 16); i += blockDim.x) {
+            const int r = i / (L1_WIN_WA / 16), c = i % (L1_WIN_WA / 16);
+            reinterpret_cast<uint4*>(&win[r][0])[c] = __ldg(reinterpret_cast<const uint4*>(base + (ptrdiff_t)r * g.hs) + c);
         }
     }
     __syncthreads();
@@ -55,7 +62,7 @@ __global__ void __launch_bounds__(ME_WARPS * 32) me_prepass_kernel(VcpGeom g, Vc
     uint32_t best = 0xffffffffu;
     if (lane < 2 * VCP_ME_R1 + 1) {
         const int dx = lane - VCP_ME_R1;
-        const int col = 8 * warp + lane;  // window column of this lane's candidates
+        const int col = 8 * warp + lane + (L1_WIN_X0 - VCP_ME_R1);  // window column of this lane's candidates
         uint32_t acc[2 * VCP_ME_R1 + 1];
 #pragma unroll
         for (int i = 0; i < 2 * VCP_ME_R1 + 1; i++) acc[i] = 0;
@@ -81,20 +88,43 @@ __global__ void __launch_bounds__(ME_WARPS * 32) me_prepass_kernel(VcpGeom g, Vc
     const int bi = (int)(best & 0xffff), W = 2 * VCP_ME_R1 + 1;
     const int cx = 2 * (bi % W - VCP_ME_R1), cy = 2 * (bi / W - VCP_ME_R1);
 
-    // ---- L0: +-2 around (cx,cy) on the full-res originals -----------------------------------
+    // ---- L0: +-2 around (cx,cy) on the full-res originals, one lane per candidate ------------
     const uint8_t* yc = b.src_y + (size_t)n * g.ysize + g.yoff;
     const uint8_t* yp = b.src_y + (size_t)(n - 1) * g.ysize + g.yoff;
-    const int row = lane >> 1, hx = (lane & 1) * 8;
-    const uint2 c8 = *reinterpret_cast<const uint2*>(yc + (size_t)(16 * my + row) * g.ys + 16 * mx + hx);
-    best = 0xffffffffu;
-#pragma unroll 5
-    for (int idx = 0; idx < 25; idx++) {
-        const int mvx = cx + idx % 5 - 2, mvy = cy + idx / 5 - 2;
-        const uint2 r8 = ld8_unaligned(yp + (ptrdiff_t)(16 * my + row + mvy) * g.ys + 16 * mx + hx + mvx);
-        const int sad = warp_sum((int)sad4(r8.y, c8.y, sad4(r8.x, c8.x, 0)));
-        const uint32_t key = ((uint32_t)(sad + VCP_ME_L0_PEN * (vcp_iabs(mvx) + vcp_iabs(mvy))) << 8) | (uint32_t)idx;
-        best = key < best ? key : best;
+    PrepassWarp& S = pw[warp];
+    {
+        const int row = lane >> 1, hx = (lane & 1) * 8;
+        *reinterpret_cast<uint2*>(&S.cur[row][hx]) =
+            *reinterpret_cast<const uint2*>(yc + (size_t)(16 * my + row) * g.ys + 16 * mx + hx);
+        // reference region: rows cy-2 .. cy+17, cols cx-2 .. cx+25
+        const uint8_t* rb = yp + (ptrdiff_t)(16 * my + cy - 2) * g.ys + 16 * mx + cx - 2;
+        const int c = lane & 7, r0 = lane >> 3;   // 7 words per row, 4 rows per pass
+        if (c < 7) {
+#pragma unroll
+            for (int r = r0; r < 20; r += 4)
+                reinterpret_cast<uint32_t*>(&S.ref[r][0])[c] = ld4_unaligned(rb + (ptrdiff_t)r * g.ys + 4 * c);
+        }
     }
+    __syncwarp();
+    best = 0xffffffffu;
+    if (lane < 25) {
+        const int ox = lane % 5, oy = lane / 5;   // candidate offset + 2
+        uint32_t sad = 0;
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const uint4 c4 = *reinterpret_cast<const uint4*>(&S.cur[r][0]);
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(&S.ref[r + oy][ox & ~3]);
+            const uint32_t sh = (uint32_t)(ox & 3) * 8;
+            const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
+            sad = sad4(__funnelshift_r(w0, w1, sh), c4.x, sad);
+            sad = sad4(__funnelshift_r(w1, w2, sh), c4.y, sad);
+            sad = sad4(__funnelshift_r(w2, w3, sh), c4.z, sad);
+            sad = sad4(__funnelshift_r(w3, w4, sh), c4.w, sad);
+        }
+        const int mvx = cx + ox - 2, mvy = cy + oy - 2;
+        best = ((sad + VCP_ME_L0_PEN * (uint32_t)(vcp_iabs(mvx) + vcp_iabs(mvy))) << 8) | (uint32_t)lane;
+    }
+    best = warp_min(best);
     if (lane == 0) {
         const int k = (int)(best & 0xff);
         b.mvfp[(size_t)n * g.nmb + my * g.mbw + mx] = make_short2((short)(cx + k % 5 - 2), (short)(cy + k / 5 - 2));
@@ -157,6 +187,10 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
         if (key < best) { best = key; bvx = vx; bvy = vy; }
     }
     uint32_t bcost = best >> 4;
+    if (bcost < VCP_SUBPEL_SKIP_COST) {   // warp-uniform
+        if (lane == 0) b.mv[(size_t)gi * g.nmb + mbi] = make_short2((short)(4 * bvx), (short)(4 * bvy));
+        return;
+    }
 
     // half-pel planes around the best full-pel position
     LumaPlanes& P = planes[warp];

@@ -28,6 +28,9 @@
 #define VCP_ME_L1_PEN 2   // cost += PEN * (|dx|+|dy|) at L1 (half-res pixels)
 #define VCP_ME_L0_PEN 2   // cost += PEN * (|mvx|+|mvy|) at L0 (full-res pixels)
 #define VCP_MV_FP_MAX 27  // |full-pel mv| bound after refine; +-111 in quarter units
+// a macroblock whose best full-pel cost is already below this keeps the full-pel vector
+// (static / perfectly tracked content: sub-pel refinement cannot pay for itself)
+#define VCP_SUBPEL_SKIP_COST 256
 
 // macroblock types stored by the encoder
 #define VCP_MB_I16 0

@@ -23,42 +23,85 @@ __device__ __forceinline__ int vcp_tap6(int a, int b, int c, int d, int e, int f
     return a - 5 * b + 20 * c + 20 * d - 5 * e + f;
 }
 
-// centre: pointer to the integer sample (0,0) of the block in the reference plane
+// centre: pointer to the integer sample (0,0) of the block in the reference plane.
+// Lane mappings are fixed (no div/mod in the loops): a lane owns one column (or word) and
+// strides over rows.
 __device__ __forceinline__ void luma_planes_build(LumaPlanes& P, const uint8_t* __restrict__ centre, int stride,
                                                   int lane, bool needB, bool needH, bool needJ) {
-    for (int i = lane; i < 22 * 6; i += 32) {
-        const int r = i / 6, c = i % 6;
-        reinterpret_cast<uint32_t*>(&P.G[r][0])[c] = ld4_unaligned(centre + (ptrdiff_t)(r - 3) * stride - 4 + 4 * c);
+    {   // integer window: 22 rows x 6 words; lane -> word (lane&7) < 6, rows (lane>>3) + 4k
+        const int c = lane & 7, r0 = lane >> 3;
+        if (c < 6) {
+            const uint8_t* src = centre - 4 + 4 * c + (ptrdiff_t)(r0 - 3) * stride;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const int r = r0 + 4 * k;
+                if (r < 22) reinterpret_cast<uint32_t*>(&P.G[r][0])[c] = ld4_unaligned(src + (ptrdiff_t)(4 * k) * stride);
+            }
+        }
     }
     __syncwarp();
     if (needB || needJ) {
-        for (int i = lane; i < 22 * 17; i += 32) {
-            const int r = i / 17, x = i % 17;
+        // b1: 22 rows x 17 columns.  lanes 0-15 / 16-31 take even / odd rows of columns 0..15;
+        // column 16 is done by lanes 0..21 (one row each)
+        const int x = lane & 15, r0 = lane >> 4;
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const int r = r0 + 2 * k;
             const uint8_t* p = &P.G[r][x + 1];
             P.b1[r][x] = (int16_t)vcp_tap6(p[0], p[1], p[2], p[3], p[4], p[5]);
         }
+        if (lane < 22) {
+            const uint8_t* p = &P.G[lane][17];
+            P.b1[lane][16] = (int16_t)vcp_tap6(p[0], p[1], p[2], p[3], p[4], p[5]);
+        }
     }
     if (needH) {
-        for (int i = lane; i < 17 * 18; i += 32) {
-            const int yy = i / 18, x = i % 18;
-            const int v = vcp_tap6(P.G[yy][x + 3], P.G[yy + 1][x + 3], P.G[yy + 2][x + 3], P.G[yy + 3][x + 3],
-                                   P.G[yy + 4][x + 3], P.G[yy + 5][x + 3]);
-            P.H[yy][x] = (uint8_t)vcp_clip255((v + 16) >> 5);
+        // h: 17 rows x 18 columns; lanes 0-15 / 16-31 take rows of columns 0..15 alternately,
+        // columns 16,17 by lanes 0..16 / 17..(unused) in a second pass
+        const int x = lane & 15, r0 = lane >> 4;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const int yy = r0 + 2 * k;
+            if (yy < 17) {
+                const int v = vcp_tap6(P.G[yy][x + 3], P.G[yy + 1][x + 3], P.G[yy + 2][x + 3], P.G[yy + 3][x + 3],
+                                       P.G[yy + 4][x + 3], P.G[yy + 5][x + 3]);
+                P.H[yy][x] = (uint8_t)vcp_clip255((v + 16) >> 5);
+            }
+        }
+#pragma unroll
+        for (int xx = 16; xx < 18; xx++) {
+            if (lane < 17) {
+                const int v = vcp_tap6(P.G[lane][xx + 3], P.G[lane + 1][xx + 3], P.G[lane + 2][xx + 3], P.G[lane + 3][xx + 3],
+                                       P.G[lane + 4][xx + 3], P.G[lane + 5][xx + 3]);
+                P.H[lane][xx] = (uint8_t)vcp_clip255((v + 16) >> 5);
+            }
         }
     }
     __syncwarp();
     if (needB) {
-        for (int i = lane; i < 18 * 17; i += 32) {
-            const int yy = i / 17, x = i % 17;
+        const int x = lane & 15, r0 = lane >> 4;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const int yy = r0 + 2 * k;
             P.B[yy][x] = (uint8_t)vcp_clip255((P.b1[yy + 2][x] + 16) >> 5);
         }
+        if (lane < 18) P.B[lane][16] = (uint8_t)vcp_clip255((P.b1[lane + 2][16] + 16) >> 5);
     }
     if (needJ) {
-        for (int i = lane; i < 17 * 17; i += 32) {
-            const int yy = i / 17, x = i % 17;
-            const int v = vcp_tap6(P.b1[yy][x], P.b1[yy + 1][x], P.b1[yy + 2][x], P.b1[yy + 3][x], P.b1[yy + 4][x],
-                                   P.b1[yy + 5][x]);
-            P.J[yy][x] = (uint8_t)vcp_clip255((v + 512) >> 10);
+        const int x = lane & 15, r0 = lane >> 4;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const int yy = r0 + 2 * k;
+            if (yy < 17) {
+                const int v = vcp_tap6(P.b1[yy][x], P.b1[yy + 1][x], P.b1[yy + 2][x], P.b1[yy + 3][x], P.b1[yy + 4][x],
+                                       P.b1[yy + 5][x]);
+                P.J[yy][x] = (uint8_t)vcp_clip255((v + 512) >> 10);
+            }
+        }
+        if (lane < 17) {
+            const int v = vcp_tap6(P.b1[lane][16], P.b1[lane + 1][16], P.b1[lane + 2][16], P.b1[lane + 3][16],
+                                   P.b1[lane + 4][16], P.b1[lane + 5][16]);
+            P.J[lane][16] = (uint8_t)vcp_clip255((v + 512) >> 10);
         }
     }
     __syncwarp();
