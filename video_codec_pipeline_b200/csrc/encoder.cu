@@ -57,8 +57,12 @@ struct vcpenc_session {
     int gop_base = 0;  // clip-level index of the first resident GOP
     cudaStream_t st = nullptr, st_copy = nullptr;
     static constexpr int kMaxGroups = 8;
-    cudaStream_t gst[kMaxGroups] = {};          // one stream per GOP group
+    cudaStream_t gst[kMaxGroups] = {};          // one stream per GOP group (the recon chain)
+    cudaStream_t est[kMaxGroups] = {};          // entropy coding of the group, off the chain
     cudaEvent_t gev[kMaxGroups] = {};
+    cudaEvent_t ev_rec[kMaxGroups][2] = {};     // records of parity p are complete (after mbinfo)
+    cudaEvent_t ev_ent[kMaxGroups][2] = {};     // entropy coding finished reading records of parity p
+    VcpBufs bpar[2]{};                          // per-parity views of the double-buffered MB records
     cudaEvent_t ev_pre = nullptr;
     int ngroups = 4;
     std::vector<void*> allocs;
@@ -178,7 +182,12 @@ void vcpenc_session_destroy(vcpenc_session* s) {
     if (s->h_out) cudaFreeHost(s->h_out);
     for (int i = 0; i < vcpenc_session::kMaxGroups; i++) {
         if (s->gst[i]) cudaStreamDestroy(s->gst[i]);
+        if (s->est[i]) cudaStreamDestroy(s->est[i]);
         if (s->gev[i]) cudaEventDestroy(s->gev[i]);
+        for (int q = 0; q < 2; q++) {
+            if (s->ev_rec[i][q]) cudaEventDestroy(s->ev_rec[i][q]);
+            if (s->ev_ent[i][q]) cudaEventDestroy(s->ev_ent[i][q]);
+        }
     }
     if (s->ev_pre) cudaEventDestroy(s->ev_pre);
     if (s->st) cudaStreamDestroy(s->st);
@@ -227,7 +236,12 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     }
     for (int i = 0; i < s->ngroups; i++) {
         CKS(cudaStreamCreateWithFlags(&s->gst[i], cudaStreamNonBlocking));
+        CKS(cudaStreamCreateWithFlags(&s->est[i], cudaStreamNonBlocking));
         CKS(cudaEventCreateWithFlags(&s->gev[i], cudaEventDisableTiming));
+        for (int q = 0; q < 2; q++) {
+            CKS(cudaEventCreateWithFlags(&s->ev_rec[i][q], cudaEventDisableTiming));
+            CKS(cudaEventCreateWithFlags(&s->ev_ent[i][q], cudaEventDisableTiming));
+        }
     }
     VcpBufs& b = s->b;
     const size_t N = max_frames, G = s->ngop_max, nmb = g.nmb;
@@ -239,15 +253,15 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     TRY(dev_alloc(s, &b.rec_u, G * s->ring * g.csize, err, errlen));
     TRY(dev_alloc(s, &b.rec_v, G * s->ring * g.csize, err, errlen));
     TRY(dev_alloc(s, &b.mvfp, N * nmb, err, errlen));
-    TRY(dev_alloc(s, &b.mv, G * nmb, err, errlen));
-    TRY(dev_alloc(s, &b.mvd, G * nmb, err, errlen));
-    TRY(dev_alloc(s, &b.mbtype, G * nmb, err, errlen));
-    TRY(dev_alloc(s, &b.cbp, G * nmb, err, errlen));
-    TRY(dev_alloc(s, &b.modes, G * nmb, err, errlen));
-    TRY(dev_alloc(s, &b.nnz, G * nmb * 24, err, errlen));
-    TRY(dev_alloc(s, &b.levels, G * nmb * VCP_LV_STRIDE, err, errlen));
-    TRY(dev_alloc(s, &b.mbbits, G * nmb, err, errlen));
-    TRY(dev_alloc(s, &b.mbbitoff, G * nmb, err, errlen));
+    TRY(dev_alloc(s, &b.mv, 2 * G * nmb, err, errlen));
+    TRY(dev_alloc(s, &b.mvd, 2 * G * nmb, err, errlen));
+    TRY(dev_alloc(s, &b.mbtype, 2 * G * nmb, err, errlen));
+    TRY(dev_alloc(s, &b.cbp, 2 * G * nmb, err, errlen));
+    TRY(dev_alloc(s, &b.modes, 2 * G * nmb, err, errlen));
+    TRY(dev_alloc(s, &b.nnz, 2 * G * nmb * 24, err, errlen));
+    TRY(dev_alloc(s, &b.levels, 2 * G * nmb * VCP_LV_STRIDE, err, errlen));
+    TRY(dev_alloc(s, &b.mbbits, 2 * G * nmb, err, errlen));
+    TRY(dev_alloc(s, &b.mbbitoff, 2 * G * nmb, err, errlen));
     TRY(dev_alloc(s, &b.skiprun, (size_t)1, err, errlen));
     TRY(dev_alloc(s, &b.qp, N, err, errlen));
     // raw slice payload: H.264 bounds a macroblock at 3200 bits; 512 B/MB leaves headroom
@@ -281,6 +295,13 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     CKS(cudaMemsetAsync(b.rec_v, 128, G * s->ring * g.csize, s->st));
     CKS(cudaMemsetAsync(b.mvfp, 0, N * nmb * sizeof(short2), s->st));
     CKS(cudaStreamSynchronize(s->st));
+    for (int q = 0; q < 2; q++) {
+        VcpBufs v = b;
+        v.mv += q * G * nmb; v.mvd += q * G * nmb; v.mbtype += q * G * nmb; v.cbp += q * G * nmb;
+        v.modes += q * G * nmb; v.nnz += q * G * nmb * 24; v.levels += q * G * nmb * VCP_LV_STRIDE;
+        v.mbbits += q * G * nmb; v.mbbitoff += q * G * nmb;
+        s->bpar[q] = v;
+    }
     s->sps = vcp::make_sps_nal(*pp);
     s->pps = vcp::make_pps_nal(*pp);
     *out = s;
@@ -361,8 +382,11 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
     CK(cudaEventRecord(s->ev_pre, s->st));
     for (int k = 0; k < ng; k++) CK(cudaStreamWaitEvent(s->gst[k], s->ev_pre, 0));
     for (int t = 0; t < gop && t < N; t++) {
+        const int par = t & 1;
+        const VcpBufs& bt = s->bpar[par];     // macroblock records of this step
         for (int k = 0; k < ng; k++) {
             cudaStream_t st = s->profile ? s->st : s->gst[k];
+            cudaStream_t se = s->profile ? s->st : s->est[k];   // entropy stream
             VcpStep sp;
             sp.t = t; sp.gop = gop; sp.ring = s->ring; sp.nframes = N; sp.gop0 = s->gop_base;
             // GOPs of this group that own a frame at position t
@@ -371,32 +395,42 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
             sp.g0 = gA;
             sp.ngop = std::min(gB, active) - gA;
             if (sp.ngop <= 0) continue;
+            // the records of this parity were last read by the entropy pass of step t-2
+            if (!s->profile && t >= 2) CK(cudaStreamWaitEvent(st, s->ev_ent[k][par], 0));
             if (t == 0) {
                 Prof pr(s, VCPENC_K_I_RECON, 1, st);
-                vcp_launch_i_recon(g, b, sp, st);
+                vcp_launch_i_recon(g, bt, sp, st);
             } else {
-                { Prof pr(s, VCPENC_K_ME_REFINE, 1, st); vcp_launch_me_refine(g, b, sp, st); }
-                { Prof pr(s, VCPENC_K_P_RECON, 1, st); vcp_launch_p_recon(g, b, sp, st); }
-                { Prof pr(s, VCPENC_K_MBINFO, 1, st); vcp_launch_mbinfo(g, b, sp, st); }
+                { Prof pr(s, VCPENC_K_ME_REFINE, 1, st); vcp_launch_me_refine(g, bt, sp, st); }
+                { Prof pr(s, VCPENC_K_P_RECON, 1, st); vcp_launch_p_recon(g, bt, sp, st); }
+                { Prof pr(s, VCPENC_K_MBINFO, 1, st); vcp_launch_mbinfo(g, bt, sp, st); }
             }
-            { Prof pr(s, VCPENC_K_CAVLC_COUNT, 1, st); vcp_launch_cavlc_count(g, b, sp, st); }
-            { Prof pr(s, VCPENC_K_CAVLC_SCAN, 1, st); vcp_launch_cavlc_scan(g, b, sp, st); }
-            { Prof pr(s, VCPENC_K_CAVLC_WRITE, 2, st); vcp_launch_cavlc_write(g, b, sp, st); vcp_launch_nal_pack(g, b, sp, st); }
-            if (g.deblock_idc != 1) { Prof pr(s, VCPENC_K_DEBLOCK, 1, st); vcp_launch_deblock(g, b, sp, st); }
-            { Prof pr(s, VCPENC_K_PAD, 1, st); vcp_launch_pad(g, b, sp, st); }
             if (s->p.debug) {
                 for (int gi = gA; gi < gA + sp.ngop; gi++) {
                     const size_t n = (size_t)gi * gop + t;
-                    CK(cudaMemcpyAsync(s->dbg_mv + n * g.nmb, b.mv + (size_t)gi * g.nmb, g.nmb * sizeof(short2), cudaMemcpyDeviceToDevice, st));
-                    CK(cudaMemcpyAsync(s->dbg_type + n * g.nmb, b.mbtype + (size_t)gi * g.nmb, g.nmb, cudaMemcpyDeviceToDevice, st));
-                    CK(cudaMemcpyAsync(s->dbg_cbp + n * g.nmb, b.cbp + (size_t)gi * g.nmb, g.nmb, cudaMemcpyDeviceToDevice, st));
+                    CK(cudaMemcpyAsync(s->dbg_mv + n * g.nmb, bt.mv + (size_t)gi * g.nmb, g.nmb * sizeof(short2), cudaMemcpyDeviceToDevice, st));
+                    CK(cudaMemcpyAsync(s->dbg_type + n * g.nmb, bt.mbtype + (size_t)gi * g.nmb, g.nmb, cudaMemcpyDeviceToDevice, st));
+                    CK(cudaMemcpyAsync(s->dbg_cbp + n * g.nmb, bt.cbp + (size_t)gi * g.nmb, g.nmb, cudaMemcpyDeviceToDevice, st));
                 }
             }
+            // entropy coding only reads the records: it leaves the recon chain here
+            if (!s->profile) {
+                CK(cudaEventRecord(s->ev_rec[k][par], st));
+                CK(cudaStreamWaitEvent(se, s->ev_rec[k][par], 0));
+            }
+            { Prof pr(s, VCPENC_K_CAVLC_COUNT, 1, se); vcp_launch_cavlc_count(g, bt, sp, se); }
+            { Prof pr(s, VCPENC_K_CAVLC_SCAN, 1, se); vcp_launch_cavlc_scan(g, bt, sp, se); }
+            { Prof pr(s, VCPENC_K_CAVLC_WRITE, 2, se); vcp_launch_cavlc_write(g, bt, sp, se); vcp_launch_nal_pack(g, bt, sp, se); }
+            if (!s->profile) CK(cudaEventRecord(s->ev_ent[k][par], se));
+            if (g.deblock_idc != 1) { Prof pr(s, VCPENC_K_DEBLOCK, 1, st); vcp_launch_deblock(g, bt, sp, st); }
+            { Prof pr(s, VCPENC_K_PAD, 1, st); vcp_launch_pad(g, bt, sp, st); }
         }
     }
     if (!s->profile)
         for (int k = 0; k < ng; k++) {
             CK(cudaEventRecord(s->gev[k], s->gst[k]));
+            CK(cudaStreamWaitEvent(s->st, s->gev[k], 0));
+            CK(cudaEventRecord(s->gev[k], s->est[k]));
             CK(cudaStreamWaitEvent(s->st, s->gev[k], 0));
         }
     CK(cudaGetLastError());

@@ -377,6 +377,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) cavlc_scan_kernel(VcpGeom g, Vcp
 }
 
 constexpr int PACK_THREADS = 256;
+constexpr int PACK_BYTES = 16;   // payload bytes per thread per pass
+
+// escape decision for 16 consecutive payload bytes starting at i0 (i0 % 16 == 0):
+// byte i gets a 0x03 in front iff src[i] <= 3 and the run of zero bytes right before it has
+// an even length >= 2 (equivalent to the sequential "two zeros then <= 3" rule with its reset).
+__device__ __forceinline__ uint32_t escape_mask16(const uint8_t* __restrict__ src, uint32_t i0, uint32_t bytes, uint4& v) {
+    v = *reinterpret_cast<const uint4*>(src + i0);   // rbsp slots are 16 B aligned and zero padded
+    // zero run before byte i0
+    uint32_t z = 0;
+    while (z < i0 && src[i0 - 1 - z] == 0) z++;
+    uint32_t mask = 0;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const uint32_t byte = (w[k >> 2] >> (8 * (k & 3))) & 255;
+        if (i0 + k < bytes && byte <= 3 && z >= 2 && !(z & 1)) mask |= 1u << k;
+        z = byte == 0 ? z + 1 : 0;
+    }
+    return mask;
+}
 
 // grid: x = slice, y = GOP.  NAL = 00 00 00 01 | header | escaped RBSP
 __global__ void __launch_bounds__(PACK_THREADS) nal_pack_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
@@ -391,15 +411,14 @@ __global__ void __launch_bounds__(PACK_THREADS) nal_pack_kernel(VcpGeom g, VcpBu
     if (err_seen) return;
     const uint32_t bytes = b.slice_bits[(size_t)gi * g.slices + sl] >> 3;
     const uint8_t* src = b.rbsp + ((size_t)gi * g.slices + sl) * b.rbsp_cap;
+    const uint32_t npass = (bytes + PACK_THREADS * PACK_BYTES - 1) / (PACK_THREADS * PACK_BYTES);
     // pass 1: number of emulation-prevention bytes
-    auto needs_escape = [&](uint32_t i) -> uint32_t {
-        if (src[i] > 3) return 0;
-        uint32_t z = 0;
-        while (z < i && src[i - 1 - z] == 0) z++;
-        return (z >= 2 && !(z & 1)) ? 1u : 0u;
-    };
     uint32_t cnt = 0;
-    for (uint32_t i = threadIdx.x; i < bytes; i += PACK_THREADS) cnt += needs_escape(i);
+    for (uint32_t ps = 0; ps < npass; ps++) {
+        const uint32_t i0 = (ps * PACK_THREADS + threadIdx.x) * PACK_BYTES;
+        uint4 v;
+        if (i0 < bytes) cnt += __popc(escape_mask16(src, i0, bytes, v));
+    }
     uint32_t nesc;
     block_excl_scan(cnt, wsum, nesc);
     const uint32_t size = 5 + bytes + nesc;
@@ -416,15 +435,26 @@ __global__ void __launch_bounds__(PACK_THREADS) nal_pack_kernel(VcpGeom g, VcpBu
     if (threadIdx.x < 5) dst[threadIdx.x] = threadIdx.x < 3 ? 0 : (threadIdx.x == 3 ? 1 : (uint8_t)(idr ? 0x65 : 0x41));
     dst += 5;
     uint32_t carry = 0;
-    for (uint32_t i0 = 0; i0 < bytes; i0 += PACK_THREADS) {
-        const uint32_t i = i0 + threadIdx.x;
-        const uint32_t f = i < bytes ? needs_escape(i) : 0;
+    for (uint32_t ps = 0; ps < npass; ps++) {
+        const uint32_t i0 = (ps * PACK_THREADS + threadIdx.x) * PACK_BYTES;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        const uint32_t mask = i0 < bytes ? escape_mask16(src, i0, bytes, v) : 0;
         uint32_t tot;
-        const uint32_t ex = block_excl_scan(f, wsum, tot);
-        if (i < bytes) {
-            uint32_t p = i + carry + ex;
-            if (f) dst[p++] = 3;
-            dst[p] = src[i];
+        const uint32_t ex = block_excl_scan((uint32_t)__popc(mask), wsum, tot);
+        if (i0 < bytes) {
+            uint8_t* d = dst + i0 + carry + ex;
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            const uint32_t lim = bytes - i0 < PACK_BYTES ? bytes - i0 : PACK_BYTES;
+            if (mask == 0 && lim == PACK_BYTES) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) d[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+            } else {
+                uint32_t o = 0;
+                for (uint32_t k = 0; k < lim; k++) {
+                    if ((mask >> k) & 1) d[o++] = 3;
+                    d[o++] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+                }
+            }
         }
         carry += tot;
     }
