@@ -131,7 +131,7 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, 32))
-    fpg = 6                                # IDR + 5 P per GOP prefix, per thread and step
+    fpg = 30                               # IDR + 29 P per GOP prefix, per thread and step
     base = make_workload(2)
     times, nframes = [], threads * fpg
     for i in range(args.warmup + args.steps):
@@ -287,6 +287,12 @@ def main():
         avg_ms = st["ms"] / max(1, st["launches"])
         achieved = bytes_per_launch / (avg_ms / 1000.0) / 1e9 if avg_ms > 0 else 0.0
         tot_ms = sum(v["ms"] for v in stats.values())
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):
+            per_frame = json.load(open(tpath)).get(top)
+            if per_frame:
+                traffic = int(per_frame * frames_per_launch)   # ncu --set full capture, scaled to this launch size
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True,
@@ -301,16 +307,16 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": top, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 5), "traffic": None, "peak_source": which,
+                         "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": which,
                          "share_of_step": round(st["ms"] / tot_ms, 4) if tot_ms else None,
                          "avg_launch_ms": round(avg_ms, 4), "launches": st["launches"]},
             "kernels_ms_per_step_single_stream": {k: round(v["ms"] / prof_steps, 3) for k, v in stats.items() if v["launches"]},
         }
         if not args.no_cpu_baseline and world == 1:
             cores = max(1, min(os.cpu_count() or 1, 32))
-            fps, dt = cpu_port_fps(frames, cores, 6)
+            fps, dt = cpu_port_fps(frames, cores, GOP)
             line["cpu_baseline"] = {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
-                                    "sample": "%d threads x first 6 frames of a GOP (IDR+5P) of the same clip, %.1f s; oracle/h264_oracle.c (libx264/ffmpeg absent from image)" % (cores, dt)}
+                                    "sample": "%d threads x one whole GOP (IDR+59P) of the same clip each, %.1f s; oracle/h264_oracle.c (libx264/ffmpeg absent from image)" % (cores, dt)}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)

@@ -1016,6 +1016,7 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
     e->p = *p;
     if (p->width < 16 || p->height < 16 || (p->width & 1) || (p->height & 1) || p->gop < 1 || p->slices < 1) return VCPENC_E_ARGS;
     if (p->entropy != 0 || p->codec != VCPENC_CODEC_H264 || p->in_fmt != VCPENC_FMT_YUV420P) return VCPENC_E_ARGS;
+    if (p->rc_mode == VCPENC_RC_ABR && p->bitrate <= 0) return VCPENC_E_ARGS;
     e->mbw = (p->width + 15) / 16; e->mbh = (p->height + 15) / 16; e->nmb = e->mbw * e->mbh;
     if (p->slices > e->mbh) return VCPENC_E_ARGS;
     e->cw = 16 * e->mbw; e->ch = 16 * e->mbh;
@@ -1032,9 +1033,18 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
     size_t fsz = (size_t)p->width * p->height + 2 * (size_t)((p->width + 1) / 2) * ((p->height + 1) / 2);
     size_t o = 0;
     int ri = 0, idr_count = p->first_gop;
+    /* rate control state of the current GOP (vcp_algo.h) */
+    const int abr = p->rc_mode == VCPENC_RC_ABR;
+    const int rc_qp0 = abr ? vcp_rc_initial_qp(p->bitrate, p->fps_num, p->fps_den, p->width, p->height) : 0;
+    unsigned long long rc_cum = 0;
+    int rc_qp_next[2] = {0, 0}; /* QP decided for pictures t+1, t+2 */
     for (int n = 0; n < nframes; n++) {
         int t = n % p->gop, idr = t == 0;
         int qp = idr ? p->qp_i : p->qp_p;
+        if (abr) {
+            if (idr) { rc_cum = 0; rc_qp_next[0] = rc_qp_next[1] = rc_qp0; qp = rc_qp0 - VCP_RC_QP_I_OFFSET; if (qp < 0) qp = 0; }
+            else { qp = rc_qp_next[0]; rc_qp_next[0] = rc_qp_next[1]; }
+        }
         /* K1 */
         { Frame tf = e->prev_orig; e->prev_orig = e->cur; e->cur = tf; Half th = e->hprev; e->hprev = e->hcur; e->hcur = th; }
         frame_load_yuv420p(&e->cur, frames + (size_t)n * fsz, p->width, p->height);
@@ -1075,6 +1085,7 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
             size_t k = write_sps(e, out + o, out_cap - o); if (!k) { rc = VCPENC_E_OVERFLOW; goto done; } o += k;
             k = write_pps(e, out + o, out_cap - o); if (!k) { rc = VCPENC_E_OVERFLOW; goto done; } o += k;
         }
+        unsigned long long frame_bits = 0;
         for (int s = 0; s < p->slices; s++) {
             int r0 = slice_first_row(e, s), r1 = s + 1 < p->slices ? slice_first_row(e, s + 1) : e->mbh;
             BW b; bw_init(&b, e->rbsp, e->rbsp_cap);
@@ -1084,6 +1095,16 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
             size_t k = nal_write(out + o, out_cap - o, idr ? 3 : 2, idr ? 5 : 1, e->rbsp, b.pos);
             if (!k) { rc = VCPENC_E_OVERFLOW; goto done; }
             o += k;
+            frame_bits += (unsigned long long)b.pos * 8;
+        }
+        if (abr) {
+            /* feedback lands two pictures later (entropy coding runs beside the recon chain) */
+            int gop_len = p->gop;
+            int g0 = n - t;
+            if (g0 + gop_len > nframes) gop_len = nframes - g0;
+            unsigned long long budget = (unsigned long long)p->bitrate * (unsigned)p->fps_den / (unsigned)p->fps_num * (unsigned)gop_len;
+            rc_cum += frame_bits;
+            rc_qp_next[1] = vcp_rc_next_qp(rc_qp0, rc_cum, t, gop_len, budget);
         }
         if (idr) idr_count++;
         if (info) { info[n].offset = au0; info[n].size = (uint32_t)(o - au0); info[n].is_idr = (uint8_t)idr; info[n].qp = (uint8_t)qp; }

@@ -83,6 +83,21 @@ def test_full_size_decoder_reproduces_recon(built, w, h, n, gop, sl):
         assert b"".join(parts) == got["stream"].tobytes()
 
 
+def test_bitrate_mode_equals_oracle(built):
+    """Rate control runs on the device (rc_update_kernel) with the feedback delay of the side-stream
+    entropy coder; the oracle mirrors it, so bytes and per-picture QPs must agree."""
+    from oracle import pyoracle
+    w, h, n, fps = 320, 192, 50, 25
+    clip = synth.make_clip(w, h, n, seed=12)
+    for br, gop, sl in ((500_000, 20, 1), (2_000_000, 24, 3)):
+        ref = pyoracle.encode(pyoracle.make_params(w, h, fps=fps, gop=gop, slices=sl, rc_mode=1, bitrate=br), clip)
+        got = api.encode_frames(api.default_params(w, h, fps=fps, gop=gop, slices=sl, rc_mode=1, bitrate=br), clip,
+                                want_recon=True)
+        assert [x[3] for x in got["info"]] == [x[3] for x in ref["info"]]
+        assert got["stream"].tobytes() == ref["stream"]
+        assert np.array_equal(got["recon"], ref["recon"])
+
+
 def test_edge_cases(built):
     from oracle import pyoracle
     # smallest picture, one frame; GOP 1; one slice per macroblock row; ragged last GOP

@@ -163,3 +163,23 @@ def test_oracle_edge_cases():
     bad = pyoracle.make_params(w, h, gop=0)
     with pytest.raises(RuntimeError):
         pyoracle.encode(bad, clip)
+
+
+def test_oracle_bitrate_mode():
+    """-b:v: per-GOP budget, QP feedback two pictures late (vcp_algo.h); stream must stay decodable
+    and land near the target."""
+    w, h, n, fps = 320, 192, 48, 24
+    clip = synth.make_clip(w, h, n, seed=12)
+    sizes = {}
+    for br in (400_000, 1_600_000):
+        p = pyoracle.make_params(w, h, fps=fps, gop=24, rc_mode=1, bitrate=br)
+        r = pyoracle.encode(p, clip)
+        sizes[br] = len(r["stream"]) * 8 / (n / fps)
+        qps = [x[3] for x in r["info"]]
+        assert qps[0] == qps[1] - 3 and len(set(qps)) > 2          # IDR offset, feedback moves QP
+        if arbiter.available():
+            dec = arbiter.decode_annexb(r["stream"])
+            for i in range(n):
+                assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i])
+    assert sizes[1_600_000] > 2.0 * sizes[400_000]
+    assert 0.6 * 1_600_000 < sizes[1_600_000] < 1.5 * 1_600_000

@@ -108,7 +108,14 @@ int check_params(const vcpenc_params& p, char* err, size_t errlen) {
     if (p.qp_i < 0 || p.qp_i > 51 || p.qp_p < 0 || p.qp_p > 51) { set_err(err, errlen, "qp out of range"); return VCPENC_E_ARGS; }
     if (p.in_fmt != VCPENC_FMT_YUV420P) { set_err(err, errlen, "input pixel format %d not implemented", p.in_fmt); return VCPENC_E_FORMAT; }
     if (p.deblock_idc < 0 || p.deblock_idc > 2) { set_err(err, errlen, "bad deblock_idc"); return VCPENC_E_ARGS; }
+    if (p.rc_mode == VCPENC_RC_ABR && (p.bitrate <= 0 || p.fps_num <= 0 || p.fps_den <= 0)) { set_err(err, errlen, "bitrate mode needs -b:v and a frame rate"); return VCPENC_E_ARGS; }
     return VCPENC_OK;
+}
+
+uint8_t initial_qp(const vcpenc_session* s, int n) {
+    const bool idr = (n % s->p.gop) == 0;
+    if (s->g.rc_abr) return (uint8_t)std::max(0, idr ? s->g.rc_qp0 - VCP_RC_QP_I_OFFSET : s->g.rc_qp0);
+    return (uint8_t)(idr ? s->p.qp_i : s->p.qp_p);
 }
 
 struct Prof {
@@ -219,6 +226,9 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     g.coff = VCP_PADC * g.cs + VCP_PADC;
     g.hoff = VCP_PAD1 * g.hs + VCP_PAD1;
     g.slices = pp->slices; g.deblock_idc = pp->deblock_idc;
+    g.rc_abr = pp->rc_mode == VCPENC_RC_ABR;
+    g.rc_bitrate = pp->bitrate; g.fps_num = pp->fps_num; g.fps_den = pp->fps_den;
+    g.rc_qp0 = g.rc_abr ? vcp_rc_initial_qp(pp->bitrate, pp->fps_num, pp->fps_den, pp->width, pp->height) : 0;
     s->ngop_max = (max_frames + pp->gop - 1) / pp->gop;
     s->ring = pp->debug ? std::min(pp->gop, max_frames) : std::min(2, std::min(pp->gop, max_frames));
     if (s->ring < 1) s->ring = 1;
@@ -276,6 +286,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     TRY(dev_alloc(s, &b.out_index_hi, N * g.slices, err, errlen));
     TRY(dev_alloc(s, &b.frame_bits, N, err, errlen));
     TRY(dev_alloc(s, &b.error_flag, (size_t)1, err, errlen));
+    TRY(dev_alloc(s, &b.rc_cum, G, err, errlen));
     TRY(dev_alloc(s, &b.db_sync, G * (g.mbh + 1) + 1, err, errlen));
     if (pp->debug) {
         TRY(dev_alloc(s, &s->dbg_mv, N * nmb, err, errlen));
@@ -317,7 +328,7 @@ int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes,
     s->nframes = nframes;
     s->encoded = false;
     s->h_qp.resize(nframes);
-    for (int n = 0; n < nframes; n++) s->h_qp[n] = (uint8_t)((n % s->p.gop) == 0 ? s->p.qp_i : s->p.qp_p);
+    for (int n = 0; n < nframes; n++) s->h_qp[n] = initial_qp(s, n);
     CK(cudaMemcpyAsync(s->b.qp, s->h_qp.data(), nframes, cudaMemcpyHostToDevice, s->st));
     int chunk = 0;
     for (int n0 = 0; n0 < nframes; n0 += s->staging_frames, chunk++) {
@@ -346,7 +357,7 @@ int vcpenc_session_upload_device(vcpenc_session* s, const uint8_t* dframes, int 
     s->nframes = nframes;
     s->encoded = false;
     s->h_qp.resize(nframes);
-    for (int n = 0; n < nframes; n++) s->h_qp[n] = (uint8_t)((n % s->p.gop) == 0 ? s->p.qp_i : s->p.qp_p);
+    for (int n = 0; n < nframes; n++) s->h_qp[n] = initial_qp(s, n);
     CK(cudaMemcpyAsync(s->b.qp, s->h_qp.data(), nframes, cudaMemcpyHostToDevice, s->st));
     CK(cudaEventRecord(s->ev0, s->st));
     for (int n0 = 0; n0 < nframes; n0 += 4096) {
@@ -421,6 +432,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
             { Prof pr(s, VCPENC_K_CAVLC_COUNT, 1, se); vcp_launch_cavlc_count(g, bt, sp, se); }
             { Prof pr(s, VCPENC_K_CAVLC_SCAN, 1, se); vcp_launch_cavlc_scan(g, bt, sp, se); }
             { Prof pr(s, VCPENC_K_CAVLC_WRITE, 2, se); vcp_launch_cavlc_write(g, bt, sp, se); vcp_launch_nal_pack(g, bt, sp, se); }
+            if (g.rc_abr) { Prof pr(s, VCPENC_K_RC, 1, se); vcp_launch_rc_update(g, bt, sp, se); }
             if (!s->profile) CK(cudaEventRecord(s->ev_ent[k][par], se));
             if (g.deblock_idc != 1) { Prof pr(s, VCPENC_K_DEBLOCK, 1, st); vcp_launch_deblock(g, bt, sp, st); }
             { Prof pr(s, VCPENC_K_PAD, 1, st); vcp_launch_pad(g, bt, sp, st); }
@@ -474,6 +486,7 @@ int vcpenc_session_download(vcpenc_session* s, uint8_t* out, size_t out_cap, siz
     CK(cudaMemcpyAsync(s->h_out, s->b.out, (size_t)used, cudaMemcpyDeviceToHost, s->st));
     CK(cudaMemcpyAsync(idx.data(), s->b.out_index, idx.size() * sizeof(uint2), cudaMemcpyDeviceToHost, s->st));
     CK(cudaMemcpyAsync(idx_hi.data(), s->b.out_index_hi, idx_hi.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->st));
+    if (s->g.rc_abr) CK(cudaMemcpyAsync(s->h_qp.data(), s->b.qp, (size_t)N, cudaMemcpyDeviceToHost, s->st));
     CK(cudaStreamSynchronize(s->st));
     static const uint8_t sc[4] = {0, 0, 0, 1};
     size_t o = 0;

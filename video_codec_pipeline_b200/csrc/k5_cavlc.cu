@@ -460,7 +460,29 @@ __global__ void __launch_bounds__(PACK_THREADS) nal_pack_kernel(VcpGeom g, VcpBu
     }
 }
 
+// ---- rate control feedback (one thread per GOP) -------------------------------------------------
+__global__ void rc_update_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= s.ngop) return;
+    const int gi = s.g0 + k;
+    const int n = vcp_frame_of(s, gi);
+    int gop_len = s.gop;
+    if (gi * s.gop + gop_len > s.nframes) gop_len = s.nframes - gi * s.gop;
+    const unsigned long long cum = (s.t == 0 ? 0ull : b.rc_cum[gi]) + b.frame_bits[n];
+    b.rc_cum[gi] = cum;
+    if (s.t + 2 < gop_len) {
+        const unsigned long long budget =
+            (unsigned long long)g.rc_bitrate * (unsigned)g.fps_den / (unsigned)g.fps_num * (unsigned)gop_len;
+        b.qp[n + 2] = (uint8_t)vcp_rc_next_qp(g.rc_qp0, cum, s.t, gop_len, budget);
+    }
+}
+
 }  // namespace
+
+void vcp_launch_rc_update(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
+    if (!g.rc_abr) return;
+    rc_update_kernel<<<(s.ngop + 63) / 64, 64, 0, st>>>(g, b, s);
+}
 
 void vcp_launch_cavlc_count(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
     dim3 grid((g.nmb + CV_WARPS - 1) / CV_WARPS, s.ngop);

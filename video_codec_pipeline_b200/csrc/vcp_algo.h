@@ -76,4 +76,44 @@ VCP_HD int vcp_clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi 
 VCP_HD int vcp_clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 VCP_HD int vcp_iabs(int v) { return v < 0 ? -v : v; }
 
+// ---- bitrate-targeted rate control (-b:v), integer only ------------------------------------
+// GOPs are encoded independently and in parallel, so each GOP carries its own budget:
+//   budget = bitrate * gop_frames / fps ; the IDR picture is expected to cost VCP_RC_I_WEIGHT
+//   P pictures.  After picture t has been entropy coded, the QP of picture t+2 (the feedback
+//   arrives two pictures late because entropy coding runs beside the reconstruction chain) is
+//   qp0 + round(6*log2(bits spent / bits expected so far)), clamped.
+#define VCP_RC_I_WEIGHT 6
+#define VCP_RC_QP_I_OFFSET 3   // IDR pictures use qp - 3
+#define VCP_RC_DOWN 8          // qp range relative to qp0
+#define VCP_RC_UP 12
+
+// round(6*log2(num/den)), clamped to [-36, 36]
+VCP_HD int vcp_rc_log2x6(unsigned long long num, unsigned long long den) {
+    if (den == 0) den = 1;
+    if (num == 0) return -36;
+    unsigned long long r = (num << 16) / den;   // 16.16
+    if (r == 0) return -36;
+    int q = 0;
+    while (r >= (2ull << 16) && q < 36) { r >>= 1; q += 6; }
+    while (r < (1ull << 16) && q > -42) { r <<= 1; q -= 6; }
+    const unsigned r1024 = (unsigned)(r >> 6);  // [1024, 2048)
+    const unsigned mid[6] = {1085, 1218, 1367, 1534, 1722, 1933};  // 1024 * 2^((i+0.5)/6)
+    for (int i = 0; i < 6; i++) q += r1024 >= mid[i];
+    return q < -36 ? -36 : (q > 36 ? 36 : q);
+}
+// starting QP of every GOP from bits per pixel: 0.1 bpp <-> QP 28, -6 QP per doubling
+VCP_HD int vcp_rc_initial_qp(int bitrate, int fps_num, int fps_den, int w, int h) {
+    const unsigned long long bits_per_frame = (unsigned long long)bitrate * (unsigned)fps_den / (unsigned)(fps_num > 0 ? fps_num : 1);
+    const int q = 28 - vcp_rc_log2x6(bits_per_frame * 10ull, (unsigned long long)w * (unsigned)h);
+    return q < 14 ? 14 : (q > 45 ? 45 : q);
+}
+// QP of picture t+2 given the bits spent on pictures 0..t of a GOP of L pictures
+VCP_HD int vcp_rc_next_qp(int qp0, unsigned long long cum_bits, int t, int L, unsigned long long gop_budget) {
+    const unsigned long long expected = gop_budget * (unsigned)(VCP_RC_I_WEIGHT + t) / (unsigned)(VCP_RC_I_WEIGHT + L - 1);
+    int dq = vcp_rc_log2x6(cum_bits, expected);
+    dq = dq < -VCP_RC_DOWN ? -VCP_RC_DOWN : (dq > VCP_RC_UP ? VCP_RC_UP : dq);
+    const int q = qp0 + dq;
+    return q < 10 ? 10 : (q > 51 ? 51 : q);
+}
+
 #endif  // VCP_ALGO_H

@@ -25,6 +25,8 @@ struct VcpGeom {
     size_t ysize, csize, hsize;    // bytes per plane
     int slices;
     int deblock_idc;
+    // rate control (VCPENC_RC_ABR): see vcp_algo.h
+    int rc_abr, rc_qp0, rc_bitrate, fps_num, fps_den;
 };
 
 __host__ __device__ __forceinline__ int vcp_slice_first_row(int s, int slices, int mbh) {
@@ -80,6 +82,7 @@ struct VcpBufs {
     uint32_t* out_index_hi;
     uint32_t* frame_bits;  // [nframes] coded bits per frame (for rate control)
     int* error_flag;
+    unsigned long long* rc_cum;  // [ngop_max] bits spent so far in the GOP
     int* db_sync;          // deblocking: [0] row ticket, [1 + gop*mbh + row] progress
     size_t rbsp_cap;
     size_t out_cap;
@@ -99,6 +102,7 @@ void vcp_launch_cavlc_count(const VcpGeom& g, const VcpBufs& b, const VcpStep& s
 void vcp_launch_cavlc_scan(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_cavlc_write(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_nal_pack(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
+void vcp_launch_rc_update(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 
 #ifdef __CUDACC__
 // ---- small device helpers ------------------------------------------------------------------
