@@ -145,6 +145,82 @@ static void frame_load_yuv420p(Frame* f, const uint8_t* src, int w, int h) {
     frame_pad(f);
 }
 
+/* K1 restated: any accepted input format -> tight yuv420p of the same size (vcp_algo.h) */
+static void to_yuv420p(int fmt, const uint8_t* src, int w, int h, uint8_t* dst) {
+    const int cw = (w + 1) / 2, ch = (h + 1) / 2;
+    uint8_t *Y = dst, *U = dst + (size_t)w * h, *V = U + (size_t)cw * ch;
+    if (fmt == VCPENC_FMT_YUV420P) { memcpy(dst, src, (size_t)w * h + 2 * (size_t)cw * ch); return; }
+    if (fmt == VCPENC_FMT_NV12) {
+        memcpy(Y, src, (size_t)w * h);
+        const uint8_t* uv = src + (size_t)w * h;
+        for (int i = 0; i < cw * ch; i++) { U[i] = uv[2 * i]; V[i] = uv[2 * i + 1]; }
+        return;
+    }
+    if (fmt == VCPENC_FMT_RGB24 || fmt == VCPENC_FMT_BGR24) {
+        const int ro = fmt == VCPENC_FMT_RGB24 ? 0 : 2, bo = 2 - ro;
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                const uint8_t* p = src + ((size_t)y * w + x) * 3;
+                Y[(size_t)y * w + x] = (uint8_t)vcp_rgb_y(p[ro], p[1], p[bo]);
+            }
+        for (int y = 0; y < ch; y++)
+            for (int x = 0; x < cw; x++) {
+                int r = 0, g = 0, b = 0;
+                for (int dy = 0; dy < 2; dy++)
+                    for (int dx = 0; dx < 2; dx++) {
+                        int yy = 2 * y + dy < h ? 2 * y + dy : h - 1, xx = 2 * x + dx < w ? 2 * x + dx : w - 1;
+                        const uint8_t* p = src + ((size_t)yy * w + xx) * 3;
+                        r += p[ro]; g += p[1]; b += p[bo];
+                    }
+                r = (r + 2) >> 2; g = (g + 2) >> 2; b = (b + 2) >> 2;
+                U[(size_t)y * cw + x] = (uint8_t)vcp_rgb_u(r, g, b);
+                V[(size_t)y * cw + x] = (uint8_t)vcp_rgb_v(r, g, b);
+            }
+        return;
+    }
+    memcpy(Y, src, (size_t)w * h);
+    if (fmt == VCPENC_FMT_YUV444P) {
+        for (int pl = 0; pl < 2; pl++) {
+            const uint8_t* s = src + (size_t)w * h * (1 + pl);
+            uint8_t* d = pl ? V : U;
+            for (int y = 0; y < ch; y++)
+                for (int x = 0; x < cw; x++) {
+                    int y1 = 2 * y + 1 < h ? 2 * y + 1 : h - 1, x1 = 2 * x + 1 < w ? 2 * x + 1 : w - 1;
+                    d[(size_t)y * cw + x] = (uint8_t)((s[(size_t)2 * y * w + 2 * x] + s[(size_t)2 * y * w + x1] +
+                                                        s[(size_t)y1 * w + 2 * x] + s[(size_t)y1 * w + x1] + 2) >> 2);
+                }
+        }
+    } else { /* yuv422p */
+        for (int pl = 0; pl < 2; pl++) {
+            const uint8_t* s = src + (size_t)w * h + (size_t)pl * cw * h;
+            uint8_t* d = pl ? V : U;
+            for (int y = 0; y < ch; y++)
+                for (int x = 0; x < cw; x++) {
+                    int y1 = 2 * y + 1 < h ? 2 * y + 1 : h - 1;
+                    d[(size_t)y * cw + x] = (uint8_t)((s[(size_t)2 * y * cw + x] + s[(size_t)y1 * cw + x] + 1) >> 1);
+                }
+        }
+    }
+}
+static void scale_plane(const uint8_t* s, int sw, int sh, uint8_t* d, int dw, int dh) {
+    for (int y = 0; y < dh; y++) {
+        long long py = vcp_scale_pos(y, sh, dh);
+        int y0 = (int)(py >> 16), fy = (int)((py & 0xffff) >> 8), y1 = y0 + 1 < sh ? y0 + 1 : sh - 1;
+        for (int x = 0; x < dw; x++) {
+            long long px = vcp_scale_pos(x, sw, dw);
+            int x0 = (int)(px >> 16), fx = (int)((px & 0xffff) >> 8), x1 = x0 + 1 < sw ? x0 + 1 : sw - 1;
+            d[(size_t)y * dw + x] = (uint8_t)vcp_bilerp(s[(size_t)y0 * sw + x0], s[(size_t)y0 * sw + x1],
+                                                        s[(size_t)y1 * sw + x0], s[(size_t)y1 * sw + x1], fx, fy);
+        }
+    }
+}
+static void scale_yuv420p(const uint8_t* s, int sw, int sh, uint8_t* d, int dw, int dh) {
+    int scw = (sw + 1) / 2, sch = (sh + 1) / 2, dcw = (dw + 1) / 2, dch = (dh + 1) / 2;
+    scale_plane(s, sw, sh, d, dw, dh);
+    scale_plane(s + (size_t)sw * sh, scw, sch, d + (size_t)dw * dh, dcw, dch);
+    scale_plane(s + (size_t)sw * sh + (size_t)scw * sch, scw, sch, d + (size_t)dw * dh + (size_t)dcw * dch, dcw, dch);
+}
+
 /* half-resolution luma with border VCP_PAD1, computed from the padded full-res plane */
 typedef struct { int w, h, s; uint8_t* buf; uint8_t* p; } Half;
 static int half_alloc(Half* hf, int w, int h) {
@@ -1015,7 +1091,7 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
     memset(e, 0, sizeof *e);
     e->p = *p;
     if (p->width < 16 || p->height < 16 || (p->width & 1) || (p->height & 1) || p->gop < 1 || p->slices < 1) return VCPENC_E_ARGS;
-    if (p->entropy != 0 || p->codec != VCPENC_CODEC_H264 || p->in_fmt != VCPENC_FMT_YUV420P) return VCPENC_E_ARGS;
+    if (p->entropy != 0 || p->codec != VCPENC_CODEC_H264 || p->in_fmt < 0 || p->in_fmt > VCPENC_FMT_BGR24) return VCPENC_E_ARGS;
     if (p->rc_mode == VCPENC_RC_ABR && p->bitrate <= 0) return VCPENC_E_ARGS;
     e->mbw = (p->width + 15) / 16; e->mbh = (p->height + 15) / 16; e->nmb = e->mbw * e->mbh;
     if (p->slices > e->mbh) return VCPENC_E_ARGS;
@@ -1031,6 +1107,12 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
     if (!e->mbs || !e->mvfp || !e->rbsp) goto done;
 
     size_t fsz = (size_t)p->width * p->height + 2 * (size_t)((p->width + 1) / 2) * ((p->height + 1) / 2);
+    const int iw = p->in_width > 0 ? p->in_width : p->width, ih = p->in_height > 0 ? p->in_height : p->height;
+    const size_t in_fsz = (size_t)vcp_in_frame_bytes(p->in_fmt, iw, ih);
+    const int need_k1 = p->in_fmt != VCPENC_FMT_YUV420P || iw != p->width || ih != p->height;
+    uint8_t* k1_a = need_k1 ? (uint8_t*)malloc((size_t)iw * ih * 3 / 2 + iw + ih + 16) : NULL;
+    uint8_t* k1_b = need_k1 ? (uint8_t*)malloc(fsz + 16) : NULL;
+    if (need_k1 && (!k1_a || !k1_b)) { free(k1_a); free(k1_b); goto done; }
     size_t o = 0;
     int ri = 0, idr_count = p->first_gop;
     /* rate control state of the current GOP (vcp_algo.h) */
@@ -1047,7 +1129,15 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
         }
         /* K1 */
         { Frame tf = e->prev_orig; e->prev_orig = e->cur; e->cur = tf; Half th = e->hprev; e->hprev = e->hcur; e->hcur = th; }
-        frame_load_yuv420p(&e->cur, frames + (size_t)n * fsz, p->width, p->height);
+        {
+            const uint8_t* fin = frames + (size_t)n * in_fsz;
+            if (need_k1) {
+                to_yuv420p(p->in_fmt, fin, iw, ih, k1_a);
+                if (iw != p->width || ih != p->height) { scale_yuv420p(k1_a, iw, ih, k1_b, p->width, p->height); fin = k1_b; }
+                else fin = k1_a;
+            }
+            frame_load_yuv420p(&e->cur, fin, p->width, p->height);
+        }
         half_build(&e->hcur, &e->cur);
         Frame* rec = &e->recon[ri]; const Frame* ref = &e->recon[ri ^ 1];
         if (idr) {
@@ -1116,6 +1206,7 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
     }
     *out_len = o;
     rc = VCPENC_OK;
+    free(k1_a); free(k1_b);
 done:
     frame_free(&e->cur); frame_free(&e->prev_orig); frame_free(&e->recon[0]); frame_free(&e->recon[1]);
     free(e->hcur.buf); free(e->hprev.buf); free(e->mbs); free(e->mvfp); free(e->rbsp);

@@ -71,16 +71,25 @@ def frame_bytes(w, h):
     return w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)
 
 
+def in_frame_bytes(p) -> int:
+    w = p.in_width if p.in_width > 0 else p.width
+    h = p.in_height if p.in_height > 0 else p.height
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    return {0: w * h + 2 * cw * ch, 1: w * h + 2 * cw * ch, 2: 3 * w * h, 3: 3 * w * h,
+            4: w * h + 2 * cw * h, 5: 3 * w * h}[p.in_fmt]
+
+
 def encode(params: Params, frames: np.ndarray, want_recon=True, want_dump=False):
-    """frames: uint8 array [n, frame_bytes] (yuv420p, display size).
+    """frames: uint8 array [n, input frame bytes] (params.in_fmt at the input size; yuv420p at
+    the display size by default).
 
     Returns dict(stream=bytes, info=[(offset,size,is_idr,qp)], recon=np.ndarray|None, dump=dict|None).
     """
     L = lib()
     frames = np.ascontiguousarray(frames, dtype=np.uint8)
-    n = frames.shape[0]
     fb = frame_bytes(params.width, params.height)
-    assert frames.size == n * fb
+    n = frames.size // in_frame_bytes(params)
+    assert frames.size == n * in_frame_bytes(params)
     cap = n * fb + (1 << 16)
     out = np.empty(cap, dtype=np.uint8)
     out_len = C.c_size_t(0)

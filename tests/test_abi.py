@@ -68,6 +68,10 @@ def test_parse_reference_presets(built):
     p = api.parse_args("-c:v libx264 -qp 30 -g 30 -slices 4 -coder 0 -bf 0 -r 60000/1001".split())
     assert (p.qp_p, p.gop, p.slices, p.entropy, p.fps_num, p.fps_den) == (30, 30, 4, 0, 60000, 1001)
     assert api.parse_args([]).codec == 0                    # empty ffmpeg_args is legal (consumer.go:377)
+    p = api.parse_args("-c:v libx264 -vf scale=1280:-2 -crf 20".split())
+    assert (p.width, p.height) == (1280, -2)
+    with pytest.raises(api.VcpencError):
+        api.parse_args("-vf hflip".split())
 
 
 @pytest.mark.skipif(api.lib().vcpenc_device_count() > 0, reason="CPU-only behaviour")

@@ -98,6 +98,23 @@ def test_bitrate_mode_equals_oracle(built):
         assert np.array_equal(got["recon"], ref["recon"])
 
 
+@pytest.mark.parametrize("fmt", [1, 2, 3, 4, 5])
+def test_k1_input_formats_equal_oracle(built, fmt):
+    """K1 front stages (nv12 / rgb24 / yuv444p / yuv422p / bgr24, with and without scaling)."""
+    from oracle import pyoracle
+    rng = np.random.default_rng(100 + fmt)
+    for (iw, ih, ow, oh) in ((96, 64, 96, 64), (130, 98, 64, 48), (64, 48, 208, 114)):
+        kw = dict(gop=2, in_fmt=fmt, in_width=iw, in_height=ih)
+        nb = api.in_frame_bytes(api.default_params(ow, oh, **kw))
+        # smooth content plus noise so that both prediction paths are exercised
+        base = np.linspace(30, 220, nb)[None, :] + rng.integers(-20, 21, (3, nb))
+        frames = np.clip(base, 0, 255).astype(np.uint8)
+        ref = pyoracle.encode(pyoracle.make_params(ow, oh, **kw), frames)
+        got = api.encode_frames(api.default_params(ow, oh, **kw), frames, want_recon=True)
+        assert got["stream"].tobytes() == ref["stream"], (fmt, iw, ih, ow, oh)
+        assert np.array_equal(got["recon"], ref["recon"])
+
+
 def test_edge_cases(built):
     from oracle import pyoracle
     # smallest picture, one frame; GOP 1; one slice per macroblock row; ragged last GOP
@@ -162,6 +179,26 @@ def test_transcode_drop_in(built, tmp_path):
     pr = subprocess.run([os.path.join(libdir, "vcp-ffprobe"), "-v", "error", "-select_streams", "v:0", "-show_entries",
                          "stream=codec_type", "-of", "csv=p=0", str(out2)], capture_output=True)
     assert pr.returncode == 0 and b"video" in pr.stdout
+    # K1 through the front door: a 4:4:4 y4m scaled down with -vf scale, and headerless rgb24 with -s
+    y444 = tmp_path / "in444.y4m"
+    with open(y444, "wb") as f:
+        f.write(b"YUV4MPEG2 W%d H%d F30:1 Ip A1:1 C444\n" % (w, h))
+        for fr in clip[:6]:
+            y, u, v = synth.split_planes(fr, w, h)
+            up = lambda c: np.repeat(np.repeat(c, 2, 0), 2, 1)
+            f.write(b"FRAME\n" + y.tobytes() + up(u).tobytes() + up(v).tobytes())
+    out4 = tmp_path / "out4.mp4"
+    api.transcode(str(y444), str(out4), "-c:v libx264 -crf 23 -vf scale=320:-2 -g 3")
+    api.verify(str(out4))
+    if arbiter.available():
+        dec = arbiter.decode_file(str(out4))
+        assert len(dec) == 6 and dec[0][0].shape == (180, 320)
+    rgb = tmp_path / "in.rgb"
+    rgb.write_bytes(np.random.default_rng(2).integers(0, 256, 4 * 64 * 48 * 3, dtype=np.uint8).tobytes())
+    out5 = tmp_path / "out5.h264"
+    api.transcode(str(rgb), str(out5), "-c:v libx264 -qp 30 -s 64x48")
+    if arbiter.available():
+        assert len(arbiter.decode_annexb(out5.read_bytes())) == 4
     # failure semantics: unknown container -> error class, no output left behind
     bad = tmp_path / "in.mkv"
     bad.write_bytes(b"\x1a\x45\xdf\xa3junk")

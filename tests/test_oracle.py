@@ -183,3 +183,75 @@ def test_oracle_bitrate_mode():
                 assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i])
     assert sizes[1_600_000] > 2.0 * sizes[400_000]
     assert 0.6 * 1_600_000 < sizes[1_600_000] < 1.5 * 1_600_000
+
+
+# ---- K1: other input formats and scaling (vcp_algo.h: vcp_rgb_*, vcp_scale_pos, vcp_bilerp) ----
+def _k1_inputs(clip, w, h):
+    """The same yuv420p content re-expressed in formats whose conversion back is lossless."""
+    cw, ch = w // 2, h // 2
+    out = {}
+    nv12, p444, p422 = [], [], []
+    for fr in clip:
+        y, u, v = synth.split_planes(fr, w, h)
+        nv12.append(np.concatenate([y.ravel(), np.stack([u, v], -1).ravel()]))
+        up = lambda c: np.repeat(np.repeat(c, 2, 0), 2, 1)
+        p444.append(np.concatenate([y.ravel(), up(u).ravel(), up(v).ravel()]))
+        p422.append(np.concatenate([y.ravel(), np.repeat(u, 2, 0).ravel(), np.repeat(v, 2, 0).ravel()]))
+    out[1] = np.stack(nv12); out[3] = np.stack(p444); out[4] = np.stack(p422)
+    return out
+
+
+def test_k1_formats_lossless_roundtrip():
+    w, h, n = 96, 64, 3
+    clip = synth.make_clip(w, h, n, seed=21)
+    base = pyoracle.encode(pyoracle.make_params(w, h, gop=2), clip)
+    for fmt, frames in _k1_inputs(clip, w, h).items():
+        got = pyoracle.encode(pyoracle.make_params(w, h, gop=2, in_fmt=fmt), frames)
+        assert got["stream"] == base["stream"], fmt
+
+
+def test_k1_rgb_known_answers():
+    """BT.601 limited range, 8-bit fixed point: grey -> Y = 16 + ((220 v + 128) >> 8), U = V = 128;
+    primaries hit the textbook values; bgr24 is rgb24 with the channels swapped."""
+    w, h = 32, 32
+    p = pyoracle.make_params(w, h, gop=1, qp_i=8, qp_p=8, in_fmt=2)   # (QP<4 clamps |level| to the CAVLC escape range)
+    for v in (0, 1, 127, 200, 255):
+        rgb = np.full((1, w * h * 3), v, np.uint8)
+        rec = pyoracle.encode(p, rgb)["recon"][0]
+        y, u, vv = synth.split_planes(rec, w, h)
+        assert abs(int(y[8, 8]) - (16 + ((220 * v + 128) >> 8))) <= 1 and abs(int(u[4, 4]) - 128) <= 1 and abs(int(vv[4, 4]) - 128) <= 1
+    red = np.tile(np.array([255, 0, 0], np.uint8), w * h)[None]
+    rec = pyoracle.encode(p, red)["recon"][0]
+    y, u, vv = synth.split_planes(rec, w, h)
+    assert abs(int(y[8, 8]) - 82) <= 1 and abs(int(u[4, 4]) - 90) <= 1 and abs(int(vv[4, 4]) - 240) <= 1
+    rng = np.random.default_rng(5)
+    rgb = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    a = pyoracle.encode(pyoracle.make_params(w, h, gop=2, in_fmt=2), rgb.reshape(2, -1))
+    b = pyoracle.encode(pyoracle.make_params(w, h, gop=2, in_fmt=5), rgb[..., ::-1].reshape(2, -1))
+    assert a["stream"] == b["stream"]
+
+
+def test_k1_scale():
+    """Scaling: identity when the sizes agree, constant pictures stay constant, the decoder still
+    reproduces the reconstruction, and a 2:1 reduction of a linear ramp stays a linear ramp."""
+    w, h = 128, 96
+    clip = synth.make_clip(w, h, 2, seed=4)
+    a = pyoracle.encode(pyoracle.make_params(w, h, gop=2), clip)
+    b = pyoracle.encode(pyoracle.make_params(w, h, gop=2, in_width=w, in_height=h), clip)
+    assert a["stream"] == b["stream"]
+    for (dw, dh) in ((64, 48), (208, 114), (96, 96)):
+        p = pyoracle.make_params(dw, dh, gop=2, in_width=w, in_height=h)
+        got = pyoracle.encode(p, clip)
+        if arbiter.available():
+            dec = arbiter.decode_annexb(got["stream"])
+            for i in range(2):
+                assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), got["recon"][i])
+    flat = np.full((1, w * h * 3 // 2), 77, np.uint8)
+    rec = pyoracle.encode(pyoracle.make_params(48, 32, gop=1, qp_i=8, qp_p=8, in_width=w, in_height=h), flat)["recon"][0]
+    assert np.abs(rec.astype(int) - 77).max() <= 1
+    ramp = np.empty((1, w * h * 3 // 2), np.uint8)
+    ramp[0, : w * h] = np.tile(np.arange(w, dtype=np.uint8) + 20, h)
+    ramp[0, w * h:] = 128
+    rec = pyoracle.encode(pyoracle.make_params(64, 48, gop=1, qp_i=8, qp_p=8, in_width=w, in_height=h), ramp)["recon"][0]
+    y = rec[: 64 * 48].reshape(48, 64).astype(int)
+    assert np.abs(y[10] - (2 * np.arange(64) + 20.5)).max() <= 1.5

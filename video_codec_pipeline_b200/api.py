@@ -106,6 +106,15 @@ def frame_bytes(w, h):
     return w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)
 
 
+def in_frame_bytes(p) -> int:
+    """Bytes of one INPUT frame (p.in_fmt at p.in_width x p.in_height; vcp_in_frame_bytes)."""
+    w = p.in_width if p.in_width > 0 else p.width
+    h = p.in_height if p.in_height > 0 else p.height
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    return {0: w * h + 2 * cw * ch, 1: w * h + 2 * cw * ch, 2: 3 * w * h, 3: 3 * w * h,
+            4: w * h + 2 * cw * h, 5: 3 * w * h}[p.in_fmt]
+
+
 def _ptr(a):
     if a is None:
         return None
@@ -128,7 +137,7 @@ def encode_frames(params: Params, frames, nframes=None, device=0, want_recon=Fal
     fb = frame_bytes(params.width, params.height)
     if isinstance(frames, np.ndarray):
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
-        nframes = frames.size // fb
+        nframes = frames.size // in_frame_bytes(params)
     cap = nframes * fb + (1 << 20)
     if out is None:
         out = np.empty(cap, np.uint8)
@@ -167,7 +176,7 @@ class Session:
     def upload(self, frames, nframes=None):
         if isinstance(frames, np.ndarray):
             frames = np.ascontiguousarray(frames, dtype=np.uint8)
-            nframes = frames.size // self.fb
+            nframes = frames.size // in_frame_bytes(self.params)
         self._keep = frames
         self._ck(self.L.vcpenc_session_upload(self.h, _ptr(frames), nframes, self.err, 512))
         self.nframes = nframes

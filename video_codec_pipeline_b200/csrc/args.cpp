@@ -147,6 +147,16 @@ extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_param
             int w = 0, h = 0;
             if (sscanf(v, "%dx%d", &w, &h) != 2 || w <= 0 || h <= 0) { set_err(err, errlen, "bad size '%s'", v); return VCPENC_E_ARGS; }
             p->in_width = w; p->in_height = h;
+        } else if (t == "-vf" || t == "-filter:v") {
+            // only the filter the presets could need: scale=W:H (-1 / -2 keep the aspect ratio;
+            // resolved against the input size by vcpenc_transcode)
+            if (!need(&v)) return VCPENC_E_ARGS;
+            int w = 0, h = 0;
+            if (sscanf(v, "scale=%d:%d", &w, &h) != 2 || w == 0 || h == 0 || w < -2 || h < -2 || (w < 0 && h < 0)) {
+                set_err(err, errlen, "unsupported filter '%s' (scale=W:H only)", v);
+                return VCPENC_E_ARGS;
+            }
+            p->width = w; p->height = h;
         } else if (t == "-pix_fmt") {
             if (!need(&v)) return VCPENC_E_ARGS;
             if (strcmp(v, "yuv420p")) { set_err(err, errlen, "output pix_fmt '%s' unsupported (yuv420p only)", v); return VCPENC_E_ARGS; }

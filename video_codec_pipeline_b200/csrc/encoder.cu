@@ -67,6 +67,10 @@ struct vcpenc_session {
     int ngroups = 4;
     std::vector<void*> allocs;
     uint8_t* staging[2] = {nullptr, nullptr};
+    // K1 front stages (other pixel formats, scaling): scratch pictures of staging_frames each
+    int in_w = 0, in_h = 0; size_t in_fb = 0;
+    bool need_conv = false, need_scale = false;
+    uint8_t *norm_a = nullptr, *norm_b = nullptr;
     cudaEvent_t staging_free[2] = {nullptr, nullptr}, staging_ready[2] = {nullptr, nullptr};
     int staging_frames = 0;
     // debug taps
@@ -106,7 +110,8 @@ int check_params(const vcpenc_params& p, char* err, size_t errlen) {
     if (p.width < 16 || p.height < 16 || (p.width & 1) || (p.height & 1)) { set_err(err, errlen, "unsupported picture size %dx%d", p.width, p.height); return VCPENC_E_ARGS; }
     if (p.gop < 1 || p.slices < 1 || p.slices > (p.height + 15) / 16) { set_err(err, errlen, "bad gop/slices"); return VCPENC_E_ARGS; }
     if (p.qp_i < 0 || p.qp_i > 51 || p.qp_p < 0 || p.qp_p > 51) { set_err(err, errlen, "qp out of range"); return VCPENC_E_ARGS; }
-    if (p.in_fmt != VCPENC_FMT_YUV420P) { set_err(err, errlen, "input pixel format %d not implemented", p.in_fmt); return VCPENC_E_FORMAT; }
+    if (p.in_fmt < VCPENC_FMT_YUV420P || p.in_fmt > VCPENC_FMT_BGR24) { set_err(err, errlen, "input pixel format %d not implemented", p.in_fmt); return VCPENC_E_FORMAT; }
+    if (p.in_width < 0 || p.in_height < 0 || (p.in_width > 0) != (p.in_height > 0)) { set_err(err, errlen, "bad input size %dx%d", p.in_width, p.in_height); return VCPENC_E_ARGS; }
     if (p.deblock_idc < 0 || p.deblock_idc > 2) { set_err(err, errlen, "bad deblock_idc"); return VCPENC_E_ARGS; }
     if (p.rc_mode == VCPENC_RC_ABR && (p.bitrate <= 0 || p.fps_num <= 0 || p.fps_den <= 0)) { set_err(err, errlen, "bitrate mode needs -b:v and a frame rate"); return VCPENC_E_ARGS; }
     return VCPENC_OK;
@@ -146,6 +151,29 @@ void collect_profile(vcpenc_session* s) {
         s->stats[s->events[i].kind].launches++;
     }
     s->events_used = 0;
+}
+
+// K1 over `cnt` raw frames already in device memory at `din` -> padded planes of frames n0..
+// Other pixel formats / sizes go through the scratch pictures, staging_frames at a time.
+void k1_chain(vcpenc_session* s, const uint8_t* din, int n0, int cnt, cudaStream_t st) {
+    const size_t fb = frame_bytes_of(s->p);
+    if (!s->need_conv) {
+        Prof pr(s, VCPENC_K_CSC, 1, st);
+        vcp_launch_k1_yuv420p(din, fb, n0, cnt, s->g, s->b, st);
+        return;
+    }
+    const size_t afb = (size_t)vcp_in_frame_bytes(VCPENC_FMT_YUV420P, s->in_w, s->in_h);
+    for (int i = 0; i < cnt; i += s->staging_frames) {
+        const int k = std::min(s->staging_frames, cnt - i);
+        Prof pr(s, VCPENC_K_CSC, s->need_scale ? 3 : 2, st);
+        vcp_launch_k1_to_yuv420p(din + (size_t)i * s->in_fb, s->in_fb, s->p.in_fmt, s->in_w, s->in_h, s->norm_a, afb, k, st);
+        const uint8_t* tight = s->norm_a;
+        if (s->need_scale) {
+            vcp_launch_k1_scale(s->norm_a, afb, s->in_w, s->in_h, s->norm_b, fb, s->p.width, s->p.height, k, st);
+            tight = s->norm_b;
+        }
+        vcp_launch_k1_yuv420p(tight, fb, n0 + i, k, s->g, s->b, st);
+    }
 }
 
 }  // namespace
@@ -295,8 +323,15 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     }
     // upload staging: two buffers of up to 16 frames
     s->staging_frames = std::max(1, std::min(16, max_frames));
+    s->in_w = pp->in_width > 0 ? pp->in_width : pp->width;
+    s->in_h = pp->in_height > 0 ? pp->in_height : pp->height;
+    s->in_fb = (size_t)vcp_in_frame_bytes(pp->in_fmt, s->in_w, s->in_h);
+    s->need_scale = s->in_w != pp->width || s->in_h != pp->height;
+    s->need_conv = pp->in_fmt != VCPENC_FMT_YUV420P || s->need_scale;
+    if (s->need_conv) TRY(dev_alloc(s, &s->norm_a, (size_t)s->staging_frames * vcp_in_frame_bytes(VCPENC_FMT_YUV420P, s->in_w, s->in_h), err, errlen));
+    if (s->need_scale) TRY(dev_alloc(s, &s->norm_b, (size_t)s->staging_frames * frame_bytes_of(*pp), err, errlen));
     for (int i = 0; i < 2; i++) {
-        TRY(dev_alloc(s, &s->staging[i], (size_t)s->staging_frames * frame_bytes_of(*pp), err, errlen));
+        TRY(dev_alloc(s, &s->staging[i], (size_t)s->staging_frames * s->in_fb, err, errlen));
         CKS(cudaEventCreateWithFlags(&s->staging_free[i], cudaEventDisableTiming));
         CKS(cudaEventCreateWithFlags(&s->staging_ready[i], cudaEventDisableTiming));
     }
@@ -324,7 +359,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
 int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes, char* err, size_t errlen) {
     if (!s || !frames || nframes < 1 || nframes > s->max_frames) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
     CK(cudaSetDevice(s->device));
-    const size_t fb = frame_bytes_of(s->p);
+    const size_t fb = s->in_fb;
     s->nframes = nframes;
     s->encoded = false;
     s->h_qp.resize(nframes);
@@ -338,10 +373,7 @@ int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes,
         CK(cudaMemcpyAsync(s->staging[k], frames + (size_t)n0 * fb, (size_t)cnt * fb, cudaMemcpyHostToDevice, s->st_copy));
         CK(cudaEventRecord(s->staging_ready[k], s->st_copy));
         CK(cudaStreamWaitEvent(s->st, s->staging_ready[k], 0));
-        {
-            Prof pr(s, VCPENC_K_CSC);
-            vcp_launch_k1_yuv420p(s->staging[k], fb, n0, cnt, s->g, s->b, s->st);
-        }
+        k1_chain(s, s->staging[k], n0, cnt, s->st);
         CK(cudaEventRecord(s->staging_free[k], s->st));
     }
     CK(cudaGetLastError());
@@ -353,17 +385,15 @@ int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes,
 int vcpenc_session_upload_device(vcpenc_session* s, const uint8_t* dframes, int nframes, float* ms, char* err, size_t errlen) {
     if (!s || !dframes || nframes < 1 || nframes > s->max_frames) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
     CK(cudaSetDevice(s->device));
-    const size_t fb = frame_bytes_of(s->p);
+    const size_t fb = s->in_fb;
     s->nframes = nframes;
     s->encoded = false;
     s->h_qp.resize(nframes);
     for (int n = 0; n < nframes; n++) s->h_qp[n] = initial_qp(s, n);
     CK(cudaMemcpyAsync(s->b.qp, s->h_qp.data(), nframes, cudaMemcpyHostToDevice, s->st));
     CK(cudaEventRecord(s->ev0, s->st));
-    for (int n0 = 0; n0 < nframes; n0 += 4096) {
-        Prof pr(s, VCPENC_K_CSC);
-        vcp_launch_k1_yuv420p(dframes + (size_t)n0 * fb, fb, n0, std::min(4096, nframes - n0), s->g, s->b, s->st);
-    }
+    for (int n0 = 0; n0 < nframes; n0 += 4096)
+        k1_chain(s, dframes + (size_t)n0 * fb, n0, std::min(4096, nframes - n0), s->st);
     CK(cudaEventRecord(s->ev1, s->st));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s->st));
@@ -583,12 +613,13 @@ int vcpenc_encode_frames(const vcpenc_params* p, int device, const uint8_t* fram
     int rc = vcpenc_session_create(&q, device, std::min(chunk, nframes), &s, err, errlen);
     if (rc) return rc;
     const size_t fb = frame_bytes_of(q);
+    const size_t in_fb = (size_t)vcp_in_frame_bytes(q.in_fmt, q.in_width > 0 ? q.in_width : q.width, q.in_height > 0 ? q.in_height : q.height);
     size_t o = 0;
     for (int n0 = 0; n0 < nframes && !rc; n0 += chunk) {
         if (cancel && *cancel) { set_err(err, errlen, "任务被取消"); rc = VCPENC_E_CANCELLED; break; }
         const int cnt = std::min(chunk, nframes - n0);
         s->gop_base = q.first_gop + n0 / q.gop;
-        rc = vcpenc_session_upload(s, frames + (size_t)n0 * fb, cnt, err, errlen);
+        rc = vcpenc_session_upload(s, frames + (size_t)n0 * in_fb, cnt, err, errlen);
         if (!rc) rc = vcpenc_session_encode(s, nullptr, err, errlen);
         size_t len = 0;
         if (!rc) rc = vcpenc_session_download(s, out + o, out_cap - o, &len, info ? info + n0 : nullptr,

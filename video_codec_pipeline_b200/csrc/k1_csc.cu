@@ -8,6 +8,7 @@
 //
 // Algorithmic bytes per frame (yuv420p in): read 1.5*W*H + write 1.5*W*H; the
 // half-res plane and the borders are extra (~ +20 %) and are counted as overhead.
+#include "../../include/vcpenc.h"
 #include "vcp_dev.cuh"
 
 namespace {
@@ -89,6 +90,100 @@ __global__ void __launch_bounds__(64) k1_yuv420p_kernel(const uint8_t* __restric
     }
 }
 
+
+// ---- other input formats and scaling ---------------------------------------------------------
+// Two optional front stages normalise what ffmpeg's auto-inserted swscale would: any accepted
+// pixel format -> tight yuv420p of the input size, then bilinear resampling to the output size.
+// Both restate vcp_algo.h (vcp_rgb_*, vcp_scale_pos, vcp_bilerp) so the oracle computes the
+// same bytes.  They write a scratch picture that the layout kernel above then pads; yuv420p at
+// the output size (the north-star case) skips both.
+
+// thread = one chroma sample = one 2x2 luma quad; grid z = frame
+__global__ void __launch_bounds__(128) k1_to_yuv420p_kernel(const uint8_t* __restrict__ in, size_t in_fb, int fmt,
+                                                            int w, int h, uint8_t* __restrict__ out, size_t out_fb) {
+    const int cw = (w + 1) >> 1, chh = (h + 1) >> 1;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cw || y >= chh) return;
+    const uint8_t* f = in + (size_t)blockIdx.z * in_fb;
+    uint8_t* Y = out + (size_t)blockIdx.z * out_fb;
+    uint8_t* U = Y + (size_t)w * h;
+    uint8_t* V = U + (size_t)cw * chh;
+    const int x0 = 2 * x, y0 = 2 * y;
+    const int x1 = x0 + 1 < w ? x0 + 1 : w - 1, y1 = y0 + 1 < h ? y0 + 1 : h - 1;
+    const bool hx = x0 + 1 < w, hy = y0 + 1 < h;
+    const size_t wh = (size_t)w * h;
+    if (fmt == VCPENC_FMT_RGB24 || fmt == VCPENC_FMT_BGR24) {
+        const int ro = fmt == VCPENC_FMT_RGB24 ? 0 : 2, bo = 2 - ro;
+        int r = 0, gsum = 0, bsum = 0;
+#pragma unroll
+        for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 2; dx++) {
+                const int xx = dx ? x1 : x0, yy = dy ? y1 : y0;
+                const uint8_t* p = f + ((size_t)yy * w + xx) * 3;
+                const int R = __ldg(p + ro), G = __ldg(p + 1), B = __ldg(p + bo);
+                r += R; gsum += G; bsum += B;
+                if ((!dx || hx) && (!dy || hy)) Y[(size_t)yy * w + xx] = (uint8_t)vcp_rgb_y(R, G, B);
+            }
+        r = (r + 2) >> 2; gsum = (gsum + 2) >> 2; bsum = (bsum + 2) >> 2;
+        U[(size_t)y * cw + x] = (uint8_t)vcp_rgb_u(r, gsum, bsum);
+        V[(size_t)y * cw + x] = (uint8_t)vcp_rgb_v(r, gsum, bsum);
+        return;
+    }
+    // planar / semi-planar: luma is a copy
+    Y[(size_t)y0 * w + x0] = __ldg(f + (size_t)y0 * w + x0);
+    if (hx) Y[(size_t)y0 * w + x1] = __ldg(f + (size_t)y0 * w + x1);
+    if (hy) {
+        Y[(size_t)y1 * w + x0] = __ldg(f + (size_t)y1 * w + x0);
+        if (hx) Y[(size_t)y1 * w + x1] = __ldg(f + (size_t)y1 * w + x1);
+    }
+    if (fmt == VCPENC_FMT_NV12) {
+        const uint8_t* uv = f + wh + ((size_t)y * cw + x) * 2;
+        U[(size_t)y * cw + x] = __ldg(uv);
+        V[(size_t)y * cw + x] = __ldg(uv + 1);
+    } else if (fmt == VCPENC_FMT_YUV444P) {
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            const uint8_t* s = f + wh * (1 + pl);
+            const int v = (__ldg(s + (size_t)y0 * w + x0) + __ldg(s + (size_t)y0 * w + x1) + __ldg(s + (size_t)y1 * w + x0) +
+                           __ldg(s + (size_t)y1 * w + x1) + 2) >> 2;
+            (pl ? V : U)[(size_t)y * cw + x] = (uint8_t)v;
+        }
+    } else if (fmt == VCPENC_FMT_YUV422P) {
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            const uint8_t* s = f + wh + (size_t)pl * cw * h;
+            const int v = (__ldg(s + (size_t)y0 * cw + x) + __ldg(s + (size_t)y1 * cw + x) + 1) >> 1;
+            (pl ? V : U)[(size_t)y * cw + x] = (uint8_t)v;
+        }
+    } else {  // yuv420p
+        U[(size_t)y * cw + x] = __ldg(f + wh + (size_t)y * cw + x);
+        V[(size_t)y * cw + x] = __ldg(f + wh + (size_t)cw * chh + (size_t)y * cw + x);
+    }
+}
+
+// bilinear resample of tight yuv420p; thread = one output sample, grid y = rows of Y then U then V
+__global__ void __launch_bounds__(128) k1_scale_kernel(const uint8_t* __restrict__ in, size_t in_fb, int sw, int sh,
+                                                       uint8_t* __restrict__ out, size_t out_fb, int dw, int dh) {
+    const int scw = (sw + 1) >> 1, sch = (sh + 1) >> 1, dcw = (dw + 1) >> 1, dch = (dh + 1) >> 1;
+    int row = blockIdx.y;
+    const uint8_t* s = in + (size_t)blockIdx.z * in_fb;
+    uint8_t* d = out + (size_t)blockIdx.z * out_fb;
+    int pw = sw, ph = sh, qw = dw, qh = dh;
+    if (row >= dh) {
+        row -= dh; s += (size_t)sw * sh; d += (size_t)dw * dh;
+        pw = scw; ph = sch; qw = dcw; qh = dch;
+        if (row >= dch) { row -= dch; s += (size_t)scw * sch; d += (size_t)dcw * dch; }
+    }
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= qw) return;
+    const long long py = vcp_scale_pos(row, ph, qh), px = vcp_scale_pos(x, pw, qw);
+    const int yy0 = (int)(py >> 16), fy = (int)((py & 0xffff) >> 8), yy1 = yy0 + 1 < ph ? yy0 + 1 : ph - 1;
+    const int xx0 = (int)(px >> 16), fx = (int)((px & 0xffff) >> 8), xx1 = xx0 + 1 < pw ? xx0 + 1 : pw - 1;
+    d[(size_t)row * qw + x] = (uint8_t)vcp_bilerp(__ldg(s + (size_t)yy0 * pw + xx0), __ldg(s + (size_t)yy0 * pw + xx1),
+                                                  __ldg(s + (size_t)yy1 * pw + xx0), __ldg(s + (size_t)yy1 * pw + xx1), fx, fy);
+}
+
 }  // namespace
 
 void vcp_launch_k1_yuv420p(const uint8_t* in, size_t frame_bytes, int n0, int n, const VcpGeom& g,
@@ -97,4 +192,19 @@ void vcp_launch_k1_yuv420p(const uint8_t* in, size_t frame_bytes, int n0, int n,
     int tiles = g.ys / 32;
     dim3 grid((tiles + 63) / 64, (g.ch + 2 * VCP_PAD) / 2, n);
     k1_yuv420p_kernel<<<grid, 64, 0, st>>>(in, frame_bytes, n0, g, b);
+}
+
+void vcp_launch_k1_to_yuv420p(const uint8_t* in, size_t in_fb, int fmt, int w, int h, uint8_t* out, size_t out_fb, int n,
+                              cudaStream_t st) {
+    if (n <= 0) return;
+    const int cw = (w + 1) / 2, chh = (h + 1) / 2;
+    dim3 grid((cw + 127) / 128, chh, n);
+    k1_to_yuv420p_kernel<<<grid, 128, 0, st>>>(in, in_fb, fmt, w, h, out, out_fb);
+}
+
+void vcp_launch_k1_scale(const uint8_t* in, size_t in_fb, int sw, int sh, uint8_t* out, size_t out_fb, int dw, int dh,
+                         int n, cudaStream_t st) {
+    if (n <= 0) return;
+    dim3 grid((dw + 127) / 128, dh + 2 * ((dh + 1) / 2), n);
+    k1_scale_kernel<<<grid, 128, 0, st>>>(in, in_fb, sw, sh, out, out_fb, dw, dh);
 }

@@ -18,6 +18,8 @@
 
 #include "host_bits.h"
 #include "host_util.h"
+#include "vcp_algo.h"
+#include <sys/stat.h>
 
 using namespace vcp;
 
@@ -26,7 +28,9 @@ namespace {
 struct FrameSource {
     virtual ~FrameSource() {}
     int width = 0, height = 0, fps_num = 0, fps_den = 1;
-    // read up to `max` frames (tight yuv420p) into dst; returns frames read, <0 on error
+    int fmt = VCPENC_FMT_YUV420P;
+    size_t fbytes() const { return (size_t)vcp_in_frame_bytes(fmt, width, height); }
+    // read up to `max` frames (tight, `fmt`) into dst; returns frames read, <0 on error
     virtual int read(uint8_t* dst, int max, char* err, size_t errlen) = 0;
 };
 
@@ -49,15 +53,19 @@ struct Y4mSource : FrameSource {
             else if (t[0] == 'C') cs = t + 1;
             else if (t[0] == 'I' && t[1] != 'p' && t[1] != '?') { set_err(err, errlen, "interlaced y4m not supported"); return VCPENC_E_FORMAT; }
         }
-        if (cs.compare(0, 3, "420") != 0 || cs.find("p10") != std::string::npos || cs.find("p12") != std::string::npos) {
-            set_err(err, errlen, "y4m colourspace C%s not supported (8-bit 4:2:0 only)", cs.c_str());
+        const bool deep = cs.find("p10") != std::string::npos || cs.find("p12") != std::string::npos || cs.find("p16") != std::string::npos;
+        if (!deep && cs.compare(0, 3, "420") == 0) fmt = VCPENC_FMT_YUV420P;
+        else if (!deep && cs == "422") fmt = VCPENC_FMT_YUV422P;
+        else if (!deep && cs == "444") fmt = VCPENC_FMT_YUV444P;
+        else {
+            set_err(err, errlen, "y4m colourspace C%s not supported (8-bit 4:2:0 / 4:2:2 / 4:4:4 only)", cs.c_str());
             return VCPENC_E_FORMAT;
         }
         if (width <= 0 || height <= 0) { set_err(err, errlen, "bad y4m header"); return VCPENC_E_FORMAT; }
         return VCPENC_OK;
     }
     int read(uint8_t* dst, int max, char* err, size_t errlen) override {
-        const size_t fb = fbytes(width, height);
+        const size_t fb = fbytes();
         int n = 0;
         while (n < max) {
             char line[128];
@@ -73,15 +81,16 @@ struct Y4mSource : FrameSource {
 struct RawSource : FrameSource {
     FILE* f = nullptr;
     ~RawSource() override { if (f) fclose(f); }
-    int open(const char* path, const vcpenc_params& p, char* err, size_t errlen) {
-        if (p.in_width <= 0 || p.in_height <= 0) { set_err(err, errlen, "raw .yuv input needs -s WxH"); return VCPENC_E_FORMAT; }
+    int open(const char* path, const vcpenc_params& p, int pixfmt, char* err, size_t errlen) {
+        if (p.in_width <= 0 || p.in_height <= 0) { set_err(err, errlen, "raw input needs -s WxH"); return VCPENC_E_FORMAT; }
+        fmt = pixfmt;
         width = p.in_width; height = p.in_height; fps_num = p.fps_num; fps_den = p.fps_den;
         f = fopen(path, "rb");
         if (!f) { set_err(err, errlen, "cannot open %s", path); return VCPENC_E_IO; }
         return VCPENC_OK;
     }
     int read(uint8_t* dst, int max, char*, size_t) override {
-        const size_t fb = fbytes(width, height);
+        const size_t fb = fbytes();
         int n = 0;
         while (n < max && fread(dst + (size_t)n * fb, 1, fb, f) == fb) n++;
         return n;
@@ -120,25 +129,44 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
         rc = s->open(input, err, errlen);
         if (rc) return rc;
         src = std::move(s);
-    } else if (ends_with(in, ".yuv")) {
+    } else if (ends_with(in, ".yuv") || ends_with(in, ".nv12") || ends_with(in, ".rgb") || ends_with(in, ".bgr")) {
+        // headerless frames: the size comes from -s WxH, the pixel format from the extension
+        const int pf = ends_with(in, ".nv12") ? VCPENC_FMT_NV12 : ends_with(in, ".rgb") ? VCPENC_FMT_RGB24
+                     : ends_with(in, ".bgr") ? VCPENC_FMT_BGR24 : VCPENC_FMT_YUV420P;
         auto s = std::make_unique<RawSource>();
-        rc = s->open(input, p, err, errlen);
+        rc = s->open(input, p, pf, err, errlen);
         if (rc) return rc;
         src = std::move(s);
+        p.in_width = p.in_height = 0;   // consumed as the input size
     } else {
         set_err(err, errlen, "input container of '%s' needs the demux/decode front end, which is not built yet (SURVEY 8f1); y4m and raw yuv420p are accepted", input);
         return VCPENC_E_FORMAT;
     }
-    p.width = src->width; p.height = src->height;
-    p.in_width = p.in_height = 0;
+    // output size: -vf scale=W:H (negative = keep aspect, rounded to even), else -s WxH on a
+    // self-describing input, else the input size
+    {
+        int ow = p.width, oh = p.height;
+        if (ow == 0 && oh == 0 && p.in_width > 0) { ow = p.in_width; oh = p.in_height; }
+        if (ow == 0 && oh == 0) { ow = src->width; oh = src->height; }
+        if (ow < 0) ow = (int)(((long long)src->width * oh / src->height + 1) & ~1LL);
+        if (oh < 0) oh = (int)(((long long)src->height * ow / src->width + 1) & ~1LL);
+        p.width = ow; p.height = oh;
+    }
+    p.in_fmt = src->fmt;
+    p.in_width = src->width; p.in_height = src->height;
     p.fps_num = src->fps_num; p.fps_den = src->fps_den;
     if ((p.width & 1) || (p.height & 1) || p.width < 16 || p.height < 16) { set_err(err, errlen, "unsupported picture size %dx%d", p.width, p.height); return VCPENC_E_FORMAT; }
     if (p.slices > (p.height + 15) / 16) p.slices = (p.height + 15) / 16;
 
-    const size_t fb = fbytes(p.width, p.height);
+    const size_t fb = std::max(fbytes(p.width, p.height), src->fbytes());
     // chunk: whole GOPs, at most ~3 GiB of raw frames resident per pass
     int chunk = (int)std::max<size_t>(1, ((size_t)3 << 30) / fb);
-    chunk = std::max(p.gop, chunk / p.gop * p.gop);
+    {   // short clips: do not page-lock more host memory than the file can fill
+        struct stat sb;
+        if (stat(input, &sb) == 0 && sb.st_size > 0)
+            chunk = (int)std::min<size_t>((size_t)chunk, (size_t)sb.st_size / src->fbytes() + 1);
+    }
+    chunk = std::max(p.gop, (chunk + p.gop - 1) / p.gop * p.gop);
     PinnedBuf frames;
     frames.p = (uint8_t*)vcpenc_host_alloc((size_t)chunk * fb);
     if (!frames.p) { set_err(err, errlen, "cannot allocate %zu bytes of pinned host memory", (size_t)chunk * fb); return VCPENC_E_CUDA; }

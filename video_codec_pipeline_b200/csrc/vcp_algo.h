@@ -76,6 +76,32 @@ VCP_HD int vcp_clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi 
 VCP_HD int vcp_clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 VCP_HD int vcp_iabs(int v) { return v < 0 ? -v : v; }
 
+// ---- K1: colour conversion and scaling, integer only ------------------------------------------
+// RGB -> YCbCr: BT.601 limited range (what swscale assumes for untagged RGB), 8-bit fixed point.
+VCP_HD int vcp_rgb_y(int r, int g, int b) { return 16 + ((66 * r + 129 * g + 25 * b + 128) >> 8); }
+VCP_HD int vcp_rgb_u(int r, int g, int b) { return 128 + ((-38 * r - 74 * g + 112 * b + 128) >> 8); }
+VCP_HD int vcp_rgb_v(int r, int g, int b) { return 128 + ((112 * r - 94 * g - 18 * b + 128) >> 8); }
+// Bilinear scaling, centre-aligned sample positions in 16.16 fixed point, 8-bit weights:
+//   pos(d) = (2d+1) * in * 32768 / out - 32768, clamped to [0, (in-1)<<16]
+VCP_HD long long vcp_scale_pos(int d, int in, int out) {
+    long long p = ((long long)(2 * d + 1) * in * 32768) / out - 32768;
+    const long long hi = (long long)(in - 1) << 16;
+    return p < 0 ? 0 : (p > hi ? hi : p);
+}
+VCP_HD int vcp_bilerp(int p00, int p01, int p10, int p11, int fx, int fy) {
+    return ((256 - fx) * (256 - fy) * p00 + fx * (256 - fy) * p01 + (256 - fx) * fy * p10 + fx * fy * p11 + 32768) >> 16;
+}
+// bytes of one input frame in format fmt (VCPENC_FMT_*: 0 yuv420p 1 nv12 2 rgb24 3 yuv444p 4 yuv422p 5 bgr24)
+VCP_HD unsigned long long vcp_in_frame_bytes(int fmt, int w, int h) {
+    const unsigned long long wh = (unsigned long long)w * h, c = (unsigned long long)((w + 1) / 2) * ((h + 1) / 2);
+    switch (fmt) {
+    case 0: case 1: return wh + 2 * c;
+    case 2: case 5: case 3: return 3 * wh;
+    case 4: return wh + 2ull * ((w + 1) / 2) * h;
+    default: return 0;
+    }
+}
+
 // ---- bitrate-targeted rate control (-b:v), integer only ------------------------------------
 // GOPs are encoded independently and in parallel, so each GOP carries its own budget:
 //   budget = bitrate * gop_frames / fps ; the IDR picture is expected to cost VCP_RC_I_WEIGHT
