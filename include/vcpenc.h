@@ -104,7 +104,8 @@ typedef struct vcpenc_frame_info {
 #define VCPENC_K_CAVLC_SCAN 9  /* K5 pass 2: per-slice prefix sums + slice headers  */
 #define VCPENC_K_CAVLC_WRITE 10/* K5 pass 3: bit-exact placement into the RBSP      */
 #define VCPENC_K_RC 11         /* rate-control update                               */
-#define VCPENC_K_COUNT 12
+#define VCPENC_K_HPEL 12       /* K2c half-sample planes of the reconstruction      */
+#define VCPENC_K_COUNT 13
 
 typedef struct vcpenc_kernel_stat {
     double   ms;               /* summed CUDA-event time                            */

@@ -287,7 +287,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     TRY(dev_alloc(s, &b.src_u, N * g.csize, err, errlen));
     TRY(dev_alloc(s, &b.src_v, N * g.csize, err, errlen));
     TRY(dev_alloc(s, &b.src_h, N * g.hsize, err, errlen));
-    TRY(dev_alloc(s, &b.rec_y, G * s->ring * g.ysize, err, errlen));
+    TRY(dev_alloc(s, &b.rec_y, G * s->ring * VCP_REC_PLANES * g.ysize, err, errlen));
     TRY(dev_alloc(s, &b.rec_u, G * s->ring * g.csize, err, errlen));
     TRY(dev_alloc(s, &b.rec_v, G * s->ring * g.csize, err, errlen));
     TRY(dev_alloc(s, &b.mvfp, N * nmb, err, errlen));
@@ -316,6 +316,17 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     TRY(dev_alloc(s, &b.error_flag, (size_t)1, err, errlen));
     TRY(dev_alloc(s, &b.rc_cum, G, err, errlen));
     TRY(dev_alloc(s, &b.db_sync, G * (g.mbh + 1) + 1, err, errlen));
+    {
+        uint32_t* ri = nullptr;
+        TRY(dev_alloc(s, &ri, (size_t)g.mbh, err, errlen));
+        std::vector<uint32_t> h((size_t)g.mbh);
+        for (int r = 0; r < g.mbh; r++) {
+            const int sl = vcp_slice_of_row(r, g.slices, g.mbh);
+            h[r] = (uint32_t)vcp_slice_first_row(sl, g.slices, g.mbh) | ((uint32_t)sl << 16);
+        }
+        CKS(cudaMemcpy(ri, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        b.rowinfo = ri;
+    }
     if (pp->debug) {
         TRY(dev_alloc(s, &s->dbg_mv, N * nmb, err, errlen));
         TRY(dev_alloc(s, &s->dbg_type, N * nmb, err, errlen));
@@ -336,7 +347,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
         CKS(cudaEventCreateWithFlags(&s->staging_ready[i], cudaEventDisableTiming));
     }
     // recon must never hold uninitialised borders when a vector reads them
-    CKS(cudaMemsetAsync(b.rec_y, 128, G * s->ring * g.ysize, s->st));
+    CKS(cudaMemsetAsync(b.rec_y, 128, G * s->ring * VCP_REC_PLANES * g.ysize, s->st));
     CKS(cudaMemsetAsync(b.rec_u, 128, G * s->ring * g.csize, s->st));
     CKS(cudaMemsetAsync(b.rec_v, 128, G * s->ring * g.csize, s->st));
     CKS(cudaMemsetAsync(b.mvfp, 0, N * nmb * sizeof(short2), s->st));
@@ -466,6 +477,8 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
             if (!s->profile) CK(cudaEventRecord(s->ev_ent[k][par], se));
             if (g.deblock_idc != 1) { Prof pr(s, VCPENC_K_DEBLOCK, 1, st); vcp_launch_deblock(g, bt, sp, st); }
             { Prof pr(s, VCPENC_K_PAD, 1, st); vcp_launch_pad(g, bt, sp, st); }
+            // half-sample planes of this reconstruction for the next picture's search and prediction
+            if (t + 1 < gop && t + 1 < N) { Prof pr(s, VCPENC_K_HPEL, 1, st); vcp_launch_hpel(g, bt, sp, st); }
         }
     }
     if (!s->profile)
@@ -551,7 +564,7 @@ int vcpenc_session_download(vcpenc_session* s, uint8_t* out, size_t out_cap, siz
             const int gi = n / s->p.gop, t = n % s->p.gop;
             const size_t slot = (size_t)gi * s->ring + (t % s->ring);
             uint8_t* d = recon + (size_t)n * fb;
-            CK(cudaMemcpy2DAsync(d, w, s->b.rec_y + slot * g.ysize + g.yoff, g.ys, w, h, cudaMemcpyDeviceToHost, s->st));
+            CK(cudaMemcpy2DAsync(d, w, vcp_rec_luma(s->b, g, (int)slot) + g.yoff, g.ys, w, h, cudaMemcpyDeviceToHost, s->st));
             CK(cudaMemcpy2DAsync(d + (size_t)w * h, cw, s->b.rec_u + slot * g.csize + g.coff, g.cs, cw, chh, cudaMemcpyDeviceToHost, s->st));
             CK(cudaMemcpy2DAsync(d + (size_t)w * h + (size_t)cw * chh, cw, s->b.rec_v + slot * g.csize + g.coff, g.cs, cw, chh, cudaMemcpyDeviceToHost, s->st));
         }

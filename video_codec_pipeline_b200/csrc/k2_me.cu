@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(ME_WARPS * 32) me_prepass_kernel(VcpGeom g, Vc
 }
 
 // predictor estimate from the neighbours' pre-pass vectors (oracle: pmv_estimate)
-__device__ __forceinline__ void pmv_estimate(const VcpGeom& g, const short2* __restrict__ mvfp, int mx, int my, int& px, int& py) {
-    const int row0 = vcp_slice_first_row(vcp_slice_of_row(my, g.slices, g.mbh), g.slices, g.mbh);
+__device__ __forceinline__ void pmv_estimate(const VcpGeom& g, const VcpBufs& b, const short2* __restrict__ mvfp, int mx, int my, int& px, int& py) {
+    const int row0 = vcp_row_first(b, my);
     const bool aA = mx > 0, aB = my > row0, aC = aB && mx + 1 < g.mbw, aD = aB && mx > 0;
     const int i = my * g.mbw + mx;
     int ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
@@ -148,7 +148,7 @@ __device__ __forceinline__ void pmv_estimate(const VcpGeom& g, const short2* __r
 constexpr int RF_WARPS = 4;
 
 __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
-    __shared__ LumaPlanes planes[RF_WARPS];
+    __shared__ HpelWindow win[RF_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mbi = blockIdx.x * RF_WARPS + warp;
     const int gi = blockIdx.y + s.g0;
@@ -159,63 +159,95 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
     const int lam = vcp_lambda(qp);
     const short2* mvfp = b.mvfp + (size_t)n * g.nmb;
     int pmx, pmy;
-    pmv_estimate(g, mvfp, mx, my, pmx, pmy);
+    pmv_estimate(g, b, mvfp, mx, my, pmx, pmy);
     const uint8_t* yc = b.src_y + (size_t)n * g.ysize + g.yoff;
-    const uint8_t* yr = b.rec_y + (size_t)vcp_rec_slot(s, gi, s.t - 1) * g.ysize + g.yoff;
+    const uint8_t* yr = vcp_rec_luma(b, g, vcp_rec_slot(s, gi, s.t - 1)) + g.yoff;
     const int row = lane >> 1, hx = (lane & 1) * 8;
     const int px = 16 * mx, py = 16 * my;
     const uint2 c8 = *reinterpret_cast<const uint2*>(yc + (size_t)(py + row) * g.ys + px + hx);
     const short2 f = mvfp[mbi];
+    const uint8_t* mb0 = yr + (ptrdiff_t)py * g.ys + px;               // sample (0,0) at mv (0,0)
+    HpelWindow& W = win[warp];
 
-    // full-pel candidates
-    uint32_t best = 0xffffffffu;
-    int bvx = 0, bvy = 0;
-#pragma unroll 1
-    for (int k = 0; k < 11; k++) {
-        int vx, vy;
-        if (k == 0) { vx = f.x; vy = f.y; }
-        else if (k < 9) { const int q = k - 1 + (k > 4); vx = f.x + q % 3 - 1; vy = f.y + q / 3 - 1; }
-        else if (k == 9) { vx = 0; vy = 0; }
-        else {
-            vx = vcp_clip3(-VCP_MV_FP_MAX, VCP_MV_FP_MAX, (pmx + 2) >> 2);
-            vy = vcp_clip3(-VCP_MV_FP_MAX, VCP_MV_FP_MAX, (pmy + 2) >> 2);
-        }
-        const uint2 r8 = ld8_unaligned(yr + (ptrdiff_t)(py + row + vy) * g.ys + px + hx + vx);
-        const int sad = warp_sum((int)sad4(r8.y, c8.y, sad4(r8.x, c8.x, 0)));
-        const int cost = sad + lam * (vcp_se_len(4 * vx - pmx) + vcp_se_len(4 * vy - pmy));
-        const uint32_t key = ((uint32_t)cost << 4) | (uint32_t)k;
-        if (key < best) { best = key; bvx = vx; bvy = vy; }
+    // Scalar work (candidate vectors, vector costs, plane addressing) is done once by the lane
+    // whose index equals the candidate; the 32 lanes share only the SAD loop.
+    const uint32_t* Ww = &W.w[0][0][0];
+
+    // full-pel candidates: the pre-pass vector and its 8 neighbours from one staged window, plus
+    // the zero vector and the rounded predictor from global memory
+    int mis = hpel_window_stage(W, mb0 + (ptrdiff_t)f.y * g.ys + f.x, g.ys, g.ysize, lane, 1);
+    const int pvx = vcp_clip3(-VCP_MV_FP_MAX, VCP_MV_FP_MAX, (pmx + 2) >> 2);
+    const int pvy = vcp_clip3(-VCP_MV_FP_MAX, VCP_MV_FP_MAX, (pmy + 2) >> 2);
+    int cvx, cvy;   // candidate `lane`
+    {
+        const int k = lane;
+        if (k == 0) { cvx = f.x; cvy = f.y; }
+        else if (k < 9) { const int q = k - 1 + (k > 4); cvx = f.x + q % 3 - 1; cvy = f.y + q / 3 - 1; }
+        else if (k == 9) { cvx = 0; cvy = 0; }
+        else { cvx = pvx; cvy = pvy; }
     }
+    int mycost = lam * (vcp_se_len(4 * cvx - pmx) + vcp_se_len(4 * cvy - pmy));
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        const int q = k == 0 ? 4 : k - 1 + (k > 4);
+        const uint2 r8 = hpel_row8(W.w[0][row + q / 3], mis + hx + q % 3);
+        const int sad = warp_sum((int)sad4(r8.y, c8.y, sad4(r8.x, c8.x, 0)));
+        if (lane == k) mycost += sad;
+    }
+    {
+        const uint8_t* blk = mb0 + (ptrdiff_t)row * g.ys + hx;
+        const uint2 z8 = ld8_unaligned(blk), p8 = ld8_unaligned(blk + (ptrdiff_t)pvy * g.ys + pvx);
+        const int s9 = warp_sum((int)sad4(z8.y, c8.y, sad4(z8.x, c8.x, 0)));
+        const int s10 = warp_sum((int)sad4(p8.y, c8.y, sad4(p8.x, c8.x, 0)));
+        if (lane == 9) mycost += s9;
+        if (lane == 10) mycost += s10;
+    }
+    uint32_t best = warp_min(lane < 11 ? (((uint32_t)mycost << 4) | (uint32_t)lane) : 0xffffffffu);
+    const int bvx = __shfl_sync(0xffffffffu, cvx, (int)(best & 15)), bvy = __shfl_sync(0xffffffffu, cvy, (int)(best & 15));
     uint32_t bcost = best >> 4;
     if (bcost < VCP_SUBPEL_SKIP_COST) {   // warp-uniform
         if (lane == 0) b.mv[(size_t)gi * g.nmb + mbi] = make_short2((short)(4 * bvx), (short)(4 * bvy));
         return;
     }
 
-    // half-pel planes around the best full-pel position
-    LumaPlanes& P = planes[warp];
-    luma_planes_build(P, yr + (ptrdiff_t)(py + bvy) * g.ys + px + bvx, g.ys, lane, true, true, true);
+    // half-pel then quarter-pel neighbours from the half-sample planes of the reference, staged
+    // once around the best full-pel position
     __syncwarp();
-    int bx = 4 * bvx, by = 4 * bvy;
-    int ox = 0, oy = 0;  // offset of the running best relative to the plane centre, quarter-pel
-#pragma unroll 1
+    mis = hpel_window_stage(W, mb0 + (ptrdiff_t)bvy * g.ys + bvx, g.ys, g.ysize, lane, 4);
+    const int lane_byte = (row + 1) * 24 + mis + 1 + hx;   // this lane's first sample at displacement 0 inside a plane window
+    int ox = 0, oy = 0;
+#pragma unroll
     for (int step = 2; step >= 1; step--) {
-        uint32_t sb = bcost << 4;
-        int nox = ox, noy = oy;
-#pragma unroll 1
-        for (int k = 1; k <= 8; k++) {
-            const int q = k - 1 + (k > 4);
-            const int cxq = ox + (q % 3 - 1) * step, cyq = oy + (q / 3 - 1) * step;
-            const uint2 p8 = luma_planes_fetch8(P, cxq, cyq, row, hx);
-            const int sad = warp_sum((int)sad4(p8.y, c8.y, sad4(p8.x, c8.x, 0)));
-            const int cost = sad + lam * (vcp_se_len(4 * bvx + cxq - pmx) + vcp_se_len(4 * bvy + cyq - pmy));
-            const uint32_t key = ((uint32_t)cost << 4) | (uint32_t)k;
-            if (key < sb) { sb = key; nox = cxq; noy = cyq; }
+        // lane k (1..8): candidate k -> byte offsets of its two grid samples, and its vector cost
+        int o1 = 0, o2 = 0, cq = 0, cr = 0;
+        {
+            const int k = (lane - 1) & 7, q = k + (k > 3);
+            cq = ox + (q % 3 - 1) * step; cr = oy + (q / 3 - 1) * step;
+            const HpelPoints h = hpel_points(cq, cr);
+            o1 = (hpel_plane(h.x1, h.y1) * 18 + (h.y1 >> 1)) * 24 + (h.x1 >> 1);
+            o2 = (hpel_plane(h.x2, h.y2) * 18 + (h.y2 >> 1)) * 24 + (h.x2 >> 1);
         }
-        bcost = sb >> 4; ox = nox; oy = noy;
+        mycost = lam * (vcp_se_len(4 * bvx + cq - pmx) + vcp_se_len(4 * bvy + cr - pmy));
+        if (lane == 0) mycost = (int)bcost;
+#pragma unroll
+        for (int k = 1; k <= 8; k++) {
+            const int a1 = lane_byte + __shfl_sync(0xffffffffu, o1, k);
+            uint2 p8 = hpel_row8(Ww, a1);
+            if (step == 1) {   // quarter positions average two grid samples; half positions are one
+                const int a2 = lane_byte + __shfl_sync(0xffffffffu, o2, k);
+                const uint2 c2 = hpel_row8(Ww, a2);
+                p8 = make_uint2(__vavgu4(p8.x, c2.x), __vavgu4(p8.y, c2.y));
+            }
+            const int sad = warp_sum((int)sad4(p8.y, c8.y, sad4(p8.x, c8.x, 0)));
+            if (lane == k) mycost += sad;
+        }
+        best = warp_min(lane < 9 ? (((uint32_t)mycost << 4) | (uint32_t)lane) : 0xffffffffu);
+        bcost = best >> 4;
+        const int bk = (int)(best & 15);
+        ox = __shfl_sync(0xffffffffu, bk ? cq : ox, bk);
+        oy = __shfl_sync(0xffffffffu, bk ? cr : oy, bk);
     }
-    bx += ox; by += oy;
-    if (lane == 0) b.mv[(size_t)gi * g.nmb + mbi] = make_short2((short)bx, (short)by);
+    if (lane == 0) b.mv[(size_t)gi * g.nmb + mbi] = make_short2((short)(4 * bvx + ox), (short)(4 * bvy + oy));
 }
 
 }  // namespace

@@ -23,7 +23,6 @@ __device__ __forceinline__ int blk_ras(int b) { return blk_y4(b) * 4 + blk_x4(b)
 // ---- shared tail: chroma residual of lanes 16..23, writes levels / nnz / recon ---------------
 // pred4[r] = the lane's four predicted rows (packed 4 px); returns per-lane nz of the AC part
 struct __align__(16) McScratch {
-    LumaPlanes P;
     uint8_t pred[16][16];
 };
 
@@ -51,7 +50,7 @@ __device__ __forceinline__ void mb_transform(const VcpGeom& g, const VcpBufs& b,
     if (is_luma) {
         bx = blk_x4(lane) * 4; by = blk_y4(lane) * 4;
         src = b.src_y + (size_t)n * g.ysize + g.yoff + (size_t)(16 * my + by) * g.ys + 16 * mx + bx;
-        dst = b.rec_y + (size_t)slot * g.ysize + g.yoff + (size_t)(16 * my + by) * g.ys + 16 * mx + bx;
+        dst = vcp_rec_luma(b, g, slot) + g.yoff + (size_t)(16 * my + by) * g.ys + 16 * mx + bx;
         sstride = g.ys;
     } else if (is_chroma) {
         bx = (cb & 1) * 4; by = (cb >> 1) * 4;
@@ -176,13 +175,9 @@ __global__ void __launch_bounds__(PR_WARPS * 32) p_recon_kernel(VcpGeom g, VcpBu
     // luma prediction into shared memory
     McScratch& S = scr[warp];
     {
-        const int ix = mv.x >> 2, iy = mv.y >> 2, fx = mv.x & 3, fy = mv.y & 3;
-        bool nb, nh, nj;
-        luma_planes_needs(fx, fy, nb, nh, nj);
-        const uint8_t* yr = b.rec_y + (size_t)rslot * g.ysize + g.yoff;
-        luma_planes_build(S.P, yr + (ptrdiff_t)(16 * my + iy) * g.ys + 16 * mx + ix, g.ys, lane, nb, nh, nj);
         const int row = lane >> 1, hx = (lane & 1) * 8;
-        const uint2 p8 = luma_planes_fetch8(S.P, fx, fy, row, hx);
+        const uint8_t* blk = vcp_rec_luma(b, g, rslot) + g.yoff + (ptrdiff_t)(16 * my + row) * g.ys + 16 * mx + hx;
+        const uint2 p8 = hpel_fetch8(blk, mv.x, mv.y, g.ys, g.ysize);
         *reinterpret_cast<uint2*>(&S.pred[row][hx]) = p8;
     }
     // chroma prediction: lane -> plane, row, 4 px
@@ -243,7 +238,7 @@ __device__ void i16_encode_mb(const VcpGeom& g, const VcpBufs& b, IScratch& S, i
                               int row0, int qp, int lane) {
     const int mbi = my * g.mbw + mx;
     const bool aL = mx > 0, aT = my > row0;
-    uint8_t* ry = b.rec_y + (size_t)slot * g.ysize + g.yoff + (size_t)(16 * my) * g.ys + 16 * mx;
+    uint8_t* ry = vcp_rec_luma(b, g, slot) + g.yoff + (size_t)(16 * my) * g.ys + 16 * mx;
     uint8_t* ru = b.rec_u + (size_t)slot * g.csize + g.coff + (size_t)(8 * my) * g.cs + 8 * mx;
     uint8_t* rv = b.rec_v + (size_t)slot * g.csize + g.coff + (size_t)(8 * my) * g.cs + 8 * mx;
     // neighbours (unfiltered reconstruction of this picture)

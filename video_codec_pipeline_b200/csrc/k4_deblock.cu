@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(128) mbinfo_kernel(VcpGeom g, VcpBufs b, VcpSt
     if (mbi >= g.nmb) return;
     const size_t base = (size_t)gi * g.nmb;
     const int mx = mbi % g.mbw, my = mbi / g.mbw;
-    const int row0 = vcp_slice_first_row(vcp_slice_of_row(my, g.slices, g.mbh), g.slices, g.mbh);
+    const int row0 = vcp_row_first(b, my);
     // 0:A left 1:B top 2:C top-right 3:D top-left
     const int nx[4] = {mx - 1, mx, mx + 1, mx - 1}, ny[4] = {my, my - 1, my - 1, my - 1};
     bool av[4]; int rf[4], vx[4], vy[4];
@@ -242,13 +242,13 @@ __global__ void __launch_bounds__(512) deblock_kernel(VcpGeom g, VcpBufs b, VcpS
 #pragma unroll
     for (int i = 0; i < 3; i++) tc[i] = lum ? vcp_tc0_tab[qp][i] : vcp_tc0_tab[qpc][i];
     bool top_ok = my > 0;
-    if (g.deblock_idc == 2) top_ok = my > vcp_slice_first_row(vcp_slice_of_row(my, g.slices, g.mbh), g.slices, g.mbh);
+    if (g.deblock_idc == 2) top_ok = my > vcp_row_first(b, my);
     const bool top_smem = warp > 0;                                   // row above is in this CTA
     const bool has_below = my + 1 < g.mbh;
     const bool below_smem = has_below && warp + 1 < BH;               // consumer is in this CTA
     const bool below_gmem = has_below && !below_smem;                 // consumer is the next band
     const size_t base = (size_t)gi * g.nmb;
-    uint8_t* Y = b.rec_y + (size_t)slot * g.ysize + g.yoff + (size_t)(16 * my) * g.ys;
+    uint8_t* Y = vcp_rec_luma(b, g, slot) + g.yoff + (size_t)(16 * my) * g.ys;
     uint8_t* U = b.rec_u + (size_t)slot * g.csize + g.coff + (size_t)(8 * my) * g.cs;
     uint8_t* V = b.rec_v + (size_t)slot * g.csize + g.coff + (size_t)(8 * my) * g.cs;
     const int* prog_up = progress + (size_t)gi * g.mbh + my - 1;
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(256) pad_kernel(VcpGeom g, VcpBufs b, VcpStep 
     const int gi = blockIdx.y + s.g0;
     const int slot = vcp_rec_slot(s, gi, s.t);
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < ny) { pad_plane<16>(b.rec_y + (size_t)slot * g.ysize + g.yoff, g.ys, g.cw, g.ch, VCP_PAD, idx); return; }
+    if (idx < ny) { pad_plane<16>(vcp_rec_luma(b, g, slot) + g.yoff, g.ys, g.cw, g.ch, VCP_PAD, idx); return; }
     idx -= ny;
     if (idx < nc) { pad_plane<8>(b.rec_u + (size_t)slot * g.csize + g.coff, g.cs, g.cw / 2, g.ch / 2, VCP_PADC, idx); return; }
     idx -= nc;

@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(CV_WARPS * 32) cavlc_mb_kernel(VcpGeom g, VcpB
     if (type == VCP_MB_PSKIP) { if (!WRITE && lane == 0) b.mbbits[o] = 0; return; }
     const bool idr = s.t == 0;
     const int mx = mbi % g.mbw, my = mbi / g.mbw;
-    const int sl = vcp_slice_of_row(my, g.slices, g.mbh);
-    const int row0 = vcp_slice_first_row(sl, g.slices, g.mbh);
+    const int sl = vcp_row_slice(b, my);
+    const int row0 = vcp_row_first(b, my);
     const bool aL = mx > 0, aT = my > row0;
     CvScratch& S = scr[warp];
     // stage levels (816 B = 51 x 16 B) and the nnz of cur / left / top

@@ -61,10 +61,10 @@ VCP_HD int vcp_se_len(int v) {
 
 // SAD-domain Lagrangian multiplier, ~ 2^((qp-12)/6)
 VCP_HD int vcp_lambda(int qp) {
-    const int frac[6] = {64, 72, 81, 91, 102, 114};  // 64 * 2^(i/6)
+    // 64 * 2^(r/6) for r = 0..5: 64, 72, 81, 91, 102, 114 (one byte each, no local array)
     int q = qp < 12 ? 12 : qp;
     int e = (q - 12) / 6, r = (q - 12) % 6;
-    int l = (frac[r] << e) >> 6;
+    int l = ((int)((0x72665B514840ull >> (8 * r)) & 255) << e) >> 6;
     return l < 1 ? 1 : l;
 }
 

@@ -51,6 +51,8 @@ struct VcpStep {
 };
 __host__ __device__ __forceinline__ int vcp_frame_of(const VcpStep& s, int g) { return g * s.gop + s.t; }
 __host__ __device__ __forceinline__ int vcp_rec_slot(const VcpStep& s, int g, int t) { return g * s.ring + (t % s.ring); }
+// luma planes per reconstruction slot: integer samples + the three half-sample planes (k2_hpel.cu)
+#define VCP_REC_PLANES 4
 
 // All device pointers of a session (plain struct passed by value to kernels).
 struct VcpBufs {
@@ -84,9 +86,15 @@ struct VcpBufs {
     int* error_flag;
     unsigned long long* rc_cum;  // [ngop_max] bits spent so far in the GOP
     int* db_sync;          // deblocking: [0] row ticket, [1 + gop*mbh + row] progress
+    const uint32_t* rowinfo;  // [mbh]: first macroblock row of the row's slice | slice index << 16 (host-built)
     size_t rbsp_cap;
     size_t out_cap;
 };
+
+// first luma plane (integer samples G) of a reconstruction slot; B, H, J follow at +ysize each
+__host__ __device__ __forceinline__ uint8_t* vcp_rec_luma(const VcpBufs& b, const VcpGeom& g, int slot) {
+    return b.rec_y + (size_t)slot * VCP_REC_PLANES * g.ysize;
+}
 
 // ---- launchers (one per kernel family); all asynchronous on `st` -------------------------
 void vcp_launch_k1_yuv420p(const uint8_t* in, size_t frame_bytes, int n0, int n, const VcpGeom& g,
@@ -102,6 +110,7 @@ void vcp_launch_i_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cu
 void vcp_launch_mbinfo(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_deblock(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_pad(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
+void vcp_launch_hpel(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_cavlc_count(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_cavlc_scan(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_cavlc_write(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
@@ -109,6 +118,9 @@ void vcp_launch_nal_pack(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, c
 void vcp_launch_rc_update(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 
 #ifdef __CUDACC__
+// slice geometry of a macroblock row without divisions (table built by the host at session create)
+__device__ __forceinline__ int vcp_row_first(const VcpBufs& b, int my) { return (int)(__ldg(b.rowinfo + my) & 0xffff); }
+__device__ __forceinline__ int vcp_row_slice(const VcpBufs& b, int my) { return (int)(__ldg(b.rowinfo + my) >> 16); }
 // ---- small device helpers ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ld_u32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
 // 8 consecutive bytes starting at an arbitrary byte address (global or shared)
