@@ -105,7 +105,9 @@ typedef struct vcpenc_frame_info {
 #define VCPENC_K_CAVLC_WRITE 10/* K5 pass 3: bit-exact placement into the RBSP      */
 #define VCPENC_K_RC 11         /* rate-control update                               */
 #define VCPENC_K_HPEL 12       /* K2c half-sample planes of the reconstruction      */
-#define VCPENC_K_COUNT 13
+#define VCPENC_K_CABAC_BINS 13 /* K5 CABAC: binarisation + context selection        */
+#define VCPENC_K_CABAC_CODE 14 /* K5 CABAC: arithmetic coder (lane per slice) + NAL */
+#define VCPENC_K_COUNT 15
 
 typedef struct vcpenc_kernel_stat {
     double   ms;               /* summed CUDA-event time                            */

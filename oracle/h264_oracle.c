@@ -948,6 +948,228 @@ static void cavlc_residual(BW* b, const Enc* e, const MB* mb, int mx, int my) {
             cavlc_block(b, mb->lv + VCP_LV_CHROMA_AC + (pl * 4 + blk) * 16 + 1, 15, nnz_ctx(e, mx, my, blk & 1, blk >> 1, pl + 1));
 }
 
+
+/* ------------------------------------------------------------------------------------ */
+/* K5 (CABAC): 9.3 — binarisation, context modelling and the arithmetic encoder, restated */
+/* bit by bit from the standard (PutBit / RenormE / EncodeDecision / EncodeBypass /        */
+/* EncodeFlush).  The CUDA coder uses a byte-wise equivalent; parity proves them equal.    */
+#include "../video_codec_pipeline_b200/csrc/h264_cabac_tables.h"
+
+typedef struct {
+    BW* b;
+    uint32_t low, range;
+    int outstanding, first;
+    uint8_t state[1024];   /* pStateIdx << 1 | valMPS */
+    unsigned long long nbins;
+} Cabac;
+
+static void cabac_init(Cabac* c, BW* b, int tab /*0 I, 1+cabac_init_idc P*/, int qp) {
+    c->b = b; c->low = 0; c->range = 510; c->outstanding = 0; c->first = 1; c->nbins = 0;
+    for (int i = 0; i < 1024; i++) {
+        int m = vcp_cabac_init_mn[tab][i][0], n = vcp_cabac_init_mn[tab][i][1];
+        int pre = vcp_clip3(1, 126, ((m * vcp_clip3(0, 51, qp)) >> 4) + n);
+        c->state[i] = pre <= 63 ? (uint8_t)((63 - pre) << 1) : (uint8_t)(((pre - 64) << 1) | 1);
+    }
+}
+static void cabac_putbit(Cabac* c, int bit) {
+    if (c->first) c->first = 0; else bw_put(c->b, 1, (uint32_t)bit);
+    while (c->outstanding > 0) { bw_put(c->b, 1, (uint32_t)(1 - bit)); c->outstanding--; }
+}
+static void cabac_renorm(Cabac* c) {
+    while (c->range < 256) {
+        if (c->low < 256) cabac_putbit(c, 0);
+        else if (c->low >= 512) { c->low -= 512; cabac_putbit(c, 1); }
+        else { c->low -= 256; c->outstanding++; }
+        c->range <<= 1; c->low <<= 1;
+    }
+}
+static void cabac_encode(Cabac* c, int ctx, int bin) {
+    int st = c->state[ctx] >> 1, mps = c->state[ctx] & 1;
+    uint32_t rlps = vcp_cabac_range_lps[st][(c->range >> 6) & 3];
+    c->range -= rlps;
+    if (bin != mps) {
+        c->low += c->range; c->range = rlps;
+        if (st == 0) mps ^= 1;
+        st = vcp_cabac_trans_lps[st];
+    } else if (st < 62) st++;
+    c->state[ctx] = (uint8_t)((st << 1) | mps);
+    cabac_renorm(c);
+    c->nbins++;
+}
+static void cabac_bypass(Cabac* c, int bin) {
+    c->low <<= 1;
+    if (bin) c->low += c->range;
+    if (c->low >= 1024) { cabac_putbit(c, 1); c->low -= 1024; }
+    else if (c->low < 512) cabac_putbit(c, 0);
+    else { c->low -= 512; c->outstanding++; }
+    c->nbins++;
+}
+static void cabac_terminate(Cabac* c, int bin) {
+    c->range -= 2;
+    if (bin) {
+        c->low += c->range;
+        c->range = 2;
+        cabac_renorm(c);
+        cabac_putbit(c, (c->low >> 9) & 1);
+        bw_put(c->b, 2, ((c->low >> 7) & 3) | 1);   /* the final 1 is rbsp_stop_one_bit */
+    } else cabac_renorm(c);
+    c->nbins++;
+}
+
+/* unsigned Exp-Golomb of order k in bypass bins (9.3.2.3 suffix) */
+static void cabac_ueg_bypass(Cabac* c, unsigned v, int k) {
+    while (v >= (1u << k)) { cabac_bypass(c, 1); v -= 1u << k; k++; }
+    cabac_bypass(c, 0);
+    while (k--) cabac_bypass(c, (int)((v >> k) & 1));
+}
+
+/* flags a neighbour contributes to context selection */
+static int mb_dc_cbf(const MB* m, int which /*0 luma DC, 1 Cb DC, 2 Cr DC*/) {
+    if (which == 0) {
+        if (m->type != VCP_MB_I16) return 0;
+        for (int i = 0; i < 16; i++) if (m->lv[VCP_LV_LUMA_DC + i]) return 1;
+        return 0;
+    }
+    if (m->type == VCP_MB_PSKIP || !(m->cbp >> 4)) return 0;
+    for (int i = 0; i < 4; i++) if (m->lv[VCP_LV_CHROMA_DC + (which - 1) * 4 + i]) return 1;
+    return 0;
+}
+
+/* residual_block_cabac (7.3.5.3.3) for coefficients c[0..n-1] in scan order */
+static void cabac_block(Cabac* cb, const int16_t* c, int n, int cat, int cbf_inc) {
+    static const int cbf_off[5] = {0, 4, 8, 12, 16}, sig_off[5] = {0, 15, 29, 44, 47}, abs_off[5] = {0, 10, 20, 30, 39};
+    int last = -1;
+    for (int i = 0; i < n; i++) if (c[i]) last = i;
+    cabac_encode(cb, 85 + cbf_off[cat] + cbf_inc, last >= 0);
+    if (last < 0) return;
+    for (int i = 0; i < n - 1; i++) {
+        int inc = cat == 3 ? (i < 2 ? i : 2) : i;
+        cabac_encode(cb, 105 + sig_off[cat] + inc, c[i] != 0);
+        if (c[i]) {
+            cabac_encode(cb, 166 + sig_off[cat] + inc, i == last);
+            if (i == last) break;
+        }
+    }
+    int gt1 = 0, eq1 = 0;
+    for (int i = last; i >= 0; i--) {
+        if (!c[i]) continue;
+        int a = abs(c[i]) - 1;   /* coeff_abs_level_minus1: prefix TU cMax 14, suffix EG0 */
+        int inc = gt1 ? 0 : (1 + eq1 < 4 ? 1 + eq1 : 4);
+        cabac_encode(cb, 227 + abs_off[cat] + inc, a > 0);
+        if (a > 0) {
+            int lim = 4 - (cat == 3);
+            int ctx = 227 + abs_off[cat] + 5 + (gt1 < lim ? gt1 : lim);
+            for (int k = 1; k < (a < 14 ? a : 14); k++) cabac_encode(cb, ctx, 1);
+            if (a < 14) cabac_encode(cb, ctx, 0);
+            else cabac_ueg_bypass(cb, (unsigned)(a - 14), 0);
+            gt1++;
+        } else eq1++;
+        cabac_bypass(cb, c[i] < 0);
+    }
+}
+
+static void cabac_mvd(Cabac* c, int base, int v, int amvd) {
+    int a = abs(v);
+    cabac_encode(c, base + (amvd < 3 ? 0 : amvd > 32 ? 2 : 1), a > 0);
+    if (!a) return;
+    /* prefix TU cMax 9: bins 1.. use ctx base+3,+4,+5,+6,+6,... ; suffix EG3 ; sign */
+    for (int k = 1; k < (a < 9 ? a : 9); k++) cabac_encode(c, base + 3 + (k - 1 < 3 ? k - 1 : 3), 1);
+    if (a < 9) cabac_encode(c, base + 3 + (a - 1 < 3 ? a - 1 : 3), 0);
+    else cabac_ueg_bypass(c, (unsigned)(a - 9), 3);
+    cabac_bypass(c, v < 0);
+}
+
+static void cabac_i16_type(Cabac* c, const MB* mb, int ctx0, int base, int islice) {
+    /* prefix bin "not I_NxN" at ctx0, then terminate(0) = not I_PCM, then 5 fields (9.3.2.5) */
+    cabac_encode(c, ctx0, 1);
+    cabac_terminate(c, 0);
+    int cc = mb->cbp >> 4;
+    cabac_encode(c, base + 1, (mb->cbp & 15) != 0);
+    cabac_encode(c, base + 2, cc != 0);
+    if (cc) cabac_encode(c, base + 2 + islice, cc == 2);
+    cabac_encode(c, base + 3 + islice, mb->i16_mode >> 1);
+    cabac_encode(c, base + 3 + 2 * islice, mb->i16_mode & 1);
+}
+
+/* slice data (7.3.4) with entropy_coding_mode_flag = 1 for MB rows [r0,r1) */
+static void write_slice_data_cabac(Enc* e, BW* b, int r0, int r1, int idr, int qp, unsigned long long* nbins) {
+    while (b->nbits) bw_put(b, 1, 1);   /* cabac_alignment_one_bit */
+    Cabac c; cabac_init(&c, b, idr ? 0 : 1, qp);
+    for (int my = r0; my < r1; my++)
+        for (int mx = 0; mx < e->mbw; mx++) {
+            const MB* mb = &e->mbs[my * e->mbw + mx];
+            const MB* A = mx > 0 ? mb - 1 : NULL;
+            const MB* B = my > r0 ? mb - e->mbw : NULL;
+            const int intra = mb->type == VCP_MB_I16;
+            if (!idr) {
+                int inc = (A && A->type != VCP_MB_PSKIP) + (B && B->type != VCP_MB_PSKIP);
+                cabac_encode(&c, 11 + inc, mb->type == VCP_MB_PSKIP);
+            }
+            if (mb->type != VCP_MB_PSKIP) {
+                if (idr) {
+                    /* neighbours here are always Intra16x16: condTermFlag = available */
+                    cabac_i16_type(&c, mb, 3 + (A != NULL) + (B != NULL), 5, 1);
+                } else if (intra) {
+                    cabac_encode(&c, 14, 1);
+                    cabac_i16_type(&c, mb, 17, 17, 0);
+                } else {
+                    cabac_encode(&c, 14, 0); cabac_encode(&c, 15, 0); cabac_encode(&c, 16, 0);   /* P_L0_16x16 */
+                }
+                if (intra) {
+                    int inc = (A && A->type == VCP_MB_I16 && A->chroma_mode) + (B && B->type == VCP_MB_I16 && B->chroma_mode);
+                    cabac_encode(&c, 64 + inc, mb->chroma_mode > 0);
+                    if (mb->chroma_mode > 0) {
+                        cabac_encode(&c, 67, mb->chroma_mode > 1);
+                        if (mb->chroma_mode > 1) cabac_encode(&c, 67, mb->chroma_mode > 2);
+                    }
+                } else {
+                    for (int k = 0; k < 2; k++) {
+                        int am = (A && A->type == VCP_MB_P16 ? abs(A->mvd[k]) : 0) + (B && B->type == VCP_MB_P16 ? abs(B->mvd[k]) : 0);
+                        cabac_mvd(&c, k ? 47 : 40, mb->mvd[k], am);
+                    }
+                    /* coded_block_pattern: 4 luma bins (8x8 raster), then chroma */
+                    int cbpA = A ? (A->type == VCP_MB_PSKIP ? 0 : A->cbp) : 0x0f, cbpB = B ? (B->type == VCP_MB_PSKIP ? 0 : B->cbp) : 0x0f;
+                    int cur = mb->cbp;
+                    for (int k = 0; k < 4; k++) {
+                        int a = (k & 1) ? (cur >> (k - 1)) & 1 : (cbpA >> (k + 1)) & 1;
+                        int bb = (k & 2) ? (cur >> (k - 2)) & 1 : (cbpB >> (k + 2)) & 1;
+                        cabac_encode(&c, 73 + !a + 2 * !bb, (cur >> k) & 1);
+                    }
+                    int ca = A ? (A->type == VCP_MB_PSKIP ? 0 : A->cbp >> 4) : 0, cbb = B ? (B->type == VCP_MB_PSKIP ? 0 : B->cbp >> 4) : 0;
+                    cabac_encode(&c, 77 + (ca > 0) + 2 * (cbb > 0), (cur >> 4) > 0);
+                    if (cur >> 4) cabac_encode(&c, 77 + 4 + (ca == 2) + 2 * (cbb == 2), (cur >> 4) == 2);
+                }
+                if (intra || mb->cbp) cabac_encode(&c, 60, 0);   /* mb_qp_delta = 0 (and so was the previous one) */
+                /* residual */
+                const int un = intra ? 1 : 0;   /* flag assumed for an unavailable neighbour */
+                if (intra)
+                    cabac_block(&c, mb->lv + VCP_LV_LUMA_DC, 16, 0, (A ? mb_dc_cbf(A, 0) : un) + 2 * (B ? mb_dc_cbf(B, 0) : un));
+                for (int blk = 0; blk < 16; blk++) {
+                    if (!(mb->cbp & (1 << (blk >> 2)))) continue;
+                    int bx = vcp_blk_x[blk], by = vcp_blk_y[blk];
+                    int fa = bx > 0 ? mb->nnz_y[by * 4 + bx - 1] != 0 : A ? (A->type != VCP_MB_PSKIP && A->nnz_y[by * 4 + 3] != 0) : un;
+                    int fb = by > 0 ? mb->nnz_y[(by - 1) * 4 + bx] != 0 : B ? (B->type != VCP_MB_PSKIP && B->nnz_y[12 + bx] != 0) : un;
+                    const int16_t* lv = mb->lv + VCP_LV_LUMA + blk * 16;
+                    if (intra) cabac_block(&c, lv + 1, 15, 1, fa + 2 * fb); else cabac_block(&c, lv, 16, 2, fa + 2 * fb);
+                }
+                int cc = mb->cbp >> 4;
+                if (cc) for (int pl = 0; pl < 2; pl++)
+                    cabac_block(&c, mb->lv + VCP_LV_CHROMA_DC + pl * 4, 4, 3,
+                                (A ? mb_dc_cbf(A, 1 + pl) : un) + 2 * (B ? mb_dc_cbf(B, 1 + pl) : un));
+                if (cc & 2) for (int pl = 0; pl < 2; pl++)
+                    for (int blk = 0; blk < 4; blk++) {
+                        int bx = blk & 1, by = blk >> 1;
+                        int fa = bx > 0 ? mb->nnz_c[pl][by * 2] != 0 : A ? (A->type != VCP_MB_PSKIP && A->nnz_c[pl][by * 2 + 1] != 0) : un;
+                        int fb = by > 0 ? mb->nnz_c[pl][bx] != 0 : B ? (B->type != VCP_MB_PSKIP && B->nnz_c[pl][2 + bx] != 0) : un;
+                        cabac_block(&c, mb->lv + VCP_LV_CHROMA_AC + (pl * 4 + blk) * 16 + 1, 15, 4, fa + 2 * fb);
+                    }
+            }
+            cabac_terminate(&c, my == r1 - 1 && mx == e->mbw - 1);   /* end_of_slice_flag */
+        }
+    while (b->nbits) bw_put(b, 1, 0);   /* rbsp_alignment_zero_bit (stop bit came from the flush) */
+    if (nbins) *nbins += c.nbins;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* headers                                                                                */
 static int level_idc_for(int mbw, int mbh, int fps_num, int fps_den) {
@@ -966,8 +1188,8 @@ static int level_idc_for(int mbw, int mbh, int fps_num, int fps_den) {
 static size_t write_sps(const Enc* e, uint8_t* out, size_t cap) {
     uint8_t tmp[128]; BW b; bw_init(&b, tmp, sizeof tmp);
     const vcpenc_params* p = &e->p;
-    bw_put(&b, 8, 66);              /* profile_idc: Baseline */
-    bw_put(&b, 8, 0xC0);            /* constraint_set0,1 (constrained baseline) */
+    if (p->entropy) { bw_put(&b, 8, 77); bw_put(&b, 8, 0x40); }   /* Main (CABAC), constraint_set1 */
+    else { bw_put(&b, 8, 66); bw_put(&b, 8, 0xC0); }              /* Constrained Baseline: constraint_set0,1 */
     bw_put(&b, 8, level_idc_for(e->mbw, e->mbh, p->fps_num, p->fps_den));
     bw_ue(&b, 0);                   /* sps id */
     bw_ue(&b, 4);                   /* log2_max_frame_num_minus4 -> 8 bits */
@@ -1007,7 +1229,7 @@ static size_t write_sps(const Enc* e, uint8_t* out, size_t cap) {
 static size_t write_pps(const Enc* e, uint8_t* out, size_t cap) {
     uint8_t tmp[64]; BW b; bw_init(&b, tmp, sizeof tmp);
     bw_ue(&b, 0); bw_ue(&b, 0);
-    bw_put(&b, 1, 0);               /* entropy_coding_mode: CAVLC */
+    bw_put(&b, 1, e->p.entropy ? 1 : 0); /* entropy_coding_mode: 0 CAVLC, 1 CABAC */
     bw_put(&b, 1, 0);               /* bottom_field_pic_order_in_frame_present */
     bw_ue(&b, 0);                   /* num_slice_groups_minus1 */
     bw_ue(&b, 0); bw_ue(&b, 0);     /* num_ref_idx_l0/l1_default_active_minus1 */
@@ -1035,6 +1257,7 @@ static void write_slice_header(const Enc* e, BW* b, int first_mb, int idr, int f
     }
     if (idr) { bw_put(b, 1, 0); bw_put(b, 1, 0); } /* no_output_of_prior_pics, long_term_reference */
     else bw_put(b, 1, 0);           /* adaptive_ref_pic_marking_mode */
+    if (e->p.entropy && !idr) bw_ue(b, 0); /* cabac_init_idc */
     bw_se(b, qp - 26);              /* slice_qp_delta */
     bw_ue(b, (unsigned)e->p.deblock_idc);
     if (e->p.deblock_idc != 1) { bw_se(b, 0); bw_se(b, 0); }
@@ -1091,7 +1314,7 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
     memset(e, 0, sizeof *e);
     e->p = *p;
     if (p->width < 16 || p->height < 16 || (p->width & 1) || (p->height & 1) || p->gop < 1 || p->slices < 1) return VCPENC_E_ARGS;
-    if (p->entropy != 0 || p->codec != VCPENC_CODEC_H264 || p->in_fmt < 0 || p->in_fmt > VCPENC_FMT_BGR24) return VCPENC_E_ARGS;
+    if (p->entropy < 0 || p->entropy > 1 || p->codec != VCPENC_CODEC_H264 || p->in_fmt < 0 || p->in_fmt > VCPENC_FMT_BGR24) return VCPENC_E_ARGS;
     if (p->rc_mode == VCPENC_RC_ABR && p->bitrate <= 0) return VCPENC_E_ARGS;
     e->mbw = (p->width + 15) / 16; e->mbh = (p->height + 15) / 16; e->nmb = e->mbw * e->mbh;
     if (p->slices > e->mbh) return VCPENC_E_ARGS;
@@ -1180,12 +1403,15 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
             int r0 = slice_first_row(e, s), r1 = s + 1 < p->slices ? slice_first_row(e, s + 1) : e->mbh;
             BW b; bw_init(&b, e->rbsp, e->rbsp_cap);
             write_slice_header(e, &b, r0 * e->mbw, idr, t, idr_count & 1, qp);
-            write_slice_data(e, &b, r0, r1, idr);
+            unsigned long long nb = 0;
+            if (p->entropy) write_slice_data_cabac(e, &b, r0, r1, idr, qp, &nb); else write_slice_data(e, &b, r0, r1, idr);
             if (b.overflow) { rc = VCPENC_E_OVERFLOW; goto done; }
             size_t k = nal_write(out + o, out_cap - o, idr ? 3 : 2, idr ? 5 : 1, e->rbsp, b.pos);
             if (!k) { rc = VCPENC_E_OVERFLOW; goto done; }
             o += k;
-            frame_bits += (unsigned long long)b.pos * 8;
+            /* CABAC runs after the whole recon chain on the device: rate control sees the bin
+             * count scaled by VCP_CABAC_BITS_PER_BIN_Q4/16 instead of the final bits */
+            frame_bits += p->entropy ? (nb * VCP_CABAC_BITS_PER_BIN_Q4) >> 4 : (unsigned long long)b.pos * 8;
         }
         if (abr) {
             /* feedback lands two pictures later (entropy coding runs beside the recon chain) */

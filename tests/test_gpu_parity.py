@@ -26,14 +26,15 @@ def _flat(planes):
     return np.concatenate([pl.ravel() for pl in planes])
 
 
+@pytest.mark.parametrize("entropy", [0, 1], ids=["cavlc", "cabac"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "%dx%d_n%d_g%d_s%d_d%d_q%d" % c)
-def test_cuda_equals_oracle(built, case):
+def test_cuda_equals_oracle(built, case, entropy):
     from oracle import pyoracle
     w, h, n, gop, sl, idc, qp = case
     clip = synth.make_clip(w, h, n, seed=1000 + w + qp)
-    ref = pyoracle.encode(pyoracle.make_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc),
-                          clip, want_dump=True)
-    p = api.default_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc, debug=1)
+    ref = pyoracle.encode(pyoracle.make_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc,
+                                               entropy=entropy), clip, want_dump=True)
+    p = api.default_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc, debug=1, entropy=entropy)
     with api.Session(p, n) as s:
         s.upload(clip)
         s.encode()
@@ -46,11 +47,11 @@ def test_cuda_equals_oracle(built, case):
     assert [x[1] for x in got["info"]] == [x[1] for x in ref["info"]]
 
 
-@pytest.mark.parametrize("g", GOLD, ids=lambda g: "%dx%d_q%d_s%d" % (g["w"], g["h"], g["qp"], g["slices"]))
+@pytest.mark.parametrize("g", GOLD, ids=lambda g: "%dx%d_q%d_s%d_e%d" % (g["w"], g["h"], g["qp"], g["slices"], g.get("entropy", 0)))
 def test_cuda_matches_golden(built, g):
     clip = synth.make_clip(g["w"], g["h"], g["frames"], seed=g["seed"])
     p = api.default_params(g["w"], g["h"], gop=g["gop"], qp_i=max(0, g["qp"] - 2), qp_p=g["qp"],
-                           slices=g["slices"], deblock_idc=g["deblock_idc"])
+                           slices=g["slices"], deblock_idc=g["deblock_idc"], entropy=g.get("entropy", 0))
     got = api.encode_frames(p, clip, want_recon=True)             # host buffers in, host buffers out
     assert [x[1] for x in got["info"]] == g["frame_sizes"]
     assert hashlib.sha256(got["stream"].tobytes()).hexdigest() == g["stream_sha256"]
@@ -115,6 +116,26 @@ def test_k1_input_formats_equal_oracle(built, fmt):
         assert np.array_equal(got["recon"], ref["recon"])
 
 
+def test_cabac_long_gops_and_bitrate_mode(built):
+    """CABAC runs as batches of 8 pictures per GOP behind the reconstruction chain: GOPs longer than
+    one batch, ragged last GOPs, many slices, and the bin-count fed rate control."""
+    from oracle import pyoracle
+    w, h = 176, 144
+    for (n, gop, sl, kw) in ((21, 10, 1, {}), (19, 9, 3, {}), (30, 17, 2, dict(rc_mode=1, bitrate=600_000, fps=25))):
+        clip = synth.make_clip(w, h, n, seed=40 + n)
+        ref = pyoracle.encode(pyoracle.make_params(w, h, gop=gop, slices=sl, entropy=1, **kw), clip)
+        got = api.encode_frames(api.default_params(w, h, gop=gop, slices=sl, entropy=1, **kw), clip, want_recon=True)
+        assert [x[3] for x in got["info"]] == [x[3] for x in ref["info"]]
+        assert got["stream"].tobytes() == ref["stream"], (n, gop, sl)
+        assert np.array_equal(got["recon"], ref["recon"])
+    # extreme content: white noise at low and high QP (long escape codes, outstanding-byte runs)
+    noise = np.random.default_rng(1).integers(0, 256, (3, 64 * 64 * 3 // 2), dtype=np.uint8)
+    for qp in (4, 51):
+        ref = pyoracle.encode(pyoracle.make_params(64, 64, gop=60, qp_i=qp, qp_p=qp, entropy=1), noise)
+        got = api.encode_frames(api.default_params(64, 64, gop=60, qp_i=qp, qp_p=qp, entropy=1), noise)
+        assert got["stream"].tobytes() == ref["stream"], qp
+
+
 def test_edge_cases(built):
     from oracle import pyoracle
     # smallest picture, one frame; GOP 1; one slice per macroblock row; ragged last GOP
@@ -145,7 +166,7 @@ def test_edge_cases(built):
         api.encode_frames(api.default_params(64, 64, gop=0), noise)
     assert e.value.code == 1
     with pytest.raises(api.VcpencError) as e:
-        api.encode_frames(api.default_params(64, 64, entropy=1), noise)
+        api.encode_frames(api.default_params(64, 64, entropy=2), noise)
     assert e.value.code == 1
 
 

@@ -112,13 +112,14 @@ def test_luma_interpolation_flat_and_ramp():
     assert L.orc_luma_qpel(ramp.ctypes.data, 32, 10, 10, 0, 2) == 40
 
 
+@pytest.mark.parametrize("entropy", [0, 1], ids=["cavlc", "cabac"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "%dx%d_n%d_g%d_s%d_d%d_q%d" % c)
-def test_oracle_stream_decodes_to_its_own_recon(case):
+def test_oracle_stream_decodes_to_its_own_recon(case, entropy):
     if not arbiter.available():
         pytest.skip("bundled FFmpeg decoder not present")
     w, h, n, gop, sl, idc, qp = case
     clip = synth.make_clip(w, h, n, seed=1000 + w + qp)
-    p = pyoracle.make_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc)
+    p = pyoracle.make_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc, entropy=entropy)
     r = pyoracle.encode(p, clip)
     dec = arbiter.decode_annexb(r["stream"])
     assert len(dec) == n
@@ -131,12 +132,12 @@ def test_oracle_stream_decodes_to_its_own_recon(case):
     assert arbiter.psnr(dec[n - 1][0], y) > (18 if qp > 45 else 28)
 
 
-@pytest.mark.parametrize("g", GOLD, ids=lambda g: "%dx%d_q%d_s%d" % (g["w"], g["h"], g["qp"], g["slices"]))
+@pytest.mark.parametrize("g", GOLD, ids=lambda g: "%dx%d_q%d_s%d_e%d" % (g["w"], g["h"], g["qp"], g["slices"], g.get("entropy", 0)))
 def test_oracle_matches_golden(g):
     clip = synth.make_clip(g["w"], g["h"], g["frames"], seed=g["seed"])
     assert hashlib.sha256(clip.tobytes()).hexdigest() == g["clip_sha256"], "synthetic clip generator drifted"
     p = pyoracle.make_params(g["w"], g["h"], gop=g["gop"], qp_i=max(0, g["qp"] - 2), qp_p=g["qp"],
-                             slices=g["slices"], deblock_idc=g["deblock_idc"])
+                             slices=g["slices"], deblock_idc=g["deblock_idc"], entropy=g.get("entropy", 0))
     r = pyoracle.encode(p, clip)
     assert [x[1] for x in r["info"]] == g["frame_sizes"]
     assert hashlib.sha256(r["stream"]).hexdigest() == g["stream_sha256"]
@@ -163,6 +164,21 @@ def test_oracle_edge_cases():
     bad = pyoracle.make_params(w, h, gop=0)
     with pytest.raises(RuntimeError):
         pyoracle.encode(bad, clip)
+
+
+def test_cabac_engine_known_answers():
+    """The arithmetic coder restated from 9.3.4.2 against hand-checkable facts: context
+    initialisation of ctxIdx 0 at QP 26 (m=20, n=-15 -> preCtxState 17 -> pStateIdx 46, valMPS 0),
+    and CABAC streams are smaller than CAVLC ones while reconstructing the same pictures."""
+    m, n = 20, -15
+    pre = max(1, min(126, ((m * 26) >> 4) + n))
+    assert pre == 17 and 63 - pre == 46
+    w, h = 320, 180
+    clip = synth.make_clip(w, h, 6, seed=9)
+    a = pyoracle.encode(pyoracle.make_params(w, h, gop=3, qp_i=26, qp_p=28), clip)
+    b = pyoracle.encode(pyoracle.make_params(w, h, gop=3, qp_i=26, qp_p=28, entropy=1), clip)
+    assert np.array_equal(a["recon"], b["recon"])            # entropy coding is lossless
+    assert len(b["stream"]) < 0.97 * len(a["stream"])
 
 
 def test_oracle_bitrate_mode():

@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvcpenc.so")
 
 K_NAMES = ["csc", "me_prepass", "me_refine", "p_recon", "i_recon", "mbinfo", "deblock", "pad",
-           "cavlc_count", "cavlc_scan", "cavlc_write_pack", "rc", "hpel"]
+           "cavlc_count", "cavlc_scan", "cavlc_write_pack", "rc", "hpel", "cabac_bins", "cabac_code"]
 
 ERR_NAMES = {0: "OK", 1: "ARGS", 2: "IO", 3: "FORMAT", 4: "NODEVICE", 5: "CUDA", 6: "CANCELLED",
              7: "TIMEOUT", 8: "NOTENCODE", 9: "AUDIO", 10: "VERIFY", 11: "OVERFLOW", 12: "INTERNAL"}

@@ -45,6 +45,7 @@ size_t frame_bytes_of(const vcpenc_params& p) {
 }
 
 struct EventPair { cudaEvent_t a, b; int kind; };
+constexpr int kCabacBatch = 8;   // pictures per GOP handed to the arithmetic coder at once
 
 }  // namespace
 
@@ -59,12 +60,15 @@ struct vcpenc_session {
     static constexpr int kMaxGroups = 8;
     cudaStream_t gst[kMaxGroups] = {};          // one stream per GOP group (the recon chain)
     cudaStream_t est[kMaxGroups] = {};          // entropy coding of the group, off the chain
+    cudaStream_t cst[kMaxGroups] = {};          // CABAC arithmetic coder batches (long, few warps)
+    cudaEvent_t ev_bins[kMaxGroups] = {};       // bins of the batch are complete
     cudaEvent_t gev[kMaxGroups] = {};
     cudaEvent_t ev_rec[kMaxGroups][2] = {};     // records of parity p are complete (after mbinfo)
     cudaEvent_t ev_ent[kMaxGroups][2] = {};     // entropy coding finished reading records of parity p
     VcpBufs bpar[2]{};                          // per-parity views of the double-buffered MB records
     cudaEvent_t ev_pre = nullptr;
     int ngroups = 4;
+    int bins_per_mb = 128;                      // CABAC bin arena sizing (VCPENC_BINS_PER_MB)
     std::vector<void*> allocs;
     uint8_t* staging[2] = {nullptr, nullptr};
     // K1 front stages (other pixel formats, scaling): scratch pictures of staging_frames each
@@ -106,7 +110,7 @@ int dev_alloc(vcpenc_session* s, T** p, size_t count, char* err, size_t errlen) 
 
 int check_params(const vcpenc_params& p, char* err, size_t errlen) {
     if (p.codec != VCPENC_CODEC_H264) { set_err(err, errlen, "codec %d not implemented (H.264 only)", p.codec); return VCPENC_E_ARGS; }
-    if (p.entropy != 0) { set_err(err, errlen, "CABAC not implemented yet (use -coder 0)"); return VCPENC_E_ARGS; }
+    if (p.entropy < 0 || p.entropy > 1) { set_err(err, errlen, "bad entropy coder %d", p.entropy); return VCPENC_E_ARGS; }
     if (p.width < 16 || p.height < 16 || (p.width & 1) || (p.height & 1)) { set_err(err, errlen, "unsupported picture size %dx%d", p.width, p.height); return VCPENC_E_ARGS; }
     if (p.gop < 1 || p.slices < 1 || p.slices > (p.height + 15) / 16) { set_err(err, errlen, "bad gop/slices"); return VCPENC_E_ARGS; }
     if (p.qp_i < 0 || p.qp_i > 51 || p.qp_p < 0 || p.qp_p > 51) { set_err(err, errlen, "qp out of range"); return VCPENC_E_ARGS; }
@@ -153,6 +157,25 @@ void collect_profile(vcpenc_session* s) {
     s->events_used = 0;
 }
 
+// CABAC arenas: bins_per_mb bins per macroblock on average over the whole session (128 ~ 25 Mb/s at
+// 1080p30).  A picture may use more as long as the total fits; if it does not, the encode call
+// grows the arenas and runs again (vcpenc_session_encode).
+int alloc_cabac_arenas(vcpenc_session* s, char* err, size_t errlen) {
+    VcpBufs& b = s->b;
+    if (b.bins) { cudaFree(b.bins); s->allocs.erase(std::find(s->allocs.begin(), s->allocs.end(), (void*)b.bins)); b.bins = nullptr; }
+    if (b.crbsp) { cudaFree(b.crbsp); s->allocs.erase(std::find(s->allocs.begin(), s->allocs.end(), (void*)b.crbsp)); b.crbsp = nullptr; }
+    const size_t N = s->max_frames;
+    b.bins_cap = std::max<size_t>(N * s->g.nmb * (size_t)s->bins_per_mb, (size_t)1 << 18);
+    b.crbsp_cap = b.bins_cap / 2 + N * s->g.slices * 96;
+    int rc = dev_alloc(s, &b.bins, b.bins_cap, err, errlen);
+    if (!rc) rc = dev_alloc(s, &b.crbsp, b.crbsp_cap, err, errlen);
+    for (int q = 0; q < 2; q++) {
+        s->bpar[q].bins = b.bins; s->bpar[q].bins_cap = b.bins_cap;
+        s->bpar[q].crbsp = b.crbsp; s->bpar[q].crbsp_cap = b.crbsp_cap;
+    }
+    return rc;
+}
+
 // K1 over `cnt` raw frames already in device memory at `din` -> padded planes of frames n0..
 // Other pixel formats / sizes go through the scratch pictures, staging_frames at a time.
 void k1_chain(vcpenc_session* s, const uint8_t* din, int n0, int cnt, cudaStream_t st) {
@@ -186,7 +209,7 @@ int vcpenc_device_count(void) {
     return n;
 }
 
-const char* vcpenc_version(void) { return "vcpenc 0.1 (sm_100a, H.264 CAVLC I/P)"; }
+const char* vcpenc_version(void) { return "vcpenc 0.2 (sm_100a, H.264 CAVLC/CABAC I/P)"; }
 
 void vcpenc_default_params(vcpenc_params* p) {
     memset(p, 0, sizeof *p);
@@ -218,6 +241,8 @@ void vcpenc_session_destroy(vcpenc_session* s) {
     for (int i = 0; i < vcpenc_session::kMaxGroups; i++) {
         if (s->gst[i]) cudaStreamDestroy(s->gst[i]);
         if (s->est[i]) cudaStreamDestroy(s->est[i]);
+        if (s->cst[i]) cudaStreamDestroy(s->cst[i]);
+        if (s->ev_bins[i]) cudaEventDestroy(s->ev_bins[i]);
         if (s->gev[i]) cudaEventDestroy(s->gev[i]);
         for (int q = 0; q < 2; q++) {
             if (s->ev_rec[i][q]) cudaEventDestroy(s->ev_rec[i][q]);
@@ -253,7 +278,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     g.yoff = VCP_PAD * g.ys + VCP_PAD;
     g.coff = VCP_PADC * g.cs + VCP_PADC;
     g.hoff = VCP_PAD1 * g.hs + VCP_PAD1;
-    g.slices = pp->slices; g.deblock_idc = pp->deblock_idc;
+    g.slices = pp->slices; g.deblock_idc = pp->deblock_idc; g.cabac = pp->entropy;
     g.rc_abr = pp->rc_mode == VCPENC_RC_ABR;
     g.rc_bitrate = pp->bitrate; g.fps_num = pp->fps_num; g.fps_den = pp->fps_den;
     g.rc_qp0 = g.rc_abr ? vcp_rc_initial_qp(pp->bitrate, pp->fps_num, pp->fps_den, pp->width, pp->height) : 0;
@@ -271,10 +296,14 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
         const char* e = getenv("VCPENC_STREAMS");
         int ng = e ? atoi(e) : 4;
         s->ngroups = std::max(1, std::min(ng, (int)vcpenc_session::kMaxGroups));
+        const char* e2 = getenv("VCPENC_BINS_PER_MB");
+        if (e2 && atoi(e2) > 0) s->bins_per_mb = std::min(atoi(e2), 65536);
     }
     for (int i = 0; i < s->ngroups; i++) {
         CKS(cudaStreamCreateWithFlags(&s->gst[i], cudaStreamNonBlocking));
         CKS(cudaStreamCreateWithFlags(&s->est[i], cudaStreamNonBlocking));
+        CKS(cudaStreamCreateWithFlags(&s->cst[i], cudaStreamNonBlocking));
+        CKS(cudaEventCreateWithFlags(&s->ev_bins[i], cudaEventDisableTiming));
         CKS(cudaEventCreateWithFlags(&s->gev[i], cudaEventDisableTiming));
         for (int q = 0; q < 2; q++) {
             CKS(cudaEventCreateWithFlags(&s->ev_rec[i][q], cudaEventDisableTiming));
@@ -316,6 +345,15 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     TRY(dev_alloc(s, &b.error_flag, (size_t)1, err, errlen));
     TRY(dev_alloc(s, &b.rc_cum, G, err, errlen));
     TRY(dev_alloc(s, &b.db_sync, G * (g.mbh + 1) + 1, err, errlen));
+    if (g.cabac) {
+        TRY(dev_alloc(s, &b.bins_cursor, (size_t)1, err, errlen));
+        TRY(dev_alloc(s, &b.mbdesc, N * nmb, err, errlen));
+        TRY(dev_alloc(s, &b.slice_bins, N * g.slices, err, errlen));
+        TRY(dev_alloc(s, &b.crbsp_cursor, (size_t)1, err, errlen));
+        TRY(dev_alloc(s, &b.cslice_off, N * g.slices, err, errlen));
+        TRY(dev_alloc(s, &b.cslice_bytes, N * g.slices, err, errlen));
+        TRY(alloc_cabac_arenas(s, err, errlen));
+    }
     {
         uint32_t* ri = nullptr;
         TRY(dev_alloc(s, &ri, (size_t)g.mbh, err, errlen));
@@ -423,6 +461,12 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
     CK(cudaMemsetAsync(b.out_cursor, 0, sizeof(unsigned long long), s->st));
     CK(cudaMemsetAsync(b.error_flag, 0, sizeof(int), s->st));
     CK(cudaMemsetAsync(b.frame_bits, 0, (size_t)N * sizeof(uint32_t), s->st));
+    if (g.cabac) {
+        CK(cudaMemsetAsync(b.bins_cursor, 0, sizeof(unsigned long long), s->st));
+        CK(cudaMemsetAsync(b.crbsp_cursor, 0, sizeof(unsigned long long), s->st));
+        CK(cudaMemsetAsync(b.slice_bins, 0, (size_t)N * g.slices * sizeof(uint32_t), s->st));
+        CK(cudaMemsetAsync(b.out_index, 0, (size_t)N * g.slices * sizeof(uint2), s->st));
+    }
     {
         Prof pr(s, VCPENC_K_ME_PRE);
         vcp_launch_me_prepass(g, b, N, gop, s->st);
@@ -470,10 +514,28 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 CK(cudaEventRecord(s->ev_rec[k][par], st));
                 CK(cudaStreamWaitEvent(se, s->ev_rec[k][par], 0));
             }
-            { Prof pr(s, VCPENC_K_CAVLC_COUNT, 1, se); vcp_launch_cavlc_count(g, bt, sp, se); }
-            { Prof pr(s, VCPENC_K_CAVLC_SCAN, 1, se); vcp_launch_cavlc_scan(g, bt, sp, se); }
-            { Prof pr(s, VCPENC_K_CAVLC_WRITE, 2, se); vcp_launch_cavlc_write(g, bt, sp, se); vcp_launch_nal_pack(g, bt, sp, se); }
-            if (g.rc_abr) { Prof pr(s, VCPENC_K_RC, 1, se); vcp_launch_rc_update(g, bt, sp, se); }
+            if (g.cabac) {
+                { Prof pr(s, VCPENC_K_CABAC_BINS, g.rc_abr ? 2 : 1, se); vcp_launch_cabac_bins(g, bt, sp, se); }
+                if (g.rc_abr) { Prof pr(s, VCPENC_K_RC, 1, se); vcp_launch_rc_update(g, bt, sp, se); }
+                // the arithmetic coder takes the bins in batches of kCabacBatch pictures per GOP, on
+                // its own stream: one lane per slice, long-running but only a few warps wide
+                const int last_t = std::min(gop, N) - 1;
+                const int next_active = std::min(gB, (N - (t + 1) + gop - 1) / gop) - gA;   // GOPs of the group with a picture t+1
+                if ((t + 1) % kCabacBatch == 0 || t == last_t || next_active <= 0) {
+                    const int t0 = t / kCabacBatch * kCabacBatch;
+                    cudaStream_t sc = s->profile ? s->st : s->cst[k];
+                    VcpStep sb = sp;
+                    sb.ngop = std::min(gB, (N - t0 + gop - 1) / gop) - gA;   // GOPs of the group that own picture t0
+                    if (!s->profile) { CK(cudaEventRecord(s->ev_bins[k], se)); CK(cudaStreamWaitEvent(sc, s->ev_bins[k], 0)); }
+                    Prof pr(s, VCPENC_K_CABAC_CODE, 2, sc);
+                    vcp_launch_cabac_encode(g, bt, sb, t0, t + 1, sc);
+                }
+            } else {
+                { Prof pr(s, VCPENC_K_CAVLC_COUNT, 1, se); vcp_launch_cavlc_count(g, bt, sp, se); }
+                { Prof pr(s, VCPENC_K_CAVLC_SCAN, 1, se); vcp_launch_cavlc_scan(g, bt, sp, se); }
+                { Prof pr(s, VCPENC_K_CAVLC_WRITE, 2, se); vcp_launch_cavlc_write(g, bt, sp, se); vcp_launch_nal_pack(g, bt, sp, se); }
+                if (g.rc_abr) { Prof pr(s, VCPENC_K_RC, 1, se); vcp_launch_rc_update(g, bt, sp, se); }
+            }
             if (!s->profile) CK(cudaEventRecord(s->ev_ent[k][par], se));
             if (g.deblock_idc != 1) { Prof pr(s, VCPENC_K_DEBLOCK, 1, st); vcp_launch_deblock(g, bt, sp, st); }
             { Prof pr(s, VCPENC_K_PAD, 1, st); vcp_launch_pad(g, bt, sp, st); }
@@ -487,6 +549,8 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
             CK(cudaStreamWaitEvent(s->st, s->gev[k], 0));
             CK(cudaEventRecord(s->gev[k], s->est[k]));
             CK(cudaStreamWaitEvent(s->st, s->gev[k], 0));
+            CK(cudaEventRecord(s->gev[k], s->cst[k]));
+            CK(cudaStreamWaitEvent(s->st, s->gev[k], 0));
         }
     CK(cudaGetLastError());
     return VCPENC_OK;
@@ -495,15 +559,25 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
 int vcpenc_session_encode(vcpenc_session* s, float* ms, char* err, size_t errlen) {
     if (!s || s->nframes < 1) { set_err(err, errlen, "no frames uploaded"); return VCPENC_E_ARGS; }
     CK(cudaSetDevice(s->device));
-    CK(cudaEventRecord(s->ev0, s->st));
-    int rc = run_encode(s, err, errlen);
-    if (rc) return rc;
-    CK(cudaEventRecord(s->ev1, s->st));
-    CK(cudaStreamSynchronize(s->st));
-    if (ms) CK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
-    if (s->profile) collect_profile(s);
     int flag = 0;
-    CK(cudaMemcpy(&flag, s->b.error_flag, sizeof flag, cudaMemcpyDeviceToHost));
+    for (int attempt = 0;; attempt++) {
+        CK(cudaEventRecord(s->ev0, s->st));
+        int rc = run_encode(s, err, errlen);
+        if (rc) return rc;
+        CK(cudaEventRecord(s->ev1, s->st));
+        CK(cudaStreamSynchronize(s->st));
+        if (ms) CK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+        if (s->profile) collect_profile(s);
+        CK(cudaMemcpy(&flag, s->b.error_flag, sizeof flag, cudaMemcpyDeviceToHost));
+        // CABAC arenas too small for this content (very low QP): grow x4 and run the pass again
+        if ((flag == 3 || flag == 4) && attempt < 6 && s->bins_per_mb < 65536) {
+            s->bins_per_mb = std::min(65536, s->bins_per_mb * 4);
+            rc = alloc_cabac_arenas(s, err, errlen);
+            if (rc) return rc;
+            continue;
+        }
+        break;
+    }
     if (flag) { set_err(err, errlen, "bitstream buffer overflow on device (flag %d)", flag); return VCPENC_E_OVERFLOW; }
     s->encoded = true;
     return VCPENC_OK;

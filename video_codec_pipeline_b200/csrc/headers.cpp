@@ -20,8 +20,8 @@ int level_idc_for(int mbw, int mbh, int fps_num, int fps_den) {
 std::vector<uint8_t> make_sps_nal(const vcpenc_params& p) {
     const int mbw = (p.width + 15) / 16, mbh = (p.height + 15) / 16;
     BitWriter b;
-    b.put(8, 66);    // profile_idc: Baseline
-    b.put(8, 0xC0);  // constraint_set0/1: constrained baseline
+    if (p.entropy) { b.put(8, 77); b.put(8, 0x40); }   // Main (CABAC), constraint_set1
+    else { b.put(8, 66); b.put(8, 0xC0); }             // Constrained Baseline: constraint_set0/1
     b.put(8, (uint32_t)level_idc_for(mbw, mbh, p.fps_num, p.fps_den));
     b.ue(0);         // seq_parameter_set_id
     b.ue(4);         // log2_max_frame_num_minus4
@@ -60,10 +60,9 @@ std::vector<uint8_t> make_sps_nal(const vcpenc_params& p) {
 }
 
 std::vector<uint8_t> make_pps_nal(const vcpenc_params& p) {
-    (void)p;
     BitWriter b;
     b.ue(0); b.ue(0);
-    b.put(1, 0);     // entropy_coding_mode_flag: CAVLC
+    b.put(1, p.entropy ? 1 : 0);   // entropy_coding_mode_flag: 0 CAVLC, 1 CABAC
     b.put(1, 0);     // bottom_field_pic_order_in_frame_present_flag
     b.ue(0);         // num_slice_groups_minus1
     b.ue(0); b.ue(0);

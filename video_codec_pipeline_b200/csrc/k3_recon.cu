@@ -89,6 +89,8 @@ __device__ __forceinline__ void mb_transform(const VcpGeom& g, const VcpBufs& b,
         const uint32_t acnz = __ballot_sync(0xffffffffu, is_chroma && nz != 0);
         const uint32_t cbpc = acnz ? 2u : (dcnz ? 1u : 0u);
         cbp_out = cbpc << 4;
+        // coded_block_flag of the two chroma DC blocks (CABAC context selection of the neighbours)
+        cbp_out |= ((dcnz & 0x000f0000u) ? 0x200u : 0u) | ((dcnz & 0x00f00000u) ? 0x400u : 0u);
         if (is_chroma && !acnz) nz = 0;
     }
     // luma DC for Intra16x16: 4x4 Hadamard over the 16 block DCs (8.5.10 restated forward)
@@ -113,6 +115,7 @@ __device__ __forceinline__ void mb_transform(const VcpGeom& g, const VcpBufs& b,
             lvl = vcp_quant1(sum >> 1, vcp_quant_mf[qp % 6][0], 2 * f, qbits + 1);
         }
         __syncwarp();
+        if (__ballot_sync(0xffffffffu, is_luma && lvl != 0)) cbp_out |= 0x100u;   // coded_block_flag of the luma DC block
         if (is_luma) dcbuf[lane] = lvl;  // raster
         __syncwarp();
         int dq = 0;
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32) p_recon_kernel(VcpGeom g, VcpBu
     if (lane == 0) {
         b.cbp[(size_t)gi * g.nmb + mbi] = (uint8_t)cbp;
         b.mbtype[(size_t)gi * g.nmb + mbi] = VCP_MB_P16;
-        b.modes[(size_t)gi * g.nmb + mbi] = 0;
+        b.modes[(size_t)gi * g.nmb + mbi] = (uint8_t)((cbp >> 8) << 4);   // DC coded_block_flags (VCP_MODES_DCF_SHIFT)
     }
 }
 
@@ -365,7 +368,7 @@ __device__ void i16_encode_mb(const VcpGeom& g, const VcpBufs& b, IScratch& S, i
         const size_t o = (size_t)gi * g.nmb + mbi;
         b.cbp[o] = (uint8_t)cbp;
         b.mbtype[o] = VCP_MB_I16;
-        b.modes[o] = (uint8_t)(i16mode | (cmode << 2));
+        b.modes[o] = (uint8_t)(i16mode | (cmode << 2) | ((cbp >> 8) << 4));
         b.mv[o] = make_short2(0, 0);
         b.mvd[o] = make_short2(0, 0);
     }

@@ -102,6 +102,10 @@ VCP_HD unsigned long long vcp_in_frame_bytes(int fmt, int w, int h) {
     }
 }
 
+// CABAC is coded after the reconstruction chain (one sequential coder per slice, all pictures at
+// once), so bitrate-targeted rate control is fed an estimate: bins * 12/16 bits
+#define VCP_CABAC_BITS_PER_BIN_Q4 12
+
 // ---- bitrate-targeted rate control (-b:v), integer only ------------------------------------
 // GOPs are encoded independently and in parallel, so each GOP carries its own budget:
 //   budget = bitrate * gop_frames / fps ; the IDR picture is expected to cost VCP_RC_I_WEIGHT

@@ -25,6 +25,7 @@ struct VcpGeom {
     size_t ysize, csize, hsize;    // bytes per plane
     int slices;
     int deblock_idc;
+    int cabac;         // entropy_coding_mode_flag
     // rate control (VCPENC_RC_ABR): see vcp_algo.h
     int rc_abr, rc_qp0, rc_bitrate, fps_num, fps_den;
 };
@@ -86,6 +87,17 @@ struct VcpBufs {
     int* error_flag;
     unsigned long long* rc_cum;  // [ngop_max] bits spent so far in the GOP
     int* db_sync;          // deblocking: [0] row ticket, [1 + gop*mbh + row] progress
+    // CABAC (k5_cabac.cu): bins of every resident picture, per-macroblock descriptors, slice RBSPs
+    uint16_t* bins;                  // arena, bump-allocated per macroblock
+    unsigned long long* bins_cursor;
+    size_t bins_cap;                 // in bins
+    uint2* mbdesc;                   // [nframes][nmb]: offset low 32 | count (20 bits) + offset high << 20
+    uint32_t* slice_bins;            // [nframes][slices] bins per slice
+    uint8_t* crbsp;                  // arena of slice RBSPs written by the arithmetic coder
+    unsigned long long* crbsp_cursor;
+    size_t crbsp_cap;
+    unsigned long long* cslice_off;  // [nframes][slices]
+    uint32_t* cslice_bytes;          // [nframes][slices]
     const uint32_t* rowinfo;  // [mbh]: first macroblock row of the row's slice | slice index << 16 (host-built)
     size_t rbsp_cap;
     size_t out_cap;
@@ -115,6 +127,8 @@ void vcp_launch_cavlc_count(const VcpGeom& g, const VcpBufs& b, const VcpStep& s
 void vcp_launch_cavlc_scan(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_cavlc_write(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_nal_pack(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
+void vcp_launch_cabac_bins(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
+void vcp_launch_cabac_encode(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, int t0, int t1, cudaStream_t st);
 void vcp_launch_rc_update(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 
 #ifdef __CUDACC__
