@@ -30,6 +30,8 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # see video_codec_pipeline_b200/csrc/encoder.cu
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -38,7 +40,24 @@ from video_codec_pipeline_b200 import synth  # noqa: E402
 W, H, FPS, GOP = 1920, 1080, 30, 60
 QP_I, QP_P = 25, 27
 SEED = 1080
+ENTROPY = 0
 METRIC = "1080p H.264 encode fps (GOP=60, CAVLC, I+P)"
+WORKLOAD = "configs[1]: 1080p30 yuv420p, GOP=60, CAVLC, I+P, deblock, CQP 25/27"
+
+
+def select_workload(name: str, entropy: int):
+    """Default = BASELINE.json configs[1].  `4k` = the single-GPU shard of configs[2] (4K60, CABAC by
+    default; the 8x8 transform of High profile is not built yet, so the stream is Main profile)."""
+    global W, H, FPS, SEED, ENTROPY, METRIC, WORKLOAD
+    if name == "4k":
+        W, H, FPS, SEED = 3840, 2160, 60, 2160
+        ENTROPY = 1 if entropy < 0 else entropy
+    else:
+        ENTROPY = 0 if entropy < 0 else entropy
+    coder = "CABAC" if ENTROPY else "CAVLC"
+    METRIC = "%s H.264 encode fps (GOP=60, %s, I+P)" % ("4K" if name == "4k" else "1080p", coder)
+    WORKLOAD = "%s: %dx%d@%d yuv420p, GOP=60, %s, I+P, deblock, CQP %d/%d" % (
+        "configs[2] (one GPU's GOP shard, Main profile)" if name == "4k" else "configs[1]", W, H, FPS, coder, QP_I, QP_P)
 
 
 def make_workload(gops: int) -> np.ndarray:
@@ -86,8 +105,9 @@ class ClockSampler(threading.Thread):
 
 def algorithmic_bytes_per_frame(kernel: str) -> float:
     """compulsory HBM bytes per frame for the stage a kernel belongs to."""
-    P = 1920 * 1088          # coded luma samples
-    nmb = 120 * 68
+    mbw, mbh = (W + 15) // 16, (H + 15) // 16
+    P = 256 * mbw * mbh      # coded luma samples
+    nmb = mbw * mbh
     return {
         "csc": 3.0 * W * H,                    # K1: read 1.5WH + write 1.5WH
         "me_prepass": 2.0 * P + 8 * nmb,       # K2: cur + ref luma, vector out
@@ -97,6 +117,8 @@ def algorithmic_bytes_per_frame(kernel: str) -> float:
         "deblock": 3.0 * P,                    # K4
         "pad": 0.0, "mbinfo": 0.0, "rc": 0.0,
         "cavlc_count": 3.0 * P, "cavlc_scan": 0.0, "cavlc_write_pack": 3.0 * P,   # K5: levels 3P
+        "hpel": 4.0 * P,                       # K2c: read the reconstruction, write its three half-sample planes
+        "cabac_bins": 3.0 * P, "cabac_code": 0.0,   # K5 (CABAC): levels 3P; the coder itself reads 2 B per bin
     }[kernel]
 
 
@@ -112,7 +134,7 @@ def cpu_port_fps(frames: np.ndarray, threads: int, frames_per_gop: int):
         jobs.append(frames[g * GOP: g * GOP + frames_per_gop])
 
     def one(fr):
-        p = pyoracle.make_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P)
+        p = pyoracle.make_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, entropy=ENTROPY)
         return len(pyoracle.encode(p, fr, want_recon=False)["stream"])
 
     pyoracle.lib()
@@ -144,8 +166,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[1]: 1080p30 yuv420p, GOP=60, CAVLC, I+P, deblock, CQP %d/%d" % (QP_I, QP_P),
-                   "frames_per_step": nframes, "seed": SEED},
+        "config": {"workload": WORKLOAD, "frames_per_step": nframes, "seed": SEED},
         "cpu_baseline": {"value": round(value, 3), "unit": "frames/s", "cores": threads, "kind": "port",
                          "sample": "%d threads x first %d frames of a GOP (IDR+P), oracle/h264_oracle.c; libx264/ffmpeg absent from image" % (threads, fpg)},
         "e2e": {"value": round(value, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -162,7 +183,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gops", type=int, default=32, help="closed GOPs per GPU per step (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="1080p", choices=["1080p", "4k"], help="default: BASELINE.json configs[1]")
+    ap.add_argument("--entropy", type=int, default=-1, help="0 CAVLC, 1 CABAC (default: what the workload names)")
     args = ap.parse_args()
+    select_workload(args.workload, args.entropy)
+    if args.workload == "4k" and args.gops == 32:
+        args.gops = 8                      # 480 frames of 4K = 6 GB of raw input per GPU
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -185,7 +211,7 @@ def main():
     n = frames.shape[0]
     fb = frames.shape[1]
     p = api.default_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, slices=1, deblock_idc=0,
-                           first_gop=rank * args.gops)
+                           first_gop=rank * args.gops, entropy=ENTROPY)
     host = torch.from_numpy(frames).pin_memory()
     dev = host.to("cuda", non_blocking=False)
     out_host = torch.empty(n * fb // 2 + (1 << 20), dtype=torch.uint8).pin_memory()
@@ -297,7 +323,7 @@ def main():
             "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: 1080p30 yuv420p, GOP=60, CAVLC, I+P, deblock, CQP %d/%d, --verify-able Annex-B" % (QP_I, QP_P),
+            "config": {"workload": WORKLOAD + ", --verify-able Annex-B",
                        "frames_per_step_per_gpu": n, "gops_per_gpu": args.gops, "seed": SEED,
                        "l2": "inputs (%.1f GB/GPU) larger than L2" % (n * fb / 1e9),
                        "realtime_x": round(value / FPS, 1), "wall_ms_per_step": round(wall_ms / args.steps, 3),

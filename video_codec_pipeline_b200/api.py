@@ -15,6 +15,10 @@ import os
 
 import numpy as np
 
+# more hardware queues than the default 8: the encoder overlaps ~45 streams (see encoder.cu); must be
+# in the environment before the CUDA context exists, so also before torch touches the device
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvcpenc.so")
 

@@ -31,6 +31,13 @@
 
 namespace {
 
+// The encoder drives up to ~45 CUDA streams (GOP-group chains, entropy side streams, CABAC batches,
+// copies).  The driver multiplexes streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues
+// (default 8); aliased streams serialise behind each other's long kernels (measured: CABAC 2 970 ->
+// 8 330 fps with 32 queues).  The variable is read when the context is created, so it is set when
+// the library is loaded, unless the operator chose a value.
+__attribute__((constructor)) void vcp_more_hw_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 void set_err(char* err, size_t errlen, const char* fmt, ...) {
     if (!err || !errlen) return;
     va_list ap;
@@ -60,7 +67,9 @@ struct vcpenc_session {
     static constexpr int kMaxGroups = 8;
     cudaStream_t gst[kMaxGroups] = {};          // one stream per GOP group (the recon chain)
     cudaStream_t est[kMaxGroups] = {};          // entropy coding of the group, off the chain
-    cudaStream_t cst[kMaxGroups] = {};          // CABAC arithmetic coder batches (long, few warps)
+    static constexpr int kCabacStreams = 8;
+    cudaStream_t cst[kMaxGroups][kCabacStreams] = {};   // CABAC arithmetic coder batches: long-running, few
+                                                        // warps each, independent -> they overlap each other
     cudaEvent_t ev_bins[kMaxGroups] = {};       // bins of the batch are complete
     cudaEvent_t gev[kMaxGroups] = {};
     cudaEvent_t ev_rec[kMaxGroups][2] = {};     // records of parity p are complete (after mbinfo)
@@ -241,7 +250,7 @@ void vcpenc_session_destroy(vcpenc_session* s) {
     for (int i = 0; i < vcpenc_session::kMaxGroups; i++) {
         if (s->gst[i]) cudaStreamDestroy(s->gst[i]);
         if (s->est[i]) cudaStreamDestroy(s->est[i]);
-        if (s->cst[i]) cudaStreamDestroy(s->cst[i]);
+        for (int q = 0; q < vcpenc_session::kCabacStreams; q++) if (s->cst[i][q]) cudaStreamDestroy(s->cst[i][q]);
         if (s->ev_bins[i]) cudaEventDestroy(s->ev_bins[i]);
         if (s->gev[i]) cudaEventDestroy(s->gev[i]);
         for (int q = 0; q < 2; q++) {
@@ -302,7 +311,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     for (int i = 0; i < s->ngroups; i++) {
         CKS(cudaStreamCreateWithFlags(&s->gst[i], cudaStreamNonBlocking));
         CKS(cudaStreamCreateWithFlags(&s->est[i], cudaStreamNonBlocking));
-        CKS(cudaStreamCreateWithFlags(&s->cst[i], cudaStreamNonBlocking));
+        if (pp->entropy) for (int q = 0; q < vcpenc_session::kCabacStreams; q++) CKS(cudaStreamCreateWithFlags(&s->cst[i][q], cudaStreamNonBlocking));
         CKS(cudaEventCreateWithFlags(&s->ev_bins[i], cudaEventDisableTiming));
         CKS(cudaEventCreateWithFlags(&s->gev[i], cudaEventDisableTiming));
         for (int q = 0; q < 2; q++) {
@@ -523,7 +532,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 const int next_active = std::min(gB, (N - (t + 1) + gop - 1) / gop) - gA;   // GOPs of the group with a picture t+1
                 if ((t + 1) % kCabacBatch == 0 || t == last_t || next_active <= 0) {
                     const int t0 = t / kCabacBatch * kCabacBatch;
-                    cudaStream_t sc = s->profile ? s->st : s->cst[k];
+                    cudaStream_t sc = s->profile ? s->st : s->cst[k][(t / kCabacBatch) % vcpenc_session::kCabacStreams];
                     VcpStep sb = sp;
                     sb.ngop = std::min(gB, (N - t0 + gop - 1) / gop) - gA;   // GOPs of the group that own picture t0
                     if (!s->profile) { CK(cudaEventRecord(s->ev_bins[k], se)); CK(cudaStreamWaitEvent(sc, s->ev_bins[k], 0)); }
@@ -549,8 +558,10 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
             CK(cudaStreamWaitEvent(s->st, s->gev[k], 0));
             CK(cudaEventRecord(s->gev[k], s->est[k]));
             CK(cudaStreamWaitEvent(s->st, s->gev[k], 0));
-            CK(cudaEventRecord(s->gev[k], s->cst[k]));
-            CK(cudaStreamWaitEvent(s->st, s->gev[k], 0));
+            if (g.cabac) for (int q = 0; q < vcpenc_session::kCabacStreams; q++) {
+                CK(cudaEventRecord(s->gev[k], s->cst[k][q]));
+                CK(cudaStreamWaitEvent(s->st, s->gev[k], 0));
+            }
         }
     CK(cudaGetLastError());
     return VCPENC_OK;

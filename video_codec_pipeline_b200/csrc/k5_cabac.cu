@@ -11,11 +11,11 @@
 //                         -> a stream of 16-bit bins {ctxIdx, value, kind} in a bump-allocated
 //                         arena + a (offset,count) descriptor per macroblock.  Runs on the entropy
 //                         side stream next to the reconstruction chain.
-//   cabac_encode_kernel : for a batch of pictures of every resident GOP, one LANE per slice walks
-//                         its macroblocks' bins through the arithmetic coder (byte-wise
-//                         low/queue/outstanding form, bit-identical to 9.3.4.2's PutBit procedure)
-//                         and writes the slice RBSP.  32 slices per warp; context states live in
-//                         shared memory, column per lane.
+//   cabac_encode_kernel : for a batch of pictures of every resident GOP, one WARP per slice: lane 0
+//                         walks the bins through the arithmetic coder (byte-wise low/queue/
+//                         outstanding form, bit-identical to 9.3.4.2's PutBit procedure) out of
+//                         shared memory while the other lanes stage bins and drain bytes with
+//                         coalesced accesses.  The chain is latency-bound; slices interleave per SM.
 //   cabac_pack_kernel   : NAL encapsulation of those RBSPs (shared with CAVLC, vcp_entropy.cuh).
 //
 // Replaces x264's cabac.c inside the ffmpeg child (/root/reference/cmd/consumer.go:376-382; the
@@ -256,130 +256,216 @@ __global__ void __launch_bounds__(CB_WARPS * 32) cabac_bins_kernel(VcpGeom g, Vc
     mb_bins<true>(wr, S, M, lane);
 }
 
-// ---- arithmetic coder, one lane per slice -------------------------------------------------------
-struct ArithLane {
+// ---- arithmetic coder, one WARP per slice ------------------------------------------------------
+// The coder is a serial dependency chain (state -> rLPS -> range/low -> renormalisation), so what
+// bounds a slice is latency per bin, not throughput.  Lane 0 runs the chain out of shared memory;
+// the other 31 lanes exist to keep it fed: they gather the macroblocks' bins into a shared ring
+// with coalesced loads and drain the produced bytes with coalesced stores.  Many such warps share
+// an SM, so the machine interleaves as many independent chains as there are slices in the batch.
+constexpr int AC_WARPS = 4;          // slices per CTA
+constexpr int BINBUF = 2048;         // bins staged per round
+constexpr int OUTBUF = BINBUF + 32;  // a bin renormalises by at most 7 bits
+
+struct ArithCoder {
     uint32_t low, range;
     int queue, outstanding, last;   // last: pending byte not yet stored (-1: none)
-    uint8_t* p;
-    uint8_t* end;
-    bool overflow;
-    __device__ __forceinline__ void store(int v) { if (p < end) *p++ = (uint8_t)v; else overflow = true; }
-    __device__ __forceinline__ void emit(int out) {   // out: 8 bits + carry in bit 8
-        if ((out & 0xff) == 0xff) { outstanding++; return; }
-        const int carry = out >> 8;
+    uint8_t* out;                   // shared staging of this round
+    int nout;
+    bool ovf;                       // a run of outstanding 0xff bytes longer than the staging (never seen; reported)
+    __device__ __forceinline__ void store(int v) { if (nout < OUTBUF) out[nout++] = (uint8_t)v; else ovf = true; }
+    __device__ __forceinline__ void emit(int o) {   // 8 bits + carry in bit 8
+        if ((o & 0xff) == 0xff) { outstanding++; return; }
+        const int carry = o >> 8;
         if (last >= 0) store(last + carry);
         while (outstanding > 0) { store(carry ? 0x00 : 0xff); outstanding--; }
-        last = out & 0xff;
+        last = o & 0xff;
     }
     __device__ __forceinline__ void putbyte() {
         if (queue >= 0) {
-            const int out = (int)(low >> (queue + 10));
+            const int o = (int)(low >> (queue + 10));
             low &= (0x400u << queue) - 1;
             queue -= 8;
-            emit(out);
+            emit(o);
         }
-    }
-    __device__ __forceinline__ void renorm() {
-        const int sh = __clz(range) - 23;     // range in [2, 510] -> bring bit 8 up
-        range <<= sh; low <<= sh; queue += sh;
-        putbyte();
     }
 };
 
-// batch = pictures at GOP positions [t0, t1) of GOPs [g0, g0 + ngop); one lane per (GOP, t, slice)
-__global__ void __launch_bounds__(32) cabac_encode_kernel(VcpGeom g, VcpBufs b, VcpStep s, int t0, int t1) {
-    __shared__ uint8_t state[NCTX][32];
-    __shared__ uint32_t lps4[64];
-    __shared__ uint8_t next_mps[128], next_lps[128];
-    const int lane = threadIdx.x;
-    for (int i = lane; i < 64; i += 32)
-        lps4[i] = (uint32_t)vcp_cabac_range_lps[i][0] | ((uint32_t)vcp_cabac_range_lps[i][1] << 8) |
-                  ((uint32_t)vcp_cabac_range_lps[i][2] << 16) | ((uint32_t)vcp_cabac_range_lps[i][3] << 24);
-    for (int i = lane; i < 128; i += 32) {
+// A context's record is a copy of the table entry of its probability state, so the range/low
+// chain never waits for a table lookup: x = the four rLPS bytes, y = next state on MPS | next state
+// on LPS << 8 | valMPS << 16.  The lookup of the successor entry runs beside the chain.
+struct __align__(16) AcScratch {
+    uint2 rec[NCTX];
+    uint16_t bins[BINBUF + 2];
+    uint8_t out[OUTBUF];
+};
+
+// batch = pictures at GOP positions [t0, t1) of GOPs [g0, g0 + ngop); one warp per (GOP, t, slice)
+__global__ void __launch_bounds__(AC_WARPS * 32) cabac_encode_kernel(VcpGeom g, VcpBufs b, VcpStep s, int t0, int t1) {
+    __shared__ AcScratch scr[AC_WARPS];
+    __shared__ uint2 ent[128];      // per state<<1|mps: x = four rLPS bytes, y = next on MPS | next on LPS << 8 | valMPS << 16
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
         const int st = i >> 1, mps = i & 1;
-        next_mps[i] = (uint8_t)(((st < 62 ? st + 1 : st) << 1) | mps);
-        next_lps[i] = (uint8_t)((vcp_cabac_trans_lps[st] << 1) | (st == 0 ? mps ^ 1 : mps));
+        const uint32_t l4 = (uint32_t)vcp_cabac_range_lps[st][0] | ((uint32_t)vcp_cabac_range_lps[st][1] << 8) |
+                            ((uint32_t)vcp_cabac_range_lps[st][2] << 16) | ((uint32_t)vcp_cabac_range_lps[st][3] << 24);
+        const uint32_t nm = (uint32_t)(((st < 62 ? st + 1 : st) << 1) | mps);
+        const uint32_t nl = (uint32_t)((vcp_cabac_trans_lps[st] << 1) | (st == 0 ? mps ^ 1 : mps));
+        ent[i] = make_uint2(l4, nm | (nl << 8) | ((uint32_t)mps << 16));
     }
-    __syncwarp();
+    __syncthreads();
     const int S = g.slices, nt = t1 - t0;
-    const int id = blockIdx.x * 32 + lane;
+    const int id = blockIdx.x * AC_WARPS + warp;
     if (id >= s.ngop * nt * S) return;
     const int sl = id % S, t = t0 + (id / S) % nt, gi = s.g0 + id / (S * nt);
     const int n = gi * s.gop + t;
     if (n >= s.nframes) return;
     const bool idr = t == 0;
     const int qp = b.qp[n];
-    {   // context initialisation (9.3.1.1)
+    AcScratch& A = scr[warp];
+    {   // context initialisation (9.3.1.1), lanes share the contexts
         const int tab = idr ? 0 : 1;
-        for (int i = 0; i < NCTX; i++) {
+        for (int i = lane; i < NCTX; i += 32) {
             const int m = vcp_cabac_init_mn[tab][i][0], nn = vcp_cabac_init_mn[tab][i][1];
             const int pre = vcp_clip3(1, 126, ((m * vcp_clip3(0, 51, qp)) >> 4) + nn);
-            state[i][lane] = pre <= 63 ? (uint8_t)((63 - pre) << 1) : (uint8_t)(((pre - 64) << 1) | 1);
+            A.rec[i] = ent[pre <= 63 ? ((63 - pre) << 1) : (((pre - 64) << 1) | 1)];
         }
     }
     const int r0 = vcp_slice_first_row(sl, S, g.mbh);
     const int r1 = sl + 1 < S ? vcp_slice_first_row(sl + 1, S, g.mbh) : g.mbh;
     const int first = r0 * g.mbw, count = (r1 - r0) * g.mbw;
-    // output region: slice header + 4 bits per bin is more than the coder can produce
+    // output region: slice header + 4 bits per bin is more than the coder can produce on average
     const uint32_t nb = b.slice_bins[(size_t)n * S + sl];
-    const unsigned long long cap = ((unsigned long long)nb / 2 + 64 + 15) & ~15ull;
-    const unsigned long long base = atomicAdd(b.crbsp_cursor, cap);
-    if (base + cap > b.crbsp_cap) { atomicExch(b.error_flag, 4); b.cslice_bytes[(size_t)n * S + sl] = 0; return; }
+    const unsigned long long cap = ((unsigned long long)nb / 2 + 96 + 15) & ~15ull;
+    unsigned long long base = 0;
+    if (lane == 0) {
+        base = atomicAdd(b.crbsp_cursor, cap);
+        if (base + cap > b.crbsp_cap) { atomicExch(b.error_flag, 4); b.cslice_bytes[(size_t)n * S + sl] = 0; base = ~0ull; }
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base == ~0ull) return;
     uint8_t* dst = b.crbsp + base;
-    reinterpret_cast<uint4*>(dst)[0] = make_uint4(0, 0, 0, 0);
-    reinterpret_cast<uint4*>(dst)[1] = make_uint4(0, 0, 0, 0);
-    SeqBits w{dst, 0};
-    slice_header_bits(g, first, idr, t, (s.gop0 + gi) & 1, qp, &w);
-    while (w.pos & 7) w.put(1, 1);   // cabac_alignment_one_bit
-    ArithLane A;
-    A.low = 0; A.range = 510; A.queue = -9; A.outstanding = 0; A.last = -1;
-    A.p = dst + (w.pos >> 3); A.end = dst + cap; A.overflow = false;
+    uint32_t wpos = 0;   // bytes written to dst (lane 0's view is broadcast)
+    if (lane == 0) {
+        reinterpret_cast<uint4*>(dst)[0] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(dst)[1] = make_uint4(0, 0, 0, 0);
+        SeqBits w{dst, 0};
+        slice_header_bits(g, first, idr, t, (s.gop0 + gi) & 1, qp, &w);
+        while (w.pos & 7) w.put(1, 1);   // cabac_alignment_one_bit
+        wpos = w.pos >> 3;
+    }
+    wpos = __shfl_sync(0xffffffffu, wpos, 0);
+    __syncwarp();
+    ArithCoder C;
+    C.low = 0; C.range = 510; C.queue = -9; C.outstanding = 0; C.last = -1; C.out = A.out; C.nout = 0; C.ovf = false;
     const uint2* desc = b.mbdesc + (size_t)n * g.nmb + first;
-    for (int i = 0; i < count; i++) {
-        const uint2 d = desc[i];
-        const uint16_t* bp = b.bins + (((unsigned long long)(d.y >> 20) << 32) | d.x);
-        const int cnt = (int)(d.y & 0xfffff);
-        for (int k = 0; k < cnt; k++) {
-            const uint32_t v = bp[k];
-            const int bin = (v >> 10) & 1;
-            if (v & BIN_BYPASS) {
-                A.low <<= 1;
-                if (bin) A.low += A.range;
-                A.queue += 1;
-                A.putbyte();
-            } else if (v & BIN_TERM) {
-                A.range -= 2;
-                if (bin) {   // end of slice: flush (9.3.4.5), stop bit included
-                    A.low += A.range;
-                    A.range = 2;
-                    A.renorm();
-                    A.low = (A.low << 3) | 0x400u;
-                    A.queue += 3;
-                    A.putbyte();
-                } else A.renorm();
-            } else {
-                const int ctx = (int)(v & 1023);
-                const int st = state[ctx][lane];
-                const uint32_t rlps = (lps4[st >> 1] >> (((A.range >> 6) & 3) * 8)) & 255;
-                A.range -= rlps;
-                if (bin != (st & 1)) { A.low += A.range; A.range = rlps; state[ctx][lane] = next_lps[st]; }
-                else state[ctx][lane] = next_mps[st];
-                A.renorm();
+    int mb = 0;           // next macroblock to stage
+    uint32_t part = 0;    // bins of macroblock `mb` already consumed (macroblocks larger than the ring)
+    bool overflow = false;
+    while (mb < count) {
+        // ---- stage: lanes look at the next 32 macroblocks, take as many as fit --------------------
+        uint2 d = make_uint2(0, 0);
+        if (mb + lane < count) d = desc[mb + lane];
+        uint32_t cnt = d.y & 0xfffff;
+        if (lane == 0) cnt -= part;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, k);
+            if (lane >= k) incl += v;
+        }
+        const uint32_t fits = __ballot_sync(0xffffffffu, incl <= (uint32_t)BINBUF && mb + lane < count);
+        int take = __ffs(~fits) - 1;                 // leading macroblocks that fit entirely
+        if (take < 0) take = 32;
+        uint32_t nstaged;
+        if (take == 0) {                             // one macroblock larger than the ring: take a piece
+            const unsigned long long off = (((unsigned long long)(__shfl_sync(0xffffffffu, d.y, 0) >> 20)) << 32) | __shfl_sync(0xffffffffu, d.x, 0);
+            for (int e = lane; e < BINBUF; e += 32) A.bins[e] = b.bins[off + part + e];
+            nstaged = BINBUF;
+            part += BINBUF;
+        } else {
+            for (int j = 0; j < take; j++) {
+                const uint32_t dx = __shfl_sync(0xffffffffu, d.x, j), dy = __shfl_sync(0xffffffffu, d.y, j);
+                const uint32_t c = __shfl_sync(0xffffffffu, cnt, j), o = __shfl_sync(0xffffffffu, incl, j) - c;
+                const uint16_t* src = b.bins + ((((unsigned long long)(dy >> 20)) << 32) | dx) + (j == 0 ? part : 0u);
+                for (uint32_t e = lane; e < c; e += 32) A.bins[o + e] = src[e];
+            }
+            nstaged = __shfl_sync(0xffffffffu, incl, take - 1);
+            mb += take;
+            part = 0;
+        }
+        __syncwarp();
+        // ---- the chain: lane 0 ----------------------------------------------------------------------
+        if (lane == 0) {
+            C.nout = 0;
+            // software pipeline: the next bin and its context record are fetched while the current
+            // bin is coded; a repeated context takes the freshly updated record instead.  Bypass and
+            // terminate bins carry ctx 0, so the record fetch needs no test.
+            A.bins[nstaged] = 0;
+            uint32_t cur = A.bins[0];
+            uint2 rc = A.rec[cur & 1023u];
+            uint32_t low = C.low, range = C.range;
+            int queue = C.queue;
+#pragma unroll 2
+            for (uint32_t k = 0; k < nstaged; k++) {
+                const uint32_t nxt = A.bins[k + 1];
+                uint2 rn = A.rec[nxt & 1023u];
+                if (cur & (BIN_BYPASS | BIN_TERM)) {
+                    if (cur & BIN_BYPASS) {
+                        low = (low << 1) + ((cur & 0x400u) ? range : 0u);
+                        queue += 1;
+                    } else {
+                        range -= 2;
+                        if (cur & 0x400u) {   // end of slice: flush (9.3.4.5), stop bit included
+                            low += range;
+                            C.low = low << 7; C.range = 2u << 7; C.queue = queue + 7;
+                            C.putbyte();
+                            low = (C.low << 3) | 0x400u; queue = C.queue + 3; range = C.range;
+                        } else {
+                            const int sh = __clz(range) - 23;
+                            range <<= sh; low <<= sh; queue += sh;
+                        }
+                    }
+                } else {
+                    const uint32_t rlps = __byte_perm(rc.x, 0u, 0x4440u | ((range >> 6) & 3u));
+                    const uint32_t lps = ((cur >> 10) ^ (rc.y >> 16)) & 1u;
+                    const uint2 nrec = ent[__byte_perm(rc.y, 0u, 0x4440u + lps)];   // successor entry, beside the chain
+                    range -= rlps;
+                    if (lps) { low += range; range = rlps; }
+                    A.rec[cur & 1023u] = nrec;
+                    if (((nxt ^ cur) & 1023u) == 0u) rn = nrec;    // (a special next bin has ctx 0 != ctx of a decision... unless ctx 0: never coded)
+                    const int sh = __clz(range) - 23;
+                    range <<= sh; low <<= sh; queue += sh;
+                }
+                if (queue >= 0) {
+                    C.low = low; C.queue = queue;
+                    C.putbyte();
+                    low = C.low; queue = C.queue;
+                }
+                cur = nxt; rc = rn;
+            }
+            C.low = low; C.range = range; C.queue = queue;
+            if (mb >= count && part == 0) {
+                // remaining bits above the register's ready boundary, then the pending bytes
+                const int r = C.queue + 8;                      // 0..7 bits left
+                const int o = (int)(C.low >> 10);
+                const int carry = o >> r;
+                if (C.last >= 0) C.store(C.last + carry);
+                while (C.outstanding > 0) { C.store(carry ? 0x00 : 0xff); C.outstanding--; }
+                if (r > 0) C.store((o & ((1 << r) - 1)) << (8 - r));
             }
         }
+        __syncwarp();
+        // ---- drain: all lanes ---------------------------------------------------------------------
+        const int nout = __shfl_sync(0xffffffffu, C.nout, 0);
+        if (__shfl_sync(0xffffffffu, (int)C.ovf, 0) || (unsigned long long)wpos + (unsigned)nout > cap) overflow = true;
+        else for (int e = lane; e < nout; e += 32) dst[wpos + e] = A.out[e];
+        wpos += (uint32_t)nout;
+        __syncwarp();
     }
-    // remaining bits above the register's ready boundary, then the pending bytes
-    {
-        const int r = A.queue + 8;                      // 0..7 bits left
-        const int out = (int)(A.low >> 10);
-        const int carry = out >> r;
-        if (A.last >= 0) A.store(A.last + carry);
-        while (A.outstanding > 0) { A.store(carry ? 0x00 : 0xff); A.outstanding--; }
-        if (r > 0) A.store((out & ((1 << r) - 1)) << (8 - r));
+    if (lane == 0) {
+        if (overflow) { atomicExch(b.error_flag, 4); b.cslice_bytes[(size_t)n * S + sl] = 0; }
+        else { b.cslice_bytes[(size_t)n * S + sl] = wpos; b.cslice_off[(size_t)n * S + sl] = base; }
     }
-    if (A.overflow) { atomicExch(b.error_flag, 4); b.cslice_bytes[(size_t)n * S + sl] = 0; return; }
-    b.cslice_bytes[(size_t)n * S + sl] = (uint32_t)(A.p - dst);
-    b.cslice_off[(size_t)n * S + sl] = base;
 }
 
 // grid: x = (GOP, t, slice) of the batch
@@ -416,6 +502,6 @@ void vcp_launch_cabac_bins(const VcpGeom& g, const VcpBufs& b, const VcpStep& s,
 void vcp_launch_cabac_encode(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, int t0, int t1, cudaStream_t st) {
     const int total = s.ngop * (t1 - t0) * g.slices;
     if (total <= 0) return;
-    cabac_encode_kernel<<<(total + 31) / 32, 32, 0, st>>>(g, b, s, t0, t1);
+    cabac_encode_kernel<<<(total + AC_WARPS - 1) / AC_WARPS, AC_WARPS * 32, 0, st>>>(g, b, s, t0, t1);
     cabac_pack_kernel<<<total, PACK_THREADS, 0, st>>>(g, b, s, t0, t1);
 }
