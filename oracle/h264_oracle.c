@@ -441,6 +441,29 @@ static void pmv_estimate(const Enc* e, int mx, int my, int* px, int* py) {
 }
 
 /* ---- K2b: refine on the reconstructed reference ------------------------------------------ */
+/* Intra-vs-inter decision for a P macroblock (vcp_algo.h: vcp_intra_wins).  The intra cost is an
+ * ESTIMATE on the original picture (V / H / DC prediction of Intra16x16 from original neighbours),
+ * so that it needs no reconstruction and every macroblock decides in parallel. */
+static int intra_estimate(const Enc* e, int mx, int my) {
+    int row0 = slice_first_row(e, slice_of_row(e, my));
+    int aL = mx > 0, aT = my > row0;
+    const uint8_t* c = e->cur.y + (size_t)(16 * my) * e->cur.ys + 16 * mx;
+    const int s = e->cur.ys;
+    int st = 0, sl = 0;
+    for (int i = 0; i < 16; i++) { st += c[-s + i]; sl += c[i * s - 1]; }
+    int dc = (aT && aL) ? (st + sl + 16) >> 5 : aT ? (st + 8) >> 4 : aL ? (sl + 8) >> 4 : 128;
+    int sv = 0, sh = 0, sd = 0;
+    for (int y = 0; y < 16; y++)
+        for (int x = 0; x < 16; x++) {
+            int p = c[y * s + x];
+            sv += abs(p - c[-s + x]); sh += abs(p - c[y * s - 1]); sd += abs(p - dc);
+        }
+    int best = sd;
+    if (aT && sv < best) best = sv;
+    if (aL && sh < best) best = sh;
+    return best;
+}
+
 static void me_refine_mb(Enc* e, const Frame* ref, int mx, int my, int qp, int16_t mv[2]) {
     int lam = vcp_lambda(qp), pmx, pmy;
     pmv_estimate(e, mx, my, &pmx, &pmy);
@@ -468,6 +491,7 @@ static void me_refine_mb(Enc* e, const Frame* ref, int mx, int my, int qp, int16
     }
     int bx = 4 * cand[best & 15][0], by = 4 * cand[best & 15][1];
     uint32_t bcost = best >> 4;
+    e->mbs[i].type = VCP_MB_P16;
     if (bcost < VCP_SUBPEL_SKIP_COST) { mv[0] = (int16_t)bx; mv[1] = (int16_t)by; return; }
     /* half-pel then quarter-pel: 8 neighbours each, raster order, strict improvement */
     for (int step = 2; step >= 1; step--) {
@@ -487,6 +511,7 @@ static void me_refine_mb(Enc* e, const Frame* ref, int mx, int my, int qp, int16
         bcost = sb >> 4;
     }
     mv[0] = (int16_t)bx; mv[1] = (int16_t)by;
+    if (vcp_intra_wins(intra_estimate(e, mx, my), (int)bcost, lam)) e->mbs[i].type = VCP_MB_I16;
 }
 
 /* ---- K3 (inter): predict, transform, quantise, reconstruct ------------------------------- */
@@ -552,6 +577,7 @@ static void encode_chroma(Enc* e, MB* mb, Frame* rec, int mx, int my, int qp, in
 
 static void encode_p_mb(Enc* e, const Frame* ref, Frame* rec, int mx, int my, int qp) {
     MB* mb = &e->mbs[my * e->mbw + mx];
+    if (mb->type == VCP_MB_I16) return;   /* decided intra by the refine: coded after the inter macroblocks */
     memset(mb->lv, 0, sizeof mb->lv);
     mb->type = VCP_MB_P16; mb->cbp = 0;
     uint8_t pred[256], pu[64], pv[64];
@@ -1375,13 +1401,17 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
                 me_refine_mb(e, ref, i % e->mbw, i / e->mbw, qp, e->mbs[i].mv);
                 encode_p_mb(e, ref, rec, i % e->mbw, i / e->mbw, qp);
             }
+            /* intra macroblocks of the P picture: they predict from the reconstruction of their
+             * neighbours (inter ones are complete, intra ones precede in raster order) */
+            for (int i = 0; i < e->nmb; i++)
+                if (e->mbs[i].type == VCP_MB_I16) encode_i_mb(e, rec, i % e->mbw, i / e->mbw, qp);
             /* post-hoc: predictors, differences, skip */
             for (int i = 0; i < e->nmb; i++) {
                 MB* mb = &e->mbs[i];
                 int sx, sy, px, py;
                 mv_pskip(e, i % e->mbw, i / e->mbw, &sx, &sy);
                 mvp16(e, i % e->mbw, i / e->mbw, &px, &py);
-                if (!mb->cbp && mb->mv[0] == sx && mb->mv[1] == sy) mb->type = VCP_MB_PSKIP;
+                if (mb->type == VCP_MB_P16 && !mb->cbp && mb->mv[0] == sx && mb->mv[1] == sy) mb->type = VCP_MB_PSKIP;
                 mb->mvd[0] = (int16_t)(mb->mv[0] - px); mb->mvd[1] = (int16_t)(mb->mv[1] - py);
             }
             if (dump && dump->mv_prepass)

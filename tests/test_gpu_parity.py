@@ -136,6 +136,31 @@ def test_cabac_long_gops_and_bitrate_mode(built):
         assert got["stream"].tobytes() == ref["stream"], qp
 
 
+def test_intra_macroblocks_in_p_pictures(built):
+    """A scene cut in the middle of a GOP: the refine flags macroblocks intra (estimate on the original
+    picture), i_fix_kernel codes them on a wavefront after the inter ones.  Both entropy coders."""
+    from oracle import pyoracle
+    w, h = 320, 192
+    a = synth.make_clip(w, h, 4, seed=1)
+    cut = np.concatenate([a, np.roll(a, 7777, axis=1)[:2], synth.make_clip(w, h, 3, seed=77, start=9)])
+    for kw in (dict(entropy=0), dict(entropy=1), dict(entropy=0, slices=3, deblock_idc=2), dict(entropy=1, slices=4)):
+        ref = pyoracle.encode(pyoracle.make_params(w, h, gop=60, qp_i=26, qp_p=28, **kw), cut, want_dump=True)
+        assert (ref["dump"]["mb_type"][4] == 0).sum() > 100       # the cut picture is mostly intra
+        p = api.default_params(w, h, gop=60, qp_i=26, qp_p=28, debug=1, **kw)
+        with api.Session(p, cut.shape[0]) as s:
+            s.upload(cut)
+            s.encode()
+            got = s.download(want_recon=True)
+            dbg = s.debug_mbs()
+        assert np.array_equal(dbg["mb_type"], ref["dump"]["mb_type"]), kw
+        assert np.array_equal(got["recon"], ref["recon"]), kw
+        assert got["stream"].tobytes() == ref["stream"], kw
+        if arbiter.available():
+            dec = arbiter.decode_annexb(got["stream"].tobytes())
+            for i in range(cut.shape[0]):
+                assert np.array_equal(_flat(dec[i]), got["recon"][i])
+
+
 def test_edge_cases(built):
     from oracle import pyoracle
     # smallest picture, one frame; GOP 1; one slice per macroblock row; ragged last GOP

@@ -181,6 +181,23 @@ def test_cabac_engine_known_answers():
     assert len(b["stream"]) < 0.97 * len(a["stream"])
 
 
+def test_oracle_intra_in_p_pictures():
+    """Scene cut inside a GOP: most macroblocks of the cut picture turn Intra16x16, the stream stays
+    decodable bit-exactly with both entropy coders, and quality recovers at once."""
+    w, h = 320, 192
+    a = synth.make_clip(w, h, 4, seed=1)
+    cut = np.concatenate([a, np.roll(a, 7777, axis=1)[:3]])
+    for ent in (0, 1):
+        r = pyoracle.encode(pyoracle.make_params(w, h, gop=60, qp_i=26, qp_p=28, entropy=ent, slices=2), cut, want_dump=True)
+        t = r["dump"]["mb_type"]
+        assert (t[4] == 0).sum() > 100 and (t[1:4] == 0).sum() < 10
+        if arbiter.available():
+            dec = arbiter.decode_annexb(r["stream"])
+            for i in range(cut.shape[0]):
+                assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i])
+            assert arbiter.psnr(dec[4][0], synth.split_planes(cut[4], w, h)[0]) > 35
+
+
 def test_oracle_bitrate_mode():
     """-b:v: per-GOP budget, QP feedback two pictures late (vcp_algo.h); stream must stay decodable
     and land near the target."""

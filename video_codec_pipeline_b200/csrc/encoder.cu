@@ -354,6 +354,8 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     TRY(dev_alloc(s, &b.error_flag, (size_t)1, err, errlen));
     TRY(dev_alloc(s, &b.rc_cum, G, err, errlen));
     TRY(dev_alloc(s, &b.db_sync, G * (g.mbh + 1) + 1, err, errlen));
+    TRY(dev_alloc(s, &b.icount, G * g.slices, err, errlen));
+    CKS(cudaMemset(b.icount, 0, G * g.slices * sizeof(int)));
     if (g.cabac) {
         TRY(dev_alloc(s, &b.bins_cursor, (size_t)1, err, errlen));
         TRY(dev_alloc(s, &b.mbdesc, N * nmb, err, errlen));
@@ -507,7 +509,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 vcp_launch_i_recon(g, bt, sp, st);
             } else {
                 { Prof pr(s, VCPENC_K_ME_REFINE, 1, st); vcp_launch_me_refine(g, bt, sp, st); }
-                { Prof pr(s, VCPENC_K_P_RECON, 1, st); vcp_launch_p_recon(g, bt, sp, st); }
+                { Prof pr(s, VCPENC_K_P_RECON, 2, st); vcp_launch_p_recon(g, bt, sp, st); vcp_launch_i_fix(g, bt, sp, st); }
                 { Prof pr(s, VCPENC_K_MBINFO, 1, st); vcp_launch_mbinfo(g, bt, sp, st); }
             }
             if (s->p.debug) {

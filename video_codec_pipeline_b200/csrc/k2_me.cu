@@ -206,7 +206,10 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
     const int bvx = __shfl_sync(0xffffffffu, cvx, (int)(best & 15)), bvy = __shfl_sync(0xffffffffu, cvy, (int)(best & 15));
     uint32_t bcost = best >> 4;
     if (bcost < VCP_SUBPEL_SKIP_COST) {   // warp-uniform
-        if (lane == 0) b.mv[(size_t)gi * g.nmb + mbi] = make_short2((short)(4 * bvx), (short)(4 * bvy));
+        if (lane == 0) {
+            b.mv[(size_t)gi * g.nmb + mbi] = make_short2((short)(4 * bvx), (short)(4 * bvy));
+            b.mbtype[(size_t)gi * g.nmb + mbi] = VCP_MB_P16;
+        }
         return;
     }
 
@@ -247,7 +250,34 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
         ox = __shfl_sync(0xffffffffu, bk ? cq : ox, bk);
         oy = __shfl_sync(0xffffffffu, bk ? cr : oy, bk);
     }
-    if (lane == 0) b.mv[(size_t)gi * g.nmb + mbi] = make_short2((short)(4 * bvx + ox), (short)(4 * bvy + oy));
+    // intra or inter?  Intra16x16 estimated on the ORIGINAL picture (best of V / H / DC from original
+    // neighbours): no reconstruction needed, so the decision stays macroblock-parallel (oracle:
+    // intra_estimate, vcp_intra_wins).  Intra macroblocks are coded by i_fix_kernel after the inter ones.
+    int type = VCP_MB_P16;
+    {
+        const int row0 = vcp_row_first(b, my);
+        const bool aL = mx > 0, aT = my > row0;
+        const uint8_t* cr = yc + (size_t)(py + row) * g.ys + px;
+        const uint2 top8 = *reinterpret_cast<const uint2*>(yc + (ptrdiff_t)(py - 1) * g.ys + px + hx);
+        const uint32_t left = cr[-1];
+        const uint32_t l4 = left * 0x01010101u;
+        const int st = warp_sum(lane < 2 ? (int)sad4(top8.x, 0u, sad4(top8.y, 0u, 0u)) : 0);   // 16 samples above
+        const int sl = warp_sum((lane & 1) ? 0 : (int)left);                                     // 16 samples to the left
+        const int dc = (aT && aL) ? (st + sl + 16) >> 5 : aT ? (st + 8) >> 4 : aL ? (sl + 8) >> 4 : 128;
+        const uint32_t d4 = (uint32_t)dc * 0x01010101u;
+        const int sv = warp_sum((int)sad4(c8.y, top8.y, sad4(c8.x, top8.x, 0u)));
+        const int sh = warp_sum((int)sad4(c8.y, l4, sad4(c8.x, l4, 0u)));
+        const int sd = warp_sum((int)sad4(c8.y, d4, sad4(c8.x, d4, 0u)));
+        int best_i = sd;
+        if (aT && sv < best_i) best_i = sv;
+        if (aL && sh < best_i) best_i = sh;
+        if (vcp_intra_wins(best_i, (int)bcost, lam)) type = VCP_MB_I16;
+    }
+    if (lane == 0) {
+        b.mv[(size_t)gi * g.nmb + mbi] = make_short2((short)(4 * bvx + ox), (short)(4 * bvy + oy));
+        b.mbtype[(size_t)gi * g.nmb + mbi] = (uint8_t)type;
+        if (type == VCP_MB_I16) atomicAdd(&b.icount[(size_t)gi * g.slices + vcp_row_slice(b, my)], 1);
+    }
 }
 
 }  // namespace

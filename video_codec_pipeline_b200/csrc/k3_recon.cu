@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32) p_recon_kernel(VcpGeom g, VcpBu
     const int mx = mbi % g.mbw, my = mbi / g.mbw;
     const int qp = b.qp[n];
     const short2 mv = b.mv[(size_t)gi * g.nmb + mbi];
+    if (b.mbtype[(size_t)gi * g.nmb + mbi] == VCP_MB_I16) return;   // decided intra by the refine: i_fix_kernel codes it
 
     // luma prediction into shared memory
     McScratch& S = scr[warp];
@@ -396,7 +397,54 @@ __global__ void __launch_bounds__(IR_WARPS * 32) i_recon_kernel(VcpGeom g, VcpBu
     }
 }
 
+// Intra16x16 macroblocks INSIDE P pictures (flagged by the refine).  They predict from the
+// reconstruction of their left/top neighbours in the same picture: inter neighbours are complete
+// once p_recon_kernel has run, intra neighbours come earlier on the anti-diagonal wavefront.
+// grid: x = slice, y = GOP; a slice without flagged macroblocks leaves at once.
+__global__ void __launch_bounds__(IR_WARPS * 32) i_fix_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
+    __shared__ IScratch scr[IR_WARPS];
+    __shared__ int todo;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sl = blockIdx.x, gi = blockIdx.y + s.g0;
+    if (threadIdx.x == 0) { todo = b.icount[(size_t)gi * g.slices + sl]; b.icount[(size_t)gi * g.slices + sl] = 0; }
+    __syncthreads();
+    if (!todo) return;
+    const int n = vcp_frame_of(s, gi);
+    const int slot = vcp_rec_slot(s, gi, s.t);
+    const int qp = b.qp[n];
+    const int r0 = vcp_slice_first_row(sl, g.slices, g.mbh);
+    const int r1 = sl + 1 < g.slices ? vcp_slice_first_row(sl + 1, g.slices, g.mbh) : g.mbh;
+    const int rows = r1 - r0;
+    const int ndiag = g.mbw + rows - 1;
+    // which anti-diagonals hold intra macroblocks at all: only those cost a barrier
+    __shared__ uint32_t dmask[32];   // up to 1024 diagonals
+    if (threadIdx.x < 32) dmask[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * g.mbw; i += blockDim.x)
+        if (b.mbtype[(size_t)gi * g.nmb + r0 * g.mbw + i] == VCP_MB_I16) {
+            const int d = i % g.mbw + i / g.mbw;
+            atomicOr(&dmask[(d >> 5) & 31], 1u << (d & 31));
+        }
+    __syncthreads();
+    for (int d = 0; d < ndiag; d++) {
+        if (!((dmask[(d >> 5) & 31] >> (d & 31)) & 1)) continue;
+        const int k0 = d - (g.mbw - 1) > 0 ? d - (g.mbw - 1) : 0;
+        const int k1 = d < rows - 1 ? d : rows - 1;
+        for (int k = k0 + warp; k <= k1; k += IR_WARPS) {
+            const int mx = d - k, my = r0 + k;
+            if (b.mbtype[(size_t)gi * g.nmb + my * g.mbw + mx] == VCP_MB_I16)
+                i16_encode_mb(g, b, scr[warp], n, slot, gi, mx, my, r0, qp, lane);
+        }
+        __syncthreads();   // reconstruction of this diagonal is visible to the next
+    }
+}
+
 }  // namespace
+
+void vcp_launch_i_fix(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
+    dim3 grid(g.slices, s.ngop);
+    i_fix_kernel<<<grid, IR_WARPS * 32, 0, st>>>(g, b, s);
+}
 
 void vcp_launch_p_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
     dim3 grid((g.nmb + PR_WARPS - 1) / PR_WARPS, s.ngop);

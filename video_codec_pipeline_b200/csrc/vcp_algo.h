@@ -32,6 +32,13 @@
 // (static / perfectly tracked content: sub-pel refinement cannot pay for itself)
 #define VCP_SUBPEL_SKIP_COST 256
 
+// Intra16x16 inside P pictures: chosen when the intra estimate (SAD of the best of V/H/DC
+// prediction from ORIGINAL neighbours) beats the inter cost by a margin; intra macroblocks cost
+// more side information and cannot be skipped, hence the 25 % + 16 lambda handicap.
+VCP_HD int vcp_intra_wins(int intra_sad, int inter_cost, int lam) {
+    return intra_sad + (intra_sad >> 2) + 16 * lam < inter_cost;
+}
+
 // macroblock types stored by the encoder
 #define VCP_MB_I16 0
 #define VCP_MB_P16 1

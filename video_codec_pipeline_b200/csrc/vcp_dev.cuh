@@ -98,6 +98,7 @@ struct VcpBufs {
     size_t crbsp_cap;
     unsigned long long* cslice_off;  // [nframes][slices]
     uint32_t* cslice_bytes;          // [nframes][slices]
+    int* icount;                     // [ngop_max][slices] macroblocks of the step decided intra inside P pictures
     const uint32_t* rowinfo;  // [mbh]: first macroblock row of the row's slice | slice index << 16 (host-built)
     size_t rbsp_cap;
     size_t out_cap;
@@ -118,6 +119,7 @@ void vcp_launch_k1_scale(const uint8_t* in, size_t in_fb, int sw, int sh, uint8_
 void vcp_launch_me_prepass(const VcpGeom& g, const VcpBufs& b, int nframes, int gop, cudaStream_t st);
 void vcp_launch_me_refine(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_p_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
+void vcp_launch_i_fix(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_i_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_mbinfo(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_deblock(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
