@@ -41,23 +41,28 @@ W, H, FPS, GOP = 1920, 1080, 30, 60
 QP_I, QP_P = 25, 27
 SEED = 1080
 ENTROPY = 0
+SLICES = 1
 METRIC = "1080p H.264 encode fps (GOP=60, CAVLC, I+P)"
 WORKLOAD = "configs[1]: 1080p30 yuv420p, GOP=60, CAVLC, I+P, deblock, CQP 25/27"
 
 
-def select_workload(name: str, entropy: int):
+def select_workload(name: str, entropy: int, slices: int = -1):
     """Default = BASELINE.json configs[1].  `4k` = the single-GPU shard of configs[2] (4K60, CABAC by
     default; the 8x8 transform of High profile is not built yet, so the stream is Main profile)."""
-    global W, H, FPS, SEED, ENTROPY, METRIC, WORKLOAD
+    global W, H, FPS, SEED, ENTROPY, METRIC, WORKLOAD, SLICES
     if name == "4k":
         W, H, FPS, SEED = 3840, 2160, 60, 2160
         ENTROPY = 1 if entropy < 0 else entropy
     else:
         ENTROPY = 0 if entropy < 0 else entropy
     coder = "CABAC" if ENTROPY else "CAVLC"
+    mbh = (H + 15) // 16
+    # slices: the encoder's own choice unless given (vcp_algo.h vcp_auto_slices: CAVLC 1; CABAC one per ~17 rows)
+    SLICES = slices if slices >= 0 else (max(1, mbh // 17) if ENTROPY else 1)
     METRIC = "%s H.264 encode fps (GOP=60, %s, I+P)" % ("4K" if name == "4k" else "1080p", coder)
-    WORKLOAD = "%s: %dx%d@%d yuv420p, GOP=60, %s, I+P, deblock, CQP %d/%d" % (
-        "configs[2] (one GPU's GOP shard, Main profile)" if name == "4k" else "configs[1]", W, H, FPS, coder, QP_I, QP_P)
+    WORKLOAD = "%s: %dx%d@%d yuv420p, GOP=60, %s, %d slice%s, I+P, deblock, CQP %d/%d" % (
+        "configs[2] (one GPU's GOP shard, Main profile)" if name == "4k" else "configs[1]", W, H, FPS, coder,
+        SLICES, "" if SLICES == 1 else "s", QP_I, QP_P)
 
 
 def make_workload(gops: int) -> np.ndarray:
@@ -134,7 +139,7 @@ def cpu_port_fps(frames: np.ndarray, threads: int, frames_per_gop: int):
         jobs.append(frames[g * GOP: g * GOP + frames_per_gop])
 
     def one(fr):
-        p = pyoracle.make_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, entropy=ENTROPY)
+        p = pyoracle.make_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, entropy=ENTROPY, slices=SLICES)
         return len(pyoracle.encode(p, fr, want_recon=False)["stream"])
 
     pyoracle.lib()
@@ -185,10 +190,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="1080p", choices=["1080p", "4k"], help="default: BASELINE.json configs[1]")
     ap.add_argument("--entropy", type=int, default=-1, help="0 CAVLC, 1 CABAC (default: what the workload names)")
+    ap.add_argument("--slices", type=int, default=-1, help="slices per picture (default: the encoder's choice)")
     args = ap.parse_args()
-    select_workload(args.workload, args.entropy)
+    select_workload(args.workload, args.entropy, args.slices)
     if args.workload == "4k" and args.gops == 32:
-        args.gops = 8                      # 480 frames of 4K = 6 GB of raw input per GPU
+        args.gops = 16                     # 960 frames of 4K = 12 GB of raw input per GPU
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,7 +216,7 @@ def main():
     frames = make_workload(args.gops)
     n = frames.shape[0]
     fb = frames.shape[1]
-    p = api.default_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, slices=1, deblock_idc=0,
+    p = api.default_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, slices=SLICES, deblock_idc=0,
                            first_gop=rank * args.gops, entropy=ENTROPY)
     host = torch.from_numpy(frames).pin_memory()
     dev = host.to("cuda", non_blocking=False)

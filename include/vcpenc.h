@@ -131,6 +131,10 @@ int vcpenc_verify(const char* path, char* err, size_t errlen);
 /* ---- supporting entry points ---------------------------------------------------------- */
 
 int vcpenc_device_count(void);           /* honours CUDA_VISIBLE_DEVICES; 0 if none    */
+/* Device used by vcpenc_transcode calls made from the CALLING THREAD (default 0).  The reference
+ * runs one consumer process per GPU under CUDA_VISIBLE_DEVICES (install.sh:279-297), where 0 is
+ * right; a host that drives several GPUs from one process binds each worker thread with this. */
+int vcpenc_set_thread_device(int device);
 const char* vcpenc_version(void);
 void vcpenc_default_params(vcpenc_params* p);
 

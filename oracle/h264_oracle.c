@@ -1339,7 +1339,9 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
     Enc E; Enc* e = &E;
     memset(e, 0, sizeof *e);
     e->p = *p;
-    if (p->width < 16 || p->height < 16 || (p->width & 1) || (p->height & 1) || p->gop < 1 || p->slices < 1) return VCPENC_E_ARGS;
+    if (e->p.slices == 0) e->p.slices = vcp_auto_slices((p->height + 15) / 16, p->entropy);
+    p = &e->p;
+    if (p->width < 16 || p->height < 16 || (p->width & 1) || (p->height & 1) || p->gop < 1 || p->slices < 0) return VCPENC_E_ARGS;
     if (p->entropy < 0 || p->entropy > 1 || p->codec != VCPENC_CODEC_H264 || p->in_fmt < 0 || p->in_fmt > VCPENC_FMT_BGR24) return VCPENC_E_ARGS;
     if (p->rc_mode == VCPENC_RC_ABR && p->bitrate <= 0) return VCPENC_E_ARGS;
     e->mbw = (p->width + 15) / 16; e->mbh = (p->height + 15) / 16; e->nmb = e->mbw * e->mbh;

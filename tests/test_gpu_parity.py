@@ -136,6 +136,19 @@ def test_cabac_long_gops_and_bitrate_mode(built):
         assert got["stream"].tobytes() == ref["stream"], qp
 
 
+def test_auto_slices_1080p_cabac(built):
+    """slices=0 leaves the slice count to the encoder (vcp_auto_slices: 4 at 1080p with CABAC, 1 with CAVLC)."""
+    from oracle import pyoracle
+    w, h, n = 1920, 1080, 3
+    clip = synth.make_clip(w, h, n, seed=31)
+    for ent, want in ((1, 4), (0, 1)):
+        ref = pyoracle.encode(pyoracle.make_params(w, h, gop=3, qp_i=25, qp_p=27, slices=0, entropy=ent), clip)
+        got = api.encode_frames(api.default_params(w, h, gop=3, qp_i=25, qp_p=27, slices=0, entropy=ent), clip)
+        assert got["stream"].tobytes() == ref["stream"]
+        nal_types = [b[0] & 31 for b in got["stream"].tobytes().split(b"\x00\x00\x00\x01")[1:]]
+        assert sum(t in (1, 5) for t in nal_types) == want * n
+
+
 def test_intra_macroblocks_in_p_pictures(built):
     """A scene cut in the middle of a GOP: the refine flags macroblocks intra (estimate on the original
     picture), i_fix_kernel codes them on a wavefront after the inter ones.  Both entropy coders."""

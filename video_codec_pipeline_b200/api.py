@@ -245,6 +245,13 @@ class Session:
         self.close()
 
 
+def set_thread_device(device: int):
+    """Bind transcode() calls of the calling thread to a GPU (one consumer worker per device)."""
+    rc = lib().vcpenc_set_thread_device(int(device))
+    if rc:
+        raise VcpencError(rc, "device %d not available" % device)
+
+
 def parse_args(tokens):
     """strings.Fields(ffmpeg_args) -> Params (raises VcpencError, e.g. NOTENCODE for `-c copy`)."""
     L = lib()

@@ -51,6 +51,8 @@ using namespace vcp;
 extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_params* p, char* err, size_t errlen) {
     if (!p || (argc > 0 && !argv)) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
     vcpenc_default_params(p);
+    p->slices = 0;     // unless -slices is given the encoder chooses (vcp_auto_slices)
+    p->entropy = -1;   // unless -coder / -profile:v says otherwise: the codec's default (CABAC for libx264 / nvenc)
     bool have_codec = false, have_crf = false, have_qp = false;
     int crf = 23;
     for (int i = 0; i < argc; i++) {
@@ -84,7 +86,11 @@ extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_param
             else if (s == "medium" || s == "p4" || s == "p5") p->effort = 1;
             else if (s == "slow" || s == "slower" || s == "veryslow" || s == "placebo" || s == "p6" || s == "p7") p->effort = 2;
             else { set_err(err, errlen, "unknown preset '%s'", v); return VCPENC_E_ARGS; }
-        } else if (t == "-tune" || t == "-profile:v" || t == "-level" || t == "-threads" || t == "-refs" ||
+        } else if (t == "-profile:v" || t == "-profile") {
+            if (!need(&v)) return VCPENC_E_ARGS;
+            // baseline has no CABAC; main / high default to it (an explicit -coder still wins)
+            if (p->entropy < 0 && !strcmp(v, "baseline")) p->entropy = 0;
+        } else if (t == "-tune" || t == "-level" || t == "-threads" || t == "-refs" ||
                    t == "-c:a" || t == "-acodec" || t == "-b:a" || t == "-ar" || t == "-ac" || t == "-f" ||
                    t == "-rc" || t == "-rc-lookahead" || t == "-x264-params" || t == "-x264opts") {
             if (!need(&v)) return VCPENC_E_ARGS;  // accepted, no effect on this encoder
@@ -166,6 +172,7 @@ extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_param
         }
     }
     (void)have_codec;
+    if (p->entropy < 0) p->entropy = 1;   // x264 and NVENC both default to CABAC
     if (have_crf && !have_qp) {
         // constant quality: one QP per picture type (x264's default ipratio 1.4 ~ 3 QP)
         p->qp_p = crf + 1 > 51 ? 51 : crf + 1;

@@ -121,7 +121,7 @@ int check_params(const vcpenc_params& p, char* err, size_t errlen) {
     if (p.codec != VCPENC_CODEC_H264) { set_err(err, errlen, "codec %d not implemented (H.264 only)", p.codec); return VCPENC_E_ARGS; }
     if (p.entropy < 0 || p.entropy > 1) { set_err(err, errlen, "bad entropy coder %d", p.entropy); return VCPENC_E_ARGS; }
     if (p.width < 16 || p.height < 16 || (p.width & 1) || (p.height & 1)) { set_err(err, errlen, "unsupported picture size %dx%d", p.width, p.height); return VCPENC_E_ARGS; }
-    if (p.gop < 1 || p.slices < 1 || p.slices > (p.height + 15) / 16) { set_err(err, errlen, "bad gop/slices"); return VCPENC_E_ARGS; }
+    if (p.gop < 1 || p.slices < 0 || p.slices > (p.height + 15) / 16) { set_err(err, errlen, "bad gop/slices"); return VCPENC_E_ARGS; }
     if (p.qp_i < 0 || p.qp_i > 51 || p.qp_p < 0 || p.qp_p > 51) { set_err(err, errlen, "qp out of range"); return VCPENC_E_ARGS; }
     if (p.in_fmt < VCPENC_FMT_YUV420P || p.in_fmt > VCPENC_FMT_BGR24) { set_err(err, errlen, "input pixel format %d not implemented", p.in_fmt); return VCPENC_E_FORMAT; }
     if (p.in_width < 0 || p.in_height < 0 || (p.in_width > 0) != (p.in_height > 0)) { set_err(err, errlen, "bad input size %dx%d", p.in_width, p.in_height); return VCPENC_E_ARGS; }
@@ -275,6 +275,8 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     CK(cudaSetDevice(device));
     vcpenc_session* s = new vcpenc_session();
     s->p = *pp; s->device = device; s->max_frames = max_frames; s->gop_base = pp->first_gop;
+    if (s->p.slices == 0) s->p.slices = vcp_auto_slices((pp->height + 15) / 16, pp->entropy);   // encoder's choice
+    pp = &s->p;
     VcpGeom& g = s->g;
     g.w = pp->width; g.h = pp->height;
     g.mbw = (g.w + 15) / 16; g.mbh = (g.h + 15) / 16; g.nmb = g.mbw * g.mbh;

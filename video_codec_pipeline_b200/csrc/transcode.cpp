@@ -112,6 +112,13 @@ struct PinnedBuf {
 
 }  // namespace
 
+static thread_local int t_device = 0;
+extern "C" int vcpenc_set_thread_device(int device) {
+    if (device < 0 || device >= vcpenc_device_count()) return VCPENC_E_NODEVICE;
+    t_device = device;
+    return VCPENC_OK;
+}
+
 extern "C" int vcpenc_transcode(const char* input, const char* output, int argc, const char* const* argv,
                                 int timeout_ms, volatile int* cancel, char* err, size_t errlen) {
     using clock = std::chrono::steady_clock;
@@ -156,6 +163,7 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
     p.in_width = src->width; p.in_height = src->height;
     p.fps_num = src->fps_num; p.fps_den = src->fps_den;
     if ((p.width & 1) || (p.height & 1) || p.width < 16 || p.height < 16) { set_err(err, errlen, "unsupported picture size %dx%d", p.width, p.height); return VCPENC_E_FORMAT; }
+    if (p.slices == 0) p.slices = vcp_auto_slices((p.height + 15) / 16, p.entropy);
     if (p.slices > (p.height + 15) / 16) p.slices = (p.height + 15) / 16;
 
     const size_t fb = std::max(fbytes(p.width, p.height), src->fbytes());
@@ -191,7 +199,7 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
         if (n == 0) break;
         if (!ses) {
             p.first_gop = 0;
-            rc = vcpenc_session_create(&p, 0, std::min(chunk, std::max(n, 1)), &ses, err, errlen);
+            rc = vcpenc_session_create(&p, t_device, std::min(chunk, std::max(n, 1)), &ses, err, errlen);
             if (rc) return fail(rc);
         }
         // idr_pic_id parity continues across chunks
