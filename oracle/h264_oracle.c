@@ -1452,7 +1452,7 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
             if (g0 + gop_len > nframes) gop_len = nframes - g0;
             unsigned long long budget = (unsigned long long)p->bitrate * (unsigned)p->fps_den / (unsigned)p->fps_num * (unsigned)gop_len;
             rc_cum += frame_bits;
-            rc_qp_next[1] = vcp_rc_next_qp(rc_qp0, rc_cum, t, gop_len, budget);
+            rc_qp_next[1] = vcp_rc_next_qp(rc_qp0, qp, rc_qp_next[0], idr, frame_bits, rc_cum, t, gop_len, budget);
         }
         if (idr) idr_count++;
         if (info) { info[n].offset = au0; info[n].size = (uint32_t)(o - au0); info[n].is_idr = (uint8_t)idr; info[n].qp = (uint8_t)qp; }

@@ -336,7 +336,7 @@ __global__ void rc_update_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
     if (s.t + 2 < gop_len) {
         const unsigned long long budget =
             (unsigned long long)g.rc_bitrate * (unsigned)g.fps_den / (unsigned)g.fps_num * (unsigned)gop_len;
-        b.qp[n + 2] = (uint8_t)vcp_rc_next_qp(g.rc_qp0, cum, s.t, gop_len, budget);
+        b.qp[n + 2] = (uint8_t)vcp_rc_next_qp(g.rc_qp0, b.qp[n], b.qp[n + 1], s.t == 0, b.frame_bits[n], cum, s.t, gop_len, budget);
     }
 }
 
