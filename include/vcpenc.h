@@ -79,7 +79,9 @@ typedef struct vcpenc_params {
                                   decisions resident for the parity taps            */
     int32_t first_gop;         /* index of the first GOP handed in (sharded encodes):
                                   keeps idr_pic_id alternating across shards        */
-    int32_t reserved[10];
+    int32_t drop_audio;        /* -an: container inputs with an audio stream are accepted,
+                                  the audio is dropped (else VCPENC_E_AUDIO)         */
+    int32_t reserved[9];
 } vcpenc_params;
 
 /* per coded picture, filled by the encode calls */
@@ -188,6 +190,14 @@ void vcpenc_session_destroy(vcpenc_session* s);
  * rate).  NULL on failure. */
 void* vcpenc_host_alloc(size_t bytes);
 void vcpenc_host_free(void* p);
+
+/* What vcpenc_transcode sees of a CONTAINER input (.mp4 .mkv .avi .mov .webm ...; demux + decode by
+ * libavformat/libavcodec loaded at run time, $VCPENC_FFMPEG_LIBDIR or the system's): geometry,
+ * frame rate, VCPENC_FMT_* of the decoded pictures, and optionally up to max_frames decoded
+ * pictures (tight layout) in `frames`.  Host-only. */
+int vcpenc_probe_input(const char* path, int* width, int* height, int* fps_num, int* fps_den, int* fmt,
+                       uint8_t* frames, size_t frames_cap, int max_frames, int* nframes, char* err,
+                       size_t errlen);
 
 /* Wrap an Annex-B stream produced above into an MP4 file (avc1/avcC, moov-first when
  * faststart).  Host-only. */

@@ -142,3 +142,27 @@ def test_verify_rejects_bad_files(built, tmp_path):
     novid.write_bytes(b"\x00\x00\x00\x10ftypisom\x00\x00\x02\x00" + b"\x00\x00\x00\x08moov")
     with pytest.raises(api.VcpencError):
         api.verify(str(novid))
+
+
+def test_container_front_end_decodes_what_we_mux(built, tmp_path):
+    """SURVEY 8f1, host-only: an MP4 written by our muxer goes back in through the container front end
+    (libavformat demux + libavcodec decode, loaded at run time) and yields exactly the pictures the
+    encoder reconstructed, with the right geometry and frame rate."""
+    if not arbiter.available():
+        pytest.skip("bundled FFmpeg libraries not present")
+    w, h, n = 320, 180, 9
+    clip = synth.make_clip(w, h, n, seed=33)
+    r = pyoracle.encode(pyoracle.make_params(w, h, fps=24, gop=4, qp_i=24, qp_p=26, entropy=1, slices=2), clip)
+    path = str(tmp_path / "in.mp4")
+    api.mux_mp4(api.default_params(w, h, fps=24, gop=4, faststart=1), np.frombuffer(r["stream"], np.uint8), r["info"], path)
+    info = api.probe_input(path, max_frames=n + 3)
+    assert (info["width"], info["height"], info["fmt"]) == (w, h, 0)
+    assert info["fps"][0] / info["fps"][1] == 24
+    assert info["frames"].shape[0] == n
+    assert np.array_equal(info["frames"], r["recon"])
+    # not a media file -> FORMAT
+    junk = tmp_path / "junk.mkv"
+    junk.write_bytes(b"\x1a\x45\xdf\xa3" + os.urandom(2000))
+    with pytest.raises(api.VcpencError) as e:
+        api.probe_input(str(junk))
+    assert e.value.code == 3

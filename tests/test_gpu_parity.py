@@ -258,6 +258,17 @@ def test_transcode_drop_in(built, tmp_path):
     api.transcode(str(rgb), str(out5), "-c:v libx264 -qp 30 -s 64x48")
     if arbiter.available():
         assert len(arbiter.decode_annexb(out5.read_bytes())) == 4
+    # container input (what the producer forwards): our own MP4 goes back in through the libavformat /
+    # libavcodec front end and is re-encoded; -s after -i scales the output
+    out6 = tmp_path / "out6.mp4"
+    api.transcode(str(out), str(out6), "-c:v h264_nvenc -preset p4 -b:v 2M -g 10 -s 320x180")
+    api.verify(str(out6))
+    if arbiter.available():
+        dec = arbiter.decode_file(str(out6))
+        assert len(dec) == n and dec[0][0].shape == (180, 320)
+        y5 = synth.split_planes(clip[5], w, h)[0].astype(np.int32)
+        small = ((y5[0::2, 0::2] + y5[0::2, 1::2] + y5[1::2, 0::2] + y5[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+        assert arbiter.psnr(dec[5][0], small) > 24      # two generations of lossy coding at low bitrate
     # failure semantics: unknown container -> error class, no output left behind
     bad = tmp_path / "in.mkv"
     bad.write_bytes(b"\x1a\x45\xdf\xa3junk")

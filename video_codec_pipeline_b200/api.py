@@ -33,7 +33,7 @@ class Params(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "width", "height", "fps_num", "fps_den", "codec", "gop", "rc_mode", "qp_i", "qp_p",
         "bitrate", "maxrate", "bufsize", "slices", "deblock_idc", "entropy", "in_fmt",
-        "in_width", "in_height", "faststart", "effort", "debug", "first_gop")] + [("reserved", C.c_int32 * 10)]
+        "in_width", "in_height", "faststart", "effort", "debug", "first_gop", "drop_audio")] + [("reserved", C.c_int32 * 9)]
 
 
 class FrameInfo(C.Structure):
@@ -252,6 +252,42 @@ def set_thread_device(device: int):
         raise VcpencError(rc, "device %d not available" % device)
 
 
+def ffmpeg_libdir():
+    """Where a loadable libavformat/libavcodec lives in this image (the opencv-bundled LGPL build);
+    exported as VCPENC_FFMPEG_LIBDIR for the container front end unless the operator set one."""
+    from . import arbiter
+    d = arbiter._find_libdir()
+    if d and "VCPENC_FFMPEG_LIBDIR" not in os.environ:
+        os.environ["VCPENC_FFMPEG_LIBDIR"] = d
+    return os.environ.get("VCPENC_FFMPEG_LIBDIR")
+
+
+def probe_input(path, max_frames=0):
+    """Geometry (and optionally decoded pictures) of a container input, as transcode() will see it."""
+    L = lib()
+    ffmpeg_libdir()
+    L.vcpenc_probe_input.argtypes = [C.c_char_p] + [C.POINTER(C.c_int)] * 5 + [C.c_void_p, C.c_size_t, C.c_int,
+                                                                             C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
+    w, h, fn, fd, fmt, n = (C.c_int(0) for _ in range(6))
+    err = C.create_string_buffer(512)
+    rc = L.vcpenc_probe_input(os.fsencode(path), C.byref(w), C.byref(h), C.byref(fn), C.byref(fd), C.byref(fmt),
+                              None, 0, 0, C.byref(n), err, 512)
+    if rc:
+        raise VcpencError(rc, err.value.decode(errors="replace"))
+    info = {"width": w.value, "height": h.value, "fps": (fn.value, fd.value), "fmt": fmt.value}
+    if max_frames > 0:
+        p = Params()
+        p.in_fmt, p.width, p.height = fmt.value, w.value, h.value
+        fb = in_frame_bytes(p)
+        buf = np.empty(max_frames * fb, np.uint8)
+        rc = L.vcpenc_probe_input(os.fsencode(path), None, None, None, None, None, buf.ctypes.data, buf.size, max_frames,
+                                  C.byref(n), err, 512)
+        if rc:
+            raise VcpencError(rc, err.value.decode(errors="replace"))
+        info["frames"] = buf[: n.value * fb].reshape(n.value, fb)
+    return info
+
+
 def parse_args(tokens):
     """strings.Fields(ffmpeg_args) -> Params (raises VcpencError, e.g. NOTENCODE for `-c copy`)."""
     L = lib()
@@ -269,6 +305,7 @@ def transcode(input_path, output_path, ffmpeg_args: str, timeout_ms=60 * 60 * 10
     whitespace only (strings.Fields), `-y` overwrite semantics, error classes for timeout
     and cancellation.  `cancel` is an optional ctypes.c_int polled by the library."""
     L = lib()
+    ffmpeg_libdir()
     toks = ffmpeg_args.split()
     arr = (C.c_char_p * max(1, len(toks)))(*[t.encode() for t in toks])
     err = C.create_string_buffer(1024)

@@ -94,7 +94,9 @@ extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_param
                    t == "-c:a" || t == "-acodec" || t == "-b:a" || t == "-ar" || t == "-ac" || t == "-f" ||
                    t == "-rc" || t == "-rc-lookahead" || t == "-x264-params" || t == "-x264opts") {
             if (!need(&v)) return VCPENC_E_ARGS;  // accepted, no effect on this encoder
-        } else if (t == "-an" || t == "-sn" || t == "-dn" || t == "-y" || t == "-hide_banner" || t == "-nostdin") {
+        } else if (t == "-an") {
+            p->drop_audio = 1;
+        } else if (t == "-sn" || t == "-dn" || t == "-y" || t == "-hide_banner" || t == "-nostdin") {
             // accepted
         } else if (t == "-loglevel" || t == "-v") {
             if (!need(&v)) return VCPENC_E_ARGS;

@@ -16,6 +16,7 @@
 #include <memory>
 #include <string>
 
+#include "frontend.h"
 #include "host_bits.h"
 #include "host_util.h"
 #include "vcp_algo.h"
@@ -24,15 +25,6 @@
 using namespace vcp;
 
 namespace {
-
-struct FrameSource {
-    virtual ~FrameSource() {}
-    int width = 0, height = 0, fps_num = 0, fps_den = 1;
-    int fmt = VCPENC_FMT_YUV420P;
-    size_t fbytes() const { return (size_t)vcp_in_frame_bytes(fmt, width, height); }
-    // read up to `max` frames (tight, `fmt`) into dst; returns frames read, <0 on error
-    virtual int read(uint8_t* dst, int max, char* err, size_t errlen) = 0;
-};
 
 size_t fbytes(int w, int h) { return (size_t)w * h + 2 * (size_t)((w + 1) / 2) * ((h + 1) / 2); }
 
@@ -146,8 +138,10 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
         src = std::move(s);
         p.in_width = p.in_height = 0;   // consumed as the input size
     } else {
-        set_err(err, errlen, "input container of '%s' needs the demux/decode front end, which is not built yet (SURVEY 8f1); y4m and raw yuv420p are accepted", input);
-        return VCPENC_E_FORMAT;
+        // container input: what the producer forwards (.mp4 .mkv .avi .mov .webm, cmd/producer.go:485-488)
+        rc = open_container_source(input, p.drop_audio != 0, &src, err, errlen);
+        if (rc) return rc;
+        if (p.in_width > 0 && p.width == 0) { p.width = p.in_width; p.height = p.in_height; }   // -s after -i = output size
     }
     // output size: -vf scale=W:H (negative = keep aspect, rounded to even), else -s WxH on a
     // self-describing input, else the input size
