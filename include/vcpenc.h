@@ -81,7 +81,9 @@ typedef struct vcpenc_params {
                                   keeps idr_pic_id alternating across shards        */
     int32_t drop_audio;        /* -an: container inputs with an audio stream are accepted,
                                   the audio is dropped (else VCPENC_E_AUDIO)         */
-    int32_t reserved[9];
+    int32_t transform8x8;      /* 1: High profile, transform_8x8_mode_flag: inter macroblocks use the
+                                  8x8 integer transform (-profile:v high, the libx264 default)  */
+    int32_t reserved[8];
 } vcpenc_params;
 
 /* per coded picture, filled by the encode calls */

@@ -248,6 +248,10 @@ typedef struct {
     int16_t mvd[2];
     uint8_t nnz_y[16];   /* raster (y*4+x) total_coeff of each luma 4x4 (AC only for I16) */
     uint8_t nnz_c[2][4]; /* raster (y*2+x), AC */
+    uint8_t t8x8;        /* transform_size_8x8_flag: luma coded as four 8x8 blocks.  Levels then sit in
+                          * lv[VCP_LV_LUMA..] as the entropy coder wants them: CAVLC = the four interleaved
+                          * 4x4 blocks of each 8x8 (block 4k+j, coefficient i <- scan position 4i+j, 9.2.1),
+                          * CABAC = 64 scan positions per 8x8; nnz_y likewise (per 4x4 / whole 8x8) */
     int16_t lv[VCP_LV_STRIDE];
 } MB;
 
@@ -281,6 +285,55 @@ static void idct4(const int c[16], int r[16]) {
         r[8 + i] = (e1 - e2 + 32) >> 6; r[12 + i] = (e0 - e3 + 32) >> 6;
     }
 }
+/* 8x8 forward transform (encoder's choice, matched by vcp_quant8_mf): rows, then columns */
+static void fdct8_1d(const int x[8], int y[8]) {
+    int a0 = x[0] + x[7], a1 = x[1] + x[6], a2 = x[2] + x[5], a3 = x[3] + x[4];
+    int b0 = a0 + a3, b1 = a1 + a2, b2 = a0 - a3, b3 = a1 - a2;
+    int a4 = x[0] - x[7], a5 = x[1] - x[6], a6 = x[2] - x[5], a7 = x[3] - x[4];
+    int b4 = a5 + a6 + ((a4 >> 1) + a4), b5 = a4 - a7 - ((a6 >> 1) + a6);
+    int b6 = a4 + a7 - ((a5 >> 1) + a5), b7 = a5 - a6 + ((a7 >> 1) + a7);
+    y[0] = b0 + b1; y[1] = b4 + (b7 >> 2); y[2] = b2 + (b3 >> 1); y[3] = b5 + (b6 >> 2);
+    y[4] = b0 - b1; y[5] = b6 - (b5 >> 2); y[6] = (b2 >> 1) - b3; y[7] = (b4 >> 2) - b7;
+}
+static void fdct8(const int d[64], int w[64]) {
+    int t[64], in[8], out[8];
+    for (int r = 0; r < 8; r++) { fdct8_1d(d + 8 * r, t + 8 * r); }
+    for (int c = 0; c < 8; c++) {
+        for (int r = 0; r < 8; r++) in[r] = t[8 * r + c];
+        fdct8_1d(in, out);
+        for (int r = 0; r < 8; r++) w[8 * r + c] = out[r];
+    }
+}
+/* 8.5.13: one-dimensional inverse of the 8x8 transform */
+static void idct8_1d(const int d[8], int o[8]) {
+    int a0 = d[0] + d[4], a4 = d[0] - d[4], a2 = (d[2] >> 1) - d[6], a6 = d[2] + (d[6] >> 1);
+    int b0 = a0 + a6, b2 = a4 + a2, b4 = a4 - a2, b6 = a0 - a6;
+    int a1 = -d[3] + d[5] - d[7] - (d[7] >> 1), a3 = d[1] + d[7] - d[3] - (d[3] >> 1);
+    int a5 = -d[1] + d[7] + d[5] + (d[5] >> 1), a7 = d[3] + d[5] + d[1] + (d[1] >> 1);
+    int b1 = a1 + (a7 >> 2), b3 = a3 + (a5 >> 2), b5 = (a3 >> 2) - a5, b7 = a7 - (a1 >> 2);
+    o[0] = b0 + b7; o[1] = b2 + b5; o[2] = b4 + b3; o[3] = b6 + b1;
+    o[4] = b6 - b1; o[5] = b4 - b3; o[6] = b2 - b5; o[7] = b0 - b7;
+}
+static void idct8(const int c[64], int r[64]) {   /* each row first, then each column, then (x + 32) >> 6 */
+    int t[64], in[8], out[8];
+    for (int y = 0; y < 8; y++) idct8_1d(c + 8 * y, t + 8 * y);
+    for (int x = 0; x < 8; x++) {
+        for (int y = 0; y < 8; y++) in[y] = t[8 * y + x];
+        idct8_1d(in, out);
+        for (int y = 0; y < 8; y++) r[8 * y + x] = (out[y] + 32) >> 6;
+    }
+}
+/* position class of normAdjust8x8 (8-318) for raster index i = y*8+x */
+static int coef8_class(int i) {
+    int y = i >> 3, x = i & 7;
+    if (!(y & 3) && !(x & 3)) return 0;
+    if ((y & 1) && (x & 1)) return 1;
+    if ((y & 3) == 2 && (x & 3) == 2) return 2;
+    if ((!(y & 3) && (x & 1)) || ((y & 1) && !(x & 3))) return 3;
+    if ((!(y & 3) && (x & 3) == 2) || ((y & 3) == 2 && !(x & 3))) return 4;
+    return 5;
+}
+
 static int quant1(int w, int mf, int f, int qbits) {
     int a = w < 0 ? -w : w;
     int l = (int)(((int64_t)a * mf + f) >> qbits);
@@ -308,6 +361,25 @@ static void dequant4x4(const int16_t lv[16], int qp, int first, int c[16]) {
 
 /* ------------------------------------------------------------------------------------ */
 /* inter prediction                                                                       */
+/* 8x8: levels in zig-zag order; returns the non-zero count */
+static int quant8x8(const int w[64], int qp, int intra, int16_t lv[64]) {
+    int qbits = 16 + qp / 6, f = (1 << qbits) / (intra ? 3 : 6), nz = 0;
+    for (int k = 0; k < 64; k++) {
+        int i = vcp_zigzag8x8[k];
+        lv[k] = (int16_t)quant1(w[i], vcp_quant8_mf[qp % 6][coef8_class(i)], f, qbits);
+        nz += lv[k] != 0;
+    }
+    return nz;
+}
+/* 8.5.12.1 with flat scaling lists: LevelScale8x8 = 16 * normAdjust8x8 */
+static void dequant8x8(const int16_t lv[64], int qp, int c[64]) {
+    for (int k = 0; k < 64; k++) {
+        int i = vcp_zigzag8x8[k];
+        int ls = 16 * vcp_dequant8_v[qp % 6][coef8_class(i)];
+        c[i] = qp >= 36 ? (lv[k] * ls) << (qp / 6 - 6) : (lv[k] * ls + (1 << (5 - qp / 6))) >> (6 - qp / 6);
+    }
+}
+
 static inline int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
 static inline int hb1(const uint8_t* r, int s, int x, int y) { /* horizontal half between x,x+1 */
     const uint8_t* p = r + (size_t)y * s + x; (void)s;
@@ -514,6 +586,40 @@ static void me_refine_mb(Enc* e, const Frame* ref, int mx, int my, int qp, int16
     if (vcp_intra_wins(intra_estimate(e, mx, my), (int)bcost, lam)) e->mbs[i].type = VCP_MB_I16;
 }
 
+/* 4x4 or 8x8 transform for an inter macroblock?  Sum of absolute Hadamard coefficients of the
+ * prediction residual, 4x4 blocks against 8x8 blocks (orthonormal scaling: |H8|/8 vs |H4|/4), the
+ * transform that compacts the residual better wins (vcp_algo.h: vcp_prefer_8x8). */
+static void hadamard4_2d(const int d[16], int h[16]) {
+    int t[16];
+    for (int i = 0; i < 4; i++) {
+        int a = d[4 * i] + d[4 * i + 1], b = d[4 * i] - d[4 * i + 1], c = d[4 * i + 2] + d[4 * i + 3], e2 = d[4 * i + 2] - d[4 * i + 3];
+        t[4 * i] = a + c; t[4 * i + 1] = b + e2; t[4 * i + 2] = a - c; t[4 * i + 3] = b - e2;
+    }
+    for (int i = 0; i < 4; i++) {
+        int a = t[i] + t[4 + i], b = t[i] - t[4 + i], c = t[8 + i] + t[12 + i], e2 = t[8 + i] - t[12 + i];
+        h[i] = a + c; h[4 + i] = b + e2; h[8 + i] = a - c; h[12 + i] = b - e2;
+    }
+}
+static int prefer_8x8(const uint8_t* src, int ss, const uint8_t pred[256]) {
+    long cost4 = 0, cost8 = 0;
+    for (int k = 0; k < 4; k++) {
+        int h[4][16];
+        for (int j = 0; j < 4; j++) {
+            int bx = (k & 1) * 8 + (j & 1) * 4, by = (k >> 1) * 8 + (j >> 1) * 4, d[16];
+            for (int y = 0; y < 4; y++)
+                for (int x = 0; x < 4; x++) d[4 * y + x] = src[(by + y) * ss + bx + x] - pred[(by + y) * 16 + bx + x];
+            hadamard4_2d(d, h[j]);
+            for (int i = 0; i < 16; i++) cost4 += abs(h[j][i]);
+        }
+        /* the 8x8 Hadamard of [[A,B],[C,D]] is the 4x4 Hadamard of A+-B+-C+-D */
+        for (int i = 0; i < 16; i++) {
+            int A = h[0][i], B = h[1][i], Cc = h[2][i], D = h[3][i];
+            cost8 += abs(A + B + Cc + D) + abs(A - B + Cc - D) + abs(A + B - Cc - D) + abs(A - B - Cc + D);
+        }
+    }
+    return vcp_prefer_8x8((int)cost4, (int)cost8);
+}
+
 /* ---- K3 (inter): predict, transform, quantise, reconstruct ------------------------------- */
 static void chroma_dc_fwd_quant(int dc[4], int qpc, int intra, int16_t lv[4], int deq[4]) {
     /* 2x2 Hadamard, quantise (8.5.11.2 inverse restated forward), dequantise */
@@ -586,6 +692,34 @@ static void encode_p_mb(Enc* e, const Frame* ref, Frame* rec, int mx, int my, in
     mc_chroma8(ref->v, ref->cs, 8 * mx, 8 * my, mb->mv[0], mb->mv[1], pv);
     const uint8_t* src = e->cur.y + (size_t)(16 * my) * e->cur.ys + 16 * mx;
     uint8_t* dst = rec->y + (size_t)(16 * my) * rec->ys + 16 * mx;
+    mb->t8x8 = 0;
+    if (e->p.transform8x8 && prefer_8x8(src, e->cur.ys, pred)) {
+        /* High profile: the four 8x8 luma blocks of an inter macroblock */
+        for (int k = 0; k < 4; k++) {
+            int bx = (k & 1) * 8, by = (k >> 1) * 8, d[64], w[64], c[64], r[64];
+            int16_t lv8[64];
+            for (int y = 0; y < 8; y++)
+                for (int x = 0; x < 8; x++)
+                    d[y * 8 + x] = src[(by + y) * e->cur.ys + bx + x] - pred[(by + y) * 16 + bx + x];
+            fdct8(d, w);
+            int nz = quant8x8(w, qp, 0, lv8);
+            if (nz) mb->cbp |= (uint8_t)(1 << k);
+            int cnt4[4] = {0, 0, 0, 0};
+            for (int i = 0; i < 64; i++) {
+                if (e->p.entropy) mb->lv[VCP_LV_LUMA + k * 64 + i] = lv8[i];
+                else mb->lv[VCP_LV_LUMA + (k * 4 + (i & 3)) * 16 + (i >> 2)] = lv8[i];
+                cnt4[i & 3] += lv8[i] != 0;
+            }
+            for (int j = 0; j < 4; j++)   /* luma4x4BlkIdx 4k+j */
+                mb->nnz_y[vcp_blk_y[4 * k + j] * 4 + vcp_blk_x[4 * k + j]] = (uint8_t)(e->p.entropy ? nz : cnt4[j]);
+            dequant8x8(lv8, qp, c);
+            idct8(c, r);
+            for (int y = 0; y < 8; y++)
+                for (int x = 0; x < 8; x++)
+                    dst[(by + y) * rec->ys + bx + x] = (uint8_t)vcp_clip255(pred[(by + y) * 16 + bx + x] + r[y * 8 + x]);
+        }
+        mb->t8x8 = (mb->cbp & 15) != 0;   /* the flag is only transmitted (else inferred 0) with coded luma */
+    } else
     for (int b = 0; b < 16; b++) {
         int bx = vcp_blk_x[b] * 4, by = vcp_blk_y[b] * 4, d[16], w[16], c[16], r[16];
         for (int y = 0; y < 4; y++)
@@ -693,7 +827,7 @@ static void pred_c8(const uint8_t* plane, int s, int mx, int my, int mode, int a
 static void encode_i_mb(Enc* e, Frame* rec, int mx, int my, int qp) {
     MB* mb = &e->mbs[my * e->mbw + mx];
     memset(mb->lv, 0, sizeof mb->lv);
-    mb->type = VCP_MB_I16; mb->cbp = 0; mb->mv[0] = mb->mv[1] = 0; mb->mvd[0] = mb->mvd[1] = 0;
+    mb->type = VCP_MB_I16; mb->cbp = 0; mb->mv[0] = mb->mv[1] = 0; mb->mvd[0] = mb->mvd[1] = 0; mb->t8x8 = 0;
     int row0 = slice_first_row(e, slice_of_row(e, my));
     int aL = mx > 0, aT = my > row0;
     const uint8_t* src = e->cur.y + (size_t)(16 * my) * e->cur.ys + 16 * mx;
@@ -794,9 +928,14 @@ static void encode_i_mb(Enc* e, Frame* rec, int mx, int my, int qp) {
 
 /* ------------------------------------------------------------------------------------ */
 /* K4: deblocking (8.7), macroblock raster order                                           */
+/* does the transform block holding 4x4 block `blk` (raster) carry coefficients? (8x8: the whole 8x8) */
+static int blk_coded(const MB* m, int blk) {
+    if (m->t8x8) return (m->cbp >> ((blk >> 3) * 2 + ((blk & 3) >> 1))) & 1;
+    return m->nnz_y[blk] != 0;
+}
 static int bs_of(const MB* p, const MB* q, int pblk, int qblk, int mbedge) {
     if (p->type == VCP_MB_I16 || q->type == VCP_MB_I16) return mbedge ? 4 : 3;
-    if (p->nnz_y[pblk] || q->nnz_y[qblk]) return 2;
+    if (blk_coded(p, pblk) || blk_coded(q, qblk)) return 2;
     if (abs(p->mv[0] - q->mv[0]) >= 4 || abs(p->mv[1] - q->mv[1]) >= 4) return 1;
     return 0;
 }
@@ -851,9 +990,10 @@ static void deblock_frame(Enc* e, Frame* f, int qp) {
             uint8_t* Y = f->y + (size_t)(16 * my) * f->ys + 16 * mx;
             uint8_t* U = f->u + (size_t)(8 * my) * f->cs + 8 * mx;
             uint8_t* V = f->v + (size_t)(8 * my) * f->cs + 8 * mx;
-            /* vertical edges */
+            /* vertical edges (transform_size_8x8_flag: luma edges 1 and 3 are not transform edges) */
             for (int ed = 0; ed < 4; ed++) {
                 if (ed == 0 && !left_ok) continue;
+                if ((ed & 1) && q->t8x8) continue;
                 const MB* p = ed == 0 ? q - 1 : q;
                 int bS[4];
                 for (int k = 0; k < 4; k++) bS[k] = bs_of(p, q, k * 4 + (ed == 0 ? 3 : ed - 1), k * 4 + ed, ed == 0);
@@ -872,6 +1012,7 @@ static void deblock_frame(Enc* e, Frame* f, int qp) {
             /* horizontal edges */
             for (int ed = 0; ed < 4; ed++) {
                 if (ed == 0 && !top_ok) continue;
+                if ((ed & 1) && q->t8x8) continue;
                 const MB* p = ed == 0 ? q - e->mbw : q;
                 int bS[4];
                 for (int k = 0; k < 4; k++) bS[k] = bs_of(p, q, (ed == 0 ? 12 : 4 * (ed - 1)) + k, 4 * ed + k, ed == 0);
@@ -1063,16 +1204,20 @@ static int mb_dc_cbf(const MB* m, int which /*0 luma DC, 1 Cb DC, 2 Cr DC*/) {
 
 /* residual_block_cabac (7.3.5.3.3) for coefficients c[0..n-1] in scan order */
 static void cabac_block(Cabac* cb, const int16_t* c, int n, int cat, int cbf_inc) {
-    static const int cbf_off[5] = {0, 4, 8, 12, 16}, sig_off[5] = {0, 15, 29, 44, 47}, abs_off[5] = {0, 10, 20, 30, 39};
+    /* ctxBlockCat 0..4 (tables 9-34, 9-40); 5 = luma 8x8: own context ranges 402 / 417 / 426, position
+     * dependent increments (table 9-43), no coded_block_flag (inferred from the coded block pattern) */
+    static const int cbf_off[5] = {0, 4, 8, 12, 16}, sig_off[5] = {0, 15, 29, 44, 47}, abs_off[6] = {0, 10, 20, 30, 39, 199};
     int last = -1;
     for (int i = 0; i < n; i++) if (c[i]) last = i;
-    cabac_encode(cb, 85 + cbf_off[cat] + cbf_inc, last >= 0);
+    if (cat != 5) cabac_encode(cb, 85 + cbf_off[cat] + cbf_inc, last >= 0);
     if (last < 0) return;
     for (int i = 0; i < n - 1; i++) {
-        int inc = cat == 3 ? (i < 2 ? i : 2) : i;
-        cabac_encode(cb, 105 + sig_off[cat] + inc, c[i] != 0);
+        int sctx, lctx;
+        if (cat == 5) { sctx = 402 + vcp_cabac_sig8x8[i]; lctx = 417 + vcp_cabac_last8x8[i]; }
+        else { int inc = cat == 3 ? (i < 2 ? i : 2) : i; sctx = 105 + sig_off[cat] + inc; lctx = 166 + sig_off[cat] + inc; }
+        cabac_encode(cb, sctx, c[i] != 0);
         if (c[i]) {
-            cabac_encode(cb, 166 + sig_off[cat] + inc, i == last);
+            cabac_encode(cb, lctx, i == last);
             if (i == last) break;
         }
     }
@@ -1165,11 +1310,17 @@ static void write_slice_data_cabac(Enc* e, BW* b, int r0, int r1, int idr, int q
                     cabac_encode(&c, 77 + (ca > 0) + 2 * (cbb > 0), (cur >> 4) > 0);
                     if (cur >> 4) cabac_encode(&c, 77 + 4 + (ca == 2) + 2 * (cbb == 2), (cur >> 4) == 2);
                 }
+                if (!intra && e->p.transform8x8 && (mb->cbp & 15))
+                    cabac_encode(&c, 399 + (A && A->t8x8) + (B && B->t8x8), mb->t8x8);   /* transform_size_8x8_flag */
                 if (intra || mb->cbp) cabac_encode(&c, 60, 0);   /* mb_qp_delta = 0 (and so was the previous one) */
                 /* residual */
                 const int un = intra ? 1 : 0;   /* flag assumed for an unavailable neighbour */
                 if (intra)
                     cabac_block(&c, mb->lv + VCP_LV_LUMA_DC, 16, 0, (A ? mb_dc_cbf(A, 0) : un) + 2 * (B ? mb_dc_cbf(B, 0) : un));
+                if (mb->t8x8) {
+                    for (int k = 0; k < 4; k++)
+                        if (mb->cbp & (1 << k)) cabac_block(&c, mb->lv + VCP_LV_LUMA + k * 64, 64, 5, 0);
+                } else
                 for (int blk = 0; blk < 16; blk++) {
                     if (!(mb->cbp & (1 << (blk >> 2)))) continue;
                     int bx = vcp_blk_x[blk], by = vcp_blk_y[blk];
@@ -1214,10 +1365,17 @@ static int level_idc_for(int mbw, int mbh, int fps_num, int fps_den) {
 static size_t write_sps(const Enc* e, uint8_t* out, size_t cap) {
     uint8_t tmp[128]; BW b; bw_init(&b, tmp, sizeof tmp);
     const vcpenc_params* p = &e->p;
-    if (p->entropy) { bw_put(&b, 8, 77); bw_put(&b, 8, 0x40); }   /* Main (CABAC), constraint_set1 */
-    else { bw_put(&b, 8, 66); bw_put(&b, 8, 0xC0); }              /* Constrained Baseline: constraint_set0,1 */
+    if (p->transform8x8) { bw_put(&b, 8, 100); bw_put(&b, 8, 0x00); }  /* High */
+    else if (p->entropy) { bw_put(&b, 8, 77); bw_put(&b, 8, 0x40); }   /* Main (CABAC), constraint_set1 */
+    else { bw_put(&b, 8, 66); bw_put(&b, 8, 0xC0); }                   /* Constrained Baseline: constraint_set0,1 */
     bw_put(&b, 8, level_idc_for(e->mbw, e->mbh, p->fps_num, p->fps_den));
     bw_ue(&b, 0);                   /* sps id */
+    if (p->transform8x8) {          /* profile_idc 100: chroma format and bit depth fields */
+        bw_ue(&b, 1);               /* chroma_format_idc 4:2:0 */
+        bw_ue(&b, 0); bw_ue(&b, 0); /* bit_depth_luma/chroma_minus8 */
+        bw_put(&b, 1, 0);           /* qpprime_y_zero_transform_bypass */
+        bw_put(&b, 1, 0);           /* seq_scaling_matrix_present */
+    }
     bw_ue(&b, 4);                   /* log2_max_frame_num_minus4 -> 8 bits */
     bw_ue(&b, 2);                   /* pic_order_cnt_type 2: output order == decode order */
     bw_ue(&b, 1);                   /* max_num_ref_frames */
@@ -1267,8 +1425,12 @@ static size_t write_pps(const Enc* e, uint8_t* out, size_t cap) {
     bw_put(&b, 1, 1);               /* deblocking_filter_control_present */
     bw_put(&b, 1, 0);               /* constrained_intra_pred */
     bw_put(&b, 1, 0);               /* redundant_pic_cnt_present */
+    if (e->p.transform8x8) {
+        bw_put(&b, 1, 1);           /* transform_8x8_mode_flag */
+        bw_put(&b, 1, 0);           /* pic_scaling_matrix_present */
+        bw_se(&b, 0);               /* second_chroma_qp_index_offset */
+    }
     bw_trailing(&b);
-    (void)e;
     return nal_write(out, cap, 3, 8, tmp, b.pos);
 }
 static void write_slice_header(const Enc* e, BW* b, int first_mb, int idr, int frame_num, int idr_id, int qp) {
@@ -1308,6 +1470,7 @@ static void write_slice_data(Enc* e, BW* b, int r0, int r1, int idr) {
                 bw_ue(b, 0); /* P_L0_16x16 */
                 bw_se(b, mb->mvd[0]); bw_se(b, mb->mvd[1]);
                 bw_ue(b, vcp_cbp_to_golomb_inter[mb->cbp]);
+                if (e->p.transform8x8 && (mb->cbp & 15)) bw_put(b, 1, mb->t8x8);   /* transform_size_8x8_flag */
                 if (mb->cbp) bw_se(b, 0);
             }
             cavlc_residual(b, e, mb, mx, my);
@@ -1487,3 +1650,8 @@ int orc_ue_bits(unsigned k, uint8_t* out) { BW b; bw_init(&b, out, 8); bw_ue(&b,
 int orc_se_bits(int v, uint8_t* out) { BW b; bw_init(&b, out, 8); bw_se(&b, v); int n = (int)bw_bits(&b); if (b.nbits) bw_put(&b, 8 - b.nbits, 0); return n; }
 int orc_luma_qpel(const uint8_t* plane, int stride, int ix, int iy, int fx, int fy) { return luma_qpel(plane, stride, ix, iy, fx, fy); }
 int orc_lambda(int qp) { return vcp_lambda(qp); }
+void orc_fdct8(const int* d, int* w) { fdct8(d, w); }
+void orc_roundtrip8(const int* d, int qp, int* r) {
+    int w[64], c[64]; int16_t lv[64];
+    fdct8(d, w); quant8x8(w, qp, 0, lv); dequant8x8(lv, qp, c); idct8(c, r);
+}

@@ -20,9 +20,10 @@ from oracle import pyoracle  # noqa: E402
 from video_codec_pipeline_b200 import arbiter, synth  # noqa: E402
 
 out = []
-for (w, h, n, gop, sl, idc, qp, ent) in [c + (0,) for c in CASES] + [c + (1,) for c in CASES]:
+for (w, h, n, gop, sl, idc, qp, ent, t8) in [c + (0, 0) for c in CASES] + [c + (1, 0) for c in CASES] + \
+        [c + (0, 1) for c in CASES[2:]] + [c + (1, 1) for c in CASES[2:]]:
     clip = synth.make_clip(w, h, n, seed=1000 + w + qp)
-    p = pyoracle.make_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc, entropy=ent)
+    p = pyoracle.make_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc, entropy=ent, transform8x8=t8)
     r = pyoracle.encode(p, clip)
     dec = arbiter.decode_annexb(r["stream"])
     assert len(dec) == n
@@ -30,7 +31,7 @@ for (w, h, n, gop, sl, idc, qp, ent) in [c + (0,) for c in CASES] + [c + (1,) fo
         flat = np.concatenate([pl.ravel() for pl in dec[i]])
         assert np.array_equal(flat, r["recon"][i]), (w, h, i)
     out.append({
-        "w": w, "h": h, "frames": n, "gop": gop, "slices": sl, "deblock_idc": idc, "qp": qp, "entropy": ent,
+        "w": w, "h": h, "frames": n, "gop": gop, "slices": sl, "deblock_idc": idc, "qp": qp, "entropy": ent, "transform8x8": t8,
         "seed": 1000 + w + qp,
         "clip_sha256": hashlib.sha256(clip.tobytes()).hexdigest(),
         "stream_bytes": len(r["stream"]),
@@ -38,6 +39,6 @@ for (w, h, n, gop, sl, idc, qp, ent) in [c + (0,) for c in CASES] + [c + (1,) fo
         "recon_sha256": hashlib.sha256(r["recon"].tobytes()).hexdigest(),
         "frame_sizes": [x[1] for x in r["info"]],
     })
-    print("ok", w, h, n, gop, sl, idc, qp, ent, len(r["stream"]))
+    print("ok", w, h, n, gop, sl, idc, qp, ent, t8, len(r["stream"]))
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "h264_golden.json"), "w") as f:
     json.dump(out, f, indent=1)

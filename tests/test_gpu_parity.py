@@ -26,15 +26,16 @@ def _flat(planes):
     return np.concatenate([pl.ravel() for pl in planes])
 
 
-@pytest.mark.parametrize("entropy", [0, 1], ids=["cavlc", "cabac"])
+@pytest.mark.parametrize("entropy,t8", [(0, 0), (1, 0), (0, 1), (1, 1)], ids=["cavlc", "cabac", "cavlc-high", "cabac-high"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "%dx%d_n%d_g%d_s%d_d%d_q%d" % c)
-def test_cuda_equals_oracle(built, case, entropy):
+def test_cuda_equals_oracle(built, case, entropy, t8):
     from oracle import pyoracle
     w, h, n, gop, sl, idc, qp = case
     clip = synth.make_clip(w, h, n, seed=1000 + w + qp)
     ref = pyoracle.encode(pyoracle.make_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc,
-                                               entropy=entropy), clip, want_dump=True)
-    p = api.default_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc, debug=1, entropy=entropy)
+                                               entropy=entropy, transform8x8=t8), clip, want_dump=True)
+    p = api.default_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc, debug=1, entropy=entropy,
+                           transform8x8=t8)
     with api.Session(p, n) as s:
         s.upload(clip)
         s.encode()
@@ -47,23 +48,27 @@ def test_cuda_equals_oracle(built, case, entropy):
     assert [x[1] for x in got["info"]] == [x[1] for x in ref["info"]]
 
 
-@pytest.mark.parametrize("g", GOLD, ids=lambda g: "%dx%d_q%d_s%d_e%d" % (g["w"], g["h"], g["qp"], g["slices"], g.get("entropy", 0)))
+@pytest.mark.parametrize("g", GOLD, ids=lambda g: "%dx%d_q%d_s%d_e%d_t%d" % (g["w"], g["h"], g["qp"], g["slices"], g.get("entropy", 0), g.get("transform8x8", 0)))
 def test_cuda_matches_golden(built, g):
     clip = synth.make_clip(g["w"], g["h"], g["frames"], seed=g["seed"])
     p = api.default_params(g["w"], g["h"], gop=g["gop"], qp_i=max(0, g["qp"] - 2), qp_p=g["qp"],
-                           slices=g["slices"], deblock_idc=g["deblock_idc"], entropy=g.get("entropy", 0))
+                           slices=g["slices"], deblock_idc=g["deblock_idc"], entropy=g.get("entropy", 0),
+                           transform8x8=g.get("transform8x8", 0))
     got = api.encode_frames(p, clip, want_recon=True)             # host buffers in, host buffers out
     assert [x[1] for x in got["info"]] == g["frame_sizes"]
     assert hashlib.sha256(got["stream"].tobytes()).hexdigest() == g["stream_sha256"]
     assert hashlib.sha256(got["recon"].tobytes()).hexdigest() == g["recon_sha256"]
 
 
-@pytest.mark.parametrize("w,h,n,gop,sl", [(1920, 1080, 24, 8, 1), (1920, 1080, 12, 6, 4), (3840, 2160, 6, 3, 1)])
-def test_full_size_decoder_reproduces_recon(built, w, h, n, gop, sl):
+@pytest.mark.parametrize("w,h,n,gop,sl,kw", [(1920, 1080, 24, 8, 1, {}), (1920, 1080, 12, 6, 4, {}), (3840, 2160, 6, 3, 1, {}),
+                                             (1920, 1080, 12, 6, 0, dict(entropy=1, transform8x8=1)),
+                                             (3840, 2160, 6, 3, 0, dict(entropy=1, transform8x8=1))],
+                         ids=["1080p", "1080p-4slices", "4k", "1080p-high-cabac", "4k-high-cabac"])
+def test_full_size_decoder_reproduces_recon(built, w, h, n, gop, sl, kw):
     if not arbiter.available():
         pytest.skip("bundled FFmpeg decoder not present")
     clip = synth.make_clip(w, h, n, seed=w)
-    p = api.default_params(w, h, gop=gop, qp_i=25, qp_p=27, slices=sl, debug=1)
+    p = api.default_params(w, h, gop=gop, qp_i=25, qp_p=27, slices=sl, debug=1, **kw)
     got = api.encode_frames(p, clip, want_recon=True)
     dec = arbiter.decode_annexb(got["stream"].tobytes(), threads=8)
     assert len(dec) == n
@@ -79,7 +84,7 @@ def test_full_size_decoder_reproduces_recon(built, w, h, n, gop, sl):
         parts = []
         for f0, cnt, g0 in gop_ranges(n, gop, world):
             if cnt:
-                q = api.default_params(w, h, gop=gop, qp_i=25, qp_p=27, slices=sl, first_gop=g0)
+                q = api.default_params(w, h, gop=gop, qp_i=25, qp_p=27, slices=sl, first_gop=g0, **kw)
                 parts.append(api.encode_frames(q, clip[f0:f0 + cnt])["stream"].tobytes())
         assert b"".join(parts) == got["stream"].tobytes()
 

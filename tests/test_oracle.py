@@ -112,14 +112,15 @@ def test_luma_interpolation_flat_and_ramp():
     assert L.orc_luma_qpel(ramp.ctypes.data, 32, 10, 10, 0, 2) == 40
 
 
-@pytest.mark.parametrize("entropy", [0, 1], ids=["cavlc", "cabac"])
+@pytest.mark.parametrize("entropy,t8", [(0, 0), (1, 0), (0, 1), (1, 1)], ids=["cavlc", "cabac", "cavlc-high", "cabac-high"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "%dx%d_n%d_g%d_s%d_d%d_q%d" % c)
-def test_oracle_stream_decodes_to_its_own_recon(case, entropy):
+def test_oracle_stream_decodes_to_its_own_recon(case, entropy, t8):
     if not arbiter.available():
         pytest.skip("bundled FFmpeg decoder not present")
     w, h, n, gop, sl, idc, qp = case
     clip = synth.make_clip(w, h, n, seed=1000 + w + qp)
-    p = pyoracle.make_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc, entropy=entropy)
+    p = pyoracle.make_params(w, h, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc, entropy=entropy,
+                             transform8x8=t8)
     r = pyoracle.encode(p, clip)
     dec = arbiter.decode_annexb(r["stream"])
     assert len(dec) == n
@@ -132,12 +133,13 @@ def test_oracle_stream_decodes_to_its_own_recon(case, entropy):
     assert arbiter.psnr(dec[n - 1][0], y) > (18 if qp > 45 else 28)
 
 
-@pytest.mark.parametrize("g", GOLD, ids=lambda g: "%dx%d_q%d_s%d_e%d" % (g["w"], g["h"], g["qp"], g["slices"], g.get("entropy", 0)))
+@pytest.mark.parametrize("g", GOLD, ids=lambda g: "%dx%d_q%d_s%d_e%d_t%d" % (g["w"], g["h"], g["qp"], g["slices"], g.get("entropy", 0), g.get("transform8x8", 0)))
 def test_oracle_matches_golden(g):
     clip = synth.make_clip(g["w"], g["h"], g["frames"], seed=g["seed"])
     assert hashlib.sha256(clip.tobytes()).hexdigest() == g["clip_sha256"], "synthetic clip generator drifted"
     p = pyoracle.make_params(g["w"], g["h"], gop=g["gop"], qp_i=max(0, g["qp"] - 2), qp_p=g["qp"],
-                             slices=g["slices"], deblock_idc=g["deblock_idc"], entropy=g.get("entropy", 0))
+                             slices=g["slices"], deblock_idc=g["deblock_idc"], entropy=g.get("entropy", 0),
+                             transform8x8=g.get("transform8x8", 0))
     r = pyoracle.encode(p, clip)
     assert [x[1] for x in r["info"]] == g["frame_sizes"]
     assert hashlib.sha256(r["stream"]).hexdigest() == g["stream_sha256"]
@@ -164,6 +166,24 @@ def test_oracle_edge_cases():
     bad = pyoracle.make_params(w, h, gop=0)
     with pytest.raises(RuntimeError):
         pyoracle.encode(bad, clip)
+
+
+def test_transform8x8_roundtrip_and_tables():
+    """High profile 8x8: forward transform + quantiser + normative dequantiser + inverse transform give the
+    residual back (flat at QP 0 within 1, the quantiser's MF table matches the forward transform's norms),
+    and a DC-only block has the expected coefficient."""
+    L = _lib()
+    rng = np.random.default_rng(8)
+    d = np.full(64, 5, np.int32)
+    w = np.zeros(64, np.int32)
+    L.orc_fdct8(d.ctypes.data_as(C.POINTER(C.c_int)), w.ctypes.data_as(C.POINTER(C.c_int)))
+    assert w[0] == 5 * 64 and not w[1:].any()
+    for qp, tol in ((0, 1), (12, 5), (24, 20)):   # quantiser step 0.625, 2.5, 10
+        for _ in range(20):
+            d = rng.integers(-200, 201, 64).astype(np.int32)
+            r = np.zeros(64, np.int32)
+            L.orc_roundtrip8(d.ctypes.data_as(C.POINTER(C.c_int)), qp, r.ctypes.data_as(C.POINTER(C.c_int)))
+            assert np.abs(r - d).max() <= tol, (qp, np.abs(r - d).max())
 
 
 def test_cabac_engine_known_answers():

@@ -53,6 +53,7 @@ extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_param
     vcpenc_default_params(p);
     p->slices = 0;     // unless -slices is given the encoder chooses (vcp_auto_slices)
     p->entropy = -1;   // unless -coder / -profile:v says otherwise: the codec's default (CABAC for libx264 / nvenc)
+    p->transform8x8 = -1;   // likewise: High profile tools unless -profile:v baseline / main
     bool have_codec = false, have_crf = false, have_qp = false;
     int crf = 23;
     for (int i = 0; i < argc; i++) {
@@ -90,6 +91,7 @@ extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_param
             if (!need(&v)) return VCPENC_E_ARGS;
             // baseline has no CABAC; main / high default to it (an explicit -coder still wins)
             if (p->entropy < 0 && !strcmp(v, "baseline")) p->entropy = 0;
+            p->transform8x8 = !strncmp(v, "high", 4) ? 1 : 0;   // baseline, main: 4x4 transform only
         } else if (t == "-tune" || t == "-level" || t == "-threads" || t == "-refs" ||
                    t == "-c:a" || t == "-acodec" || t == "-b:a" || t == "-ar" || t == "-ac" || t == "-f" ||
                    t == "-rc" || t == "-rc-lookahead" || t == "-x264-params" || t == "-x264opts") {
@@ -175,6 +177,7 @@ extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_param
     }
     (void)have_codec;
     if (p->entropy < 0) p->entropy = 1;   // x264 and NVENC both default to CABAC
+    if (p->transform8x8 < 0) p->transform8x8 = 1;   // ... and to High profile
     if (have_crf && !have_qp) {
         // constant quality: one QP per picture type (x264's default ipratio 1.4 ~ 3 QP)
         p->qp_p = crf + 1 > 51 ? 51 : crf + 1;

@@ -289,7 +289,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     g.yoff = VCP_PAD * g.ys + VCP_PAD;
     g.coff = VCP_PADC * g.cs + VCP_PADC;
     g.hoff = VCP_PAD1 * g.hs + VCP_PAD1;
-    g.slices = pp->slices; g.deblock_idc = pp->deblock_idc; g.cabac = pp->entropy;
+    g.slices = pp->slices; g.deblock_idc = pp->deblock_idc; g.cabac = pp->entropy; g.t8x8 = pp->transform8x8 ? 1 : 0;
     g.rc_abr = pp->rc_mode == VCPENC_RC_ABR;
     g.rc_bitrate = pp->bitrate; g.fps_num = pp->fps_num; g.fps_den = pp->fps_den;
     g.rc_qp0 = g.rc_abr ? vcp_rc_initial_qp(pp->bitrate, pp->fps_num, pp->fps_den, pp->width, pp->height) : 0;

@@ -20,10 +20,17 @@ int level_idc_for(int mbw, int mbh, int fps_num, int fps_den) {
 std::vector<uint8_t> make_sps_nal(const vcpenc_params& p) {
     const int mbw = (p.width + 15) / 16, mbh = (p.height + 15) / 16;
     BitWriter b;
-    if (p.entropy) { b.put(8, 77); b.put(8, 0x40); }   // Main (CABAC), constraint_set1
-    else { b.put(8, 66); b.put(8, 0xC0); }             // Constrained Baseline: constraint_set0/1
+    if (p.transform8x8) { b.put(8, 100); b.put(8, 0x00); }   // High
+    else if (p.entropy) { b.put(8, 77); b.put(8, 0x40); }    // Main (CABAC), constraint_set1
+    else { b.put(8, 66); b.put(8, 0xC0); }                   // Constrained Baseline: constraint_set0/1
     b.put(8, (uint32_t)level_idc_for(mbw, mbh, p.fps_num, p.fps_den));
     b.ue(0);         // seq_parameter_set_id
+    if (p.transform8x8) {   // profile_idc 100 carries the chroma format / bit depth fields
+        b.ue(1);            // chroma_format_idc: 4:2:0
+        b.ue(0); b.ue(0);   // bit_depth_luma_minus8, bit_depth_chroma_minus8
+        b.put(1, 0);        // qpprime_y_zero_transform_bypass_flag
+        b.put(1, 0);        // seq_scaling_matrix_present_flag
+    }
     b.ue(4);         // log2_max_frame_num_minus4
     b.ue(2);         // pic_order_cnt_type
     b.ue(1);         // max_num_ref_frames
@@ -74,6 +81,11 @@ std::vector<uint8_t> make_pps_nal(const vcpenc_params& p) {
     b.put(1, 1);     // deblocking_filter_control_present_flag
     b.put(1, 0);     // constrained_intra_pred_flag
     b.put(1, 0);     // redundant_pic_cnt_present_flag
+    if (p.transform8x8) {
+        b.put(1, 1); // transform_8x8_mode_flag
+        b.put(1, 0); // pic_scaling_matrix_present_flag
+        b.se(0);     // second_chroma_qp_index_offset
+    }
     b.trailing();
     return nal_escape(3, 8, b.bytes());
 }

@@ -24,7 +24,161 @@ __device__ __forceinline__ int blk_ras(int b) { return blk_y4(b) * 4 + blk_x4(b)
 // pred4[r] = the lane's four predicted rows (packed 4 px); returns per-lane nz of the AC part
 struct __align__(16) McScratch {
     uint8_t pred[16][16];
+    int t8[4][64];          // 8x8 transform staging (High profile): one 8x8 block per four lanes
 };
+
+// ---- 8x8 transform path of an inter macroblock (High profile) --------------------------------------
+__device__ __forceinline__ void fdct8_1d(const int x[8], int y[8]) {
+    const int a0 = x[0] + x[7], a1 = x[1] + x[6], a2 = x[2] + x[5], a3 = x[3] + x[4];
+    const int b0 = a0 + a3, b1 = a1 + a2, b2 = a0 - a3, b3 = a1 - a2;
+    const int a4 = x[0] - x[7], a5 = x[1] - x[6], a6 = x[2] - x[5], a7 = x[3] - x[4];
+    const int b4 = a5 + a6 + ((a4 >> 1) + a4), b5 = a4 - a7 - ((a6 >> 1) + a6);
+    const int b6 = a4 + a7 - ((a5 >> 1) + a5), b7 = a5 - a6 + ((a7 >> 1) + a7);
+    y[0] = b0 + b1; y[1] = b4 + (b7 >> 2); y[2] = b2 + (b3 >> 1); y[3] = b5 + (b6 >> 2);
+    y[4] = b0 - b1; y[5] = b6 - (b5 >> 2); y[6] = (b2 >> 1) - b3; y[7] = (b4 >> 2) - b7;
+}
+__device__ __forceinline__ void idct8_1d(const int d[8], int o[8]) {   // 8.5.13
+    const int a0 = d[0] + d[4], a4 = d[0] - d[4], a2 = (d[2] >> 1) - d[6], a6 = d[2] + (d[6] >> 1);
+    const int b0 = a0 + a6, b2 = a4 + a2, b4 = a4 - a2, b6 = a0 - a6;
+    const int a1 = -d[3] + d[5] - d[7] - (d[7] >> 1), a3 = d[1] + d[7] - d[3] - (d[3] >> 1);
+    const int a5 = -d[1] + d[7] + d[5] + (d[5] >> 1), a7 = d[3] + d[5] + d[1] + (d[1] >> 1);
+    const int b1 = a1 + (a7 >> 2), b3 = a3 + (a5 >> 2), b5 = (a3 >> 2) - a5, b7 = a7 - (a1 >> 2);
+    o[0] = b0 + b7; o[1] = b2 + b5; o[2] = b4 + b3; o[3] = b6 + b1;
+    o[4] = b6 - b1; o[5] = b4 - b3; o[6] = b2 - b5; o[7] = b0 - b7;
+}
+
+// 4x4 or 8x8?  Sums of absolute Hadamard coefficients of the residual (oracle: prefer_8x8).  Lanes 0..15
+// hold the residual of their 4x4 block; the 8x8 Hadamard of [[A,B],[C,D]] is the 4x4 Hadamard of
+// A+-B+-C+-D, i.e. two shuffle butterflies among the four lanes of an 8x8 block.
+__device__ __forceinline__ bool prefer_8x8(const uint8_t* __restrict__ src, int stride, const uint32_t predw[4], int lane) {
+    int h[16];
+    int c4 = 0, c8 = 0;
+    {
+        int d[16], t[16];
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            const uint32_t s4 = lane < 16 ? ld_u32(src + (size_t)y * stride) : 0u, p4 = lane < 16 ? predw[y] : 0u;
+#pragma unroll
+            for (int x = 0; x < 4; x++) d[4 * y + x] = (int)((s4 >> (8 * x)) & 255) - (int)((p4 >> (8 * x)) & 255);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int a = d[4 * i] + d[4 * i + 1], bb = d[4 * i] - d[4 * i + 1], c = d[4 * i + 2] + d[4 * i + 3], e = d[4 * i + 2] - d[4 * i + 3];
+            t[4 * i] = a + c; t[4 * i + 1] = bb + e; t[4 * i + 2] = a - c; t[4 * i + 3] = bb - e;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int a = t[i] + t[4 + i], bb = t[i] - t[4 + i], c = t[8 + i] + t[12 + i], e = t[8 + i] - t[12 + i];
+            h[i] = a + c; h[4 + i] = bb + e; h[8 + i] = a - c; h[12 + i] = bb - e;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        c4 += vcp_iabs(h[i]);
+        const int p1 = __shfl_xor_sync(0xffffffffu, h[i], 1);
+        const int u = (lane & 1) ? p1 - h[i] : h[i] + p1;          // A+B | A-B | C+D | C-D
+        const int p2 = __shfl_xor_sync(0xffffffffu, u, 2);
+        const int v = (lane & 2) ? p2 - u : u + p2;                // the four sign combinations
+        c8 += vcp_iabs(v);
+    }
+    const int cost4 = warp_sum(lane < 16 ? c4 : 0), cost8 = warp_sum(lane < 16 ? c8 : 0);
+    return vcp_prefer_8x8(cost4, cost8) != 0;
+}
+
+// Luma of an inter macroblock as four 8x8 blocks: four lanes per block (k = lane >> 2, q = lane & 3),
+// a lane owns rows 2q,2q+1 in the row passes and columns 2q,2q+1 in the column passes; the passes
+// meet in shared memory.  The inverse runs rows first, then columns, as 8.5.13 prescribes.
+// S.pred holds the prediction on entry and the reconstruction on exit.  Returns the luma cbp.
+__device__ __forceinline__ uint32_t luma8x8_transform(const VcpGeom& g, const VcpBufs& b, McScratch& S, int n, int gi, int mbi,
+                                                      int mx, int my, int qp, int lane) {
+    const bool act = lane < 16;
+    const int k = (lane >> 2) & 3, q = lane & 3;
+    const int bx = (k & 1) * 8, by = (k >> 1) * 8;
+    int* T = S.t8[k];
+    const uint8_t* src = b.src_y + (size_t)n * g.ysize + g.yoff + (size_t)(16 * my + by) * g.ys + 16 * mx + bx;
+    if (act) {
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const int r = 2 * q + rr;
+            const uint2 s8 = *reinterpret_cast<const uint2*>(src + (size_t)r * g.ys);
+            const uint2 p8 = *reinterpret_cast<const uint2*>(&S.pred[by + r][bx]);
+            int d[8], y[8];
+#pragma unroll
+            for (int x = 0; x < 8; x++) {
+                const uint32_t sw = x < 4 ? s8.x : s8.y, pw = x < 4 ? p8.x : p8.y;
+                d[x] = (int)((sw >> (8 * (x & 3))) & 255) - (int)((pw >> (8 * (x & 3))) & 255);
+            }
+            fdct8_1d(d, y);
+#pragma unroll
+            for (int x = 0; x < 8; x++) T[8 * r + x] = y[x];
+        }
+    }
+    __syncwarp();
+    const int qbits = 16 + qp / 6, f = (1 << qbits) / 6, rem = qp % 6, sh = qp / 6;
+    int nz = 0, cnt4 = 0;   // cnt4: four 8-bit counters, one per interleaved 4x4 block (CAVLC)
+    int16_t* lvp = b.levels + ((size_t)gi * g.nmb + mbi) * VCP_LV_STRIDE + VCP_LV_LUMA;
+    if (act) {
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            const int col = 2 * q + cc;
+            int in[8], w[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) in[r] = T[8 * r + col];
+            fdct8_1d(in, w);
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int i = 8 * r + col;
+                const int cls = vcp_coef8_class[i], zz = vcp_izigzag8x8[i];
+                const int l = vcp_quant1(w[r], vcp_quant8_mf[rem][cls], f, qbits);
+                nz += l != 0;
+                cnt4 += (l != 0) << (8 * (zz & 3));
+                lvp[g.cabac ? k * 64 + zz : (k * 4 + (zz & 3)) * 16 + (zz >> 2)] = (int16_t)l;
+                const int ls = 16 * vcp_dequant8_v[rem][cls];
+                T[i] = qp >= 36 ? (l * ls) << (sh - 6) : (l * ls + (1 << (5 - sh))) >> (6 - sh);
+            }
+        }
+    }
+    // totals of the 8x8 block over its four lanes
+    nz += __shfl_xor_sync(0xffffffffu, nz, 1); nz += __shfl_xor_sync(0xffffffffu, nz, 2);
+    cnt4 += __shfl_xor_sync(0xffffffffu, cnt4, 1); cnt4 += __shfl_xor_sync(0xffffffffu, cnt4, 2);
+    if (act) {
+        // nnz of luma4x4BlkIdx 4k+q: CABAC = coefficients of the whole 8x8; CAVLC = of its interleaved
+        // 4x4, with bit 7 flagging "the 8x8 holds coefficients" for the deblocking strength
+        const int blk = 4 * k + q;
+        const int v = g.cabac ? (nz > 255 ? 255 : nz) : (((cnt4 >> (8 * q)) & 255) | (nz ? 0x80 : 0));
+        b.nnz[((size_t)gi * g.nmb + mbi) * 24 + blk_y4(blk) * 4 + blk_x4(blk)] = (uint8_t)v;
+    }
+    __syncwarp();
+    if (act) {   // inverse: rows
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const int r = 2 * q + rr;
+            int in[8], o[8];
+#pragma unroll
+            for (int x = 0; x < 8; x++) in[x] = T[8 * r + x];
+            idct8_1d(in, o);
+#pragma unroll
+            for (int x = 0; x < 8; x++) T[8 * r + x] = o[x];
+        }
+    }
+    __syncwarp();
+    if (act) {   // inverse: columns, then reconstruct in place of the prediction
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            const int col = 2 * q + cc;
+            int in[8], o[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) in[r] = T[8 * r + col];
+            idct8_1d(in, o);
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+                S.pred[by + r][bx + col] = (uint8_t)vcp_clip255((int)S.pred[by + r][bx + col] + ((o[r] + 32) >> 6));
+        }
+    }
+    __syncwarp();
+    const uint32_t coded = __ballot_sync(0xffffffffu, act && nz > 0);
+    return ((coded & 0x000fu) ? 1u : 0u) | ((coded & 0x00f0u) ? 2u : 0u) | ((coded & 0x0f00u) ? 4u : 0u) | ((coded & 0xf000u) ? 8u : 0u);
+}
 
 __device__ __forceinline__ void store_block_recon(uint8_t* dst, int stride, const uint32_t pred[4], const int r[16]) {
 #pragma unroll
@@ -39,9 +193,9 @@ __device__ __forceinline__ void store_block_recon(uint8_t* dst, int stride, cons
 // intra16: luma DC goes through the 4x4 Hadamard (dcbuf = 16 ints of shared scratch).
 __device__ __forceinline__ void mb_transform(const VcpGeom& g, const VcpBufs& b, int n, int slot, int gi, int mbi,
                                              int mx, int my, int qp, bool intra16, const uint32_t predw[4],
-                                             int* dcbuf, int lane, uint32_t& cbp_out) {
+                                             int* dcbuf, int lane, uint32_t& cbp_out, bool luma_off = false) {
     const int qpc = vcp_chroma_qp[vcp_clip3(0, 51, qp)];
-    const bool is_luma = lane < 16, is_chroma = lane >= 16 && lane < 24;
+    const bool is_luma = lane < 16 && !luma_off, is_chroma = lane >= 16 && lane < 24;
     const int pl = (lane - 16) >> 2, cb = lane & 3;
     int bx = 0, by = 0;
     const uint8_t* src = nullptr;
@@ -215,11 +369,30 @@ __global__ void __launch_bounds__(PR_WARPS * 32) p_recon_kernel(VcpGeom g, VcpBu
         for (int y = 0; y < 4; y++) predw[y] = *reinterpret_cast<const uint32_t*>(&cpred[warp][pl][by + y][bx]);
     }
     uint32_t cbp;
-    mb_transform(g, b, n, slot, gi, mbi, mx, my, qp, false, predw, nullptr, lane, cbp);
+    bool use8 = false;
+    if (g.t8x8) {
+        const uint8_t* sb = b.src_y + (size_t)n * g.ysize + g.yoff + (size_t)(16 * my + blk_y4(lane & 15) * 4) * g.ys + 16 * mx + blk_x4(lane & 15) * 4;
+        use8 = prefer_8x8(sb, g.ys, predw, lane);
+    }
+    if (use8) {
+        const uint32_t cbpl = luma8x8_transform(g, b, S, n, gi, mbi, mx, my, qp, lane);
+        if (lane < 16) {   // the reconstruction sits where the prediction was: write this lane's 4x4 block
+            const int bx = blk_x4(lane) * 4, by = blk_y4(lane) * 4;
+            uint8_t* dst = vcp_rec_luma(b, g, slot) + g.yoff + (size_t)(16 * my + by) * g.ys + 16 * mx + bx;
+#pragma unroll
+            for (int y = 0; y < 4; y++) *reinterpret_cast<uint32_t*>(dst + (size_t)y * g.ys) = *reinterpret_cast<const uint32_t*>(&S.pred[by + y][bx]);
+        }
+        mb_transform(g, b, n, slot, gi, mbi, mx, my, qp, false, predw, nullptr, lane, cbp, true);   // chroma only
+        cbp = (cbp & ~15u) | cbpl;
+        use8 = cbpl != 0;   // transform_size_8x8_flag is only transmitted (else inferred 0) with coded luma
+    } else {
+        mb_transform(g, b, n, slot, gi, mbi, mx, my, qp, false, predw, nullptr, lane, cbp);
+    }
     if (lane == 0) {
         b.cbp[(size_t)gi * g.nmb + mbi] = (uint8_t)cbp;
         b.mbtype[(size_t)gi * g.nmb + mbi] = VCP_MB_P16;
-        b.modes[(size_t)gi * g.nmb + mbi] = (uint8_t)((cbp >> 8) << 4);   // DC coded_block_flags (VCP_MODES_DCF_SHIFT)
+        // DC coded_block_flags in bits 4..6, transform_size_8x8_flag in bit 7
+        b.modes[(size_t)gi * g.nmb + mbi] = (uint8_t)(((cbp >> 8) << 4) | (use8 ? 0x80 : 0));
     }
 }
 

@@ -118,6 +118,7 @@ struct DbPrefetch {
     uint32_t y0, y1;   // luma: lane -> row = lane>>1, words 2*(lane&1), +1
     uint32_t c;        // chroma: lane -> plane = lane>>4, row = (lane>>1)&7, word lane&1
     uint8_t pt, qt, pn, qn;   // types and nnz of the two 4x4 blocks across this lane's edge segment
+    uint8_t qf;               // modes byte of the current macroblock (bit 7: transform_size_8x8_flag)
     short2 pm, qm;
 };
 
@@ -128,6 +129,7 @@ struct DbLaneAddr {
     const uint8_t* c;     // chroma: plane lane>>4, row (lane>>1)&7, 4 bytes at 4*(lane&1)
     const uint8_t* qt;    // mbtype of the current macroblock
     const uint8_t* qn;    // nnz of the q-side block
+    const uint8_t* qf;    // modes of the current macroblock
     const short2* qm;     // mv of the current macroblock
     int p_mb_off;         // macroblock offset of the p side (0, -1 or -mbw)
     int pn_off;           // nnz byte offset of the p-side block relative to qn
@@ -148,6 +150,7 @@ __device__ __forceinline__ DbLaneAddr db_lane_addr(const VcpGeom& g, const VcpBu
     const size_t qo = base + (size_t)my * g.mbw;
     a.qt = b.mbtype + qo;
     a.qn = b.nnz + qo * 24 + qblk;
+    a.qf = b.modes + qo;
     a.qm = b.mv + qo;
     a.needs_left = mbedge && dir == 0;
     a.off = mbedge && dir == 1 && !top_ok;
@@ -165,6 +168,7 @@ __device__ __forceinline__ DbPrefetch db_prefetch(const DbLaneAddr& a, int mx) {
     const int po = dead ? 0 : a.p_mb_off;
     f.qt = a.qt[mx]; f.pt = a.qt[mx + po];
     f.qn = a.qn[24 * mx]; f.pn = a.qn[24 * mx + (dead ? 0 : a.pn_off)];
+    f.qf = a.qf[mx];
     f.qm = a.qm[mx]; f.pm = a.qm[mx + po];
     if (dead) f.pt = 0xff;   // marks "edge not filtered"
     return f;
@@ -173,6 +177,9 @@ __device__ __forceinline__ DbPrefetch db_prefetch(const DbLaneAddr& a, int mx) {
 __device__ __forceinline__ int db_strength(const DbPrefetch& f, int lane) {
     const bool mbedge = ((lane >> 2) & 3) == 0;
     if (f.pt == 0xff) return 0;
+    // transform_size_8x8_flag: luma edges 1 and 3 are not transform block edges (chroma takes its
+    // strengths from edges 0 and 2 only)
+    if ((lane & 4) && f.qt == VCP_MB_P16 && (f.qf & 0x80)) return 0;
     if (f.pt == VCP_MB_I16 || f.qt == VCP_MB_I16) return mbedge ? 4 : 3;
     if (f.pn || f.qn) return 2;
     if (mbedge && (vcp_iabs(f.pm.x - f.qm.x) >= 4 || vcp_iabs(f.pm.y - f.qm.y) >= 4)) return 1;

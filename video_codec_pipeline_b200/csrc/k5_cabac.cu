@@ -25,6 +25,7 @@
 
 #define VCP_TAB static __device__ const
 #include "h264_cabac_tables.h"
+#include "h264_tables.h"
 #include "vcp_entropy.cuh"
 
 namespace {
@@ -90,6 +91,42 @@ __device__ __forceinline__ void cabac_block(BinSink<WRITE>& bs, const int16_t* c
     }
 }
 
+// ctxBlockCat 5: one 8x8 luma block, 64 scan positions, no coded_block_flag (inferred from the coded
+// block pattern); significance contexts by position (table 9-43), levels from ctxIdx 426
+template <bool WRITE>
+__device__ __forceinline__ void cabac_block8x8(BinSink<WRITE>& bs, const int16_t* c) {
+    unsigned long long mask = 0;
+    for (int i = 0; i < 64; i++) mask |= (unsigned long long)(c[i] != 0) << i;
+    if (!mask) return;
+    const int last = 63 - __clzll((long long)mask);
+    for (int i = 0; i < 63; i++) {
+        const int sig = (int)((mask >> i) & 1);
+        bs.put(402 + vcp_cabac_sig8x8[i], sig);
+        if (sig) {
+            bs.put(417 + vcp_cabac_last8x8[i], i == last);
+            if (i == last) break;
+        }
+    }
+    int gt1 = 0, eq1 = 0;
+    unsigned long long m = mask;
+    while (m) {
+        const int i = 63 - __clzll((long long)m);
+        m &= ~(1ull << i);
+        const int v = c[i];
+        const int a = vcp_iabs(v) - 1;
+        const int inc = gt1 ? 0 : (1 + eq1 < 4 ? 1 + eq1 : 4);
+        bs.put(426 + inc, a > 0);
+        if (a > 0) {
+            const int ctx = 426 + 5 + (gt1 < 4 ? gt1 : 4);
+            const int ones = a < 14 ? a : 14;
+            for (int k = 1; k < ones; k++) bs.put(ctx, 1);
+            if (a < 14) bs.put(ctx, 0); else bs.ueg((uint32_t)(a - 14), 0);
+            gt1++;
+        } else eq1++;
+        bs.bypass(v < 0);
+    }
+}
+
 template <bool WRITE>
 __device__ __forceinline__ void cabac_mvd(BinSink<WRITE>& bs, int base, int v, int amvd) {
     const int a = vcp_iabs(v);
@@ -110,7 +147,7 @@ struct MbCtx {
     int type, cbp, modes;           // this macroblock
     int tA, cbpA, modesA, tB, cbpB, modesB;   // neighbours (t = -1: unavailable)
     short2 mvd, mvdA, mvdB;
-    bool idr, last_in_slice;
+    bool idr, last_in_slice, t8x8_mode;
 };
 
 // all bins of one macroblock; `lane` selects the syntax group
@@ -160,6 +197,8 @@ __device__ __forceinline__ void mb_bins(BinSink<WRITE>& bs, const CbScratch& S, 
             const int ca = aA && M.tA != VCP_MB_PSKIP ? M.cbpA >> 4 : 0, cb = aB && M.tB != VCP_MB_PSKIP ? M.cbpB >> 4 : 0;
             bs.put(77 + (ca > 0) + 2 * (cb > 0), cbpc > 0);
             if (cbpc) bs.put(77 + 4 + (ca == 2) + 2 * (cb == 2), cbpc == 2);
+            if (M.t8x8_mode && cbpl)   // transform_size_8x8_flag
+                bs.put(399 + (aA && (M.modesA & 0x80) && M.tA == VCP_MB_P16) + (aB && (M.modesB & 0x80) && M.tB == VCP_MB_P16), (M.modes >> 7) & 1);
         }
         if (intra || M.cbp) bs.put(60, 0);   // mb_qp_delta == 0
     } else if (lane == 1) {
@@ -170,7 +209,9 @@ __device__ __forceinline__ void mb_bins(BinSink<WRITE>& bs, const CbScratch& S, 
         }
     } else if (lane < 18) {
         const int blk = lane - 2;
-        if (cbpl & (1 << (blk >> 2))) {
+        if (!intra && (M.modes & 0x80)) {
+            if (!(blk & 3) && (cbpl & (1 << (blk >> 2)))) cabac_block8x8<WRITE>(bs, S.lv + VCP_LV_LUMA + (blk >> 2) * 64);
+        } else if (cbpl & (1 << (blk >> 2))) {
             const int bx = (blk & 1) | ((blk >> 1) & 2), by = ((blk >> 1) & 1) | ((blk >> 2) & 2);
             const int fa = bx > 0 ? S.nnz[0][by * 4 + bx - 1] != 0 : aA ? S.nnz[1][by * 4 + 3] != 0 : un;
             const int fb = by > 0 ? S.nnz[0][(by - 1) * 4 + bx] != 0 : aB ? S.nnz[2][12 + bx] != 0 : un;
@@ -215,6 +256,7 @@ __global__ void __launch_bounds__(CB_WARPS * 32) cabac_bins_kernel(VcpGeom g, Vc
     M.mvdA = aL ? b.mvd[o - 1] : make_short2(0, 0);
     M.mvdB = aT ? b.mvd[o - g.mbw] : make_short2(0, 0);
     M.idr = s.t == 0;
+    M.t8x8_mode = g.t8x8 != 0;
     {
         const int r1 = sl + 1 < g.slices ? vcp_slice_first_row(sl + 1, g.slices, g.mbh) : g.mbh;
         M.last_in_slice = (my == r1 - 1) && (mx == g.mbw - 1);

@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(CV_WARPS * 32) cavlc_mb_kernel(VcpGeom g, VcpB
         const int w = lane / 6, c = lane % 6;
         const size_t src = w == 0 ? o : (w == 1 ? o - 1 : o - g.mbw);
         const bool ok = w == 0 || (w == 1 ? aL : aT);
-        reinterpret_cast<uint32_t*>(S.nnz[w])[c] = ok ? reinterpret_cast<const uint32_t*>(b.nnz + src * 24)[c] : 0u;
+        // bit 7 of a luma count only tells the deblocking filter that the 8x8 block is coded
+        reinterpret_cast<uint32_t*>(S.nnz[w])[c] = ok ? (reinterpret_cast<const uint32_t*>(b.nnz + src * 24)[c] & 0x7f7f7f7fu) : 0u;
     }
     // preceding skip run (P slices): cooperative look-back inside the slice
     int skip_run = 0;
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(CV_WARPS * 32) cavlc_mb_kernel(VcpGeom g, VcpB
             bs.ue(0);
             bs.se(d.x); bs.se(d.y);
             bs.ue(vcp_cbp_to_golomb_inter[cbp]);
+            if (g.t8x8 && cbpl) bs.put(1, (uint32_t)(b.modes[o] >> 7));   // transform_size_8x8_flag
             if (cbp) bs.se(0);
         }
     } else if (lane == 1) {

@@ -49,6 +49,10 @@ VCP_HD int vcp_auto_slices(int mbh, int cabac) {
     return n < 1 ? 1 : n;
 }
 
+// transform size of an inter macroblock (High profile): cost4 / cost8 = sums of absolute 4x4 / 8x8
+// Hadamard coefficients of the prediction residual; with orthonormal scaling the 8x8 sum weighs half
+VCP_HD int vcp_prefer_8x8(int cost4, int cost8) { return cost8 < 2 * cost4; }
+
 // macroblock types stored by the encoder
 #define VCP_MB_I16 0
 #define VCP_MB_P16 1

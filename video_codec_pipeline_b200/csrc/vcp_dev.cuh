@@ -26,6 +26,7 @@ struct VcpGeom {
     int slices;
     int deblock_idc;
     int cabac;         // entropy_coding_mode_flag
+    int t8x8;          // transform_8x8_mode_flag (High profile)
     // rate control (VCPENC_RC_ABR): see vcp_algo.h
     int rc_abr, rc_qp0, rc_bitrate, fps_num, fps_den;
 };
