@@ -42,26 +42,28 @@ QP_I, QP_P = 25, 27
 SEED = 1080
 ENTROPY = 0
 SLICES = 1
+T8X8 = 0
 METRIC = "1080p H.264 encode fps (GOP=60, CAVLC, I+P)"
 WORKLOAD = "configs[1]: 1080p30 yuv420p, GOP=60, CAVLC, I+P, deblock, CQP 25/27"
 
 
 def select_workload(name: str, entropy: int, slices: int = -1):
-    """Default = BASELINE.json configs[1].  `4k` = the single-GPU shard of configs[2] (4K60, CABAC by
-    default; the 8x8 transform of High profile is not built yet, so the stream is Main profile)."""
-    global W, H, FPS, SEED, ENTROPY, METRIC, WORKLOAD, SLICES
+    """Default = BASELINE.json configs[1].  `4k` = the single-GPU shard of configs[2]: 4K60, High
+    profile (CABAC + 8x8 transform) unless --entropy 0 asks for the CAVLC/Baseline variant."""
+    global W, H, FPS, SEED, ENTROPY, METRIC, WORKLOAD, SLICES, T8X8
     if name == "4k":
         W, H, FPS, SEED = 3840, 2160, 60, 2160
         ENTROPY = 1 if entropy < 0 else entropy
+        T8X8 = 1 if ENTROPY else 0
     else:
         ENTROPY = 0 if entropy < 0 else entropy
     coder = "CABAC" if ENTROPY else "CAVLC"
     mbh = (H + 15) // 16
     # slices: the encoder's own choice unless given (vcp_algo.h vcp_auto_slices: CAVLC 1; CABAC one per ~17 rows)
     SLICES = slices if slices >= 0 else (max(1, mbh // 17) if ENTROPY else 1)
-    METRIC = "%s H.264 encode fps (GOP=60, %s, I+P)" % ("4K" if name == "4k" else "1080p", coder)
+    METRIC = "%s H.264 encode fps (GOP=60, %s%s, I+P)" % ("4K" if name == "4k" else "1080p", "High profile, " if T8X8 else "", coder)
     WORKLOAD = "%s: %dx%d@%d yuv420p, GOP=60, %s, %d slice%s, I+P, deblock, CQP %d/%d" % (
-        "configs[2] (one GPU's GOP shard, Main profile)" if name == "4k" else "configs[1]", W, H, FPS, coder,
+        ("configs[2] (one GPU's GOP shard, %s profile)" % ("High" if T8X8 else "Baseline")) if name == "4k" else "configs[1]", W, H, FPS, coder,
         SLICES, "" if SLICES == 1 else "s", QP_I, QP_P)
 
 
@@ -139,7 +141,7 @@ def cpu_port_fps(frames: np.ndarray, threads: int, frames_per_gop: int):
         jobs.append(frames[g * GOP: g * GOP + frames_per_gop])
 
     def one(fr):
-        p = pyoracle.make_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, entropy=ENTROPY, slices=SLICES)
+        p = pyoracle.make_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, entropy=ENTROPY, slices=SLICES, transform8x8=T8X8)
         return len(pyoracle.encode(p, fr, want_recon=False)["stream"])
 
     pyoracle.lib()
@@ -217,7 +219,7 @@ def main():
     n = frames.shape[0]
     fb = frames.shape[1]
     p = api.default_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, slices=SLICES, deblock_idc=0,
-                           first_gop=rank * args.gops, entropy=ENTROPY)
+                           first_gop=rank * args.gops, entropy=ENTROPY, transform8x8=T8X8)
     host = torch.from_numpy(frames).pin_memory()
     dev = host.to("cuda", non_blocking=False)
     out_host = torch.empty(n * fb // 2 + (1 << 20), dtype=torch.uint8).pin_memory()

@@ -139,6 +139,11 @@ int vcpenc_device_count(void);           /* honours CUDA_VISIBLE_DEVICES; 0 if n
  * runs one consumer process per GPU under CUDA_VISIBLE_DEVICES (install.sh:279-297), where 0 is
  * right; a host that drives several GPUs from one process binds each worker thread with this. */
 int vcpenc_set_thread_device(int device);
+/* vcpenc_transcode keeps the encoder session and the page-locked staging buffer of the calling
+ * thread for its next task (creating and freeing ~15 GB of device buffers costs more than encoding
+ * a short clip).  A host that retires a worker thread releases them with this call; VCPENC_NO_CACHE=1
+ * in the environment turns the reuse off. */
+void vcpenc_thread_release(void);
 const char* vcpenc_version(void);
 void vcpenc_default_params(vcpenc_params* p);
 

@@ -49,6 +49,8 @@ def test_parse_reference_presets(built):
     p = api.parse_args(PRESETS["h264-cpu"].split())
     assert p.codec == 0 and p.rc_mode == 0 and p.faststart == 1 and p.qp_p == 24 and p.qp_i == 21
     assert p.entropy == 1 and p.slices == 0          # x264's default coder; slice count left to the encoder
+    assert p.transform8x8 == 1                       # ... and x264's default profile (High)
+    assert api.parse_args("-c:v libx264 -profile:v main".split()).transform8x8 == 0
     assert api.parse_args("-c:v libx264 -profile:v baseline".split()).entropy == 0
     assert api.parse_args("-c:v libx264 -profile:v baseline -coder 1".split()).entropy == 1
     p = api.parse_args(PRESETS["h264-nvenc"].split())

@@ -228,6 +228,13 @@ def test_transcode_drop_in(built, tmp_path):
     api.verify(str(out))
     data = out.read_bytes()
     assert data.find(b"moov") < data.find(b"mdat")
+    # the calling thread keeps its session for the next task: same bytes from the reused session,
+    # from a differently sized task in between, and after an explicit release
+    api.transcode(str(y4m), str(out), "-c:v libx264 -preset medium -crf 23 -c:a aac -b:a 128k -movflags +faststart -g 8")
+    assert out.read_bytes() == data
+    api.thread_release()
+    api.transcode(str(y4m), str(out), "-c:v libx264 -preset medium -crf 23 -c:a aac -b:a 128k -movflags +faststart -g 8")
+    assert out.read_bytes() == data
     if arbiter.available():
         assert arbiter.probe_has_video(str(out))
         dec = arbiter.decode_file(str(out))

@@ -288,6 +288,11 @@ def probe_input(path, max_frames=0):
     return info
 
 
+def thread_release():
+    """Free the session / pinned buffer transcode() keeps for the calling thread."""
+    lib().vcpenc_thread_release()
+
+
 def parse_args(tokens):
     """strings.Fields(ffmpeg_args) -> Params (raises VcpencError, e.g. NOTENCODE for `-c copy`)."""
     L = lib()

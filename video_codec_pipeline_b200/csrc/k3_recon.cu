@@ -22,9 +22,17 @@ __device__ __forceinline__ int blk_ras(int b) { return blk_y4(b) * 4 + blk_x4(b)
 
 // ---- shared tail: chroma residual of lanes 16..23, writes levels / nnz / recon ---------------
 // pred4[r] = the lane's four predicted rows (packed 4 px); returns per-lane nz of the AC part
+constexpr int T8_STRIDE = 72;   // ints per 8x8 block: 64 + 8 of padding keeps the four blocks on different banks
 struct __align__(16) McScratch {
     uint8_t pred[16][16];
-    int t8[4][64];          // 8x8 transform staging (High profile): one 8x8 block per four lanes
+    int t8[4][T8_STRIDE];   // 8x8 transform staging (High profile): one 8x8 block per four lanes
+    int16_t lv8[256];       // levels of the four 8x8 blocks in record order, written out as 16-byte vectors
+};
+// per-CTA copies of the 8x8 tables: indexed per lane, so shared memory rather than constant
+struct T8Tables {
+    uint8_t cls[64], izz[64];
+    uint16_t mf[6][6];
+    uint8_t v[6][6];
 };
 
 // ---- 8x8 transform path of an inter macroblock (High profile) --------------------------------------
@@ -89,8 +97,8 @@ __device__ __forceinline__ bool prefer_8x8(const uint8_t* __restrict__ src, int 
 // a lane owns rows 2q,2q+1 in the row passes and columns 2q,2q+1 in the column passes; the passes
 // meet in shared memory.  The inverse runs rows first, then columns, as 8.5.13 prescribes.
 // S.pred holds the prediction on entry and the reconstruction on exit.  Returns the luma cbp.
-__device__ __forceinline__ uint32_t luma8x8_transform(const VcpGeom& g, const VcpBufs& b, McScratch& S, int n, int gi, int mbi,
-                                                      int mx, int my, int qp, int lane) {
+__device__ __forceinline__ uint32_t luma8x8_transform(const VcpGeom& g, const VcpBufs& b, McScratch& S, const T8Tables& TT,
+                                                      int n, int gi, int mbi, int mx, int my, int qp, int lane) {
     const bool act = lane < 16;
     const int k = (lane >> 2) & 3, q = lane & 3;
     const int bx = (k & 1) * 8, by = (k >> 1) * 8;
@@ -116,7 +124,7 @@ __device__ __forceinline__ uint32_t luma8x8_transform(const VcpGeom& g, const Vc
     __syncwarp();
     const int qbits = 16 + qp / 6, f = (1 << qbits) / 6, rem = qp % 6, sh = qp / 6;
     int nz = 0, cnt4 = 0;   // cnt4: four 8-bit counters, one per interleaved 4x4 block (CAVLC)
-    int16_t* lvp = b.levels + ((size_t)gi * g.nmb + mbi) * VCP_LV_STRIDE + VCP_LV_LUMA;
+    int16_t* lvp = S.lv8;
     if (act) {
 #pragma unroll
         for (int cc = 0; cc < 2; cc++) {
@@ -128,12 +136,12 @@ __device__ __forceinline__ uint32_t luma8x8_transform(const VcpGeom& g, const Vc
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 const int i = 8 * r + col;
-                const int cls = vcp_coef8_class[i], zz = vcp_izigzag8x8[i];
-                const int l = vcp_quant1(w[r], vcp_quant8_mf[rem][cls], f, qbits);
+                const int cls = TT.cls[i], zz = TT.izz[i];
+                const int l = vcp_quant1(w[r], TT.mf[rem][cls], f, qbits);
                 nz += l != 0;
                 cnt4 += (l != 0) << (8 * (zz & 3));
                 lvp[g.cabac ? k * 64 + zz : (k * 4 + (zz & 3)) * 16 + (zz >> 2)] = (int16_t)l;
-                const int ls = 16 * vcp_dequant8_v[rem][cls];
+                const int ls = 16 * TT.v[rem][cls];
                 T[i] = qp >= 36 ? (l * ls) << (sh - 6) : (l * ls + (1 << (5 - sh))) >> (6 - sh);
             }
         }
@@ -176,6 +184,8 @@ __device__ __forceinline__ uint32_t luma8x8_transform(const VcpGeom& g, const Vc
         }
     }
     __syncwarp();
+    // levels: 512 bytes per macroblock, one 16-byte vector per lane
+    reinterpret_cast<uint4*>(b.levels + ((size_t)gi * g.nmb + mbi) * VCP_LV_STRIDE + VCP_LV_LUMA)[lane] = reinterpret_cast<const uint4*>(S.lv8)[lane];
     const uint32_t coded = __ballot_sync(0xffffffffu, act && nz > 0);
     return ((coded & 0x000fu) ? 1u : 0u) | ((coded & 0x00f0u) ? 2u : 0u) | ((coded & 0x0f00u) ? 4u : 0u) | ((coded & 0xf000u) ? 8u : 0u);
 }
@@ -319,6 +329,12 @@ constexpr int PR_WARPS = 4;
 __global__ void __launch_bounds__(PR_WARPS * 32) p_recon_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
     __shared__ McScratch scr[PR_WARPS];
     __shared__ uint8_t cpred[PR_WARPS][2][8][8];
+    __shared__ T8Tables t8t;
+    if (g.t8x8) {
+        if (threadIdx.x < 64) { t8t.cls[threadIdx.x] = vcp_coef8_class[threadIdx.x]; t8t.izz[threadIdx.x] = vcp_izigzag8x8[threadIdx.x]; }
+        if (threadIdx.x < 36) { t8t.mf[threadIdx.x / 6][threadIdx.x % 6] = vcp_quant8_mf[threadIdx.x / 6][threadIdx.x % 6]; t8t.v[threadIdx.x / 6][threadIdx.x % 6] = vcp_dequant8_v[threadIdx.x / 6][threadIdx.x % 6]; }
+        __syncthreads();
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mbi = blockIdx.x * PR_WARPS + warp;
     const int gi = blockIdx.y + s.g0;
@@ -375,7 +391,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32) p_recon_kernel(VcpGeom g, VcpBu
         use8 = prefer_8x8(sb, g.ys, predw, lane);
     }
     if (use8) {
-        const uint32_t cbpl = luma8x8_transform(g, b, S, n, gi, mbi, mx, my, qp, lane);
+        const uint32_t cbpl = luma8x8_transform(g, b, S, t8t, n, gi, mbi, mx, my, qp, lane);
         if (lane < 16) {   // the reconstruction sits where the prediction was: write this lane's 4x4 block
             const int bx = blk_x4(lane) * 4, by = blk_y4(lane) * 4;
             uint8_t* dst = vcp_rec_luma(b, g, slot) + g.yoff + (size_t)(16 * my + by) * g.ys + 16 * mx + bx;

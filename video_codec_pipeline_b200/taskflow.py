@@ -24,6 +24,7 @@ calls in the reference and for the client below; a real Redis works the same way
 from __future__ import annotations
 
 import os
+import sys
 import queue
 import socket
 import socketserver
@@ -333,9 +334,12 @@ class Stats:
 def process_task(client, task: Task, transcode, verify, poll=0.5, cancelled=lambda: False, stats: Stats | None = None):
     """cmd/consumer.go:220-318.  `transcode(input, output, ffmpeg_args, timeout_ms)` and `verify(path)`
     are the two executor calls (api.transcode / api.verify for the B200 path); they raise on failure."""
+    t_start = time.time()
+    marks = {}
+
     def note(kind, msg=""):
         if stats is not None:
-            stats.log.append((task.id, kind, msg))
+            stats.log.append((task.id, kind, msg, dict(marks, total=round(time.time() - t_start, 3))))
 
     def fail(reason, remove=None):
         note("failed", reason)
@@ -354,6 +358,7 @@ def process_task(client, task: Task, transcode, verify, poll=0.5, cancelled=lamb
         wait_for_file(task.input_path, 30.0, poll, cancelled)
     except Exception as e:  # noqa: BLE001
         return fail("input_file_unavailable: %s" % e)
+    marks["wait"] = round(time.time() - t_start, 3)
     try:
         os.makedirs(task.output_dir, mode=0o755, exist_ok=True)
     except OSError as e:
@@ -363,6 +368,7 @@ def process_task(client, task: Task, transcode, verify, poll=0.5, cancelled=lamb
         transcode(task.input_path, out, task.ffmpeg_args, 60 * 60 * 1000)
     except Exception as e:  # noqa: BLE001
         return fail("ffmpeg_failed: %s" % e, remove=out)
+    marks["encoded"] = round(time.time() - t_start, 3)
     if task.verify_output:
         try:
             verify(out)
@@ -385,8 +391,9 @@ def process_task(client, task: Task, transcode, verify, poll=0.5, cancelled=lamb
 class Consumer:
     """cmd/consumer.go:119-175: one reader (COUNT 1, BLOCK 3 s) feeding a channel of depth 2j, j workers."""
 
-    def __init__(self, addr, name, transcode, verify, concurrency=1, poll=0.5):
+    def __init__(self, addr, name, transcode, verify, concurrency=1, poll=0.5, on_exit=None):
         self.addr, self.name, self.j, self.poll = addr, name, max(1, concurrency), poll
+        self.on_exit = on_exit
         self.transcode, self.verify = transcode, verify
         self.stats = Stats()
         self.stop = threading.Event()
@@ -411,6 +418,8 @@ class Consumer:
                 self.stats.success += ok
                 self.stats.failed += not ok
         client.close()
+        if self.on_exit:
+            self.on_exit()          # e.g. api.thread_release: free the worker's cached encoder session
 
     def _reader(self):
         client = RedisClient(*self.addr)
@@ -491,13 +500,17 @@ def main(argv=None):
         return run
 
     t0 = time.time()
-    cons = [Consumer(srv.addr, "gpu%d" % (i % ngpu), make_exec(i % ngpu), api.verify, a.j, a.poll).start() for i in range(k)]
+    cons = [Consumer(srv.addr, "gpu%d" % (i % ngpu), make_exec(i % ngpu), api.verify, a.j, a.poll, api.thread_release).start() for i in range(k)]
     while sum(c.stats.processed for c in cons) < a.clips and time.time() - t0 < 3600:
         time.sleep(0.05)
     dt = time.time() - t0
     for c in cons:
         c.shutdown()
     ok = sum(c.stats.success for c in cons)
+    if os.environ.get("VCPENC_TRACE"):
+        for c in cons:
+            for entry in c.stats.log:
+                print("[taskflow]", c.name, entry, file=sys.stderr)
     print(json.dumps({"config": "configs[4]-style: %d clips x %d frames, preset %s, %d consumers x -j %d, MiniRedis stand-in" %
                       (a.clips, a.frames, a.preset, k, a.j), "tasks": a.clips, "succeeded": ok, "wall_s": round(dt, 3),
                       "tasks_per_s": round(a.clips / dt, 3), "aggregate_fps": round(total_frames / dt, 1),
