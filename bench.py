@@ -193,6 +193,8 @@ def main():
     ap.add_argument("--workload", default="1080p", choices=["1080p", "4k"], help="default: BASELINE.json configs[1]")
     ap.add_argument("--entropy", type=int, default=-1, help="0 CAVLC, 1 CABAC (default: what the workload names)")
     ap.add_argument("--slices", type=int, default=-1, help="slices per picture (default: the encoder's choice)")
+    ap.add_argument("--e2e-threads", type=int, default=2, help="host threads (sessions) of the end-to-end pipeline, like consumer -j")
+    ap.add_argument("--deblock-idc", type=int, default=0, help="experiments only: 1 switches the in-loop filter off")
     args = ap.parse_args()
     select_workload(args.workload, args.entropy, args.slices)
     if args.workload == "4k" and args.gops == 32:
@@ -218,7 +220,7 @@ def main():
     frames = make_workload(args.gops)
     n = frames.shape[0]
     fb = frames.shape[1]
-    p = api.default_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, slices=SLICES, deblock_idc=0,
+    p = api.default_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, slices=SLICES, deblock_idc=args.deblock_idc,
                            first_gop=rank * args.gops, entropy=ENTROPY, transform8x8=T8X8)
     host = torch.from_numpy(frames).pin_memory()
     dev = host.to("cuda", non_blocking=False)
@@ -266,7 +268,7 @@ def main():
     # drives the executor: the H2D copy of one batch overlaps the kernels of the other.  Every batch
     # still pays its own H2D of all frames and D2H of the whole bitstream inside the timed region.
     import threading as _th
-    nthreads = 2
+    nthreads = max(1, args.e2e_threads)
     sessions = [api.Session(p, n, device=local_rank) for _ in range(nthreads)]
     outs = [torch.empty(n * fb // 2 + (1 << 20), dtype=torch.uint8).pin_memory().numpy() for _ in range(nthreads)]
     errors = []

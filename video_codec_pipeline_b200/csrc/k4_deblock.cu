@@ -493,8 +493,8 @@ void vcp_launch_deblock(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cu
     // run concurrently on different streams)
     int* sync = b.db_sync + (size_t)s.g0 * (g.mbh + 1);
     cudaMemsetAsync(sync, 0, (size_t)(s.ngop * g.mbh + 1) * sizeof(int), st);
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(deblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr_set = true; }
+    // function attributes are per device: a process may drive several GPUs from different threads
+    if (smem > 48 * 1024) cudaFuncSetAttribute(deblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     deblock_kernel<<<s.ngop * nbands, BH * 32, smem, st>>>(g, b, s, BH, nbands, sync, sync + 1 - (size_t)s.g0 * g.mbh);
 }
 
