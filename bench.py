@@ -272,13 +272,19 @@ def main():
     sessions = [api.Session(p, n, device=local_rank) for _ in range(nthreads)]
     outs = [torch.empty(n * fb // 2 + (1 << 20), dtype=torch.uint8).pin_memory().numpy() for _ in range(nthreads)]
     errors = []
+    phase = [[0.0, 0.0, 0.0] for _ in range(nthreads)]   # host wall time in upload / encode / download
 
     def e2e_worker(i, count):
         try:
             for _ in range(count):
+                t_a = time.perf_counter()
                 sessions[i].upload(host.data_ptr(), n)
+                t_b = time.perf_counter()
                 sessions[i].encode()
+                t_c = time.perf_counter()
                 sessions[i].download(out=outs[i])
+                t_d = time.perf_counter()
+                phase[i][0] += t_b - t_a; phase[i][1] += t_c - t_b; phase[i][2] += t_d - t_c
         except Exception as ex:  # noqa: BLE001
             errors.append(ex)
 
@@ -291,6 +297,7 @@ def main():
             t.join()
 
     e2e_round(2)                       # warm-up
+    phase = [[0.0, 0.0, 0.0] for _ in range(nthreads)]
     barrier()
     t0 = time.perf_counter()
     e2e_round(args.steps)
@@ -339,7 +346,8 @@ def main():
                        "realtime_x": round(value / FPS, 1), "wall_ms_per_step": round(wall_ms / args.steps, 3),
                        "bitstream_bytes_per_step": stream_bytes},
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": n * fb,
-                    "d2h_bytes_per_step": stream_bytes},
+                    "d2h_bytes_per_step": stream_bytes, "threads": nthreads,
+                    "host_ms_per_step_upload_encode_download": [round(1000.0 * sum(ph[k] for ph in phase) / max(1, args.steps), 1) for k in range(3)]},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": top, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",

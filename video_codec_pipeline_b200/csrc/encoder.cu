@@ -64,6 +64,11 @@ struct vcpenc_session {
     int max_frames = 0, nframes = 0, ngop_max = 0, ring = 2;
     int gop_base = 0;  // clip-level index of the first resident GOP
     cudaStream_t st = nullptr, st_copy = nullptr;
+    cudaStream_t st_pre = nullptr;  // motion-search pre-pass, picture by picture, LOW priority: pure throughput work
+                                    // that fills the latency gaps of the reconstruction chains
+    std::vector<cudaEvent_t> ev_pre_t;   // pre-pass of picture t complete
+    cudaStream_t st_up = nullptr;   // K1 of an upload: high priority, so that it is not queued behind the
+                                    // thousands of CTAs of another session's encode on the same GPU
     static constexpr int kMaxGroups = 8;
     cudaStream_t gst[kMaxGroups] = {};          // one stream per GOP group (the recon chain)
     cudaStream_t est[kMaxGroups] = {};          // entropy coding of the group, off the chain
@@ -261,6 +266,9 @@ void vcpenc_session_destroy(vcpenc_session* s) {
     if (s->ev_pre) cudaEventDestroy(s->ev_pre);
     if (s->st) cudaStreamDestroy(s->st);
     if (s->st_copy) cudaStreamDestroy(s->st_copy);
+    if (s->st_up) cudaStreamDestroy(s->st_up);
+    if (s->st_pre) cudaStreamDestroy(s->st_pre);
+    for (auto e : s->ev_pre_t) cudaEventDestroy(e);
     delete s;
 }
 
@@ -301,6 +309,16 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
 #define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(err, errlen, "%s failed: %s", #call, cudaGetErrorString(e_)); vcpenc_session_destroy(s); return VCPENC_E_CUDA; } } while (0)
     CKS(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
     CKS(cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CKS(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        // lowest priority for both: K1 of an upload and the pre-pass are throughput work; the chains of a
+        // running encode (this session's or another one's on the same GPU) are latency-critical
+        CKS(cudaStreamCreateWithPriority(&s->st_up, cudaStreamNonBlocking, lo));
+        CKS(cudaStreamCreateWithPriority(&s->st_pre, cudaStreamNonBlocking, lo));
+        s->ev_pre_t.resize((size_t)std::min(pp->gop, max_frames));
+        for (auto& e : s->ev_pre_t) CKS(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     CKS(cudaEventCreate(&s->ev0)); CKS(cudaEventCreate(&s->ev1));
     CKS(cudaEventCreateWithFlags(&s->ev_pre, cudaEventDisableTiming));
     {
@@ -426,7 +444,7 @@ int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes,
     s->encoded = false;
     s->h_qp.resize(nframes);
     for (int n = 0; n < nframes; n++) s->h_qp[n] = initial_qp(s, n);
-    CK(cudaMemcpyAsync(s->b.qp, s->h_qp.data(), nframes, cudaMemcpyHostToDevice, s->st));
+    CK(cudaMemcpyAsync(s->b.qp, s->h_qp.data(), nframes, cudaMemcpyHostToDevice, s->st_up));
     int chunk = 0;
     for (int n0 = 0; n0 < nframes; n0 += s->staging_frames, chunk++) {
         const int k = chunk & 1;
@@ -434,12 +452,12 @@ int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes,
         if (chunk >= 2) CK(cudaStreamWaitEvent(s->st_copy, s->staging_free[k], 0));
         CK(cudaMemcpyAsync(s->staging[k], frames + (size_t)n0 * fb, (size_t)cnt * fb, cudaMemcpyHostToDevice, s->st_copy));
         CK(cudaEventRecord(s->staging_ready[k], s->st_copy));
-        CK(cudaStreamWaitEvent(s->st, s->staging_ready[k], 0));
-        k1_chain(s, s->staging[k], n0, cnt, s->st);
-        CK(cudaEventRecord(s->staging_free[k], s->st));
+        CK(cudaStreamWaitEvent(s->st_up, s->staging_ready[k], 0));
+        k1_chain(s, s->staging[k], n0, cnt, s->st_up);
+        CK(cudaEventRecord(s->staging_free[k], s->st_up));
     }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(s->st));
+    CK(cudaStreamSynchronize(s->st_up));
     if (s->profile) collect_profile(s);
     return VCPENC_OK;
 }
@@ -480,9 +498,19 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
         CK(cudaMemsetAsync(b.slice_bins, 0, (size_t)N * g.slices * sizeof(uint32_t), s->st));
         CK(cudaMemsetAsync(b.out_index, 0, (size_t)N * g.slices * sizeof(uint2), s->st));
     }
-    {
+    const int T = std::min(gop, N);
+    if (s->profile) {
         Prof pr(s, VCPENC_K_ME_PRE);
-        vcp_launch_me_prepass(g, b, N, gop, s->st);
+        vcp_launch_me_prepass(g, b, N, gop, -1, s->st);
+    } else {
+        // picture by picture on its own stream: chain step t only waits for the vectors of picture t
+        CK(cudaEventRecord(s->ev_pre, s->st));
+        CK(cudaStreamWaitEvent(s->st_pre, s->ev_pre, 0));
+        for (int t = 1; t < T; t++) {
+            s->launches += 1;
+            vcp_launch_me_prepass(g, b, N, gop, t, s->st_pre);
+            CK(cudaEventRecord(s->ev_pre_t[t], s->st_pre));
+        }
     }
     // GOP groups advance on their own streams: the latency-bound wavefront kernels (intra
     // recon, deblocking) of one group overlap the throughput-bound kernels of the others.
@@ -510,6 +538,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 Prof pr(s, VCPENC_K_I_RECON, 1, st);
                 vcp_launch_i_recon(g, bt, sp, st);
             } else {
+                if (!s->profile) CK(cudaStreamWaitEvent(st, s->ev_pre_t[t], 0));
                 { Prof pr(s, VCPENC_K_ME_REFINE, 1, st); vcp_launch_me_refine(g, bt, sp, st); }
                 { Prof pr(s, VCPENC_K_P_RECON, 2, st); vcp_launch_p_recon(g, bt, sp, st); vcp_launch_i_fix(g, bt, sp, st); }
                 { Prof pr(s, VCPENC_K_MBINFO, 1, st); vcp_launch_mbinfo(g, bt, sp, st); }

@@ -32,12 +32,14 @@ struct __align__(16) PrepassWarp {
     uint8_t ref[20][L0_W];
 };
 
-__global__ void __launch_bounds__(ME_WARPS * 32) me_prepass_kernel(VcpGeom g, VcpBufs b, int nframes, int gop) {
+// grid z = frame (t < 0: every resident frame) or GOP (t >= 0: picture t of every GOP, so that the
+// pre-pass of later pictures runs beside the reconstruction chain of earlier ones)
+__global__ void __launch_bounds__(ME_WARPS * 32) me_prepass_kernel(VcpGeom g, VcpBufs b, int nframes, int gop, int t) {
     __shared__ __align__(16) uint8_t win[L1_WIN_H][L1_WIN_WA];
     __shared__ PrepassWarp pw[ME_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.z;
-    if (n % gop == 0) return;  // IDR: no search
+    const int n = t < 0 ? (int)blockIdx.z : (int)blockIdx.z * gop + t;
+    if (n >= nframes || n % gop == 0) return;  // IDR: no search
     const int my = blockIdx.y, mx0 = blockIdx.x * ME_WARPS, mx = mx0 + warp;
     const uint8_t* hc = b.src_h + (size_t)n * g.hsize + g.hoff;
     const uint8_t* hp = b.src_h + (size_t)(n - 1) * g.hsize + g.hoff;
@@ -282,10 +284,12 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
 
 }  // namespace
 
-void vcp_launch_me_prepass(const VcpGeom& g, const VcpBufs& b, int nframes, int gop, cudaStream_t st) {
+void vcp_launch_me_prepass(const VcpGeom& g, const VcpBufs& b, int nframes, int gop, int t, cudaStream_t st) {
     if (nframes <= 0) return;
-    dim3 grid((g.mbw + ME_WARPS - 1) / ME_WARPS, g.mbh, nframes);
-    me_prepass_kernel<<<grid, ME_WARPS * 32, 0, st>>>(g, b, nframes, gop);
+    const int nz = t < 0 ? nframes : (nframes - t + gop - 1) / gop;   // GOPs that own a picture t
+    if (nz <= 0) return;
+    dim3 grid((g.mbw + ME_WARPS - 1) / ME_WARPS, g.mbh, nz);
+    me_prepass_kernel<<<grid, ME_WARPS * 32, 0, st>>>(g, b, nframes, gop, t);
 }
 
 void vcp_launch_me_refine(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {

@@ -13,6 +13,8 @@
 //
 // Replaces x264's deblock inside the ffmpeg child (/root/reference/cmd/consumer.go:376-382);
 // bit-identical to oracle/h264_oracle.c (deblock_frame, mvp16, mv_pskip).
+#include <cstdlib>
+
 #include "vcp_dev.cuh"
 
 #define VCP_TAB static __device__ const
@@ -224,7 +226,7 @@ struct DbShared {
 };
 
 __global__ void __launch_bounds__(512) deblock_kernel(VcpGeom g, VcpBufs b, VcpStep s, int BH, int nbands,
-                                                        int* __restrict__ ticket, int* __restrict__ progress) {
+                                                        int* __restrict__ ticket, int* __restrict__ progress, unsigned spin_ns) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int my_ticket;
     DbShared sh;
@@ -284,7 +286,8 @@ __global__ void __launch_bounds__(512) deblock_kernel(VcpGeom g, VcpBufs b, VcpS
             if (seen_up < need) {
                 int v = 0;
                 if (lane == 0) {
-                    if (top_smem) { while ((v = sh.done[warp - 1]) < need) { } __threadfence_block(); }
+                    // a waiting row yields its issue slots: the SM is shared with other GOP groups' kernels
+                    if (top_smem) { while ((v = sh.done[warp - 1]) < need) { if (spin_ns) __nanosleep(spin_ns); } __threadfence_block(); }
                     else { while ((v = ld_relaxed_gpu(prog_up)) < need) __nanosleep(20); fence_acq_rel_gpu(); }
                 }
                 seen_up = __shfl_sync(0xffffffffu, v, 0);
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(512) deblock_kernel(VcpGeom g, VcpBufs b, VcpS
         // (4) hand-down ring: bottom 4 luma / 2 chroma rows.  Words 0..2 of macroblock mx are final
         //     now; word 3 (x=12..15) of macroblock mx-1 became final with this vertical-edge pass.
         if (below_smem) {
-            if (mx >= DB_RING && lane == 0) while (sh.taken[warp + 1] < mx - DB_RING + 1) { }
+            if (mx >= DB_RING && lane == 0) while (sh.taken[warp + 1] < mx - DB_RING + 1) { if (spin_ns) __nanosleep(spin_ns); }
             __syncwarp();
             uint32_t* cur = reinterpret_cast<uint32_t*>(ring_me + (mx % DB_RING) * DB_SLOT);
             uint32_t* prv = reinterpret_cast<uint32_t*>(ring_me + ((mx + DB_RING - 1) % DB_RING) * DB_SLOT);
@@ -495,7 +498,8 @@ void vcp_launch_deblock(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cu
     cudaMemsetAsync(sync, 0, (size_t)(s.ngop * g.mbh + 1) * sizeof(int), st);
     // function attributes are per device: a process may drive several GPUs from different threads
     if (smem > 48 * 1024) cudaFuncSetAttribute(deblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    deblock_kernel<<<s.ngop * nbands, BH * 32, smem, st>>>(g, b, s, BH, nbands, sync, sync + 1 - (size_t)s.g0 * g.mbh);
+    static const unsigned spin_ns = [] { const char* e = getenv("VCPENC_DB_SPIN_NS"); return e ? (unsigned)atoi(e) : 0u; }();
+    deblock_kernel<<<s.ngop * nbands, BH * 32, smem, st>>>(g, b, s, BH, nbands, sync, sync + 1 - (size_t)s.g0 * g.mbh, spin_ns);
 }
 
 void vcp_launch_pad(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
