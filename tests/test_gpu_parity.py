@@ -121,6 +121,28 @@ def test_k1_input_formats_equal_oracle(built, fmt):
         assert np.array_equal(got["recon"], ref["recon"])
 
 
+def test_one_task_sharded_across_gpus(built, tmp_path, monkeypatch):
+    """VCPENC_GPUS=N: the closed GOPs of one task are encoded on N devices and concatenated on the host;
+    the file must be byte-identical to the single-GPU one (needs >= 2 visible GPUs)."""
+    if api.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    w, h, n = 640, 360, 50
+    clip = synth.make_clip(w, h, n, seed=7)
+    y4m = tmp_path / "in.y4m"
+    with open(y4m, "wb") as f:
+        f.write(b"YUV4MPEG2 W%d H%d F30:1 Ip A1:1 C420jpeg\n" % (w, h))
+        for fr in clip:
+            f.write(b"FRAME\n" + fr.tobytes())
+    outs = {}
+    for gpus in ("1", "2", "all"):
+        monkeypatch.setenv("VCPENC_GPUS", gpus)
+        out = tmp_path / ("o%s.mp4" % gpus)
+        api.transcode(str(y4m), str(out), "-c:v libx264 -crf 24 -g 8")
+        outs[gpus] = out.read_bytes()
+    api.thread_release()
+    assert outs["1"] == outs["2"] == outs["all"]
+
+
 def test_cabac_long_gops_and_bitrate_mode(built):
     """CABAC runs as batches of 8 pictures per GOP behind the reconstruction chain: GOPs longer than
     one batch, ragged last GOPs, many slices, and the bin-count fed rate control."""

@@ -699,7 +699,8 @@ int vcpenc_session_set_first_gop(vcpenc_session* s, int first_gop) {
 
 void* vcpenc_host_alloc(size_t bytes) {
     void* p = nullptr;
-    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    // portable: a task sharded across several GPUs uploads from one staging buffer
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return p;
 }
 

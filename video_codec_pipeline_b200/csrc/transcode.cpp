@@ -15,6 +15,8 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "frontend.h"
 #include "host_bits.h"
@@ -110,7 +112,7 @@ static thread_local int t_device = 0;
 // Measured on the task-flow harness: session create + destroy 0.1-1.4 s and cudaMallocHost 0.1-0.3 s
 // per task against 0.13 s of GPU work for a 120-frame 1080p clip.
 namespace {
-constexpr int kCacheSlots = 4;   // mixed task sizes (720p / 1080p / 4K of config #5) each keep their session
+constexpr int kCacheSlots = 16;   // mixed task sizes (720p / 1080p / 4K of config #5) each keep their session
 struct CachedSession {
     vcpenc_session* ses = nullptr;
     vcpenc_params key{};
@@ -127,6 +129,43 @@ thread_local ThreadCache t_cache;
 bool cache_enabled() { static const bool on = getenv("VCPENC_NO_CACHE") == nullptr; return on; }
 bool same_key(vcpenc_params a, vcpenc_params b) { a.first_gop = b.first_gop = 0; return memcmp(&a, &b, sizeof a) == 0; }
 }  // namespace
+
+// session of `want` frames on `device` for parameters p: from the calling thread's cache, else new
+// (and cached).  *cached tells whether the cache owns it.
+int acquire_session(const vcpenc_params& p, int device, int want, vcpenc_session** out, bool* cached, char* err, size_t errlen) {
+    *cached = false;
+    if (cache_enabled())
+        for (auto& c : t_cache.slot)
+            if (c.ses && c.device == device && c.max_frames >= want && same_key(c.key, p)) {
+                c.stamp = ++t_cache.clock; *out = c.ses; *cached = true;
+                return VCPENC_OK;
+            }
+    CachedSession* victim = nullptr;
+    if (cache_enabled()) {   // an empty slot, else the one with the same parameters but too small, else the least recently used
+        for (auto& c : t_cache.slot) if (!c.ses) { victim = &c; break; }
+        if (!victim) for (auto& c : t_cache.slot) if (same_key(c.key, p) && c.device == device) { victim = &c; break; }
+        if (!victim) { victim = &t_cache.slot[0]; for (auto& c : t_cache.slot) if (c.stamp < victim->stamp) victim = &c; }
+        if (victim->ses) { vcpenc_session_destroy(victim->ses); *victim = CachedSession(); }
+    }
+    const int rc = vcpenc_session_create(&p, device, want, out, err, errlen);
+    if (rc) return rc;
+    if (victim) { victim->ses = *out; victim->key = p; victim->max_frames = want; victim->device = device; victim->stamp = ++t_cache.clock; *cached = true; }
+    return VCPENC_OK;
+}
+void forget_session(vcpenc_session* ses) {   // after a failure the session's state is not trusted
+    vcpenc_session_destroy(ses);
+    for (auto& c : t_cache.slot) if (c.ses == ses) c = CachedSession();
+}
+
+// GPUs one task may use: VCPENC_GPUS=N|all shards the closed GOPs of every chunk across N devices
+// (the calling thread's device first), concatenated on the host in GOP order -- no collective.
+int task_gpus() {
+    const char* e = getenv("VCPENC_GPUS");
+    if (!e) return 1;
+    const int have = vcpenc_device_count();
+    const int want = !strcmp(e, "all") ? have : atoi(e);
+    return std::max(1, std::min(want, have));
+}
 
 extern "C" void vcpenc_thread_release(void) {
     for (auto& c : t_cache.slot) if (c.ses) vcpenc_session_destroy(c.ses);
@@ -196,7 +235,7 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
 
     const size_t fb = std::max(fbytes(p.width, p.height), src->fbytes());
     // chunk: whole GOPs, at most ~3 GiB of raw frames resident per pass
-    int chunk = (int)std::max<size_t>(1, ((size_t)3 << 30) / fb);
+    int chunk = (int)std::max<size_t>(1, ((size_t)3 << 30) * (size_t)task_gpus() / fb);
     {   // short clips: do not page-lock more host memory than the file can fill
         struct stat sb;
         if (stat(input, &sb) == 0 && sb.st_size > 0)
@@ -219,22 +258,24 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
     if (!fbuf) { set_err(err, errlen, "cannot allocate %zu bytes of pinned host memory", (size_t)chunk * fb); return VCPENC_E_CUDA; }
     t_alloc = lap(tl);
 
-    vcpenc_session* ses = nullptr;
-    std::vector<uint8_t> bits((size_t)chunk * fb / 2 + (1 << 20));
-    std::vector<vcpenc_frame_info> info((size_t)chunk);
+    const int ndev = task_gpus();
+    struct Shard {
+        int device = 0; vcpenc_session* ses = nullptr; bool cached = false;
+        std::vector<uint8_t> bits; std::vector<vcpenc_frame_info> info;
+        int f0 = 0, n = 0, g0 = 0; size_t len = 0; int rc = 0; char err[256] = {0};
+    };
+    std::vector<Shard> shards((size_t)ndev);
+    for (int d = 0; d < ndev; d++) shards[d].device = (t_device + d) % std::max(1, vcpenc_device_count());
     std::vector<uint8_t> mdat, annexb_all, sps, pps;
     std::vector<Mp4Sample> samples;
     const bool raw_out = ends_with(outp, ".h264") || ends_with(outp, ".264");
     long total = 0;
     int gop_index = 0;
-    bool ses_cached = false;
-    auto drop_session = [&]() {
-        if (!ses) return;
-        vcpenc_session_destroy(ses);
-        if (ses_cached) for (auto& c : t_cache.slot) if (c.ses == ses) c = CachedSession();   // state after a failure is not trusted
-        ses = nullptr;
+    auto fail = [&](int code) {
+        for (auto& sh : shards) if (sh.ses) { forget_session(sh.ses); sh.ses = nullptr; }
+        remove(output);
+        return code;
     };
-    auto fail = [&](int code) { drop_session(); remove(output); return code; };
     for (;;) {
         if (cancel && *cancel) { set_err(err, errlen, "任务被取消"); return fail(VCPENC_E_CANCELLED); }
         if (timeout_ms > 0 && std::chrono::duration_cast<std::chrono::milliseconds>(clock::now() - t0).count() > timeout_ms) {
@@ -245,47 +286,51 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
         t_read += lap(tl);
         if (n < 0) return fail(-n);
         if (n == 0) break;
-        if (!ses) {
-            p.first_gop = 0;
-            const int want = std::min(chunk, std::max(n, 1));
-            CachedSession* hit = nullptr;
-            if (cache_enabled())
-                for (auto& c : t_cache.slot)
-                    if (c.ses && c.device == t_device && c.max_frames >= want && same_key(c.key, p)) { hit = &c; break; }
-            if (hit) { ses = hit->ses; hit->stamp = ++t_cache.clock; ses_cached = true; }
-            else {
-                CachedSession* victim = nullptr;
-                if (cache_enabled()) {   // an empty slot, else the one with the same parameters but too small, else the least recently used
-                    for (auto& c : t_cache.slot) if (!c.ses) { victim = &c; break; }
-                    if (!victim) for (auto& c : t_cache.slot) if (same_key(c.key, p) && c.device == t_device) { victim = &c; break; }
-                    if (!victim) { victim = &t_cache.slot[0]; for (auto& c : t_cache.slot) if (c.stamp < victim->stamp) victim = &c; }
-                    if (victim->ses) { vcpenc_session_destroy(victim->ses); *victim = CachedSession(); }
-                }
-                rc = vcpenc_session_create(&p, t_device, want, &ses, err, errlen);
+        // closed GOPs of this chunk, contiguous ranges per device
+        const int ngops = (n + p.gop - 1) / p.gop;
+        const int used = std::min(ndev, ngops);
+        for (int d = 0; d < ndev; d++) {
+            Shard& sh = shards[d];
+            const int ga = d < used ? (int)((long long)ngops * d / used) : 0, gb = d < used ? (int)((long long)ngops * (d + 1) / used) : 0;
+            sh.f0 = ga * p.gop; sh.n = std::min(n, gb * p.gop) - sh.f0; sh.g0 = gop_index + ga; sh.rc = 0; sh.len = 0;
+            if (sh.n <= 0) { sh.n = 0; continue; }
+            if (!sh.ses) {
+                p.first_gop = 0;
+                const int want = std::min((chunk / p.gop + used - 1) / used * p.gop, std::max(sh.n, 1));
+                rc = acquire_session(p, sh.device, std::max(want, sh.n), &sh.ses, &sh.cached, err, errlen);
                 if (rc) return fail(rc);
-                if (victim) { victim->ses = ses; victim->key = p; victim->max_frames = want; victim->device = t_device; victim->stamp = ++t_cache.clock; ses_cached = true; }
             }
-            t_create += lap(tl);
+            if (sh.bits.size() < (size_t)sh.n * fb / 2 + (1 << 20)) sh.bits.resize((size_t)sh.n * fb / 2 + (1 << 20));
+            if (sh.info.size() < (size_t)sh.n) sh.info.resize((size_t)sh.n);
         }
-        // idr_pic_id parity continues across chunks
-        vcpenc_session_set_first_gop(ses, gop_index);
-        rc = vcpenc_session_upload(ses, fbuf, n, err, errlen);
-        if (!rc) rc = vcpenc_session_encode(ses, nullptr, err, errlen);
-        size_t len = 0;
-        if (!rc) {
-            rc = vcpenc_session_download(ses, bits.data(), bits.size(), &len, info.data(), nullptr, err, errlen);
-            if (rc == VCPENC_E_OVERFLOW) {
-                bits.resize((size_t)chunk * fb + (1 << 20));
-                rc = vcpenc_session_download(ses, bits.data(), bits.size(), &len, info.data(), nullptr, err, errlen);
+        t_create += lap(tl);
+        auto run = [&](Shard& sh) {
+            if (!sh.n) return;
+            vcpenc_session_set_first_gop(sh.ses, sh.g0);          // idr_pic_id parity continues across ranges and chunks
+            sh.rc = vcpenc_session_upload(sh.ses, fbuf + (size_t)sh.f0 * src->fbytes(), sh.n, sh.err, sizeof sh.err);
+            if (!sh.rc) sh.rc = vcpenc_session_encode(sh.ses, nullptr, sh.err, sizeof sh.err);
+            if (!sh.rc) {
+                sh.rc = vcpenc_session_download(sh.ses, sh.bits.data(), sh.bits.size(), &sh.len, sh.info.data(), nullptr, sh.err, sizeof sh.err);
+                if (sh.rc == VCPENC_E_OVERFLOW) {
+                    sh.bits.resize((size_t)sh.n * fb + (1 << 20));
+                    sh.rc = vcpenc_session_download(sh.ses, sh.bits.data(), sh.bits.size(), &sh.len, sh.info.data(), nullptr, sh.err, sizeof sh.err);
+                }
             }
-        }
-        if (rc) return fail(rc);
-        t_gpu += lap(tl);
-        if (raw_out) annexb_all.insert(annexb_all.end(), bits.begin(), bits.begin() + len);
+        };
+        if (used <= 1) run(shards[0]);
         else {
-            for (int i = 0; i < n; i++) {
-                Mp4Sample s{mdat.size(), 0, info[i].is_idr != 0};
-                for (const auto& nal : split_annexb(bits.data() + info[i].offset, info[i].size)) {
+            std::vector<std::thread> th;
+            for (int d = 0; d < used; d++) th.emplace_back(run, std::ref(shards[d]));
+            for (auto& t : th) t.join();
+        }
+        for (auto& sh : shards) if (sh.n && sh.rc) { set_err(err, errlen, "%s", sh.err); return fail(sh.rc); }
+        t_gpu += lap(tl);
+        for (auto& sh : shards) {            // host concatenation in GOP order
+            if (!sh.n) continue;
+            if (raw_out) { annexb_all.insert(annexb_all.end(), sh.bits.begin(), sh.bits.begin() + sh.len); continue; }
+            for (int i = 0; i < sh.n; i++) {
+                Mp4Sample sm{mdat.size(), 0, sh.info[i].is_idr != 0};
+                for (const auto& nal : split_annexb(sh.bits.data() + sh.info[i].offset, sh.info[i].size)) {
                     if (!nal.n) continue;
                     const int t = nal.p[0] & 31;
                     if (t == 7) { if (sps.empty()) sps.assign(nal.p, nal.p + nal.n); continue; }
@@ -295,16 +340,15 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
                     mdat.insert(mdat.end(), h, h + 4);
                     mdat.insert(mdat.end(), nal.p, nal.p + nal.n);
                 }
-                s.size = (uint32_t)(mdat.size() - s.offset);
-                samples.push_back(s);
+                sm.size = (uint32_t)(mdat.size() - sm.offset);
+                samples.push_back(sm);
             }
         }
         total += n;
-        gop_index += (n + p.gop - 1) / p.gop;
+        gop_index += ngops;
         if (n < chunk) break;
     }
-    if (ses && !ses_cached) vcpenc_session_destroy(ses);
-    ses = nullptr;
+    for (auto& sh : shards) { if (sh.ses && !sh.cached) vcpenc_session_destroy(sh.ses); sh.ses = nullptr; }
     if (total == 0) { set_err(err, errlen, "input has no frames"); remove(output); return VCPENC_E_FORMAT; }
     if (raw_out) {
         FILE* f = fopen(output, "wb");
