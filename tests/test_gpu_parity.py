@@ -121,6 +121,70 @@ def test_k1_input_formats_equal_oracle(built, fmt):
         assert np.array_equal(got["recon"], ref["recon"])
 
 
+def _same_as_oracle(w, h, clip, **kw):
+    from oracle import pyoracle
+    ref = pyoracle.encode(pyoracle.make_params(w, h, **kw), clip)
+    got = api.encode_frames(api.default_params(w, h, **kw), clip, want_recon=True)
+    assert [x[3] for x in got["info"]] == [x[3] for x in ref["info"]], kw
+    assert got["stream"].tobytes() == ref["stream"], kw
+    assert np.array_equal(got["recon"], ref["recon"]), kw
+    return got
+
+
+def test_breadth_against_oracle(built):
+    """Corners the headline configurations do not reach: long GOPs across several CABAC batches, cropped
+    sizes (1366x768), fast pans that push vectors to the border clamp, flat pictures, rate control with
+    High profile and slices, nv12 at 1080p, and a session reused for different content."""
+    rng = np.random.default_rng(4)
+    # GOP 250-style long GOP (62 pictures in one GOP = 8 CABAC batches) + a ragged second GOP
+    w, h = 176, 144
+    _same_as_oracle(w, h, synth.make_clip(w, h, 70, seed=2), gop=62, qp_i=28, qp_p=30, entropy=1, transform8x8=1, slices=2)
+    # width / height not multiples of 16: frame cropping in the SPS, padded macroblocks
+    w, h = 1366, 768
+    g = _same_as_oracle(w, h, synth.make_clip(w, h, 4, seed=3), gop=4, qp_i=26, qp_p=28, entropy=1, transform8x8=1, slices=0)
+    if arbiter.available():
+        dec = arbiter.decode_annexb(g["stream"].tobytes())
+        assert dec[0][0].shape == (768, 1366)
+    # fast pan: 23 px / picture horizontally, 9 vertically (search range and border clamps)
+    w, h = 320, 192
+    base = rng.integers(0, 256, (h + 64, w + 256), dtype=np.uint8)
+    base = (base.astype(np.int32) + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, 2, 1)) // 4
+    frames = []
+    for i in range(6):
+        y = base[9 * i % 60: 9 * i % 60 + h, 23 * i: 23 * i + w].astype(np.uint8)
+        frames.append(np.concatenate([y.ravel(), np.full(w * h // 2, 128, np.uint8)]))
+    pan = np.stack(frames)
+    for ent in (0, 1):
+        _same_as_oracle(w, h, pan, gop=6, qp_i=24, qp_p=26, entropy=ent, transform8x8=ent)
+    # flat pictures: everything skips; black, white, mid-grey
+    for v in (0, 128, 255):
+        flat = np.full((4, w * h * 3 // 2), v, np.uint8)
+        for ent in (0, 1):
+            _same_as_oracle(w, h, flat, gop=4, qp_i=30, qp_p=30, entropy=ent)
+    # bitrate target + High profile + slices + CABAC
+    w, h = 640, 360
+    _same_as_oracle(w, h, synth.make_clip(w, h, 45, seed=6), gop=20, fps=30, rc_mode=1, bitrate=1_500_000, entropy=1,
+                    transform8x8=1, slices=3)
+    # nv12 at 1080p through K1, High profile
+    w, h = 1920, 1080
+    yuv = synth.make_clip(w, h, 3, seed=9)
+    nv = np.stack([np.concatenate([fr[: w * h], np.stack([fr[w * h: w * h + w * h // 4], fr[w * h + w * h // 4:]], -1).ravel()]) for fr in yuv])
+    a = _same_as_oracle(w, h, nv, gop=3, qp_i=25, qp_p=27, in_fmt=1, entropy=1, transform8x8=1, slices=0)
+    b = api.encode_frames(api.default_params(w, h, gop=3, qp_i=25, qp_p=27, entropy=1, transform8x8=1, slices=0), yuv)
+    assert a["stream"].tobytes() == b["stream"].tobytes()
+    # one session, two different clips back to back == two fresh sessions
+    w, h = 320, 192
+    c1, c2 = synth.make_clip(w, h, 9, seed=11), synth.make_clip(w, h, 7, seed=12)
+    p = api.default_params(w, h, gop=4, qp_i=24, qp_p=26, entropy=1, transform8x8=1)
+    with api.Session(p, 9) as ses:
+        outs = []
+        for c in (c1, c2, c1):
+            ses.upload(c); ses.encode()
+            outs.append(ses.download()["stream"].tobytes())
+    assert outs[0] == outs[2] == api.encode_frames(p, c1)["stream"].tobytes()
+    assert outs[1] == api.encode_frames(p, c2)["stream"].tobytes()
+
+
 def test_one_task_sharded_across_gpus(built, tmp_path, monkeypatch):
     """VCPENC_GPUS=N: the closed GOPs of one task are encoded on N devices and concatenated on the host;
     the file must be byte-identical to the single-GPU one (needs >= 2 visible GPUs)."""
