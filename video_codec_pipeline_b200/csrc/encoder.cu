@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -84,7 +85,8 @@ struct vcpenc_session {
     int ngroups = 4;
     int bins_per_mb = 128;                      // CABAC bin arena sizing (VCPENC_BINS_PER_MB)
     std::vector<void*> allocs;
-    uint8_t* staging[2] = {nullptr, nullptr};
+    uint8_t* staging[2] = {nullptr, nullptr};   // (scratch of the K1 front stages is sized by staging_frames)
+    uint8_t* raw_dev = nullptr;                 // the raw frames of an upload, whole batch: H2D copies never wait for a kernel
     // K1 front stages (other pixel formats, scaling): scratch pictures of staging_frames each
     int in_w = 0, in_h = 0; size_t in_fb = 0;
     bool need_conv = false, need_scale = false;
@@ -309,9 +311,14 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
 #define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_err(err, errlen, "%s failed: %s", #call, cudaGetErrorString(e_)); vcpenc_session_destroy(s); return VCPENC_E_CUDA; } } while (0)
     CKS(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
     CKS(cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking));
+    // Stream priorities (numerically lower = more urgent; plain streams sit at the least urgent level):
+    // the reconstruction chains are latency-critical, the entropy side streams less so, and K1 of an
+    // upload and the motion-search pre-pass are throughput work that should only fill gaps -- also
+    // across sessions sharing the GPU (another consumer thread's upload must not slow this encode).
+    int lo = 0, hi = 0;
+    CKS(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const int prio_chain = hi, prio_entropy = hi < lo ? hi + (lo - hi + 1) / 2 : lo;
     {
-        int lo = 0, hi = 0;
-        CKS(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         // lowest priority for both: K1 of an upload and the pre-pass are throughput work; the chains of a
         // running encode (this session's or another one's on the same GPU) are latency-critical
         CKS(cudaStreamCreateWithPriority(&s->st_up, cudaStreamNonBlocking, lo));
@@ -329,9 +336,9 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
         if (e2 && atoi(e2) > 0) s->bins_per_mb = std::min(atoi(e2), 65536);
     }
     for (int i = 0; i < s->ngroups; i++) {
-        CKS(cudaStreamCreateWithFlags(&s->gst[i], cudaStreamNonBlocking));
-        CKS(cudaStreamCreateWithFlags(&s->est[i], cudaStreamNonBlocking));
-        if (pp->entropy) for (int q = 0; q < vcpenc_session::kCabacStreams; q++) CKS(cudaStreamCreateWithFlags(&s->cst[i][q], cudaStreamNonBlocking));
+        CKS(cudaStreamCreateWithPriority(&s->gst[i], cudaStreamNonBlocking, prio_chain));
+        CKS(cudaStreamCreateWithPriority(&s->est[i], cudaStreamNonBlocking, prio_entropy));
+        if (pp->entropy) for (int q = 0; q < vcpenc_session::kCabacStreams; q++) CKS(cudaStreamCreateWithPriority(&s->cst[i][q], cudaStreamNonBlocking, prio_entropy));
         CKS(cudaEventCreateWithFlags(&s->ev_bins[i], cudaEventDisableTiming));
         CKS(cudaEventCreateWithFlags(&s->gev[i], cudaEventDisableTiming));
         for (int q = 0; q < 2; q++) {
@@ -411,7 +418,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     if (s->need_conv) TRY(dev_alloc(s, &s->norm_a, (size_t)s->staging_frames * vcp_in_frame_bytes(VCPENC_FMT_YUV420P, s->in_w, s->in_h), err, errlen));
     if (s->need_scale) TRY(dev_alloc(s, &s->norm_b, (size_t)s->staging_frames * frame_bytes_of(*pp), err, errlen));
     for (int i = 0; i < 2; i++) {
-        TRY(dev_alloc(s, &s->staging[i], (size_t)s->staging_frames * s->in_fb, err, errlen));
+        if (i == 0) TRY(dev_alloc(s, &s->raw_dev, (size_t)max_frames * s->in_fb, err, errlen));
         CKS(cudaEventCreateWithFlags(&s->staging_free[i], cudaEventDisableTiming));
         CKS(cudaEventCreateWithFlags(&s->staging_ready[i], cudaEventDisableTiming));
     }
@@ -445,16 +452,16 @@ int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes,
     s->h_qp.resize(nframes);
     for (int n = 0; n < nframes; n++) s->h_qp[n] = initial_qp(s, n);
     CK(cudaMemcpyAsync(s->b.qp, s->h_qp.data(), nframes, cudaMemcpyHostToDevice, s->st_up));
-    int chunk = 0;
-    for (int n0 = 0; n0 < nframes; n0 += s->staging_frames, chunk++) {
-        const int k = chunk & 1;
-        const int cnt = std::min(s->staging_frames, nframes - n0);
-        if (chunk >= 2) CK(cudaStreamWaitEvent(s->st_copy, s->staging_free[k], 0));
-        CK(cudaMemcpyAsync(s->staging[k], frames + (size_t)n0 * fb, (size_t)cnt * fb, cudaMemcpyHostToDevice, s->st_copy));
-        CK(cudaEventRecord(s->staging_ready[k], s->st_copy));
-        CK(cudaStreamWaitEvent(s->st_up, s->staging_ready[k], 0));
-        k1_chain(s, s->staging[k], n0, cnt, s->st_up);
-        CK(cudaEventRecord(s->staging_free[k], s->st_up));
+    // All H2D copies are queued up front into a device buffer that holds the whole batch, so the DMA
+    // runs at PCIe rate whatever the GPU is busy with (another session's encode delays K1, never the
+    // copies); K1 trails the copies in a few large pieces.
+    const int pieces = std::min(4, nframes);
+    for (int k = 0; k < pieces; k++) {
+        const int n0 = (int)((long long)nframes * k / pieces), n1 = (int)((long long)nframes * (k + 1) / pieces);
+        CK(cudaMemcpyAsync(s->raw_dev + (size_t)n0 * fb, frames + (size_t)n0 * fb, (size_t)(n1 - n0) * fb, cudaMemcpyHostToDevice, s->st_copy));
+        CK(cudaEventRecord(s->staging_ready[k & 1], s->st_copy));
+        CK(cudaStreamWaitEvent(s->st_up, s->staging_ready[k & 1], 0));
+        k1_chain(s, s->raw_dev + (size_t)n0 * fb, n0, n1 - n0, s->st_up);
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s->st_up));
@@ -606,10 +613,17 @@ int vcpenc_session_encode(vcpenc_session* s, float* ms, char* err, size_t errlen
     int flag = 0;
     for (int attempt = 0;; attempt++) {
         CK(cudaEventRecord(s->ev0, s->st));
+        const auto h0 = std::chrono::steady_clock::now();
         int rc = run_encode(s, err, errlen);
         if (rc) return rc;
         CK(cudaEventRecord(s->ev1, s->st));
+        const auto h1 = std::chrono::steady_clock::now();
         CK(cudaStreamSynchronize(s->st));
+        if (getenv("VCPENC_TRACE_ENCODE")) {
+            const auto h2 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[vcpenc] encode: host issue %.1f ms, then waited %.1f ms\n",
+                    std::chrono::duration<double, std::milli>(h1 - h0).count(), std::chrono::duration<double, std::milli>(h2 - h1).count());
+        }
         if (ms) CK(cudaEventElapsedTime(ms, s->ev0, s->ev1));
         if (s->profile) collect_profile(s);
         CK(cudaMemcpy(&flag, s->b.error_flag, sizeof flag, cudaMemcpyDeviceToHost));
