@@ -367,6 +367,19 @@ def test_transcode_drop_in(built, tmp_path):
         y5 = synth.split_planes(clip[5], w, h)[0].astype(np.int32)
         small = ((y5[0::2, 0::2] + y5[0::2, 1::2] + y5[1::2, 0::2] + y5[1::2, 1::2] + 2) >> 2).astype(np.uint8)
         assert arbiter.psnr(dec[5][0], small) > 24      # two generations of lossy coding at low bitrate
+    # long inputs are processed in chunks of whole GOPs: forcing 2-GOP chunks must not change a byte
+    import os as _os
+    _os.environ["VCPENC_CHUNK_BYTES"] = str(16 * w * h * 3 // 2)
+    try:
+        out7 = tmp_path / "out7.mp4"
+        api.transcode(str(y4m), str(out7), "-c:v libx264 -preset medium -crf 23 -c:a aac -b:a 128k -movflags +faststart -g 8")
+        assert out7.read_bytes() == data
+    finally:
+        del _os.environ["VCPENC_CHUNK_BYTES"]
+    # HEVC presets parse, and are refused with their own class (the Go side may fall back to a stock ffmpeg)
+    with pytest.raises(api.VcpencError) as e:
+        api.transcode(str(y4m), str(tmp_path / "x.mp4"), "-c:v libx265 -preset medium -crf 28")
+    assert e.value.code == 13
     # failure semantics: unknown container -> error class, no output left behind
     bad = tmp_path / "in.mkv"
     bad.write_bytes(b"\x1a\x45\xdf\xa3junk")

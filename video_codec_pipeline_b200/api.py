@@ -26,7 +26,7 @@ K_NAMES = ["csc", "me_prepass", "me_refine", "p_recon", "i_recon", "mbinfo", "de
            "cavlc_count", "cavlc_scan", "cavlc_write_pack", "rc", "hpel", "cabac_bins", "cabac_code"]
 
 ERR_NAMES = {0: "OK", 1: "ARGS", 2: "IO", 3: "FORMAT", 4: "NODEVICE", 5: "CUDA", 6: "CANCELLED",
-             7: "TIMEOUT", 8: "NOTENCODE", 9: "AUDIO", 10: "VERIFY", 11: "OVERFLOW", 12: "INTERNAL"}
+             7: "TIMEOUT", 8: "NOTENCODE", 9: "AUDIO", 10: "VERIFY", 11: "OVERFLOW", 12: "INTERNAL", 13: "UNSUPPORTED"}
 
 
 class Params(C.Structure):

@@ -191,6 +191,7 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
     vcpenc_params p;
     int rc = vcpenc_parse_args(argc, argv, &p, err, errlen);
     if (rc) return rc;
+    if (p.codec != VCPENC_CODEC_H264) { set_err(err, errlen, "HEVC encoding is not implemented yet (H.264 only)"); return VCPENC_E_UNSUPPORTED; }
     if (vcpenc_device_count() <= 0) { set_err(err, errlen, "no CUDA device available (libvcpenc has no CPU fallback)"); return VCPENC_E_NODEVICE; }
 
     const std::string in = input, outp = output;
@@ -235,7 +236,9 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
 
     const size_t fb = std::max(fbytes(p.width, p.height), src->fbytes());
     // chunk: whole GOPs, at most ~3 GiB of raw frames resident per pass
-    int chunk = (int)std::max<size_t>(1, ((size_t)3 << 30) * (size_t)task_gpus() / fb);
+    size_t chunk_bytes = ((size_t)3 << 30) * (size_t)task_gpus();
+    if (const char* e = getenv("VCPENC_CHUNK_BYTES")) { const long long v = atoll(e); if (v > 0) chunk_bytes = (size_t)v; }   // tests: force many chunks
+    int chunk = (int)std::max<size_t>(1, chunk_bytes / fb);
     {   // short clips: do not page-lock more host memory than the file can fill
         struct stat sb;
         if (stat(input, &sb) == 0 && sb.st_size > 0)
