@@ -85,14 +85,13 @@ struct vcpenc_session {
     int ngroups = 4;
     int bins_per_mb = 128;                      // CABAC bin arena sizing (VCPENC_BINS_PER_MB)
     std::vector<void*> allocs;
-    uint8_t* staging[2] = {nullptr, nullptr};   // (scratch of the K1 front stages is sized by staging_frames)
     uint8_t* raw_dev = nullptr;                 // the raw frames of an upload, whole batch: H2D copies never wait for a kernel
     // K1 front stages (other pixel formats, scaling): scratch pictures of staging_frames each
     int in_w = 0, in_h = 0; size_t in_fb = 0;
     bool need_conv = false, need_scale = false;
     uint8_t *norm_a = nullptr, *norm_b = nullptr;
-    cudaEvent_t staging_free[2] = {nullptr, nullptr}, staging_ready[2] = {nullptr, nullptr};
-    int staging_frames = 0;
+    cudaEvent_t staging_ready[2] = {nullptr, nullptr};   // H2D piece k landed in raw_dev
+    int staging_frames = 0;                              // frames per pass of the K1 front stages' scratch
     // debug taps
     short2* dbg_mv = nullptr; uint8_t* dbg_type = nullptr; uint8_t* dbg_cbp = nullptr;
     // host
@@ -248,7 +247,6 @@ void vcpenc_session_destroy(vcpenc_session* s) {
     for (void* q : s->allocs) cudaFree(q);
     for (auto& e : s->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int i = 0; i < 2; i++) {
-        if (s->staging_free[i]) cudaEventDestroy(s->staging_free[i]);
         if (s->staging_ready[i]) cudaEventDestroy(s->staging_ready[i]);
     }
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -408,7 +406,6 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
         TRY(dev_alloc(s, &s->dbg_type, N * nmb, err, errlen));
         TRY(dev_alloc(s, &s->dbg_cbp, N * nmb, err, errlen));
     }
-    // upload staging: two buffers of up to 16 frames
     s->staging_frames = std::max(1, std::min(16, max_frames));
     s->in_w = pp->in_width > 0 ? pp->in_width : pp->width;
     s->in_h = pp->in_height > 0 ? pp->in_height : pp->height;
@@ -419,7 +416,6 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     if (s->need_scale) TRY(dev_alloc(s, &s->norm_b, (size_t)s->staging_frames * frame_bytes_of(*pp), err, errlen));
     for (int i = 0; i < 2; i++) {
         if (i == 0) TRY(dev_alloc(s, &s->raw_dev, (size_t)max_frames * s->in_fb, err, errlen));
-        CKS(cudaEventCreateWithFlags(&s->staging_free[i], cudaEventDisableTiming));
         CKS(cudaEventCreateWithFlags(&s->staging_ready[i], cudaEventDisableTiming));
     }
     // recon must never hold uninitialised borders when a vector reads them
