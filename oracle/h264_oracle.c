@@ -1655,3 +1655,6 @@ void orc_roundtrip8(const int* d, int qp, int* r) {
     int w[64], c[64]; int16_t lv[64];
     fdct8(d, w); quant8x8(w, qp, 0, lv); dequant8x8(lv, qp, c); idct8(c, r);
 }
+
+/* HEVC oracle (config #4): shares the helpers above */
+#include "hevc_oracle.inc.c"

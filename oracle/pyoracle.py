@@ -48,7 +48,7 @@ def make_params(width, height, fps=30, gop=60, qp_i=24, qp_p=26, slices=1, deblo
 
 def build(force=False):
     if force or not os.path.exists(LIB_PATH) or \
-            os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(HERE, "h264_oracle.c")):
+            os.path.getmtime(LIB_PATH) < max(os.path.getmtime(os.path.join(HERE, f)) for f in ("h264_oracle.c", "hevc_oracle.inc.c")):
         subprocess.check_call(["make", "-C", HERE, "-s"] + (["-B"] if force else []))
     return LIB_PATH
 
@@ -69,6 +69,27 @@ def lib():
 
 def frame_bytes(w, h):
     return w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)
+
+
+def encode_hevc(params: Params, frames: np.ndarray):
+    """HEVC oracle (oracle/hevc_oracle.inc.c): yuv420p frames -> dict(stream, info, recon)."""
+    L = lib()
+    L.hevc_orc_encode.argtypes = [C.POINTER(Params), C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                  C.c_void_p, C.c_void_p]
+    L.hevc_orc_encode.restype = C.c_int
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    fb = frame_bytes(params.width, params.height)
+    n = frames.size // fb
+    cap = n * fb + (1 << 16)
+    out = np.empty(cap, np.uint8)
+    out_len = C.c_size_t(0)
+    info = (FrameInfo * n)()
+    recon = np.empty((n, fb), np.uint8)
+    rc = L.hevc_orc_encode(C.byref(params), frames.ctypes.data, n, out.ctypes.data, cap, C.byref(out_len),
+                           C.cast(info, C.c_void_p), recon.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("hevc_orc_encode failed rc=%d" % rc)
+    return {"stream": out[: out_len.value].tobytes(), "info": [(i.offset, i.size, i.is_idr, i.qp) for i in info], "recon": recon}
 
 
 def in_frame_bytes(p) -> int:

@@ -308,3 +308,38 @@ def test_k1_scale():
     rec = pyoracle.encode(pyoracle.make_params(64, 48, gop=1, qp_i=8, qp_p=8, in_width=w, in_height=h), ramp)["recon"][0]
     y = rec[: 64 * 48].reshape(48, 64).astype(int)
     assert np.abs(y[10] - (2 * np.arange(64) + 20.5)).max() <= 1.5
+
+
+# ---- HEVC oracle (oracle/hevc_oracle.inc.c): pinned by the FFmpeg hevc decoder -------------------------
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%dx%d_n%d_g%d_s%d_d%d_q%d" % c)
+def test_hevc_oracle_stream_decodes_to_its_own_recon(case):
+    if not arbiter.available():
+        pytest.skip("bundled FFmpeg decoder not present")
+    w, h, n, gop, sl, _idc, qp = case
+    clip = synth.make_clip(w, h, n, seed=1000 + w + qp)
+    r = pyoracle.encode_hevc(pyoracle.make_params(w, h, codec=1, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl), clip)
+    dec = arbiter.decode_annexb_hevc(r["stream"])
+    assert len(dec) == n
+    for i in range(n):
+        assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i]), "frame %d" % i
+    y = synth.split_planes(clip[n - 1], w, h)[0]
+    assert arbiter.psnr(dec[n - 1][0], y) > (18 if qp > 45 else 28)
+    assert len(r["stream"]) < clip.size // 2 or qp <= 12
+
+
+def test_hevc_tables_match_decoder_rodata():
+    """CABAC initValues (tables 9-5..9-37) typed in the oracle must appear in the decoder's own tables."""
+    import glob
+    import re
+    d = arbiter._find_libdir()
+    if d is None:
+        pytest.skip("bundled libavcodec not present")
+    data = open(sorted(glob.glob(os.path.join(d, "libavcodec-*.so*")))[0], "rb").read()
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "hevc_oracle.inc.c")).read()
+    body = re.search(r"hevc_init_values\[2\]\[HC_NCTX\] = \{(.*?)\}\};", src, re.S).group(1)
+    rows = [[int(x) for x in re.findall(r"\b\d+\b", re.sub(r"/\*.*?\*/", "", part))] for part in body.split("},")]
+    assert [len(r) for r in rows] == [130, 130]
+    for row in rows:
+        # last_sig_coeff prefix (18), coded_sub_block (4), sig_coeff (42), greater1 (24), greater2 (6) are contiguous runs
+        for a, b in ((18, 36), (54, 58), (58, 100), (100, 124), (124, 130)):
+            assert data.find(bytes(row[a:b])) >= 0, (a, b)

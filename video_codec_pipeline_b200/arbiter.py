@@ -254,6 +254,36 @@ def decode_annexb(data: bytes, codec=b"h264", threads=0):
         dec.close()
 
 
+def group_access_units_hevc(nals):
+    """HEVC: a new access unit starts at a VCL NAL with first_slice_segment_in_pic_flag, or at a parameter set /
+    AUD after VCL data."""
+    aus, cur, have_vcl = [], [], False
+    for nal in nals:
+        t = (nal[0] >> 1) & 63
+        is_vcl = t < 32
+        new_pic = (is_vcl and have_vcl and (nal[2] & 0x80)) or (not is_vcl and have_vcl)
+        if new_pic:
+            aus.append(b"".join(b"\x00\x00\x00\x01" + x for x in cur))
+            cur, have_vcl = [], False
+        cur.append(nal)
+        have_vcl = have_vcl or is_vcl
+    if cur:
+        aus.append(b"".join(b"\x00\x00\x00\x01" + x for x in cur))
+    return aus
+
+
+def decode_annexb_hevc(data: bytes, threads=0):
+    """Decode an HEVC Annex-B elementary stream with the FFmpeg `hevc` decoder."""
+    dec = _Decoder(b"hevc", threads)
+    try:
+        for au in group_access_units_hevc(split_annexb(data)):
+            dec.send(au)
+        dec.flush()
+        return dec.frames
+    finally:
+        dec.close()
+
+
 def _open_input(path):
     _, _, avformat = _load()
     fmt = C.c_void_p(None)
