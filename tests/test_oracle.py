@@ -335,7 +335,7 @@ def test_hevc_tables_match_decoder_rodata():
     if d is None:
         pytest.skip("bundled libavcodec not present")
     data = open(sorted(glob.glob(os.path.join(d, "libavcodec-*.so*")))[0], "rb").read()
-    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "hevc_oracle.inc.c")).read()
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "video_codec_pipeline_b200", "csrc", "hevc_tables.h")).read()
     body = re.search(r"hevc_init_values\[2\]\[HC_NCTX\] = \{(.*?)\}\};", src, re.S).group(1)
     rows = [[int(x) for x in re.findall(r"\b\d+\b", re.sub(r"/\*.*?\*/", "", part))] for part in body.split("},")]
     assert [len(r) for r in rows] == [130, 130]

@@ -1,0 +1,436 @@
+// K6 — HEVC (ITU-T H.265) reconstruction kernels: the h265-* presets of the reference
+// (/root/reference/internal/config/config.go:47-50) on the same execution model as the H.264 path:
+// closed GOPs in lock-step, motion search shared with H.264 (pre-pass on originals + full-sample refine),
+// everything else macroblock- (here: coding-unit-) parallel, the IDR picture on an anti-diagonal wavefront.
+//
+// Stream structure (oracle/hevc_oracle.inc.c restates the same): Main profile, CTB = CU = 16x16 in raster
+// order, luma transform blocks 8x8 (the 16x16 root splits because MaxTb = 8), chroma 4x4, DCT only, DC intra
+// prediction per transform block, one 16x16 PU with full-sample luma vectors (chroma on half samples: 4-tap
+// filter), AMVP / merge (one candidate) / skip decided after all vectors exist (hevc_cuinfo_kernel), in-loop
+// filters disabled.  Entropy coding: k5_cabac.cu (hevc_bins_kernel + the shared arithmetic coder).
+//
+//   hevc_p_recon_kernel : warp = CU; lanes 0-15 = four lanes per 8x8 luma transform block (rows, then columns
+//                         through shared memory), lanes 16-23 = one 4x4 chroma block each
+//   hevc_i_recon_kernel : CTA = (GOP, slice), wavefront over anti-diagonals, warp = CU, the four transform
+//                         units of a CU in z-order (each predicts from the reconstruction of the previous ones)
+//   hevc_cuinfo_kernel  : thread = CU: merge candidate, AMVP list, vector difference, skip
+//
+// Record layout per CU (same arrays as H.264): mbtype 0 intra / 1 inter / 2 skip; cbp bits 0-3 = cbf_luma of
+// the four TUs, bit 4 = merge_flag, bit 5 = mvp_l0_flag; modes bits 0-3 = cbf_cb, 4-7 = cbf_cr; levels:
+// luma [z*64 + y*8 + x], Cb [256 + z*16 + y*4 + x], Cr [320 + z*16 + y*4 + x].
+#include "vcp_dev.cuh"
+
+#define VCP_TAB static __device__ const
+#include "hevc_tables.h"
+
+namespace {
+
+constexpr int HV_T_STRIDE = 72;   // ints per 8x8 staging block (64 + padding: the four blocks land on different banks)
+
+struct __align__(16) HvScratch {
+    uint8_t pred[16][16];         // luma prediction, then reconstruction
+    uint8_t cpred[2][8][8];
+    int t[4][HV_T_STRIDE];
+    int16_t lv[384];
+};
+
+__device__ __forceinline__ int hevc_chroma_qp(int qp) { return qp < 30 ? qp : qp > 43 ? qp - 6 : hevc_qpc_tab[qp - 30]; }
+
+// one-dimensional core transforms (8.6.4.2): exact integer sums, so the butterfly order is free
+__device__ __forceinline__ void hv_fwd8(const int x[8], int y[8]) {
+    const int e0 = x[0] + x[7], e1 = x[1] + x[6], e2 = x[2] + x[5], e3 = x[3] + x[4];
+    const int o0 = x[0] - x[7], o1 = x[1] - x[6], o2 = x[2] - x[5], o3 = x[3] - x[4];
+    const int ee0 = e0 + e3, eo0 = e0 - e3, ee1 = e1 + e2, eo1 = e1 - e2;
+    y[0] = 64 * (ee0 + ee1); y[4] = 64 * (ee0 - ee1); y[2] = 83 * eo0 + 36 * eo1; y[6] = 36 * eo0 - 83 * eo1;
+    y[1] = 89 * o0 + 75 * o1 + 50 * o2 + 18 * o3; y[3] = 75 * o0 - 18 * o1 - 89 * o2 - 50 * o3;
+    y[5] = 50 * o0 - 89 * o1 + 18 * o2 + 75 * o3; y[7] = 18 * o0 - 50 * o1 + 75 * o2 - 89 * o3;
+}
+__device__ __forceinline__ void hv_inv8(const int c[8], int x[8]) {
+    const int o0 = 89 * c[1] + 75 * c[3] + 50 * c[5] + 18 * c[7], o1 = 75 * c[1] - 18 * c[3] - 89 * c[5] - 50 * c[7];
+    const int o2 = 50 * c[1] - 89 * c[3] + 18 * c[5] + 75 * c[7], o3 = 18 * c[1] - 50 * c[3] + 75 * c[5] - 89 * c[7];
+    const int eo0 = 83 * c[2] + 36 * c[6], eo1 = 36 * c[2] - 83 * c[6], ee0 = 64 * (c[0] + c[4]), ee1 = 64 * (c[0] - c[4]);
+    const int e0 = ee0 + eo0, e3 = ee0 - eo0, e1 = ee1 + eo1, e2 = ee1 - eo1;
+    x[0] = e0 + o0; x[7] = e0 - o0; x[1] = e1 + o1; x[6] = e1 - o1; x[2] = e2 + o2; x[5] = e2 - o2; x[3] = e3 + o3; x[4] = e3 - o3;
+}
+__device__ __forceinline__ void hv_fwd4(const int x[4], int y[4]) {
+    const int a = x[0] + x[3], b = x[1] + x[2], c = x[0] - x[3], d = x[1] - x[2];
+    y[0] = 64 * (a + b); y[2] = 64 * (a - b); y[1] = 83 * c + 36 * d; y[3] = 36 * c - 83 * d;
+}
+__device__ __forceinline__ void hv_inv4(const int c[4], int x[4]) {
+    const int e0 = 64 * (c[0] + c[2]), e1 = 64 * (c[0] - c[2]), o0 = 83 * c[1] + 36 * c[3], o1 = 36 * c[1] - 83 * c[3];
+    x[0] = e0 + o0; x[3] = e0 - o0; x[1] = e1 + o1; x[2] = e1 - o1;
+}
+__device__ __forceinline__ int hv_quant1(int w, int qs, long long offs, int qbits) {
+    const long long a = w < 0 ? -(long long)w : w;
+    long long l = (a * qs + offs) >> qbits;
+    if (l > 32767) l = 32767;
+    return (int)(w < 0 ? -l : l);
+}
+__device__ __forceinline__ int hv_dequant1(int l, int ls, int sh, int bdshift) {
+    const long long v = ((long long)l * 16 * ls) << sh;
+    return vcp_clip3(-32768, 32767, (int)((v + (1 << (bdshift - 1))) >> bdshift));
+}
+
+// Luma 8x8 transform blocks, four lanes per block (k = block slot, q = lane in the block).  S.pred holds the
+// prediction of the block at (bx,by) on entry and its reconstruction on exit; levels go to S.lv[k*64..].
+// Every lane of the warp calls this (shared-memory passes are separated by warp barriers); `act` masks.
+__device__ __forceinline__ int hv_luma_tu(HvScratch& S, bool act, int k, int q, int bx, int by, const uint8_t* __restrict__ src,
+                                          int stride, int qp, bool intra) {
+    int* T = S.t[k];
+    if (act) {   // rows: residual, horizontal transform, stage shift log2(8) + 8 - 9 = 2
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const int r = 2 * q + rr;
+            const uint2 s8 = *reinterpret_cast<const uint2*>(src + (size_t)r * stride);
+            const uint2 p8 = *reinterpret_cast<const uint2*>(&S.pred[by + r][bx]);
+            int d[8], y[8];
+#pragma unroll
+            for (int x = 0; x < 8; x++) {
+                const uint32_t sw = x < 4 ? s8.x : s8.y, pw = x < 4 ? p8.x : p8.y;
+                d[x] = (int)((sw >> (8 * (x & 3))) & 255) - (int)((pw >> (8 * (x & 3))) & 255);
+            }
+            hv_fwd8(d, y);
+#pragma unroll
+            for (int x = 0; x < 8; x++) T[8 * r + x] = (y[x] + 2) >> 2;
+        }
+    }
+    __syncwarp();
+    int nz = 0;
+    if (act) {   // columns: vertical transform (shift 9), quantise, dequantise, vertical inverse (columns first, 8.6.4.2)
+        const int qbits = 14 + qp / 6 + 4, qs = hevc_quant_scale[qp % 6], ls = hevc_level_scale[qp % 6], sh = qp / 6;
+        const long long offs = (long long)(intra ? 171 : 85) << (qbits - 9);
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            const int col = 2 * q + cc;
+            int in[8], w[8], c[8], g[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) in[r] = T[8 * r + col];
+            hv_fwd8(in, w);
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int l = hv_quant1((w[r] + 256) >> 9, qs, offs, qbits);
+                S.lv[k * 64 + 8 * r + col] = (int16_t)l;
+                nz += l != 0;
+                c[r] = hv_dequant1(l, ls, sh, 6);
+            }
+            hv_inv8(c, g);
+#pragma unroll
+            for (int r = 0; r < 8; r++) T[8 * r + col] = vcp_clip3(-32768, 32767, (g[r] + 64) >> 7);
+        }
+    }
+    nz += __shfl_xor_sync(0xffffffffu, nz, 1);
+    nz += __shfl_xor_sync(0xffffffffu, nz, 2);
+    __syncwarp();
+    if (act) {   // rows: horizontal inverse (shift 12), reconstruct in place of the prediction
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const int r = 2 * q + rr;
+            int in[8], o[8];
+#pragma unroll
+            for (int x = 0; x < 8; x++) in[x] = T[8 * r + x];
+            hv_inv8(in, o);
+            if (nz) {
+#pragma unroll
+                for (int x = 0; x < 8; x++) S.pred[by + r][bx + x] = (uint8_t)vcp_clip255((int)S.pred[by + r][bx + x] + ((o[x] + 2048) >> 12));
+            }
+        }
+    }
+    __syncwarp();
+    return nz;
+}
+
+// One 4x4 chroma transform block per lane, in registers.  pred: 4 rows packed; returns nz, writes levels and recon.
+__device__ __forceinline__ int hv_chroma_tu(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int stride, const uint32_t pred[4],
+                                            int qpc, bool intra, int16_t* lv) {
+    int t[16], w[16];
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        const uint32_t s4 = ld_u32(src + (size_t)y * stride), p4 = pred[y];
+        int d[4], o[4];
+#pragma unroll
+        for (int x = 0; x < 4; x++) d[x] = (int)((s4 >> (8 * x)) & 255) - (int)((p4 >> (8 * x)) & 255);
+        hv_fwd4(d, o);
+#pragma unroll
+        for (int x = 0; x < 4; x++) t[4 * y + x] = (o[x] + 1) >> 1;       // stage shift log2(4) + 8 - 9 = 1
+    }
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+        int in[4] = {t[x], t[4 + x], t[8 + x], t[12 + x]}, o[4];
+        hv_fwd4(in, o);
+#pragma unroll
+        for (int y = 0; y < 4; y++) w[4 * y + x] = (o[y] + 128) >> 8;     // log2(4) + 6
+    }
+    const int qbits = 14 + qpc / 6 + 5, qs = hevc_quant_scale[qpc % 6], ls = hevc_level_scale[qpc % 6], sh = qpc / 6;
+    const long long offs = (long long)(intra ? 171 : 85) << (qbits - 9);
+    int nz = 0, c[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int l = hv_quant1(w[i], qs, offs, qbits);
+        lv[i] = (int16_t)l;
+        nz += l != 0;
+        c[i] = hv_dequant1(l, ls, sh, 5);
+    }
+    if (nz) {
+        int g[16];
+#pragma unroll
+        for (int x = 0; x < 4; x++) {     // columns first
+            int in[4] = {c[x], c[4 + x], c[8 + x], c[12 + x]}, o[4];
+            hv_inv4(in, o);
+#pragma unroll
+            for (int y = 0; y < 4; y++) g[4 * y + x] = vcp_clip3(-32768, 32767, (o[y] + 64) >> 7);
+        }
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            int o[4];
+            hv_inv4(&g[4 * y], o);
+            uint32_t outw = 0;
+#pragma unroll
+            for (int x = 0; x < 4; x++) outw |= (uint32_t)vcp_clip255((int)((pred[y] >> (8 * x)) & 255) + ((o[x] + 2048) >> 12)) << (8 * x);
+            *reinterpret_cast<uint32_t*>(dst + (size_t)y * stride) = outw;
+        }
+    } else {
+#pragma unroll
+        for (int y = 0; y < 4; y++) *reinterpret_cast<uint32_t*>(dst + (size_t)y * stride) = pred[y];
+    }
+    return nz;
+}
+
+// ---- inter CUs -------------------------------------------------------------------------------------
+constexpr int HP_WARPS = 4;
+
+__global__ void __launch_bounds__(HP_WARPS * 32) hevc_p_recon_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
+    __shared__ HvScratch scr[HP_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mbi = blockIdx.x * HP_WARPS + warp;
+    const int gi = blockIdx.y + s.g0;
+    if (mbi >= g.nmb) return;
+    HvScratch& S = scr[warp];
+    const int n = vcp_frame_of(s, gi);
+    const int slot = vcp_rec_slot(s, gi, s.t), rslot = vcp_rec_slot(s, gi, s.t - 1);
+    const int mx = mbi % g.mbw, my = mbi / g.mbw;
+    const int qp = b.qp[n], qpc = hevc_chroma_qp(qp);
+    const size_t o = (size_t)gi * g.nmb + mbi;
+    const short2 mv = b.mv[o];
+    // luma prediction: full-sample vector, a copy of the reference
+    {
+        const int row = lane >> 1, hx = (lane & 1) * 8;
+        const uint8_t* r = vcp_rec_luma(b, g, rslot) + g.yoff + (ptrdiff_t)(16 * my + row + (mv.y >> 2)) * g.ys + 16 * mx + hx + (mv.x >> 2);
+        *reinterpret_cast<uint2*>(&S.pred[row][hx]) = ld8_unaligned(r);
+    }
+    // chroma prediction (8.5.3.3.3.2): the luma vector in 1/8 chroma samples -> fractions 0 or 4, 4-tap filter (-4, 36, 36, -4)
+    {
+        const int pl = lane >> 4, row = (lane >> 1) & 7, x0 = (lane & 1) * 4;
+        const int ix = mv.x >> 3, iy = mv.y >> 3, fx = mv.x & 7, fy = mv.y & 7;
+        const uint8_t* base = (pl ? b.rec_v : b.rec_u) + (size_t)rslot * g.csize + g.coff + (ptrdiff_t)(8 * my + row + iy) * g.cs + 8 * mx + x0 + ix;
+        uint32_t outw = 0;
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            const uint8_t* p = base + x;
+            int v;
+            if (!fx && !fy) v = (int)p[0] << 6;
+            else if (!fy) v = -4 * p[-1] + 36 * p[0] + 36 * p[1] - 4 * p[2];
+            else if (!fx) v = -4 * p[-g.cs] + 36 * p[0] + 36 * p[g.cs] - 4 * p[2 * g.cs];
+            else {
+                int t[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { const uint8_t* q = p + (ptrdiff_t)(k - 1) * g.cs; t[k] = -4 * q[-1] + 36 * q[0] + 36 * q[1] - 4 * q[2]; }
+                v = (-4 * t[0] + 36 * t[1] + 36 * t[2] - 4 * t[3]) >> 6;
+            }
+            outw |= (uint32_t)vcp_clip255((v + 32) >> 6) << (8 * x);
+        }
+        *reinterpret_cast<uint32_t*>(&S.cpred[pl][row][x0]) = outw;
+    }
+    __syncwarp();
+    // luma: four lanes per 8x8 block
+    const int k = (lane >> 2) & 3, q = lane & 3, bx = (k & 1) * 8, by = (k >> 1) * 8;
+    const uint8_t* srcy = b.src_y + (size_t)n * g.ysize + g.yoff + (size_t)(16 * my + by) * g.ys + 16 * mx + bx;
+    const int nzy = hv_luma_tu(S, lane < 16, k, q, bx, by, srcy, g.ys, qp, false);
+    const uint32_t ymask = __ballot_sync(0xffffffffu, lane < 16 && nzy > 0);
+    // chroma: lanes 16..23, one 4x4 block each (plane, z)
+    int nzc = 0;
+    if (lane >= 16 && lane < 24) {
+        const int pl = (lane - 16) >> 2, z = lane & 3, cx = (z & 1) * 4, cy = (z >> 1) * 4;
+        const size_t co = g.coff + (size_t)(8 * my + cy) * g.cs + 8 * mx + cx;
+        const uint8_t* sc = (pl ? b.src_v : b.src_u) + (size_t)n * g.csize + co;
+        uint8_t* dc = (pl ? b.rec_v : b.rec_u) + (size_t)slot * g.csize + co;
+        uint32_t pw[4];
+#pragma unroll
+        for (int y = 0; y < 4; y++) pw[y] = *reinterpret_cast<const uint32_t*>(&S.cpred[pl][cy + y][cx]);
+        nzc = hv_chroma_tu(sc, dc, g.cs, pw, qpc, false, &S.lv[256 + pl * 64 + z * 16]);
+    }
+    const uint32_t cmask = __ballot_sync(0xffffffffu, nzc > 0);
+    __syncwarp();
+    // reconstruction and levels out
+    if (lane < 16) {
+        const int bx4 = (lane & 3) * 4, by4 = (lane >> 2) * 4;
+        uint8_t* dst = vcp_rec_luma(b, g, slot) + g.yoff + (size_t)(16 * my + by4) * g.ys + 16 * mx + bx4;
+#pragma unroll
+        for (int y = 0; y < 4; y++) *reinterpret_cast<uint32_t*>(dst + (size_t)y * g.ys) = *reinterpret_cast<const uint32_t*>(&S.pred[by4 + y][bx4]);
+    }
+    for (int i = lane; i < 48; i += 32) reinterpret_cast<uint4*>(b.levels + o * VCP_LV_STRIDE)[i] = reinterpret_cast<const uint4*>(S.lv)[i];
+    if (lane == 0) {
+        uint32_t cbf_y = 0;
+#pragma unroll
+        for (int z = 0; z < 4; z++) cbf_y |= ((ymask >> (4 * z)) & 15u) ? 1u << z : 0u;
+        b.cbp[o] = (uint8_t)cbf_y;
+        b.modes[o] = (uint8_t)((cmask >> 16) & 0xff);      // cbf_cb in bits 0-3, cbf_cr in bits 4-7
+        b.mbtype[o] = 1;
+    }
+}
+
+// ---- intra CUs (IDR pictures), wavefront ---------------------------------------------------------------
+constexpr int HI_WARPS = 16;
+
+// DC prediction of one transform block from the reconstruction of the current picture (8.4.4.2.2 / 8.4.4.2.5).
+// Only the N samples above and the N to the left enter a DC prediction; with 16x16 CTBs in raster order their
+// substitution rules reduce to: nothing available -> 128; left missing -> first top sample; top missing ->
+// topmost left sample.  Returns the four (luma: eight) rows through `rows`.
+__device__ __forceinline__ void hv_dc_pred(const uint8_t* __restrict__ rec, int stride, bool aL, bool aT, int n, bool luma, uint8_t* out /* n*n */) {
+    int top[8], left[8];
+    if (aT) for (int i = 0; i < n; i++) top[i] = rec[-(ptrdiff_t)stride + i];
+    if (aL) for (int i = 0; i < n; i++) left[i] = rec[(ptrdiff_t)i * stride - 1];
+    if (!aT && !aL) { for (int i = 0; i < n; i++) top[i] = left[i] = 128; }
+    else if (!aL) { for (int i = 0; i < n; i++) left[i] = top[0]; }
+    else if (!aT) { for (int i = 0; i < n; i++) top[i] = left[0]; }
+    int sum = n;
+    for (int i = 0; i < n; i++) sum += top[i] + left[i];
+    const int dc = sum >> (n == 8 ? 4 : 3);
+    for (int i = 0; i < n * n; i++) out[i] = (uint8_t)dc;
+    if (luma) {
+        out[0] = (uint8_t)((left[0] + 2 * dc + top[0] + 2) >> 2);
+        for (int x = 1; x < n; x++) out[x] = (uint8_t)((top[x] + 3 * dc + 2) >> 2);
+        for (int y = 1; y < n; y++) out[y * n] = (uint8_t)((left[y] + 3 * dc + 2) >> 2);
+    }
+}
+
+__device__ void hv_encode_intra_cu(const VcpGeom& g, const VcpBufs& b, HvScratch& S, int n, int slot, int gi, int mx, int my, int row0,
+                                   int qp, int qpc, int lane) {
+    const size_t o = (size_t)gi * g.nmb + my * g.mbw + mx;
+    uint8_t* ry = vcp_rec_luma(b, g, slot) + g.yoff + (size_t)(16 * my) * g.ys + 16 * mx;
+    uint32_t cbf_y = 0, cbf_c = 0;
+    for (int z = 0; z < 4; z++) {
+        const int bx = (z & 1) * 8, by = (z >> 1) * 8;
+        const bool aL = bx > 0 || mx > 0, aT = by > 0 || my > row0;
+        // luma prediction by lane 0 into the tile, chroma by lanes 4, 5 into registers
+        if (lane == 0) {
+            uint8_t tmp[64];
+            hv_dc_pred(ry + (size_t)by * g.ys + bx, g.ys, aL, aT, 8, true, tmp);
+            for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) S.pred[by + y][bx + x] = tmp[8 * y + x];
+        }
+        __syncwarp();
+        const uint8_t* srcy = b.src_y + (size_t)n * g.ysize + g.yoff + (size_t)(16 * my + by) * g.ys + 16 * mx + bx;
+        const int nzy = hv_luma_tu(S, lane < 4, z, lane & 3, bx, by, srcy, g.ys, qp, true);
+        if (__shfl_sync(0xffffffffu, nzy, 0) > 0) cbf_y |= 1u << z;
+        // this TU's luma reconstruction must be in memory before the next TU predicts from it
+        if (lane < 16) {
+            const int r = lane >> 1, hx = (lane & 1) * 4;
+            *reinterpret_cast<uint32_t*>(ry + (size_t)(by + r) * g.ys + bx + hx) = *reinterpret_cast<const uint32_t*>(&S.pred[by + r][bx + hx]);
+        }
+        int nzc = 0;
+        if (lane == 4 || lane == 5) {
+            const int pl = lane - 4, cx = (z & 1) * 4, cy = (z >> 1) * 4;
+            const size_t co = g.coff + (size_t)(8 * my + cy) * g.cs + 8 * mx + cx;
+            const uint8_t* sc = (pl ? b.src_v : b.src_u) + (size_t)n * g.csize + co;
+            uint8_t* dc = (pl ? b.rec_v : b.rec_u) + (size_t)slot * g.csize + co;
+            uint8_t tmp[16];
+            hv_dc_pred(dc, g.cs, aL, aT, 4, false, tmp);
+            uint32_t pw[4];
+            for (int y = 0; y < 4; y++) pw[y] = (uint32_t)tmp[4 * y] | ((uint32_t)tmp[4 * y + 1] << 8) | ((uint32_t)tmp[4 * y + 2] << 16) | ((uint32_t)tmp[4 * y + 3] << 24);
+            nzc = hv_chroma_tu(sc, dc, g.cs, pw, qpc, true, &S.lv[256 + pl * 64 + z * 16]);
+        }
+        const uint32_t cm = __ballot_sync(0xffffffffu, nzc > 0);
+        if (cm & 0x10u) cbf_c |= 1u << z;
+        if (cm & 0x20u) cbf_c |= 16u << z;
+        __syncwarp();
+    }
+    for (int i = lane; i < 48; i += 32) reinterpret_cast<uint4*>(b.levels + o * VCP_LV_STRIDE)[i] = reinterpret_cast<const uint4*>(S.lv)[i];
+    if (lane == 0) {
+        b.cbp[o] = (uint8_t)cbf_y; b.modes[o] = (uint8_t)cbf_c; b.mbtype[o] = 0;
+        b.mv[o] = make_short2(0, 0); b.mvd[o] = make_short2(0, 0);
+    }
+}
+
+// grid: x = slice, y = GOP
+__global__ void __launch_bounds__(HI_WARPS * 32) hevc_i_recon_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
+    __shared__ HvScratch scr[HI_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sl = blockIdx.x, gi = blockIdx.y + s.g0;
+    const int n = vcp_frame_of(s, gi);
+    const int slot = vcp_rec_slot(s, gi, s.t);
+    const int qp = b.qp[n], qpc = hevc_chroma_qp(qp);
+    const int r0 = vcp_slice_first_row(sl, g.slices, g.mbh);
+    const int r1 = sl + 1 < g.slices ? vcp_slice_first_row(sl + 1, g.slices, g.mbh) : g.mbh;
+    const int rows = r1 - r0;
+    const int ndiag = g.mbw + rows - 1;
+    for (int d = 0; d < ndiag; d++) {
+        const int k0 = d - (g.mbw - 1) > 0 ? d - (g.mbw - 1) : 0;
+        const int k1 = d < rows - 1 ? d : rows - 1;
+        for (int k = k0 + warp; k <= k1; k += HI_WARPS)
+            hv_encode_intra_cu(g, b, scr[warp], n, slot, gi, d - k, r0 + k, r0, qp, qpc, lane);
+        __syncthreads();
+    }
+}
+
+// ---- merge / AMVP / skip, once every vector of the picture is final -----------------------------------------
+__global__ void __launch_bounds__(128) hevc_cuinfo_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
+    const int mbi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gi = blockIdx.y + s.g0;
+    if (mbi >= g.nmb) return;
+    const size_t base = (size_t)gi * g.nmb;
+    const int mx = mbi % g.mbw, my = mbi / g.mbw;
+    const int row0 = vcp_row_first(b, my);
+    // neighbours: 0 A1 left, 1 B1 above, 2 B0 above-right, 3 B2 above-left (A0 is never decoded before us)
+    const int nx[4] = {mx - 1, mx, mx + 1, mx - 1}, ny[4] = {my, my - 1, my - 1, my - 1};
+    bool av[4], inter[4]; int vx[4], vy[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        av[k] = nx[k] >= 0 && nx[k] < g.mbw && ny[k] >= row0;
+        inter[k] = false; vx[k] = vy[k] = 0;
+        if (av[k]) {
+            const size_t o = base + ny[k] * g.mbw + nx[k];
+            if (b.mbtype[o] != 0) { inter[k] = true; const short2 v = b.mv[o]; vx[k] = v.x; vy[k] = v.y; }
+        }
+    }
+    const size_t o = base + mbi;
+    if (b.mbtype[o] == 0) return;     // intra
+    const short2 mv = b.mv[o];
+    // merge candidate 0: A1, B1, B0, B2, else the zero vector
+    int mgx = 0, mgy = 0;
+    { const int k = inter[0] ? 0 : inter[1] ? 1 : inter[2] ? 2 : inter[3] ? 3 : -1; if (k >= 0) { mgx = vx[k]; mgy = vy[k]; } }
+    const int cbf_any = (b.cbp[o] & 15) | b.modes[o];
+    if (mgx == mv.x && mgy == mv.y) {
+        b.cbp[o] = (uint8_t)((b.cbp[o] & 15) | 16);           // merge_flag
+        b.mvd[o] = make_short2(0, 0);
+        if (!cbf_any) b.mbtype[o] = 2;                           // cu_skip_flag
+        return;
+    }
+    // AMVP (8.5.3.2.6/7), one reference picture, no temporal candidate
+    bool have_a = inter[0], have_b = inter[2] || inter[1] || inter[3];
+    int ax = vx[0], ay = vy[0];
+    const int kb = inter[2] ? 2 : inter[1] ? 1 : 3;
+    const int bx = have_b ? vx[kb] : 0, by = have_b ? vy[kb] : 0;
+    if (!av[0] && have_b) { have_a = true; ax = bx; ay = by; }   // isScaledFlag == 0: B stands in for A
+    int lx[2] = {0, 0}, ly[2] = {0, 0}, cnt = 0;
+    if (have_a) { lx[cnt] = ax; ly[cnt] = ay; cnt++; }
+    if (have_b && !(have_a && ax == bx && ay == by)) { lx[cnt] = bx; ly[cnt] = by; cnt++; }
+    const int c0 = vcp_se_len(mv.x - lx[0]) + vcp_se_len(mv.y - ly[0]);
+    const int c1 = vcp_se_len(mv.x - lx[1]) + vcp_se_len(mv.y - ly[1]);
+    const int idx = c1 < c0 ? 1 : 0;
+    b.cbp[o] = (uint8_t)((b.cbp[o] & 15) | (idx << 5));
+    b.mvd[o] = make_short2((short)(mv.x - lx[idx]), (short)(mv.y - ly[idx]));
+}
+
+}  // namespace
+
+void vcp_launch_hevc_p_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
+    dim3 grid((g.nmb + HP_WARPS - 1) / HP_WARPS, s.ngop);
+    hevc_p_recon_kernel<<<grid, HP_WARPS * 32, 0, st>>>(g, b, s);
+}
+void vcp_launch_hevc_i_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
+    dim3 grid(g.slices, s.ngop);
+    hevc_i_recon_kernel<<<grid, HI_WARPS * 32, 0, st>>>(g, b, s);
+}
+void vcp_launch_hevc_cuinfo(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
+    dim3 grid((g.nmb + 127) / 128, s.ngop);
+    hevc_cuinfo_kernel<<<grid, 128, 0, st>>>(g, b, s);
+}
