@@ -1,8 +1,8 @@
 /* CPU oracle of the HEVC path (BASELINE config #4) -- TEST INFRASTRUCTURE ONLY.
  * Included at the end of h264_oracle.c so that it shares the frame / motion-search / bit-writer /
- * arithmetic-coder helpers.  The CUDA product path for HEVC is NOT built yet: this
- * file exists so that the kernels have a pinned target; it is pinned the same way as the H.264
- * oracle, by the FFmpeg `hevc` decoder reproducing the reconstruction bit-exactly.
+ * arithmetic-coder helpers.  This
+ * file is pinned the same way as the H.264 oracle, by the FFmpeg `hevc` decoder reproducing the
+ * reconstruction bit-exactly; the CUDA path (csrc/k6_hevc.cu, k5_cabac.cu) must match it byte for byte.
  *
  * No reference file to follow (the reference shells out to libx265 / hevc_nvenc through ffmpeg,
  * /root/reference/internal/config/config.go:47-50); the arithmetic restates ITU-T H.265.
@@ -448,7 +448,7 @@ static void hevc_write_mvd(Cabac* c, int dx, int dy) {
     if (ax) { if (ax > 1) cabac_ueg_bypass(c, (unsigned)(ax - 2), 1); cabac_bypass(c, dx < 0); }
     if (ay) { if (ay > 1) cabac_ueg_bypass(c, (unsigned)(ay - 2), 1); cabac_bypass(c, dy < 0); }
 }
-static void hevc_write_slice_data(HEnc* h, BW* b, int r0, int r1) {
+static unsigned long long hevc_write_slice_data(HEnc* h, BW* b, int r0, int r1) {
     Enc* e = h->e;
     Cabac c; hevc_cabac_init(&c, b, h->idr ? 0 : 1, h->qp);
     for (int cy = r0; cy < r1; cy++)
@@ -482,6 +482,7 @@ static void hevc_write_slice_data(HEnc* h, BW* b, int r0, int r1) {
             cabac_terminate(&c, cy == r1 - 1 && cx == e->mbw - 1);       /* end_of_slice_segment_flag */
         }
     while (b->nbits) bw_put(b, 1, 0);
+    return c.nbins;
 }
 
 /* ---- parameter sets and slice header ----------------------------------------------------------- */
@@ -619,7 +620,8 @@ int hevc_orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, 
     memset(e, 0, sizeof *e);
     e->p = *p;
     if (p->width < 16 || p->height < 16 || (p->width & 1) || (p->height & 1) || p->gop < 1 || p->slices < 0) return VCPENC_E_ARGS;
-    if (p->in_fmt != VCPENC_FMT_YUV420P || p->rc_mode != VCPENC_RC_CQP) return VCPENC_E_ARGS;
+    if (p->in_fmt != VCPENC_FMT_YUV420P) return VCPENC_E_ARGS;
+    if (p->rc_mode == VCPENC_RC_ABR && (p->bitrate <= 0 || p->fps_num <= 0 || p->fps_den <= 0)) return VCPENC_E_ARGS;
     e->mbw = (p->width + 15) / 16; e->mbh = (p->height + 15) / 16; e->nmb = e->mbw * e->mbh;
     if (e->p.slices == 0) e->p.slices = vcp_auto_slices(e->mbh, 1);
     if (e->p.slices > e->mbh) return VCPENC_E_ARGS;
@@ -637,9 +639,18 @@ int hevc_orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, 
     const size_t fsz = (size_t)p->width * p->height + 2 * (size_t)((p->width + 1) / 2) * ((p->height + 1) / 2);
     size_t o = 0;
     int ri = 0;
+    /* rate control: the same model and two-picture feedback delay as the H.264 path (vcp_algo.h) */
+    const int abr = p->rc_mode == VCPENC_RC_ABR;
+    const int rc_qp0 = abr ? vcp_rc_initial_qp(p->bitrate, p->fps_num, p->fps_den, p->width, p->height) : 0;
+    unsigned long long rc_cum = 0;
+    int rc_qp_next[2] = {0, 0};
     for (int n = 0; n < nframes; n++) {
         const int t = n % p->gop, idr = t == 0;
-        const int qp = idr ? p->qp_i : p->qp_p;
+        int qp = idr ? p->qp_i : p->qp_p;
+        if (abr) {
+            if (idr) { rc_cum = 0; rc_qp_next[0] = rc_qp_next[1] = rc_qp0; qp = rc_qp0 - VCP_RC_QP_I_OFFSET; if (qp < 0) qp = 0; }
+            else { qp = rc_qp_next[0]; rc_qp_next[0] = rc_qp_next[1]; }
+        }
         h.qp = qp; h.qpc = hevc_chroma_qp(qp); h.idr = idr;
         { Frame tf = e->prev_orig; e->prev_orig = e->cur; e->cur = tf; Half th = e->hprev; e->hprev = e->hcur; e->hcur = th; }
         frame_load_yuv420p(&e->cur, frames + (size_t)n * fsz, p->width, p->height);
@@ -681,15 +692,23 @@ int hevc_orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, 
             k = hevc_write_sps(e, out + o, out_cap - o); if (!k) { rc = VCPENC_E_OVERFLOW; goto done; } o += k;
             k = hevc_write_pps(out + o, out_cap - o); if (!k) { rc = VCPENC_E_OVERFLOW; goto done; } o += k;
         }
+        unsigned long long frame_bits = 0;
         for (int s = 0; s < p->slices; s++) {
             const int r0 = slice_first_row(e, s), r1 = s + 1 < p->slices ? slice_first_row(e, s + 1) : e->mbh;
             BW b; bw_init(&b, e->rbsp, e->rbsp_cap);
             hevc_write_slice_header(e, &b, r0 * e->mbw, idr, t, qp);
-            hevc_write_slice_data(&h, &b, r0, r1);
+            frame_bits += (hevc_write_slice_data(&h, &b, r0, r1) * VCP_CABAC_BITS_PER_BIN_Q4) >> 4;
             if (b.overflow) { rc = VCPENC_E_OVERFLOW; goto done; }
             const size_t k = hevc_nal_write(out + o, out_cap - o, idr ? 19 : 1, e->rbsp, b.pos);   /* IDR_W_RADL / TRAIL_R */
             if (!k) { rc = VCPENC_E_OVERFLOW; goto done; }
             o += k;
+        }
+        if (abr) {
+            int gop_len = p->gop;
+            if (n - t + gop_len > nframes) gop_len = nframes - (n - t);
+            const unsigned long long budget = (unsigned long long)p->bitrate * (unsigned)p->fps_den / (unsigned)p->fps_num * (unsigned)gop_len;
+            rc_cum += frame_bits;
+            rc_qp_next[1] = vcp_rc_next_qp(rc_qp0, qp, rc_qp_next[0], idr, frame_bits, rc_cum, t, gop_len, budget);
         }
         if (info) { info[n].offset = au0; info[n].size = (uint32_t)(o - au0); info[n].is_idr = (uint8_t)idr; info[n].qp = (uint8_t)qp; }
         frame_pad(h.rec);

@@ -95,7 +95,7 @@ struct vcpenc_session {
     // debug taps
     short2* dbg_mv = nullptr; uint8_t* dbg_type = nullptr; uint8_t* dbg_cbp = nullptr;
     // host
-    std::vector<uint8_t> sps, pps;
+    std::vector<uint8_t> vps, sps, pps;   // vps: HEVC only
     std::vector<uint8_t> h_qp;
     uint8_t* h_out = nullptr; size_t h_out_cap = 0;   // pinned
     bool encoded = false;
@@ -124,7 +124,7 @@ int dev_alloc(vcpenc_session* s, T** p, size_t count, char* err, size_t errlen) 
 }
 
 int check_params(const vcpenc_params& p, char* err, size_t errlen) {
-    if (p.codec != VCPENC_CODEC_H264) { set_err(err, errlen, "HEVC encoding is not implemented yet (H.264 only)"); return VCPENC_E_UNSUPPORTED; }
+    if (p.codec != VCPENC_CODEC_H264 && p.codec != VCPENC_CODEC_HEVC) { set_err(err, errlen, "unknown codec %d", p.codec); return VCPENC_E_ARGS; }
     if (p.entropy < 0 || p.entropy > 1) { set_err(err, errlen, "bad entropy coder %d", p.entropy); return VCPENC_E_ARGS; }
     if (p.width < 16 || p.height < 16 || (p.width & 1) || (p.height & 1)) { set_err(err, errlen, "unsupported picture size %dx%d", p.width, p.height); return VCPENC_E_ARGS; }
     if (p.gop < 1 || p.slices < 0 || p.slices > (p.height + 15) / 16) { set_err(err, errlen, "bad gop/slices"); return VCPENC_E_ARGS; }
@@ -283,7 +283,8 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     CK(cudaSetDevice(device));
     vcpenc_session* s = new vcpenc_session();
     s->p = *pp; s->device = device; s->max_frames = max_frames; s->gop_base = pp->first_gop;
-    if (s->p.slices == 0) s->p.slices = vcp_auto_slices((pp->height + 15) / 16, pp->entropy);   // encoder's choice
+    if (s->p.codec == VCPENC_CODEC_HEVC) { s->p.entropy = 1; s->p.transform8x8 = 0; s->p.deblock_idc = 1; }   // HEVC: CABAC only; in-loop filters off
+    if (s->p.slices == 0) s->p.slices = vcp_auto_slices((pp->height + 15) / 16, s->p.entropy);   // encoder's choice
     pp = &s->p;
     VcpGeom& g = s->g;
     g.w = pp->width; g.h = pp->height;
@@ -298,6 +299,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     g.coff = VCP_PADC * g.cs + VCP_PADC;
     g.hoff = VCP_PAD1 * g.hs + VCP_PAD1;
     g.slices = pp->slices; g.deblock_idc = pp->deblock_idc; g.cabac = pp->entropy; g.t8x8 = pp->transform8x8 ? 1 : 0;
+    g.hevc = pp->codec == VCPENC_CODEC_HEVC;
     g.rc_abr = pp->rc_mode == VCPENC_RC_ABR;
     g.rc_bitrate = pp->bitrate; g.fps_num = pp->fps_num; g.fps_den = pp->fps_den;
     g.rc_qp0 = g.rc_abr ? vcp_rc_initial_qp(pp->bitrate, pp->fps_num, pp->fps_den, pp->width, pp->height) : 0;
@@ -431,8 +433,8 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
         v.mbbits += q * G * nmb; v.mbbitoff += q * G * nmb;
         s->bpar[q] = v;
     }
-    s->sps = vcp::make_sps_nal(*pp);
-    s->pps = vcp::make_pps_nal(*pp);
+    if (g.hevc) { s->vps = vcp::make_hevc_vps_nal(*pp); s->sps = vcp::make_hevc_sps_nal(*pp); s->pps = vcp::make_hevc_pps_nal(*pp); }
+    else { s->sps = vcp::make_sps_nal(*pp); s->pps = vcp::make_pps_nal(*pp); }
     *out = s;
     return VCPENC_OK;
 #undef TRY
@@ -537,7 +539,16 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
             if (sp.ngop <= 0) continue;
             // the records of this parity were last read by the entropy pass of step t-2
             if (!s->profile && t >= 2) CK(cudaStreamWaitEvent(st, s->ev_ent[k][par], 0));
-            if (t == 0) {
+            if (g.hevc) {
+                // same chain, HEVC kernels (k6_hevc.cu): no intra in P pictures, no in-loop filter, no half-sample planes
+                if (t == 0) { Prof pr(s, VCPENC_K_I_RECON, 1, st); vcp_launch_hevc_i_recon(g, bt, sp, st); }
+                else {
+                    if (!s->profile) CK(cudaStreamWaitEvent(st, s->ev_pre_t[t], 0));
+                    { Prof pr(s, VCPENC_K_ME_REFINE, 1, st); vcp_launch_me_refine(g, bt, sp, st); }
+                    { Prof pr(s, VCPENC_K_P_RECON, 1, st); vcp_launch_hevc_p_recon(g, bt, sp, st); }
+                    { Prof pr(s, VCPENC_K_MBINFO, 1, st); vcp_launch_hevc_cuinfo(g, bt, sp, st); }
+                }
+            } else if (t == 0) {
                 Prof pr(s, VCPENC_K_I_RECON, 1, st);
                 vcp_launch_i_recon(g, bt, sp, st);
             } else {
@@ -560,7 +571,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 CK(cudaStreamWaitEvent(se, s->ev_rec[k][par], 0));
             }
             if (g.cabac) {
-                { Prof pr(s, VCPENC_K_CABAC_BINS, g.rc_abr ? 2 : 1, se); vcp_launch_cabac_bins(g, bt, sp, se); }
+                { Prof pr(s, VCPENC_K_CABAC_BINS, g.rc_abr ? 2 : 1, se); if (g.hevc) vcp_launch_hevc_bins(g, bt, sp, se); else vcp_launch_cabac_bins(g, bt, sp, se); }
                 if (g.rc_abr) { Prof pr(s, VCPENC_K_RC, 1, se); vcp_launch_rc_update(g, bt, sp, se); }
                 // the arithmetic coder takes the bins in batches of kCabacBatch pictures per GOP, on
                 // its own stream: one lane per slice, long-running but only a few warps wide
@@ -582,10 +593,10 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 if (g.rc_abr) { Prof pr(s, VCPENC_K_RC, 1, se); vcp_launch_rc_update(g, bt, sp, se); }
             }
             if (!s->profile) CK(cudaEventRecord(s->ev_ent[k][par], se));
-            if (g.deblock_idc != 1) { Prof pr(s, VCPENC_K_DEBLOCK, 1, st); vcp_launch_deblock(g, bt, sp, st); }
+            if (g.deblock_idc != 1 && !g.hevc) { Prof pr(s, VCPENC_K_DEBLOCK, 1, st); vcp_launch_deblock(g, bt, sp, st); }
             { Prof pr(s, VCPENC_K_PAD, 1, st); vcp_launch_pad(g, bt, sp, st); }
             // half-sample planes of this reconstruction for the next picture's search and prediction
-            if (t + 1 < gop && t + 1 < N) { Prof pr(s, VCPENC_K_HPEL, 1, st); vcp_launch_hpel(g, bt, sp, st); }
+            if (t + 1 < gop && t + 1 < N && !g.hevc) { Prof pr(s, VCPENC_K_HPEL, 1, st); vcp_launch_hpel(g, bt, sp, st); }
         }
     }
     if (!s->profile)
@@ -665,10 +676,11 @@ int vcpenc_session_download(vcpenc_session* s, uint8_t* out, size_t out_cap, siz
         const bool idr = (n % s->p.gop) == 0;
         const size_t au0 = o;
         size_t need = 0;
-        if (idr) need += 8 + s->sps.size() + s->pps.size();
+        if (idr) need += 12 + s->vps.size() + s->sps.size() + s->pps.size();
         for (int k = 0; k < S; k++) need += idx[(size_t)n * S + k].y;
         if (o + need > out_cap) { set_err(err, errlen, "output buffer too small (%zu needed)", o + need); return VCPENC_E_OVERFLOW; }
         if (idr) {
+            if (!s->vps.empty()) { memcpy(out + o, sc, 4); o += 4; memcpy(out + o, s->vps.data(), s->vps.size()); o += s->vps.size(); }
             memcpy(out + o, sc, 4); o += 4; memcpy(out + o, s->sps.data(), s->sps.size()); o += s->sps.size();
             memcpy(out + o, sc, 4); o += 4; memcpy(out + o, s->pps.data(), s->pps.size()); o += s->pps.size();
         }

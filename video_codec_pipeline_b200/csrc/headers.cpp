@@ -90,4 +90,124 @@ std::vector<uint8_t> make_pps_nal(const vcpenc_params& p) {
     return nal_escape(3, 8, b.bytes());
 }
 
+// ---- HEVC (H.265 7.3.2.1 - 7.3.2.3, 7.3.3, E.2.1) ------------------------------------------------------
+// Main profile, 16x16 coding tree blocks that are never split, 8x8 / 4x4 transform blocks, one reference
+// picture (short-term RPS {-1}), no temporal vector prediction, in-loop filters off.
+
+int hevc_level_idc_for(int cw, int ch, int fps_num, int fps_den) {
+    // table A.8: general_level_idc = 30 x level; MaxLumaPs, MaxLumaSr
+    static const struct { int idc; long ps; double sr; } L[] = {
+        {30, 36864, 552960},        {60, 122880, 3686400},       {63, 245760, 7372800},      {90, 552960, 16588800},
+        {93, 983040, 33177600},     {120, 2228224, 66846720},    {123, 2228224, 133693440},  {150, 8912896, 267386880},
+        {153, 8912896, 534773760},  {156, 8912896, 1069547520},  {180, 35651584, 1069547520},
+        {183, 35651584, 2139095040.0}, {186, 35651584, 4278190080.0}};
+    const long ps = (long)cw * ch;
+    const double sr = (double)ps * fps_num / (fps_den > 0 ? fps_den : 1);
+    for (const auto& l : L)
+        if (ps <= l.ps && sr <= l.sr) return l.idc;
+    return 186;
+}
+
+static void hevc_profile_tier_level(BitWriter& b, const vcpenc_params& p) {
+    const int cw = (p.width + 15) / 16 * 16, ch = (p.height + 15) / 16 * 16;
+    b.put(2, 0); b.put(1, 0); b.put(5, 1);      // general_profile_space, tier, profile_idc: Main
+    b.put32(0x60000000u);                       // compatibility flags: Main, Main 10
+    b.put(1, 1); b.put(1, 0); b.put(1, 0); b.put(1, 1);   // progressive, interlaced, non-packed, frame-only
+    b.put(22, 0); b.put(22, 0);                 // reserved zero bits (43) and general_inbld_flag
+    b.put(8, (uint32_t)hevc_level_idc_for(cw, ch, p.fps_num, p.fps_den));
+}
+
+std::vector<uint8_t> make_hevc_vps_nal(const vcpenc_params& p) {
+    BitWriter b;
+    b.put(4, 0);            // vps_video_parameter_set_id
+    b.put(1, 1); b.put(1, 1);   // base layer internal / available
+    b.put(6, 0);            // vps_max_layers_minus1
+    b.put(3, 0);            // vps_max_sub_layers_minus1
+    b.put(1, 1);            // vps_temporal_id_nesting_flag
+    b.put(16, 0xffff);
+    hevc_profile_tier_level(b, p);
+    b.put(1, 1);            // vps_sub_layer_ordering_info_present_flag
+    b.ue(1); b.ue(0); b.ue(0);  // max_dec_pic_buffering_minus1, max_num_reorder_pics, max_latency_increase_plus1
+    b.put(6, 0);            // vps_max_layer_id
+    b.ue(0);                // vps_num_layer_sets_minus1
+    b.put(1, 0);            // vps_timing_info_present_flag
+    b.put(1, 0);            // vps_extension_flag
+    b.trailing();
+    return hevc_nal_escape(32, b.bytes());
+}
+
+std::vector<uint8_t> make_hevc_sps_nal(const vcpenc_params& p) {
+    const int cw = (p.width + 15) / 16 * 16, ch = (p.height + 15) / 16 * 16;
+    BitWriter b;
+    b.put(4, 0); b.put(3, 0); b.put(1, 1);      // vps id, max_sub_layers_minus1, temporal_id_nesting
+    hevc_profile_tier_level(b, p);
+    b.ue(0);                // sps_seq_parameter_set_id
+    b.ue(1);                // chroma_format_idc
+    b.ue((uint32_t)cw); b.ue((uint32_t)ch);
+    const int cr = cw - p.width, cb = ch - p.height;
+    if (cr || cb) { b.put(1, 1); b.ue(0); b.ue((uint32_t)(cr / 2)); b.ue(0); b.ue((uint32_t)(cb / 2)); }
+    else b.put(1, 0);
+    b.ue(0); b.ue(0);       // bit_depth_luma_minus8, bit_depth_chroma_minus8
+    b.ue(4);                // log2_max_pic_order_cnt_lsb_minus4
+    b.put(1, 1); b.ue(1); b.ue(0); b.ue(0);     // sub-layer ordering info
+    b.ue(1);                // log2_min_luma_coding_block_size_minus3 (16)
+    b.ue(0);                // log2_diff_max_min_luma_coding_block_size
+    b.ue(0);                // log2_min_luma_transform_block_size_minus2 (4)
+    b.ue(1);                // log2_diff_max_min_luma_transform_block_size (8)
+    b.ue(0); b.ue(0);       // max_transform_hierarchy_depth_inter / intra
+    b.put(1, 0);            // scaling_list_enabled_flag
+    b.put(1, 0);            // amp_enabled_flag
+    b.put(1, 0);            // sample_adaptive_offset_enabled_flag
+    b.put(1, 0);            // pcm_enabled_flag
+    b.ue(1);                // num_short_term_ref_pic_sets
+    b.ue(1); b.ue(0); b.ue(0); b.put(1, 1);     // one negative picture: delta_poc_s0_minus1 0, used
+    b.put(1, 0);            // long_term_ref_pics_present_flag
+    b.put(1, 0);            // sps_temporal_mvp_enabled_flag
+    b.put(1, 0);            // strong_intra_smoothing_enabled_flag
+    b.put(1, 1);            // vui_parameters_present_flag
+    b.put(1, 0); b.put(1, 0); b.put(1, 0); b.put(1, 0);   // aspect ratio, overscan, video signal, chroma loc
+    b.put(1, 0); b.put(1, 0); b.put(1, 0);                // neutral chroma, field_seq, frame_field_info
+    b.put(1, 0);            // default_display_window_flag
+    b.put(1, 1);            // vui_timing_info_present_flag
+    b.put32((uint32_t)p.fps_den); b.put32((uint32_t)p.fps_num);
+    b.put(1, 0);            // vui_poc_proportional_to_timing_flag
+    b.put(1, 0);            // vui_hrd_parameters_present_flag
+    b.put(1, 0);            // bitstream_restriction_flag
+    b.put(1, 0);            // sps_extension_present_flag
+    b.trailing();
+    return hevc_nal_escape(33, b.bytes());
+}
+
+std::vector<uint8_t> make_hevc_pps_nal(const vcpenc_params&) {
+    BitWriter b;
+    b.ue(0); b.ue(0);       // pps id, sps id
+    b.put(1, 0);            // dependent_slice_segments_enabled_flag
+    b.put(1, 0);            // output_flag_present_flag
+    b.put(3, 0);            // num_extra_slice_header_bits
+    b.put(1, 0);            // sign_data_hiding_enabled_flag
+    b.put(1, 0);            // cabac_init_present_flag
+    b.ue(0); b.ue(0);       // num_ref_idx_l0/l1_default_active_minus1
+    b.se(0);                // init_qp_minus26
+    b.put(1, 0);            // constrained_intra_pred_flag
+    b.put(1, 0);            // transform_skip_enabled_flag
+    b.put(1, 0);            // cu_qp_delta_enabled_flag
+    b.se(0); b.se(0);       // pps_cb_qp_offset, pps_cr_qp_offset
+    b.put(1, 0);            // pps_slice_chroma_qp_offsets_present_flag
+    b.put(1, 0); b.put(1, 0);   // weighted_pred_flag, weighted_bipred_flag
+    b.put(1, 0);            // transquant_bypass_enabled_flag
+    b.put(1, 0);            // tiles_enabled_flag
+    b.put(1, 0);            // entropy_coding_sync_enabled_flag
+    b.put(1, 0);            // pps_loop_filter_across_slices_enabled_flag
+    b.put(1, 1);            // deblocking_filter_control_present_flag
+    b.put(1, 0);            // deblocking_filter_override_enabled_flag
+    b.put(1, 1);            // pps_deblocking_filter_disabled_flag
+    b.put(1, 0);            // pps_scaling_list_data_present_flag
+    b.put(1, 0);            // lists_modification_present_flag
+    b.ue(0);                // log2_parallel_merge_level_minus2
+    b.put(1, 0);            // slice_segment_header_extension_present_flag
+    b.put(1, 0);            // pps_extension_present_flag
+    b.trailing();
+    return hevc_nal_escape(34, b.bytes());
+}
+
 }  // namespace vcp

@@ -47,9 +47,28 @@ inline std::vector<uint8_t> nal_escape(int ref_idc, int type, const std::vector<
     return o;
 }
 
+// HEVC: two-byte nal_unit_header (layer 0, temporal id 0), same emulation prevention
+inline std::vector<uint8_t> hevc_nal_escape(int type, const std::vector<uint8_t>& rbsp) {
+    std::vector<uint8_t> o;
+    o.push_back((uint8_t)(type << 1));
+    o.push_back(1);
+    int zeros = 0;
+    for (uint8_t b : rbsp) {
+        if (zeros >= 2 && b <= 3) { o.push_back(3); zeros = 0; }
+        o.push_back(b);
+        zeros = b == 0 ? zeros + 1 : 0;
+    }
+    return o;
+}
+
 int level_idc_for(int mbw, int mbh, int fps_num, int fps_den);
 std::vector<uint8_t> make_sps_nal(const vcpenc_params& p);  // NAL payload incl. header byte
 std::vector<uint8_t> make_pps_nal(const vcpenc_params& p);
+// HEVC parameter sets for the stream structure of k6_hevc.cu (NAL payload incl. the two header bytes)
+int hevc_level_idc_for(int cw, int ch, int fps_num, int fps_den);
+std::vector<uint8_t> make_hevc_vps_nal(const vcpenc_params& p);
+std::vector<uint8_t> make_hevc_sps_nal(const vcpenc_params& p);
+std::vector<uint8_t> make_hevc_pps_nal(const vcpenc_params& p);
 
 }  // namespace vcp
 

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
     uint32_t best = warp_min(lane < 11 ? (((uint32_t)mycost << 4) | (uint32_t)lane) : 0xffffffffu);
     const int bvx = __shfl_sync(0xffffffffu, cvx, (int)(best & 15)), bvy = __shfl_sync(0xffffffffu, cvy, (int)(best & 15));
     uint32_t bcost = best >> 4;
-    if (bcost < VCP_SUBPEL_SKIP_COST) {   // warp-uniform
+    if (bcost < VCP_SUBPEL_SKIP_COST || g.hevc) {   // warp-uniform; the HEVC path keeps luma vectors on full samples
         if (lane == 0) {
             b.mv[(size_t)gi * g.nmb + mbi] = make_short2((short)(4 * bvx), (short)(4 * bvy));
             b.mbtype[(size_t)gi * g.nmb + mbi] = VCP_MB_P16;

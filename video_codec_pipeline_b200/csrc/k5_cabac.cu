@@ -26,6 +26,7 @@
 #define VCP_TAB static __device__ const
 #include "h264_cabac_tables.h"
 #include "h264_tables.h"
+#include "hevc_tables.h"
 #include "vcp_entropy.cuh"
 
 namespace {
@@ -298,6 +299,252 @@ __global__ void __launch_bounds__(CB_WARPS * 32) cabac_bins_kernel(VcpGeom g, Vc
     mb_bins<true>(wr, S, M, lane);
 }
 
+
+// ================================= HEVC (k6_hevc.cu records) =======================================
+// residual_coding (7.3.8.11) of one transform block: 8x8 luma (four 4x4 sub-blocks) or 4x4 chroma, diagonal
+// scan, no sign hiding, no transform skip.  lv: levels in raster order (shared memory).
+// Mirrors oracle/hevc_oracle.inc.c hevc_residual bin for bin.
+template <bool WRITE>
+__device__ __forceinline__ void hevc_residual_bins(BinSink<WRITE>& bs, const int16_t* lv, int log2n, int cidx) {
+    const int n = 1 << log2n, nsb = n == 8 ? 4 : 1;
+    unsigned long long mask = 0;       // bit 16 i + p: coefficient p of sub-block i (scan order) is non-zero
+    for (int i = 0; i < nsb; i++)
+        for (int p = 0; p < 16; p++) {
+            const int x = (n == 8 ? 4 * hevc_diag2_x[i] : 0) + hevc_diag4_x[p], y = (n == 8 ? 4 * hevc_diag2_y[i] : 0) + hevc_diag4_y[p];
+            mask |= (unsigned long long)(lv[y * n + x] != 0) << (16 * i + p);
+        }
+    if (!mask) return;
+    const int last = 63 - __clzll((long long)mask), lastsb = last >> 4;
+    {   // last_sig_coeff_{x,y}_prefix (context coded, truncated unary), then the suffixes (bypass)
+        const int lx = (n == 8 ? 4 * hevc_diag2_x[lastsb] : 0) + hevc_diag4_x[last & 15];
+        const int ly = (n == 8 ? 4 * hevc_diag2_y[lastsb] : 0) + hevc_diag4_y[last & 15];
+        int off, shift;
+        if (cidx == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; }
+        else { off = 15; shift = log2n - 2; }
+        const int cmax = (log2n << 1) - 1;
+#pragma unroll
+        for (int comp = 0; comp < 2; comp++) {
+            const int v = comp ? ly : lx, base = (comp ? HC_LAST_Y : HC_LAST_X) + off;
+            const int prefix = v < 4 ? v : (v < 6 ? 4 : 5);
+            for (int i = 0; i < prefix; i++) bs.put(base + (i >> shift), 1);
+            if (prefix < cmax) bs.put(base + (prefix >> shift), 0);
+        }
+        if (lx >= 4) bs.bypass(lx & 1);
+        if (ly >= 4) bs.bypass(ly & 1);
+    }
+    uint32_t csbf = 0;                 // bit ys * 2 + xs
+    bool prev_gt1_zero = false, first_sb = true;
+    for (int i = lastsb; i >= 0; i--) {
+        const int xs = n == 8 ? hevc_diag2_x[i] : 0, ys = n == 8 ? hevc_diag2_y[i] : 0;
+        const uint32_t sm = (uint32_t)(mask >> (16 * i)) & 0xffffu;
+        bool any = sm != 0;
+        const int right = (n == 8 && xs + 1 < 2) ? (csbf >> (ys * 2 + xs + 1)) & 1 : 0;
+        const int below = (n == 8 && ys + 1 < 2) ? (csbf >> ((ys + 1) * 2 + xs)) & 1 : 0;
+        bool infer_dc = false;
+        if (i < lastsb && i > 0) { bs.put(HC_CSBF + (cidx ? 2 : 0) + ((right | below) ? 1 : 0), any); infer_dc = true; }
+        else any = true;               // first and last sub-block: coded_sub_block_flag inferred 1
+        csbf |= (any ? 1u : 0u) << (ys * 2 + xs);
+        if (!any) continue;
+        // sig_coeff_flag
+        const int start = i == lastsb ? (last & 15) - 1 : 15;
+        for (int p = start; p >= 0; p--) {
+            if (p == 0 && infer_dc && !(sm & 0xfffeu)) break;    // the only coefficient of a coded sub-block: inferred
+            const int xp = hevc_diag4_x[p], yp = hevc_diag4_y[p];
+            int sc;
+            if (log2n == 2) sc = hevc_sig_ctx_map4[(yp << 2) + xp];
+            else if (i == 0 && p == 0) sc = 0;
+            else {
+                const int pat = right | (below << 1);
+                if (pat == 0) sc = (xp + yp == 0) ? 2 : (xp + yp < 3) ? 1 : 0;
+                else if (pat == 1) sc = yp == 0 ? 2 : yp == 1 ? 1 : 0;
+                else if (pat == 2) sc = xp == 0 ? 2 : xp == 1 ? 1 : 0;
+                else sc = 2;
+                if (cidx == 0) { if (i > 0) sc += 3; sc += 9; } else sc += 9;
+            }
+            bs.put(HC_SIG + (cidx == 0 ? sc : 27 + sc), (sm >> p) & 1);
+        }
+        // levels from the highest scan position down
+        const int x0 = n == 8 ? 4 * xs : 0, y0 = n == 8 ? 4 * ys : 0;
+#define HV_COEF(p_) ((int)lv[(y0 + hevc_diag4_y[p_]) * n + x0 + hevc_diag4_x[p_]])
+        int ctxset = (i == 0 || cidx > 0) ? 0 : 2;
+        if (!first_sb && prev_gt1_zero) ctxset++;
+        first_sb = false;
+        int g1ctx = 1, first_g2 = -1, k = 0;
+        uint32_t g1mask = 0;
+        for (uint32_t m = sm; m && k < 8; k++) {
+            const int p = 31 - __clz(m);
+            m &= ~(1u << p);
+            const int g1 = vcp_iabs(HV_COEF(p)) > 1;
+            g1mask |= (uint32_t)g1 << k;
+            bs.put(HC_GT1 + (cidx ? 16 : 0) + ctxset * 4 + g1ctx, g1);
+            if (g1) { g1ctx = 0; if (first_g2 < 0) first_g2 = k; }
+            else if (g1ctx > 0 && g1ctx < 3) g1ctx++;
+        }
+        prev_gt1_zero = g1ctx == 0;
+        int g2flag = 0;
+        if (first_g2 >= 0) {
+            uint32_t m = sm;
+            for (int q = 0; q < first_g2; q++) m &= ~(1u << (31 - __clz(m)));
+            g2flag = vcp_iabs(HV_COEF(31 - __clz(m))) > 2;
+            bs.put(HC_GT2 + (cidx ? 4 : 0) + ctxset, g2flag);
+        }
+        for (uint32_t m = sm; m;) { const int p = 31 - __clz(m); m &= ~(1u << p); bs.bypass(HV_COEF(p) < 0); }
+        int rice = 0;
+        k = 0;
+        for (uint32_t m = sm; m; k++) {
+            const int p = 31 - __clz(m);
+            m &= ~(1u << p);
+            const int a = vcp_iabs(HV_COEF(p));
+            const int base = k < 8 ? 1 + (int)((g1mask >> k) & 1) + (k == first_g2 ? g2flag : 0) : 1;
+            const int thresh = k < 8 ? (k == first_g2 ? 3 : 2) : 1;
+            if (base != thresh) continue;
+            const int rem = a - base;      // coeff_abs_level_remaining (9.3.3.11)
+            if (rem < (3 << rice)) {
+                const int len = rem >> rice;
+                for (int q = 0; q < len; q++) bs.bypass(1);
+                bs.bypass(0);
+                for (int q = rice - 1; q >= 0; q--) bs.bypass((rem >> q) & 1);
+            } else {
+                int len = rice, v = rem - (3 << rice);
+                while (v >= (1 << len)) { v -= 1 << len; len++; }
+                for (int q = 0; q < 3 + len - rice; q++) bs.bypass(1);
+                bs.bypass(0);
+                for (int q = len - 1; q >= 0; q--) bs.bypass((v >> q) & 1);
+            }
+            if (a > 3 * (1 << rice) && rice < 4) rice++;
+        }
+#undef HV_COEF
+    }
+}
+
+struct CuCtx {
+    int type, cbf_y, cbf_c, merge, mvp_idx;   // cbf_c: Cb in bits 0-3, Cr in bits 4-7
+    int tA, tB;                               // neighbours' types (-1: unavailable)
+    short2 mvd;
+    bool idr, last_in_slice;
+};
+
+// all bins of one coding unit (oracle: hevc_write_slice_data / hevc_write_tu_tree); `lane` selects the syntax group:
+// 0 = CU header + chroma cbf at depth 0; per transform unit z: 1+4z flags, 2+4z luma, 3+4z Cb, 4+4z Cr; 17 = end_of_slice_segment_flag
+template <bool WRITE>
+__device__ __forceinline__ void hevc_cu_bins(BinSink<WRITE>& bs, const int16_t* lv, const CuCtx& M, int lane) {
+    const bool skip = M.type == 2, intra = M.type == 0;
+    const int any_cb = (M.cbf_c & 15) != 0, any_cr = (M.cbf_c >> 4) != 0;
+    const bool any = M.cbf_y || M.cbf_c;
+    const bool tree = !skip && (intra || any);
+    if (lane == 0) {
+        if (!M.idr) bs.put(HC_SKIP + (M.tA == 2) + (M.tB == 2), skip);
+        if (skip) return;
+        if (!M.idr) bs.put(HC_PRED_MODE, intra);
+        bs.put(HC_PART_MODE, 1);                                 // PART_2Nx2N
+        if (intra) {
+            bs.put(HC_PREV_INTRA, 1);                            // prev_intra_luma_pred_flag
+            bs.bypass(1); bs.bypass(0);                          // mpm_idx 1: DC
+            bs.put(HC_CHROMA_MODE, 0);                           // intra_chroma_pred_mode 4
+        } else {
+            bs.put(HC_MERGE_FLAG, M.merge);
+            if (!M.merge) {
+                const int dx = M.mvd.x, dy = M.mvd.y, ax = vcp_iabs(dx), ay = vcp_iabs(dy);
+                bs.put(HC_MVD_GT0, ax > 0);
+                bs.put(HC_MVD_GT0, ay > 0);
+                if (ax) bs.put(HC_MVD_GT1, ax > 1);
+                if (ay) bs.put(HC_MVD_GT1, ay > 1);
+                if (ax) { if (ax > 1) bs.ueg((uint32_t)(ax - 2), 1); bs.bypass(dx < 0); }
+                if (ay) { if (ay > 1) bs.ueg((uint32_t)(ay - 2), 1); bs.bypass(dy < 0); }
+                bs.put(HC_MVP_FLAG, M.mvp_idx);
+                bs.put(HC_RQT_ROOT_CBF, any);
+            }
+        }
+        if (tree) { bs.put(HC_CBF_CHROMA + 0, any_cb); bs.put(HC_CBF_CHROMA + 0, any_cr); }
+    } else if (lane < 17) {
+        if (!tree) return;
+        const int z = (lane - 1) >> 2, part = (lane - 1) & 3;
+        if (part == 0) {
+            if (any_cb) bs.put(HC_CBF_CHROMA + 1, (M.cbf_c >> z) & 1);
+            if (any_cr) bs.put(HC_CBF_CHROMA + 1, (M.cbf_c >> (4 + z)) & 1);
+            bs.put(HC_CBF_LUMA + 0, (M.cbf_y >> z) & 1);
+        } else if (part == 1) {
+            if ((M.cbf_y >> z) & 1) hevc_residual_bins<WRITE>(bs, lv + z * 64, 3, 0);
+        } else if (part == 2) {
+            if ((M.cbf_c >> z) & 1) hevc_residual_bins<WRITE>(bs, lv + 256 + z * 16, 2, 1);
+        } else {
+            if ((M.cbf_c >> (4 + z)) & 1) hevc_residual_bins<WRITE>(bs, lv + 320 + z * 16, 2, 2);
+        }
+    } else if (lane == 17) {
+        bs.term(M.last_in_slice);
+    }
+}
+
+__global__ void __launch_bounds__(CB_WARPS * 32) hevc_bins_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
+    __shared__ __align__(16) int16_t lvs[CB_WARPS][384];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mbi = blockIdx.x * CB_WARPS + warp;
+    const int gi = blockIdx.y + s.g0;
+    if (mbi >= g.nmb) return;
+    const int n = vcp_frame_of(s, gi);
+    const size_t o = (size_t)gi * g.nmb + mbi;
+    const int mx = mbi % g.mbw, my = mbi / g.mbw;
+    const int sl = vcp_row_slice(b, my), row0 = vcp_row_first(b, my);
+    CuCtx M;
+    M.type = b.mbtype[o];
+    { const int c = b.cbp[o]; M.cbf_y = c & 15; M.merge = (c >> 4) & 1; M.mvp_idx = (c >> 5) & 1; }
+    M.cbf_c = b.modes[o]; M.mvd = b.mvd[o];
+    M.tA = mx > 0 ? b.mbtype[o - 1] : -1;
+    M.tB = my > row0 ? b.mbtype[o - g.mbw] : -1;
+    M.idr = s.t == 0;
+    {
+        const int r1 = sl + 1 < g.slices ? vcp_slice_first_row(sl + 1, g.slices, g.mbh) : g.mbh;
+        M.last_in_slice = (my == r1 - 1) && (mx == g.mbw - 1);
+    }
+    if (M.type != 2)
+        for (int i = lane; i < 48; i += 32) reinterpret_cast<uint4*>(lvs[warp])[i] = reinterpret_cast<const uint4*>(b.levels + o * VCP_LV_STRIDE)[i];
+    __syncwarp();
+    BinSink<false> cnt{nullptr, 0};
+    hevc_cu_bins<false>(cnt, lvs[warp], M, lane);
+    int incl = cnt.n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long off = 0;
+    if (lane == 0) {
+        off = atomicAdd(b.bins_cursor, (unsigned long long)total);
+        if (off + (unsigned long long)total > b.bins_cap) { atomicExch(b.error_flag, 3); off = ~0ull; }
+        else {
+            b.mbdesc[(size_t)n * g.nmb + mbi] = make_uint2((uint32_t)off, (uint32_t)total | ((uint32_t)(off >> 32) << 20));
+            atomicAdd(&b.slice_bins[(size_t)n * g.slices + sl], (uint32_t)total);
+        }
+    }
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (off == ~0ull) return;
+    BinSink<true> wr{b.bins + off + (incl - cnt.n), 0};
+    hevc_cu_bins<true>(wr, lvs[warp], M, lane);
+}
+
+// slice_segment_header (7.3.6.1) for the stream structure of k6_hevc.cu, byte_alignment() included
+__device__ __forceinline__ void hevc_slice_header(const VcpGeom& g, int first_ctb, bool idr, int poc, int qp, SeqBits& w) {
+    w.put(1, first_ctb == 0);
+    if (idr) w.put(1, 0);                  // no_output_of_prior_pics_flag
+    w.ue(0);                               // slice_pic_parameter_set_id
+    if (first_ctb) {
+        int bits = 0;
+        while ((1 << bits) < g.nmb) bits++;
+        w.put(bits, (uint32_t)first_ctb);  // slice_segment_address
+    }
+    w.ue(idr ? 2 : 1);                     // slice_type
+    if (!idr) {
+        w.put(8, (uint32_t)(poc & 255));   // slice_pic_order_cnt_lsb
+        w.put(1, 1);                       // short_term_ref_pic_set_sps_flag
+        w.put(1, 0);                       // num_ref_idx_active_override_flag
+        w.ue(4);                           // five_minus_max_num_merge_cand
+    }
+    w.se(qp - 26);
+    w.put(1, 1);
+    while (w.pos & 7) w.pos++;             // the buffer is zero-filled
+}
+
 // ---- arithmetic coder, one WARP per slice ------------------------------------------------------
 // The coder is a serial dependency chain (state -> rLPS -> range/low -> renormalisation), so what
 // bounds a slice is latency per bin, not throughput.  Lane 0 runs the chain out of shared memory;
@@ -366,8 +613,12 @@ __global__ void __launch_bounds__(AC_WARPS * 32) cabac_encode_kernel(VcpGeom g, 
     AcScratch& A = scr[warp];
     {   // context initialisation (9.3.1.1), lanes share the contexts
         const int tab = idr ? 0 : 1;
-        for (int i = lane; i < NCTX; i += 32) {
-            const int m = vcp_cabac_init_mn[tab][i][0], nn = vcp_cabac_init_mn[tab][i][1];
+        for (int i = lane; i < (g.hevc ? (int)HC_NCTX : NCTX); i += 32) {
+            int m, nn;
+            if (g.hevc) {   // H.265 9.3.2.2: slope / offset nibbles of initValue
+                const int v = hevc_init_values[tab][i];
+                m = (v >> 4) * 5 - 45; nn = ((v & 15) << 3) - 16;
+            } else { m = vcp_cabac_init_mn[tab][i][0]; nn = vcp_cabac_init_mn[tab][i][1]; }
             const int pre = vcp_clip3(1, 126, ((m * vcp_clip3(0, 51, qp)) >> 4) + nn);
             A.rec[i] = ent[pre <= 63 ? ((63 - pre) << 1) : (((pre - 64) << 1) | 1)];
         }
@@ -391,8 +642,11 @@ __global__ void __launch_bounds__(AC_WARPS * 32) cabac_encode_kernel(VcpGeom g, 
         reinterpret_cast<uint4*>(dst)[0] = make_uint4(0, 0, 0, 0);
         reinterpret_cast<uint4*>(dst)[1] = make_uint4(0, 0, 0, 0);
         SeqBits w{dst, 0};
-        slice_header_bits(g, first, idr, t, (s.gop0 + gi) & 1, qp, &w);
-        while (w.pos & 7) w.put(1, 1);   // cabac_alignment_one_bit
+        if (g.hevc) hevc_slice_header(g, first, idr, t, qp, w);
+        else {
+            slice_header_bits(g, first, idr, t, (s.gop0 + gi) & 1, qp, &w);
+            while (w.pos & 7) w.put(1, 1);   // cabac_alignment_one_bit
+        }
         wpos = w.pos >> 3;
     }
     wpos = __shfl_sync(0xffffffffu, wpos, 0);
@@ -538,6 +792,12 @@ __global__ void cabac_rc_bits_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
 void vcp_launch_cabac_bins(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
     dim3 grid((g.nmb + CB_WARPS - 1) / CB_WARPS, s.ngop);
     cabac_bins_kernel<<<grid, CB_WARPS * 32, 0, st>>>(g, b, s);
+    if (g.rc_abr) cabac_rc_bits_kernel<<<(s.ngop + 63) / 64, 64, 0, st>>>(g, b, s);
+}
+
+void vcp_launch_hevc_bins(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
+    dim3 grid((g.nmb + CB_WARPS - 1) / CB_WARPS, s.ngop);
+    hevc_bins_kernel<<<grid, CB_WARPS * 32, 0, st>>>(g, b, s);
     if (g.rc_abr) cabac_rc_bits_kernel<<<(s.ngop + 63) / 64, 64, 0, st>>>(g, b, s);
 }
 

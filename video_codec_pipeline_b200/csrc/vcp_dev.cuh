@@ -27,6 +27,7 @@ struct VcpGeom {
     int deblock_idc;
     int cabac;         // entropy_coding_mode_flag
     int t8x8;          // transform_8x8_mode_flag (High profile)
+    int hevc;          // codec: 0 H.264, 1 HEVC (k6_hevc.cu; the motion search and the arithmetic coder are shared)
     // rate control (VCPENC_RC_ABR): see vcp_algo.h
     int rc_abr, rc_qp0, rc_bitrate, fps_num, fps_den;
 };
@@ -132,6 +133,10 @@ void vcp_launch_cavlc_write(const VcpGeom& g, const VcpBufs& b, const VcpStep& s
 void vcp_launch_nal_pack(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_cabac_bins(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_cabac_encode(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, int t0, int t1, cudaStream_t st);
+void vcp_launch_hevc_p_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
+void vcp_launch_hevc_i_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
+void vcp_launch_hevc_cuinfo(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
+void vcp_launch_hevc_bins(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_rc_update(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 
 #ifdef __CUDACC__

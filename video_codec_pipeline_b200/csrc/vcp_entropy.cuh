@@ -115,7 +115,8 @@ __device__ __forceinline__ void nal_pack_body(const VcpGeom& g, const VcpBufs& b
     }
     uint32_t nesc;
     block_excl_scan(cnt, wsum, nesc);
-    const uint32_t size = 5 + bytes + nesc;
+    const uint32_t hdr = g.hevc ? 6 : 5;   // start code + nal_unit_header (two bytes in HEVC)
+    const uint32_t size = hdr + bytes + nesc;
     if (threadIdx.x == 0) {
         const unsigned long long o = atomicAdd(b.out_cursor, (unsigned long long)size);
         out_base = o;
@@ -126,8 +127,12 @@ __device__ __forceinline__ void nal_pack_body(const VcpGeom& g, const VcpBufs& b
     __syncthreads();
     if (out_base + size > b.out_cap) return;
     uint8_t* dst = b.out + out_base;
-    if (threadIdx.x < 5) dst[threadIdx.x] = threadIdx.x < 3 ? 0 : (threadIdx.x == 3 ? 1 : (uint8_t)(idr ? 0x65 : 0x41));
-    dst += 5;
+    if (threadIdx.x < hdr) {
+        // H.264: nal_ref_idc 3 | type 5 / nal_ref_idc 2 | type 1.  HEVC: IDR_W_RADL (19) / TRAIL_R (1), layer 0, temporal id 0
+        const uint8_t h0 = g.hevc ? (uint8_t)(idr ? 19 << 1 : 1 << 1) : (uint8_t)(idr ? 0x65 : 0x41);
+        dst[threadIdx.x] = threadIdx.x < 3 ? 0 : threadIdx.x == 3 ? 1 : threadIdx.x == 4 ? h0 : 1;
+    }
+    dst += hdr;
     uint32_t carry = 0;
     for (uint32_t ps = 0; ps < npass; ps++) {
         const uint32_t i0 = (ps * PACK_THREADS + threadIdx.x) * PACK_BYTES;
