@@ -341,6 +341,37 @@ def test_edge_cases(built):
     assert e.value.code == 1
 
 
+def test_transcode_hevc_presets(built, tmp_path):
+    """The reference's h265-* presets (internal/config/config.go:47-50) through the transcode entry point: the MP4
+    (hvc1 + hvcC) demuxes and decodes with FFmpeg to the pictures the raw .h265 output decodes to."""
+    w, h, n = 640, 360, 20
+    clip = synth.make_clip(w, h, n, seed=79)
+    y4m = tmp_path / "in.y4m"
+    with open(y4m, "wb") as f:
+        f.write(b"YUV4MPEG2 W%d H%d F30:1 Ip A1:1 C420jpeg\n" % (w, h))
+        for fr in clip:
+            f.write(b"FRAME\n" + fr.tobytes())
+    for name, args in (("cpu", "-c:v libx265 -preset medium -crf 28 -c:a aac -b:a 128k -movflags +faststart -g 10"),
+                       ("nvenc", "-c:v hevc_nvenc -preset p4 -b:v 8M -c:a aac -b:a 128k -movflags +faststart -g 10"),
+                       ("nvenc-hq", "-c:v hevc_nvenc -preset p7 -tune hq -b:v 10M -c:a aac -b:a 192k -movflags +faststart -g 10")):
+        out = tmp_path / ("out_%s.mp4" % name)
+        raw = tmp_path / ("out_%s.h265" % name)
+        api.transcode(str(y4m), str(out), args)
+        api.transcode(str(y4m), str(raw), args)
+        api.verify(str(out))
+        api.verify(str(raw))
+        data = out.read_bytes()
+        assert b"hvc1" in data and b"hvcC" in data and data.find(b"moov") < data.find(b"mdat")
+        if arbiter.available():
+            assert arbiter.probe_has_video(str(out))
+            dec = arbiter.decode_file(str(out))
+            ref = arbiter.decode_annexb_hevc(raw.read_bytes())
+            assert len(dec) == n and len(ref) == n
+            for i in range(n):
+                assert np.array_equal(_flat(dec[i]), _flat(ref[i])), (name, i)
+            assert arbiter.psnr(dec[5][0], synth.split_planes(clip[5], w, h)[0]) > 32
+
+
 def test_transcode_drop_in(built, tmp_path):
     """The call the consumer makes: path in, path out, the reference's preset string, --verify."""
     w, h, n = 640, 360, 20

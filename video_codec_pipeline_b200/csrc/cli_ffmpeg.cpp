@@ -32,7 +32,7 @@ int main(int argc, char** argv) {
                 input = argv[++i]; seen_input = true; continue;
             }
             if (a == "-version") { printf("%s\n", vcpenc_version()); return 0; }
-            if (a == "-encoders") { printf(" V..... h264_nvenc           B200 CUDA H.264 encoder (libvcpenc)\n V..... libx264              B200 CUDA H.264 encoder (libvcpenc)\n"); return 0; }
+            if (a == "-encoders") { printf(" V..... h264_nvenc           B200 CUDA H.264 encoder (libvcpenc)\n V..... libx264              B200 CUDA H.264 encoder (libvcpenc)\n V..... hevc_nvenc           B200 CUDA HEVC encoder (libvcpenc)\n V..... libx265              B200 CUDA HEVC encoder (libvcpenc)\n"); return 0; }
             // options that take a value and precede -i (-s, -r, -f, -pix_fmt for raw input)
             toks.push_back(argv[i]);
             continue;

@@ -1,5 +1,5 @@
-// ISO BMFF (MP4) writer for one AVC video track: ftyp / moov / mdat with
-// stsd(avc1+avcC), stts, stss, stsc, stsz, stco|co64; `moov` first when faststart.
+// ISO BMFF (MP4) writer for one AVC or HEVC video track: ftyp / moov / mdat with
+// stsd(avc1+avcC | hvc1+hvcC), stts, stss, stsc, stsz, stco|co64; `moov` first when faststart.
 //
 // Replaces libavformat's `mov` muxer (and its second pass for `-movflags +faststart`) inside
 // the ffmpeg child the reference spawns (/root/reference/cmd/consumer.go:376-382; output is
@@ -55,8 +55,41 @@ void unity_matrix(Box& b) {
     for (uint32_t v : m) b.u32(v);
 }
 
-std::vector<uint8_t> build_moov(const vcpenc_params& p, const std::vector<uint8_t>& sps, const std::vector<uint8_t>& pps,
+// HEVCDecoderConfigurationRecord (ISO/IEC 14496-15 8.3.3.1): profile / tier / level copied out of the SPS,
+// then one complete array per parameter-set type
+void hvcc_box(Box& b, const ParamSets& ps) {
+    std::vector<uint8_t> sps;            // SPS without emulation prevention bytes
+    for (size_t i = 0, z = 0; i < ps.sps.size(); i++) {
+        const uint8_t v = ps.sps[i];
+        if (z >= 2 && v == 3) { z = 0; continue; }
+        sps.push_back(v);
+        z = v == 0 ? z + 1 : 0;
+    }
+    size_t c = b.begin("hvcC");
+    b.u8(1);
+    // sps: 2 bytes NAL header, 1 byte vps id / sub layers / nesting, then general profile_tier_level: 12 bytes
+    for (int i = 0; i < 12; i++) b.u8(sps.size() > (size_t)(3 + i) ? sps[3 + i] : 0);
+    b.u16(0xF000);                       // min_spatial_segmentation_idc 0
+    b.u8(0xFC);                          // parallelismType 0 (unknown)
+    b.u8(0xFC | 1);                      // chroma_format_idc 4:2:0
+    b.u8(0xF8); b.u8(0xF8);              // bit depth luma / chroma minus 8
+    b.u16(0);                            // avgFrameRate: unspecified
+    b.u8((0 << 6) | (1 << 3) | (1 << 2) | 3);   // constantFrameRate 0, numTemporalLayers 1, temporalIdNested 1, 4-byte lengths
+    b.u8(3);
+    const std::vector<uint8_t>* arr[3] = {&ps.vps, &ps.sps, &ps.pps};
+    const int types[3] = {32, 33, 34};
+    for (int i = 0; i < 3; i++) {
+        b.u8(0x80 | types[i]);           // array_completeness 1
+        b.u16(1);
+        b.u16((uint32_t)arr[i]->size()); b.bytes(arr[i]->data(), arr[i]->size());
+    }
+    b.end(c);
+}
+
+std::vector<uint8_t> build_moov(const vcpenc_params& p, const ParamSets& ps,
                                 const std::vector<Mp4Sample>& samples, uint64_t chunk_offset) {
+    const std::vector<uint8_t>&sps = ps.sps, &pps = ps.pps;
+    const bool hevc = p.codec == VCPENC_CODEC_HEVC;
     const uint32_t n = (uint32_t)samples.size();
     const uint32_t mts = (uint32_t)p.fps_num, delta = (uint32_t)p.fps_den;   // media timescale / sample delta
     const uint64_t mdur = (uint64_t)n * delta;
@@ -101,18 +134,22 @@ std::vector<uint8_t> build_moov(const vcpenc_params& p, const std::vector<uint8_
     size_t stbl = b.begin("stbl");
     {
         size_t a = b.begin("stsd"); b.full(0, 0); b.u32(1);
-        size_t e = b.begin("avc1");
+        size_t e = b.begin(hevc ? "hvc1" : "avc1");
         b.zeros(6); b.u16(1);
         b.zeros(16);
         b.u16((uint32_t)p.width); b.u16((uint32_t)p.height);
         b.u32(0x00480000); b.u32(0x00480000); b.u32(0); b.u16(1);
         b.zeros(32);
         b.u16(0x0018); b.u16(0xFFFF);
-        size_t c = b.begin("avcC");
-        b.u8(1); b.u8(sps.size() > 1 ? sps[1] : 66); b.u8(sps.size() > 2 ? sps[2] : 0); b.u8(sps.size() > 3 ? sps[3] : 40);
-        b.u8(0xFF); b.u8(0xE1); b.u16((uint32_t)sps.size()); b.bytes(sps.data(), sps.size());
-        b.u8(1); b.u16((uint32_t)pps.size()); b.bytes(pps.data(), pps.size());
-        b.end(c); b.end(e); b.end(a);
+        if (hevc) hvcc_box(b, ps);
+        else {
+            size_t c = b.begin("avcC");
+            b.u8(1); b.u8(sps.size() > 1 ? sps[1] : 66); b.u8(sps.size() > 2 ? sps[2] : 0); b.u8(sps.size() > 3 ? sps[3] : 40);
+            b.u8(0xFF); b.u8(0xE1); b.u16((uint32_t)sps.size()); b.bytes(sps.data(), sps.size());
+            b.u8(1); b.u16((uint32_t)pps.size()); b.bytes(pps.data(), pps.size());
+            b.end(c);
+        }
+        b.end(e); b.end(a);
 
         a = b.begin("stts"); b.full(0, 0); b.u32(1); b.u32(n); b.u32(delta); b.end(a);
         a = b.begin("stss"); b.full(0, 0);
@@ -134,12 +171,12 @@ std::vector<uint8_t> build_moov(const vcpenc_params& p, const std::vector<uint8_
 
 }  // namespace
 
-int write_mp4(const vcpenc_params& p, const std::vector<uint8_t>& sps, const std::vector<uint8_t>& pps,
+int write_mp4(const vcpenc_params& p, const ParamSets& ps,
               const std::vector<Mp4Sample>& samples, const uint8_t* mdat, uint64_t mdat_len, const char* path,
               char* err, size_t errlen) {
     Box ftyp;
     size_t a = ftyp.begin("ftyp");
-    ftyp.tag("isom"); ftyp.u32(0x200); ftyp.tag("isom"); ftyp.tag("iso2"); ftyp.tag("avc1"); ftyp.tag("mp41");
+    ftyp.tag("isom"); ftyp.u32(0x200); ftyp.tag("isom"); ftyp.tag("iso2"); ftyp.tag(p.codec == VCPENC_CODEC_HEVC ? "hvc1" : "avc1"); ftyp.tag("mp41");
     ftyp.end(a);
     const bool big = mdat_len + 8 > 0xFFFFFFFFull;
     const uint64_t mdat_hdr = big ? 16 : 8;
@@ -147,14 +184,14 @@ int write_mp4(const vcpenc_params& p, const std::vector<uint8_t>& sps, const std
     std::vector<uint8_t> moov;
     if (p.faststart) {
         // moov size depends on stco vs co64; iterate once
-        moov = build_moov(p, sps, pps, samples, 0);
+        moov = build_moov(p, ps, samples, 0);
         chunk_off = ftyp.d.size() + moov.size() + mdat_hdr;
-        std::vector<uint8_t> m2 = build_moov(p, sps, pps, samples, chunk_off);
-        if (m2.size() != moov.size()) { chunk_off = ftyp.d.size() + m2.size() + mdat_hdr; m2 = build_moov(p, sps, pps, samples, chunk_off); }
+        std::vector<uint8_t> m2 = build_moov(p, ps, samples, chunk_off);
+        if (m2.size() != moov.size()) { chunk_off = ftyp.d.size() + m2.size() + mdat_hdr; m2 = build_moov(p, ps, samples, chunk_off); }
         moov.swap(m2);
     } else {
         chunk_off = ftyp.d.size() + mdat_hdr;
-        moov = build_moov(p, sps, pps, samples, chunk_off);
+        moov = build_moov(p, ps, samples, chunk_off);
     }
     FILE* f = fopen(path, "wb");
     if (!f) { set_err(err, errlen, "cannot create %s", path); return VCPENC_E_IO; }
@@ -174,12 +211,13 @@ int write_mp4(const vcpenc_params& p, const std::vector<uint8_t>& sps, const std
 
 using namespace vcp;
 
-// Annex-B (with per-frame index) -> MP4.  Parameter sets go to avcC and are dropped from the
+// Annex-B (with per-frame index) -> MP4.  Parameter sets go to avcC / hvcC and are dropped from the
 // samples; every other NAL gets a 4-byte length prefix.
 extern "C" int vcpenc_mux_mp4(const vcpenc_params* p, const uint8_t* annexb, size_t len, const vcpenc_frame_info* info,
                               int nframes, const char* path, char* err, size_t errlen) {
     if (!p || !annexb || !info || nframes < 1 || !path) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
-    std::vector<uint8_t> sps, pps, mdat;
+    std::vector<uint8_t> mdat;
+    ParamSets ps;
     std::vector<Mp4Sample> samples;
     mdat.reserve(len + (size_t)nframes * 8);
     for (int i = 0; i < nframes; i++) {
@@ -188,9 +226,7 @@ extern "C" int vcpenc_mux_mp4(const vcpenc_params* p, const uint8_t* annexb, siz
         Mp4Sample s{mdat.size(), 0, info[i].is_idr != 0};
         for (const auto& nal : nals) {
             if (!nal.n) continue;
-            const int t = nal.p[0] & 31;
-            if (t == 7) { if (sps.empty()) sps.assign(nal.p, nal.p + nal.n); continue; }
-            if (t == 8) { if (pps.empty()) pps.assign(nal.p, nal.p + nal.n); continue; }
+            if (ps.take(p->codec, nal)) continue;
             const uint32_t n = (uint32_t)nal.n;
             const uint8_t h[4] = {(uint8_t)(n >> 24), (uint8_t)(n >> 16), (uint8_t)(n >> 8), (uint8_t)n};
             mdat.insert(mdat.end(), h, h + 4);
@@ -199,7 +235,9 @@ extern "C" int vcpenc_mux_mp4(const vcpenc_params* p, const uint8_t* annexb, siz
         s.size = (uint32_t)(mdat.size() - s.offset);
         samples.push_back(s);
     }
-    if (sps.empty()) sps = make_sps_nal(*p);
-    if (pps.empty()) pps = make_pps_nal(*p);
-    return write_mp4(*p, sps, pps, samples, mdat.data(), mdat.size(), path, err, errlen);
+    const bool hevc = p->codec == VCPENC_CODEC_HEVC;
+    if (hevc && ps.vps.empty()) ps.vps = make_hevc_vps_nal(*p);
+    if (ps.sps.empty()) ps.sps = hevc ? make_hevc_sps_nal(*p) : make_sps_nal(*p);
+    if (ps.pps.empty()) ps.pps = hevc ? make_hevc_pps_nal(*p) : make_pps_nal(*p);
+    return write_mp4(*p, ps, samples, mdat.data(), mdat.size(), path, err, errlen);
 }

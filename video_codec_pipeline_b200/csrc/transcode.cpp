@@ -191,7 +191,6 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
     vcpenc_params p;
     int rc = vcpenc_parse_args(argc, argv, &p, err, errlen);
     if (rc) return rc;
-    if (p.codec != VCPENC_CODEC_H264) { set_err(err, errlen, "HEVC encoding is not implemented yet (H.264 only)"); return VCPENC_E_UNSUPPORTED; }
     if (vcpenc_device_count() <= 0) { set_err(err, errlen, "no CUDA device available (libvcpenc has no CPU fallback)"); return VCPENC_E_NODEVICE; }
 
     const std::string in = input, outp = output;
@@ -269,9 +268,10 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
     };
     std::vector<Shard> shards((size_t)ndev);
     for (int d = 0; d < ndev; d++) shards[d].device = (t_device + d) % std::max(1, vcpenc_device_count());
-    std::vector<uint8_t> mdat, annexb_all, sps, pps;
+    std::vector<uint8_t> mdat, annexb_all;
+    ParamSets psets;
     std::vector<Mp4Sample> samples;
-    const bool raw_out = ends_with(outp, ".h264") || ends_with(outp, ".264");
+    const bool raw_out = ends_with(outp, ".h264") || ends_with(outp, ".264") || ends_with(outp, ".h265") || ends_with(outp, ".265") || ends_with(outp, ".hevc");
     long total = 0;
     int gop_index = 0;
     auto fail = [&](int code) {
@@ -335,9 +335,7 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
                 Mp4Sample sm{mdat.size(), 0, sh.info[i].is_idr != 0};
                 for (const auto& nal : split_annexb(sh.bits.data() + sh.info[i].offset, sh.info[i].size)) {
                     if (!nal.n) continue;
-                    const int t = nal.p[0] & 31;
-                    if (t == 7) { if (sps.empty()) sps.assign(nal.p, nal.p + nal.n); continue; }
-                    if (t == 8) { if (pps.empty()) pps.assign(nal.p, nal.p + nal.n); continue; }
+                    if (psets.take(p.codec, nal)) continue;
                     const uint32_t k = (uint32_t)nal.n;
                     const uint8_t h[4] = {(uint8_t)(k >> 24), (uint8_t)(k >> 16), (uint8_t)(k >> 8), (uint8_t)k};
                     mdat.insert(mdat.end(), h, h + 4);
@@ -359,7 +357,7 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
         const bool ok = fwrite(annexb_all.data(), 1, annexb_all.size(), f) == annexb_all.size();
         if (fclose(f) != 0 || !ok) { set_err(err, errlen, "short write to %s", output); remove(output); return VCPENC_E_IO; }
     } else {
-        rc = write_mp4(p, sps, pps, samples, mdat.data(), mdat.size(), output, err, errlen);
+        rc = write_mp4(p, psets, samples, mdat.data(), mdat.size(), output, err, errlen);
         if (rc) { remove(output); return rc; }
     }
     t_mux = lap(tl);

@@ -3,7 +3,7 @@
 // Reference: verifyOutputFile (/root/reference/cmd/consumer.go:396-419): the file must exist,
 // be non-empty, and `ffprobe -select_streams v:0 -show_entries stream=codec_type` must print
 // "video".  Here: the container must parse as ISO BMFF with a `moov` holding a track whose
-// handler is 'vide' with a non-empty sample table, or be an Annex-B H.264 elementary stream
+// handler is 'vide' with a non-empty sample table, or be an Annex-B H.264 / HEVC elementary stream
 // starting with a parameter set.  Error strings follow the reference's.
 #include <sys/stat.h>
 
@@ -83,8 +83,11 @@ extern "C" int vcpenc_verify(const char* path, char* err, size_t errlen) {
             o += sz;
         }
     } else if (got >= 5 && head[0] == 0 && head[1] == 0 && (head[2] == 1 || (head[2] == 0 && head[3] == 1))) {
-        const int t = (head[2] == 1 ? head[3] : head[4]) & 31;
-        video = t == 7 || t == 9 || t == 5 || t == 1;
+        const uint8_t* h = head[2] == 1 ? head + 3 : head + 4;
+        const int t = h[0] & 31;                 // H.264 nal_unit_type
+        const int t5 = (h[0] >> 1) & 63;         // HEVC nal_unit_type (two-byte header: layer 0, temporal id + 1 != 0)
+        video = t == 7 || t == 9 || t == 5 || t == 1 ||
+                (!(h[0] & 0x81) && (h[1] & 7) && !(h[1] >> 3) && (t5 == 32 || t5 == 33 || t5 == 35 || (t5 >= 16 && t5 <= 21) || t5 <= 9));
     }
     fclose(f);
     if (!video) { set_err(err, errlen, "无有效视频流"); return VCPENC_E_VERIFY; }
