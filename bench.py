@@ -43,14 +43,28 @@ SEED = 1080
 ENTROPY = 0
 SLICES = 1
 T8X8 = 0
+CODEC = 0          # 0 H.264, 1 HEVC (--codec hevc: BASELINE.json configs[3], one GPU's GOP shard)
 METRIC = "1080p H.264 encode fps (GOP=60, CAVLC, I+P)"
 WORKLOAD = "configs[1]: 1080p30 yuv420p, GOP=60, CAVLC, I+P, deblock, CQP 25/27"
 
 
-def select_workload(name: str, entropy: int, slices: int = -1):
+def select_workload(name: str, entropy: int, slices: int = -1, codec: str = "h264"):
     """Default = BASELINE.json configs[1].  `4k` = the single-GPU shard of configs[2]: 4K60, High
     profile (CABAC + 8x8 transform) unless --entropy 0 asks for the CAVLC/Baseline variant."""
-    global W, H, FPS, SEED, ENTROPY, METRIC, WORKLOAD, SLICES, T8X8
+    global W, H, FPS, SEED, ENTROPY, METRIC, WORKLOAD, SLICES, T8X8, CODEC
+    if codec == "hevc":
+        # configs[3]: the h265-* presets' path.  Stream structure of csrc/k6_hevc.cu: Main profile, 16x16 coding
+        # units, 8x8 transforms, full-sample motion, CABAC, no in-loop filters (DESIGN.md 1, "HEVC")
+        CODEC = 1
+        if name == "4k":
+            W, H, FPS, SEED = 3840, 2160, 60, 2160
+        ENTROPY, T8X8 = 1, 0
+        mbh = (H + 15) // 16
+        SLICES = slices if slices >= 0 else max(1, mbh // 17)
+        METRIC = "%s HEVC encode fps (GOP=60, Main profile, I+P)" % ("4K" if name == "4k" else "1080p")
+        WORKLOAD = "%s: %dx%d@%d yuv420p, HEVC Main, GOP=60, CABAC, %d slice%s, I+P, CQP %d/%d" % (
+            "configs[3] (one GPU's GOP shard)" if name == "4k" else "configs[3] at 1080p", W, H, FPS, SLICES, "" if SLICES == 1 else "s", QP_I, QP_P)
+        return
     if name == "4k":
         W, H, FPS, SEED = 3840, 2160, 60, 2160
         ENTROPY = 1 if entropy < 0 else entropy
@@ -141,7 +155,9 @@ def cpu_port_fps(frames: np.ndarray, threads: int, frames_per_gop: int):
         jobs.append(frames[g * GOP: g * GOP + frames_per_gop])
 
     def one(fr):
-        p = pyoracle.make_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, entropy=ENTROPY, slices=SLICES, transform8x8=T8X8)
+        p = pyoracle.make_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, entropy=ENTROPY, slices=SLICES, transform8x8=T8X8, codec=CODEC)
+        if CODEC:
+            return len(pyoracle.encode_hevc(p, fr)["stream"])
         return len(pyoracle.encode(p, fr, want_recon=False)["stream"])
 
     pyoracle.lib()
@@ -175,7 +191,7 @@ def run_reference(args, rank, world):
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step": nframes, "seed": SEED},
         "cpu_baseline": {"value": round(value, 3), "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "%d threads x first %d frames of a GOP (IDR+P), oracle/h264_oracle.c; libx264/ffmpeg absent from image" % (threads, fpg)},
+                         "sample": "%d threads x first %d frames of a GOP (IDR+P), oracle/%s; libx264/libx265/ffmpeg absent from image" % (threads, fpg, "hevc_oracle.inc.c" if CODEC else "h264_oracle.c")},
         "e2e": {"value": round(value, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -191,12 +207,13 @@ def main():
     ap.add_argument("--gops", type=int, default=32, help="closed GOPs per GPU per step (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="1080p", choices=["1080p", "4k"], help="default: BASELINE.json configs[1]")
+    ap.add_argument("--codec", default="h264", choices=["h264", "hevc"], help="hevc: BASELINE.json configs[3] (use with --workload 4k)")
     ap.add_argument("--entropy", type=int, default=-1, help="0 CAVLC, 1 CABAC (default: what the workload names)")
     ap.add_argument("--slices", type=int, default=-1, help="slices per picture (default: the encoder's choice)")
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads (sessions) of the end-to-end pipeline, like consumer -j")
     ap.add_argument("--deblock-idc", type=int, default=0, help="experiments only: 1 switches the in-loop filter off")
     args = ap.parse_args()
-    select_workload(args.workload, args.entropy, args.slices)
+    select_workload(args.workload, args.entropy, args.slices, args.codec)
     if args.workload == "4k" and args.gops == 32:
         args.gops = 16                     # 960 frames of 4K = 12 GB of raw input per GPU
 
@@ -221,7 +238,7 @@ def main():
     n = frames.shape[0]
     fb = frames.shape[1]
     p = api.default_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, slices=SLICES, deblock_idc=args.deblock_idc,
-                           first_gop=rank * args.gops, entropy=ENTROPY, transform8x8=T8X8)
+                           first_gop=rank * args.gops, entropy=ENTROPY, transform8x8=T8X8, codec=CODEC)
     host = torch.from_numpy(frames).pin_memory()
     dev = host.to("cuda", non_blocking=False)
     out_host = torch.empty(n * fb // 2 + (1 << 20), dtype=torch.uint8).pin_memory()
@@ -360,7 +377,7 @@ def main():
             cores = max(1, min(os.cpu_count() or 1, 32))
             fps, dt = cpu_port_fps(frames, cores, GOP)
             line["cpu_baseline"] = {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
-                                    "sample": "%d threads x one whole GOP (IDR+59P) of the same clip each, %.1f s; oracle/h264_oracle.c (libx264/ffmpeg absent from image)" % (cores, dt)}
+                                    "sample": "%d threads x one whole GOP (IDR+59P) of the same clip each, %.1f s; oracle/%s (libx264/libx265/ffmpeg absent from image)" % (cores, dt, "hevc_oracle.inc.c" if CODEC else "h264_oracle.c")}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)

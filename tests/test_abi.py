@@ -125,6 +125,40 @@ def test_mux_and_verify_host_only(built, tmp_path):
         assert out.returncode == 0 and b"video" in out.stdout   # cmd/consumer.go:409-418
 
 
+def test_hevc_mux_and_parameter_sets_host_only(built, tmp_path):
+    """HEVC host pieces without a GPU: the library's VPS/SPS/PPS are the oracle's (the stream the FFmpeg hevc
+    decoder accepts), and an oracle stream wrapped as hvc1 + hvcC demuxes / decodes to the oracle's recon."""
+    w, h, n = 328, 184, 7                                   # cropped coded size: conformance window in the SPS
+    clip = synth.make_clip(w, h, n, seed=22)
+    r = pyoracle.encode_hevc(pyoracle.make_params(w, h, codec=1, gop=3, qp_i=24, qp_p=26, slices=2), clip)
+    p = api.default_params(w, h, codec=1, gop=3, faststart=1)
+    path = str(tmp_path / "o.mp4")
+    api.mux_mp4(p, np.frombuffer(r["stream"], np.uint8), r["info"], path)
+    api.verify(path)
+    data = open(path, "rb").read()
+    assert b"hvc1" in data and b"hvcC" in data and b"avcC" not in data
+    raw = str(tmp_path / "o.h265")
+    open(raw, "wb").write(r["stream"])
+    api.verify(raw)
+    if arbiter.available():
+        assert arbiter.probe_has_video(path)
+        dec = arbiter.decode_file(path)
+        assert len(dec) == n
+        for i in range(n):
+            assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i])
+    # a stream with its parameter sets stripped: the muxer regenerates them (headers.cpp) -- same file
+    off, size = r["info"][0][0], r["info"][0][1]
+    au0 = r["stream"][off:off + size]
+    first_slice = au0.find(b"\x00\x00\x00\x01\x26")           # IDR_W_RADL
+    assert first_slice > 0
+    stripped = au0[first_slice:] + r["stream"][off + size:]
+    info = [(0, size - first_slice, 1, r["info"][0][3])] + [(o - first_slice, s_, i_, q) for (o, s_, i_, q) in r["info"][1:]]
+    # later IDR access units still carry their own parameter sets; the first one relies on headers.cpp
+    path2 = str(tmp_path / "o2.mp4")
+    api.mux_mp4(p, np.frombuffer(stripped, np.uint8), info, path2)
+    assert open(path2, "rb").read() == data
+
+
 def test_verify_rejects_bad_files(built, tmp_path):
     empty = tmp_path / "e.mp4"
     empty.write_bytes(b"")
