@@ -9,8 +9,8 @@
 // filter), AMVP / merge (one candidate) / skip decided after all vectors exist (hevc_cuinfo_kernel), in-loop
 // filters disabled.  Entropy coding: k5_cabac.cu (hevc_bins_kernel + the shared arithmetic coder).
 //
-//   hevc_p_recon_kernel : warp = CU; lanes 0-15 = four lanes per 8x8 luma transform block (rows, then columns
-//                         through shared memory), lanes 16-23 = one 4x4 chroma block each
+//   hevc_p_recon_kernel : warp = CU; eight lanes per 8x8 luma transform block (a row, a column, a row each, through
+//                         shared memory), then four lanes per 4x4 chroma block the same way
 //   hevc_i_recon_kernel : CTA = (GOP, slice), wavefront over anti-diagonals, warp = CU, the four transform
 //                         units of a CU in z-order (each predicts from the reconstruction of the previous ones)
 //   hevc_cuinfo_kernel  : thread = CU: merge candidate, AMVP list, vector difference, skip
@@ -71,70 +71,115 @@ __device__ __forceinline__ int hv_dequant1(int l, int ls, int sh, int bdshift) {
     return vcp_clip3(-32768, 32767, (int)((v + (1 << (bdshift - 1))) >> bdshift));
 }
 
-// Luma 8x8 transform blocks, four lanes per block (k = block slot, q = lane in the block).  S.pred holds the
-// prediction of the block at (bx,by) on entry and its reconstruction on exit; levels go to S.lv[k*64..].
-// Every lane of the warp calls this (shared-memory passes are separated by warp barriers); `act` masks.
+// Luma 8x8 transform blocks, eight lanes per block (k = block slot, q = lane in the block: one row, then one
+// column, then one row).  S.pred holds the prediction of the block at (bx,by) on entry and its reconstruction on
+// exit; levels go to S.lv[k*64..].  Every lane of the warp calls this (the shared-memory passes are separated by
+// warp barriers); `act` masks.  Returns the number of non-zero levels of the block (valid in its eight lanes).
 __device__ __forceinline__ int hv_luma_tu(HvScratch& S, bool act, int k, int q, int bx, int by, const uint8_t* __restrict__ src,
                                           int stride, int qp, bool intra) {
     int* T = S.t[k];
-    if (act) {   // rows: residual, horizontal transform, stage shift log2(8) + 8 - 9 = 2
+    if (act) {   // row q: residual, horizontal transform, stage shift log2(8) + 8 - 9 = 2
+        const uint2 s8 = *reinterpret_cast<const uint2*>(src + (size_t)q * stride);
+        const uint2 p8 = *reinterpret_cast<const uint2*>(&S.pred[by + q][bx]);
+        int d[8], y[8];
 #pragma unroll
-        for (int rr = 0; rr < 2; rr++) {
-            const int r = 2 * q + rr;
-            const uint2 s8 = *reinterpret_cast<const uint2*>(src + (size_t)r * stride);
-            const uint2 p8 = *reinterpret_cast<const uint2*>(&S.pred[by + r][bx]);
-            int d[8], y[8];
-#pragma unroll
-            for (int x = 0; x < 8; x++) {
-                const uint32_t sw = x < 4 ? s8.x : s8.y, pw = x < 4 ? p8.x : p8.y;
-                d[x] = (int)((sw >> (8 * (x & 3))) & 255) - (int)((pw >> (8 * (x & 3))) & 255);
-            }
-            hv_fwd8(d, y);
-#pragma unroll
-            for (int x = 0; x < 8; x++) T[8 * r + x] = (y[x] + 2) >> 2;
+        for (int x = 0; x < 8; x++) {
+            const uint32_t sw = x < 4 ? s8.x : s8.y, pw = x < 4 ? p8.x : p8.y;
+            d[x] = (int)((sw >> (8 * (x & 3))) & 255) - (int)((pw >> (8 * (x & 3))) & 255);
         }
+        hv_fwd8(d, y);
+#pragma unroll
+        for (int x = 0; x < 8; x++) T[8 * q + ((x + q) & 7)] = (y[x] + 2) >> 2;     // rotated within the row: conflict-free column reads
     }
     __syncwarp();
     int nz = 0;
-    if (act) {   // columns: vertical transform (shift 9), quantise, dequantise, vertical inverse (columns first, 8.6.4.2)
+    if (act) {   // column q: vertical transform (shift 9), quantise, dequantise, vertical inverse (columns first, 8.6.4.2)
         const int qbits = 14 + qp / 6 + 4, qs = hevc_quant_scale[qp % 6], ls = hevc_level_scale[qp % 6], sh = qp / 6;
         const long long offs = (long long)(intra ? 171 : 85) << (qbits - 9);
+        int in[8], w[8], c[8], g[8];
 #pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-            const int col = 2 * q + cc;
-            int in[8], w[8], c[8], g[8];
+        for (int r = 0; r < 8; r++) in[r] = T[8 * r + ((q + r) & 7)];
+        hv_fwd8(in, w);
 #pragma unroll
-            for (int r = 0; r < 8; r++) in[r] = T[8 * r + col];
-            hv_fwd8(in, w);
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const int l = hv_quant1((w[r] + 256) >> 9, qs, offs, qbits);
-                S.lv[k * 64 + 8 * r + col] = (int16_t)l;
-                nz += l != 0;
-                c[r] = hv_dequant1(l, ls, sh, 6);
-            }
-            hv_inv8(c, g);
-#pragma unroll
-            for (int r = 0; r < 8; r++) T[8 * r + col] = vcp_clip3(-32768, 32767, (g[r] + 64) >> 7);
+        for (int r = 0; r < 8; r++) {
+            const int l = hv_quant1((w[r] + 256) >> 9, qs, offs, qbits);
+            S.lv[k * 64 + 8 * r + q] = (int16_t)l;
+            nz += l != 0;
+            c[r] = hv_dequant1(l, ls, sh, 6);
         }
+        hv_inv8(c, g);
+#pragma unroll
+        for (int r = 0; r < 8; r++) T[8 * r + ((q + r) & 7)] = vcp_clip3(-32768, 32767, (g[r] + 64) >> 7);
+    }
+    nz += __shfl_xor_sync(0xffffffffu, nz, 1);
+    nz += __shfl_xor_sync(0xffffffffu, nz, 2);
+    nz += __shfl_xor_sync(0xffffffffu, nz, 4);
+    __syncwarp();
+    if (act && nz) {   // row q: horizontal inverse (shift 12), reconstruct in place of the prediction
+        int in[8], o[8];
+#pragma unroll
+        for (int x = 0; x < 8; x++) in[x] = T[8 * q + ((x + q) & 7)];
+        hv_inv8(in, o);
+        const uint2 p8 = *reinterpret_cast<const uint2*>(&S.pred[by + q][bx]);
+        uint2 r8 = make_uint2(0, 0);
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+            const uint32_t pw = x < 4 ? p8.x : p8.y;
+            const uint32_t v = (uint32_t)vcp_clip255((int)((pw >> (8 * (x & 3))) & 255) + ((o[x] + 2048) >> 12)) << (8 * (x & 3));
+            if (x < 4) r8.x |= v; else r8.y |= v;
+        }
+        *reinterpret_cast<uint2*>(&S.pred[by + q][bx]) = r8;
+    }
+    __syncwarp();
+    return nz;
+}
+
+// Eight 4x4 chroma transform blocks of a coding unit at once, four lanes per block (blk = lane >> 2 = plane * 4 + z,
+// r = lane & 3: one row, one column, one row), staged through S.t viewed as 8 x 16 ints.  Returns the number of
+// non-zero levels of the lane's block; levels go to S.lv[256 + blk * 16 ..], the reconstruction to `dst`.
+__device__ __forceinline__ int hv_chroma_cu(HvScratch& S, int lane, const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int stride,
+                                            uint32_t pred, int qpc, bool intra) {
+    const int blk = lane >> 2, r = lane & 3;
+    int* T = &S.t[0][0] + blk * 20;     // 16 + padding
+    {
+        const uint32_t s4 = ld_u32(src);
+        int d[4], o[4];
+#pragma unroll
+        for (int x = 0; x < 4; x++) d[x] = (int)((s4 >> (8 * x)) & 255) - (int)((pred >> (8 * x)) & 255);
+        hv_fwd4(d, o);
+#pragma unroll
+        for (int x = 0; x < 4; x++) T[4 * r + x] = (o[x] + 1) >> 1;        // stage shift log2(4) + 8 - 9 = 1
+    }
+    __syncwarp();
+    int nz = 0;
+    {
+        const int qbits = 14 + qpc / 6 + 5, qs = hevc_quant_scale[qpc % 6], ls = hevc_level_scale[qpc % 6], sh = qpc / 6;
+        const long long offs = (long long)(intra ? 171 : 85) << (qbits - 9);
+        int in[4] = {T[r], T[4 + r], T[8 + r], T[12 + r]}, w[4], c[4], g[4];
+        hv_fwd4(in, w);
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            const int l = hv_quant1((w[y] + 128) >> 8, qs, offs, qbits);
+            S.lv[256 + blk * 16 + 4 * y + r] = (int16_t)l;
+            nz += l != 0;
+            c[y] = hv_dequant1(l, ls, sh, 5);
+        }
+        hv_inv4(c, g);
+#pragma unroll
+        for (int y = 0; y < 4; y++) T[4 * y + r] = vcp_clip3(-32768, 32767, (g[y] + 64) >> 7);
     }
     nz += __shfl_xor_sync(0xffffffffu, nz, 1);
     nz += __shfl_xor_sync(0xffffffffu, nz, 2);
     __syncwarp();
-    if (act) {   // rows: horizontal inverse (shift 12), reconstruct in place of the prediction
+    uint32_t outw = pred;
+    if (nz) {
+        int in[4] = {T[4 * r], T[4 * r + 1], T[4 * r + 2], T[4 * r + 3]}, o[4];
+        hv_inv4(in, o);
+        outw = 0;
 #pragma unroll
-        for (int rr = 0; rr < 2; rr++) {
-            const int r = 2 * q + rr;
-            int in[8], o[8];
-#pragma unroll
-            for (int x = 0; x < 8; x++) in[x] = T[8 * r + x];
-            hv_inv8(in, o);
-            if (nz) {
-#pragma unroll
-                for (int x = 0; x < 8; x++) S.pred[by + r][bx + x] = (uint8_t)vcp_clip255((int)S.pred[by + r][bx + x] + ((o[x] + 2048) >> 12));
-            }
-        }
+        for (int x = 0; x < 4; x++) outw |= (uint32_t)vcp_clip255((int)((pred >> (8 * x)) & 255) + ((o[x] + 2048) >> 12)) << (8 * x);
     }
+    *reinterpret_cast<uint32_t*>(dst) = outw;
     __syncwarp();
     return nz;
 }
@@ -241,25 +286,21 @@ __global__ void __launch_bounds__(HP_WARPS * 32) hevc_p_recon_kernel(VcpGeom g, 
         *reinterpret_cast<uint32_t*>(&S.cpred[pl][row][x0]) = outw;
     }
     __syncwarp();
-    // luma: four lanes per 8x8 block
-    const int k = (lane >> 2) & 3, q = lane & 3, bx = (k & 1) * 8, by = (k >> 1) * 8;
+    // luma: eight lanes per 8x8 block
+    const int k = lane >> 3, q = lane & 7, bx = (k & 1) * 8, by = (k >> 1) * 8;
     const uint8_t* srcy = b.src_y + (size_t)n * g.ysize + g.yoff + (size_t)(16 * my + by) * g.ys + 16 * mx + bx;
-    const int nzy = hv_luma_tu(S, lane < 16, k, q, bx, by, srcy, g.ys, qp, false);
-    const uint32_t ymask = __ballot_sync(0xffffffffu, lane < 16 && nzy > 0);
-    // chroma: lanes 16..23, one 4x4 block each (plane, z)
-    int nzc = 0;
-    if (lane >= 16 && lane < 24) {
-        const int pl = (lane - 16) >> 2, z = lane & 3, cx = (z & 1) * 4, cy = (z >> 1) * 4;
+    const int nzy = hv_luma_tu(S, true, k, q, bx, by, srcy, g.ys, qp, false);
+    const uint32_t ymask = __ballot_sync(0xffffffffu, nzy > 0);
+    // chroma: four lanes per 4x4 block, lane = (plane * 4 + z) * 4 + row
+    int nzc;
+    {
+        const int pl = lane >> 4, z = (lane >> 2) & 3, r = lane & 3, cx = (z & 1) * 4, cy = (z >> 1) * 4 + r;
         const size_t co = g.coff + (size_t)(8 * my + cy) * g.cs + 8 * mx + cx;
         const uint8_t* sc = (pl ? b.src_v : b.src_u) + (size_t)n * g.csize + co;
         uint8_t* dc = (pl ? b.rec_v : b.rec_u) + (size_t)slot * g.csize + co;
-        uint32_t pw[4];
-#pragma unroll
-        for (int y = 0; y < 4; y++) pw[y] = *reinterpret_cast<const uint32_t*>(&S.cpred[pl][cy + y][cx]);
-        nzc = hv_chroma_tu(sc, dc, g.cs, pw, qpc, false, &S.lv[256 + pl * 64 + z * 16]);
+        nzc = hv_chroma_cu(S, lane, sc, dc, g.cs, *reinterpret_cast<const uint32_t*>(&S.cpred[pl][cy][cx]), qpc, false);
     }
     const uint32_t cmask = __ballot_sync(0xffffffffu, nzc > 0);
-    __syncwarp();
     // reconstruction and levels out
     if (lane < 16) {
         const int bx4 = (lane & 3) * 4, by4 = (lane >> 2) * 4;
@@ -269,11 +310,13 @@ __global__ void __launch_bounds__(HP_WARPS * 32) hevc_p_recon_kernel(VcpGeom g, 
     }
     for (int i = lane; i < 48; i += 32) reinterpret_cast<uint4*>(b.levels + o * VCP_LV_STRIDE)[i] = reinterpret_cast<const uint4*>(S.lv)[i];
     if (lane == 0) {
-        uint32_t cbf_y = 0;
+        uint32_t cbf_y = 0, cbf_c = 0;
 #pragma unroll
-        for (int z = 0; z < 4; z++) cbf_y |= ((ymask >> (4 * z)) & 15u) ? 1u << z : 0u;
+        for (int z = 0; z < 4; z++) cbf_y |= ((ymask >> (8 * z)) & 1u) << z;
+#pragma unroll
+        for (int z = 0; z < 8; z++) cbf_c |= ((cmask >> (4 * z)) & 1u) << z;
         b.cbp[o] = (uint8_t)cbf_y;
-        b.modes[o] = (uint8_t)((cmask >> 16) & 0xff);      // cbf_cb in bits 0-3, cbf_cr in bits 4-7
+        b.modes[o] = (uint8_t)cbf_c;                       // cbf_cb in bits 0-3, cbf_cr in bits 4-7
         b.mbtype[o] = 1;
     }
 }
@@ -311,7 +354,7 @@ __device__ void hv_encode_intra_cu(const VcpGeom& g, const VcpBufs& b, HvScratch
     for (int z = 0; z < 4; z++) {
         const int bx = (z & 1) * 8, by = (z >> 1) * 8;
         const bool aL = bx > 0 || mx > 0, aT = by > 0 || my > row0;
-        // luma prediction by lane 0 into the tile, chroma by lanes 4, 5 into registers
+        // luma prediction by lane 0 into the tile, chroma by lanes 8, 9 into registers
         if (lane == 0) {
             uint8_t tmp[64];
             hv_dc_pred(ry + (size_t)by * g.ys + bx, g.ys, aL, aT, 8, true, tmp);
@@ -319,7 +362,7 @@ __device__ void hv_encode_intra_cu(const VcpGeom& g, const VcpBufs& b, HvScratch
         }
         __syncwarp();
         const uint8_t* srcy = b.src_y + (size_t)n * g.ysize + g.yoff + (size_t)(16 * my + by) * g.ys + 16 * mx + bx;
-        const int nzy = hv_luma_tu(S, lane < 4, z, lane & 3, bx, by, srcy, g.ys, qp, true);
+        const int nzy = hv_luma_tu(S, lane < 8, z, lane & 7, bx, by, srcy, g.ys, qp, true);
         if (__shfl_sync(0xffffffffu, nzy, 0) > 0) cbf_y |= 1u << z;
         // this TU's luma reconstruction must be in memory before the next TU predicts from it
         if (lane < 16) {
@@ -327,8 +370,8 @@ __device__ void hv_encode_intra_cu(const VcpGeom& g, const VcpBufs& b, HvScratch
             *reinterpret_cast<uint32_t*>(ry + (size_t)(by + r) * g.ys + bx + hx) = *reinterpret_cast<const uint32_t*>(&S.pred[by + r][bx + hx]);
         }
         int nzc = 0;
-        if (lane == 4 || lane == 5) {
-            const int pl = lane - 4, cx = (z & 1) * 4, cy = (z >> 1) * 4;
+        if (lane == 8 || lane == 9) {
+            const int pl = lane - 8, cx = (z & 1) * 4, cy = (z >> 1) * 4;
             const size_t co = g.coff + (size_t)(8 * my + cy) * g.cs + 8 * mx + cx;
             const uint8_t* sc = (pl ? b.src_v : b.src_u) + (size_t)n * g.csize + co;
             uint8_t* dc = (pl ? b.rec_v : b.rec_u) + (size_t)slot * g.csize + co;
@@ -339,8 +382,8 @@ __device__ void hv_encode_intra_cu(const VcpGeom& g, const VcpBufs& b, HvScratch
             nzc = hv_chroma_tu(sc, dc, g.cs, pw, qpc, true, &S.lv[256 + pl * 64 + z * 16]);
         }
         const uint32_t cm = __ballot_sync(0xffffffffu, nzc > 0);
-        if (cm & 0x10u) cbf_c |= 1u << z;
-        if (cm & 0x20u) cbf_c |= 16u << z;
+        if (cm & 0x100u) cbf_c |= 1u << z;
+        if (cm & 0x200u) cbf_c |= 16u << z;
         __syncwarp();
     }
     for (int i = lane; i < 48; i += 32) reinterpret_cast<uint4*>(b.levels + o * VCP_LV_STRIDE)[i] = reinterpret_cast<const uint4*>(S.lv)[i];
