@@ -41,8 +41,9 @@ extern "C" {
 #define VCPENC_E_VERIFY 10     /* verify: no valid video stream ("无有效视频流")     */
 #define VCPENC_E_OVERFLOW 11   /* output buffer too small                          */
 #define VCPENC_E_INTERNAL 12
-#define VCPENC_E_UNSUPPORTED 13 /* a video encode this library does not implement yet (HEVC presets):
-                                  like NOTENCODE the caller may hand the task to a stock ffmpeg   */
+#define VCPENC_E_UNSUPPORTED 13 /* a video encode this library does not implement (reserved; the HEVC
+                                  presets run since k6_hevc.cu): like NOTENCODE the caller may hand the
+                                  task to a stock ffmpeg                                           */
 
 /* codecs */
 #define VCPENC_CODEC_H264 0

@@ -15,7 +15,8 @@
  *   - inter: one 16x16 PU, full-sample luma vectors (chroma lands on half samples: 4-tap filter),
  *     AMVP with spatial candidates, merge (1 candidate) / skip
  *   - CABAC (same engine as H.264 9.3.4.2; HEVC context tables 9-5..9-37), no sign hiding
- *   - in-loop filters (deblocking, SAO) disabled in the PPS / SPS, constant QP
+ *   - in-loop deblocking (all vertical edges, then all horizontal ones; not across slices) unless deblock_idc = 1;
+ *     SAO disabled in the SPS; constant QP or the bitrate model of the H.264 path
  */
 
 #include "../video_codec_pipeline_b200/csrc/hevc_tables.h"
@@ -421,6 +422,85 @@ static void hevc_amvp(const HEnc* h, int cx, int cy, int list[2][2]) {
     while (n < 2) { list[n][0] = list[n][1] = 0; n++; }
 }
 
+/* ---- in-loop deblocking (8.7.2) ------------------------------------------------------------------
+ * Edges lie on the 8x8 luma grid.  All vertical edges of the picture are filtered first, then all horizontal
+ * edges on the result; edges of one direction never overlap (a filter reads 4 and changes at most 3 samples
+ * on each side), so both passes are order-free -- the reason the GPU path needs no wavefront here.
+ * pps_loop_filter_across_slices_enabled_flag = 0: the top edge of a slice is not filtered. */
+static int hevc_bs(const HEnc* h, int xq, int yq, int vertical) {
+    const Enc* e = h->e;
+    const int xp = vertical ? xq - 1 : xq, yp = vertical ? yq : yq - 1;
+    if (xp < 0 || yp < 0) return 0;
+    const HCU* cq = &h->cus[(yq >> 4) * e->mbw + (xq >> 4)];
+    const HCU* cp = &h->cus[(yp >> 4) * e->mbw + (xp >> 4)];
+    if (!vertical && (yq & 15) == 0 && slice_first_row(e, slice_of_row(e, yq >> 4)) == (yq >> 4)) return 0;
+    if (cp->type == HCU_INTRA || cq->type == HCU_INTRA) return 2;
+    const int zq = ((yq >> 3) & 1) * 2 + ((xq >> 3) & 1), zp = ((yp >> 3) & 1) * 2 + ((xp >> 3) & 1);
+    if ((cq->type != HCU_SKIP && cq->cbf_y[zq]) || (cp->type != HCU_SKIP && cp->cbf_y[zp])) return 1;
+    if (cp == cq) return 0;
+    return abs(cp->mv[0] - cq->mv[0]) >= 4 || abs(cp->mv[1] - cq->mv[1]) >= 4;
+}
+/* one 4-line segment of a luma edge; p points at q0 of line 0, `step` walks across the edge, `line` along it */
+static void hevc_filter_luma(uint8_t* q0, ptrdiff_t step, ptrdiff_t line, int beta, int tc) {
+#define P(i, l) ((int)q0[-(ptrdiff_t)((i) + 1) * step + (ptrdiff_t)(l) * line])
+#define Q(i, l) ((int)q0[(ptrdiff_t)(i) * step + (ptrdiff_t)(l) * line])
+    const int dp0 = abs(P(2, 0) - 2 * P(1, 0) + P(0, 0)), dp3 = abs(P(2, 3) - 2 * P(1, 3) + P(0, 3));
+    const int dq0 = abs(Q(2, 0) - 2 * Q(1, 0) + Q(0, 0)), dq3 = abs(Q(2, 3) - 2 * Q(1, 3) + Q(0, 3));
+    const int dpq0 = dp0 + dq0, dpq3 = dp3 + dq3, dp = dp0 + dp3, dq = dq0 + dq3;
+    if (dpq0 + dpq3 >= beta) return;
+    const int s0 = 2 * dpq0 < (beta >> 2) && abs(P(3, 0) - P(0, 0)) + abs(Q(0, 0) - Q(3, 0)) < (beta >> 3) && abs(P(0, 0) - Q(0, 0)) < ((5 * tc + 1) >> 1);
+    const int s3 = 2 * dpq3 < (beta >> 2) && abs(P(3, 3) - P(0, 3)) + abs(Q(0, 3) - Q(3, 3)) < (beta >> 3) && abs(P(0, 3) - Q(0, 3)) < ((5 * tc + 1) >> 1);
+    const int side = (beta + (beta >> 1)) >> 3, dep = dp < side, deq = dq < side;
+    for (int l = 0; l < 4; l++) {
+        const int p0 = P(0, l), p1 = P(1, l), p2 = P(2, l), p3 = P(3, l), a0 = Q(0, l), a1 = Q(1, l), a2 = Q(2, l), a3 = Q(3, l);
+        uint8_t* c = q0 + (ptrdiff_t)l * line;
+        if (s0 && s3) {
+            c[-1 * step] = (uint8_t)vcp_clip3(p0 - 2 * tc, p0 + 2 * tc, (p2 + 2 * p1 + 2 * p0 + 2 * a0 + a1 + 4) >> 3);
+            c[-2 * step] = (uint8_t)vcp_clip3(p1 - 2 * tc, p1 + 2 * tc, (p2 + p1 + p0 + a0 + 2) >> 2);
+            c[-3 * step] = (uint8_t)vcp_clip3(p2 - 2 * tc, p2 + 2 * tc, (2 * p3 + 3 * p2 + p1 + p0 + a0 + 4) >> 3);
+            c[0] = (uint8_t)vcp_clip3(a0 - 2 * tc, a0 + 2 * tc, (p1 + 2 * p0 + 2 * a0 + 2 * a1 + a2 + 4) >> 3);
+            c[step] = (uint8_t)vcp_clip3(a1 - 2 * tc, a1 + 2 * tc, (p0 + a0 + a1 + a2 + 2) >> 2);
+            c[2 * step] = (uint8_t)vcp_clip3(a2 - 2 * tc, a2 + 2 * tc, (p0 + a0 + a1 + 3 * a2 + 2 * a3 + 4) >> 3);
+        } else {
+            int d = (9 * (a0 - p0) - 3 * (a1 - p1) + 8) >> 4;
+            if (abs(d) >= tc * 10) continue;
+            d = vcp_clip3(-tc, tc, d);
+            c[-1 * step] = (uint8_t)vcp_clip255(p0 + d);
+            c[0] = (uint8_t)vcp_clip255(a0 - d);
+            if (dep) c[-2 * step] = (uint8_t)vcp_clip255(p1 + vcp_clip3(-(tc >> 1), tc >> 1, (((p2 + p0 + 1) >> 1) - p1 + d) >> 1));
+            if (deq) c[step] = (uint8_t)vcp_clip255(a1 + vcp_clip3(-(tc >> 1), tc >> 1, (((a2 + a0 + 1) >> 1) - a1 - d) >> 1));
+        }
+    }
+#undef P
+#undef Q
+}
+static void hevc_filter_chroma(uint8_t* q0, ptrdiff_t step, ptrdiff_t line, int tc) {
+    for (int l = 0; l < 2; l++) {      /* 4 luma lines = 2 chroma lines */
+        uint8_t* c = q0 + (ptrdiff_t)l * line;
+        const int p0 = c[-step], p1 = c[-2 * step], a0 = c[0], a1 = c[step];
+        const int d = vcp_clip3(-tc, tc, (((a0 - p0) << 2) + p1 - a1 + 4) >> 3);
+        c[-step] = (uint8_t)vcp_clip255(p0 + d);
+        c[0] = (uint8_t)vcp_clip255(a0 - d);
+    }
+}
+static void hevc_deblock_picture(HEnc* h) {
+    const Enc* e = h->e;
+    Frame* f = h->rec;
+    for (int vertical = 1; vertical >= 0; vertical--)
+        for (int y = 0; y < e->ch; y += vertical ? 4 : 8)
+            for (int x = 0; x < e->cw; x += vertical ? 8 : 4) {
+                const int bs = hevc_bs(h, x, y, vertical);
+                if (!bs) continue;
+                const int beta = hevc_beta_tab[vcp_clip3(0, 51, h->qp)], tc = hevc_tc_tab[vcp_clip3(0, 53, h->qp + 2 * (bs - 1))];
+                hevc_filter_luma(f->y + (size_t)y * f->ys + x, vertical ? 1 : f->ys, vertical ? f->ys : 1, beta, tc);
+                if (bs == 2 && ((vertical ? x : y) & 15) == 0) {
+                    const int tcc = hevc_tc_tab[vcp_clip3(0, 53, h->qpc + 2)];
+                    hevc_filter_chroma(f->u + (size_t)(y >> 1) * f->cs + (x >> 1), vertical ? 1 : f->cs, vertical ? f->cs : 1, tcc);
+                    hevc_filter_chroma(f->v + (size_t)(y >> 1) * f->cs + (x >> 1), vertical ? 1 : f->cs, vertical ? f->cs : 1, tcc);
+                }
+            }
+}
+
 /* ---- syntax ------------------------------------------------------------------------------------- */
 static void hevc_write_tu_tree(Cabac* c, const HCU* cu, int intra) {
     int any_cb = 0, any_cr = 0;
@@ -573,7 +653,7 @@ static size_t hevc_write_sps(const Enc* e, uint8_t* out, size_t cap) {
     bw_trailing(&b);
     return hevc_nal_write(out, cap, 33, tmp, b.pos);
 }
-static size_t hevc_write_pps(uint8_t* out, size_t cap) {
+static size_t hevc_write_pps(const Enc* e, uint8_t* out, size_t cap) {
     uint8_t tmp[64]; BW b; bw_init(&b, tmp, sizeof tmp);
     bw_ue(&b, 0); bw_ue(&b, 0);
     bw_put(&b, 1, 0); bw_put(&b, 1, 0); bw_put(&b, 3, 0);       /* dependent slices, output flag, extra header bits */
@@ -585,7 +665,8 @@ static size_t hevc_write_pps(uint8_t* out, size_t cap) {
     bw_put(&b, 1, 0); bw_put(&b, 1, 0); bw_put(&b, 1, 0); bw_put(&b, 1, 0);   /* slice chroma offsets, weighted pred x2, transquant bypass */
     bw_put(&b, 1, 0); bw_put(&b, 1, 0);                         /* tiles, entropy_coding_sync */
     bw_put(&b, 1, 0);                                           /* pps_loop_filter_across_slices_enabled_flag */
-    bw_put(&b, 1, 1); bw_put(&b, 1, 0); bw_put(&b, 1, 1);       /* deblocking control present, no override, DISABLED */
+    if (e->p.deblock_idc == 1) { bw_put(&b, 1, 1); bw_put(&b, 1, 0); bw_put(&b, 1, 1); }   /* deblocking control present, no override, DISABLED */
+    else bw_put(&b, 1, 0);                                      /* no deblocking control: enabled, beta / tc offsets 0 */
     bw_put(&b, 1, 0); bw_put(&b, 1, 0);                         /* scaling list data, lists modification */
     bw_ue(&b, 0);                                               /* log2_parallel_merge_level_minus2 */
     bw_put(&b, 1, 0); bw_put(&b, 1, 0);                         /* slice header extension, pps extension */
@@ -690,7 +771,7 @@ int hevc_orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, 
         if (idr) {
             size_t k = hevc_write_vps(e, out + o, out_cap - o); if (!k) { rc = VCPENC_E_OVERFLOW; goto done; } o += k;
             k = hevc_write_sps(e, out + o, out_cap - o); if (!k) { rc = VCPENC_E_OVERFLOW; goto done; } o += k;
-            k = hevc_write_pps(out + o, out_cap - o); if (!k) { rc = VCPENC_E_OVERFLOW; goto done; } o += k;
+            k = hevc_write_pps(e, out + o, out_cap - o); if (!k) { rc = VCPENC_E_OVERFLOW; goto done; } o += k;
         }
         unsigned long long frame_bits = 0;
         for (int s = 0; s < p->slices; s++) {
@@ -711,6 +792,7 @@ int hevc_orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, 
             rc_qp_next[1] = vcp_rc_next_qp(rc_qp0, qp, rc_qp_next[0], idr, frame_bits, rc_cum, t, gop_len, budget);
         }
         if (info) { info[n].offset = au0; info[n].size = (uint32_t)(o - au0); info[n].is_idr = (uint8_t)idr; info[n].qp = (uint8_t)qp; }
+        if (p->deblock_idc != 1) hevc_deblock_picture(&h);
         frame_pad(h.rec);
         if (recon) store_recon(e, h.rec, recon + (size_t)n * fsz);
         ri ^= 1;

@@ -54,10 +54,10 @@ def test_hevc_cuda_equals_oracle(built, case):
     pre-pass vectors, reconstruction and Annex-B bytes identical; the oracle itself is pinned by the FFmpeg hevc
     decoder (tests/test_oracle.py)."""
     from oracle import pyoracle
-    w, h, n, gop, sl, _idc, qp = case
+    w, h, n, gop, sl, idc, qp = case                       # idc 1: in-loop deblocking off
     clip = synth.make_clip(w, h, n, seed=1000 + w + qp)
-    ref = pyoracle.encode_hevc(pyoracle.make_params(w, h, codec=1, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl), clip)
-    p = api.default_params(w, h, codec=1, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, debug=1)
+    ref = pyoracle.encode_hevc(pyoracle.make_params(w, h, codec=1, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc), clip)
+    p = api.default_params(w, h, codec=1, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, debug=1, deblock_idc=idc)
     with api.Session(p, n) as s:
         s.upload(clip)
         s.encode()

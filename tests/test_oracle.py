@@ -315,9 +315,9 @@ def test_k1_scale():
 def test_hevc_oracle_stream_decodes_to_its_own_recon(case):
     if not arbiter.available():
         pytest.skip("bundled FFmpeg decoder not present")
-    w, h, n, gop, sl, _idc, qp = case
+    w, h, n, gop, sl, idc, qp = case                       # idc 1: in-loop deblocking off
     clip = synth.make_clip(w, h, n, seed=1000 + w + qp)
-    r = pyoracle.encode_hevc(pyoracle.make_params(w, h, codec=1, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl), clip)
+    r = pyoracle.encode_hevc(pyoracle.make_params(w, h, codec=1, gop=gop, qp_i=max(0, qp - 2), qp_p=qp, slices=sl, deblock_idc=idc), clip)
     dec = arbiter.decode_annexb_hevc(r["stream"])
     assert len(dec) == n
     for i in range(n):

@@ -92,7 +92,7 @@ std::vector<uint8_t> make_pps_nal(const vcpenc_params& p) {
 
 // ---- HEVC (H.265 7.3.2.1 - 7.3.2.3, 7.3.3, E.2.1) ------------------------------------------------------
 // Main profile, 16x16 coding tree blocks that are never split, 8x8 / 4x4 transform blocks, one reference
-// picture (short-term RPS {-1}), no temporal vector prediction, in-loop filters off.
+// picture (short-term RPS {-1}), no temporal vector prediction, deblocking unless deblock_idc = 1, no SAO.
 
 int hevc_level_idc_for(int cw, int ch, int fps_num, int fps_den) {
     // table A.8: general_level_idc = 30 x level; MaxLumaPs, MaxLumaSr
@@ -178,7 +178,7 @@ std::vector<uint8_t> make_hevc_sps_nal(const vcpenc_params& p) {
     return hevc_nal_escape(33, b.bytes());
 }
 
-std::vector<uint8_t> make_hevc_pps_nal(const vcpenc_params&) {
+std::vector<uint8_t> make_hevc_pps_nal(const vcpenc_params& p) {
     BitWriter b;
     b.ue(0); b.ue(0);       // pps id, sps id
     b.put(1, 0);            // dependent_slice_segments_enabled_flag
@@ -198,9 +198,11 @@ std::vector<uint8_t> make_hevc_pps_nal(const vcpenc_params&) {
     b.put(1, 0);            // tiles_enabled_flag
     b.put(1, 0);            // entropy_coding_sync_enabled_flag
     b.put(1, 0);            // pps_loop_filter_across_slices_enabled_flag
-    b.put(1, 1);            // deblocking_filter_control_present_flag
-    b.put(1, 0);            // deblocking_filter_override_enabled_flag
-    b.put(1, 1);            // pps_deblocking_filter_disabled_flag
+    if (p.deblock_idc == 1) {
+        b.put(1, 1);        // deblocking_filter_control_present_flag
+        b.put(1, 0);        // deblocking_filter_override_enabled_flag
+        b.put(1, 1);        // pps_deblocking_filter_disabled_flag
+    } else b.put(1, 0);     // no control syntax: deblocking on, beta / tc offsets 0
     b.put(1, 0);            // pps_scaling_list_data_present_flag
     b.put(1, 0);            // lists_modification_present_flag
     b.ue(0);                // log2_parallel_merge_level_minus2

@@ -69,4 +69,12 @@ VCP_TAB uint8_t hevc_diag2_x[4] = {0, 0, 1, 1}, hevc_diag2_y[4] = {0, 1, 0, 1};
 VCP_TAB uint8_t hevc_sig_ctx_map4[16] = {0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8};   /* index (yC << 2) + xC */
 
 
+/* deblocking (8.7.2.5.3, table 8-12): beta' by Q = 0..51, tc' by Q = 0..53 */
+VCP_TAB uint8_t hevc_beta_tab[52] = {
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 22, 24,
+    26, 28, 30, 32, 34, 36, 38, 40, 42, 44, 46, 48, 50, 52, 54, 56, 58, 60, 62, 64};
+VCP_TAB uint8_t hevc_tc_tab[54] = {
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3,
+    3, 3, 3, 4, 4, 4, 5, 5, 6, 6, 7, 8, 9, 10, 11, 13, 14, 16, 18, 20, 22, 24};
+
 #endif  // VCP_HEVC_TABLES_H

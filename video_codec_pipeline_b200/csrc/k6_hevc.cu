@@ -7,13 +7,14 @@
 // order, luma transform blocks 8x8 (the 16x16 root splits because MaxTb = 8), chroma 4x4, DCT only, DC intra
 // prediction per transform block, one 16x16 PU with full-sample luma vectors (chroma on half samples: 4-tap
 // filter), AMVP / merge (one candidate) / skip decided after all vectors exist (hevc_cuinfo_kernel), in-loop
-// filters disabled.  Entropy coding: k5_cabac.cu (hevc_bins_kernel + the shared arithmetic coder).
+// deblocking as two order-free passes (hevc_deblock_kernel), SAO disabled.  Entropy coding: k5_cabac.cu (hevc_bins_kernel + the shared arithmetic coder).
 //
 //   hevc_p_recon_kernel : warp = CU; eight lanes per 8x8 luma transform block (a row, a column, a row each, through
 //                         shared memory), then four lanes per 4x4 chroma block the same way
 //   hevc_i_recon_kernel : CTA = (GOP, slice), wavefront over anti-diagonals, warp = CU, the four transform
 //                         units of a CU in z-order (each predicts from the reconstruction of the previous ones)
 //   hevc_cuinfo_kernel  : thread = CU: merge candidate, AMVP list, vector difference, skip
+//   hevc_deblock_kernel : thread = 4-line segment of an 8x8-grid edge; vertical edges, then horizontal edges
 //
 // Record layout per CU (same arrays as H.264): mbtype 0 intra / 1 inter / 2 skip; cbp bits 0-3 = cbf_luma of
 // the four TUs, bit 4 = merge_flag, bit 5 = mvp_l0_flag; modes bits 0-3 = cbf_cb, 4-7 = cbf_cr; levels:
@@ -463,6 +464,136 @@ __global__ void __launch_bounds__(128) hevc_cuinfo_kernel(VcpGeom g, VcpBufs b, 
     b.mvd[o] = make_short2((short)(mv.x - lx[idx]), (short)(mv.y - ly[idx]));
 }
 
+// ---- in-loop deblocking (8.7.2) ------------------------------------------------------------------------------
+// All vertical edges of the picture, then (second launch) all horizontal edges on the result.  Edges sit on the
+// 8x8 luma grid and a filter reads 4 / changes at most 3 samples on each side, so within one direction every
+// 4-line edge segment is independent: thread = segment, no wavefront (unlike H.264's K4).  The thread holds the
+// 8 x 4 samples around its segment in registers (vertical: two words per row; horizontal: one word per row, the
+// four lines are the bytes), decides (bS, dE, dEp, dEq) and writes the block back.  Chroma (bS = 2 only, i.e. IDR
+// pictures; 16-sample luma grid) rides on the same thread.  Slices are not filtered across
+// (pps_loop_filter_across_slices_enabled_flag = 0).
+template <bool VERTICAL>
+__global__ void __launch_bounds__(256) hevc_deblock_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
+    const int nx = VERTICAL ? g.cw >> 3 : g.cw >> 2, ny = VERTICAL ? g.ch >> 2 : g.ch >> 3;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= nx * ny) return;
+    const int gi = blockIdx.y + s.g0;
+    const int n = vcp_frame_of(s, gi), slot = vcp_rec_slot(s, gi, s.t);
+    const int x = (tid % nx) * (VERTICAL ? 8 : 4), y = (tid / nx) * (VERTICAL ? 4 : 8);
+    const int xp = VERTICAL ? x - 1 : x, yp = VERTICAL ? y : y - 1;
+    if (xp < 0 || yp < 0) return;
+    if (!VERTICAL && (y & 15) == 0 && vcp_row_first(b, y >> 4) == (y >> 4)) return;     // top edge of a slice
+    // boundary strength
+    const size_t base = (size_t)gi * g.nmb;
+    const size_t oq = base + (size_t)(y >> 4) * g.mbw + (x >> 4), op = base + (size_t)(yp >> 4) * g.mbw + (xp >> 4);
+    int bs;
+    if (s.t == 0) bs = 2;                                           // IDR: every CU is intra
+    else {
+        const int zq = ((y >> 3) & 1) * 2 + ((x >> 3) & 1), zp = ((yp >> 3) & 1) * 2 + ((xp >> 3) & 1);
+        if (((b.cbp[oq] >> zq) | (b.cbp[op] >> zp)) & 1) bs = 1;    // a transform block with coefficients on either side
+        else if (op == oq) return;
+        else {
+            const short2 vq = b.mv[oq], vp = b.mv[op];
+            if (vcp_iabs(vp.x - vq.x) < 4 && vcp_iabs(vp.y - vq.y) < 4) return;
+            bs = 1;
+        }
+    }
+    const int qp = b.qp[n];
+    const int beta = hevc_beta_tab[qp], tc = hevc_tc_tab[min(53, qp + 2 * (bs - 1))];
+    uint8_t* Y = vcp_rec_luma(b, g, slot) + g.yoff + (size_t)y * g.ys + x;
+    // P[i][l], Q[i][l]: distance i from the edge, line l along it
+    int P[4][4], Q[4][4];
+    if (VERTICAL) {
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+            const uint32_t wp = ld_u32(Y + (size_t)l * g.ys - 4), wq = ld_u32(Y + (size_t)l * g.ys);
+#pragma unroll
+            for (int i = 0; i < 4; i++) { P[i][l] = (int)((wp >> (8 * (3 - i))) & 255); Q[i][l] = (int)((wq >> (8 * i)) & 255); }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t wp = ld_u32(Y - (ptrdiff_t)(i + 1) * g.ys), wq = ld_u32(Y + (size_t)i * g.ys);
+#pragma unroll
+            for (int l = 0; l < 4; l++) { P[i][l] = (int)((wp >> (8 * l)) & 255); Q[i][l] = (int)((wq >> (8 * l)) & 255); }
+        }
+    }
+    bool changed = false;
+    if (beta) {
+        const int dp0 = vcp_iabs(P[2][0] - 2 * P[1][0] + P[0][0]), dp3 = vcp_iabs(P[2][3] - 2 * P[1][3] + P[0][3]);
+        const int dq0 = vcp_iabs(Q[2][0] - 2 * Q[1][0] + Q[0][0]), dq3 = vcp_iabs(Q[2][3] - 2 * Q[1][3] + Q[0][3]);
+        const int dpq0 = dp0 + dq0, dpq3 = dp3 + dq3;
+        if (dpq0 + dpq3 < beta) {
+            const int tc25 = (5 * tc + 1) >> 1;
+            const bool s0 = 2 * dpq0 < (beta >> 2) && vcp_iabs(P[3][0] - P[0][0]) + vcp_iabs(Q[0][0] - Q[3][0]) < (beta >> 3) && vcp_iabs(P[0][0] - Q[0][0]) < tc25;
+            const bool s3 = 2 * dpq3 < (beta >> 2) && vcp_iabs(P[3][3] - P[0][3]) + vcp_iabs(Q[0][3] - Q[3][3]) < (beta >> 3) && vcp_iabs(P[0][3] - Q[0][3]) < tc25;
+            const int side = (beta + (beta >> 1)) >> 3;
+            const bool dep = dp0 + dp3 < side, deq = dq0 + dq3 < side;
+            changed = true;
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                const int p0 = P[0][l], p1 = P[1][l], p2 = P[2][l], p3 = P[3][l], q0 = Q[0][l], q1 = Q[1][l], q2 = Q[2][l], q3 = Q[3][l];
+                if (s0 && s3) {
+                    P[0][l] = vcp_clip3(p0 - 2 * tc, p0 + 2 * tc, (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+                    P[1][l] = vcp_clip3(p1 - 2 * tc, p1 + 2 * tc, (p2 + p1 + p0 + q0 + 2) >> 2);
+                    P[2][l] = vcp_clip3(p2 - 2 * tc, p2 + 2 * tc, (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+                    Q[0][l] = vcp_clip3(q0 - 2 * tc, q0 + 2 * tc, (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+                    Q[1][l] = vcp_clip3(q1 - 2 * tc, q1 + 2 * tc, (p0 + q0 + q1 + q2 + 2) >> 2);
+                    Q[2][l] = vcp_clip3(q2 - 2 * tc, q2 + 2 * tc, (p0 + q0 + q1 + 3 * q2 + 2 * q3 + 4) >> 3);
+                } else {
+                    int d = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
+                    if (vcp_iabs(d) < tc * 10) {
+                        d = vcp_clip3(-tc, tc, d);
+                        P[0][l] = vcp_clip255(p0 + d);
+                        Q[0][l] = vcp_clip255(q0 - d);
+                        if (dep) P[1][l] = vcp_clip255(p1 + vcp_clip3(-(tc >> 1), tc >> 1, (((p2 + p0 + 1) >> 1) - p1 + d) >> 1));
+                        if (deq) Q[1][l] = vcp_clip255(q1 + vcp_clip3(-(tc >> 1), tc >> 1, (((q2 + q0 + 1) >> 1) - q1 - d) >> 1));
+                    }
+                }
+            }
+        }
+    }
+    if (changed) {
+        if (VERTICAL) {
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                uint32_t wp = 0, wq = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) { wp |= (uint32_t)P[i][l] << (8 * (3 - i)); wq |= (uint32_t)Q[i][l] << (8 * i); }
+                *reinterpret_cast<uint32_t*>(Y + (size_t)l * g.ys - 4) = wp;
+                *reinterpret_cast<uint32_t*>(Y + (size_t)l * g.ys) = wq;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; i++) {      // P[3], Q[3] never change
+                uint32_t wp = 0, wq = 0;
+#pragma unroll
+                for (int l = 0; l < 4; l++) { wp |= (uint32_t)P[i][l] << (8 * l); wq |= (uint32_t)Q[i][l] << (8 * l); }
+                *reinterpret_cast<uint32_t*>(Y - (ptrdiff_t)(i + 1) * g.ys) = wp;
+                *reinterpret_cast<uint32_t*>(Y + (size_t)i * g.ys) = wq;
+            }
+        }
+    }
+    // chroma: bS 2 on the 8-sample chroma grid, two chroma lines per segment
+    if (bs == 2 && ((VERTICAL ? x : y) & 15) == 0) {
+        const int tcc = hevc_tc_tab[min(53, hevc_chroma_qp(qp) + 2)];
+        if (tcc == 0) return;
+        const ptrdiff_t step = VERTICAL ? 1 : g.cs, line = VERTICAL ? g.cs : 1;
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            uint8_t* C = (pl ? b.rec_v : b.rec_u) + (size_t)slot * g.csize + g.coff + (size_t)(y >> 1) * g.cs + (x >> 1);
+#pragma unroll
+            for (int l = 0; l < 2; l++) {
+                uint8_t* c = C + l * line;
+                const int p0 = c[-step], p1 = c[-2 * step], q0 = c[0], q1 = c[step];
+                const int d = vcp_clip3(-tcc, tcc, (((q0 - p0) << 2) + p1 - q1 + 4) >> 3);
+                c[-step] = (uint8_t)vcp_clip255(p0 + d);
+                c[0] = (uint8_t)vcp_clip255(q0 - d);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 void vcp_launch_hevc_p_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
@@ -476,4 +607,9 @@ void vcp_launch_hevc_i_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& 
 void vcp_launch_hevc_cuinfo(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
     dim3 grid((g.nmb + 127) / 128, s.ngop);
     hevc_cuinfo_kernel<<<grid, 128, 0, st>>>(g, b, s);
+}
+void vcp_launch_hevc_deblock(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
+    const int nv = (g.cw >> 3) * (g.ch >> 2), nh = (g.cw >> 2) * (g.ch >> 3);
+    hevc_deblock_kernel<true><<<dim3((nv + 255) / 256, s.ngop), 256, 0, st>>>(g, b, s);
+    hevc_deblock_kernel<false><<<dim3((nh + 255) / 256, s.ngop), 256, 0, st>>>(g, b, s);
 }

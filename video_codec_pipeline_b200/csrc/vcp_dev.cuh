@@ -136,6 +136,7 @@ void vcp_launch_cabac_encode(const VcpGeom& g, const VcpBufs& b, const VcpStep& 
 void vcp_launch_hevc_p_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_hevc_i_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_hevc_cuinfo(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
+void vcp_launch_hevc_deblock(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_hevc_bins(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_rc_update(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 
