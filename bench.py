@@ -282,8 +282,9 @@ def main():
 
     # ---- end to end through the public API: pinned host frames -> bitstream in host memory ----
     # Two sessions driven by two host threads, the way a consumer with `-j 2` (cmd/consumer.go:123)
-    # drives the executor: the H2D copy of one batch overlaps the kernels of the other.  Every batch
-    # still pays its own H2D of all frames and D2H of the whole bitstream inside the timed region.
+    # drives the executor: the H2D copy of one batch overlaps the kernels of the other, and inside a
+    # batch the upload is streamed (each GOP group's chain starts when its frames have landed).  Every
+    # batch still pays its own H2D of all frames and D2H of the whole bitstream inside the timed region.
     import threading as _th
     nthreads = max(1, args.e2e_threads)
     sessions = [api.Session(p, n, device=local_rank) for _ in range(nthreads)]
@@ -295,7 +296,7 @@ def main():
         try:
             for _ in range(count):
                 t_a = time.perf_counter()
-                sessions[i].upload(host.data_ptr(), n)
+                sessions[i].upload(host.data_ptr(), n, wait=False)   # streamed: GOP groups start as their frames land
                 t_b = time.perf_counter()
                 sessions[i].encode()
                 t_c = time.perf_counter()

@@ -172,6 +172,11 @@ int vcpenc_session_create(const vcpenc_params* p, int device, int max_frames,
 /* copy host frames to the device and run K1 (convert, pad, pyramid) */
 int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes, char* err,
                           size_t errlen);
+/* same, but returns once the copies are queued: the next vcpenc_session_encode starts each group of GOPs as
+ * soon as ITS frames have landed, so the encode overlaps the rest of the transfer.  `frames` (pinned host
+ * memory, vcpenc_host_alloc, for a truly asynchronous copy) must stay valid until that encode returns. */
+int vcpenc_session_upload_async(vcpenc_session* s, const uint8_t* frames, int nframes, char* err,
+                                size_t errlen);
 /* same, but the raw frames are already in device memory (`dframes` is a device pointer):
  * runs K1 only.  `ms` (optional) receives the CUDA-event time on the launching stream. */
 int vcpenc_session_upload_device(vcpenc_session* s, const uint8_t* dframes, int nframes, float* ms,

@@ -341,6 +341,24 @@ def test_edge_cases(built):
     assert e.value.code == 1
 
 
+def test_streamed_upload_is_identical(built):
+    """upload(wait=False): the encode starts each GOP group when its frames have landed; same bytes as the
+    synchronous upload, for both codecs, also when the session is reused and when GOPs do not fill the groups."""
+    w, h = 320, 240
+    for codec, n, gop in ((0, 40, 8), (1, 40, 8), (0, 13, 5), (1, 7, 60)):
+        clip = synth.make_clip(w, h, n, seed=300 + n)
+        p = api.default_params(w, h, codec=codec, gop=gop, qp_i=26, qp_p=28, slices=0)
+        want = api.encode_frames(p, clip)["stream"].tobytes()
+        with api.Session(p, n) as s:
+            for _ in range(2):
+                s.upload(clip, wait=False)
+                s.encode()
+                assert s.download()["stream"].tobytes() == want, (codec, n, gop)
+            s.upload(clip)
+            s.encode()
+            assert s.download()["stream"].tobytes() == want
+
+
 def test_transcode_hevc_presets(built, tmp_path):
     """The reference's h265-* presets (internal/config/config.go:47-50) through the transcode entry point: the MP4
     (hvc1 + hvcC) demuxes and decodes with FFmpeg to the pictures the raw .h265 output decodes to."""

@@ -1,6 +1,6 @@
 """Quality / rate report of the B200 encoder on the synthetic S1080 clip:
 QP sweep {22,27,32,37} for both entropy coders and one bitrate-target run at 10 Mb/s.  For every
-point: bitrate, PSNR-Y/U/V and SSIM-Y of the DECODED stream (FFmpeg h264 decoder) against the source,
+point: bitrate, PSNR-Y/U/V and SSIM-Y of the DECODED stream (FFmpeg h264 / hevc decoder) against the source,
 decoder-vs-encoder-reconstruction bit-exactness, and the MP4 verify result.
 The libx264 side of the north-star's "within 0.5 dB at matched bitrate" cannot be produced in this
 image (no ffmpeg / libx264): the JSON says so instead of inventing numbers.
@@ -37,7 +37,7 @@ def measure(p, clip, w, h, fps, label):
     n = clip.shape[0]
     got = api.encode_frames(p, clip, want_recon=True)
     stream = got["stream"].tobytes()
-    dec = arbiter.decode_annexb(stream, threads=8)
+    dec = arbiter.decode_annexb_hevc(stream, threads=8) if p.codec == 1 else arbiter.decode_annexb(stream, threads=8)
     exact = len(dec) == n and all(np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), got["recon"][i]) for i in range(n))
     ps = [[], [], []]
     ss = []
@@ -73,6 +73,19 @@ def main():
             p = api.default_params(w, h, fps=fps, gop=gop, qp_i=qp - 2, qp_p=qp, entropy=ent, slices=0)
             rows.append(measure(p, clip, w, h, fps, "%s qp%d" % ("cabac" if ent else "cavlc", qp)))
             print(rows[-1], flush=True)
+    for t8 in (1,):       # High profile: CABAC + 8x8 transform, the default of the libx264 / nvenc presets
+        for qp in (22, 27, 32, 37):
+            p = api.default_params(w, h, fps=fps, gop=gop, qp_i=qp - 2, qp_p=qp, entropy=1, transform8x8=t8, slices=0)
+            rows.append(measure(p, clip, w, h, fps, "high qp%d" % qp))
+            print(rows[-1], flush=True)
+    for idc in (0, 1):    # HEVC (h265-* presets), with and without in-loop deblocking
+        for qp in (22, 27, 32, 37):
+            p = api.default_params(w, h, fps=fps, gop=gop, qp_i=qp - 2, qp_p=qp, codec=1, deblock_idc=idc, slices=0)
+            rows.append(measure(p, clip, w, h, fps, "hevc%s qp%d" % (" no-deblock" if idc else "", qp)))
+            print(rows[-1], flush=True)
+    p = api.default_params(w, h, fps=fps, gop=gop, rc_mode=1, bitrate=8_000_000, codec=1, slices=0)
+    rows.append(measure(p, clip, w, h, fps, "hevc 8Mb/s target (h265-nvenc preset)"))
+    print(rows[-1], flush=True)
     for ent in (0, 1):
         p = api.default_params(w, h, fps=fps, gop=gop, rc_mode=1, bitrate=10_000_000, entropy=ent, slices=0)
         rows.append(measure(p, clip, w, h, fps, "%s 10Mb/s target" % ("cabac" if ent else "cavlc")))

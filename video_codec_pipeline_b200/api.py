@@ -71,6 +71,7 @@ def lib():
                                            vp, cp, sz]
         L.vcpenc_session_create.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(vp), cp, sz]
         L.vcpenc_session_upload.argtypes = [vp, vp, C.c_int, cp, sz]
+        L.vcpenc_session_upload_async.argtypes = [vp, vp, C.c_int, cp, sz]
         L.vcpenc_session_upload_device.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_float), cp, sz]
         L.vcpenc_session_launch_count.argtypes = [vp]
         L.vcpenc_session_launch_count.restype = C.c_uint64
@@ -177,12 +178,15 @@ class Session:
         if rc:
             raise VcpencError(rc, self.err.value.decode(errors="replace"))
 
-    def upload(self, frames, nframes=None):
+    def upload(self, frames, nframes=None, wait=True):
+        """Host frames -> device planes.  wait=False: return once the copies are queued; the following encode()
+        starts each GOP group when its frames have landed (frames must stay alive until encode() returns)."""
         if isinstance(frames, np.ndarray):
             frames = np.ascontiguousarray(frames, dtype=np.uint8)
             nframes = frames.size // in_frame_bytes(self.params)
         self._keep = frames
-        self._ck(self.L.vcpenc_session_upload(self.h, _ptr(frames), nframes, self.err, 512))
+        fn = self.L.vcpenc_session_upload if wait else self.L.vcpenc_session_upload_async
+        self._ck(fn(self.h, _ptr(frames), nframes, self.err, 512))
         self.nframes = nframes
 
     def upload_device(self, dptr: int, nframes: int) -> float:

@@ -67,10 +67,13 @@ struct vcpenc_session {
     cudaStream_t st = nullptr, st_copy = nullptr;
     cudaStream_t st_pre = nullptr;  // motion-search pre-pass, picture by picture, LOW priority: pure throughput work
                                     // that fills the latency gaps of the reconstruction chains
-    std::vector<cudaEvent_t> ev_pre_t;   // pre-pass of picture t complete
+    std::vector<cudaEvent_t> ev_pre_t;   // [group][t]: pre-pass of picture t of the group's GOPs complete
+    int pre_T = 0;                       // pictures per GOP the events cover
+    bool streamed = false;               // the last upload was asynchronous: encode waits per group
     cudaStream_t st_up = nullptr;   // K1 of an upload: high priority, so that it is not queued behind the
                                     // thousands of CTAs of another session's encode on the same GPU
     static constexpr int kMaxGroups = 8;
+    cudaEvent_t ev_piece[kMaxGroups] = {};      // streamed upload: the frames of GOP group k are in their planes
     cudaStream_t gst[kMaxGroups] = {};          // one stream per GOP group (the recon chain)
     cudaStream_t est[kMaxGroups] = {};          // entropy coding of the group, off the chain
     static constexpr int kCabacStreams = 8;
@@ -269,6 +272,7 @@ void vcpenc_session_destroy(vcpenc_session* s) {
     if (s->st_up) cudaStreamDestroy(s->st_up);
     if (s->st_pre) cudaStreamDestroy(s->st_pre);
     for (auto e : s->ev_pre_t) cudaEventDestroy(e);
+    for (auto e : s->ev_piece) if (e) cudaEventDestroy(e);
     delete s;
 }
 
@@ -323,8 +327,10 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
         // running encode (this session's or another one's on the same GPU) are latency-critical
         CKS(cudaStreamCreateWithPriority(&s->st_up, cudaStreamNonBlocking, lo));
         CKS(cudaStreamCreateWithPriority(&s->st_pre, cudaStreamNonBlocking, lo));
-        s->ev_pre_t.resize((size_t)std::min(pp->gop, max_frames));
+        s->pre_T = std::min(pp->gop, max_frames);
+        s->ev_pre_t.resize((size_t)s->pre_T * 8);   // kMaxGroups
         for (auto& e : s->ev_pre_t) CKS(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : s->ev_piece) CKS(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     CKS(cudaEventCreate(&s->ev0)); CKS(cudaEventCreate(&s->ev1));
     CKS(cudaEventCreateWithFlags(&s->ev_pre, cudaEventDisableTiming));
@@ -444,7 +450,17 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
 #undef CKS
 }
 
-int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes, char* err, size_t errlen) {
+// GOP groups of an encode of N frames: group k covers GOPs [first, last)
+static int group_count(const vcpenc_session* s, int N) {
+    const int ngop_total = (N + s->p.gop - 1) / s->p.gop;
+    return std::max(1, std::min(s->ngroups, ngop_total));
+}
+static void group_gops(const vcpenc_session* s, int N, int ng, int k, int* gA, int* gB) {
+    const int ngop_total = (N + s->p.gop - 1) / s->p.gop;
+    *gA = (int)((long long)ngop_total * k / ng); *gB = (int)((long long)ngop_total * (k + 1) / ng);
+}
+
+static int upload_host(vcpenc_session* s, const uint8_t* frames, int nframes, bool wait, char* err, size_t errlen) {
     if (!s || !frames || nframes < 1 || nframes > s->max_frames) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
     CK(cudaSetDevice(s->device));
     const size_t fb = s->in_fb;
@@ -455,19 +471,38 @@ int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes,
     CK(cudaMemcpyAsync(s->b.qp, s->h_qp.data(), nframes, cudaMemcpyHostToDevice, s->st_up));
     // All H2D copies are queued up front into a device buffer that holds the whole batch, so the DMA
     // runs at PCIe rate whatever the GPU is busy with (another session's encode delays K1, never the
-    // copies); K1 trails the copies in a few large pieces.
-    const int pieces = std::min(4, nframes);
-    for (int k = 0; k < pieces; k++) {
-        const int n0 = (int)((long long)nframes * k / pieces), n1 = (int)((long long)nframes * (k + 1) / pieces);
+    // copies); K1 trails the copies piece by piece.  Pieces = the GOP groups of the encode, so that a
+    // streamed upload (wait = false) lets group k start its chain as soon as ITS frames have landed.
+    const int ng = s->profile ? 1 : group_count(s, nframes);
+    for (int k = 0; k < ng; k++) {
+        int gA, gB;
+        group_gops(s, nframes, ng, k, &gA, &gB);
+        const int n0 = gA * s->p.gop, n1 = std::min(nframes, gB * s->p.gop);
+        if (n1 <= n0) { CK(cudaEventRecord(s->ev_piece[k], s->st_up)); continue; }
         CK(cudaMemcpyAsync(s->raw_dev + (size_t)n0 * fb, frames + (size_t)n0 * fb, (size_t)(n1 - n0) * fb, cudaMemcpyHostToDevice, s->st_copy));
         CK(cudaEventRecord(s->staging_ready[k & 1], s->st_copy));
         CK(cudaStreamWaitEvent(s->st_up, s->staging_ready[k & 1], 0));
         k1_chain(s, s->raw_dev + (size_t)n0 * fb, n0, n1 - n0, s->st_up);
+        CK(cudaEventRecord(s->ev_piece[k], s->st_up));
     }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(s->st_up));
-    if (s->profile) collect_profile(s);
+    s->streamed = !wait && !s->profile;
+    if (!s->streamed) {
+        CK(cudaStreamSynchronize(s->st_up));
+        if (s->profile) collect_profile(s);
+    }
     return VCPENC_OK;
+}
+
+int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes, char* err, size_t errlen) {
+    return upload_host(s, frames, nframes, true, err, errlen);
+}
+
+// Same, but returns as soon as the copies are queued: the following vcpenc_session_encode starts each GOP
+// group when its frames have arrived, so the encode overlaps the rest of the transfer.  `frames` (pinned
+// host memory for a truly asynchronous copy) must stay valid until that encode returns.
+int vcpenc_session_upload_async(vcpenc_session* s, const uint8_t* frames, int nframes, char* err, size_t errlen) {
+    return upload_host(s, frames, nframes, false, err, errlen);
 }
 
 int vcpenc_session_upload_device(vcpenc_session* s, const uint8_t* dframes, int nframes, float* ms, char* err, size_t errlen) {
@@ -476,6 +511,7 @@ int vcpenc_session_upload_device(vcpenc_session* s, const uint8_t* dframes, int 
     const size_t fb = s->in_fb;
     s->nframes = nframes;
     s->encoded = false;
+    s->streamed = false;
     s->h_qp.resize(nframes);
     for (int n = 0; n < nframes; n++) s->h_qp[n] = initial_qp(s, n);
     CK(cudaMemcpyAsync(s->b.qp, s->h_qp.data(), nframes, cudaMemcpyHostToDevice, s->st));
@@ -496,7 +532,6 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
     const VcpGeom& g = s->g;
     const VcpBufs& b = s->b;
     const int N = s->nframes, gop = s->p.gop;
-    const int ngop_total = (N + gop - 1) / gop;
     CK(cudaMemsetAsync(b.out_cursor, 0, sizeof(unsigned long long), s->st));
     CK(cudaMemsetAsync(b.error_flag, 0, sizeof(int), s->st));
     CK(cudaMemsetAsync(b.frame_bits, 0, (size_t)N * sizeof(uint32_t), s->st));
@@ -507,25 +542,44 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
         CK(cudaMemsetAsync(b.out_index, 0, (size_t)N * g.slices * sizeof(uint2), s->st));
     }
     const int T = std::min(gop, N);
+    // GOP groups advance on their own streams: the latency-bound wavefront kernels (intra
+    // recon, deblocking) of one group overlap the throughput-bound kernels of the others.
+    // Per-kernel profiling wants clean timings, so it runs everything on one stream.
+    const int ng = s->profile ? 1 : group_count(s, N);
+    const bool streamed = s->streamed && !s->profile;
+    if (s->streamed && s->profile) CK(cudaStreamSynchronize(s->st_up));   // profiling was switched on after an asynchronous upload
     if (s->profile) {
         Prof pr(s, VCPENC_K_ME_PRE);
         vcp_launch_me_prepass(g, b, N, gop, -1, s->st);
     } else {
-        // picture by picture on its own stream: chain step t only waits for the vectors of picture t
+        // picture by picture and group by group on its own stream: chain step t of a group only waits for
+        // the vectors of picture t of its GOPs.  Resident input: pictures outermost (every group gets its
+        // first vectors early).  Streamed input: groups outermost, each behind the arrival of its frames.
         CK(cudaEventRecord(s->ev_pre, s->st));
         CK(cudaStreamWaitEvent(s->st_pre, s->ev_pre, 0));
-        for (int t = 1; t < T; t++) {
+        auto pre = [&](int k, int t) -> int {
+            int gA, gB;
+            group_gops(s, N, ng, k, &gA, &gB);
             s->launches += 1;
-            vcp_launch_me_prepass(g, b, N, gop, t, s->st_pre);
-            CK(cudaEventRecord(s->ev_pre_t[t], s->st_pre));
+            vcp_launch_me_prepass(g, b, N, gop, t, s->st_pre, gA, gB);
+            CK(cudaEventRecord(s->ev_pre_t[(size_t)k * s->pre_T + t], s->st_pre));
+            return VCPENC_OK;
+        };
+        if (streamed) {
+            for (int k = 0; k < ng; k++) {
+                CK(cudaStreamWaitEvent(s->st_pre, s->ev_piece[k], 0));
+                for (int t = 1; t < T; t++) { const int rc = pre(k, t); if (rc) return rc; }
+            }
+        } else {
+            for (int t = 1; t < T; t++)
+                for (int k = 0; k < ng; k++) { const int rc = pre(k, t); if (rc) return rc; }
         }
     }
-    // GOP groups advance on their own streams: the latency-bound wavefront kernels (intra
-    // recon, deblocking) of one group overlap the throughput-bound kernels of the others.
-    // Per-kernel profiling wants clean timings, so it runs everything on one stream.
-    const int ng = s->profile ? 1 : std::max(1, std::min(s->ngroups, ngop_total));
     CK(cudaEventRecord(s->ev_pre, s->st));
-    for (int k = 0; k < ng; k++) CK(cudaStreamWaitEvent(s->gst[k], s->ev_pre, 0));
+    for (int k = 0; k < ng; k++) {
+        CK(cudaStreamWaitEvent(s->gst[k], s->ev_pre, 0));
+        if (streamed) CK(cudaStreamWaitEvent(s->gst[k], s->ev_piece[k], 0));
+    }
     for (int t = 0; t < gop && t < N; t++) {
         const int par = t & 1;
         const VcpBufs& bt = s->bpar[par];     // macroblock records of this step
@@ -535,7 +589,8 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
             VcpStep sp;
             sp.t = t; sp.gop = gop; sp.ring = s->ring; sp.nframes = N; sp.gop0 = s->gop_base;
             // GOPs of this group that own a frame at position t
-            const int gA = (int)((long long)ngop_total * k / ng), gB = (int)((long long)ngop_total * (k + 1) / ng);
+            int gA, gB;
+            group_gops(s, N, ng, k, &gA, &gB);
             const int active = (N - t + gop - 1) / gop;      // GOPs (from 0) that have frame t
             sp.g0 = gA;
             sp.ngop = std::min(gB, active) - gA;
@@ -546,7 +601,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 // same chain, HEVC kernels (k6_hevc.cu): no intra in P pictures, no half-sample planes
                 if (t == 0) { Prof pr(s, VCPENC_K_I_RECON, 1, st); vcp_launch_hevc_i_recon(g, bt, sp, st); }
                 else {
-                    if (!s->profile) CK(cudaStreamWaitEvent(st, s->ev_pre_t[t], 0));
+                    if (!s->profile) CK(cudaStreamWaitEvent(st, s->ev_pre_t[(size_t)k * s->pre_T + t], 0));
                     { Prof pr(s, VCPENC_K_ME_REFINE, 1, st); vcp_launch_me_refine(g, bt, sp, st); }
                     { Prof pr(s, VCPENC_K_P_RECON, 1, st); vcp_launch_hevc_p_recon(g, bt, sp, st); }
                     { Prof pr(s, VCPENC_K_MBINFO, 1, st); vcp_launch_hevc_cuinfo(g, bt, sp, st); }
@@ -555,7 +610,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 Prof pr(s, VCPENC_K_I_RECON, 1, st);
                 vcp_launch_i_recon(g, bt, sp, st);
             } else {
-                if (!s->profile) CK(cudaStreamWaitEvent(st, s->ev_pre_t[t], 0));
+                if (!s->profile) CK(cudaStreamWaitEvent(st, s->ev_pre_t[(size_t)k * s->pre_T + t], 0));
                 { Prof pr(s, VCPENC_K_ME_REFINE, 1, st); vcp_launch_me_refine(g, bt, sp, st); }
                 { Prof pr(s, VCPENC_K_P_RECON, 2, st); vcp_launch_p_recon(g, bt, sp, st); vcp_launch_i_fix(g, bt, sp, st); }
                 { Prof pr(s, VCPENC_K_MBINFO, 1, st); vcp_launch_mbinfo(g, bt, sp, st); }

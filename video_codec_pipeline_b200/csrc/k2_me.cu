@@ -34,11 +34,11 @@ struct __align__(16) PrepassWarp {
 
 // grid z = frame (t < 0: every resident frame) or GOP (t >= 0: picture t of every GOP, so that the
 // pre-pass of later pictures runs beside the reconstruction chain of earlier ones)
-__global__ void __launch_bounds__(ME_WARPS * 32) me_prepass_kernel(VcpGeom g, VcpBufs b, int nframes, int gop, int t) {
+__global__ void __launch_bounds__(ME_WARPS * 32) me_prepass_kernel(VcpGeom g, VcpBufs b, int nframes, int gop, int t, int g0) {
     __shared__ __align__(16) uint8_t win[L1_WIN_H][L1_WIN_WA];
     __shared__ PrepassWarp pw[ME_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = t < 0 ? (int)blockIdx.z : (int)blockIdx.z * gop + t;
+    const int n = t < 0 ? (int)blockIdx.z : ((int)blockIdx.z + g0) * gop + t;
     if (n >= nframes || n % gop == 0) return;  // IDR: no search
     const int my = blockIdx.y, mx0 = blockIdx.x * ME_WARPS, mx = mx0 + warp;
     const uint8_t* hc = b.src_h + (size_t)n * g.hsize + g.hoff;
@@ -284,12 +284,14 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
 
 }  // namespace
 
-void vcp_launch_me_prepass(const VcpGeom& g, const VcpBufs& b, int nframes, int gop, int t, cudaStream_t st) {
+// t < 0: every resident frame.  t >= 0: picture t of GOPs [g0, g1) (g1 < 0: up to the last GOP)
+void vcp_launch_me_prepass(const VcpGeom& g, const VcpBufs& b, int nframes, int gop, int t, cudaStream_t st, int g0, int g1) {
     if (nframes <= 0) return;
-    const int nz = t < 0 ? nframes : (nframes - t + gop - 1) / gop;   // GOPs that own a picture t
+    int nz = t < 0 ? nframes : (nframes - t + gop - 1) / gop;   // GOPs that own a picture t
+    if (t >= 0) { if (g1 >= 0 && g1 < nz) nz = g1; nz -= g0; } else g0 = 0;
     if (nz <= 0) return;
     dim3 grid((g.mbw + ME_WARPS - 1) / ME_WARPS, g.mbh, nz);
-    me_prepass_kernel<<<grid, ME_WARPS * 32, 0, st>>>(g, b, nframes, gop, t);
+    me_prepass_kernel<<<grid, ME_WARPS * 32, 0, st>>>(g, b, nframes, gop, t, g0);
 }
 
 void vcp_launch_me_refine(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
