@@ -25,7 +25,7 @@ __device__ __forceinline__ int blk_ras(int b) { return blk_y4(b) * 4 + blk_x4(b)
 constexpr int T8_STRIDE = 72;   // ints per 8x8 block: 64 + 8 of padding keeps the four blocks on different banks
 struct __align__(16) McScratch {
     uint8_t pred[16][16];
-    int t8[4][T8_STRIDE];   // 8x8 transform staging (High profile): one 8x8 block per four lanes
+    int t8[4][T8_STRIDE];   // 8x8 transform staging (High profile): one 8x8 block per eight lanes
     int16_t lv8[256];       // levels of the four 8x8 blocks in record order, written out as 16-byte vectors
 };
 // per-CTA copies of the 8x8 tables: indexed per lane, so shared memory rather than constant
@@ -93,63 +93,55 @@ __device__ __forceinline__ bool prefer_8x8(const uint8_t* __restrict__ src, int 
     return vcp_prefer_8x8(cost4, cost8) != 0;
 }
 
-// Luma of an inter macroblock as four 8x8 blocks: four lanes per block (k = lane >> 2, q = lane & 3),
-// a lane owns rows 2q,2q+1 in the row passes and columns 2q,2q+1 in the column passes; the passes
-// meet in shared memory.  The inverse runs rows first, then columns, as 8.5.13 prescribes.
-// S.pred holds the prediction on entry and the reconstruction on exit.  Returns the luma cbp.
+// Luma of an inter macroblock as four 8x8 blocks: eight lanes per block (k = lane >> 3, q = lane & 7); a lane
+// owns row q in the row passes and column q in the column passes; the passes meet in shared memory, each row
+// rotated by its index so that row and column accesses are both conflict-free.  The inverse runs rows first,
+// then columns, as 8.5.13 prescribes.  S.pred holds the prediction on entry and the reconstruction on exit.
+// Returns the luma cbp.
 __device__ __forceinline__ uint32_t luma8x8_transform(const VcpGeom& g, const VcpBufs& b, McScratch& S, const T8Tables& TT,
                                                       int n, int gi, int mbi, int mx, int my, int qp, int lane) {
-    const bool act = lane < 16;
-    const int k = (lane >> 2) & 3, q = lane & 3;
+    const int k = lane >> 3, q = lane & 7;
     const int bx = (k & 1) * 8, by = (k >> 1) * 8;
     int* T = S.t8[k];
     const uint8_t* src = b.src_y + (size_t)n * g.ysize + g.yoff + (size_t)(16 * my + by) * g.ys + 16 * mx + bx;
-    if (act) {
+    {
+        const uint2 s8 = *reinterpret_cast<const uint2*>(src + (size_t)q * g.ys);
+        const uint2 p8 = *reinterpret_cast<const uint2*>(&S.pred[by + q][bx]);
+        int d[8], y[8];
 #pragma unroll
-        for (int rr = 0; rr < 2; rr++) {
-            const int r = 2 * q + rr;
-            const uint2 s8 = *reinterpret_cast<const uint2*>(src + (size_t)r * g.ys);
-            const uint2 p8 = *reinterpret_cast<const uint2*>(&S.pred[by + r][bx]);
-            int d[8], y[8];
-#pragma unroll
-            for (int x = 0; x < 8; x++) {
-                const uint32_t sw = x < 4 ? s8.x : s8.y, pw = x < 4 ? p8.x : p8.y;
-                d[x] = (int)((sw >> (8 * (x & 3))) & 255) - (int)((pw >> (8 * (x & 3))) & 255);
-            }
-            fdct8_1d(d, y);
-#pragma unroll
-            for (int x = 0; x < 8; x++) T[8 * r + x] = y[x];
+        for (int x = 0; x < 8; x++) {
+            const uint32_t sw = x < 4 ? s8.x : s8.y, pw = x < 4 ? p8.x : p8.y;
+            d[x] = (int)((sw >> (8 * (x & 3))) & 255) - (int)((pw >> (8 * (x & 3))) & 255);
         }
+        fdct8_1d(d, y);
+#pragma unroll
+        for (int x = 0; x < 8; x++) T[8 * q + ((x + q) & 7)] = y[x];
     }
     __syncwarp();
     const int qbits = 16 + qp / 6, f = (1 << qbits) / 6, rem = qp % 6, sh = qp / 6;
     int nz = 0, cnt4 = 0;   // cnt4: four 8-bit counters, one per interleaved 4x4 block (CAVLC)
     int16_t* lvp = S.lv8;
-    if (act) {
+    {
+        int in[8], w[8];
 #pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-            const int col = 2 * q + cc;
-            int in[8], w[8];
+        for (int r = 0; r < 8; r++) in[r] = T[8 * r + ((q + r) & 7)];
+        fdct8_1d(in, w);
 #pragma unroll
-            for (int r = 0; r < 8; r++) in[r] = T[8 * r + col];
-            fdct8_1d(in, w);
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const int i = 8 * r + col;
-                const int cls = TT.cls[i], zz = TT.izz[i];
-                const int l = vcp_quant1(w[r], TT.mf[rem][cls], f, qbits);
-                nz += l != 0;
-                cnt4 += (l != 0) << (8 * (zz & 3));
-                lvp[g.cabac ? k * 64 + zz : (k * 4 + (zz & 3)) * 16 + (zz >> 2)] = (int16_t)l;
-                const int ls = 16 * TT.v[rem][cls];
-                T[i] = qp >= 36 ? (l * ls) << (sh - 6) : (l * ls + (1 << (5 - sh))) >> (6 - sh);
-            }
+        for (int r = 0; r < 8; r++) {
+            const int i = 8 * r + q;
+            const int cls = TT.cls[i], zz = TT.izz[i];
+            const int l = vcp_quant1(w[r], TT.mf[rem][cls], f, qbits);
+            nz += l != 0;
+            cnt4 += (l != 0) << (8 * (zz & 3));
+            lvp[g.cabac ? k * 64 + zz : (k * 4 + (zz & 3)) * 16 + (zz >> 2)] = (int16_t)l;
+            const int ls = 16 * TT.v[rem][cls];
+            T[8 * r + ((q + r) & 7)] = qp >= 36 ? (l * ls) << (sh - 6) : (l * ls + (1 << (5 - sh))) >> (6 - sh);
         }
     }
-    // totals of the 8x8 block over its four lanes
-    nz += __shfl_xor_sync(0xffffffffu, nz, 1); nz += __shfl_xor_sync(0xffffffffu, nz, 2);
-    cnt4 += __shfl_xor_sync(0xffffffffu, cnt4, 1); cnt4 += __shfl_xor_sync(0xffffffffu, cnt4, 2);
-    if (act) {
+    // totals of the 8x8 block over its eight lanes
+    nz += __shfl_xor_sync(0xffffffffu, nz, 1); nz += __shfl_xor_sync(0xffffffffu, nz, 2); nz += __shfl_xor_sync(0xffffffffu, nz, 4);
+    cnt4 += __shfl_xor_sync(0xffffffffu, cnt4, 1); cnt4 += __shfl_xor_sync(0xffffffffu, cnt4, 2); cnt4 += __shfl_xor_sync(0xffffffffu, cnt4, 4);
+    if (q < 4) {
         // nnz of luma4x4BlkIdx 4k+q: CABAC = coefficients of the whole 8x8; CAVLC = of its interleaved
         // 4x4, with bit 7 flagging "the 8x8 holds coefficients" for the deblocking strength
         const int blk = 4 * k + q;
@@ -157,37 +149,29 @@ __device__ __forceinline__ uint32_t luma8x8_transform(const VcpGeom& g, const Vc
         b.nnz[((size_t)gi * g.nmb + mbi) * 24 + blk_y4(blk) * 4 + blk_x4(blk)] = (uint8_t)v;
     }
     __syncwarp();
-    if (act) {   // inverse: rows
+    if (nz) {   // inverse: row q (uniform over the eight lanes of the block)
+        int in[8], o[8];
 #pragma unroll
-        for (int rr = 0; rr < 2; rr++) {
-            const int r = 2 * q + rr;
-            int in[8], o[8];
+        for (int x = 0; x < 8; x++) in[x] = T[8 * q + ((x + q) & 7)];
+        idct8_1d(in, o);
 #pragma unroll
-            for (int x = 0; x < 8; x++) in[x] = T[8 * r + x];
-            idct8_1d(in, o);
-#pragma unroll
-            for (int x = 0; x < 8; x++) T[8 * r + x] = o[x];
-        }
+        for (int x = 0; x < 8; x++) T[8 * q + ((x + q) & 7)] = o[x];
     }
     __syncwarp();
-    if (act) {   // inverse: columns, then reconstruct in place of the prediction
+    if (nz) {   // inverse: column q, then reconstruct in place of the prediction
+        int in[8], o[8];
 #pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-            const int col = 2 * q + cc;
-            int in[8], o[8];
+        for (int r = 0; r < 8; r++) in[r] = T[8 * r + ((q + r) & 7)];
+        idct8_1d(in, o);
 #pragma unroll
-            for (int r = 0; r < 8; r++) in[r] = T[8 * r + col];
-            idct8_1d(in, o);
-#pragma unroll
-            for (int r = 0; r < 8; r++)
-                S.pred[by + r][bx + col] = (uint8_t)vcp_clip255((int)S.pred[by + r][bx + col] + ((o[r] + 32) >> 6));
-        }
+        for (int r = 0; r < 8; r++)
+            S.pred[by + r][bx + q] = (uint8_t)vcp_clip255((int)S.pred[by + r][bx + q] + ((o[r] + 32) >> 6));
     }
     __syncwarp();
     // levels: 512 bytes per macroblock, one 16-byte vector per lane
     reinterpret_cast<uint4*>(b.levels + ((size_t)gi * g.nmb + mbi) * VCP_LV_STRIDE + VCP_LV_LUMA)[lane] = reinterpret_cast<const uint4*>(S.lv8)[lane];
-    const uint32_t coded = __ballot_sync(0xffffffffu, act && nz > 0);
-    return ((coded & 0x000fu) ? 1u : 0u) | ((coded & 0x00f0u) ? 2u : 0u) | ((coded & 0x0f00u) ? 4u : 0u) | ((coded & 0xf000u) ? 8u : 0u);
+    const uint32_t coded = __ballot_sync(0xffffffffu, nz > 0);
+    return ((coded & 0x000000ffu) ? 1u : 0u) | ((coded & 0x0000ff00u) ? 2u : 0u) | ((coded & 0x00ff0000u) ? 4u : 0u) | ((coded & 0xff000000u) ? 8u : 0u);
 }
 
 __device__ __forceinline__ void store_block_recon(uint8_t* dst, int stride, const uint32_t pred[4], const int r[16]) {

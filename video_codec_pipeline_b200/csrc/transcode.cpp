@@ -310,7 +310,8 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
         auto run = [&](Shard& sh) {
             if (!sh.n) return;
             vcpenc_session_set_first_gop(sh.ses, sh.g0);          // idr_pic_id parity continues across ranges and chunks
-            sh.rc = vcpenc_session_upload(sh.ses, fbuf + (size_t)sh.f0 * src->fbytes(), sh.n, sh.err, sizeof sh.err);
+            // streamed: the pinned chunk buffer outlives the encode, whose GOP groups start as their frames land
+            sh.rc = vcpenc_session_upload_async(sh.ses, fbuf + (size_t)sh.f0 * src->fbytes(), sh.n, sh.err, sizeof sh.err);
             if (!sh.rc) sh.rc = vcpenc_session_encode(sh.ses, nullptr, sh.err, sizeof sh.err);
             if (!sh.rc) {
                 sh.rc = vcpenc_session_download(sh.ses, sh.bits.data(), sh.bits.size(), &sh.len, sh.info.data(), nullptr, sh.err, sizeof sh.err);
