@@ -11,7 +11,8 @@
  *   - Main profile, 8-bit 4:2:0, closed GOPs (IDR_W_RADL + TRAIL_R), one reference, POC = decode order
  *   - CTB = CU = 16x16 (no split flags), coded in raster order; slices = whole CTB rows
  *   - transform blocks: luma 8x8 (the 16x16 root is split because MaxTb = 8), chroma 4x4; DCT only
- *   - intra: DC prediction per transform block (mode signalled through the MPM list), chroma derived
+ *   - intra: DC prediction per transform block (mode signalled through the MPM list), chroma derived; every CU of an
+ *     IDR picture, and CUs of P pictures where the refine finds intra cheaper (scene cuts)
  *   - inter: one 16x16 PU, full-sample luma vectors (chroma lands on half samples: 4-tap filter),
  *     AMVP with spatial candidates, merge (1 candidate) / skip
  *   - CABAC (same engine as H.264 9.3.4.2; HEVC context tables 9-5..9-37), no sign hiding
@@ -336,8 +337,10 @@ static void hevc_mc_chroma(const uint8_t* ref, int rs, int x0, int y0, int mvx, 
         }
 }
 
-/* full-sample refine on the reconstructed reference: pre-pass vector and its 8 neighbours, zero, predictor */
-static void hevc_refine_cu(HEnc* h, int cx, int cy, int16_t mv[2]) {
+/* full-sample refine on the reconstructed reference: pre-pass vector and its 8 neighbours, zero, predictor.
+ * Returns 1 when the CU should be coded intra instead (same estimate on the original picture and the same rule
+ * as the H.264 path: intra_estimate, vcp_intra_wins -- every CU decides in parallel). */
+static int hevc_refine_cu(HEnc* h, int cx, int cy, int16_t mv[2]) {
     Enc* e = h->e;
     const int lam = vcp_lambda(h->qp);
     int pmx, pmy;
@@ -361,6 +364,9 @@ static void hevc_refine_cu(HEnc* h, int cx, int cy, int16_t mv[2]) {
         if (key < best) best = key;
     }
     mv[0] = (int16_t)(4 * cand[best & 15][0]); mv[1] = (int16_t)(4 * cand[best & 15][1]);
+    const uint32_t bcost = best >> 4;
+    if (bcost < VCP_SUBPEL_SKIP_COST) return 0;
+    return vcp_intra_wins(intra_estimate(e, cx, cy), (int)bcost, lam) != 0;
 }
 
 static void hevc_encode_inter_cu(HEnc* h, int cx, int cy) {
@@ -743,13 +749,18 @@ int hevc_orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, 
             me_prepass(e);
             for (int i = 0; i < e->nmb; i++) {
                 int16_t mv[2];
-                hevc_refine_cu(&h, i % e->mbw, i / e->mbw, mv);
+                const int intra = hevc_refine_cu(&h, i % e->mbw, i / e->mbw, mv);
                 h.cus[i].mv[0] = mv[0]; h.cus[i].mv[1] = mv[1];
-                hevc_encode_inter_cu(&h, i % e->mbw, i / e->mbw);
+                if (intra) h.cus[i].type = HCU_INTRA;     /* coded below, once the inter CUs around it are reconstructed */
+                else hevc_encode_inter_cu(&h, i % e->mbw, i / e->mbw);
             }
+            /* intra CUs inside the P picture (scene cuts): raster order, predicting from whatever surrounds them */
+            for (int i = 0; i < e->nmb; i++)
+                if (h.cus[i].type == HCU_INTRA) hevc_encode_intra_cu(&h, i % e->mbw, i / e->mbw);
             /* post-hoc: merge / skip / AMVP index, once every vector of the picture is final */
             for (int i = 0; i < e->nmb; i++) {
                 HCU* cu = &h.cus[i];
+                if (cu->type == HCU_INTRA) continue;
                 const int cx = i % e->mbw, cy = i / e->mbw;
                 int mg[2], list[2][2], any = 0;
                 hevc_merge_cand(&h, cx, cy, mg);

@@ -341,6 +341,31 @@ def test_edge_cases(built):
     assert e.value.code == 1
 
 
+def test_hevc_intra_cus_in_p_pictures(built):
+    """HEVC, a scene cut inside a GOP: the refine flags CUs intra, hevc_i_fix codes them on a wavefront after the
+    inter ones; merge / AMVP skip them, deblocking filters their edges with bS 2 (chroma included)."""
+    from oracle import pyoracle
+    w, h = 320, 192
+    a = synth.make_clip(w, h, 4, seed=1)
+    cut = np.concatenate([a, np.roll(a, 7777, axis=1)[:2], synth.make_clip(w, h, 3, seed=77, start=9)])
+    for kw in (dict(slices=1), dict(slices=3), dict(slices=2, deblock_idc=1)):
+        ref = pyoracle.encode_hevc(pyoracle.make_params(w, h, codec=1, gop=60, qp_i=26, qp_p=28, **kw), cut)
+        assert ref["info"][4][1] > 8 * ref["info"][3][1]          # the cut picture is mostly intra
+        p = api.default_params(w, h, codec=1, gop=60, qp_i=26, qp_p=28, debug=1, **kw)
+        with api.Session(p, cut.shape[0]) as s:
+            s.upload(cut)
+            s.encode()
+            got = s.download(want_recon=True)
+            dbg = s.debug_mbs()
+        assert (dbg["mb_type"][4] == 0).sum() > 100, kw
+        assert np.array_equal(got["recon"], ref["recon"]), kw
+        assert got["stream"].tobytes() == ref["stream"], kw
+        if arbiter.available():
+            dec = arbiter.decode_annexb_hevc(got["stream"].tobytes())
+            for i in range(cut.shape[0]):
+                assert np.array_equal(_flat(dec[i]), got["recon"][i])
+
+
 def test_streamed_upload_is_identical(built):
     """upload(wait=False): the encode starts each GOP group when its frames have landed; same bytes as the
     synchronous upload, for both codecs, also when the session is reused and when GOPs do not fill the groups."""

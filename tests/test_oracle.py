@@ -327,6 +327,23 @@ def test_hevc_oracle_stream_decodes_to_its_own_recon(case):
     assert len(r["stream"]) < clip.size // 2 or qp <= 12
 
 
+def test_hevc_oracle_intra_cus_in_p_pictures():
+    """Scene cut inside a GOP: CUs of the P picture are coded intra; the FFmpeg hevc decoder still agrees."""
+    if not arbiter.available():
+        pytest.skip("bundled FFmpeg decoder not present")
+    w, h = 320, 192
+    a = synth.make_clip(w, h, 4, seed=1)
+    cut = np.concatenate([a, np.roll(a, 7777, axis=1)[:2], synth.make_clip(w, h, 3, seed=77, start=9)])
+    for kw in (dict(slices=1), dict(slices=3), dict(slices=2, deblock_idc=1)):
+        r = pyoracle.encode_hevc(pyoracle.make_params(w, h, codec=1, gop=60, qp_i=26, qp_p=28, **kw), cut)
+        assert r["info"][4][1] > 8 * r["info"][3][1]
+        dec = arbiter.decode_annexb_hevc(r["stream"])
+        assert len(dec) == cut.shape[0]
+        for i in range(cut.shape[0]):
+            assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i]), (kw, i)
+        assert arbiter.psnr(dec[4][0], synth.split_planes(cut[4], w, h)[0]) > 34
+
+
 def test_hevc_tables_match_decoder_rodata():
     """CABAC initValues (tables 9-5..9-37) typed in the oracle must appear in the decoder's own tables."""
     import glob

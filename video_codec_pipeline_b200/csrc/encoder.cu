@@ -598,12 +598,12 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
             // the records of this parity were last read by the entropy pass of step t-2
             if (!s->profile && t >= 2) CK(cudaStreamWaitEvent(st, s->ev_ent[k][par], 0));
             if (g.hevc) {
-                // same chain, HEVC kernels (k6_hevc.cu): no intra in P pictures, no half-sample planes
+                // same chain, HEVC kernels (k6_hevc.cu): no half-sample planes
                 if (t == 0) { Prof pr(s, VCPENC_K_I_RECON, 1, st); vcp_launch_hevc_i_recon(g, bt, sp, st); }
                 else {
                     if (!s->profile) CK(cudaStreamWaitEvent(st, s->ev_pre_t[(size_t)k * s->pre_T + t], 0));
                     { Prof pr(s, VCPENC_K_ME_REFINE, 1, st); vcp_launch_me_refine(g, bt, sp, st); }
-                    { Prof pr(s, VCPENC_K_P_RECON, 1, st); vcp_launch_hevc_p_recon(g, bt, sp, st); }
+                    { Prof pr(s, VCPENC_K_P_RECON, 2, st); vcp_launch_hevc_p_recon(g, bt, sp, st); vcp_launch_hevc_i_fix(g, bt, sp, st); }
                     { Prof pr(s, VCPENC_K_MBINFO, 1, st); vcp_launch_hevc_cuinfo(g, bt, sp, st); }
                 }
             } else if (t == 0) {

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
     uint32_t best = warp_min(lane < 11 ? (((uint32_t)mycost << 4) | (uint32_t)lane) : 0xffffffffu);
     const int bvx = __shfl_sync(0xffffffffu, cvx, (int)(best & 15)), bvy = __shfl_sync(0xffffffffu, cvy, (int)(best & 15));
     uint32_t bcost = best >> 4;
-    if (bcost < VCP_SUBPEL_SKIP_COST || g.hevc) {   // warp-uniform; the HEVC path keeps luma vectors on full samples
+    if (bcost < VCP_SUBPEL_SKIP_COST) {   // warp-uniform
         if (lane == 0) {
             b.mv[(size_t)gi * g.nmb + mbi] = make_short2((short)(4 * bvx), (short)(4 * bvy));
             b.mbtype[(size_t)gi * g.nmb + mbi] = VCP_MB_P16;
@@ -215,42 +215,44 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
         return;
     }
 
-    // half-pel then quarter-pel neighbours from the half-sample planes of the reference, staged
-    // once around the best full-pel position
-    __syncwarp();
-    mis = hpel_window_stage(W, mb0 + (ptrdiff_t)bvy * g.ys + bvx, g.ys, g.ysize, lane, 4);
-    const int lane_byte = (row + 1) * 24 + mis + 1 + hx;   // this lane's first sample at displacement 0 inside a plane window
     int ox = 0, oy = 0;
+    if (!g.hevc) {   // the HEVC path keeps luma vectors on full samples (k6_hevc.cu)
+        // half-pel then quarter-pel neighbours from the half-sample planes of the reference, staged
+        // once around the best full-pel position
+        __syncwarp();
+        mis = hpel_window_stage(W, mb0 + (ptrdiff_t)bvy * g.ys + bvx, g.ys, g.ysize, lane, 4);
+        const int lane_byte = (row + 1) * 24 + mis + 1 + hx;   // this lane's first sample at displacement 0 inside a plane window
 #pragma unroll
-    for (int step = 2; step >= 1; step--) {
-        // lane k (1..8): candidate k -> byte offsets of its two grid samples, and its vector cost
-        int o1 = 0, o2 = 0, cq = 0, cr = 0;
-        {
-            const int k = (lane - 1) & 7, q = k + (k > 3);
-            cq = ox + (q % 3 - 1) * step; cr = oy + (q / 3 - 1) * step;
-            const HpelPoints h = hpel_points(cq, cr);
-            o1 = (hpel_plane(h.x1, h.y1) * 18 + (h.y1 >> 1)) * 24 + (h.x1 >> 1);
-            o2 = (hpel_plane(h.x2, h.y2) * 18 + (h.y2 >> 1)) * 24 + (h.x2 >> 1);
-        }
-        mycost = lam * (vcp_se_len(4 * bvx + cq - pmx) + vcp_se_len(4 * bvy + cr - pmy));
-        if (lane == 0) mycost = (int)bcost;
-#pragma unroll
-        for (int k = 1; k <= 8; k++) {
-            const int a1 = lane_byte + __shfl_sync(0xffffffffu, o1, k);
-            uint2 p8 = hpel_row8(Ww, a1);
-            if (step == 1) {   // quarter positions average two grid samples; half positions are one
-                const int a2 = lane_byte + __shfl_sync(0xffffffffu, o2, k);
-                const uint2 c2 = hpel_row8(Ww, a2);
-                p8 = make_uint2(__vavgu4(p8.x, c2.x), __vavgu4(p8.y, c2.y));
+        for (int step = 2; step >= 1; step--) {
+            // lane k (1..8): candidate k -> byte offsets of its two grid samples, and its vector cost
+            int o1 = 0, o2 = 0, cq = 0, cr = 0;
+            {
+                const int k = (lane - 1) & 7, q = k + (k > 3);
+                cq = ox + (q % 3 - 1) * step; cr = oy + (q / 3 - 1) * step;
+                const HpelPoints h = hpel_points(cq, cr);
+                o1 = (hpel_plane(h.x1, h.y1) * 18 + (h.y1 >> 1)) * 24 + (h.x1 >> 1);
+                o2 = (hpel_plane(h.x2, h.y2) * 18 + (h.y2 >> 1)) * 24 + (h.x2 >> 1);
             }
-            const int sad = warp_sum((int)sad4(p8.y, c8.y, sad4(p8.x, c8.x, 0)));
-            if (lane == k) mycost += sad;
+            mycost = lam * (vcp_se_len(4 * bvx + cq - pmx) + vcp_se_len(4 * bvy + cr - pmy));
+            if (lane == 0) mycost = (int)bcost;
+#pragma unroll
+            for (int k = 1; k <= 8; k++) {
+                const int a1 = lane_byte + __shfl_sync(0xffffffffu, o1, k);
+                uint2 p8 = hpel_row8(Ww, a1);
+                if (step == 1) {   // quarter positions average two grid samples; half positions are one
+                    const int a2 = lane_byte + __shfl_sync(0xffffffffu, o2, k);
+                    const uint2 c2 = hpel_row8(Ww, a2);
+                    p8 = make_uint2(__vavgu4(p8.x, c2.x), __vavgu4(p8.y, c2.y));
+                }
+                const int sad = warp_sum((int)sad4(p8.y, c8.y, sad4(p8.x, c8.x, 0)));
+                if (lane == k) mycost += sad;
+            }
+            best = warp_min(lane < 9 ? (((uint32_t)mycost << 4) | (uint32_t)lane) : 0xffffffffu);
+            bcost = best >> 4;
+            const int bk = (int)(best & 15);
+            ox = __shfl_sync(0xffffffffu, bk ? cq : ox, bk);
+            oy = __shfl_sync(0xffffffffu, bk ? cr : oy, bk);
         }
-        best = warp_min(lane < 9 ? (((uint32_t)mycost << 4) | (uint32_t)lane) : 0xffffffffu);
-        bcost = best >> 4;
-        const int bk = (int)(best & 15);
-        ox = __shfl_sync(0xffffffffu, bk ? cq : ox, bk);
-        oy = __shfl_sync(0xffffffffu, bk ? cr : oy, bk);
     }
     // intra or inter?  Intra16x16 estimated on the ORIGINAL picture (best of V / H / DC from original
     // neighbours): no reconstruction needed, so the decision stays macroblock-parallel (oracle:

@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(HP_WARPS * 32) hevc_p_recon_kernel(VcpGeom g, 
     const int mx = mbi % g.mbw, my = mbi / g.mbw;
     const int qp = b.qp[n], qpc = hevc_chroma_qp(qp);
     const size_t o = (size_t)gi * g.nmb + mbi;
+    if (b.mbtype[o] == VCP_MB_I16) return;   // flagged intra by the refine: coded by hevc_i_fix_kernel once we are done
     const short2 mv = b.mv[o];
     // luma prediction: full-sample vector, a copy of the reference
     {
@@ -318,7 +319,6 @@ __global__ void __launch_bounds__(HP_WARPS * 32) hevc_p_recon_kernel(VcpGeom g, 
         for (int z = 0; z < 8; z++) cbf_c |= ((cmask >> (4 * z)) & 1u) << z;
         b.cbp[o] = (uint8_t)cbf_y;
         b.modes[o] = (uint8_t)cbf_c;                       // cbf_cb in bits 0-3, cbf_cr in bits 4-7
-        b.mbtype[o] = 1;
     }
 }
 
@@ -394,23 +394,45 @@ __device__ void hv_encode_intra_cu(const VcpGeom& g, const VcpBufs& b, HvScratch
     }
 }
 
-// grid: x = slice, y = GOP
+// grid: x = slice, y = GOP.  FIX = false: IDR picture, every CU.  FIX = true: the CUs of a P picture that the
+// refine flagged intra (scene cuts), after hevc_p_recon_kernel -- they predict from the reconstruction around
+// them whatever its type; only anti-diagonals that hold flagged CUs cost a barrier, a slice without any leaves
+// at once.
+template <bool FIX>
 __global__ void __launch_bounds__(HI_WARPS * 32) hevc_i_recon_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
     __shared__ HvScratch scr[HI_WARPS];
+    __shared__ int todo;
+    __shared__ uint32_t dmask[32];   // up to 1024 anti-diagonals
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sl = blockIdx.x, gi = blockIdx.y + s.g0;
-    const int n = vcp_frame_of(s, gi);
-    const int slot = vcp_rec_slot(s, gi, s.t);
-    const int qp = b.qp[n], qpc = hevc_chroma_qp(qp);
     const int r0 = vcp_slice_first_row(sl, g.slices, g.mbh);
     const int r1 = sl + 1 < g.slices ? vcp_slice_first_row(sl + 1, g.slices, g.mbh) : g.mbh;
     const int rows = r1 - r0;
     const int ndiag = g.mbw + rows - 1;
+    if (FIX) {
+        if (threadIdx.x == 0) { todo = b.icount[(size_t)gi * g.slices + sl]; b.icount[(size_t)gi * g.slices + sl] = 0; }
+        if (threadIdx.x < 32) dmask[threadIdx.x] = 0;
+        __syncthreads();
+        if (!todo) return;
+        for (int i = threadIdx.x; i < rows * g.mbw; i += blockDim.x)
+            if (b.mbtype[(size_t)gi * g.nmb + r0 * g.mbw + i] == VCP_MB_I16) {
+                const int d = i % g.mbw + i / g.mbw;
+                atomicOr(&dmask[(d >> 5) & 31], 1u << (d & 31));
+            }
+        __syncthreads();
+    }
+    const int n = vcp_frame_of(s, gi);
+    const int slot = vcp_rec_slot(s, gi, s.t);
+    const int qp = b.qp[n], qpc = hevc_chroma_qp(qp);
     for (int d = 0; d < ndiag; d++) {
+        if (FIX && !((dmask[(d >> 5) & 31] >> (d & 31)) & 1)) continue;
         const int k0 = d - (g.mbw - 1) > 0 ? d - (g.mbw - 1) : 0;
         const int k1 = d < rows - 1 ? d : rows - 1;
-        for (int k = k0 + warp; k <= k1; k += HI_WARPS)
-            hv_encode_intra_cu(g, b, scr[warp], n, slot, gi, d - k, r0 + k, r0, qp, qpc, lane);
+        for (int k = k0 + warp; k <= k1; k += HI_WARPS) {
+            const int mx = d - k, my = r0 + k;
+            if (FIX && b.mbtype[(size_t)gi * g.nmb + my * g.mbw + mx] != VCP_MB_I16) continue;
+            hv_encode_intra_cu(g, b, scr[warp], n, slot, gi, mx, my, r0, qp, qpc, lane);
+        }
         __syncthreads();
     }
 }
@@ -470,7 +492,7 @@ __global__ void __launch_bounds__(128) hevc_cuinfo_kernel(VcpGeom g, VcpBufs b, 
 // 4-line edge segment is independent: thread = segment, no wavefront (unlike H.264's K4).  The thread holds the
 // 8 x 4 samples around its segment in registers (vertical: two words per row; horizontal: one word per row, the
 // four lines are the bytes), decides (bS, dE, dEp, dEq) and writes the block back.  Chroma (bS = 2 only, i.e. IDR
-// pictures; 16-sample luma grid) rides on the same thread.  Slices are not filtered across
+// pictures and intra CUs of P pictures; 16-sample luma grid) rides on the same thread.  Slices are not filtered across
 // (pps_loop_filter_across_slices_enabled_flag = 0).
 template <bool VERTICAL>
 __global__ void __launch_bounds__(256) hevc_deblock_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
@@ -487,7 +509,7 @@ __global__ void __launch_bounds__(256) hevc_deblock_kernel(VcpGeom g, VcpBufs b,
     const size_t base = (size_t)gi * g.nmb;
     const size_t oq = base + (size_t)(y >> 4) * g.mbw + (x >> 4), op = base + (size_t)(yp >> 4) * g.mbw + (xp >> 4);
     int bs;
-    if (s.t == 0) bs = 2;                                           // IDR: every CU is intra
+    if (s.t == 0 || b.mbtype[oq] == VCP_MB_I16 || b.mbtype[op] == VCP_MB_I16) bs = 2;   // intra on either side (IDR: every CU)
     else {
         const int zq = ((y >> 3) & 1) * 2 + ((x >> 3) & 1), zp = ((yp >> 3) & 1) * 2 + ((xp >> 3) & 1);
         if (((b.cbp[oq] >> zq) | (b.cbp[op] >> zp)) & 1) bs = 1;    // a transform block with coefficients on either side
@@ -602,7 +624,11 @@ void vcp_launch_hevc_p_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& 
 }
 void vcp_launch_hevc_i_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
     dim3 grid(g.slices, s.ngop);
-    hevc_i_recon_kernel<<<grid, HI_WARPS * 32, 0, st>>>(g, b, s);
+    hevc_i_recon_kernel<false><<<grid, HI_WARPS * 32, 0, st>>>(g, b, s);
+}
+void vcp_launch_hevc_i_fix(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
+    dim3 grid(g.slices, s.ngop);
+    hevc_i_recon_kernel<true><<<grid, HI_WARPS * 32, 0, st>>>(g, b, s);
 }
 void vcp_launch_hevc_cuinfo(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
     dim3 grid((g.nmb + 127) / 128, s.ngop);
