@@ -77,6 +77,7 @@ struct vcpenc_session {
     cudaStream_t gst[kMaxGroups] = {};          // one stream per GOP group (the recon chain)
     cudaStream_t est[kMaxGroups] = {};          // entropy coding of the group, off the chain
     static constexpr int kCabacStreams = 8;
+    int ncst = kCabacStreams;                    // streams per group actually used (the device has 32 hardware queues)
     cudaStream_t cst[kMaxGroups][kCabacStreams] = {};   // CABAC arithmetic coder batches: long-running, few
                                                         // warps each, independent -> they overlap each other
     cudaEvent_t ev_bins[kMaxGroups] = {};       // bins of the batch are complete
@@ -344,10 +345,18 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
         const char* e2 = getenv("VCPENC_BINS_PER_MB");
         if (e2 && atoi(e2) > 0) s->bins_per_mb = std::min(atoi(e2), 65536);
     }
+    {
+        // Streams are multiplexed onto at most 32 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS); streams that
+        // share a queue serialise behind each other's long coder batches.  4 fixed + 2 per group + the coder
+        // streams of all groups should fit: 8 per group with 2 groups, 5 with 4.
+        const char* e3 = getenv("VCPENC_CABAC_STREAMS");
+        const int fit = (32 - 4 - 2 * s->ngroups) / std::max(1, s->ngroups);
+        s->ncst = std::max(1, std::min((int)vcpenc_session::kCabacStreams, e3 && atoi(e3) > 0 ? atoi(e3) : fit));
+    }
     for (int i = 0; i < s->ngroups; i++) {
         CKS(cudaStreamCreateWithPriority(&s->gst[i], cudaStreamNonBlocking, prio_chain));
         CKS(cudaStreamCreateWithPriority(&s->est[i], cudaStreamNonBlocking, prio_entropy));
-        if (pp->entropy) for (int q = 0; q < vcpenc_session::kCabacStreams; q++) CKS(cudaStreamCreateWithPriority(&s->cst[i][q], cudaStreamNonBlocking, prio_entropy));
+        if (pp->entropy) for (int q = 0; q < s->ncst; q++) CKS(cudaStreamCreateWithPriority(&s->cst[i][q], cudaStreamNonBlocking, prio_entropy));
         CKS(cudaEventCreateWithFlags(&s->ev_bins[i], cudaEventDisableTiming));
         CKS(cudaEventCreateWithFlags(&s->gev[i], cudaEventDisableTiming));
         for (int q = 0; q < 2; q++) {
@@ -637,7 +646,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 const int next_active = std::min(gB, (N - (t + 1) + gop - 1) / gop) - gA;   // GOPs of the group with a picture t+1
                 if ((t + 1) % kCabacBatch == 0 || t == last_t || next_active <= 0) {
                     const int t0 = t / kCabacBatch * kCabacBatch;
-                    cudaStream_t sc = s->profile ? s->st : s->cst[k][(t / kCabacBatch) % vcpenc_session::kCabacStreams];
+                    cudaStream_t sc = s->profile ? s->st : s->cst[k][(t / kCabacBatch) % s->ncst];
                     VcpStep sb = sp;
                     sb.ngop = std::min(gB, (N - t0 + gop - 1) / gop) - gA;   // GOPs of the group that own picture t0
                     if (!s->profile) { CK(cudaEventRecord(s->ev_bins[k], se)); CK(cudaStreamWaitEvent(sc, s->ev_bins[k], 0)); }
@@ -666,7 +675,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
             CK(cudaStreamWaitEvent(s->st, s->gev[k], 0));
             CK(cudaEventRecord(s->gev[k], s->est[k]));
             CK(cudaStreamWaitEvent(s->st, s->gev[k], 0));
-            if (g.cabac) for (int q = 0; q < vcpenc_session::kCabacStreams; q++) {
+            if (g.cabac) for (int q = 0; q < s->ncst; q++) {
                 CK(cudaEventRecord(s->gev[k], s->cst[k][q]));
                 CK(cudaStreamWaitEvent(s->st, s->gev[k], 0));
             }
