@@ -228,7 +228,7 @@ int vcpenc_device_count(void) {
     return n;
 }
 
-const char* vcpenc_version(void) { return "vcpenc 0.2 (sm_100a, H.264 CAVLC/CABAC I/P)"; }
+const char* vcpenc_version(void) { return "vcpenc 0.3 (sm_100a, H.264 Baseline/Main/High + HEVC Main, I/P)"; }
 
 void vcpenc_default_params(vcpenc_params* p) {
     memset(p, 0, sizeof *p);
