@@ -13,7 +13,8 @@
  *   - transform blocks: luma 8x8 (the 16x16 root is split because MaxTb = 8), chroma 4x4; DCT only
  *   - intra: DC prediction per transform block (mode signalled through the MPM list), chroma derived; every CU of an
  *     IDR picture, and CUs of P pictures where the refine finds intra cheaper (scene cuts)
- *   - inter: one 16x16 PU, full-sample luma vectors (chroma lands on half samples: 4-tap filter),
+ *   - inter: one 16x16 PU, full-sample luma vectors (chroma lands on half samples: 4-tap filter); with
+ *     params.hevc_subpel also the 8 half-sample neighbours (8-tap luma filter) -- oracle only so far,
  *     AMVP with spatial candidates, merge (1 candidate) / skip
  *   - CABAC (same engine as H.264 9.3.4.2; HEVC context tables 9-5..9-37), no sign hiding
  *   - in-loop deblocking (all vertical edges, then all horizontal ones; not across slices) unless deblock_idc = 1;
@@ -317,21 +318,44 @@ static void hevc_encode_intra_cu(HEnc* h, int cx, int cy) {
     }
 }
 
-/* chroma sample interpolation (8.5.3.3.3.2) for full-sample luma vectors: fractions 0 or 4 (of 8) */
+/* luma sample interpolation (8.5.3.3.3.1), 8-bit: shift1 = 0, shift2 = 6, then the default weighted prediction
+ * (x + 32) >> 6.  mv in quarter samples; the encoder uses fractions 0 and 2 (hevc_subpel), the tables are complete. */
+static const int hevc_lf[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};
+static int hevc_luma_pred(const uint8_t* ref, int rs, int x, int y, int mvx, int mvy) {
+    const int fx = mvx & 3, fy = mvy & 3;
+    const uint8_t* p = ref + (ptrdiff_t)(y + (mvy >> 2)) * rs + x + (mvx >> 2);
+    int v;
+    if (!fx && !fy) return p[0];
+    if (!fy) { v = 0; for (int i = 0; i < 8; i++) v += hevc_lf[fx][i] * p[i - 3]; }
+    else if (!fx) { v = 0; for (int i = 0; i < 8; i++) v += hevc_lf[fy][i] * p[(ptrdiff_t)(i - 3) * rs]; }
+    else {
+        v = 0;
+        for (int i = 0; i < 8; i++) {
+            int t = 0;
+            for (int j = 0; j < 8; j++) t += hevc_lf[fx][j] * p[(ptrdiff_t)(i - 3) * rs + j - 3];
+            v += hevc_lf[fy][i] * t;
+        }
+        v >>= 6;
+    }
+    return vcp_clip255((v + 32) >> 6);
+}
+/* chroma sample interpolation (8.5.3.3.3.2): the luma vector in eighths of a chroma sample, 4-tap filters */
 static void hevc_mc_chroma(const uint8_t* ref, int rs, int x0, int y0, int mvx, int mvy, uint8_t* dst /* 8x8 */) {
-    static const int f4[4] = {-4, 36, 36, -4};
+    static const int fc[8][4] = {{0, 64, 0, 0}, {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4}, {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2}};
     const int ix = mvx >> 3, iy = mvy >> 3, fx = mvx & 7, fy = mvy & 7;
+    const int* f4 = fc[fx];
+    const int* g4 = fc[fy];
     for (int y = 0; y < 8; y++)
         for (int x = 0; x < 8; x++) {
             const uint8_t* p = ref + (ptrdiff_t)(y0 + y + iy) * rs + x0 + x + ix;
             int v;
             if (!fx && !fy) v = p[0] << 6;
             else if (!fy) v = f4[0] * p[-1] + f4[1] * p[0] + f4[2] * p[1] + f4[3] * p[2];
-            else if (!fx) v = f4[0] * p[-rs] + f4[1] * p[0] + f4[2] * p[rs] + f4[3] * p[2 * rs];
+            else if (!fx) v = g4[0] * p[-rs] + g4[1] * p[0] + g4[2] * p[rs] + g4[3] * p[2 * rs];
             else {
                 int t[4];
                 for (int k = 0; k < 4; k++) { const uint8_t* q = p + (ptrdiff_t)(k - 1) * rs; t[k] = f4[0] * q[-1] + f4[1] * q[0] + f4[2] * q[1] + f4[3] * q[2]; }
-                v = (f4[0] * t[0] + f4[1] * t[1] + f4[2] * t[2] + f4[3] * t[3]) >> 6;
+                v = (g4[0] * t[0] + g4[1] * t[1] + g4[2] * t[2] + g4[3] * t[3]) >> 6;
             }
             dst[y * 8 + x] = (uint8_t)vcp_clip255((v + 32) >> 6);
         }
@@ -363,9 +387,33 @@ static int hevc_refine_cu(HEnc* h, int cx, int cy, int16_t mv[2]) {
         const uint32_t key = ((uint32_t)cost << 4) | (uint32_t)k;
         if (key < best) best = key;
     }
-    mv[0] = (int16_t)(4 * cand[best & 15][0]); mv[1] = (int16_t)(4 * cand[best & 15][1]);
-    const uint32_t bcost = best >> 4;
+    int bx = 4 * cand[best & 15][0], by = 4 * cand[best & 15][1];
+    uint32_t bcost = best >> 4;
+    mv[0] = (int16_t)bx; mv[1] = (int16_t)by;
     if (bcost < VCP_SUBPEL_SKIP_COST) return 0;
+    if (e->p.hevc_subpel) {
+        /* half-sample neighbours of the best full-sample position: raster order, strict improvement (the same rule
+         * as the H.264 refine).  Each position of each reference picture has ONE interpolated value, so a device
+         * implementation can take it from three half-sample planes built once per picture. */
+        uint32_t sb = (bcost << 4) | 0;
+        int k = 1;
+        const int ox = bx, oy = by;
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                if (!dx && !dy) continue;
+                const int vx = ox + 2 * dx, vy = oy + 2 * dy;
+                int sad = 0;
+                for (int y = 0; y < 16; y++)
+                    for (int x = 0; x < 16; x++)
+                        sad += abs(c[(size_t)y * e->cur.ys + x] - hevc_luma_pred(h->ref->y, h->ref->ys, px + x, py + y, vx, vy));
+                const int cost = sad + lam * (vcp_se_len(vx - pmx) + vcp_se_len(vy - pmy));
+                const uint32_t key = ((uint32_t)cost << 4) | (uint32_t)k;
+                if (key < sb) { sb = key; bx = vx; by = vy; }
+                k++;
+            }
+        bcost = sb >> 4;
+        mv[0] = (int16_t)bx; mv[1] = (int16_t)by;
+    }
     return vcp_intra_wins(intra_estimate(e, cx, cy), (int)bcost, lam) != 0;
 }
 
@@ -382,7 +430,7 @@ static void hevc_encode_inter_cu(HEnc* h, int cx, int cy) {
         const int xl = 16 * cx + 8 * (z & 1), yl = 16 * cy + 8 * (z >> 1);
         uint8_t pred[64];
         for (int y = 0; y < 8; y++)
-            for (int x = 0; x < 8; x++) pred[y * 8 + x] = h->ref->y[(size_t)(yl + y + (mvy >> 2)) * h->ref->ys + xl + x + (mvx >> 2)];
+            for (int x = 0; x < 8; x++) pred[y * 8 + x] = (uint8_t)hevc_luma_pred(h->ref->y, h->ref->ys, xl + x, yl + y, mvx, mvy);
         cu->cbf_y[z] = (uint8_t)hevc_code_block(h, 0, xl, yl, 8, pred, 0, cu->lv_y[z]);
         uint8_t pc[16];
         for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) pc[y * 4 + x] = pu[(4 * (z >> 1) + y) * 8 + 4 * (z & 1) + x];

@@ -344,6 +344,37 @@ def test_hevc_oracle_intra_cus_in_p_pictures():
         assert arbiter.psnr(dec[4][0], synth.split_planes(cut[4], w, h)[0]) > 34
 
 
+def test_hevc_oracle_half_sample_motion():
+    """params.hevc_subpel (oracle only this round): 8-tap luma interpolation + the full set of 4-tap chroma phases.
+    The decoder must agree bit-exactly, and on a clip that moves by half samples the tool must pay off."""
+    if not arbiter.available():
+        pytest.skip("bundled FFmpeg decoder not present")
+    w, h, n = 320, 192, 6
+    rng = np.random.default_rng(3)
+    big = rng.integers(0, 256, (2 * h + 64, 2 * w + 64)).astype(np.float64)
+    for _ in range(6):                                    # cheap low-pass: box blur, separable
+        big = (big + np.roll(big, 1, 0) + np.roll(big, -1, 0) + np.roll(big, 1, 1) + np.roll(big, -1, 1)) / 5.0
+    big = (big - big.min()) / (big.max() - big.min()) * 255.0
+    clip = np.stack([np.concatenate([np.clip(np.rint(big[i:i + 2 * h:2, 3 * i:3 * i + 2 * w:2]), 0, 255).astype(np.uint8).ravel(),
+                                     np.full(w * h // 2, 128, np.uint8)]) for i in range(n)])
+    size = {}
+    for sub in (0, 1):
+        for kw in (dict(slices=1), dict(slices=3, deblock_idc=1)):
+            r = pyoracle.encode_hevc(pyoracle.make_params(w, h, codec=1, gop=n, qp_i=26, qp_p=28, hevc_subpel=sub, **kw), clip)
+            dec = arbiter.decode_annexb_hevc(r["stream"])
+            assert len(dec) == n
+            for i in range(n):
+                assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i]), (sub, kw, i)
+            size[(sub, kw["slices"])] = len(r["stream"])
+    assert size[(1, 1)] < 0.7 * size[(0, 1)] and size[(1, 3)] < 0.7 * size[(0, 3)]
+    # the standard clip (integer motion, noise patch, scene content): still exact
+    clip2 = synth.make_clip(w, h, 6, seed=4)
+    r = pyoracle.encode_hevc(pyoracle.make_params(w, h, codec=1, gop=6, qp_i=26, qp_p=28, hevc_subpel=1, slices=2), clip2)
+    dec = arbiter.decode_annexb_hevc(r["stream"])
+    for i in range(6):
+        assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i])
+
+
 def test_hevc_tables_match_decoder_rodata():
     """CABAC initValues (tables 9-5..9-37) typed in the oracle must appear in the decoder's own tables."""
     import glob

@@ -129,6 +129,7 @@ int dev_alloc(vcpenc_session* s, T** p, size_t count, char* err, size_t errlen) 
 
 int check_params(const vcpenc_params& p, char* err, size_t errlen) {
     if (p.codec != VCPENC_CODEC_H264 && p.codec != VCPENC_CODEC_HEVC) { set_err(err, errlen, "unknown codec %d", p.codec); return VCPENC_E_ARGS; }
+    if (p.hevc_subpel) { set_err(err, errlen, "HEVC half-sample motion is implemented in the oracle only (device path: next round)"); return VCPENC_E_UNSUPPORTED; }
     if (p.entropy < 0 || p.entropy > 1) { set_err(err, errlen, "bad entropy coder %d", p.entropy); return VCPENC_E_ARGS; }
     if (p.width < 16 || p.height < 16 || (p.width & 1) || (p.height & 1)) { set_err(err, errlen, "unsupported picture size %dx%d", p.width, p.height); return VCPENC_E_ARGS; }
     if (p.gop < 1 || p.slices < 0 || p.slices > (p.height + 15) / 16) { set_err(err, errlen, "bad gop/slices"); return VCPENC_E_ARGS; }
