@@ -341,10 +341,9 @@ static int hevc_luma_pred(const uint8_t* ref, int rs, int x, int y, int mvx, int
 }
 /* chroma sample interpolation (8.5.3.3.3.2): the luma vector in eighths of a chroma sample, 4-tap filters */
 static void hevc_mc_chroma(const uint8_t* ref, int rs, int x0, int y0, int mvx, int mvy, uint8_t* dst /* 8x8 */) {
-    static const int fc[8][4] = {{0, 64, 0, 0}, {-2, 58, 10, -2}, {-4, 54, 16, -2}, {-6, 46, 28, -4}, {-4, 36, 36, -4}, {-4, 28, 46, -6}, {-2, 16, 54, -4}, {-2, 10, 58, -2}};
     const int ix = mvx >> 3, iy = mvy >> 3, fx = mvx & 7, fy = mvy & 7;
-    const int* f4 = fc[fx];
-    const int* g4 = fc[fy];
+    const int8_t* f4 = hevc_chroma_filter[fx];
+    const int8_t* g4 = hevc_chroma_filter[fy];
     for (int y = 0; y < 8; y++)
         for (int x = 0; x < 8; x++) {
             const uint8_t* p = ref + (ptrdiff_t)(y0 + y + iy) * rs + x0 + x + ix;

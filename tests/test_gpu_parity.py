@@ -366,6 +366,39 @@ def test_hevc_intra_cus_in_p_pictures(built):
                 assert np.array_equal(_flat(dec[i]), got["recon"][i])
 
 
+def test_hevc_half_sample_motion(built):
+    """params.hevc_subpel: 8-tap half-sample planes per picture (k2_hpel.cu), half-sample step of the shared refine,
+    plane fetch + four chroma phases in hevc_p_recon -- byte-identical to the oracle, on a clip that moves by half
+    samples, on the standard clip and across a scene cut."""
+    from oracle import pyoracle
+    w, h, n = 320, 192, 6
+    rng = np.random.default_rng(3)
+    big = rng.integers(0, 256, (2 * h + 64, 2 * w + 64)).astype(np.float64)
+    for _ in range(6):
+        big = (big + np.roll(big, 1, 0) + np.roll(big, -1, 0) + np.roll(big, 1, 1) + np.roll(big, -1, 1)) / 5.0
+    big = (big - big.min()) / (big.max() - big.min()) * 255.0
+    half = np.stack([np.concatenate([np.clip(np.rint(big[i:i + 2 * h:2, 3 * i:3 * i + 2 * w:2]), 0, 255).astype(np.uint8).ravel(),
+                                     np.full(w * h // 2, 128, np.uint8)]) for i in range(n)])
+    a = synth.make_clip(w, h, 4, seed=1)
+    cut = np.concatenate([a, np.roll(a, 7777, axis=1)[:2], synth.make_clip(w, h, 3, seed=77, start=9)])
+    for clip, kw in ((half, dict(slices=1)), (half, dict(slices=3, deblock_idc=1)), (synth.make_clip(w, h, 8, seed=4), dict(slices=2)),
+                     (cut, dict(slices=2)), (synth.make_clip(208, 114, 5, seed=9), dict(slices=1))):
+        cw, chh = (208, 114) if clip.shape[1] == 208 * 114 * 3 // 2 else (w, h)
+        gop = 60 if clip is cut else clip.shape[0]
+        ref = pyoracle.encode_hevc(pyoracle.make_params(cw, chh, codec=1, gop=gop, qp_i=26, qp_p=28, hevc_subpel=1, **kw), clip)
+        p = api.default_params(cw, chh, codec=1, gop=gop, qp_i=26, qp_p=28, hevc_subpel=1, debug=1, **kw)
+        with api.Session(p, clip.shape[0]) as s:
+            s.upload(clip)
+            s.encode()
+            got = s.download(want_recon=True)
+            dbg = s.debug_mbs()
+        bad = [i for i in range(clip.shape[0]) if not np.array_equal(got["recon"][i], ref["recon"][i])]
+        assert not bad, ("recon differs", kw, bad)
+        assert got["stream"].tobytes() == ref["stream"], kw
+        if clip is half:
+            assert (dbg["mv_final"] & 3).any()             # half-sample vectors were chosen
+
+
 def test_streamed_upload_is_identical(built):
     """upload(wait=False): the encode starts each GOP group when its frames have landed; same bytes as the
     synchronous upload, for both codecs, also when the session is reused and when GOPs do not fill the groups."""

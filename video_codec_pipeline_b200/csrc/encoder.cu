@@ -129,7 +129,7 @@ int dev_alloc(vcpenc_session* s, T** p, size_t count, char* err, size_t errlen) 
 
 int check_params(const vcpenc_params& p, char* err, size_t errlen) {
     if (p.codec != VCPENC_CODEC_H264 && p.codec != VCPENC_CODEC_HEVC) { set_err(err, errlen, "unknown codec %d", p.codec); return VCPENC_E_ARGS; }
-    if (p.hevc_subpel) { set_err(err, errlen, "HEVC half-sample motion is implemented in the oracle only (device path: next round)"); return VCPENC_E_UNSUPPORTED; }
+    if (p.hevc_subpel < 0 || p.hevc_subpel > 1) { set_err(err, errlen, "bad hevc_subpel %d", p.hevc_subpel); return VCPENC_E_ARGS; }
     if (p.entropy < 0 || p.entropy > 1) { set_err(err, errlen, "bad entropy coder %d", p.entropy); return VCPENC_E_ARGS; }
     if (p.width < 16 || p.height < 16 || (p.width & 1) || (p.height & 1)) { set_err(err, errlen, "unsupported picture size %dx%d", p.width, p.height); return VCPENC_E_ARGS; }
     if (p.gop < 1 || p.slices < 0 || p.slices > (p.height + 15) / 16) { set_err(err, errlen, "bad gop/slices"); return VCPENC_E_ARGS; }
@@ -306,6 +306,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     g.hoff = VCP_PAD1 * g.hs + VCP_PAD1;
     g.slices = pp->slices; g.deblock_idc = pp->deblock_idc; g.cabac = pp->entropy; g.t8x8 = pp->transform8x8 ? 1 : 0;
     g.hevc = pp->codec == VCPENC_CODEC_HEVC;
+    g.hevc_subpel = g.hevc && pp->hevc_subpel;
     g.rc_abr = pp->rc_mode == VCPENC_RC_ABR;
     g.rc_bitrate = pp->bitrate; g.fps_num = pp->fps_num; g.fps_den = pp->fps_den;
     g.rc_qp0 = g.rc_abr ? vcp_rc_initial_qp(pp->bitrate, pp->fps_num, pp->fps_den, pp->width, pp->height) : 0;
@@ -667,7 +668,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
             }
             { Prof pr(s, VCPENC_K_PAD, 1, st); vcp_launch_pad(g, bt, sp, st); }
             // half-sample planes of this reconstruction for the next picture's search and prediction
-            if (t + 1 < gop && t + 1 < N && !g.hevc) { Prof pr(s, VCPENC_K_HPEL, 1, st); vcp_launch_hpel(g, bt, sp, st); }
+            if (t + 1 < gop && t + 1 < N && (!g.hevc || g.hevc_subpel)) { Prof pr(s, VCPENC_K_HPEL, 1, st); vcp_launch_hpel(g, bt, sp, st); }
         }
     }
     if (!s->profile)

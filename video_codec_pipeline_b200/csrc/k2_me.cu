@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
     }
 
     int ox = 0, oy = 0;
-    if (!g.hevc) {   // the HEVC path keeps luma vectors on full samples (k6_hevc.cu)
+    if (!g.hevc || g.hevc_subpel) {   // HEVC: full samples only, or (hevc_subpel) the half-sample step alone
         // half-pel then quarter-pel neighbours from the half-sample planes of the reference, staged
         // once around the best full-pel position
         __syncwarp();
@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
         const int lane_byte = (row + 1) * 24 + mis + 1 + hx;   // this lane's first sample at displacement 0 inside a plane window
 #pragma unroll
         for (int step = 2; step >= 1; step--) {
+            if (step == 1 && g.hevc) continue;   // HEVC quarter positions are not averages of half-sample planes
             // lane k (1..8): candidate k -> byte offsets of its two grid samples, and its vector cost
             int o1 = 0, o2 = 0, cq = 0, cr = 0;
             {

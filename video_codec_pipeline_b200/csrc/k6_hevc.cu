@@ -20,6 +20,7 @@
 // the four TUs, bit 4 = merge_flag, bit 5 = mvp_l0_flag; modes bits 0-3 = cbf_cb, 4-7 = cbf_cr; levels:
 // luma [z*64 + y*8 + x], Cb [256 + z*16 + y*4 + x], Cr [320 + z*16 + y*4 + x].
 #include "vcp_dev.cuh"
+#include "vcp_luma_interp.cuh"
 
 #define VCP_TAB static __device__ const
 #include "hevc_tables.h"
@@ -261,13 +262,18 @@ __global__ void __launch_bounds__(HP_WARPS * 32) hevc_p_recon_kernel(VcpGeom g, 
     // luma prediction: full-sample vector, a copy of the reference
     {
         const int row = lane >> 1, hx = (lane & 1) * 8;
-        const uint8_t* r = vcp_rec_luma(b, g, rslot) + g.yoff + (ptrdiff_t)(16 * my + row + (mv.y >> 2)) * g.ys + 16 * mx + hx + (mv.x >> 2);
-        *reinterpret_cast<uint2*>(&S.pred[row][hx]) = ld8_unaligned(r);
+        const uint8_t* r0 = vcp_rec_luma(b, g, rslot) + g.yoff + (ptrdiff_t)(16 * my + row) * g.ys + 16 * mx + hx;
+        // half-sample vectors (hevc_subpel) read the 8-tap planes of the reference; full-sample ones the picture itself
+        *reinterpret_cast<uint2*>(&S.pred[row][hx]) = g.hevc_subpel ? hpel_fetch8(r0, mv.x, mv.y, g.ys, g.ysize)
+                                                                    : ld8_unaligned(r0 + (ptrdiff_t)(mv.y >> 2) * g.ys + (mv.x >> 2));
     }
-    // chroma prediction (8.5.3.3.3.2): the luma vector in 1/8 chroma samples -> fractions 0 or 4, 4-tap filter (-4, 36, 36, -4)
+    // chroma prediction (8.5.3.3.3.2): the luma vector in 1/8 chroma samples (fractions 0 / 4 with full-sample luma
+    // vectors, 0 / 2 / 4 / 6 with half-sample ones), 4-tap filters, horizontal then vertical
     {
         const int pl = lane >> 4, row = (lane >> 1) & 7, x0 = (lane & 1) * 4;
         const int ix = mv.x >> 3, iy = mv.y >> 3, fx = mv.x & 7, fy = mv.y & 7;
+        const int f0 = hevc_chroma_filter[fx][0], f1 = hevc_chroma_filter[fx][1], f2 = hevc_chroma_filter[fx][2], f3 = hevc_chroma_filter[fx][3];
+        const int g0 = hevc_chroma_filter[fy][0], g1 = hevc_chroma_filter[fy][1], g2 = hevc_chroma_filter[fy][2], g3 = hevc_chroma_filter[fy][3];
         const uint8_t* base = (pl ? b.rec_v : b.rec_u) + (size_t)rslot * g.csize + g.coff + (ptrdiff_t)(8 * my + row + iy) * g.cs + 8 * mx + x0 + ix;
         uint32_t outw = 0;
 #pragma unroll
@@ -275,13 +281,13 @@ __global__ void __launch_bounds__(HP_WARPS * 32) hevc_p_recon_kernel(VcpGeom g, 
             const uint8_t* p = base + x;
             int v;
             if (!fx && !fy) v = (int)p[0] << 6;
-            else if (!fy) v = -4 * p[-1] + 36 * p[0] + 36 * p[1] - 4 * p[2];
-            else if (!fx) v = -4 * p[-g.cs] + 36 * p[0] + 36 * p[g.cs] - 4 * p[2 * g.cs];
+            else if (!fy) v = f0 * p[-1] + f1 * p[0] + f2 * p[1] + f3 * p[2];
+            else if (!fx) v = g0 * p[-g.cs] + g1 * p[0] + g2 * p[g.cs] + g3 * p[2 * g.cs];
             else {
                 int t[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) { const uint8_t* q = p + (ptrdiff_t)(k - 1) * g.cs; t[k] = -4 * q[-1] + 36 * q[0] + 36 * q[1] - 4 * q[2]; }
-                v = (-4 * t[0] + 36 * t[1] + 36 * t[2] - 4 * t[3]) >> 6;
+                for (int k = 0; k < 4; k++) { const uint8_t* q = p + (ptrdiff_t)(k - 1) * g.cs; t[k] = f0 * q[-1] + f1 * q[0] + f2 * q[1] + f3 * q[2]; }
+                v = (g0 * t[0] + g1 * t[1] + g2 * t[2] + g3 * t[3]) >> 6;
             }
             outw |= (uint32_t)vcp_clip255((v + 32) >> 6) << (8 * x);
         }

@@ -28,6 +28,7 @@ struct VcpGeom {
     int cabac;         // entropy_coding_mode_flag
     int t8x8;          // transform_8x8_mode_flag (High profile)
     int hevc;          // codec: 0 H.264, 1 HEVC (k6_hevc.cu; the motion search and the arithmetic coder are shared)
+    int hevc_subpel;   // HEVC: half-sample luma motion from the 8-tap planes of k2_hpel.cu
     // rate control (VCPENC_RC_ABR): see vcp_algo.h
     int rc_abr, rc_qp0, rc_bitrate, fps_num, fps_den;
 };
