@@ -86,8 +86,8 @@ typedef struct vcpenc_params {
                                   the audio is dropped (else VCPENC_E_AUDIO)         */
     int32_t transform8x8;      /* 1: High profile, transform_8x8_mode_flag: inter macroblocks use the
                                   8x8 integer transform (-profile:v high, the libx264 default)  */
-    int32_t hevc_subpel;       /* HEVC: 1 = half-sample luma motion (8-tap interpolation).  The oracle implements and pins
-                                  it (oracle/hevc_oracle.inc.c); the device path does not yet: VCPENC_E_UNSUPPORTED */
+    int32_t hevc_subpel;       /* HEVC: 1 = half-sample luma motion (8-tap interpolation planes per picture); set by
+                                  the argument parser for libx265 / hevc_nvenc                                  */
     int32_t reserved[7];
 } vcpenc_params;
 
