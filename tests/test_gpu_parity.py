@@ -20,6 +20,7 @@ from video_codec_pipeline_b200.shard import gop_ranges
 pytestmark = pytest.mark.gpu
 
 GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "h264_golden.json")))
+GOLD_HEVC = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hevc_golden.json")))
 
 
 def _flat(planes):
@@ -97,6 +98,17 @@ def test_cuda_matches_golden(built, g):
                            slices=g["slices"], deblock_idc=g["deblock_idc"], entropy=g.get("entropy", 0),
                            transform8x8=g.get("transform8x8", 0))
     got = api.encode_frames(p, clip, want_recon=True)             # host buffers in, host buffers out
+    assert [x[1] for x in got["info"]] == g["frame_sizes"]
+    assert hashlib.sha256(got["stream"].tobytes()).hexdigest() == g["stream_sha256"]
+    assert hashlib.sha256(got["recon"].tobytes()).hexdigest() == g["recon_sha256"]
+
+
+@pytest.mark.parametrize("g", GOLD_HEVC, ids=lambda g: "hevc_%dx%d_q%d_s%d_d%d_h%d" % (g["w"], g["h"], g["qp"], g["slices"], g["deblock_idc"], g["hevc_subpel"]))
+def test_hevc_cuda_matches_golden(built, g):
+    clip = synth.make_clip(g["w"], g["h"], g["frames"], seed=g["seed"])
+    p = api.default_params(g["w"], g["h"], codec=1, gop=g["gop"], qp_i=max(0, g["qp"] - 2), qp_p=g["qp"], slices=g["slices"],
+                           deblock_idc=g["deblock_idc"], hevc_subpel=g["hevc_subpel"], debug=1)
+    got = api.encode_frames(p, clip, want_recon=True)
     assert [x[1] for x in got["info"]] == g["frame_sizes"]
     assert hashlib.sha256(got["stream"].tobytes()).hexdigest() == g["stream_sha256"]
     assert hashlib.sha256(got["recon"].tobytes()).hexdigest() == g["recon_sha256"]

@@ -146,6 +146,21 @@ def test_oracle_matches_golden(g):
     assert hashlib.sha256(r["recon"].tobytes()).hexdigest() == g["recon_sha256"]
 
 
+GOLD_HEVC = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hevc_golden.json")))
+
+
+@pytest.mark.parametrize("g", GOLD_HEVC, ids=lambda g: "hevc_%dx%d_q%d_s%d_d%d_h%d" % (g["w"], g["h"], g["qp"], g["slices"], g["deblock_idc"], g["hevc_subpel"]))
+def test_hevc_oracle_matches_golden(g):
+    clip = synth.make_clip(g["w"], g["h"], g["frames"], seed=g["seed"])
+    assert hashlib.sha256(clip.tobytes()).hexdigest() == g["clip_sha256"], "synthetic clip generator drifted"
+    p = pyoracle.make_params(g["w"], g["h"], codec=1, gop=g["gop"], qp_i=max(0, g["qp"] - 2), qp_p=g["qp"],
+                             slices=g["slices"], deblock_idc=g["deblock_idc"], hevc_subpel=g["hevc_subpel"])
+    r = pyoracle.encode_hevc(p, clip)
+    assert [x[1] for x in r["info"]] == g["frame_sizes"]
+    assert hashlib.sha256(r["stream"]).hexdigest() == g["stream_sha256"]
+    assert hashlib.sha256(r["recon"].tobytes()).hexdigest() == g["recon_sha256"]
+
+
 def test_oracle_edge_cases():
     # single frame; GOP of 1 (all IDR); max slices = one per macroblock row
     w, h = 64, 64

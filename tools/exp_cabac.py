@@ -1,7 +1,10 @@
 """Developer script: step time of the 1080p CABAC configuration under experiment knobs (GPU)."""
+import os
 import sys
+
 import numpy as np
-sys.path.insert(0, "/root/repo")
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from video_codec_pipeline_b200 import api, synth
 w, h, gop, gops = 1920, 1080, 60, 32
 a = synth.make_clip(w, h, gop, seed=1080)
