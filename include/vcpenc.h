@@ -88,7 +88,9 @@ typedef struct vcpenc_params {
                                   8x8 integer transform (-profile:v high, the libx264 default)  */
     int32_t hevc_subpel;       /* HEVC: 1 = half-sample luma motion (8-tap interpolation planes per picture); set by
                                   the argument parser for libx265 / hevc_nvenc                                  */
-    int32_t reserved[7];
+    int32_t hevc_sao;          /* HEVC: 1 = sample adaptive offset on luma (edge offsets, one decision per coding tree
+                                  block, taken on the deblocked picture)                                         */
+    int32_t reserved[6];
 } vcpenc_params;
 
 /* per coded picture, filled by the encode calls */

@@ -233,6 +233,9 @@ typedef struct {
     HCU* cus;
     int qp, qpc, idr;
     Frame* rec; const Frame* ref;
+    uint8_t* sao_type;        /* per CTB: 0 off, 1 + edge class */
+    int8_t* sao_off;          /* per CTB: four offsets (categories 1..4) */
+    uint8_t* sao_tmp;         /* copy of the deblocked luma picture while offsets are applied */
 } HEnc;
 
 /* availability of the 4x4 luma unit at (x,y) for a block at (xc,yc) decoded in z-order inside 16x16 CTBs (6.4.1) */
@@ -554,6 +557,72 @@ static void hevc_deblock_picture(HEnc* h) {
             }
 }
 
+/* ---- sample adaptive offset (8.7.3), luma edge offsets only ------------------------------------------------
+ * Decision and application both work on the DEBLOCKED picture; a sample whose neighbour (along the class
+ * direction) lies outside the picture or in another slice keeps its value (slices are never filtered across).
+ * Per CTB: statistics of (source - deblocked) per class and category, offsets = clipped rounded means, the class
+ * with the lowest distortion + rate cost if it beats "off" (vcp_algo.h).  CTB-parallel on the device. */
+static const int hevc_sao_dx[4][2] = {{-1, 1}, {0, 0}, {-1, 1}, {1, -1}}, hevc_sao_dy[4][2] = {{0, 0}, {-1, 1}, {-1, 1}, {-1, 1}};
+static int hevc_sao_category(const HEnc* h, const uint8_t* d, int ds, int x, int y, int cls) {
+    const Enc* e = h->e;
+    int sgn = 0;
+    for (int k = 0; k < 2; k++) {
+        const int nx = x + hevc_sao_dx[cls][k], ny = y + hevc_sao_dy[cls][k];
+        if (nx < 0 || ny < 0 || nx >= e->cw || ny >= e->ch) return 0;
+        if (slice_of_row(e, ny >> 4) != slice_of_row(e, y >> 4)) return 0;
+        const int c = d[(size_t)y * ds + x], n = d[(size_t)ny * ds + nx];
+        sgn += c < n ? -1 : c > n ? 1 : 0;
+    }
+    return sgn == -2 ? 1 : sgn == -1 ? 2 : sgn == 1 ? 3 : sgn == 2 ? 4 : 0;
+}
+static void hevc_sao_picture(HEnc* h) {
+    const Enc* e = h->e;
+    Frame* f = h->rec;
+    const int lam = vcp_lambda(h->qp), lam2 = lam * lam;
+    for (int y = 0; y < e->ch; y++) memcpy(h->sao_tmp + (size_t)y * e->cw, f->y + (size_t)y * f->ys, (size_t)e->cw);
+    const uint8_t* d = h->sao_tmp;
+    for (int cy = 0; cy < e->mbh; cy++)
+        for (int cx = 0; cx < e->mbw; cx++) {
+            const int i = cy * e->mbw + cx;
+            long long best = lam2;                 /* "off": one bin */
+            h->sao_type[i] = 0;
+            for (int cls = 0; cls < 4; cls++) {
+                int sum[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0}, off[4];
+                for (int y = 16 * cy; y < 16 * cy + 16; y++)
+                    for (int x = 16 * cx; x < 16 * cx + 16; x++) {
+                        const int k = hevc_sao_category(h, d, e->cw, x, y, cls);
+                        if (k) { sum[k - 1] += e->cur.y[(size_t)y * e->cur.ys + x] - d[(size_t)y * e->cw + x]; cnt[k - 1]++; }
+                    }
+                const long long c = vcp_sao_class_cost(sum, cnt, lam2, off);
+                if (c < best && (off[0] | off[1] | off[2] | off[3])) {
+                    best = c; h->sao_type[i] = (uint8_t)(1 + cls);
+                    for (int k = 0; k < 4; k++) h->sao_off[4 * i + k] = (int8_t)off[k];
+                }
+            }
+            if (!h->sao_type[i]) continue;
+            for (int y = 16 * cy; y < 16 * cy + 16; y++)
+                for (int x = 16 * cx; x < 16 * cx + 16; x++) {
+                    const int k = hevc_sao_category(h, d, e->cw, x, y, h->sao_type[i] - 1);
+                    if (k) f->y[(size_t)y * f->ys + x] = (uint8_t)vcp_clip255(d[(size_t)y * e->cw + x] + h->sao_off[4 * i + k - 1]);
+                }
+        }
+}
+/* sao() syntax of one CTU (7.3.8.3): no merging, luma only */
+static void hevc_write_sao(const HEnc* h, Cabac* c, int cx, int cy, int row0) {
+    const int i = cy * h->e->mbw + cx, type = h->sao_type[i];
+    if (cx > 0) cabac_encode(c, HC_SAO_MERGE, 0);
+    if (cy > row0) cabac_encode(c, HC_SAO_MERGE, 0);
+    cabac_encode(c, HC_SAO_TYPE, type != 0);
+    if (!type) return;
+    cabac_bypass(c, 1);                            /* sao_type_idx_luma = 2: edge offset */
+    for (int k = 0; k < 4; k++) {
+        const int a = abs(h->sao_off[4 * i + k]);
+        for (int j = 0; j < a; j++) cabac_bypass(c, 1);
+        if (a < 7) cabac_bypass(c, 0);
+    }
+    cabac_bypass(c, ((type - 1) >> 1) & 1); cabac_bypass(c, (type - 1) & 1);    /* sao_eo_class_luma */
+}
+
 /* ---- syntax ------------------------------------------------------------------------------------- */
 static void hevc_write_tu_tree(Cabac* c, const HCU* cu, int intra) {
     int any_cb = 0, any_cr = 0;
@@ -587,6 +656,7 @@ static unsigned long long hevc_write_slice_data(HEnc* h, BW* b, int r0, int r1) 
     for (int cy = r0; cy < r1; cy++)
         for (int cx = 0; cx < e->mbw; cx++) {
             const HCU* cu = &h->cus[cy * e->mbw + cx];
+            if (e->p.hevc_sao) hevc_write_sao(h, &c, cx, cy, r0);
             if (!h->idr) {
                 const HCU *l = hevc_nb(h, cx, cy, -1, 0), *a = hevc_nb(h, cx, cy, 0, -1);
                 cabac_encode(&c, HC_SKIP + (l && l->type == HCU_SKIP) + (a && a->type == HCU_SKIP), cu->type == HCU_SKIP);
@@ -684,7 +754,7 @@ static size_t hevc_write_sps(const Enc* e, uint8_t* out, size_t cap) {
     bw_ue(&b, 0); bw_ue(&b, 0);               /* max_transform_hierarchy_depth_inter / intra */
     bw_put(&b, 1, 0);                         /* scaling_list_enabled_flag */
     bw_put(&b, 1, 0);                         /* amp_enabled_flag */
-    bw_put(&b, 1, 0);                         /* sample_adaptive_offset_enabled_flag */
+    bw_put(&b, 1, p->hevc_sao ? 1 : 0);       /* sample_adaptive_offset_enabled_flag */
     bw_put(&b, 1, 0);                         /* pcm_enabled_flag */
     bw_ue(&b, 1);                             /* num_short_term_ref_pic_sets */
     bw_ue(&b, 1); bw_ue(&b, 0); bw_ue(&b, 0); bw_put(&b, 1, 1);   /* one negative picture, delta_poc -1, used */
@@ -739,6 +809,9 @@ static void hevc_write_slice_header(const Enc* e, BW* b, int first_ctb, int idr,
     if (!idr) {
         bw_put(b, 8, (uint32_t)(poc & 255));  /* slice_pic_order_cnt_lsb */
         bw_put(b, 1, 1);                      /* short_term_ref_pic_set_sps_flag (one set: no index) */
+    }
+    if (e->p.hevc_sao) { bw_put(b, 1, 1); bw_put(b, 1, 0); }   /* slice_sao_luma_flag, slice_sao_chroma_flag */
+    if (!idr) {
         bw_put(b, 1, 0);                      /* num_ref_idx_active_override_flag */
         bw_ue(b, 4);                          /* five_minus_max_num_merge_cand: 1 candidate */
     }
@@ -766,10 +839,13 @@ int hevc_orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, 
         frame_alloc(&e->recon[0], e->cw, e->ch) || frame_alloc(&e->recon[1], e->cw, e->ch) ||
         half_alloc(&e->hcur, e->cw, e->ch) || half_alloc(&e->hprev, e->cw, e->ch)) goto done;
     h.cus = (HCU*)calloc((size_t)e->nmb, sizeof(HCU));
+    h.sao_type = (uint8_t*)calloc((size_t)e->nmb, 1);
+    h.sao_off = (int8_t*)calloc((size_t)e->nmb, 4);
+    h.sao_tmp = (uint8_t*)malloc((size_t)e->cw * e->ch);
     e->mvfp = (int16_t*)calloc((size_t)e->nmb * 2, sizeof(int16_t));
     e->rbsp_cap = (size_t)e->nmb * 1024 + 4096;
     e->rbsp = (uint8_t*)malloc(e->rbsp_cap);
-    if (!h.cus || !e->mvfp || !e->rbsp) goto done;
+    if (!h.cus || !e->mvfp || !e->rbsp || !h.sao_type || !h.sao_off || !h.sao_tmp) goto done;
     const size_t fsz = (size_t)p->width * p->height + 2 * (size_t)((p->width + 1) / 2) * ((p->height + 1) / 2);
     size_t o = 0;
     int ri = 0;
@@ -825,6 +901,9 @@ int hevc_orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, 
                 }
             }
         }
+        /* in-loop filters run before the slice data is written: the SAO parameters are part of it */
+        if (p->deblock_idc != 1) hevc_deblock_picture(&h);
+        if (p->hevc_sao) hevc_sao_picture(&h);
         const size_t au0 = o;
         if (idr) {
             size_t k = hevc_write_vps(e, out + o, out_cap - o); if (!k) { rc = VCPENC_E_OVERFLOW; goto done; } o += k;
@@ -850,7 +929,6 @@ int hevc_orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, 
             rc_qp_next[1] = vcp_rc_next_qp(rc_qp0, qp, rc_qp_next[0], idr, frame_bits, rc_cum, t, gop_len, budget);
         }
         if (info) { info[n].offset = au0; info[n].size = (uint32_t)(o - au0); info[n].is_idr = (uint8_t)idr; info[n].qp = (uint8_t)qp; }
-        if (p->deblock_idc != 1) hevc_deblock_picture(&h);
         frame_pad(h.rec);
         if (recon) store_recon(e, h.rec, recon + (size_t)n * fsz);
         ri ^= 1;
@@ -859,6 +937,6 @@ int hevc_orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, 
     rc = VCPENC_OK;
 done:
     frame_free(&e->cur); frame_free(&e->prev_orig); frame_free(&e->recon[0]); frame_free(&e->recon[1]);
-    free(e->hcur.buf); free(e->hprev.buf); free(h.cus); free(e->mvfp); free(e->rbsp);
+    free(e->hcur.buf); free(e->hprev.buf); free(h.cus); free(h.sao_type); free(h.sao_off); free(h.sao_tmp); free(e->mvfp); free(e->rbsp);
     return rc;
 }

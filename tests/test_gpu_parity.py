@@ -411,6 +411,29 @@ def test_hevc_half_sample_motion(built):
             assert (dbg["mv_final"] & 3).any()             # half-sample vectors were chosen
 
 
+def test_hevc_sample_adaptive_offset(built):
+    """params.hevc_sao on the device (hevc_sao_kernel / hevc_sao_copy_kernel, SAO syntax in hevc_bins_kernel): identical
+    to the oracle with and without deblocking / half-sample motion, several slice counts, a scene cut, a ragged size."""
+    from oracle import pyoracle
+    w, h = 320, 192
+    a = synth.make_clip(w, h, 4, seed=1)
+    cut = np.concatenate([a, np.roll(a, 7777, axis=1)[:2], synth.make_clip(w, h, 3, seed=77, start=9)])
+    cases = ((synth.make_clip(w, h, 6, seed=4), w, h, dict(slices=1, hevc_subpel=1)),
+             (synth.make_clip(w, h, 6, seed=4), w, h, dict(slices=3)),
+             (synth.make_clip(w, h, 6, seed=5), w, h, dict(slices=2, deblock_idc=1, hevc_subpel=1)),
+             (synth.make_clip(w, h, 5, seed=6), w, h, dict(slices=12)),
+             (cut, w, h, dict(slices=2, hevc_subpel=1)),
+             (synth.make_clip(208, 114, 5, seed=9), 208, 114, dict(slices=1, hevc_subpel=1)))
+    for clip, cw, chh, kw in cases:
+        gop = 60 if clip is cut else clip.shape[0]
+        for qp in (27, 37):
+            ref = pyoracle.encode_hevc(pyoracle.make_params(cw, chh, codec=1, gop=gop, qp_i=qp - 2, qp_p=qp, hevc_sao=1, **kw), clip)
+            got = api.encode_frames(api.default_params(cw, chh, codec=1, gop=gop, qp_i=qp - 2, qp_p=qp, hevc_sao=1, debug=1, **kw), clip, want_recon=True)
+            bad = [i for i in range(clip.shape[0]) if not np.array_equal(got["recon"][i], ref["recon"][i])]
+            assert not bad, ("recon differs", kw, qp, bad)
+            assert got["stream"].tobytes() == ref["stream"], (kw, qp)
+
+
 def test_streamed_upload_is_identical(built):
     """upload(wait=False): the encode starts each GOP group when its frames have landed; same bytes as the
     synchronous upload, for both codecs, also when the session is reused and when GOPs do not fill the groups."""

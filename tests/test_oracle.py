@@ -390,6 +390,26 @@ def test_hevc_oracle_half_sample_motion():
         assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i])
 
 
+def test_hevc_oracle_sample_adaptive_offset():
+    """params.hevc_sao: luma edge offsets decided per coding tree block on the deblocked picture.  The decoder must
+    reproduce the oracle's reconstruction (syntax + process), with and without deblocking, 1..12 slices; SAO must
+    not lower the PSNR it optimises."""
+    if not arbiter.available():
+        pytest.skip("bundled FFmpeg decoder not present")
+    w, h, n = 320, 192, 6
+    for seed, kw in ((4, dict(slices=1)), (4, dict(slices=3)), (5, dict(slices=2, deblock_idc=1)), (6, dict(slices=12))):
+        clip = synth.make_clip(w, h, n, seed=seed)
+        ps = {}
+        for sao in (0, 1):
+            r = pyoracle.encode_hevc(pyoracle.make_params(w, h, codec=1, gop=n, qp_i=25, qp_p=27, hevc_sao=sao, hevc_subpel=1, **kw), clip)
+            dec = arbiter.decode_annexb_hevc(r["stream"])
+            assert len(dec) == n
+            for i in range(n):
+                assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i]), (kw, sao, i)
+            ps[sao] = np.mean([arbiter.psnr(dec[i][0], synth.split_planes(clip[i], w, h)[0]) for i in range(n)])
+        assert ps[1] >= ps[0] - 0.01, (kw, ps)
+
+
 def test_hevc_tables_match_decoder_rodata():
     """CABAC initValues (tables 9-5..9-37) typed in the oracle must appear in the decoder's own tables."""
     import glob
@@ -401,7 +421,8 @@ def test_hevc_tables_match_decoder_rodata():
     src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "video_codec_pipeline_b200", "csrc", "hevc_tables.h")).read()
     body = re.search(r"hevc_init_values\[2\]\[HC_NCTX\] = \{(.*?)\}\};", src, re.S).group(1)
     rows = [[int(x) for x in re.findall(r"\b\d+\b", re.sub(r"/\*.*?\*/", "", part))] for part in body.split("},")]
-    assert [len(r) for r in rows] == [130, 130]
+    assert [len(r) for r in rows] == [132, 132]
+    assert [r[130:] for r in rows] == [[153, 200], [153, 185]]      # sao_merge_flag, sao_type_idx (tables 9-5, 9-6)
     for row in rows:
         # last_sig_coeff prefix (18), coded_sub_block (4), sig_coeff (42), greater1 (24), greater2 (6) are contiguous runs
         for a, b in ((18, 36), (54, 58), (58, 100), (100, 124), (124, 130)):

@@ -130,6 +130,7 @@ int dev_alloc(vcpenc_session* s, T** p, size_t count, char* err, size_t errlen) 
 int check_params(const vcpenc_params& p, char* err, size_t errlen) {
     if (p.codec != VCPENC_CODEC_H264 && p.codec != VCPENC_CODEC_HEVC) { set_err(err, errlen, "unknown codec %d", p.codec); return VCPENC_E_ARGS; }
     if (p.hevc_subpel < 0 || p.hevc_subpel > 1) { set_err(err, errlen, "bad hevc_subpel %d", p.hevc_subpel); return VCPENC_E_ARGS; }
+    if (p.hevc_sao < 0 || p.hevc_sao > 1) { set_err(err, errlen, "bad hevc_sao %d", p.hevc_sao); return VCPENC_E_ARGS; }
     if (p.entropy < 0 || p.entropy > 1) { set_err(err, errlen, "bad entropy coder %d", p.entropy); return VCPENC_E_ARGS; }
     if (p.width < 16 || p.height < 16 || (p.width & 1) || (p.height & 1)) { set_err(err, errlen, "unsupported picture size %dx%d", p.width, p.height); return VCPENC_E_ARGS; }
     if (p.gop < 1 || p.slices < 0 || p.slices > (p.height + 15) / 16) { set_err(err, errlen, "bad gop/slices"); return VCPENC_E_ARGS; }
@@ -307,6 +308,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     g.slices = pp->slices; g.deblock_idc = pp->deblock_idc; g.cabac = pp->entropy; g.t8x8 = pp->transform8x8 ? 1 : 0;
     g.hevc = pp->codec == VCPENC_CODEC_HEVC;
     g.hevc_subpel = g.hevc && pp->hevc_subpel;
+    g.hevc_sao = g.hevc && pp->hevc_sao;
     g.rc_abr = pp->rc_mode == VCPENC_RC_ABR;
     g.rc_bitrate = pp->bitrate; g.fps_num = pp->fps_num; g.fps_den = pp->fps_den;
     g.rc_qp0 = g.rc_abr ? vcp_rc_initial_qp(pp->bitrate, pp->fps_num, pp->fps_den, pp->width, pp->height) : 0;
@@ -617,6 +619,11 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                     { Prof pr(s, VCPENC_K_P_RECON, 2, st); vcp_launch_hevc_p_recon(g, bt, sp, st); vcp_launch_hevc_i_fix(g, bt, sp, st); }
                     { Prof pr(s, VCPENC_K_MBINFO, 1, st); vcp_launch_hevc_cuinfo(g, bt, sp, st); }
                 }
+                if (g.hevc_sao) {
+                    // the SAO parameters are slice data: deblocking and the SAO decision run before the entropy fork
+                    if (g.deblock_idc != 1) { Prof pr(s, VCPENC_K_DEBLOCK, 2, st); vcp_launch_hevc_deblock(g, bt, sp, st); }
+                    { Prof pr(s, VCPENC_K_DEBLOCK, 1, st); vcp_launch_hevc_sao(g, bt, sp, st); }
+                }
             } else if (t == 0) {
                 Prof pr(s, VCPENC_K_I_RECON, 1, st);
                 vcp_launch_i_recon(g, bt, sp, st);
@@ -662,7 +669,8 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 if (g.rc_abr) { Prof pr(s, VCPENC_K_RC, 1, se); vcp_launch_rc_update(g, bt, sp, se); }
             }
             if (!s->profile) CK(cudaEventRecord(s->ev_ent[k][par], se));
-            if (g.deblock_idc != 1) {
+            if (g.hevc_sao) { Prof pr(s, VCPENC_K_DEBLOCK, 1, st); vcp_launch_hevc_sao_copy(g, bt, sp, st); }   // after the fork: only the picture changes
+            else if (g.deblock_idc != 1) {
                 Prof pr(s, VCPENC_K_DEBLOCK, g.hevc ? 2 : 1, st);
                 if (g.hevc) vcp_launch_hevc_deblock(g, bt, sp, st); else vcp_launch_deblock(g, bt, sp, st);
             }

@@ -157,7 +157,7 @@ std::vector<uint8_t> make_hevc_sps_nal(const vcpenc_params& p) {
     b.ue(0); b.ue(0);       // max_transform_hierarchy_depth_inter / intra
     b.put(1, 0);            // scaling_list_enabled_flag
     b.put(1, 0);            // amp_enabled_flag
-    b.put(1, 0);            // sample_adaptive_offset_enabled_flag
+    b.put(1, p.hevc_sao ? 1 : 0);   // sample_adaptive_offset_enabled_flag
     b.put(1, 0);            // pcm_enabled_flag
     b.ue(1);                // num_short_term_ref_pic_sets
     b.ue(1); b.ue(0); b.ue(0); b.put(1, 1);     // one negative picture: delta_poc_s0_minus1 0, used

@@ -38,7 +38,9 @@ enum {
     HC_SIG = 58,            /* 42 */
     HC_GT1 = 100,           /* 24 */
     HC_GT2 = 124,           /* 6 */
-    HC_NCTX = 130
+    HC_SAO_MERGE = 130,     /* 1: sao_merge_left_flag / sao_merge_up_flag */
+    HC_SAO_TYPE = 131,      /* 1: first bin of sao_type_idx_luma / _chroma */
+    HC_NCTX = 132
 };
 VCP_TAB uint8_t hevc_init_values[2][HC_NCTX] = {
     {   /* initType 0 */
@@ -50,7 +52,8 @@ VCP_TAB uint8_t hevc_init_values[2][HC_NCTX] = {
         111, 111, 125, 110, 110, 94, 124, 108, 124, 107, 125, 141, 179, 153, 125, 107, 125, 141, 179, 153, 125,
         107, 125, 141, 179, 153, 125, 140, 139, 182, 182, 152, 136, 152, 136, 153, 136, 139, 111, 136, 139, 111,
         140, 92, 137, 138, 140, 152, 138, 139, 153, 74, 149, 92, 139, 107, 122, 152, 140, 179, 166, 182, 140, 227, 122, 197,
-        138, 153, 136, 167, 152, 152},
+        138, 153, 136, 167, 152, 152,
+        153, 200},
     {   /* initType 1 */
         197, 185, 201, 149, 154, 154, 152, 110, 168, 140, 198, 79,
         153, 111, 149, 107, 167, 154,
@@ -60,7 +63,8 @@ VCP_TAB uint8_t hevc_init_values[2][HC_NCTX] = {
         155, 154, 139, 153, 139, 123, 123, 63, 153, 166, 183, 140, 136, 153, 154, 166, 183, 140, 136, 153, 154,
         166, 183, 140, 136, 153, 154, 170, 153, 123, 123, 107, 121, 107, 121, 167, 151, 183, 140, 151, 183, 140,
         154, 196, 196, 167, 154, 152, 167, 182, 182, 134, 149, 136, 153, 121, 136, 137, 169, 194, 166, 167, 154, 167, 137, 182,
-        107, 167, 91, 122, 107, 167}};
+        107, 167, 91, 122, 107, 167,
+        153, 185}};
 
 /* 4x4 up-right diagonal scan (6.5.3): scan position -> (x, y) */
 VCP_TAB uint8_t hevc_diag4_x[16] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 1, 2, 3, 2, 3, 3};

@@ -422,6 +422,9 @@ struct CuCtx {
     int tA, tB;                               // neighbours' types (-1: unavailable)
     short2 mvd;
     bool idr, last_in_slice;
+    int sao;                                  // -1: SAO not in use; else 0 off / 1 + edge class
+    int sao_off[4];
+    bool has_left, has_up;                    // CTBs of the same slice to the left / above (sao_merge flags are sent)
 };
 
 // all bins of one coding unit (oracle: hevc_write_slice_data / hevc_write_tu_tree); `lane` selects the syntax group:
@@ -433,6 +436,21 @@ __device__ __forceinline__ void hevc_cu_bins(BinSink<WRITE>& bs, const int16_t* 
     const bool any = M.cbf_y || M.cbf_c;
     const bool tree = !skip && (intra || any);
     if (lane == 0) {
+        if (M.sao >= 0) {   // sao() of the CTU (7.3.8.3): no merging, luma edge offsets only
+            if (M.has_left) bs.put(HC_SAO_MERGE, 0);
+            if (M.has_up) bs.put(HC_SAO_MERGE, 0);
+            bs.put(HC_SAO_TYPE, M.sao != 0);
+            if (M.sao) {
+                bs.bypass(1);                                    // sao_type_idx_luma = 2
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int a = vcp_iabs(M.sao_off[k]);
+                    for (int j = 0; j < a; j++) bs.bypass(1);
+                    if (a < 7) bs.bypass(0);
+                }
+                bs.bypass(((M.sao - 1) >> 1) & 1); bs.bypass((M.sao - 1) & 1);   // sao_eo_class_luma
+            }
+        }
         if (!M.idr) bs.put(HC_SKIP + (M.tA == 2) + (M.tB == 2), skip);
         if (skip) return;
         if (!M.idr) bs.put(HC_PRED_MODE, intra);
@@ -496,6 +514,13 @@ __global__ void __launch_bounds__(CB_WARPS * 32) hevc_bins_kernel(VcpGeom g, Vcp
         const int r1 = sl + 1 < g.slices ? vcp_slice_first_row(sl + 1, g.slices, g.mbh) : g.mbh;
         M.last_in_slice = (my == r1 - 1) && (mx == g.mbw - 1);
     }
+    M.sao = -1; M.has_left = mx > 0; M.has_up = my > row0;
+    M.sao_off[0] = M.sao_off[1] = M.sao_off[2] = M.sao_off[3] = 0;
+    if (g.hevc_sao) {
+        const uint8_t* rec = b.nnz + o * 24;
+        M.sao = rec[0];
+        for (int k = 0; k < 4; k++) M.sao_off[k] = (int)(int8_t)rec[1 + k];
+    }
     if (M.type != 2)
         for (int i = lane; i < 48; i += 32) reinterpret_cast<uint4*>(lvs[warp])[i] = reinterpret_cast<const uint4*>(b.levels + o * VCP_LV_STRIDE)[i];
     __syncwarp();
@@ -537,6 +562,9 @@ __device__ __forceinline__ void hevc_slice_header(const VcpGeom& g, int first_ct
     if (!idr) {
         w.put(8, (uint32_t)(poc & 255));   // slice_pic_order_cnt_lsb
         w.put(1, 1);                       // short_term_ref_pic_set_sps_flag
+    }
+    if (g.hevc_sao) { w.put(1, 1); w.put(1, 0); }   // slice_sao_luma_flag, slice_sao_chroma_flag
+    if (!idr) {
         w.put(1, 0);                       // num_ref_idx_active_override_flag
         w.ue(4);                           // five_minus_max_num_merge_cand
     }

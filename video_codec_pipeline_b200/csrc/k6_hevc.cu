@@ -622,6 +622,119 @@ __global__ void __launch_bounds__(256) hevc_deblock_kernel(VcpGeom g, VcpBufs b,
     }
 }
 
+// ---- sample adaptive offset (8.7.3), luma edge offsets ----------------------------------------------------------
+// Decision and application work on the DEBLOCKED picture D (plane G of the slot).  warp = coding tree block, lane =
+// 8 samples of one row with their 3 x 10 neighbourhood in registers.  Statistics of (source - D) per edge class and
+// category -> 32 warp reductions -> lane 0 picks "off" or the cheapest class (vcp_algo.h: vcp_sao_class_cost, mirrored
+// by the oracle) and stores it in the CTB's record (nnz[0] = 0 / 1 + class, nnz[1..4] = offsets) for the
+// binarisation; CTBs that switch SAO on write their filtered samples to the slot's second luma plane (scratch until
+// the half-sample planes are built), and hevc_sao_copy_kernel moves them back once every CTB has read its
+// neighbours' unfiltered samples.  A sample whose neighbour is outside the picture or in another slice keeps its value.
+struct SaoRow { int up[10], mid[10], dn[10]; bool up_ok, dn_ok; };
+
+__device__ __forceinline__ void hv_sao_load(const VcpGeom& g, const VcpBufs& b, const uint8_t* __restrict__ D, int mx, int my, int lane, SaoRow& R) {
+    const int r = lane >> 1, x0 = 16 * mx + (lane & 1) * 8, y = 16 * my + r;
+    R.up_ok = r > 0 || my > vcp_row_first(b, my);
+    R.dn_ok = r < 15 || (my + 1 < g.mbh && vcp_row_slice(b, my + 1) == vcp_row_slice(b, my));
+    const int xl = x0 > 0 ? x0 - 1 : 0, xr = x0 + 8 < g.cw ? x0 + 8 : g.cw - 1;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int yy = vcp_clip3(0, g.ch - 1, y + k - 1);
+        const uint8_t* p = D + (size_t)yy * g.ys;
+        const uint2 w = *reinterpret_cast<const uint2*>(p + x0);
+        int* a = k == 0 ? R.up : k == 1 ? R.mid : R.dn;
+        a[0] = p[xl]; a[9] = p[xr];
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[1 + j] = (int)(((j < 4 ? w.x : w.y) >> (8 * (j & 3))) & 255);
+    }
+}
+// edge category (0 = none, 1..4) of sample j (0..7) of the lane's row for class cls
+__device__ __forceinline__ int hv_sao_cat(const VcpGeom& g, const SaoRow& R, int x, int j, int cls) {
+    const bool lr = x > 0 && x + 1 < g.cw, ud = R.up_ok && R.dn_ok;
+    int n0, n1;
+    bool ok;
+    if (cls == 0) { n0 = R.mid[j]; n1 = R.mid[j + 2]; ok = lr; }
+    else if (cls == 1) { n0 = R.up[j + 1]; n1 = R.dn[j + 1]; ok = ud; }
+    else if (cls == 2) { n0 = R.up[j]; n1 = R.dn[j + 2]; ok = lr && ud; }
+    else { n0 = R.up[j + 2]; n1 = R.dn[j]; ok = lr && ud; }
+    if (!ok) return 0;
+    const int c = R.mid[j + 1];
+    const int sg = (c < n0 ? -1 : c > n0 ? 1 : 0) + (c < n1 ? -1 : c > n1 ? 1 : 0);
+    return sg == -2 ? 1 : sg == -1 ? 2 : sg == 1 ? 3 : sg == 2 ? 4 : 0;
+}
+
+constexpr int SAO_WARPS = 4;
+__global__ void __launch_bounds__(SAO_WARPS * 32) hevc_sao_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mbi = blockIdx.x * SAO_WARPS + warp;
+    const int gi = blockIdx.y + s.g0;
+    if (mbi >= g.nmb) return;
+    const int n = vcp_frame_of(s, gi), slot = vcp_rec_slot(s, gi, s.t);
+    const int mx = mbi % g.mbw, my = mbi / g.mbw;
+    uint8_t* D = vcp_rec_luma(b, g, slot) + g.yoff;
+    SaoRow R;
+    hv_sao_load(g, b, D, mx, my, lane, R);
+    const int r = lane >> 1, x0 = 16 * mx + (lane & 1) * 8, y = 16 * my + r;
+    const uint2 sw = *reinterpret_cast<const uint2*>(b.src_y + (size_t)n * g.ysize + g.yoff + (size_t)y * g.ys + x0);
+    int sum[4][4], cnt[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) { sum[c][k] = 0; cnt[c][k] = 0; }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int diff = (int)(((j < 4 ? sw.x : sw.y) >> (8 * (j & 3))) & 255) - R.mid[j + 1];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int k = hv_sao_cat(g, R, x0 + j, j, c);
+#pragma unroll
+            for (int q = 0; q < 4; q++) { sum[c][q] += k == q + 1 ? diff : 0; cnt[c][q] += k == q + 1; }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) { sum[c][k] = warp_sum(sum[c][k]); cnt[c][k] = warp_sum(cnt[c][k]); }
+    // decision (every lane computes the same)
+    const int lam = vcp_lambda(b.qp[n]), lam2 = lam * lam;
+    long long best = lam2;
+    int type = 0, off[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        int o[4];
+        const long long cost = vcp_sao_class_cost(sum[c], cnt[c], lam2, o);
+        if (cost < best && (o[0] | o[1] | o[2] | o[3])) { best = cost; type = 1 + c; off[0] = o[0]; off[1] = o[1]; off[2] = o[2]; off[3] = o[3]; }
+    }
+    uint8_t* rec = b.nnz + ((size_t)gi * g.nmb + mbi) * 24;
+    if (lane == 0) rec[0] = (uint8_t)type;
+    if (lane >= 1 && lane <= 4) rec[lane] = (uint8_t)(int8_t)off[lane - 1];
+    if (!type) return;
+    // filtered samples of this CTB -> scratch plane
+    uint32_t o4[2] = {0, 0};
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        int k = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) if (type == 1 + c) k = hv_sao_cat(g, R, x0 + j, j, c);
+        const int ov = k == 1 ? off[0] : k == 2 ? off[1] : k == 3 ? off[2] : k == 4 ? off[3] : 0;
+        const int v = vcp_clip255(R.mid[j + 1] + ov);
+        o4[j >> 2] |= (uint32_t)v << (8 * (j & 3));
+    }
+    *reinterpret_cast<uint2*>(D + g.ysize + (size_t)y * g.ys + x0) = make_uint2(o4[0], o4[1]);
+}
+
+__global__ void __launch_bounds__(SAO_WARPS * 32) hevc_sao_copy_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mbi = blockIdx.x * SAO_WARPS + warp;
+    const int gi = blockIdx.y + s.g0;
+    if (mbi >= g.nmb) return;
+    if (!b.nnz[((size_t)gi * g.nmb + mbi) * 24]) return;
+    const int slot = vcp_rec_slot(s, gi, s.t);
+    const int mx = mbi % g.mbw, my = mbi / g.mbw;
+    uint8_t* D = vcp_rec_luma(b, g, slot) + g.yoff + (size_t)(16 * my + (lane >> 1)) * g.ys + 16 * mx + (lane & 1) * 8;
+    *reinterpret_cast<uint2*>(D) = *reinterpret_cast<const uint2*>(D + g.ysize);
+}
+
 }  // namespace
 
 void vcp_launch_hevc_p_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
@@ -644,4 +757,12 @@ void vcp_launch_hevc_deblock(const VcpGeom& g, const VcpBufs& b, const VcpStep& 
     const int nv = (g.cw >> 3) * (g.ch >> 2), nh = (g.cw >> 2) * (g.ch >> 3);
     hevc_deblock_kernel<true><<<dim3((nv + 255) / 256, s.ngop), 256, 0, st>>>(g, b, s);
     hevc_deblock_kernel<false><<<dim3((nh + 255) / 256, s.ngop), 256, 0, st>>>(g, b, s);
+}
+void vcp_launch_hevc_sao(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
+    dim3 grid((g.nmb + SAO_WARPS - 1) / SAO_WARPS, s.ngop);
+    hevc_sao_kernel<<<grid, SAO_WARPS * 32, 0, st>>>(g, b, s);
+}
+void vcp_launch_hevc_sao_copy(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
+    dim3 grid((g.nmb + SAO_WARPS - 1) / SAO_WARPS, s.ngop);
+    hevc_sao_copy_kernel<<<grid, SAO_WARPS * 32, 0, st>>>(g, b, s);
 }

@@ -39,6 +39,31 @@ VCP_HD int vcp_intra_wins(int intra_sad, int inter_cost, int lam) {
     return intra_sad + (intra_sad >> 2) + 16 * lam < inter_cost;
 }
 
+// ---- HEVC sample adaptive offset (luma edge offsets), one decision per 16x16 coding tree block -------------
+// sum / cnt: (source - deblocked) accumulated over the samples of one edge category.  Categories 1, 2 (local
+// minimum, concave corner) take offsets 0..7, categories 3, 4 (convex corner, local maximum) -7..0 (7.4.9.3.2).
+VCP_HD int vcp_sao_offset(int sum, int cnt, int positive) {
+    if (cnt == 0) return 0;
+    int o = sum >= 0 ? (sum + (cnt >> 1)) / cnt : -((-sum + (cnt >> 1)) / cnt);
+    if (positive) return o < 0 ? 0 : o > 7 ? 7 : o;
+    return o > 0 ? 0 : o < -7 ? -7 : o;
+}
+// Cost of coding one class with its four offsets against "off" (cost lam2 for its single bin): distortion change
+// sum(cnt o^2 - 2 o sum) plus lam2 per bin (type 2, offsets |o| + 1 each up to 7, class 2).  Returns the class
+// cost; off[] receives the offsets.
+VCP_HD long long vcp_sao_class_cost(const int sum[4], const int cnt[4], int lam2, int off[4]) {
+    long long d = 0;
+    int bins = 4;
+    for (int k = 0; k < 4; k++) {
+        const int o = vcp_sao_offset(sum[k], cnt[k], k < 2);
+        off[k] = o;
+        d += (long long)cnt[k] * o * o - 2LL * o * sum[k];
+        const int a = o < 0 ? -o : o;
+        bins += a + (a < 7);
+    }
+    return d + (long long)lam2 * bins;
+}
+
 // Slices per picture when the caller leaves the choice to the encoder (slices == 0).  CAVLC is
 // macroblock-parallel, one slice is best.  CABAC is one sequential chain per slice, so pictures are cut
 // into slices of about 17 macroblock rows (1080p: 4, 4K: 7, 720p: 2) -- the usual choice of parallel

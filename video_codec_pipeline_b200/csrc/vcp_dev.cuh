@@ -29,6 +29,7 @@ struct VcpGeom {
     int t8x8;          // transform_8x8_mode_flag (High profile)
     int hevc;          // codec: 0 H.264, 1 HEVC (k6_hevc.cu; the motion search and the arithmetic coder are shared)
     int hevc_subpel;   // HEVC: half-sample luma motion from the 8-tap planes of k2_hpel.cu
+    int hevc_sao;      // HEVC: sample adaptive offset (luma edge offsets)
     // rate control (VCPENC_RC_ABR): see vcp_algo.h
     int rc_abr, rc_qp0, rc_bitrate, fps_num, fps_den;
 };
@@ -139,6 +140,8 @@ void vcp_launch_hevc_i_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& 
 void vcp_launch_hevc_i_fix(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_hevc_cuinfo(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_hevc_deblock(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
+void vcp_launch_hevc_sao(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
+void vcp_launch_hevc_sao_copy(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_hevc_bins(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_rc_update(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 
