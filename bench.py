@@ -54,7 +54,7 @@ def select_workload(name: str, entropy: int, slices: int = -1, codec: str = "h26
     global W, H, FPS, SEED, ENTROPY, METRIC, WORKLOAD, SLICES, T8X8, CODEC
     if codec == "hevc":
         # configs[3]: the h265-* presets' path.  Stream structure of csrc/k6_hevc.cu: Main profile, 16x16 coding
-        # units, 8x8 transforms, half-sample motion, CABAC, in-loop deblocking ("HEVC")
+        # units, 8x8 transforms, half-sample motion, CABAC, in-loop deblocking + SAO ("HEVC")
         CODEC = 1
         if name == "4k":
             W, H, FPS, SEED = 3840, 2160, 60, 2160
@@ -62,7 +62,7 @@ def select_workload(name: str, entropy: int, slices: int = -1, codec: str = "h26
         mbh = (H + 15) // 16
         SLICES = slices if slices >= 0 else max(1, mbh // 17)
         METRIC = "%s HEVC encode fps (GOP=60, Main profile, I+P)" % ("4K" if name == "4k" else "1080p")
-        WORKLOAD = "%s: %dx%d@%d yuv420p, HEVC Main, GOP=60, CABAC, %d slice%s, I+P, half-sample motion, deblock, CQP %d/%d" % (
+        WORKLOAD = "%s: %dx%d@%d yuv420p, HEVC Main, GOP=60, CABAC, %d slice%s, I+P, half-sample motion, deblock, SAO, CQP %d/%d" % (
             "configs[3] (one GPU's GOP shard)" if name == "4k" else "configs[3] at 1080p", W, H, FPS, SLICES, "" if SLICES == 1 else "s", QP_I, QP_P)
         return
     if name == "4k":
@@ -156,7 +156,7 @@ def cpu_port_fps(frames: np.ndarray, threads: int, frames_per_gop: int):
 
     def one(fr):
         p = pyoracle.make_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, entropy=ENTROPY, slices=SLICES, transform8x8=T8X8, codec=CODEC,
-                                 hevc_subpel=1 if CODEC else 0)
+                                 hevc_subpel=1 if CODEC else 0, hevc_sao=1 if CODEC else 0)
         if CODEC:
             return len(pyoracle.encode_hevc(p, fr)["stream"])
         return len(pyoracle.encode(p, fr, want_recon=False)["stream"])
@@ -239,7 +239,7 @@ def main():
     n = frames.shape[0]
     fb = frames.shape[1]
     p = api.default_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, slices=SLICES, deblock_idc=args.deblock_idc,
-                           first_gop=rank * args.gops, entropy=ENTROPY, transform8x8=T8X8, codec=CODEC, hevc_subpel=1 if CODEC else 0)
+                           first_gop=rank * args.gops, entropy=ENTROPY, transform8x8=T8X8, codec=CODEC, hevc_subpel=1 if CODEC else 0, hevc_sao=1 if CODEC else 0)
     host = torch.from_numpy(frames).pin_memory()
     dev = host.to("cuda", non_blocking=False)
     out_host = torch.empty(n * fb // 2 + (1 << 20), dtype=torch.uint8).pin_memory()

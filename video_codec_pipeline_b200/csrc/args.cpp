@@ -178,7 +178,7 @@ extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_param
     (void)have_codec;
     if (p->entropy < 0) p->entropy = 1;   // x264 and NVENC both default to CABAC
     if (p->transform8x8 < 0) p->transform8x8 = 1;   // ... and to High profile
-    if (p->codec == VCPENC_CODEC_HEVC) p->hevc_subpel = 1;   // libx265 / hevc_nvenc search sub-sample positions: half samples here
+    if (p->codec == VCPENC_CODEC_HEVC) { p->hevc_subpel = 1; p->hevc_sao = 1; }   // libx265 / hevc_nvenc: sub-sample motion (half samples here) and SAO are on by default
     if (have_crf && !have_qp) {
         // constant quality: one QP per picture type (x264's default ipratio 1.4 ~ 3 QP)
         p->qp_p = crf + 1 > 51 ? 51 : crf + 1;
