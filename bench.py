@@ -44,6 +44,7 @@ ENTROPY = 0
 SLICES = 1
 T8X8 = 0
 CODEC = 0          # 0 H.264, 1 HEVC (--codec hevc: BASELINE.json configs[3], one GPU's GOP shard)
+HEVC_SAO = 0       # --hevc-sao: sample adaptive offset (bit-exact; its first kernel is not yet tuned)
 METRIC = "1080p H.264 encode fps (GOP=60, CAVLC, I+P)"
 WORKLOAD = "configs[1]: 1080p30 yuv420p, GOP=60, CAVLC, I+P, deblock, CQP 25/27"
 
@@ -54,7 +55,7 @@ def select_workload(name: str, entropy: int, slices: int = -1, codec: str = "h26
     global W, H, FPS, SEED, ENTROPY, METRIC, WORKLOAD, SLICES, T8X8, CODEC
     if codec == "hevc":
         # configs[3]: the h265-* presets' path.  Stream structure of csrc/k6_hevc.cu: Main profile, 16x16 coding
-        # units, 8x8 transforms, half-sample motion, CABAC, in-loop deblocking + SAO ("HEVC")
+        # units, 8x8 transforms, half-sample motion, CABAC, in-loop deblocking (+ SAO with --hevc-sao; DESIGN.md 1, "HEVC")
         CODEC = 1
         if name == "4k":
             W, H, FPS, SEED = 3840, 2160, 60, 2160
@@ -62,8 +63,9 @@ def select_workload(name: str, entropy: int, slices: int = -1, codec: str = "h26
         mbh = (H + 15) // 16
         SLICES = slices if slices >= 0 else max(1, mbh // 17)
         METRIC = "%s HEVC encode fps (GOP=60, Main profile, I+P)" % ("4K" if name == "4k" else "1080p")
-        WORKLOAD = "%s: %dx%d@%d yuv420p, HEVC Main, GOP=60, CABAC, %d slice%s, I+P, half-sample motion, deblock, SAO, CQP %d/%d" % (
-            "configs[3] (one GPU's GOP shard)" if name == "4k" else "configs[3] at 1080p", W, H, FPS, SLICES, "" if SLICES == 1 else "s", QP_I, QP_P)
+        WORKLOAD = "%s: %dx%d@%d yuv420p, HEVC Main, GOP=60, CABAC, %d slice%s, I+P, half-sample motion, deblock%s, CQP %d/%d" % (
+            "configs[3] (one GPU's GOP shard)" if name == "4k" else "configs[3] at 1080p", W, H, FPS, SLICES, "" if SLICES == 1 else "s",
+            ", SAO" if HEVC_SAO else "", QP_I, QP_P)
         return
     if name == "4k":
         W, H, FPS, SEED = 3840, 2160, 60, 2160
@@ -156,7 +158,7 @@ def cpu_port_fps(frames: np.ndarray, threads: int, frames_per_gop: int):
 
     def one(fr):
         p = pyoracle.make_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, entropy=ENTROPY, slices=SLICES, transform8x8=T8X8, codec=CODEC,
-                                 hevc_subpel=1 if CODEC else 0, hevc_sao=1 if CODEC else 0)
+                                 hevc_subpel=1 if CODEC else 0, hevc_sao=HEVC_SAO if CODEC else 0)
         if CODEC:
             return len(pyoracle.encode_hevc(p, fr)["stream"])
         return len(pyoracle.encode(p, fr, want_recon=False)["stream"])
@@ -209,11 +211,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="1080p", choices=["1080p", "4k"], help="default: BASELINE.json configs[1]")
     ap.add_argument("--codec", default="h264", choices=["h264", "hevc"], help="hevc: BASELINE.json configs[3] (use with --workload 4k)")
+    ap.add_argument("--hevc-sao", action="store_true", help="HEVC: sample adaptive offset on (default off: its first kernel is slow)")
     ap.add_argument("--entropy", type=int, default=-1, help="0 CAVLC, 1 CABAC (default: what the workload names)")
     ap.add_argument("--slices", type=int, default=-1, help="slices per picture (default: the encoder's choice)")
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads (sessions) of the end-to-end pipeline, like consumer -j")
     ap.add_argument("--deblock-idc", type=int, default=0, help="experiments only: 1 switches the in-loop filter off")
     args = ap.parse_args()
+    global HEVC_SAO
+    HEVC_SAO = 1 if args.hevc_sao else 0
     select_workload(args.workload, args.entropy, args.slices, args.codec)
     if args.workload == "4k" and args.gops == 32:
         args.gops = 16                     # 960 frames of 4K = 12 GB of raw input per GPU
@@ -239,7 +244,7 @@ def main():
     n = frames.shape[0]
     fb = frames.shape[1]
     p = api.default_params(W, H, fps=FPS, gop=GOP, qp_i=QP_I, qp_p=QP_P, slices=SLICES, deblock_idc=args.deblock_idc,
-                           first_gop=rank * args.gops, entropy=ENTROPY, transform8x8=T8X8, codec=CODEC, hevc_subpel=1 if CODEC else 0, hevc_sao=1 if CODEC else 0)
+                           first_gop=rank * args.gops, entropy=ENTROPY, transform8x8=T8X8, codec=CODEC, hevc_subpel=1 if CODEC else 0, hevc_sao=HEVC_SAO if CODEC else 0)
     host = torch.from_numpy(frames).pin_memory()
     dev = host.to("cuda", non_blocking=False)
     out_host = torch.empty(n * fb // 2 + (1 << 20), dtype=torch.uint8).pin_memory()

@@ -73,6 +73,14 @@ def test_parse_reference_presets(built):
     p = api.parse_args("-c:v libx264 -qp 30 -g 30 -slices 4 -coder 0 -bf 0 -r 60000/1001".split())
     assert (p.qp_p, p.gop, p.slices, p.entropy, p.fps_num, p.fps_den) == (30, 30, 4, 0, 60000, 1001)
     assert api.parse_args([]).codec == 0                    # empty ffmpeg_args is legal (consumer.go:377)
+    # HEVC tools: half-sample motion by default, SAO through x265's own option string
+    p = api.parse_args("-c:v libx265 -preset medium -crf 28".split())
+    assert (p.codec, p.hevc_subpel, p.hevc_sao) == (1, 1, 0)
+    p = api.parse_args("-c:v libx265 -crf 28 -x265-params sao=1:keyint=60".split())
+    assert (p.hevc_subpel, p.hevc_sao) == (1, 1)
+    p = api.parse_args("-c:v hevc_nvenc -b:v 8M -x265-params no-sao:subme=0".split())
+    assert (p.hevc_subpel, p.hevc_sao) == (0, 0)
+    assert api.parse_args("-c:v libx264 -crf 23".split()).hevc_subpel == 0
     p = api.parse_args("-c:v libx264 -vf scale=1280:-2 -crf 20".split())
     assert (p.width, p.height) == (1280, -2)
     with pytest.raises(api.VcpencError):

@@ -56,6 +56,7 @@ extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_param
     p->transform8x8 = -1;   // likewise: High profile tools unless -profile:v baseline / main
     bool have_codec = false, have_crf = false, have_qp = false;
     int crf = 23;
+    int sao = -1, subpel = 1;   // HEVC tools from -x265-params
     for (int i = 0; i < argc; i++) {
         const std::string t = argv[i];
         auto need = [&](const char** v) -> bool {
@@ -96,6 +97,13 @@ extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_param
                    t == "-c:a" || t == "-acodec" || t == "-b:a" || t == "-ar" || t == "-ac" || t == "-f" ||
                    t == "-rc" || t == "-rc-lookahead" || t == "-x264-params" || t == "-x264opts") {
             if (!need(&v)) return VCPENC_E_ARGS;  // accepted, no effect on this encoder
+        } else if (t == "-x265-params") {
+            // x265's own option string (key=value pairs joined by ':'): sao / no-sao and the sub-sample search are understood
+            if (!need(&v)) return VCPENC_E_ARGS;
+            const std::string xs = std::string(":") + v + ":";
+            if (xs.find(":sao=1:") != std::string::npos || xs.find(":sao:") != std::string::npos) sao = 1;
+            if (xs.find(":sao=0:") != std::string::npos || xs.find(":no-sao:") != std::string::npos || xs.find(":no-sao=1:") != std::string::npos) sao = 0;
+            if (xs.find(":subme=0:") != std::string::npos) subpel = 0;
         } else if (t == "-an") {
             p->drop_audio = 1;
         } else if (t == "-sn" || t == "-dn" || t == "-y" || t == "-hide_banner" || t == "-nostdin") {
@@ -178,7 +186,12 @@ extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_param
     (void)have_codec;
     if (p->entropy < 0) p->entropy = 1;   // x264 and NVENC both default to CABAC
     if (p->transform8x8 < 0) p->transform8x8 = 1;   // ... and to High profile
-    if (p->codec == VCPENC_CODEC_HEVC) { p->hevc_subpel = 1; p->hevc_sao = 1; }   // libx265 / hevc_nvenc: sub-sample motion (half samples here) and SAO are on by default
+    if (p->codec == VCPENC_CODEC_HEVC) {
+        // libx265 / hevc_nvenc search sub-sample positions: half samples here.  SAO is implemented and bit-exact but
+        // its first kernel costs ~45 us per 1080p picture (profiles/r01_notes.md), so it is opt-in: -x265-params sao=1
+        p->hevc_subpel = subpel;
+        p->hevc_sao = sao > 0 ? 1 : 0;
+    }
     if (have_crf && !have_qp) {
         // constant quality: one QP per picture type (x264's default ipratio 1.4 ~ 3 QP)
         p->qp_p = crf + 1 > 51 ? 51 : crf + 1;
