@@ -204,6 +204,13 @@ def test_container_front_end_decodes_what_we_mux(built, tmp_path):
     assert info["fps"][0] / info["fps"][1] == 24
     assert info["frames"].shape[0] == n
     assert np.array_equal(info["frames"], r["recon"])
+    # an HEVC input (what an h265-* task leaves behind, re-submitted): hvc1 + hvcC through the same front end
+    r5 = pyoracle.encode_hevc(pyoracle.make_params(w, h, fps=24, codec=1, gop=4, qp_i=24, qp_p=26, slices=2, hevc_subpel=1, hevc_sao=1), clip)
+    path5 = str(tmp_path / "in_hevc.mp4")
+    api.mux_mp4(api.default_params(w, h, fps=24, codec=1, gop=4, faststart=1, hevc_sao=1), np.frombuffer(r5["stream"], np.uint8), r5["info"], path5)
+    info5 = api.probe_input(path5, max_frames=n + 3)
+    assert (info5["width"], info5["height"]) == (w, h) and info5["frames"].shape[0] == n
+    assert np.array_equal(info5["frames"], r5["recon"])
     # not a media file -> FORMAT
     junk = tmp_path / "junk.mkv"
     junk.write_bytes(b"\x1a\x45\xdf\xa3" + os.urandom(2000))
