@@ -90,7 +90,10 @@ typedef struct vcpenc_params {
                                   the argument parser for libx265 / hevc_nvenc                                  */
     int32_t hevc_sao;          /* HEVC: 1 = sample adaptive offset on luma (edge offsets, one decision per coding tree
                                   block, taken on the deblocked picture)                                         */
-    int32_t reserved[6];
+    int32_t hevc_intra_modes;  /* HEVC: 1 = intra CUs choose among planar / DC / horizontal / vertical prediction (else DC only).
+                                  Implemented and pinned in the oracle; the device path does not have it yet:
+                                  VCPENC_E_UNSUPPORTED                                                            */
+    int32_t reserved[5];
 } vcpenc_params;
 
 /* per coded picture, filled by the encode calls */

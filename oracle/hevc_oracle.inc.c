@@ -29,6 +29,7 @@ typedef struct {
     uint8_t type;            /* HCU_* */
     uint8_t merge;           /* inter: merge_flag */
     uint8_t mvp_idx;
+    uint8_t imode;           /* intra: luma prediction mode (0 planar, 1 DC, 10 horizontal, 26 vertical); chroma derives it */
     uint8_t cbf_y[4], cbf_cb[4], cbf_cr[4];   /* per 8x8 transform unit, z-order */
     int16_t mv[2];           /* quarter-sample units, multiples of 4 */
     int16_t mvd[2];
@@ -101,14 +102,32 @@ static void hevc_dequant(const int16_t* lv, int n, int qp, int* c) {
 }
 static int hevc_chroma_qp(int qp) { return qp < 30 ? qp : qp > 43 ? qp - 6 : hevc_qpc_tab[qp - 30]; }
 
-/* ---- residual_coding (7.3.8.11, 9.3.4.2.x) for 8x8 luma / 4x4 chroma, diagonal scan ----------- */
-static void hevc_residual(Cabac* cb, const int16_t* lv /* raster */, int log2n, int cidx) {
+/* scan position -> (x, y) inside a 4x4 block / sub-block index -> (xs, ys) inside an 8x8 block, per scanIdx
+ * (6.5.3 up-right diagonal, 6.5.4 horizontal, 6.5.5 vertical) */
+static void hevc_scan4(int scan, int p, int* x, int* y) {
+    if (scan == 0) { *x = hevc_diag4_x[p]; *y = hevc_diag4_y[p]; }
+    else if (scan == 1) { *x = p & 3; *y = p >> 2; }
+    else { *x = p >> 2; *y = p & 3; }
+}
+static void hevc_scan2(int scan, int i, int* x, int* y) {
+    if (scan == 0) { *x = hevc_diag2_x[i]; *y = hevc_diag2_y[i]; }
+    else if (scan == 1) { *x = i & 1; *y = i >> 1; }
+    else { *x = i >> 1; *y = i & 1; }
+}
+/* scanIdx of an intra block (7.4.9.11): horizontal-ish modes scan vertically, vertical-ish modes horizontally */
+static int hevc_scan_idx(int intra, int mode) { return !intra ? 0 : (mode >= 6 && mode <= 14) ? 2 : (mode >= 22 && mode <= 30) ? 1 : 0; }
+
+/* ---- residual_coding (7.3.8.11, 9.3.4.2.x) for 8x8 luma / 4x4 chroma ------------------------------ */
+static void hevc_residual(Cabac* cb, const int16_t* lv /* raster */, int log2n, int cidx, int scan) {
     const int n = 1 << log2n, nsb = n == 8 ? 4 : 1;
     /* coefficients in coding (scan) order: sub-block i, position p */
     int pos_x[64], pos_y[64], coef[64], ncoef = n * n, last = -1;
     for (int i = 0; i < nsb; i++)
         for (int p = 0; p < 16; p++) {
-            int x = (n == 8 ? 4 * hevc_diag2_x[i] : 0) + hevc_diag4_x[p], y = (n == 8 ? 4 * hevc_diag2_y[i] : 0) + hevc_diag4_y[p];
+            int sx = 0, sy = 0, x, y;
+            if (n == 8) hevc_scan2(scan, i, &sx, &sy);
+            hevc_scan4(scan, p, &x, &y);
+            x += 4 * sx; y += 4 * sy;
             pos_x[16 * i + p] = x; pos_y[16 * i + p] = y; coef[16 * i + p] = lv[y * n + x];
             if (coef[16 * i + p]) last = 16 * i + p;
         }
@@ -116,6 +135,7 @@ static void hevc_residual(Cabac* cb, const int16_t* lv /* raster */, int log2n, 
     /* last significant position: prefix (context coded, truncated unary) + suffix (bypass) */
     {
         int lx = pos_x[last], ly = pos_y[last];
+        if (scan == 2) { const int t = lx; lx = ly; ly = t; }   /* vertical scan: the position is coded transposed */
         int off, shift;
         if (cidx == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; }
         else { off = 15; shift = log2n - 2; }
@@ -135,7 +155,8 @@ static void hevc_residual(Cabac* cb, const int16_t* lv /* raster */, int log2n, 
     int prev_gt1_zero = 0;    /* the previous sub-block ended with greater1Ctx == 0 */
     int first_sb = 1;
     for (int i = last >> 4; i >= 0; i--) {
-        const int xs = n == 8 ? hevc_diag2_x[i] : 0, ys = n == 8 ? hevc_diag2_y[i] : 0;
+        int xs = 0, ys = 0;
+        if (n == 8) hevc_scan2(scan, i, &xs, &ys);
         const int* cf = coef + 16 * i;
         int any = 0;
         for (int p = 0; p < 16; p++) any |= cf[p] != 0;
@@ -163,7 +184,8 @@ static void hevc_residual(Cabac* cb, const int16_t* lv /* raster */, int log2n, 
                     if (!others) coded = 0;
                 }
                 if (coded) {
-                    int xp = hevc_diag4_x[p], yp = hevc_diag4_y[p], sc;
+                    int xp, yp, sc;
+                    hevc_scan4(scan, p, &xp, &yp);
                     if (log2n == 2) sc = hevc_sig_ctx_map4[(yp << 2) + xp];
                     else if (xs == 0 && ys == 0 && p == 0) sc = 0;
                     else {
@@ -172,7 +194,7 @@ static void hevc_residual(Cabac* cb, const int16_t* lv /* raster */, int log2n, 
                         else if (pat == 1) sc = yp == 0 ? 2 : yp == 1 ? 1 : 0;
                         else if (pat == 2) sc = xp == 0 ? 2 : xp == 1 ? 1 : 0;
                         else sc = 2;
-                        if (cidx == 0) { if (xs || ys) sc += 3; sc += 9; }   /* log2 == 3, diagonal scan */
+                        if (cidx == 0) { if (xs || ys) sc += 3; sc += scan == 0 ? 9 : 15; }   /* log2 == 3 */
                         else sc += 9;
                     }
                     cabac_encode(cb, HC_SIG + (cidx == 0 ? sc : 27 + sc), s);
@@ -252,8 +274,10 @@ static int hevc_avail(const Enc* e, int xc, int yc, int x, int y) {
     return zn < zc;
 }
 
-/* DC prediction of one transform block (8.4.4.2.2 substitution, 8.4.4.2.5 DC, edge filter for luma) */
-static void hevc_intra_dc(const HEnc* h, int cidx, int xl, int yl /* luma position of the TU */, int n, uint8_t* pred) {
+/* Intra prediction of one transform block (8.4.4.2): reference substitution (8.4.4.2.2), [1 2 1] smoothing of the
+ * references where the mode asks for it (8.4.4.2.3: luma 8x8 planar), then planar (0), DC (1), horizontal (10) or
+ * vertical (26) with the luma edge filters of DC / horizontal / vertical */
+static void hevc_intra_pred(const HEnc* h, int cidx, int xl, int yl /* luma position of the TU */, int n, int mode, uint8_t* pred) {
     const Enc* e = h->e;
     const Frame* f = h->rec;
     const uint8_t* plane = cidx == 0 ? f->y : cidx == 1 ? f->u : f->v;
@@ -274,8 +298,33 @@ static void hevc_intra_dc(const HEnc* h, int cidx, int xl, int yl /* luma positi
         if (!av[0]) { int k = 1; while (!av[k]) k++; ref[0] = ref[k]; }
         for (int k = 1; k <= 4 * n; k++) if (!av[k]) ref[k] = ref[k - 1];
     }
+    if (cidx == 0 && n == 8 && mode == 0) {           /* filterFlag: min(|mode - 26|, |mode - 10|) > 7 -- of our modes only planar */
+        int fl[33];
+        fl[0] = ref[0]; fl[4 * n] = ref[4 * n];
+        for (int k = 1; k < 4 * n; k++) fl[k] = (ref[k - 1] + 2 * ref[k] + ref[k + 1] + 2) >> 2;
+        for (int k = 0; k <= 4 * n; k++) ref[k] = fl[k];
+    }
     const int* left = ref + 2 * n - 1;   /* left[-y] = p[-1][y] */
     const int* top = ref + 2 * n + 1;    /* top[x] = p[x][-1] */
+    const int corner = ref[2 * n], lg = n == 8 ? 3 : 2;
+    if (mode == 0) {                                   /* planar (8.4.4.2.4) */
+        for (int y = 0; y < n; y++)
+            for (int x = 0; x < n; x++)
+                pred[y * n + x] = (uint8_t)(((n - 1 - x) * left[-y] + (x + 1) * top[n] + (n - 1 - y) * top[x] + (y + 1) * left[-n] + n) >> (lg + 1));
+        return;
+    }
+    if (mode == 26) {                                  /* vertical (8.4.4.2.6, intraPredAngle 0) */
+        for (int y = 0; y < n; y++)
+            for (int x = 0; x < n; x++) pred[y * n + x] = (uint8_t)top[x];
+        if (cidx == 0) for (int y = 0; y < n; y++) pred[y * n] = (uint8_t)vcp_clip255(top[0] + ((left[-y] - corner) >> 1));
+        return;
+    }
+    if (mode == 10) {                                  /* horizontal */
+        for (int y = 0; y < n; y++)
+            for (int x = 0; x < n; x++) pred[y * n + x] = (uint8_t)left[-y];
+        if (cidx == 0) for (int x = 0; x < n; x++) pred[x] = (uint8_t)vcp_clip255(left[0] + ((top[x] - corner) >> 1));
+        return;
+    }
     int sum = n;
     for (int i = 0; i < n; i++) sum += top[i] + left[-i];
     const int dc = sum >> ((n == 8 ? 3 : 2) + 1);
@@ -305,18 +354,71 @@ static int hevc_code_block(const HEnc* h, int cidx, int x0, int y0, int n, const
     return nz != 0;
 }
 
+static const HCU* hevc_nb_raw(const HEnc* h, int cx, int cy) { return cx > 0 ? &h->cus[cy * h->e->mbw + cx - 1] : NULL; }
+/* most probable modes of a CU (8.4.2): the CU above always sits in another CTB row (CTB = CU), so candidate B is DC */
+static void hevc_mpm_list(const HEnc* h, int cx, int cy, int list[3]) {
+    const HCU* l = hevc_nb_raw(h, cx, cy);
+    const int a = l && l->type == HCU_INTRA ? l->imode : 1;
+    if (a == 1) { list[0] = 0; list[1] = 1; list[2] = 26; return; }
+    list[0] = a; list[1] = 1; list[2] = a != 0 ? 0 : 26;
+}
+static int hevc_mode_bins(const int list[3], int mode) {      /* prev_intra_luma_pred_flag + mpm_idx / rem_intra_luma_pred_mode */
+    return mode == list[0] ? 2 : (mode == list[1] || mode == list[2]) ? 3 : 6;
+}
+/* Mode of an intra CU when params.hevc_intra_modes: SAD of a 16x16 prediction made from the CU's reconstructed top row,
+ * left column and corner (missing side: the other side's first sample, both missing: 128; planar takes top[15] /
+ * left[15] for the two far corners) + lambda x mode bins.  A decision rule, not a normative process. */
+static int hevc_choose_intra_mode(const HEnc* h, int cx, int cy) {
+    const Enc* e = h->e;
+    const Frame* f = h->rec;
+    const int row0 = slice_first_row(e, slice_of_row(e, cy));
+    const int aL = cx > 0, aT = cy > row0;
+    const uint8_t* r = f->y + (size_t)(16 * cy) * f->ys + 16 * cx;
+    const uint8_t* c = e->cur.y + (size_t)(16 * cy) * e->cur.ys + 16 * cx;
+    int top[16], left[16], corner;
+    for (int i = 0; i < 16; i++) { top[i] = aT ? r[-(ptrdiff_t)f->ys + i] : 0; left[i] = aL ? r[(ptrdiff_t)i * f->ys - 1] : 0; }
+    if (!aT && !aL) { for (int i = 0; i < 16; i++) top[i] = left[i] = 128; }
+    else if (!aT) { for (int i = 0; i < 16; i++) top[i] = left[0]; }
+    else if (!aL) { for (int i = 0; i < 16; i++) left[i] = top[0]; }
+    corner = aT && aL ? r[-(ptrdiff_t)f->ys - 1] : aT ? top[0] : aL ? left[0] : 128;
+    (void)corner;
+    int sum = 16;
+    for (int i = 0; i < 16; i++) sum += top[i] + left[i];
+    const int dc = sum >> 5;
+    int sad[4] = {0, 0, 0, 0};                         /* planar, DC, horizontal, vertical */
+    for (int y = 0; y < 16; y++)
+        for (int x = 0; x < 16; x++) {
+            const int s = c[(size_t)y * e->cur.ys + x];
+            const int pl = ((15 - x) * left[y] + (x + 1) * top[15] + (15 - y) * top[x] + (y + 1) * left[15] + 16) >> 5;
+            sad[0] += abs(s - pl); sad[1] += abs(s - dc); sad[2] += abs(s - left[y]); sad[3] += abs(s - top[x]);
+        }
+    static const int modes[4] = {0, 1, 10, 26};
+    int list[3];
+    hevc_mpm_list(h, cx, cy, list);
+    const int lam = vcp_lambda(h->qp);
+    int best = 1;
+    unsigned bestc = 0xffffffffu;
+    for (int k = 0; k < 4; k++) {
+        const unsigned cost = (unsigned)(sad[k] + lam * hevc_mode_bins(list, modes[k]));
+        if (cost < bestc) { bestc = cost; best = modes[k]; }
+    }
+    return best;
+}
+
 static void hevc_encode_intra_cu(HEnc* h, int cx, int cy) {
     HCU* cu = &h->cus[cy * h->e->mbw + cx];
     memset(cu, 0, sizeof *cu);
     cu->type = HCU_INTRA;
+    cu->imode = 1;
+    if (h->e->p.hevc_intra_modes) cu->imode = (uint8_t)hevc_choose_intra_mode(h, cx, cy);
     for (int z = 0; z < 4; z++) {
         const int xl = 16 * cx + 8 * (z & 1), yl = 16 * cy + 8 * (z >> 1);
         uint8_t pred[64];
-        hevc_intra_dc(h, 0, xl, yl, 8, pred);
+        hevc_intra_pred(h, 0, xl, yl, 8, cu->imode, pred);
         cu->cbf_y[z] = (uint8_t)hevc_code_block(h, 0, xl, yl, 8, pred, 1, cu->lv_y[z]);
-        hevc_intra_dc(h, 1, xl, yl, 4, pred);
+        hevc_intra_pred(h, 1, xl, yl, 4, cu->imode, pred);
         cu->cbf_cb[z] = (uint8_t)hevc_code_block(h, 1, xl >> 1, yl >> 1, 4, pred, 1, cu->lv_cb[z]);
-        hevc_intra_dc(h, 2, xl, yl, 4, pred);
+        hevc_intra_pred(h, 2, xl, yl, 4, cu->imode, pred);
         cu->cbf_cr[z] = (uint8_t)hevc_code_block(h, 2, xl >> 1, yl >> 1, 4, pred, 1, cu->lv_cr[z]);
     }
 }
@@ -635,9 +737,10 @@ static void hevc_write_tu_tree(Cabac* c, const HCU* cu, int intra) {
         if (any_cb) cabac_encode(c, HC_CBF_CHROMA + 1, cu->cbf_cb[z]);
         if (any_cr) cabac_encode(c, HC_CBF_CHROMA + 1, cu->cbf_cr[z]);
         cabac_encode(c, HC_CBF_LUMA + 0, cu->cbf_y[z]);
-        if (cu->cbf_y[z]) hevc_residual(c, cu->lv_y[z], 3, 0);
-        if (cu->cbf_cb[z]) hevc_residual(c, cu->lv_cb[z], 2, 1);
-        if (cu->cbf_cr[z]) hevc_residual(c, cu->lv_cr[z], 2, 2);
+        const int scan = hevc_scan_idx(cu->type == HCU_INTRA, cu->imode);   /* luma 8x8 and chroma 4x4 both qualify */
+        if (cu->cbf_y[z]) hevc_residual(c, cu->lv_y[z], 3, 0, scan);
+        if (cu->cbf_cb[z]) hevc_residual(c, cu->lv_cb[z], 2, 1, scan);
+        if (cu->cbf_cr[z]) hevc_residual(c, cu->lv_cr[z], 2, 2, scan);
     }
     (void)intra;
 }
@@ -665,8 +768,17 @@ static unsigned long long hevc_write_slice_data(HEnc* h, BW* b, int r0, int r1) 
                 if (!h->idr) cabac_encode(&c, HC_PRED_MODE, cu->type == HCU_INTRA);
                 cabac_encode(&c, HC_PART_MODE, 1);                       /* PART_2Nx2N */
                 if (cu->type == HCU_INTRA) {
-                    cabac_encode(&c, HC_PREV_INTRA, 1);                    /* prev_intra_luma_pred_flag */
-                    cabac_bypass(&c, 1); cabac_bypass(&c, 0);              /* mpm_idx = 1: DC in {planar, DC, 26} */
+                    int list[3];
+                    hevc_mpm_list(h, cx, cy, list);
+                    const int mi = cu->imode == list[0] ? 0 : cu->imode == list[1] ? 1 : cu->imode == list[2] ? 2 : -1;
+                    cabac_encode(&c, HC_PREV_INTRA, mi >= 0);              /* prev_intra_luma_pred_flag */
+                    if (mi >= 0) { cabac_bypass(&c, mi > 0); if (mi > 0) cabac_bypass(&c, mi > 1); }   /* mpm_idx: 0, 10, 11 */
+                    else {                                                 /* rem_intra_luma_pred_mode: 5 bits */
+                        int srt[3] = {list[0], list[1], list[2]}, rem = cu->imode;
+                        for (int a = 0; a < 2; a++) for (int b2 = a + 1; b2 < 3; b2++) if (srt[a] > srt[b2]) { const int t2 = srt[a]; srt[a] = srt[b2]; srt[b2] = t2; }
+                        for (int a = 2; a >= 0; a--) if (rem > srt[a]) rem--;
+                        for (int q = 4; q >= 0; q--) cabac_bypass(&c, (rem >> q) & 1);
+                    }
                     cabac_encode(&c, HC_CHROMA_MODE, 0);                   /* intra_chroma_pred_mode 4: derived from luma */
                     hevc_write_tu_tree(&c, cu, 1);
                 } else {

@@ -410,6 +410,33 @@ def test_hevc_oracle_sample_adaptive_offset():
         assert ps[1] >= ps[0] - 0.01, (kw, ps)
 
 
+def test_hevc_oracle_intra_modes():
+    """params.hevc_intra_modes (oracle only this round): planar / DC / horizontal / vertical per intra CU, signalled
+    through the MPM list or rem_intra_luma_pred_mode, with the mode-dependent coefficient scans (horizontal modes
+    scan vertically and vice versa) and the smoothed references of 8x8 planar.  The decoder must agree bit-exactly
+    in IDR pictures, across a scene cut inside a GOP, with SAO / half-sample motion on, and at a ragged size."""
+    if not arbiter.available():
+        pytest.skip("bundled FFmpeg decoder not present")
+    w, h, n = 320, 192, 6
+    a = synth.make_clip(w, h, 4, seed=1)
+    cut = np.concatenate([a, np.roll(a, 7777, axis=1)[:2], synth.make_clip(w, h, 3, seed=77, start=9)])
+    total = {0: 0, 1: 0}
+    for clip, cw, chh, gop, kw in ((synth.make_clip(w, h, n, seed=4), w, h, 2, dict(slices=3)),
+                                   (synth.make_clip(w, h, n, seed=5), w, h, 6, dict(slices=2, deblock_idc=1, hevc_sao=1)),
+                                   (cut, w, h, 60, dict(slices=2, hevc_subpel=1, hevc_sao=1)),
+                                   (synth.make_clip(208, 114, 5, seed=9), 208, 114, 5, dict(slices=1))):
+        for qp in (22, 32):
+            for im in (0, 1):
+                r = pyoracle.encode_hevc(pyoracle.make_params(cw, chh, codec=1, gop=gop, qp_i=qp - 2, qp_p=qp, hevc_intra_modes=im, **kw), clip)
+                total[im] += len(r["stream"])
+                if im:
+                    dec = arbiter.decode_annexb_hevc(r["stream"])
+                    assert len(dec) == clip.shape[0]
+                    for i in range(clip.shape[0]):
+                        assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i]), (kw, qp, i)
+    assert total[1] < total[0]                             # the extra modes pay for their signalling
+
+
 def test_hevc_tables_match_decoder_rodata():
     """CABAC initValues (tables 9-5..9-37) typed in the oracle must appear in the decoder's own tables."""
     import glob

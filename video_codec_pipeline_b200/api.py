@@ -33,7 +33,7 @@ class Params(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "width", "height", "fps_num", "fps_den", "codec", "gop", "rc_mode", "qp_i", "qp_p",
         "bitrate", "maxrate", "bufsize", "slices", "deblock_idc", "entropy", "in_fmt",
-        "in_width", "in_height", "faststart", "effort", "debug", "first_gop", "drop_audio", "transform8x8", "hevc_subpel", "hevc_sao")] + [("reserved", C.c_int32 * 6)]
+        "in_width", "in_height", "faststart", "effort", "debug", "first_gop", "drop_audio", "transform8x8", "hevc_subpel", "hevc_sao", "hevc_intra_modes")] + [("reserved", C.c_int32 * 5)]
 
 
 class FrameInfo(C.Structure):
