@@ -1,20 +1,25 @@
 // K6 — HEVC (ITU-T H.265) reconstruction kernels: the h265-* presets of the reference
 // (/root/reference/internal/config/config.go:47-50) on the same execution model as the H.264 path:
-// closed GOPs in lock-step, motion search shared with H.264 (pre-pass on originals + full-sample refine),
-// everything else macroblock- (here: coding-unit-) parallel, the IDR picture on an anti-diagonal wavefront.
+// closed GOPs in lock-step, motion search shared with H.264 (pre-pass on originals + refine on the
+// reconstruction), everything else coding-unit-parallel, intra CUs on an anti-diagonal wavefront.
 //
 // Stream structure (oracle/hevc_oracle.inc.c restates the same): Main profile, CTB = CU = 16x16 in raster
 // order, luma transform blocks 8x8 (the 16x16 root splits because MaxTb = 8), chroma 4x4, DCT only, DC intra
-// prediction per transform block, one 16x16 PU with full-sample luma vectors (chroma on half samples: 4-tap
-// filter), AMVP / merge (one candidate) / skip decided after all vectors exist (hevc_cuinfo_kernel), in-loop
-// deblocking as two order-free passes (hevc_deblock_kernel), SAO disabled.  Entropy coding: k5_cabac.cu (hevc_bins_kernel + the shared arithmetic coder).
+// prediction per transform block (every CU of an IDR picture; scene-cut CUs of P pictures), one 16x16 PU with
+// full-sample or (hevc_subpel) half-sample luma vectors read from the 8-tap planes of k2_hpel.cu, chroma by the
+// 4-tap filters, AMVP / merge (one candidate) / skip decided after all vectors exist (hevc_cuinfo_kernel), in-loop
+// deblocking as two order-free passes (hevc_deblock_kernel), optional SAO (hevc_sao_kernel).
+// Entropy coding: k5_cabac.cu (hevc_bins_kernel + the shared arithmetic coder).
 //
 //   hevc_p_recon_kernel : warp = CU; eight lanes per 8x8 luma transform block (a row, a column, a row each, through
 //                         shared memory), then four lanes per 4x4 chroma block the same way
 //   hevc_i_recon_kernel : CTA = (GOP, slice), wavefront over anti-diagonals, warp = CU, the four transform
-//                         units of a CU in z-order (each predicts from the reconstruction of the previous ones)
+//                         units of a CU in z-order (each predicts from the reconstruction of the previous ones);
+//                         <FIX>: only the CUs of a P picture that the refine flagged intra
 //   hevc_cuinfo_kernel  : thread = CU: merge candidate, AMVP list, vector difference, skip
 //   hevc_deblock_kernel : thread = 4-line segment of an 8x8-grid edge; vertical edges, then horizontal edges
+//   hevc_sao_kernel     : warp = CTB: edge-offset statistics on the deblocked picture, decision, filtered samples
+//                         into the slot's scratch plane; hevc_sao_copy_kernel moves them back
 //
 // Record layout per CU (same arrays as H.264): mbtype 0 intra / 1 inter / 2 skip; cbp bits 0-3 = cbf_luma of
 // the four TUs, bit 4 = merge_flag, bit 5 = mvp_l0_flag; modes bits 0-3 = cbf_cb, 4-7 = cbf_cr; levels:
