@@ -87,7 +87,8 @@ typedef struct vcpenc_params {
     int32_t transform8x8;      /* 1: High profile, transform_8x8_mode_flag: inter macroblocks use the
                                   8x8 integer transform (-profile:v high, the libx264 default)  */
     int32_t hevc_subpel;       /* HEVC: 1 = half-sample luma motion (8-tap interpolation planes per picture); set by
-                                  the argument parser for libx265 / hevc_nvenc                                  */
+                                  the argument parser for libx265 / hevc_nvenc.  2 = quarter samples as well:
+                                  oracle only so far (VCPENC_E_UNSUPPORTED)                                     */
     int32_t hevc_sao;          /* HEVC: 1 = sample adaptive offset on luma (edge offsets, one decision per coding tree
                                   block, taken on the deblocked picture)                                         */
     int32_t hevc_intra_modes;  /* HEVC: 1 = intra CUs choose among planar / DC / horizontal / vertical prediction (else DC only).

@@ -495,17 +495,19 @@ static int hevc_refine_cu(HEnc* h, int cx, int cy, int16_t mv[2]) {
     uint32_t bcost = best >> 4;
     mv[0] = (int16_t)bx; mv[1] = (int16_t)by;
     if (bcost < VCP_SUBPEL_SKIP_COST) return 0;
-    if (e->p.hevc_subpel) {
-        /* half-sample neighbours of the best full-sample position: raster order, strict improvement (the same rule
-         * as the H.264 refine).  Each position of each reference picture has ONE interpolated value, so a device
-         * implementation can take it from three half-sample planes built once per picture. */
+    /* half-sample neighbours of the best full-sample position, then (hevc_subpel = 2, oracle only so far) the
+     * quarter-sample neighbours of that: raster order, strict improvement (the same rule as the H.264 refine).
+     * Each position of each reference picture has ONE interpolated value, so the device takes the half-sample
+     * ones from three planes built once per picture (k2_hpel.cu). */
+    for (int step = 2; step >= 1 && e->p.hevc_subpel; step--) {
+        if (step == 1 && e->p.hevc_subpel < 2) break;
         uint32_t sb = (bcost << 4) | 0;
         int k = 1;
         const int ox = bx, oy = by;
         for (int dy = -1; dy <= 1; dy++)
             for (int dx = -1; dx <= 1; dx++) {
                 if (!dx && !dy) continue;
-                const int vx = ox + 2 * dx, vy = oy + 2 * dy;
+                const int vx = ox + step * dx, vy = oy + step * dy;
                 int sad = 0;
                 for (int y = 0; y < 16; y++)
                     for (int x = 0; x < 16; x++)

@@ -168,12 +168,13 @@ def test_hevc_mux_and_parameter_sets_host_only(built, tmp_path):
 
 
 def test_oracle_only_tools_are_refused_by_the_library(built):
-    """params.hevc_intra_modes exists in the oracle (pinned by the decoder) but not yet on the device: the library says
-    so with its own error class instead of silently encoding without the tool."""
-    p = api.default_params(320, 192, codec=1, hevc_intra_modes=1)
-    with pytest.raises(api.VcpencError) as e:
-        api.Session(p, 4)
-    assert e.value.code == 13
+    """params.hevc_intra_modes and hevc_subpel = 2 exist in the oracle (pinned by the decoder) but not yet on the
+    device: the library says so with its own error class instead of silently encoding without the tool."""
+    for kw in (dict(hevc_intra_modes=1), dict(hevc_subpel=2)):
+        p = api.default_params(320, 192, codec=1, **kw)
+        with pytest.raises(api.VcpencError) as e:
+            api.Session(p, 4)
+        assert e.value.code == 13, kw
 
 
 def test_verify_rejects_bad_files(built, tmp_path):

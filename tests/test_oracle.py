@@ -390,6 +390,30 @@ def test_hevc_oracle_half_sample_motion():
         assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i])
 
 
+def test_hevc_oracle_quarter_sample_motion():
+    """params.hevc_subpel = 2 (oracle only): the 7/8-tap quarter-sample filters.  Decoder-exact, and each precision
+    step pays off on a clip that moves by quarter samples."""
+    if not arbiter.available():
+        pytest.skip("bundled FFmpeg decoder not present")
+    w, h, n = 320, 192, 5
+    rng = np.random.default_rng(3)
+    big = rng.integers(0, 256, (4 * h + 64, 4 * w + 64)).astype(np.float64)
+    for _ in range(12):
+        big = (big + np.roll(big, 1, 0) + np.roll(big, -1, 0) + np.roll(big, 1, 1) + np.roll(big, -1, 1)) / 5.0
+    big = (big - big.min()) / (big.max() - big.min()) * 255.0
+    clip = np.stack([np.concatenate([np.clip(np.rint(big[i:i + 4 * h:4, 3 * i:3 * i + 4 * w:4]), 0, 255).astype(np.uint8).ravel(),
+                                     np.full(w * h // 2, 128, np.uint8)]) for i in range(n)])
+    size = {}
+    for sub in (0, 1, 2):
+        r = pyoracle.encode_hevc(pyoracle.make_params(w, h, codec=1, gop=n, qp_i=26, qp_p=28, hevc_subpel=sub, slices=2), clip)
+        dec = arbiter.decode_annexb_hevc(r["stream"])
+        assert len(dec) == n
+        for i in range(n):
+            assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i]), (sub, i)
+        size[sub] = len(r["stream"])
+    assert size[2] < size[1] < size[0]
+
+
 def test_hevc_oracle_sample_adaptive_offset():
     """params.hevc_sao: luma edge offsets decided per coding tree block on the deblocked picture.  The decoder must
     reproduce the oracle's reconstruction (syntax + process), with and without deblocking, 1..12 slices; SAO must

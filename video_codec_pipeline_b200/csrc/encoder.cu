@@ -129,7 +129,8 @@ int dev_alloc(vcpenc_session* s, T** p, size_t count, char* err, size_t errlen) 
 
 int check_params(const vcpenc_params& p, char* err, size_t errlen) {
     if (p.codec != VCPENC_CODEC_H264 && p.codec != VCPENC_CODEC_HEVC) { set_err(err, errlen, "unknown codec %d", p.codec); return VCPENC_E_ARGS; }
-    if (p.hevc_subpel < 0 || p.hevc_subpel > 1) { set_err(err, errlen, "bad hevc_subpel %d", p.hevc_subpel); return VCPENC_E_ARGS; }
+    if (p.hevc_subpel == 2) { set_err(err, errlen, "HEVC quarter-sample motion is implemented in the oracle only (device path: half samples)"); return VCPENC_E_UNSUPPORTED; }
+    if (p.hevc_subpel < 0 || p.hevc_subpel > 2) { set_err(err, errlen, "bad hevc_subpel %d", p.hevc_subpel); return VCPENC_E_ARGS; }
     if (p.hevc_intra_modes) { set_err(err, errlen, "HEVC intra modes beyond DC are implemented in the oracle only (device path: next round)"); return VCPENC_E_UNSUPPORTED; }
     if (p.hevc_sao < 0 || p.hevc_sao > 1) { set_err(err, errlen, "bad hevc_sao %d", p.hevc_sao); return VCPENC_E_ARGS; }
     if (p.entropy < 0 || p.entropy > 1) { set_err(err, errlen, "bad entropy coder %d", p.entropy); return VCPENC_E_ARGS; }
