@@ -69,10 +69,10 @@ def test_quant_dequant_tables():
     w = np.zeros(16, np.int32)
     w[0] = 6400
     lv = np.zeros(16, np.int16)
-    L.orc_quant4x4(w.ctypes.data_as(C.POINTER(C.c_int)), 28, 0, 0, lv.ctypes.data)
+    L.orc_quant4x4(w.ctypes.data_as(C.POINTER(C.c_int)), 28, 0, 0, C.c_void_p(lv.ctypes.data))
     assert lv[0] == (6400 * 8192 + (1 << 19) // 6) >> 19
     c = np.zeros(16, np.int32)
-    L.orc_dequant4x4(lv.ctypes.data, 28, 0, c.ctypes.data_as(C.POINTER(C.c_int)))
+    L.orc_dequant4x4(C.c_void_p(lv.ctypes.data), 28, 0, c.ctypes.data_as(C.POINTER(C.c_int)))
     assert c[0] == lv[0] * 16 << 4
     assert L.orc_lambda(12) == 1 and L.orc_lambda(24) == 4 and L.orc_lambda(36) == 16
 
@@ -88,15 +88,15 @@ def test_cavlc_block_known_answers():
     L = _lib()
     out = (C.c_uint8 * 64)()
     c = np.array([0, 3, 0, 1, -1, -1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0], np.int16)
-    n = L.orc_cavlc_block(c.ctypes.data, 16, 0, out, 64)
+    n = L.orc_cavlc_block(C.c_void_p(c.ctypes.data), 16, 0, out, 64)
     assert _bits(out, n) == "000010001110010111101101"
     # all-zero block, nC=0 -> coeff_token '1'
     z = np.zeros(16, np.int16)
-    n = L.orc_cavlc_block(z.ctypes.data, 16, 0, out, 64)
+    n = L.orc_cavlc_block(C.c_void_p(z.ctypes.data), 16, 0, out, 64)
     assert _bits(out, n) == "1"
     # chroma DC, single +1 at position 0: coeff_token(T1=1,TC=1) '1', sign '0', total_zeros(0)='1'
     c4 = np.array([1, 0, 0, 0], np.int16)
-    n = L.orc_cavlc_block(c4.ctypes.data, 4, -1, out, 64)
+    n = L.orc_cavlc_block(C.c_void_p(c4.ctypes.data), 4, -1, out, 64)
     assert _bits(out, n) == "101"
 
 
@@ -105,11 +105,11 @@ def test_luma_interpolation_flat_and_ramp():
     plane = np.full((32, 32), 77, np.uint8)
     for fy in range(4):
         for fx in range(4):
-            assert L.orc_luma_qpel(plane.ctypes.data, 32, 10, 10, fx, fy) == 77
+            assert L.orc_luma_qpel(C.c_void_p(plane.ctypes.data), 32, 10, 10, fx, fy) == 77
     ramp = np.tile((np.arange(32) * 4).astype(np.uint8), (32, 1))
-    assert L.orc_luma_qpel(ramp.ctypes.data, 32, 10, 10, 2, 0) == 42   # half-way between 40 and 44
-    assert L.orc_luma_qpel(ramp.ctypes.data, 32, 10, 10, 1, 0) == 41
-    assert L.orc_luma_qpel(ramp.ctypes.data, 32, 10, 10, 0, 2) == 40
+    assert L.orc_luma_qpel(C.c_void_p(ramp.ctypes.data), 32, 10, 10, 2, 0) == 42   # half-way between 40 and 44
+    assert L.orc_luma_qpel(C.c_void_p(ramp.ctypes.data), 32, 10, 10, 1, 0) == 41
+    assert L.orc_luma_qpel(C.c_void_p(ramp.ctypes.data), 32, 10, 10, 0, 2) == 40
 
 
 @pytest.mark.parametrize("entropy,t8", [(0, 0), (1, 0), (0, 1), (1, 1)], ids=["cavlc", "cabac", "cavlc-high", "cabac-high"])
