@@ -37,7 +37,8 @@ extern "C" {
 #define VCPENC_E_TIMEOUT 7     /* timeout_ms elapsed       ("编码超时")             */
 #define VCPENC_E_NOTENCODE 8   /* preset is not a video encode (-c copy, -vn): the
                                   caller should hand the task to a stock ffmpeg    */
-#define VCPENC_E_AUDIO 9       /* input has audio that would need encoding         */
+#define VCPENC_E_AUDIO 9       /* the input's audio cannot be carried into the output by the loaded FFmpeg libraries
+                                  (no decoder / no aac encoder): the caller may hand the task to a stock ffmpeg */
 #define VCPENC_E_VERIFY 10     /* verify: no valid video stream ("无有效视频流")     */
 #define VCPENC_E_OVERFLOW 11   /* output buffer too small                          */
 #define VCPENC_E_INTERNAL 12
@@ -82,8 +83,8 @@ typedef struct vcpenc_params {
                                   decisions resident for the parity taps            */
     int32_t first_gop;         /* index of the first GOP handed in (sharded encodes):
                                   keeps idr_pic_id alternating across shards        */
-    int32_t drop_audio;        /* -an: container inputs with an audio stream are accepted,
-                                  the audio is dropped (else VCPENC_E_AUDIO)         */
+    int32_t drop_audio;        /* -an: the input's audio is dropped (else it becomes an AAC track of the output:
+                                  stream copy of AAC-LC, otherwise decode + libavcodec `aac` at -b:a)            */
     int32_t transform8x8;      /* 1: High profile, transform_8x8_mode_flag: inter macroblocks use the
                                   8x8 integer transform (-profile:v high, the libx264 default)  */
     int32_t hevc_subpel;       /* HEVC: 1 = half-sample luma motion (8-tap interpolation planes per picture); set by
@@ -94,7 +95,8 @@ typedef struct vcpenc_params {
     int32_t hevc_intra_modes;  /* HEVC: 1 = intra CUs choose among planar / DC / horizontal / vertical prediction (else DC only).
                                   Implemented and pinned in the oracle; the device path does not have it yet:
                                   VCPENC_E_UNSUPPORTED                                                            */
-    int32_t reserved[5];
+    int32_t audio_bitrate;     /* -b:a (bits per second) for container inputs whose audio is re-encoded to AAC; 0: 128k */
+    int32_t reserved[4];
 } vcpenc_params;
 
 /* per coded picture, filled by the encode calls */
@@ -150,10 +152,10 @@ int vcpenc_device_count(void);           /* honours CUDA_VISIBLE_DEVICES; 0 if n
  * runs one consumer process per GPU under CUDA_VISIBLE_DEVICES (install.sh:279-297), where 0 is
  * right; a host that drives several GPUs from one process binds each worker thread with this. */
 int vcpenc_set_thread_device(int device);
-/* vcpenc_transcode keeps the encoder session and the page-locked staging buffer of the calling
- * thread for its next task (creating and freeing ~15 GB of device buffers costs more than encoding
- * a short clip).  A host that retires a worker thread releases them with this call; VCPENC_NO_CACHE=1
- * in the environment turns the reuse off. */
+/* vcpenc_transcode reuses encoder sessions (all device buffers of one geometry / preset; a process-wide pool,
+ * least recently used idle sessions are destroyed when memory is needed) and the two page-locked chunk buffers of
+ * the calling thread: creating and freeing them costs more than encoding a short clip.  A host that retires a worker
+ * thread releases its buffers (and every idle session) with this call; VCPENC_NO_CACHE=1 turns the reuse off. */
 void vcpenc_thread_release(void);
 const char* vcpenc_version(void);
 void vcpenc_default_params(vcpenc_params* p);
@@ -222,11 +224,26 @@ int vcpenc_probe_input(const char* path, int* width, int* height, int* fps_num, 
                        uint8_t* frames, size_t frames_cap, int max_frames, int* nframes, char* err,
                        size_t errlen);
 
+/* The audio side of a container input as vcpenc_transcode handles it (every encode preset carries `-c:a aac -b:a Nk`,
+ * internal/config/config.go:45-50): AAC-LC input is stream-copied, anything else is decoded and encoded with
+ * libavcodec's `aac` encoder at audio_bitrate (0: 128k).  Returns the raw AAC access units back to back in `data`
+ * with their sizes, the AudioSpecificConfig, and the encoder delay in samples.  Host-only. */
+int vcpenc_probe_audio(const char* path, int audio_bitrate, int* sample_rate, int* channels, int* copied, int* priming,
+                       uint8_t* asc, int asc_cap, int* asc_len, uint8_t* data, size_t data_cap, size_t* data_len,
+                       uint32_t* sizes, int sizes_cap, int* nframes, char* err, size_t errlen);
+
 /* Wrap an Annex-B stream produced above into an MP4 file (avc1/avcC, moov-first when
  * faststart).  Host-only. */
 int vcpenc_mux_mp4(const vcpenc_params* p, const uint8_t* annexb, size_t len,
                    const vcpenc_frame_info* info, int nframes, const char* path, char* err,
                    size_t errlen);
+
+/* Same with an AAC track: `aac` = raw access units back to back (aac_sizes[i] bytes each, 1024 samples per unit),
+ * asc = AudioSpecificConfig, priming = encoder delay in samples (edit list).  Host-only. */
+int vcpenc_mux_mp4_audio(const vcpenc_params* p, const uint8_t* annexb, size_t len, const vcpenc_frame_info* info,
+                         int nframes, const uint8_t* aac, const uint32_t* aac_sizes, int aac_frames, int sample_rate,
+                         int channels, int priming, const uint8_t* asc, int asc_len, const char* path, char* err,
+                         size_t errlen);
 
 #ifdef __cplusplus
 }

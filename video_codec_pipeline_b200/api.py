@@ -33,7 +33,7 @@ class Params(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "width", "height", "fps_num", "fps_den", "codec", "gop", "rc_mode", "qp_i", "qp_p",
         "bitrate", "maxrate", "bufsize", "slices", "deblock_idc", "entropy", "in_fmt",
-        "in_width", "in_height", "faststart", "effort", "debug", "first_gop", "drop_audio", "transform8x8", "hevc_subpel", "hevc_sao", "hevc_intra_modes")] + [("reserved", C.c_int32 * 5)]
+        "in_width", "in_height", "faststart", "effort", "debug", "first_gop", "drop_audio", "transform8x8", "hevc_subpel", "hevc_sao", "hevc_intra_modes", "audio_bitrate")] + [("reserved", C.c_int32 * 4)]
 
 
 class FrameInfo(C.Structure):
@@ -292,6 +292,34 @@ def probe_input(path, max_frames=0):
     return info
 
 
+def probe_audio(path, audio_bitrate=0):
+    """The audio side of a container input as transcode() handles it: dict(sample_rate, channels, copied, priming,
+    asc, frames=[bytes...]) -- raw AAC access units (stream copy of AAC-LC, else decode + libavcodec aac)."""
+    L = lib()
+    ffmpeg_libdir()
+    ip = C.POINTER(C.c_int)
+    L.vcpenc_probe_audio.argtypes = [C.c_char_p, C.c_int, ip, ip, ip, ip, C.c_void_p, C.c_int, ip, C.c_void_p, C.c_size_t,
+                                     C.POINTER(C.c_size_t), C.c_void_p, C.c_int, ip, C.c_char_p, C.c_size_t]
+    rate, ch, copied, prim, alen, nfr = (C.c_int(0) for _ in range(6))
+    dlen = C.c_size_t(0)
+    err = C.create_string_buffer(512)
+    asc = np.zeros(64, np.uint8)
+    cap = 64 << 20
+    data = np.empty(cap, np.uint8)
+    sizes = np.empty(1 << 20, np.uint32)
+    rc = L.vcpenc_probe_audio(os.fsencode(path), int(audio_bitrate), C.byref(rate), C.byref(ch), C.byref(copied), C.byref(prim),
+                              asc.ctypes.data, 64, C.byref(alen), data.ctypes.data, cap, C.byref(dlen), sizes.ctypes.data, sizes.size,
+                              C.byref(nfr), err, 512)
+    if rc:
+        raise VcpencError(rc, err.value.decode(errors="replace"))
+    frames, o = [], 0
+    for k in range(nfr.value):
+        frames.append(data[o:o + int(sizes[k])].tobytes())
+        o += int(sizes[k])
+    return {"sample_rate": rate.value, "channels": ch.value, "copied": bool(copied.value), "priming": prim.value,
+            "asc": asc[:alen.value].tobytes(), "frames": frames}
+
+
 def thread_release():
     """Free the session / pinned buffer transcode() keeps for the calling thread."""
     lib().vcpenc_thread_release()
@@ -333,8 +361,11 @@ def verify(path):
         raise VcpencError(rc, err.value.decode(errors="replace"))
 
 
-def mux_mp4(params: Params, stream: np.ndarray, info, path):
+def mux_mp4(params: Params, stream: np.ndarray, info, path, audio=None):
+    """audio: dict as returned by probe_audio() -> an AAC track beside the video."""
     L = lib()
+    if audio is not None:
+        return _mux_mp4_audio(L, params, stream, info, path, audio)
     n = len(info)
     fi = (FrameInfo * n)()
     for k, (off, size, idr, qp) in enumerate(info):
@@ -343,5 +374,24 @@ def mux_mp4(params: Params, stream: np.ndarray, info, path):
     err = C.create_string_buffer(512)
     rc = L.vcpenc_mux_mp4(C.byref(params), stream.ctypes.data, stream.size, C.cast(fi, C.c_void_p), n,
                           os.fsencode(path), err, 512)
+    if rc:
+        raise VcpencError(rc, err.value.decode(errors="replace"))
+
+
+def _mux_mp4_audio(L, params, stream, info, path, audio):
+    n = len(info)
+    fi = (FrameInfo * n)()
+    for k, (off, size, idr, qp) in enumerate(info):
+        fi[k].offset, fi[k].size, fi[k].is_idr, fi[k].qp = off, size, idr, qp
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    aac = np.frombuffer(b"".join(audio["frames"]), np.uint8)
+    sizes = np.array([len(f) for f in audio["frames"]], np.uint32)
+    asc = np.frombuffer(audio["asc"], np.uint8)
+    L.vcpenc_mux_mp4_audio.argtypes = [C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]
+    err = C.create_string_buffer(512)
+    rc = L.vcpenc_mux_mp4_audio(C.byref(params), stream.ctypes.data, stream.size, C.cast(fi, C.c_void_p), n, aac.ctypes.data,
+                                sizes.ctypes.data, len(sizes), audio["sample_rate"], audio["channels"], audio["priming"],
+                                asc.ctypes.data, asc.size, os.fsencode(path), err, 512)
     if rc:
         raise VcpencError(rc, err.value.decode(errors="replace"))

@@ -137,7 +137,10 @@ class _Decoder:
     def __init__(self, name=b"h264", threads=0, codecpar=None):
         avutil, avcodec, _ = _load()
         self.avutil, self.avcodec = avutil, avcodec
-        codec = avcodec.avcodec_find_decoder_by_name(name)
+        if name is None and codecpar:
+            codec = avcodec.avcodec_find_decoder(C.c_int.from_address(codecpar + 4).value)   # AVCodecParameters.codec_id
+        else:
+            codec = avcodec.avcodec_find_decoder_by_name(name)
         if not codec:
             raise RuntimeError("decoder not found: %r" % name)
         self.ctx = avcodec.avcodec_alloc_context3(codec)
@@ -352,6 +355,91 @@ def decode_file(path, threads=0):
             dec.close()
     finally:
         avformat.avformat_close_input(C.byref(fmt))
+
+
+def _audio_frame_to_float(fr: _AVFrameHead, channels: int) -> np.ndarray:
+    """decoded audio AVFrame -> float32 [nb_samples, channels] (fltp, flt, s16, s16p)."""
+    n = fr.nb_samples
+    ext = C.cast(fr.extended_data, C.POINTER(C.c_void_p))
+    if fr.format == 8:      # fltp
+        return np.stack([np.frombuffer((C.c_float * n).from_address(ext[c]), np.float32).copy() for c in range(channels)], axis=1)
+    if fr.format == 3:      # flt
+        return np.frombuffer((C.c_float * (n * channels)).from_address(ext[0]), np.float32).copy().reshape(n, channels)
+    if fr.format == 1:      # s16
+        return np.frombuffer((C.c_int16 * (n * channels)).from_address(ext[0]), np.int16).astype(np.float32).reshape(n, channels) / 32768.0
+    if fr.format == 6:      # s16p
+        return np.stack([np.frombuffer((C.c_int16 * n).from_address(ext[c]), np.int16).astype(np.float32) / 32768.0 for c in range(channels)], axis=1)
+    raise RuntimeError("unexpected sample format %d" % fr.format)
+
+
+def decode_adts(data: bytes, channels: int) -> np.ndarray:
+    """ADTS AAC stream -> float32 [samples, channels] through libavcodec's aac decoder."""
+    avutil, avcodec, _ = _load()
+    dec = _Decoder(b"aac")
+    out = []
+    o = 0
+    pkts = []
+    while o + 7 <= len(data):
+        n = ((data[o + 3] & 3) << 11) | (data[o + 4] << 3) | (data[o + 5] >> 5)
+        if n < 7 or o + n > len(data):
+            break
+        pkts.append(data[o:o + n])
+        o += n
+    frame = dec.frame
+    def drain():
+        while avcodec.avcodec_receive_frame(dec.ctx, frame) >= 0:
+            out.append(_audio_frame_to_float(_AVFrameHead.from_address(frame), channels))
+            avutil.av_frame_unref(frame)
+    for p in pkts:
+        avcodec.av_new_packet(dec.pkt, len(p))
+        ph = _AVPacketHead.from_address(dec.pkt)
+        C.memmove(ph.data, p, len(p))
+        avcodec.avcodec_send_packet(dec.ctx, dec.pkt)
+        avcodec.av_packet_unref(dec.pkt)
+        drain()
+    avcodec.avcodec_send_packet(dec.ctx, None)
+    drain()
+    dec.close()
+    return np.concatenate(out, axis=0) if out else np.zeros((0, channels), np.float32)
+
+
+def decode_audio_file(path):
+    """(first audio stream of a container file) -> (codec_id, float32 [samples, channels]) via libavformat + libavcodec;
+    None if the file has no audio stream."""
+    avutil, avcodec, avformat = _load()
+    ctx = _open_input(path)
+    try:
+        ai = avformat.av_find_best_stream(ctx, 1, -1, -1, None, 0)
+        if ai < 0:
+            return None
+        streams = C.cast(C.c_void_p.from_address(ctx.value + 48).value, C.POINTER(C.c_void_p))
+        st = streams[ai]
+        par = C.c_void_p.from_address(st + 16).value
+        codec_id = C.c_int.from_address(par + 4).value
+        dec = _Decoder(None, codecpar=par)
+        avutil.av_opt_get_chlayout.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
+        lay = (C.c_int * 6)()
+        avutil.av_opt_get_chlayout(dec.ctx, b"ch_layout", 0, lay)
+        channels = max(1, lay[1])
+        out = []
+        frame = dec.frame
+        def drain():
+            while avcodec.avcodec_receive_frame(dec.ctx, frame) >= 0:
+                out.append(_audio_frame_to_float(_AVFrameHead.from_address(frame), channels))
+                avutil.av_frame_unref(frame)
+        pkt = dec.pkt
+        while avformat.av_read_frame(ctx, pkt) >= 0:
+            ph = _AVPacketHead.from_address(pkt)
+            if ph.stream_index == ai:
+                avcodec.avcodec_send_packet(dec.ctx, pkt)
+                drain()
+            avcodec.av_packet_unref(pkt)
+        avcodec.avcodec_send_packet(dec.ctx, None)
+        drain()
+        dec.close()
+        return codec_id, (np.concatenate(out, axis=0) if out else np.zeros((0, channels), np.float32))
+    finally:
+        avformat.avformat_close_input(C.byref(ctx))
 
 
 def psnr(a: np.ndarray, b: np.ndarray) -> float:

@@ -33,6 +33,7 @@ static long parse_rate(const char* s) {
     else if (*end == 'm' || *end == 'M') { v *= 1000000; end++; }
     else if (*end == 'g' || *end == 'G') { v *= 1000000000; end++; }
     if (*end != 0) return -1;
+    if (v > 2147483647.0) return -1;   // params hold int32 bits per second
     return (long)v;
 }
 
@@ -94,9 +95,14 @@ extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_param
             if (p->entropy < 0 && !strcmp(v, "baseline")) p->entropy = 0;
             p->transform8x8 = !strncmp(v, "high", 4) ? 1 : 0;   // baseline, main: 4x4 transform only
         } else if (t == "-tune" || t == "-level" || t == "-threads" || t == "-refs" ||
-                   t == "-c:a" || t == "-acodec" || t == "-b:a" || t == "-ar" || t == "-ac" || t == "-f" ||
+                   t == "-c:a" || t == "-acodec" || t == "-ar" || t == "-ac" || t == "-f" ||
                    t == "-rc" || t == "-rc-lookahead" || t == "-x264-params" || t == "-x264opts") {
             if (!need(&v)) return VCPENC_E_ARGS;  // accepted, no effect on this encoder
+        } else if (t == "-b:a" || t == "-ab") {
+            if (!need(&v)) return VCPENC_E_ARGS;
+            const long r = parse_rate(v);
+            if (r <= 0 || r > 2000000) { set_err(err, errlen, "bad audio bitrate '%s'", v); return VCPENC_E_ARGS; }
+            p->audio_bitrate = (int32_t)r;
         } else if (t == "-x265-params") {
             // x265's own option string (key=value pairs joined by ':'): sao / no-sao and the sub-sample search are understood
             if (!need(&v)) return VCPENC_E_ARGS;

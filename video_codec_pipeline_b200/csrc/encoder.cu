@@ -20,6 +20,7 @@
 #include "../../include/vcpenc.h"
 #include "host_bits.h"
 #include "vcp_dev.cuh"
+#include "vcp_tma.cuh"
 
 #define CK(call)                                                                          \
     do {                                                                                  \
@@ -61,6 +62,7 @@ struct vcpenc_session {
     vcpenc_params p{};
     VcpGeom g{};
     VcpBufs b{};
+    VcpTmaps tm{};                              // tensor maps of the planes the motion search reads through TMA
     int device = 0;
     int max_frames = 0, nframes = 0, ngop_max = 0, ring = 2;
     int gop_base = 0;  // clip-level index of the first resident GOP
@@ -223,6 +225,38 @@ void k1_chain(vcpenc_session* s, const uint8_t* din, int n0, int cnt, cudaStream
 }
 
 }  // namespace
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: libvcpenc.so does not link libcuda, so it still
+// loads (for parse / verify / mux) on a host without a driver.
+int vcp_make_tmap(CUtensorMap* m, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); p = nullptr; }
+        return (EncodeFn)p;
+    }();
+    if (!fn) return -1;
+    cuuint64_t d[5]; cuuint64_t st[4]; cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; i++) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; i++) st[i] = strides_bytes[i];
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, base, d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+// free / total bytes of a device (transcode.cpp: session pool accounting); 0 on failure
+size_t vcp_device_free_bytes(int device, size_t* total) {
+    size_t f = 0, t = 0;
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&f, &t) != cudaSuccess) { cudaGetLastError(); f = t = 0; }
+    if (cur >= 0) cudaSetDevice(cur);
+    if (total) *total = t;
+    return f;
+}
 
 extern "C" {
 
@@ -427,6 +461,22 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
         CKS(cudaMemcpy(ri, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         b.rowinfo = ri;
     }
+    {
+        // Tensor maps (vcp_tma.cuh): the half-res and full-res originals as (x, row, frame), the reconstruction
+        // ring as (x, row, plane, slot).  Coordinates are plane coordinates (borders included), so a window
+        // that leaves the picture simply reads the replicated border.
+        const uint64_t hrows = (uint64_t)(g.ch / 2 + 2 * VCP_PAD1), yrows = (uint64_t)(g.ch + 2 * VCP_PAD);
+        const uint64_t hd[3] = {(uint64_t)g.hs, hrows, N}, hst[2] = {(uint64_t)g.hs, g.hsize};
+        const uint64_t yd[3] = {(uint64_t)g.ys, yrows, N}, yst[2] = {(uint64_t)g.ys, g.ysize};
+        const uint64_t rd[4] = {(uint64_t)g.ys, yrows, VCP_REC_PLANES, G * s->ring}, rst[3] = {(uint64_t)g.ys, g.ysize, VCP_REC_PLANES * g.ysize};
+        const uint32_t b_hwin[3] = {VCP_L1_WIN_W, VCP_L1_WIN_H, 1}, b_hcur[3] = {VCP_L1_CUR_W, 8, 1};
+        const uint32_t b_yref[3] = {VCP_L0_REF_W, VCP_L0_REF_H, 1}, b_ycur[3] = {16, 16, 1};
+        const uint32_t b_rec4[4] = {VCP_RF_WIN_W, VCP_RF_WIN_H, 4, 1}, b_rec1[4] = {VCP_RF_WIN_W, VCP_RF_WIN_H, 1, 1};
+        int bad = vcp_make_tmap(&s->tm.h_win, b.src_h, 3, hd, hst, b_hwin) | vcp_make_tmap(&s->tm.h_cur, b.src_h, 3, hd, hst, b_hcur) |
+                  vcp_make_tmap(&s->tm.y_ref, b.src_y, 3, yd, yst, b_yref) | vcp_make_tmap(&s->tm.y_cur, b.src_y, 3, yd, yst, b_ycur) |
+                  vcp_make_tmap(&s->tm.rec4, b.rec_y, 4, rd, rst, b_rec4) | vcp_make_tmap(&s->tm.rec1, b.rec_y, 4, rd, rst, b_rec1);
+        if (bad) { set_err(err, errlen, "cuTensorMapEncodeTiled failed (%d): the motion search needs TMA (sm_90+ driver)", bad); vcpenc_session_destroy(s); return VCPENC_E_CUDA; }
+    }
     if (pp->debug) {
         TRY(dev_alloc(s, &s->dbg_mv, N * nmb, err, errlen));
         TRY(dev_alloc(s, &s->dbg_type, N * nmb, err, errlen));
@@ -565,7 +615,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
     if (s->streamed && s->profile) CK(cudaStreamSynchronize(s->st_up));   // profiling was switched on after an asynchronous upload
     if (s->profile) {
         Prof pr(s, VCPENC_K_ME_PRE);
-        vcp_launch_me_prepass(g, b, N, gop, -1, s->st);
+        vcp_launch_me_prepass(g, b, s->tm, N, gop, -1, s->st);
     } else {
         // picture by picture and group by group on its own stream: chain step t of a group only waits for
         // the vectors of picture t of its GOPs.  Resident input: pictures outermost (every group gets its
@@ -576,7 +626,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
             int gA, gB;
             group_gops(s, N, ng, k, &gA, &gB);
             s->launches += 1;
-            vcp_launch_me_prepass(g, b, N, gop, t, s->st_pre, gA, gB);
+            vcp_launch_me_prepass(g, b, s->tm, N, gop, t, s->st_pre, gA, gB);
             CK(cudaEventRecord(s->ev_pre_t[(size_t)k * s->pre_T + t], s->st_pre));
             return VCPENC_OK;
         };
@@ -617,7 +667,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 if (t == 0) { Prof pr(s, VCPENC_K_I_RECON, 1, st); vcp_launch_hevc_i_recon(g, bt, sp, st); }
                 else {
                     if (!s->profile) CK(cudaStreamWaitEvent(st, s->ev_pre_t[(size_t)k * s->pre_T + t], 0));
-                    { Prof pr(s, VCPENC_K_ME_REFINE, 1, st); vcp_launch_me_refine(g, bt, sp, st); }
+                    { Prof pr(s, VCPENC_K_ME_REFINE, 1, st); vcp_launch_me_refine(g, bt, s->tm, sp, st); }
                     { Prof pr(s, VCPENC_K_P_RECON, 2, st); vcp_launch_hevc_p_recon(g, bt, sp, st); vcp_launch_hevc_i_fix(g, bt, sp, st); }
                     { Prof pr(s, VCPENC_K_MBINFO, 1, st); vcp_launch_hevc_cuinfo(g, bt, sp, st); }
                 }
@@ -631,7 +681,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 vcp_launch_i_recon(g, bt, sp, st);
             } else {
                 if (!s->profile) CK(cudaStreamWaitEvent(st, s->ev_pre_t[(size_t)k * s->pre_T + t], 0));
-                { Prof pr(s, VCPENC_K_ME_REFINE, 1, st); vcp_launch_me_refine(g, bt, sp, st); }
+                { Prof pr(s, VCPENC_K_ME_REFINE, 1, st); vcp_launch_me_refine(g, bt, s->tm, sp, st); }
                 { Prof pr(s, VCPENC_K_P_RECON, 2, st); vcp_launch_p_recon(g, bt, sp, st); vcp_launch_i_fix(g, bt, sp, st); }
                 { Prof pr(s, VCPENC_K_MBINFO, 1, st); vcp_launch_mbinfo(g, bt, sp, st); }
             }

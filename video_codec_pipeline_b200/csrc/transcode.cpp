@@ -7,13 +7,19 @@
 //   * deadline  -> "编码超时", parent cancel -> "任务被取消" (:387-392)
 //   * on failure the caller removes the partial output (:264); we also do not leave one
 //   * stdout/stderr are inherited: progress lines go to stderr in key=value form
-// Frames are pulled in chunks of whole GOPs, pushed through the device session (K1..K5) and
-// the resulting access units are appended to the muxer; no frame ever takes a CPU encode path.
+// Frames are pulled in chunks of whole GOPs by a reader thread into one of two page-locked buffers
+// while the device session (K1..K5) encodes the other; the access units of a chunk go straight into
+// the output file (mux_mp4.cpp), with the input's audio beside them; no frame ever takes a CPU encode
+// path.  Cancellation and the deadline are polled once per GOP while reading and between the stages of
+// a chunk.
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -56,6 +62,8 @@ struct Y4mSource : FrameSource {
             return VCPENC_E_FORMAT;
         }
         if (width <= 0 || height <= 0) { set_err(err, errlen, "bad y4m header"); return VCPENC_E_FORMAT; }
+        struct stat sb;
+        if (stat(path, &sb) == 0 && sb.st_size > 0) est_frames = (long)((size_t)sb.st_size / (fbytes() + 6)) + 1;
         return VCPENC_OK;
     }
     int read(uint8_t* dst, int max, char* err, size_t errlen) override {
@@ -81,6 +89,8 @@ struct RawSource : FrameSource {
         width = p.in_width; height = p.in_height; fps_num = p.fps_num; fps_den = p.fps_den;
         f = fopen(path, "rb");
         if (!f) { set_err(err, errlen, "cannot open %s", path); return VCPENC_E_IO; }
+        struct stat sb;
+        if (stat(path, &sb) == 0 && sb.st_size > 0) est_frames = (long)((size_t)sb.st_size / fbytes()) + 1;
         return VCPENC_OK;
     }
     int read(uint8_t* dst, int max, char*, size_t) override {
@@ -99,62 +109,113 @@ bool ends_with(const std::string& s, const char* suf) {
     return true;
 }
 
-struct PinnedBuf {
-    uint8_t* p = nullptr;
-    ~PinnedBuf() { if (p) vcpenc_host_free(p); }
-};
-
 }  // namespace
+
 
 static thread_local int t_device = 0;
 
-// Per-thread reuse across tasks: the session (all device buffers) and the pinned staging buffer.
-// Measured on the task-flow harness: session create + destroy 0.1-1.4 s and cudaMallocHost 0.1-0.3 s
-// per task against 0.13 s of GPU work for a 120-frame 1080p clip.
+// encoder.cu: free / total bytes of a device (0 on failure)
+size_t vcp_device_free_bytes(int device, size_t* total);
+
+// ---------------------------------------------------------------------------------------------
+// Reuse across tasks.  Measured on the task-flow harness: session create + destroy 0.1-1.4 s and
+// cudaMallocHost 0.1-0.3 s per task against 0.13 s of GPU work for a 120-frame 1080p clip.
+//   * sessions (all device buffers of one geometry / preset) live in a PROCESS-WIDE pool keyed by
+//     (device, parameters): a worker checks one out for a task and hands it back; idle sessions are
+//     destroyed least-recently-used first when a create fails for lack of memory, when the pool holds
+//     more than kPoolSlots, or when the idle ones exceed half of the device's memory;
+//   * the two page-locked chunk buffers belong to the calling thread.
+// ---------------------------------------------------------------------------------------------
 namespace {
-constexpr int kCacheSlots = 16;   // mixed task sizes (720p / 1080p / 4K of config #5) each keep their session
-struct CachedSession {
+constexpr int kPoolSlots = 8;
+struct PoolEntry {
     vcpenc_session* ses = nullptr;
     vcpenc_params key{};
     int max_frames = 0, device = -1;
+    size_t bytes = 0;
     unsigned long stamp = 0;
+    bool in_use = false;
 };
+std::mutex g_pool_mu;
+std::vector<PoolEntry> g_pool;
+unsigned long g_pool_clock = 0;
+
 struct ThreadCache {
-    CachedSession slot[kCacheSlots];
-    unsigned long clock = 0;
-    uint8_t* pinned = nullptr;
-    size_t pinned_bytes = 0;
+    uint8_t* pinned[2] = {nullptr, nullptr};
+    size_t pinned_bytes[2] = {0, 0};
 };
 thread_local ThreadCache t_cache;
 bool cache_enabled() { static const bool on = getenv("VCPENC_NO_CACHE") == nullptr; return on; }
 bool same_key(vcpenc_params a, vcpenc_params b) { a.first_gop = b.first_gop = 0; return memcmp(&a, &b, sizeof a) == 0; }
+
+// destroy the least recently used idle session of `device` (any device if < 0); pool lock held
+bool evict_one_locked(int device) {
+    int victim = -1;
+    for (int i = 0; i < (int)g_pool.size(); i++)
+        if (!g_pool[i].in_use && (device < 0 || g_pool[i].device == device) && (victim < 0 || g_pool[i].stamp < g_pool[victim].stamp)) victim = i;
+    if (victim < 0) return false;
+    vcpenc_session_destroy(g_pool[victim].ses);
+    g_pool.erase(g_pool.begin() + victim);
+    return true;
+}
 }  // namespace
 
-// session of `want` frames on `device` for parameters p: from the calling thread's cache, else new
-// (and cached).  *cached tells whether the cache owns it.
-int acquire_session(const vcpenc_params& p, int device, int want, vcpenc_session** out, bool* cached, char* err, size_t errlen) {
-    *cached = false;
-    if (cache_enabled())
-        for (auto& c : t_cache.slot)
-            if (c.ses && c.device == device && c.max_frames >= want && same_key(c.key, p)) {
-                c.stamp = ++t_cache.clock; *out = c.ses; *cached = true;
+// session of `want` frames on `device` for parameters p: an idle one from the pool, else new
+int acquire_session(const vcpenc_params& p, int device, int want, vcpenc_session** out, char* err, size_t errlen) {
+    if (cache_enabled()) {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (auto& c : g_pool)
+            if (!c.in_use && c.device == device && c.max_frames >= want && same_key(c.key, p)) {
+                c.in_use = true; c.stamp = ++g_pool_clock; *out = c.ses;
                 return VCPENC_OK;
             }
-    CachedSession* victim = nullptr;
-    if (cache_enabled()) {   // an empty slot, else the one with the same parameters but too small, else the least recently used
-        for (auto& c : t_cache.slot) if (!c.ses) { victim = &c; break; }
-        if (!victim) for (auto& c : t_cache.slot) if (same_key(c.key, p) && c.device == device) { victim = &c; break; }
-        if (!victim) { victim = &t_cache.slot[0]; for (auto& c : t_cache.slot) if (c.stamp < victim->stamp) victim = &c; }
-        if (victim->ses) { vcpenc_session_destroy(victim->ses); *victim = CachedSession(); }
+        // an idle session with the same parameters but too small is of no further use
+        for (size_t i = 0; i < g_pool.size(); i++)
+            if (!g_pool[i].in_use && g_pool[i].device == device && same_key(g_pool[i].key, p)) { vcpenc_session_destroy(g_pool[i].ses); g_pool.erase(g_pool.begin() + i); break; }
     }
-    const int rc = vcpenc_session_create(&p, device, want, out, err, errlen);
+    size_t total = 0;
+    const size_t before = vcp_device_free_bytes(device, &total);
+    int rc;
+    for (;;) {
+        rc = vcpenc_session_create(&p, device, want, out, err, errlen);
+        if (rc != VCPENC_E_CUDA) break;
+        // most likely out of memory: give back what idle sessions hold on this device and try again
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!evict_one_locked(device)) break;
+    }
     if (rc) return rc;
-    if (victim) { victim->ses = *out; victim->key = p; victim->max_frames = want; victim->device = device; victim->stamp = ++t_cache.clock; *cached = true; }
+    if (cache_enabled()) {
+        const size_t after = vcp_device_free_bytes(device, nullptr);
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        PoolEntry e;
+        e.ses = *out; e.key = p; e.max_frames = want; e.device = device; e.in_use = true; e.stamp = ++g_pool_clock;
+        e.bytes = before > after ? before - after : 0;
+        g_pool.push_back(e);
+        while ((int)g_pool.size() > kPoolSlots && evict_one_locked(-1)) {}
+    }
     return VCPENC_OK;
 }
-void forget_session(vcpenc_session* ses) {   // after a failure the session's state is not trusted
-    vcpenc_session_destroy(ses);
-    for (auto& c : t_cache.slot) if (c.ses == ses) c = CachedSession();
+
+// hand a session back; `ok` false: its state is not trusted after a failure
+void release_session(vcpenc_session* ses, bool ok) {
+    if (!ses) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (size_t i = 0; i < g_pool.size(); i++)
+        if (g_pool[i].ses == ses) {
+            if (!ok) { vcpenc_session_destroy(ses); g_pool.erase(g_pool.begin() + i); return; }
+            g_pool[i].in_use = false; g_pool[i].stamp = ++g_pool_clock;
+            // idle sessions may hold at most half of the device
+            const int device = g_pool[i].device;
+            size_t total = 0;
+            vcp_device_free_bytes(device, &total);
+            for (;;) {
+                size_t idle = 0;
+                for (const auto& c : g_pool) if (!c.in_use && c.device == device) idle += c.bytes;
+                if (total == 0 || idle <= total / 2 || !evict_one_locked(device)) break;
+            }
+            return;
+        }
+    vcpenc_session_destroy(ses);   // not pooled (VCPENC_NO_CACHE)
 }
 
 // GPUs one task may use: VCPENC_GPUS=N|all shards the closed GOPs of every chunk across N devices
@@ -168,9 +229,10 @@ int task_gpus() {
 }
 
 extern "C" void vcpenc_thread_release(void) {
-    for (auto& c : t_cache.slot) if (c.ses) vcpenc_session_destroy(c.ses);
-    if (t_cache.pinned) vcpenc_host_free(t_cache.pinned);
+    for (int i = 0; i < 2; i++) if (t_cache.pinned[i]) vcpenc_host_free(t_cache.pinned[i]);
     t_cache = ThreadCache();
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    while (evict_one_locked(-1)) {}
 }
 extern "C" int vcpenc_set_thread_device(int device) {
     if (device < 0 || device >= vcpenc_device_count()) return VCPENC_E_NODEVICE;
@@ -182,9 +244,9 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
                                 int timeout_ms, volatile int* cancel, char* err, size_t errlen) {
     using clock = std::chrono::steady_clock;
     const auto t0 = clock::now();
-    // VCPENC_TRACE=1: where the wall time of a task goes (open / pinned alloc / read+decode / session / GPU / mux)
+    // VCPENC_TRACE=1: where the wall time of a task goes (open / pinned alloc / waiting for the reader / session / GPU / mux)
     const bool trace = getenv("VCPENC_TRACE") != nullptr;
-    double t_open = 0, t_alloc = 0, t_read = 0, t_create = 0, t_gpu = 0, t_mux = 0;
+    double t_open = 0, t_alloc = 0, t_wait = 0, t_create = 0, t_gpu = 0, t_mux = 0;
     auto lap = [&](clock::time_point& from) { const auto now = clock::now(); const double d = std::chrono::duration<double>(now - from).count(); from = now; return d; };
     auto tl = t0;
     if (!input || !output) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
@@ -211,7 +273,7 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
         p.in_width = p.in_height = 0;   // consumed as the input size
     } else {
         // container input: what the producer forwards (.mp4 .mkv .avi .mov .webm, cmd/producer.go:485-488)
-        rc = open_container_source(input, p.drop_audio != 0, &src, err, errlen);
+        rc = open_container_source(input, p.drop_audio != 0, p.audio_bitrate, &src, err, errlen);
         if (rc) return rc;
         if (p.in_width > 0 && p.width == 0) { p.width = p.in_width; p.height = p.in_height; }   // -s after -i = output size
     }
@@ -232,141 +294,234 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
     if ((p.width & 1) || (p.height & 1) || p.width < 16 || p.height < 16) { set_err(err, errlen, "unsupported picture size %dx%d", p.width, p.height); return VCPENC_E_FORMAT; }
     if (p.slices == 0) p.slices = vcp_auto_slices((p.height + 15) / 16, p.entropy);
     if (p.slices > (p.height + 15) / 16) p.slices = (p.height + 15) / 16;
+    vcpenc_params pkey = p;            // session key: what the kernels see (not the muxer's / front end's settings)
+    pkey.faststart = 0; pkey.audio_bitrate = 0; pkey.drop_audio = 0; pkey.maxrate = 0; pkey.bufsize = 0; pkey.effort = 0;
 
-    const size_t fb = std::max(fbytes(p.width, p.height), src->fbytes());
-    // chunk: whole GOPs, at most ~3 GiB of raw frames resident per pass
-    size_t chunk_bytes = ((size_t)3 << 30) * (size_t)task_gpus();
+    const size_t sfb = src->fbytes();
+    const size_t fb = std::max(fbytes(p.width, p.height), sfb);
+    // chunk: whole GOPs, at most ~3 GiB of raw frames per pass and buffer
+    const int ndev = task_gpus();
+    size_t chunk_bytes = ((size_t)3 << 30) * (size_t)ndev;
     if (const char* e = getenv("VCPENC_CHUNK_BYTES")) { const long long v = atoll(e); if (v > 0) chunk_bytes = (size_t)v; }   // tests: force many chunks
     int chunk = (int)std::max<size_t>(1, chunk_bytes / fb);
-    {   // short clips: do not page-lock more host memory than the file can fill
-        struct stat sb;
-        if (stat(input, &sb) == 0 && sb.st_size > 0)
-            chunk = (int)std::min<size_t>((size_t)chunk, (size_t)sb.st_size / src->fbytes() + 1);
-    }
+    // short clips: do not page-lock more host memory than the input can fill.  The picture count is exact for raw /
+    // y4m files and an estimate (duration x frame rate) for containers; unknown (0) keeps the full chunk.
+    const long est = src->est_frames;
+    if (est > 0) chunk = (int)std::min<long>((long)chunk, est);
     chunk = std::max(p.gop, (chunk + p.gop - 1) / p.gop * p.gop);
-    PinnedBuf frames;   // owns the buffer only when the per-thread cache is off
-    uint8_t* fbuf = nullptr;
-    if (cache_enabled()) {
-        if (t_cache.pinned_bytes < (size_t)chunk * fb) {
-            if (t_cache.pinned) vcpenc_host_free(t_cache.pinned);
-            t_cache.pinned = (uint8_t*)vcpenc_host_alloc((size_t)chunk * fb);
-            t_cache.pinned_bytes = t_cache.pinned ? (size_t)chunk * fb : 0;
+    const int nbuf = (est > 0 && est <= chunk) ? 1 : 2;   // one chunk holds everything: nothing to overlap
+    uint8_t* fbuf[2] = {nullptr, nullptr};
+    bool own_pinned = !cache_enabled();
+    for (int i = 0; i < nbuf; i++) {
+        const size_t need = (size_t)chunk * sfb;
+        if (own_pinned) fbuf[i] = (uint8_t*)vcpenc_host_alloc(need);
+        else {
+            if (t_cache.pinned_bytes[i] < need) {
+                if (t_cache.pinned[i]) vcpenc_host_free(t_cache.pinned[i]);
+                t_cache.pinned[i] = (uint8_t*)vcpenc_host_alloc(need);
+                t_cache.pinned_bytes[i] = t_cache.pinned[i] ? need : 0;
+            }
+            fbuf[i] = t_cache.pinned[i];
         }
-        fbuf = t_cache.pinned;
-    } else {
-        frames.p = (uint8_t*)vcpenc_host_alloc((size_t)chunk * fb);
-        fbuf = frames.p;
+        if (!fbuf[i]) {
+            if (own_pinned) for (int k = 0; k < i; k++) vcpenc_host_free(fbuf[k]);
+            set_err(err, errlen, "cannot allocate %zu bytes of pinned host memory", need);
+            return VCPENC_E_CUDA;
+        }
     }
-    if (!fbuf) { set_err(err, errlen, "cannot allocate %zu bytes of pinned host memory", (size_t)chunk * fb); return VCPENC_E_CUDA; }
     t_alloc = lap(tl);
 
-    const int ndev = task_gpus();
     struct Shard {
-        int device = 0; vcpenc_session* ses = nullptr; bool cached = false;
+        int device = 0; vcpenc_session* ses = nullptr;
         std::vector<uint8_t> bits; std::vector<vcpenc_frame_info> info;
         int f0 = 0, n = 0, g0 = 0; size_t len = 0; int rc = 0; char err[256] = {0};
     };
     std::vector<Shard> shards((size_t)ndev);
     for (int d = 0; d < ndev; d++) shards[d].device = (t_device + d) % std::max(1, vcpenc_device_count());
-    std::vector<uint8_t> mdat, annexb_all;
-    ParamSets psets;
-    std::vector<Mp4Sample> samples;
     const bool raw_out = ends_with(outp, ".h264") || ends_with(outp, ".264") || ends_with(outp, ".h265") || ends_with(outp, ".265") || ends_with(outp, ".hevc");
-    long total = 0;
-    int gop_index = 0;
+    Mp4Writer mp4;
+    FILE* rawf = nullptr;
+    bool writer_open = false;
+
+    // ---- reader thread: fills the chunk buffers one GOP at a time, polling the stop conditions in between ----
+    std::mutex mu;
+    std::condition_variable cv;
+    int filled[2] = {-1, -1};          // frames in buffer i; -1: free for the reader
+    bool last[2] = {false, false};     // buffer i holds the end of the input
+    int read_rc = 0; char read_err[256] = {0};
+    std::atomic<int> stop{0};          // VCPENC_E_CANCELLED / VCPENC_E_TIMEOUT once a stop condition is seen
+    bool quit = false;
+    auto stop_reason = [&]() -> int {
+        if (stop.load()) return stop.load();
+        if (cancel && *cancel) { stop.store(VCPENC_E_CANCELLED); return VCPENC_E_CANCELLED; }
+        if (timeout_ms > 0 && std::chrono::duration_cast<std::chrono::milliseconds>(clock::now() - t0).count() > timeout_ms) { stop.store(VCPENC_E_TIMEOUT); return VCPENC_E_TIMEOUT; }
+        return 0;
+    };
+    std::thread reader([&] {
+        for (int i = 0;; i = (i + 1) % nbuf) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return filled[i] < 0 || quit; });
+                if (quit) return;
+            }
+            int n = 0, rcr = 0;
+            bool eof = false;
+            while (n < chunk && !eof) {
+                if (stop_reason()) break;
+                const int want = std::min(p.gop, chunk - n);
+                const int k = src->read(fbuf[i] + (size_t)n * sfb, want, read_err, sizeof read_err);
+                if (k < 0) { rcr = -k; break; }
+                n += k;
+                if (k < want) eof = true;
+            }
+            if (eof && !rcr) { const int ra = src->finish_audio(read_err, sizeof read_err); if (ra) rcr = ra; }
+            std::lock_guard<std::mutex> lk(mu);
+            filled[i] = n; last[i] = eof || rcr || stop.load(); read_rc = rcr;
+            cv.notify_all();
+            if (last[i]) return;
+        }
+    });
     auto fail = [&](int code) {
-        for (auto& sh : shards) if (sh.ses) { forget_session(sh.ses); sh.ses = nullptr; }
+        { std::lock_guard<std::mutex> lk(mu); quit = true; stop.store(stop.load() ? stop.load() : code); cv.notify_all(); }
+        if (reader.joinable()) reader.join();
+        for (auto& sh : shards) if (sh.ses) { release_session(sh.ses, false); sh.ses = nullptr; }
+        if (rawf) { fclose(rawf); rawf = nullptr; }
+        if (writer_open && !raw_out) mp4.abandon();
         remove(output);
+        if (own_pinned) for (int i = 0; i < nbuf; i++) vcpenc_host_free(fbuf[i]);
         return code;
     };
-    for (;;) {
-        if (cancel && *cancel) { set_err(err, errlen, "任务被取消"); return fail(VCPENC_E_CANCELLED); }
-        if (timeout_ms > 0 && std::chrono::duration_cast<std::chrono::milliseconds>(clock::now() - t0).count() > timeout_ms) {
-            set_err(err, errlen, "编码超时 (>%dms)", timeout_ms);
-            return fail(VCPENC_E_TIMEOUT);
+    auto stop_message = [&](int code) {
+        if (code == VCPENC_E_CANCELLED) set_err(err, errlen, "任务被取消");
+        else set_err(err, errlen, "编码超时 (>%dms)", timeout_ms);
+    };
+    // audio access units the front end has produced so far go into the file behind the video of the chunk
+    auto drain_audio = [&]() -> int {
+        if (!src->audio.present || raw_out) return 0;
+        std::vector<uint8_t> data; std::vector<uint32_t> sizes;
+        { std::lock_guard<std::mutex> lk(src->audio_mu); data.swap(src->audio.data); sizes.swap(src->audio.sizes); }
+        size_t o = 0;
+        for (uint32_t sz : sizes) { if (mp4.audio_frame(data.data() + o, sz)) return VCPENC_E_IO; o += sz; }
+        return 0;
+    };
+
+    long total = 0;
+    int gop_index = 0;
+    for (int bi = 0;; bi = (bi + 1) % nbuf) {
+        int n;
+        bool is_last;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return filled[bi] >= 0; });
+            n = filled[bi]; is_last = last[bi];
         }
-        const int n = src->read(fbuf, chunk, err, errlen);
-        t_read += lap(tl);
-        if (n < 0) return fail(-n);
-        if (n == 0) break;
-        // closed GOPs of this chunk, contiguous ranges per device
-        const int ngops = (n + p.gop - 1) / p.gop;
-        const int used = std::min(ndev, ngops);
-        for (int d = 0; d < ndev; d++) {
-            Shard& sh = shards[d];
-            const int ga = d < used ? (int)((long long)ngops * d / used) : 0, gb = d < used ? (int)((long long)ngops * (d + 1) / used) : 0;
-            sh.f0 = ga * p.gop; sh.n = std::min(n, gb * p.gop) - sh.f0; sh.g0 = gop_index + ga; sh.rc = 0; sh.len = 0;
-            if (sh.n <= 0) { sh.n = 0; continue; }
-            if (!sh.ses) {
-                p.first_gop = 0;
-                const int want = std::min((chunk / p.gop + used - 1) / used * p.gop, std::max(sh.n, 1));
-                rc = acquire_session(p, sh.device, std::max(want, sh.n), &sh.ses, &sh.cached, err, errlen);
-                if (rc) return fail(rc);
+        t_wait += lap(tl);
+        if (int sr = stop_reason()) { stop_message(sr); return fail(sr); }
+        if (read_rc) { set_err(err, errlen, "%s", read_err); return fail(read_rc); }
+        if (n > 0) {
+            // closed GOPs of this chunk, contiguous ranges per device
+            const int ngops = (n + p.gop - 1) / p.gop;
+            const int used = std::min(ndev, ngops);
+            for (int d = 0; d < ndev; d++) {
+                Shard& sh = shards[d];
+                const int ga = d < used ? (int)((long long)ngops * d / used) : 0, gb = d < used ? (int)((long long)ngops * (d + 1) / used) : 0;
+                sh.f0 = ga * p.gop; sh.n = std::min(n, gb * p.gop) - sh.f0; sh.g0 = gop_index + ga; sh.rc = 0; sh.len = 0;
+                if (sh.n <= 0) { sh.n = 0; continue; }
+                if (!sh.ses) {
+                    pkey.first_gop = 0;
+                    const int want = std::min((chunk / p.gop + used - 1) / used * p.gop, std::max(sh.n, 1));
+                    rc = acquire_session(pkey, sh.device, std::max(want, sh.n), &sh.ses, err, errlen);
+                    if (rc) return fail(rc);
+                }
+                if (sh.bits.size() < (size_t)sh.n * fb / 2 + (1 << 20)) sh.bits.resize((size_t)sh.n * fb / 2 + (1 << 20));
+                if (sh.info.size() < (size_t)sh.n) sh.info.resize((size_t)sh.n);
             }
-            if (sh.bits.size() < (size_t)sh.n * fb / 2 + (1 << 20)) sh.bits.resize((size_t)sh.n * fb / 2 + (1 << 20));
-            if (sh.info.size() < (size_t)sh.n) sh.info.resize((size_t)sh.n);
-        }
-        t_create += lap(tl);
-        auto run = [&](Shard& sh) {
-            if (!sh.n) return;
-            vcpenc_session_set_first_gop(sh.ses, sh.g0);          // idr_pic_id parity continues across ranges and chunks
-            // streamed: the pinned chunk buffer outlives the encode, whose GOP groups start as their frames land
-            sh.rc = vcpenc_session_upload_async(sh.ses, fbuf + (size_t)sh.f0 * src->fbytes(), sh.n, sh.err, sizeof sh.err);
-            if (!sh.rc) sh.rc = vcpenc_session_encode(sh.ses, nullptr, sh.err, sizeof sh.err);
-            if (!sh.rc) {
-                sh.rc = vcpenc_session_download(sh.ses, sh.bits.data(), sh.bits.size(), &sh.len, sh.info.data(), nullptr, sh.err, sizeof sh.err);
-                if (sh.rc == VCPENC_E_OVERFLOW) {
-                    sh.bits.resize((size_t)sh.n * fb + (1 << 20));
+            t_create += lap(tl);
+            auto run = [&](Shard& sh) {
+                if (!sh.n) return;
+                vcpenc_session_set_first_gop(sh.ses, sh.g0);          // idr_pic_id parity continues across ranges and chunks
+                // streamed: the pinned chunk buffer outlives the encode, whose GOP groups start as their frames land
+                sh.rc = vcpenc_session_upload_async(sh.ses, fbuf[bi] + (size_t)sh.f0 * sfb, sh.n, sh.err, sizeof sh.err);
+                if (!sh.rc) sh.rc = vcpenc_session_encode(sh.ses, nullptr, sh.err, sizeof sh.err);
+                if (!sh.rc) {
                     sh.rc = vcpenc_session_download(sh.ses, sh.bits.data(), sh.bits.size(), &sh.len, sh.info.data(), nullptr, sh.err, sizeof sh.err);
+                    if (sh.rc == VCPENC_E_OVERFLOW) {
+                        sh.bits.resize((size_t)sh.n * fb + (1 << 20));
+                        sh.rc = vcpenc_session_download(sh.ses, sh.bits.data(), sh.bits.size(), &sh.len, sh.info.data(), nullptr, sh.err, sizeof sh.err);
+                    }
                 }
+            };
+            if (used <= 1) run(shards[0]);
+            else {
+                std::vector<std::thread> th;
+                for (int d = 0; d < used; d++) th.emplace_back(run, std::ref(shards[d]));
+                for (auto& t : th) t.join();
             }
-        };
-        if (used <= 1) run(shards[0]);
-        else {
-            std::vector<std::thread> th;
-            for (int d = 0; d < used; d++) th.emplace_back(run, std::ref(shards[d]));
-            for (auto& t : th) t.join();
+            for (auto& sh : shards) if (sh.n && sh.rc) { set_err(err, errlen, "%s", sh.err); return fail(sh.rc); }
+            t_gpu += lap(tl);
         }
-        for (auto& sh : shards) if (sh.n && sh.rc) { set_err(err, errlen, "%s", sh.err); return fail(sh.rc); }
-        t_gpu += lap(tl);
-        for (auto& sh : shards) {            // host concatenation in GOP order
-            if (!sh.n) continue;
-            if (raw_out) { annexb_all.insert(annexb_all.end(), sh.bits.begin(), sh.bits.begin() + sh.len); continue; }
-            for (int i = 0; i < sh.n; i++) {
-                Mp4Sample sm{mdat.size(), 0, sh.info[i].is_idr != 0};
-                for (const auto& nal : split_annexb(sh.bits.data() + sh.info[i].offset, sh.info[i].size)) {
-                    if (!nal.n) continue;
-                    if (psets.take(p.codec, nal)) continue;
-                    const uint32_t k = (uint32_t)nal.n;
-                    const uint8_t h[4] = {(uint8_t)(k >> 24), (uint8_t)(k >> 16), (uint8_t)(k >> 8), (uint8_t)k};
-                    mdat.insert(mdat.end(), h, h + 4);
-                    mdat.insert(mdat.end(), nal.p, nal.p + nal.n);
+        // the buffer is free again: the reader fills it while this chunk is written out
+        { std::lock_guard<std::mutex> lk(mu); filled[bi] = -1; cv.notify_all(); }
+        if (int sr = stop_reason()) { stop_message(sr); return fail(sr); }
+        if (n > 0) {
+            if (!writer_open) {
+                if (raw_out) {
+                    rawf = fopen(output, "wb");
+                    if (!rawf) { set_err(err, errlen, "cannot create %s", output); return fail(VCPENC_E_IO); }
+                } else {
+                    // expected samples (moov reserve of a faststart file): the source's estimate, else what this first chunk suggests
+                    const uint64_t ev = est > 0 ? (uint64_t)est + 2 : (is_last ? (uint64_t)n : 0);
+                    uint64_t ea = 0;
+                    if (src->audio.present && ev && p.fps_num > 0)
+                        ea = ev * (uint64_t)p.fps_den * (uint64_t)src->audio.sample_rate / ((uint64_t)p.fps_num * (uint64_t)src->audio.frame_samples) + 64;
+                    else if (src->audio.present) ea = 1;
+                    rc = mp4.open(output, p, ev, ea, err, errlen);
+                    if (rc) return fail(rc);
                 }
-                sm.size = (uint32_t)(mdat.size() - sm.offset);
-                samples.push_back(sm);
+                writer_open = true;
             }
+            for (auto& sh : shards) {            // host concatenation in GOP order
+                if (!sh.n) continue;
+                if (raw_out) {
+                    if (fwrite(sh.bits.data(), 1, sh.len, rawf) != sh.len) { set_err(err, errlen, "short write to %s", output); return fail(VCPENC_E_IO); }
+                    continue;
+                }
+                for (int i = 0; i < sh.n; i++) {
+                    if (mp4.video_access_unit(sh.bits.data() + sh.info[i].offset, sh.info[i].size, sh.info[i].is_idr != 0)) { set_err(err, errlen, "short write to %s", output); return fail(VCPENC_E_IO); }
+                    if ((i + 1) % p.gop == 0) mp4.end_chunk();
+                }
+                mp4.end_chunk();
+            }
+            if (!is_last && drain_audio()) { set_err(err, errlen, "short write to %s", output); return fail(VCPENC_E_IO); }
+            total += n;
+            gop_index += (n + p.gop - 1) / p.gop;
+            t_mux += lap(tl);
         }
-        total += n;
-        gop_index += ngops;
-        if (n < chunk) break;
+        if (is_last) break;
     }
-    for (auto& sh : shards) { if (sh.ses && !sh.cached) vcpenc_session_destroy(sh.ses); sh.ses = nullptr; }
-    if (total == 0) { set_err(err, errlen, "input has no frames"); remove(output); return VCPENC_E_FORMAT; }
+    if (reader.joinable()) reader.join();
+    for (auto& sh : shards) { if (sh.ses) release_session(sh.ses, true); sh.ses = nullptr; }
+    if (own_pinned) for (int i = 0; i < nbuf; i++) vcpenc_host_free(fbuf[i]);
+    if (total == 0) {
+        if (rawf) fclose(rawf);
+        if (writer_open && !raw_out) mp4.abandon();
+        set_err(err, errlen, "input has no frames"); remove(output); return VCPENC_E_FORMAT;
+    }
     if (raw_out) {
-        FILE* f = fopen(output, "wb");
-        if (!f) { set_err(err, errlen, "cannot create %s", output); return VCPENC_E_IO; }
-        const bool ok = fwrite(annexb_all.data(), 1, annexb_all.size(), f) == annexb_all.size();
-        if (fclose(f) != 0 || !ok) { set_err(err, errlen, "short write to %s", output); remove(output); return VCPENC_E_IO; }
+        if (fclose(rawf) != 0) { set_err(err, errlen, "short write to %s", output); remove(output); return VCPENC_E_IO; }
     } else {
-        rc = write_mp4(p, psets, samples, mdat.data(), mdat.size(), output, err, errlen);
-        if (rc) { remove(output); return rc; }
+        if (drain_audio()) { set_err(err, errlen, "short write to %s", output); mp4.abandon(); return VCPENC_E_IO; }
+        rc = mp4.finish(src->audio.present ? &src->audio : nullptr, err, errlen);
+        if (rc) { mp4.abandon(); return rc; }
     }
-    t_mux = lap(tl);
-    if (trace)
-        fprintf(stderr, "[vcpenc] trace open=%.3f pinned_alloc=%.3f read_decode=%.3f session=%.3f gpu=%.3f mux_write=%.3f s\n",
-                t_open, t_alloc, t_read, t_create, t_gpu, t_mux);
+    t_mux += lap(tl);
     const double sec = std::chrono::duration<double>(clock::now() - t0).count();
-    fprintf(stderr, "[vcpenc] frames=%ld size=%dx%d fps=%.1f elapsed=%.3fs output=%s\n", total, p.width, p.height,
-            sec > 0 ? total / sec : 0.0, sec, output);
+    if (trace)
+        fprintf(stderr, "[vcpenc] trace open=%.3f pinned_alloc=%.3f wait_for_reader=%.3f session=%.3f gpu=%.3f mux_write=%.3f s\n",
+                t_open, t_alloc, t_wait, t_create, t_gpu, t_mux);
+    // the reference runs its child with `-loglevel warning` (cmd/consumer.go:376): a successful task prints nothing
+    if (trace || getenv("VCPENC_VERBOSE"))
+        fprintf(stderr, "[vcpenc] frames=%ld size=%dx%d fps=%.1f elapsed=%.3fs audio=%s output=%s\n", total, p.width, p.height,
+                sec > 0 ? total / sec : 0.0, sec, src->audio.present ? (src->audio.copied ? "aac(copy)" : "aac") : "none", output);
     return VCPENC_OK;
 }

@@ -120,8 +120,9 @@ void vcp_launch_k1_to_yuv420p(const uint8_t* in, size_t in_fb, int fmt, int w, i
                               cudaStream_t st);
 void vcp_launch_k1_scale(const uint8_t* in, size_t in_fb, int sw, int sh, uint8_t* out, size_t out_fb, int dw, int dh,
                          int n, cudaStream_t st);
-void vcp_launch_me_prepass(const VcpGeom& g, const VcpBufs& b, int nframes, int gop, int t, cudaStream_t st, int g0 = 0, int g1 = -1);
-void vcp_launch_me_refine(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
+struct VcpTmaps;   // vcp_tma.cuh: tensor maps over the picture planes (search windows are fetched by TMA)
+void vcp_launch_me_prepass(const VcpGeom& g, const VcpBufs& b, const VcpTmaps& tm, int nframes, int gop, int t, cudaStream_t st, int g0 = 0, int g1 = -1);
+void vcp_launch_me_refine(const VcpGeom& g, const VcpBufs& b, const VcpTmaps& tm, const VcpStep& s, cudaStream_t st);
 void vcp_launch_p_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_i_fix(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);
 void vcp_launch_i_recon(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st);

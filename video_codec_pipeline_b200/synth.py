@@ -90,3 +90,42 @@ def split_planes(frame: np.ndarray, w: int, h: int):
     u = frame[w * h: w * h + cw * ch].reshape(ch, cw)
     v = frame[w * h + cw * ch:].reshape(ch, cw)
     return y, u, v
+
+
+def make_hard_clip(w: int, h: int, nframes: int, seed: int, start: int = 0, noise: int = 3) -> np.ndarray:
+    """Content that defeats the encoder's cheap paths: a textured picture panning over the WHOLE frame by
+    fractional samples ((1.25, 0.75) luma samples per frame, bilinear resampling) with fresh noise of
+    +-`noise` on every sample of every frame.  No macroblock is static, no vector is integer, no residual is
+    empty: the sub-sample search, the transform and the entropy coder all run on every macroblock."""
+    rng = np.random.default_rng(seed)
+    pad = 64 + int(1.25 * (start + nframes)) + 2
+    # band-limited texture: white noise smoothed by a separable box filter, plus a coarse pattern for large structures
+    tex = rng.integers(0, 256, size=(h + pad, w + pad)).astype(np.float32)
+    for ax in (0, 1):
+        tex = (np.roll(tex, 1, ax) + tex + np.roll(tex, -1, ax) + np.roll(tex, 2, ax)) * 0.25
+    yy, xx = np.mgrid[0:h + pad, 0:w + pad]
+    tex = 0.6 * tex + 0.4 * (128 + 90 * np.sin(xx / 23.0) * np.cos(yy / 17.0))
+    tex = np.clip(tex, 16, 235).astype(np.float32)
+    cu = (128 + 40 * np.sin(xx[::2, ::2] / 61.0)).astype(np.float32)
+    cv = (128 + 40 * np.cos(yy[::2, ::2] / 47.0)).astype(np.float32)
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    out = np.empty((nframes, frame_bytes(w, h)), np.uint8)
+
+    def sample(plane, fx, fy, pw, ph):
+        ix, iy = int(np.floor(fx)), int(np.floor(fy))
+        ax, ay = np.float32(fx - ix), np.float32(fy - iy)
+        p00 = plane[iy:iy + ph, ix:ix + pw]; p01 = plane[iy:iy + ph, ix + 1:ix + 1 + pw]
+        p10 = plane[iy + 1:iy + 1 + ph, ix:ix + pw]; p11 = plane[iy + 1:iy + 1 + ph, ix + 1:ix + 1 + pw]
+        return (1 - ax) * (1 - ay) * p00 + ax * (1 - ay) * p01 + (1 - ax) * ay * p10 + ax * ay * p11
+
+    for i in range(nframes):
+        n = start + i
+        fx, fy = 1.25 * n, 0.75 * n
+        Y = sample(tex, fx, fy, w, h) + rng.integers(-noise, noise + 1, size=(h, w)).astype(np.float32)
+        U = sample(cu, fx / 2, fy / 2, cw, ch)
+        V = sample(cv, fx / 2, fy / 2, cw, ch)
+        f = out[i]
+        f[: w * h] = np.clip(Y + 0.5, 0, 255).astype(np.uint8).ravel()
+        f[w * h: w * h + cw * ch] = np.clip(U + 0.5, 0, 255).astype(np.uint8).ravel()
+        f[w * h + cw * ch:] = np.clip(V + 0.5, 0, 255).astype(np.uint8).ravel()
+    return out
