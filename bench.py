@@ -506,6 +506,37 @@ def e2e_transcode(cx: Ctx, wl: Workload, frames2: np.ndarray, tokens: str, clips
         del clip
         dsts = [os.path.join(base, "vcp_bench_%d_%s_%d.mp4" % (os.getpid(), label, i)) for i in range(2)]
         errs = []
+        # what the file system delivers: the same bytes pread() into page-locked memory by the same number of threads
+        # (2 tasks x the library's read workers), nothing else -- the ceiling of any file-to-file transcode on this box
+        read_fps = None
+        try:
+            import concurrent.futures as cf
+            fsz = os.path.getsize(src)
+            nthr = 2 * max(1, min(8, (os.cpu_count() or 2) // 2))
+            pin = cx.torch.empty(min(fsz, 1 << 30), dtype=cx.torch.uint8).pin_memory().numpy()
+            piece = 64 << 20
+            jobs = [(o, min(piece, fsz - o)) for o in range(0, fsz, piece)]
+            fd = os.open(src, os.O_RDONLY)
+
+            def rd(job):
+                o, ln = job
+                mv = memoryview(pin)[(o % (pin.size - piece + 1)) if pin.size > piece else 0:][:ln]
+                got = 0
+                while got < ln:
+                    k = os.preadv(fd, [mv[got:]], o + got)
+                    if k <= 0:
+                        break
+                    got += k
+                return got
+            t0 = time.perf_counter()
+            with cf.ThreadPoolExecutor(nthr) as ex:
+                tot = sum(ex.map(rd, jobs + jobs))                 # two tasks' worth
+            dt = time.perf_counter() - t0
+            os.close(fd)
+            read_fps = round(2 * n / dt, 1) if tot >= 2 * fsz - 16 else None
+            del pin
+        except Exception:  # noqa: BLE001
+            read_fps = None
 
         def task(i, reps):
             try:
@@ -535,7 +566,8 @@ def e2e_transcode(cx: Ctx, wl: Workload, frames2: np.ndarray, tokens: str, clips
             except Exception:  # noqa: BLE001
                 ok = False
             out[label] = {"frames_per_task": n, "tasks": 2 * reps, "fps": round(2 * reps * n / dt, 1), "seconds": round(dt, 3),
-                          "mp4_bytes": os.path.getsize(dsts[0]), "verify": ok}
+                          "mp4_bytes": os.path.getsize(dsts[0]), "verify": ok, "file_read_ceiling_fps": read_fps,
+                          "of_read_ceiling": round(2 * reps * n / dt / read_fps, 3) if read_fps else None}
         except Exception as ex:  # noqa: BLE001
             out[label] = {"error": str(ex)[:200]}
         finally:

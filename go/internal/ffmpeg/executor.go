@@ -35,10 +35,25 @@ import (
 	"unsafe"
 )
 
-// ErrNotEncode is returned for presets that are not a video encode (`-c copy`, `-vn`): the
-// caller hands those to a stock ffmpeg.  That is dispatch on preset kind, not a CPU fallback
-// of the encoder.
-var ErrNotEncode = errors.New("preset is not a video encode")
+// ErrHandOff is returned for tasks that are not a B200 video encode: presets without a video
+// encode (`-c copy`, `-vn`: VCPENC_E_NOTENCODE), inputs whose audio the loaded FFmpeg libraries
+// cannot carry into the output (VCPENC_E_AUDIO) and video tools the library does not implement
+// (VCPENC_E_UNSUPPORTED).  The caller runs those through RunStockFFmpeg -- see TranscodeOrStock.
+// That is dispatch on the kind of task, not a CPU fallback of the encoder.
+var ErrHandOff = errors.New("task is handed to the stock ffmpeg")
+
+// ErrNotEncode is kept for callers of the first version of this binding.
+var ErrNotEncode = ErrHandOff
+
+// TranscodeOrStock is what cmd/consumer.go:262 calls: the B200 encoder, and the reference's own
+// ffmpeg child for the tasks it hands off.
+func TranscodeOrStock(ctx context.Context, input, output, ffmpegArgs string, timeout time.Duration) error {
+	err := Transcode(ctx, input, output, ffmpegArgs, timeout)
+	if errors.Is(err, ErrHandOff) {
+		return RunStockFFmpeg(ctx, input, output, ffmpegArgs, timeout)
+	}
+	return err
+}
 
 // Transcode mirrors runFFmpegWithTimeout(ctx, input, output, ffmpegArgs, timeout).
 func Transcode(ctx context.Context, input, output, ffmpegArgs string, timeout time.Duration) error {
@@ -56,7 +71,7 @@ func Transcode(ctx context.Context, input, output, ffmpegArgs string, timeout ti
 	defer C.free(unsafe.Pointer(cOut))
 
 	// exec.CommandContext SIGKILLs the child on cancel; a cgo call cannot be killed, so the
-	// library polls this flag at least once per GOP batch.
+	// library polls this flag once per GOP while reading and between the stages of a chunk.
 	var flag int32
 	done := make(chan struct{})
 	go func() {
@@ -81,8 +96,8 @@ func Transcode(ctx context.Context, input, output, ffmpegArgs string, timeout ti
 	switch rc {
 	case C.VCPENC_OK:
 		return nil
-	case C.VCPENC_E_NOTENCODE:
-		return ErrNotEncode
+	case C.VCPENC_E_NOTENCODE, C.VCPENC_E_AUDIO, C.VCPENC_E_UNSUPPORTED:
+		return fmt.Errorf("%w: %s", ErrHandOff, C.GoString((*C.char)(unsafe.Pointer(&errbuf[0]))))
 	default:
 		return fmt.Errorf("vcpenc error %d: %s", int(rc), C.GoString((*C.char)(unsafe.Pointer(&errbuf[0]))))
 	}
@@ -99,7 +114,7 @@ func Verify(path string) error {
 	return nil
 }
 
-// RunStockFFmpeg is the reference's original body, kept for ErrNotEncode presets.
+// RunStockFFmpeg is the reference's original body (cmd/consumer.go:370-394), kept for the tasks Transcode hands off.
 func RunStockFFmpeg(ctx context.Context, input, output, ffmpegArgs string, timeout time.Duration) error {
 	timeoutCtx, cancel := context.WithTimeout(ctx, timeout)
 	defer cancel()

@@ -189,13 +189,19 @@ int alloc_cabac_arenas(vcpenc_session* s, char* err, size_t errlen) {
     VcpBufs& b = s->b;
     if (b.bins) { cudaFree(b.bins); s->allocs.erase(std::find(s->allocs.begin(), s->allocs.end(), (void*)b.bins)); b.bins = nullptr; }
     if (b.crbsp) { cudaFree(b.crbsp); s->allocs.erase(std::find(s->allocs.begin(), s->allocs.end(), (void*)b.crbsp)); b.crbsp = nullptr; }
+    if (b.sbins) { cudaFree(b.sbins); s->allocs.erase(std::find(s->allocs.begin(), s->allocs.end(), (void*)b.sbins)); b.sbins = nullptr; }
     const size_t N = s->max_frames;
     b.bins_cap = std::max<size_t>(N * s->g.nmb * (size_t)s->bins_per_mb, (size_t)1 << 18);
-    b.crbsp_cap = b.bins_cap / 2 + N * s->g.slices * 96;
+    // slice streams: every bin once more, each stream rounded up to a 16-byte window plus one window of read-ahead
+    b.sbins_cap = b.bins_cap + N * s->g.slices * 16;
+    // slice RBSPs: a bin renormalises by at most 6 bits, so one byte per bin (+ header and flush) bounds a slice exactly
+    b.crbsp_cap = b.bins_cap + N * s->g.slices * 160;
     int rc = dev_alloc(s, &b.bins, b.bins_cap, err, errlen);
+    if (!rc) rc = dev_alloc(s, &b.sbins, b.sbins_cap, err, errlen);
     if (!rc) rc = dev_alloc(s, &b.crbsp, b.crbsp_cap, err, errlen);
     for (int q = 0; q < 2; q++) {
         s->bpar[q].bins = b.bins; s->bpar[q].bins_cap = b.bins_cap;
+        s->bpar[q].sbins = b.sbins; s->bpar[q].sbins_cap = b.sbins_cap;
         s->bpar[q].crbsp = b.crbsp; s->bpar[q].crbsp_cap = b.crbsp_cap;
     }
     return rc;
@@ -446,6 +452,8 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
         TRY(dev_alloc(s, &b.mbdesc, N * nmb, err, errlen));
         TRY(dev_alloc(s, &b.slice_bins, N * g.slices, err, errlen));
         TRY(dev_alloc(s, &b.crbsp_cursor, (size_t)1, err, errlen));
+        TRY(dev_alloc(s, &b.sbins_cursor, (size_t)1, err, errlen));
+        TRY(dev_alloc(s, &b.sslice_off, N * g.slices, err, errlen));
         TRY(dev_alloc(s, &b.cslice_off, N * g.slices, err, errlen));
         TRY(dev_alloc(s, &b.cslice_bytes, N * g.slices, err, errlen));
         TRY(alloc_cabac_arenas(s, err, errlen));
@@ -603,6 +611,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
     if (g.cabac) {
         CK(cudaMemsetAsync(b.bins_cursor, 0, sizeof(unsigned long long), s->st));
         CK(cudaMemsetAsync(b.crbsp_cursor, 0, sizeof(unsigned long long), s->st));
+        CK(cudaMemsetAsync(b.sbins_cursor, 0, sizeof(unsigned long long), s->st));
         CK(cudaMemsetAsync(b.slice_bins, 0, (size_t)N * g.slices * sizeof(uint32_t), s->st));
         CK(cudaMemsetAsync(b.out_index, 0, (size_t)N * g.slices * sizeof(uint2), s->st));
     }
@@ -699,20 +708,25 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 CK(cudaStreamWaitEvent(se, s->ev_rec[k][par], 0));
             }
             if (g.cabac) {
-                { Prof pr(s, VCPENC_K_CABAC_BINS, g.rc_abr ? 2 : 1, se); if (g.hevc) vcp_launch_hevc_bins(g, bt, sp, se); else vcp_launch_cabac_bins(g, bt, sp, se); }
+                { Prof pr(s, VCPENC_K_CABAC_BINS, g.rc_abr ? 3 : 2, se); if (g.hevc) vcp_launch_hevc_bins(g, bt, sp, se); else vcp_launch_cabac_bins(g, bt, sp, se); }
                 if (g.rc_abr) { Prof pr(s, VCPENC_K_RC, 1, se); vcp_launch_rc_update(g, bt, sp, se); }
-                // the arithmetic coder takes the bins in batches of kCabacBatch pictures per GOP, on
-                // its own stream: one lane per slice, long-running but only a few warps wide
+                // The arithmetic coder takes the bins in batches on its own streams: one lane per slice, long-running but
+                // only a few warps wide.  The IDR pictures are a batch of their own on a stream of their own: their
+                // slices carry ten times the bins of a P slice, and a later batch queued behind them on the same stream
+                // would not start before they end (measured: 57 of 212 ms per step).  P pictures go kCabacBatch at a
+                // time, rotating over the other streams.
                 const int last_t = std::min(gop, N) - 1;
                 const int next_active = std::min(gB, (N - (t + 1) + gop - 1) / gop) - gA;   // GOPs of the group with a picture t+1
-                if ((t + 1) % kCabacBatch == 0 || t == last_t || next_active <= 0) {
-                    const int t0 = t / kCabacBatch * kCabacBatch;
-                    cudaStream_t sc = s->profile ? s->st : s->cst[k][(t / kCabacBatch) % s->ncst];
+                if (t == 0 || t % kCabacBatch == 0 || t == last_t || next_active <= 0) {
+                    const int t0 = t == 0 ? 0 : (t - 1) / kCabacBatch * kCabacBatch + 1;
+                    const int bidx = t == 0 ? 0 : 1 + (t - 1) / kCabacBatch;
+                    cudaStream_t sc = s->profile ? s->st : s->cst[k][bidx == 0 || s->ncst < 2 ? 0 : 1 + (bidx - 1) % (s->ncst - 1)];
                     VcpStep sb = sp;
                     sb.ngop = std::min(gB, (N - t0 + gop - 1) / gop) - gA;   // GOPs of the group that own picture t0
                     if (!s->profile) { CK(cudaEventRecord(s->ev_bins[k], se)); CK(cudaStreamWaitEvent(sc, s->ev_bins[k], 0)); }
                     Prof pr(s, VCPENC_K_CABAC_CODE, 2, sc);
-                    vcp_launch_cabac_encode(g, bt, sb, t0, t + 1, sc);
+                    static const int dbg_skip = [] { const char* e = getenv("VCPENC_DEBUG_SKIP_CODER"); return e ? atoi(e) : 0; }();   // timing experiments only: the output is empty
+                    if (!dbg_skip) vcp_launch_cabac_encode(g, bt, sb, t0, t + 1, sc);
                 }
             } else {
                 { Prof pr(s, VCPENC_K_CAVLC_COUNT, 1, se); vcp_launch_cavlc_count(g, bt, sp, se); }

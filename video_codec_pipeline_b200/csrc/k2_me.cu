@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
                 const uint2 p1 = fetch8(__shfl_sync(0xffffffffu, pk1, k));
                 const uint2 p2 = fetch8(__shfl_sync(0xffffffffu, pk2, k));
                 // quarter positions average two grid samples (a half position would average a sample with itself)
-                const int sad = warp_sum((int)sad4(__vavgu4(p1.y, p2.y), c8.y, sad4(__vavgu4(p1.x, p2.x), c8.x, 0)));
+                const int sad = warp_sum((int)sad4(vcp_avg4(p1.y, p2.y), c8.y, sad4(vcp_avg4(p1.x, p2.x), c8.x, 0)));
                 if (lane == k) mycost += sad;
             }
             best = warp_min(lane < 9 ? (((uint32_t)mycost << 4) | (uint32_t)lane) : 0xffffffffu);

@@ -21,6 +21,8 @@
 // Replaces x264's cabac.c inside the ffmpeg child (/root/reference/cmd/consumer.go:376-382; the
 // h264-cpu preset is High/CABAC by default).  Output bytes are identical to oracle/h264_oracle.c
 // (write_slice_data_cabac, cabac_block, cabac_mvd, cabac_encode/bypass/terminate).
+#include <cstdlib>
+
 #include "vcp_dev.cuh"
 
 #define VCP_TAB static __device__ const
@@ -573,222 +575,254 @@ __device__ __forceinline__ void hevc_slice_header(const VcpGeom& g, int first_ct
     while (w.pos & 7) w.pos++;             // the buffer is zero-filled
 }
 
-// ---- arithmetic coder, one WARP per slice ------------------------------------------------------
-// The coder is a serial dependency chain (state -> rLPS -> range/low -> renormalisation), so what
-// bounds a slice is latency per bin, not throughput.  Lane 0 runs the chain out of shared memory;
-// the other 31 lanes exist to keep it fed: they gather the macroblocks' bins into a shared ring
-// with coalesced loads and drain the produced bytes with coalesced stores.  Many such warps share
-// an SM, so the machine interleaves as many independent chains as there are slices in the batch.
-constexpr int AC_WARPS = 4;          // slices per CTA
-constexpr int BINBUF = 2048;         // bins staged per round
-constexpr int OUTBUF = BINBUF + 32;  // a bin renormalises by at most 7 bits
+// ---- slice streams -------------------------------------------------------------------------------
+// cabac_bins_kernel bump-allocates a macroblock's bins wherever the arena cursor stands, so the bins of a slice
+// are scattered.  The arithmetic coder wants ONE contiguous, 16-byte aligned stream per slice (its lanes read
+// their streams with 128-bit loads, a window ahead): this kernel lays the macroblocks' bins out in slice order.
+// One CTA per (picture, slice) of the step: block scan of the macroblock counts, then warp-per-macroblock copies.
+constexpr int GA_THREADS = 256;
 
-struct ArithCoder {
-    uint32_t low, range;
-    int queue, outstanding, last;   // last: pending byte not yet stored (-1: none)
-    uint8_t* out;                   // shared staging of this round
-    int nout;
-    bool ovf;                       // a run of outstanding 0xff bytes longer than the staging (never seen; reported)
-    __device__ __forceinline__ void store(int v) { if (nout < OUTBUF) out[nout++] = (uint8_t)v; else ovf = true; }
-    __device__ __forceinline__ void emit(int o) {   // 8 bits + carry in bit 8
-        if ((o & 0xff) == 0xff) { outstanding++; return; }
-        const int carry = o >> 8;
-        if (last >= 0) store(last + carry);
-        while (outstanding > 0) { store(carry ? 0x00 : 0xff); outstanding--; }
-        last = o & 0xff;
-    }
-    __device__ __forceinline__ void putbyte() {
-        if (queue >= 0) {
-            const int o = (int)(low >> (queue + 10));
-            low &= (0x400u << queue) - 1;
-            queue -= 8;
-            emit(o);
-        }
-    }
-};
-
-// A context's record is a copy of the table entry of its probability state, so the range/low
-// chain never waits for a table lookup: x = the four rLPS bytes, y = next state on MPS | next state
-// on LPS << 8 | valMPS << 16.  The lookup of the successor entry runs beside the chain.
-struct __align__(16) AcScratch {
-    uint2 rec[NCTX];
-    uint16_t bins[BINBUF + 2];
-    uint8_t out[OUTBUF];
-};
-
-// batch = pictures at GOP positions [t0, t1) of GOPs [g0, g0 + ngop); one warp per (GOP, t, slice)
-__global__ void __launch_bounds__(AC_WARPS * 32) cabac_encode_kernel(VcpGeom g, VcpBufs b, VcpStep s, int t0, int t1) {
-    __shared__ AcScratch scr[AC_WARPS];
-    __shared__ uint2 ent[128];      // per state<<1|mps: x = four rLPS bytes, y = next on MPS | next on LPS << 8 | valMPS << 16
+__global__ void __launch_bounds__(GA_THREADS) cabac_gather_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
+    __shared__ uint32_t wsum[GA_THREADS / 32];
+    __shared__ uint32_t offs[GA_THREADS];
+    __shared__ uint2 descs[GA_THREADS];
+    __shared__ unsigned long long base_sh;
+    const int S = g.slices;
+    const int sl = blockIdx.x % S, gi = s.g0 + blockIdx.x / S;
+    const int n = vcp_frame_of(s, gi);
+    if (n >= s.nframes) return;
+    const int r0 = vcp_slice_first_row(sl, S, g.mbh);
+    const int r1 = sl + 1 < S ? vcp_slice_first_row(sl + 1, S, g.mbh) : g.mbh;
+    const int first = r0 * g.mbw, count = (r1 - r0) * g.mbw;
+    const uint2* desc = b.mbdesc + (size_t)n * g.nmb + first;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
-        const int st = i >> 1, mps = i & 1;
-        const uint32_t l4 = (uint32_t)vcp_cabac_range_lps[st][0] | ((uint32_t)vcp_cabac_range_lps[st][1] << 8) |
-                            ((uint32_t)vcp_cabac_range_lps[st][2] << 16) | ((uint32_t)vcp_cabac_range_lps[st][3] << 24);
-        const uint32_t nm = (uint32_t)(((st < 62 ? st + 1 : st) << 1) | mps);
-        const uint32_t nl = (uint32_t)((vcp_cabac_trans_lps[st] << 1) | (st == 0 ? mps ^ 1 : mps));
-        ent[i] = make_uint2(l4, nm | (nl << 8) | ((uint32_t)mps << 16));
+    if (threadIdx.x == 0 && *b.error_flag) base_sh = ~0ull;   // an arena overflowed earlier in this pass: descriptors are not trusted, the pass is run again
+    else if (threadIdx.x == 0) {
+        const uint32_t nb = b.slice_bins[(size_t)n * S + sl];
+        // room for the stream, rounded up to whole 16-byte windows, plus one window the coder may read ahead
+        const unsigned long long need = (((unsigned long long)nb + 7) & ~7ull) + 8;
+        unsigned long long o = atomicAdd(b.sbins_cursor, need);
+        if (o + need > b.sbins_cap) { atomicExch(b.error_flag, 3); o = ~0ull; }
+        b.sslice_off[(size_t)n * S + sl] = o;
+        base_sh = o;
+    }
+    __syncthreads();
+    if (base_sh == ~0ull) { if (threadIdx.x == 0) b.sslice_off[(size_t)n * S + sl] = ~0ull; return; }
+    uint16_t* dst = b.sbins + base_sh;
+    uint32_t run = 0;
+    for (int m0 = 0; m0 < count; m0 += GA_THREADS) {
+        const int m = m0 + (int)threadIdx.x;
+        const uint2 d = m < count ? desc[m] : make_uint2(0, 0);
+        const uint32_t cnt = d.y & 0xfffff;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, k); if (lane >= k) incl += v; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        uint32_t pre = 0, tot = 0;
+#pragma unroll
+        for (int k = 0; k < GA_THREADS / 32; k++) { const uint32_t v = wsum[k]; if (k < warp) pre += v; tot += v; }
+        offs[threadIdx.x] = run + pre + incl - cnt;
+        descs[threadIdx.x] = d;
+        __syncthreads();
+        const int mend = min(GA_THREADS, count - m0);
+        for (int j = warp; j < mend; j += GA_THREADS / 32) {
+            const uint2 dj = descs[j];
+            const uint32_t c = dj.y & 0xfffff;
+            const uint16_t* src = b.bins + ((((unsigned long long)(dj.y >> 20)) << 32) | dj.x);
+            uint16_t* q = dst + offs[j];
+            for (uint32_t e = lane; e < c; e += 32) q[e] = src[e];
+        }
+        run += tot;
+        __syncthreads();
+    }
+}
+
+// ---- arithmetic coder: one LANE per slice ------------------------------------------------------------
+// The coder of a slice is a serial dependency chain (state -> rLPS -> range/low -> renormalisation).  A warp that
+// runs one chain pays an issue slot per scalar instruction (~90 per bin, measured round 1: the coder took a quarter of
+// the step's issue capacity).  Here the 32 lanes of a warp run 32 chains in lock-step: the same instruction stream
+// codes 32 bins, decision / bypass / terminate by predication, so a bin costs ~3 issue slots.
+//   * lanes of a warp = slices of the SAME position in the GOP (all GOPs of the group x all slices of that picture):
+//     their bin counts are alike, so the lanes end together (an IDR slice has ten times the bins of a P slice);
+//   * every lane reads ITS contiguous stream (cabac_gather_kernel) with 128-bit loads, one window ahead;
+//   * context states: one byte per context per lane in shared memory, [ctx][lane]; the rLPS / next-state tables are
+//     replicated per lane ([state][lane]) so that a lookup never conflicts;
+//   * bytes leave through per-lane byte stores into the slice's own output region (cap = one byte per bin + header:
+//     a bin renormalises by at most 6 bits, so the region cannot overflow).
+constexpr int AC_WARPS = 2;          // warps (32 slices each) per CTA
+constexpr int AC_NCTX = 460;         // >= HC_NCTX
+
+struct __align__(16) AcShared {
+    uint32_t rtab[64][32];           // four rLPS bytes of a state, one copy per lane
+    uint8_t ntab[64][32];            // next state on LPS
+    uint8_t ctx[AC_WARPS][AC_NCTX][32];   // pStateIdx << 1 | valMPS
+};
+
+// Per-lane coder state.  `low` is kept 64 bits wide so that the output leaves 32 bits at a time (a flush every ~50
+// bins instead of every ~13 with bytes: the flush block is the only divergent part of the loop).  Same arithmetic as
+// the byte-wise low / queue / outstanding form of the oracle (cabac_encode / cabac_putbyte): the number written is the
+// same, so the bytes are.  queue = bits shifted in since the last flush - 33 (the first output bit is dropped: 9.3.4.2's
+// firstBitFlag); a flush takes 32 bits plus the carry above them.
+struct LaneCoder {
+    unsigned long long low;
+    uint32_t range;
+    int queue;
+    uint32_t pend; bool have_pend;   // last word, not stored yet: a later carry may still increment it
+    uint32_t outw;                   // outstanding 0xffffffff words behind it
+    uint8_t* dst; uint32_t wpos;
+    __device__ __forceinline__ void store4(uint32_t w) {   // big-endian, any alignment
+        dst[wpos] = (uint8_t)(w >> 24); dst[wpos + 1] = (uint8_t)(w >> 16); dst[wpos + 2] = (uint8_t)(w >> 8); dst[wpos + 3] = (uint8_t)w;
+        wpos += 4;
+    }
+    __device__ __forceinline__ void resolve(uint32_t carry) {   // the words held back become final
+        if (have_pend) store4(pend + carry);
+        for (; outw > 0; outw--) store4(carry ? 0u : 0xffffffffu);
+        have_pend = false;
+    }
+    __device__ __forceinline__ void flush32() {
+        const unsigned long long o = low >> (queue + 10);      // 32 bits + carry
+        low &= (0x400ull << queue) - 1;
+        queue -= 32;
+        const uint32_t w = (uint32_t)o;
+        if (w == 0xffffffffu) { outw++; return; }
+        resolve((uint32_t)(o >> 32));
+        pend = w; have_pend = true;
+    }
+};
+
+// batch = pictures at GOP positions [t0, t1) of GOPs [g0, g0 + ngop); lane id = ((t - t0) * ngop + gop) * S + slice
+__global__ void __launch_bounds__(AC_WARPS * 32) cabac_encode_kernel(VcpGeom g, VcpBufs b, VcpStep s, int t0, int t1) {
+    extern __shared__ __align__(16) uint8_t ac_raw[];
+    AcShared& A = *reinterpret_cast<AcShared*>(ac_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
+        const int st = i >> 5;
+        A.rtab[st][i & 31] = (uint32_t)vcp_cabac_range_lps[st][0] | ((uint32_t)vcp_cabac_range_lps[st][1] << 8) |
+                             ((uint32_t)vcp_cabac_range_lps[st][2] << 16) | ((uint32_t)vcp_cabac_range_lps[st][3] << 24);
+        A.ntab[st][i & 31] = (uint8_t)vcp_cabac_trans_lps[st];
     }
     __syncthreads();
     const int S = g.slices, nt = t1 - t0;
-    const int id = blockIdx.x * AC_WARPS + warp;
-    if (id >= s.ngop * nt * S) return;
-    const int sl = id % S, t = t0 + (id / S) % nt, gi = s.g0 + id / (S * nt);
+    const int id = (blockIdx.x * AC_WARPS + warp) * 32 + lane;
+    const int total = s.ngop * nt * S;
+    const int sl = id % S, gl = (id / S) % s.ngop, t = t0 + id / (S * s.ngop), gi = s.g0 + gl;
     const int n = gi * s.gop + t;
-    if (n >= s.nframes) return;
+    bool live = id < total && n < s.nframes && *b.error_flag == 0;
+    const size_t si = live ? (size_t)n * S + sl : 0;
     const bool idr = t == 0;
-    const int qp = b.qp[n];
-    AcScratch& A = scr[warp];
-    {   // context initialisation (9.3.1.1), lanes share the contexts
+    const int qp = live ? b.qp[n] : 26;
+    uint8_t (*ctx)[32] = A.ctx[warp];
+    {   // context initialisation (9.3.1.1): every lane its own column
         const int tab = idr ? 0 : 1;
-        for (int i = lane; i < (g.hevc ? (int)HC_NCTX : NCTX); i += 32) {
+        const int nctx = g.hevc ? (int)HC_NCTX : NCTX;
+        for (int i = 0; i < nctx; i++) {
             int m, nn;
             if (g.hevc) {   // H.265 9.3.2.2: slope / offset nibbles of initValue
                 const int v = hevc_init_values[tab][i];
                 m = (v >> 4) * 5 - 45; nn = ((v & 15) << 3) - 16;
             } else { m = vcp_cabac_init_mn[tab][i][0]; nn = vcp_cabac_init_mn[tab][i][1]; }
             const int pre = vcp_clip3(1, 126, ((m * vcp_clip3(0, 51, qp)) >> 4) + nn);
-            A.rec[i] = ent[pre <= 63 ? ((63 - pre) << 1) : (((pre - 64) << 1) | 1)];
+            ctx[i][lane] = (uint8_t)(pre <= 63 ? ((63 - pre) << 1) : (((pre - 64) << 1) | 1));
         }
     }
-    const int r0 = vcp_slice_first_row(sl, S, g.mbh);
-    const int r1 = sl + 1 < S ? vcp_slice_first_row(sl + 1, S, g.mbh) : g.mbh;
-    const int first = r0 * g.mbw, count = (r1 - r0) * g.mbw;
-    // output region: slice header + 4 bits per bin is more than the coder can produce on average
-    const uint32_t nb = b.slice_bins[(size_t)n * S + sl];
-    const unsigned long long cap = ((unsigned long long)nb / 2 + 96 + 15) & ~15ull;
-    unsigned long long base = 0;
-    if (lane == 0) {
-        base = atomicAdd(b.crbsp_cursor, cap);
-        if (base + cap > b.crbsp_cap) { atomicExch(b.error_flag, 4); b.cslice_bytes[(size_t)n * S + sl] = 0; base = ~0ull; }
+    const uint32_t nb = live ? b.slice_bins[si] : 0u;
+    const unsigned long long soff = live ? b.sslice_off[si] : 0ull;
+    if (soff == ~0ull) live = false;
+    // output region: one byte per bin bounds what the coder can produce; + slice header and flush
+    const unsigned long long cap = ((unsigned long long)nb + 128 + 15) & ~15ull;
+    LaneCoder C;
+    C.low = 0; C.range = 510; C.queue = -33; C.pend = 0; C.have_pend = false; C.outw = 0; C.dst = nullptr; C.wpos = 0;
+    unsigned long long obase = 0;
+    if (live) {
+        obase = atomicAdd(b.crbsp_cursor, cap);
+        if (obase + cap > b.crbsp_cap) { atomicExch(b.error_flag, 4); b.cslice_bytes[si] = 0; live = false; }
     }
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base == ~0ull) return;
-    uint8_t* dst = b.crbsp + base;
-    uint32_t wpos = 0;   // bytes written to dst (lane 0's view is broadcast)
-    if (lane == 0) {
+    if (live) {
+        const int r0 = vcp_slice_first_row(sl, S, g.mbh);
+        uint8_t* dst = b.crbsp + obase;
         reinterpret_cast<uint4*>(dst)[0] = make_uint4(0, 0, 0, 0);
         reinterpret_cast<uint4*>(dst)[1] = make_uint4(0, 0, 0, 0);
         SeqBits w{dst, 0};
-        if (g.hevc) hevc_slice_header(g, first, idr, t, qp, w);
+        if (g.hevc) hevc_slice_header(g, r0 * g.mbw, idr, t, qp, w);
         else {
-            slice_header_bits(g, first, idr, t, (s.gop0 + gi) & 1, qp, &w);
+            slice_header_bits(g, r0 * g.mbw, idr, t, (s.gop0 + gi) & 1, qp, &w);
             while (w.pos & 7) w.put(1, 1);   // cabac_alignment_one_bit
         }
-        wpos = w.pos >> 3;
+        C.dst = dst; C.wpos = w.pos >> 3;
     }
-    wpos = __shfl_sync(0xffffffffu, wpos, 0);
-    __syncwarp();
-    ArithCoder C;
-    C.low = 0; C.range = 510; C.queue = -9; C.outstanding = 0; C.last = -1; C.out = A.out; C.nout = 0; C.ovf = false;
-    const uint2* desc = b.mbdesc + (size_t)n * g.nmb + first;
-    int mb = 0;           // next macroblock to stage
-    uint32_t part = 0;    // bins of macroblock `mb` already consumed (macroblocks larger than the ring)
-    bool overflow = false;
-    while (mb < count) {
-        // ---- stage: lanes look at the next 32 macroblocks, take as many as fit --------------------
-        uint2 d = make_uint2(0, 0);
-        if (mb + lane < count) d = desc[mb + lane];
-        uint32_t cnt = d.y & 0xfffff;
-        if (lane == 0) cnt -= part;
-        uint32_t incl = cnt;
+    const uint4* win = reinterpret_cast<const uint4*>(b.sbins + (live ? soff : 0ull));
+    const uint32_t mybins = live ? nb : 0u;
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    if (mybins) cur = __ldg(win);
+    bool ended = false;               // the end_of_slice terminate bin (value 1) was met: always the last bin of a stream
+    // Software pipeline: while bin j runs through the range / low chain, the context state of bin j+1 is already being
+    // fetched (before bin j's state is written back: if both use the same context the fetched byte is stale and the
+    // register value replaces it) and its table entries follow as soon as that state is known.  The state machine does
+    // not depend on range or low, so only the ~10 dependent instructions of the range update separate two bins.
+    uint32_t bin = cur.x & 0xffffu;
+    uint32_t st = ctx[bin & 1023u][lane];
+    uint32_t rl4 = A.rtab[st >> 1][lane], nlps = A.ntab[st >> 1][lane];
+    for (uint32_t k0 = 0; __any_sync(0xffffffffu, k0 < mybins); k0 += 8) {
+        // the next window is in flight while this one is coded (streams are padded by one window)
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if (k0 + 8 < mybins) nxt = __ldg(win + (k0 >> 3) + 1);
+        const uint32_t w4[5] = {cur.x, cur.y, cur.z, cur.w, nxt.x};
 #pragma unroll
-        for (int k = 1; k < 32; k <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, k);
-            if (lane >= k) incl += v;
+        for (int j = 0; j < 8; j++) {
+            // One bin per lane, decision / bypass / terminate(0) by selection, no branches.  A lane past its stream (or at
+            // its final terminate bin) runs the same instructions with "nothing": range stays, nothing is added or shifted.
+            const uint32_t bin_n = (w4[(j + 1) >> 1] >> (16 * ((j + 1) & 1))) & 0xffffu;
+            const uint32_t c = bin & 1023u, c_n = bin_n & 1023u;       // 0 for bypass / terminate bins: a harmless read
+            const uint32_t ld_n = ctx[c_n][lane];
+            const bool act = k0 + j < mybins;
+            const uint32_t val = (bin >> 10) & 1u;
+            const bool is_byp = act && (bin & BIN_BYPASS);
+            const bool is_term = act && (bin & BIN_TERM);
+            const bool is_dec = act && !(bin & (BIN_BYPASS | BIN_TERM));
+            if (is_term && val) ended = true;
+            const uint32_t ps = st >> 1, mps = st & 1u;
+            const bool lps = val != mps;
+            const uint32_t nst = lps ? ((nlps << 1) | (ps == 0 ? mps ^ 1u : mps)) : (((ps < 62 ? ps + 1 : ps) << 1) | mps);
+            if (is_dec) ctx[c][lane] = (uint8_t)nst;
+            const uint32_t st_n = (is_dec && c_n == c) ? nst : ld_n;
+            const uint32_t rl4_n = A.rtab[st_n >> 1][lane], nlps_n = A.ntab[st_n >> 1][lane];
+            // range / low: decision: LPS takes rLPS and adds the MPS range to low; bypass: low doubles first, then adds
+            // range for a 1; terminate(0): range loses 2
+            const uint32_t range = C.range;
+            const uint32_t rlps = __byte_perm(rl4, 0u, 0x4440u | ((range >> 6) & 3u));
+            const uint32_t rmps = range - rlps;
+            uint32_t r1 = range, add = 0u;
+            if (is_dec) { r1 = lps ? rlps : rmps; add = lps ? rmps : 0u; }
+            if (is_byp) add = val ? range : 0u;
+            if (is_term && !val) r1 = range - 2u;
+            const int sh = __clz(r1) - 23;                       // 0 whenever the range did not shrink below 256
+            const int tot = sh + (is_byp ? 1 : 0);
+            C.low = (C.low << tot) + ((unsigned long long)(add << sh));
+            C.range = r1 << sh;
+            C.queue += tot;
+            if (C.queue >= 0) C.flush32();
+            bin = bin_n; st = st_n; rl4 = rl4_n; nlps = nlps_n;
         }
-        const uint32_t fits = __ballot_sync(0xffffffffu, incl <= (uint32_t)BINBUF && mb + lane < count);
-        int take = __ffs(~fits) - 1;                 // leading macroblocks that fit entirely
-        if (take < 0) take = 32;
-        uint32_t nstaged;
-        if (take == 0) {                             // one macroblock larger than the ring: take a piece
-            const unsigned long long off = (((unsigned long long)(__shfl_sync(0xffffffffu, d.y, 0) >> 20)) << 32) | __shfl_sync(0xffffffffu, d.x, 0);
-            for (int e = lane; e < BINBUF; e += 32) A.bins[e] = b.bins[off + part + e];
-            nstaged = BINBUF;
-            part += BINBUF;
-        } else {
-            for (int j = 0; j < take; j++) {
-                const uint32_t dx = __shfl_sync(0xffffffffu, d.x, j), dy = __shfl_sync(0xffffffffu, d.y, j);
-                const uint32_t c = __shfl_sync(0xffffffffu, cnt, j), o = __shfl_sync(0xffffffffu, incl, j) - c;
-                const uint16_t* src = b.bins + ((((unsigned long long)(dy >> 20)) << 32) | dx) + (j == 0 ? part : 0u);
-                for (uint32_t e = lane; e < c; e += 32) A.bins[o + e] = src[e];
-            }
-            nstaged = __shfl_sync(0xffffffffu, incl, take - 1);
-            mb += take;
-            part = 0;
-        }
-        __syncwarp();
-        // ---- the chain: lane 0 ----------------------------------------------------------------------
-        if (lane == 0) {
-            C.nout = 0;
-            // software pipeline: the next bin and its context record are fetched while the current
-            // bin is coded; a repeated context takes the freshly updated record instead.  Bypass and
-            // terminate bins carry ctx 0, so the record fetch needs no test.
-            A.bins[nstaged] = 0;
-            uint32_t cur = A.bins[0];
-            uint2 rc = A.rec[cur & 1023u];
-            uint32_t low = C.low, range = C.range;
-            int queue = C.queue;
-#pragma unroll 2
-            for (uint32_t k = 0; k < nstaged; k++) {
-                const uint32_t nxt = A.bins[k + 1];
-                uint2 rn = A.rec[nxt & 1023u];
-                if (cur & (BIN_BYPASS | BIN_TERM)) {
-                    if (cur & BIN_BYPASS) {
-                        low = (low << 1) + ((cur & 0x400u) ? range : 0u);
-                        queue += 1;
-                    } else {
-                        range -= 2;
-                        if (cur & 0x400u) {   // end of slice: flush (9.3.4.5), stop bit included
-                            low += range;
-                            C.low = low << 7; C.range = 2u << 7; C.queue = queue + 7;
-                            C.putbyte();
-                            low = (C.low << 3) | 0x400u; queue = C.queue + 3; range = C.range;
-                        } else {
-                            const int sh = __clz(range) - 23;
-                            range <<= sh; low <<= sh; queue += sh;
-                        }
-                    }
-                } else {
-                    const uint32_t rlps = __byte_perm(rc.x, 0u, 0x4440u | ((range >> 6) & 3u));
-                    const uint32_t lps = ((cur >> 10) ^ (rc.y >> 16)) & 1u;
-                    const uint2 nrec = ent[__byte_perm(rc.y, 0u, 0x4440u + lps)];   // successor entry, beside the chain
-                    range -= rlps;
-                    if (lps) { low += range; range = rlps; }
-                    A.rec[cur & 1023u] = nrec;
-                    if (((nxt ^ cur) & 1023u) == 0u) rn = nrec;    // (a special next bin has ctx 0 != ctx of a decision... unless ctx 0: never coded)
-                    const int sh = __clz(range) - 23;
-                    range <<= sh; low <<= sh; queue += sh;
-                }
-                if (queue >= 0) {
-                    C.low = low; C.queue = queue;
-                    C.putbyte();
-                    low = C.low; queue = C.queue;
-                }
-                cur = nxt; rc = rn;
-            }
-            C.low = low; C.range = range; C.queue = queue;
-            if (mb >= count && part == 0) {
-                // remaining bits above the register's ready boundary, then the pending bytes
-                const int r = C.queue + 8;                      // 0..7 bits left
-                const int o = (int)(C.low >> 10);
-                const int carry = o >> r;
-                if (C.last >= 0) C.store(C.last + carry);
-                while (C.outstanding > 0) { C.store(carry ? 0x00 : 0xff); C.outstanding--; }
-                if (r > 0) C.store((o & ((1 << r) - 1)) << (8 - r));
-            }
-        }
-        __syncwarp();
-        // ---- drain: all lanes ---------------------------------------------------------------------
-        const int nout = __shfl_sync(0xffffffffu, C.nout, 0);
-        if (__shfl_sync(0xffffffffu, (int)C.ovf, 0) || (unsigned long long)wpos + (unsigned)nout > cap) overflow = true;
-        else for (int e = lane; e < nout; e += 32) dst[wpos + e] = A.out[e];
-        wpos += (uint32_t)nout;
-        __syncwarp();
+        cur = nxt;
     }
-    if (lane == 0) {
-        if (overflow) { atomicExch(b.error_flag, 4); b.cslice_bytes[(size_t)n * S + sl] = 0; }
-        else { b.cslice_bytes[(size_t)n * S + sl] = wpos; b.cslice_off[(size_t)n * S + sl] = base; }
+    if (live) {
+        if (!ended) { atomicExch(b.error_flag, 5); b.cslice_bytes[si] = 0; return; }   // a stream that does not end in end_of_slice: never produced
+        // end of slice: flush (9.3.4.5), stop bit included -- range was not touched by the final bin above
+        C.range -= 2;
+        C.low += C.range;
+        C.low = (C.low << 10) | 0x400ull;
+        C.queue += 10;
+        if (C.queue >= 0) C.flush32();
+        // what is left above the register's ready boundary: r = queue + 32 bits (0..31) and the carry over them
+        const int r = C.queue + 32;
+        const unsigned long long o = C.low >> 10;
+        C.resolve((uint32_t)(o >> r) & 1u);
+        int left = r;
+        for (; left >= 8; left -= 8) C.dst[C.wpos++] = (uint8_t)(o >> (left - 8));
+        if (left > 0) C.dst[C.wpos++] = (uint8_t)((o & ((1ull << left) - 1)) << (8 - left));
+        if ((unsigned long long)C.wpos > cap) { atomicExch(b.error_flag, 4); b.cslice_bytes[si] = 0; }   // cannot happen: cap bounds the coder's output
+        else { b.cslice_bytes[si] = C.wpos; b.cslice_off[si] = obase; }
     }
 }
 
@@ -820,18 +854,23 @@ __global__ void cabac_rc_bits_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
 void vcp_launch_cabac_bins(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
     dim3 grid((g.nmb + CB_WARPS - 1) / CB_WARPS, s.ngop);
     cabac_bins_kernel<<<grid, CB_WARPS * 32, 0, st>>>(g, b, s);
+    static const int dbg_skip = [] { const char* e = getenv("VCPENC_DEBUG_SKIP_CODER"); return e ? atoi(e) : 0; }();   // timing experiments only
+    if (dbg_skip < 2) cabac_gather_kernel<<<s.ngop * g.slices, GA_THREADS, 0, st>>>(g, b, s);
     if (g.rc_abr) cabac_rc_bits_kernel<<<(s.ngop + 63) / 64, 64, 0, st>>>(g, b, s);
 }
 
 void vcp_launch_hevc_bins(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
     dim3 grid((g.nmb + CB_WARPS - 1) / CB_WARPS, s.ngop);
     hevc_bins_kernel<<<grid, CB_WARPS * 32, 0, st>>>(g, b, s);
+    cabac_gather_kernel<<<s.ngop * g.slices, GA_THREADS, 0, st>>>(g, b, s);
     if (g.rc_abr) cabac_rc_bits_kernel<<<(s.ngop + 63) / 64, 64, 0, st>>>(g, b, s);
 }
 
 void vcp_launch_cabac_encode(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, int t0, int t1, cudaStream_t st) {
     const int total = s.ngop * (t1 - t0) * g.slices;
     if (total <= 0) return;
-    cabac_encode_kernel<<<(total + AC_WARPS - 1) / AC_WARPS, AC_WARPS * 32, 0, st>>>(g, b, s, t0, t1);
+    // function attributes are per device: a process may drive several GPUs from different threads
+    cudaFuncSetAttribute(cabac_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcShared));
+    cabac_encode_kernel<<<(total + AC_WARPS * 32 - 1) / (AC_WARPS * 32), AC_WARPS * 32, sizeof(AcShared), st>>>(g, b, s, t0, t1);
     cabac_pack_kernel<<<total, PACK_THREADS, 0, st>>>(g, b, s, t0, t1);
 }

@@ -36,8 +36,62 @@ namespace {
 
 size_t fbytes(int w, int h) { return (size_t)w * h + 2 * (size_t)((w + 1) / 2) * ((h + 1) / 2); }
 
+// Raw and y4m pictures sit at computable offsets: a chunk is filled by several threads with pread(), each taking
+// a share of the pictures (one thread copies ~4 GB/s out of the page cache; the encoder takes 40+ GB/s).
+int read_workers() {
+    static const int n = [] {
+        if (const char* e = getenv("VCPENC_READ_THREADS")) return std::max(1, atoi(e));
+        const long c = sysconf(_SC_NPROCESSORS_ONLN);
+        return (int)std::max<long>(1, std::min<long>(8, c / 2));
+    }();
+    return n;
+}
+// pictures [first, first + count) of `hdr`-prefixed records of `fb` bytes starting at `base`; checks the y4m FRAME marker
+int pread_frames(int fd, uint64_t base, size_t hdr, size_t fb, long first, int count, uint8_t* dst, bool* bad_marker) {
+    const int nw = std::min(read_workers(), std::max(1, count / 4));
+    std::vector<int> got((size_t)nw, 0);
+    auto work = [&](int k) {
+        const int a = (int)((long long)count * k / nw), b = (int)((long long)count * (k + 1) / nw);
+        int n = 0;
+        for (int i = a; i < b; i++) {
+            const uint64_t off = base + (uint64_t)(first + i) * (hdr + fb);
+            if (hdr) {
+                char m[8];
+                if (pread(fd, m, hdr, (off_t)off) != (ssize_t)hdr) break;
+                if (memcmp(m, "FRAME\n", 6)) { *bad_marker = true; break; }
+            }
+            size_t done = 0;
+            while (done < fb) {
+                const ssize_t r = pread(fd, dst + (size_t)i * fb + done, fb - done, (off_t)(off + hdr + done));
+                if (r <= 0) break;
+                done += (size_t)r;
+            }
+            if (done < fb) break;
+            n++;
+        }
+        got[(size_t)k] = n;
+    };
+    if (nw == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nw; k++) th.emplace_back(work, k);
+        for (auto& t : th) t.join();
+    }
+    // pictures are usable up to the first share that came up short
+    int n = 0;
+    for (int k = 0; k < nw; k++) {
+        const int a = (int)((long long)count * k / nw), b = (int)((long long)count * (k + 1) / nw);
+        n += got[(size_t)k];
+        if (got[(size_t)k] < b - a) break;
+    }
+    return n;
+}
+
 struct Y4mSource : FrameSource {
     FILE* f = nullptr;
+    uint64_t data0 = 0;     // offset of the first FRAME marker
+    long next = 0;          // next picture (positional reads)
+    bool plain = true;      // every marker so far was the bare "FRAME\n": offsets are computable
     ~Y4mSource() override { if (f) fclose(f); }
     int open(const char* path, char* err, size_t errlen) {
         f = fopen(path, "rb");
@@ -62,6 +116,7 @@ struct Y4mSource : FrameSource {
             return VCPENC_E_FORMAT;
         }
         if (width <= 0 || height <= 0) { set_err(err, errlen, "bad y4m header"); return VCPENC_E_FORMAT; }
+        data0 = (uint64_t)ftello(f);
         struct stat sb;
         if (stat(path, &sb) == 0 && sb.st_size > 0) est_frames = (long)((size_t)sb.st_size / (fbytes() + 6)) + 1;
         return VCPENC_OK;
@@ -69,6 +124,15 @@ struct Y4mSource : FrameSource {
     int read(uint8_t* dst, int max, char* err, size_t errlen) override {
         const size_t fb = fbytes();
         int n = 0;
+        if (plain) {
+            bool bad = false;
+            n = pread_frames(fileno(f), data0, 6, fb, next, max, dst, &bad);
+            next += n;
+            if (!bad) return n;
+            // a FRAME marker with parameters: continue with the sequential parser from the first picture not read yet
+            plain = false;
+            if (fseeko(f, (off_t)(data0 + (uint64_t)next * (6 + fb)), SEEK_SET) != 0) { set_err(err, errlen, "y4m: seek failed"); return -VCPENC_E_IO; }
+        }
         while (n < max) {
             char line[128];
             if (!fgets(line, sizeof line, f)) break;
@@ -82,6 +146,7 @@ struct Y4mSource : FrameSource {
 
 struct RawSource : FrameSource {
     FILE* f = nullptr;
+    long next = 0;
     ~RawSource() override { if (f) fclose(f); }
     int open(const char* path, const vcpenc_params& p, int pixfmt, char* err, size_t errlen) {
         if (p.in_width <= 0 || p.in_height <= 0) { set_err(err, errlen, "raw input needs -s WxH"); return VCPENC_E_FORMAT; }
@@ -94,9 +159,9 @@ struct RawSource : FrameSource {
         return VCPENC_OK;
     }
     int read(uint8_t* dst, int max, char*, size_t) override {
-        const size_t fb = fbytes();
-        int n = 0;
-        while (n < max && fread(dst + (size_t)n * fb, 1, fb, f) == fb) n++;
+        bool bad = false;
+        const int n = pread_frames(fileno(f), 0, 0, fbytes(), next, max, dst, &bad);
+        next += n;
         return n;
     }
 };
@@ -124,7 +189,7 @@ size_t vcp_device_free_bytes(int device, size_t* total);
 //     (device, parameters): a worker checks one out for a task and hands it back; idle sessions are
 //     destroyed least-recently-used first when a create fails for lack of memory, when the pool holds
 //     more than kPoolSlots, or when the idle ones exceed half of the device's memory;
-//   * the two page-locked chunk buffers belong to the calling thread.
+//   * the page-locked chunk buffers come from a process-wide pool too (smallest idle buffer that is large enough).
 // ---------------------------------------------------------------------------------------------
 namespace {
 constexpr int kPoolSlots = 8;
@@ -140,11 +205,11 @@ std::mutex g_pool_mu;
 std::vector<PoolEntry> g_pool;
 unsigned long g_pool_clock = 0;
 
-struct ThreadCache {
-    uint8_t* pinned[2] = {nullptr, nullptr};
-    size_t pinned_bytes[2] = {0, 0};
-};
-thread_local ThreadCache t_cache;
+// page-locked chunk buffers: process-wide as well (a Go caller's goroutines move between OS threads, and a worker
+// that comes back on another thread must still find its buffers); idle buffers beyond kPinnedIdleMax are freed
+struct PinnedEntry { uint8_t* p = nullptr; size_t bytes = 0; bool in_use = false; unsigned long stamp = 0; };
+std::vector<PinnedEntry> g_pinned;
+constexpr size_t kPinnedIdleMax = (size_t)16 << 30;
 bool cache_enabled() { static const bool on = getenv("VCPENC_NO_CACHE") == nullptr; return on; }
 bool same_key(vcpenc_params a, vcpenc_params b) { a.first_gop = b.first_gop = 0; return memcmp(&a, &b, sizeof a) == 0; }
 
@@ -218,6 +283,51 @@ void release_session(vcpenc_session* ses, bool ok) {
     vcpenc_session_destroy(ses);   // not pooled (VCPENC_NO_CACHE)
 }
 
+uint8_t* acquire_pinned(size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        int best = -1;
+        for (int i = 0; i < (int)g_pinned.size(); i++)
+            if (!g_pinned[i].in_use && g_pinned[i].bytes >= bytes && (best < 0 || g_pinned[i].bytes < g_pinned[best].bytes)) best = i;
+        if (best >= 0) { g_pinned[best].in_use = true; g_pinned[best].stamp = ++g_pool_clock; return g_pinned[best].p; }
+    }
+    uint8_t* p = (uint8_t*)vcpenc_host_alloc(bytes);
+    if (!p) {   // give idle buffers back to the system and try once more
+        std::vector<uint8_t*> drop;
+        {
+            std::lock_guard<std::mutex> lk(g_pool_mu);
+            for (size_t i = 0; i < g_pinned.size();) if (!g_pinned[i].in_use) { drop.push_back(g_pinned[i].p); g_pinned.erase(g_pinned.begin() + i); } else i++;
+        }
+        for (uint8_t* q : drop) vcpenc_host_free(q);
+        p = (uint8_t*)vcpenc_host_alloc(bytes);
+    }
+    if (p && cache_enabled()) {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        PinnedEntry e; e.p = p; e.bytes = bytes; e.in_use = true; e.stamp = ++g_pool_clock;
+        g_pinned.push_back(e);
+    }
+    return p;
+}
+void release_pinned(uint8_t* p) {
+    if (!p) return;
+    std::vector<uint8_t*> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        bool pooled = false;
+        for (auto& e : g_pinned) if (e.p == p) { e.in_use = false; e.stamp = ++g_pool_clock; pooled = true; }
+        if (!pooled) drop.push_back(p);
+        for (;;) {   // oldest idle buffers go first
+            size_t idle = 0; int victim = -1;
+            for (int i = 0; i < (int)g_pinned.size(); i++)
+                if (!g_pinned[i].in_use) { idle += g_pinned[i].bytes; if (victim < 0 || g_pinned[i].stamp < g_pinned[victim].stamp) victim = i; }
+            if (idle <= kPinnedIdleMax || victim < 0) break;
+            drop.push_back(g_pinned[victim].p);
+            g_pinned.erase(g_pinned.begin() + victim);
+        }
+    }
+    for (uint8_t* q : drop) vcpenc_host_free(q);
+}
+
 // GPUs one task may use: VCPENC_GPUS=N|all shards the closed GOPs of every chunk across N devices
 // (the calling thread's device first), concatenated on the host in GOP order -- no collective.
 int task_gpus() {
@@ -229,10 +339,13 @@ int task_gpus() {
 }
 
 extern "C" void vcpenc_thread_release(void) {
-    for (int i = 0; i < 2; i++) if (t_cache.pinned[i]) vcpenc_host_free(t_cache.pinned[i]);
-    t_cache = ThreadCache();
-    std::lock_guard<std::mutex> lk(g_pool_mu);
-    while (evict_one_locked(-1)) {}
+    std::vector<uint8_t*> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        while (evict_one_locked(-1)) {}
+        for (size_t i = 0; i < g_pinned.size();) if (!g_pinned[i].in_use) { drop.push_back(g_pinned[i].p); g_pinned.erase(g_pinned.begin() + i); } else i++;
+    }
+    for (uint8_t* q : drop) vcpenc_host_free(q);
 }
 extern "C" int vcpenc_set_thread_device(int device) {
     if (device < 0 || device >= vcpenc_device_count()) return VCPENC_E_NODEVICE;
@@ -254,6 +367,12 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
     int rc = vcpenc_parse_args(argc, argv, &p, err, errlen);
     if (rc) return rc;
     if (vcpenc_device_count() <= 0) { set_err(err, errlen, "no CUDA device available (libvcpenc has no CPU fallback)"); return VCPENC_E_NODEVICE; }
+    if ((p.maxrate > 0 || p.bufsize > 0) && !getenv("VCPENC_QUIET")) {
+        // a warning, as ffmpeg prints at -loglevel warning: the h264-nvenc-hq preset's cap (internal/config/config.go:46) is parsed, not modelled
+        static std::atomic<bool> once{false};
+        if (!once.exchange(true))
+            fprintf(stderr, "[vcpenc] warning: -maxrate / -bufsize are not enforced (no VBV model yet); -b:v is met per GOP (budget = bitrate x GOP duration)\n");
+    }
 
     const std::string in = input, outp = output;
     std::unique_ptr<FrameSource> src;
@@ -311,20 +430,11 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
     chunk = std::max(p.gop, (chunk + p.gop - 1) / p.gop * p.gop);
     const int nbuf = (est > 0 && est <= chunk) ? 1 : 2;   // one chunk holds everything: nothing to overlap
     uint8_t* fbuf[2] = {nullptr, nullptr};
-    bool own_pinned = !cache_enabled();
     for (int i = 0; i < nbuf; i++) {
         const size_t need = (size_t)chunk * sfb;
-        if (own_pinned) fbuf[i] = (uint8_t*)vcpenc_host_alloc(need);
-        else {
-            if (t_cache.pinned_bytes[i] < need) {
-                if (t_cache.pinned[i]) vcpenc_host_free(t_cache.pinned[i]);
-                t_cache.pinned[i] = (uint8_t*)vcpenc_host_alloc(need);
-                t_cache.pinned_bytes[i] = t_cache.pinned[i] ? need : 0;
-            }
-            fbuf[i] = t_cache.pinned[i];
-        }
+        fbuf[i] = acquire_pinned(need);
         if (!fbuf[i]) {
-            if (own_pinned) for (int k = 0; k < i; k++) vcpenc_host_free(fbuf[k]);
+            for (int k = 0; k < i; k++) release_pinned(fbuf[k]);
             set_err(err, errlen, "cannot allocate %zu bytes of pinned host memory", need);
             return VCPENC_E_CUDA;
         }
@@ -388,7 +498,7 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
         if (rawf) { fclose(rawf); rawf = nullptr; }
         if (writer_open && !raw_out) mp4.abandon();
         remove(output);
-        if (own_pinned) for (int i = 0; i < nbuf; i++) vcpenc_host_free(fbuf[i]);
+        for (int i = 0; i < nbuf; i++) release_pinned(fbuf[i]);
         return code;
     };
     auto stop_message = [&](int code) {
@@ -501,7 +611,7 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
     }
     if (reader.joinable()) reader.join();
     for (auto& sh : shards) { if (sh.ses) release_session(sh.ses, true); sh.ses = nullptr; }
-    if (own_pinned) for (int i = 0; i < nbuf; i++) vcpenc_host_free(fbuf[i]);
+    for (int i = 0; i < nbuf; i++) release_pinned(fbuf[i]);
     if (total == 0) {
         if (rawf) fclose(rawf);
         if (writer_open && !raw_out) mp4.abandon();

@@ -97,6 +97,10 @@ struct VcpBufs {
     size_t bins_cap;                 // in bins
     uint2* mbdesc;                   // [nframes][nmb]: offset low 32 | count (20 bits) + offset high << 20
     uint32_t* slice_bins;            // [nframes][slices] bins per slice
+    uint16_t* sbins;                 // the same bins laid out as one contiguous, 16-byte aligned stream per slice (cabac_gather_kernel)
+    unsigned long long* sbins_cursor;
+    size_t sbins_cap;                // in bins
+    unsigned long long* sslice_off;  // [nframes][slices] start of the slice's stream in sbins (bins)
     uint8_t* crbsp;                  // arena of slice RBSPs written by the arithmetic coder
     unsigned long long* crbsp_cursor;
     size_t crbsp_cap;

@@ -48,8 +48,9 @@ __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(vcp_smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Wait for phase `parity`.  A box that never lands would spin forever: after ~2^26 probes the kernel traps,
-// so a bad coordinate or byte count shows up as a launch failure, not a hung GPU.
+// Wait for phase `parity` (a probe suspends the thread for a hardware-chosen time; an explicit suspend-time hint of 2 us
+// doubled me_refine's duration, measured, so none is given).  A box that never lands would wait forever: after ~2^26
+// probes the kernel traps, so a bad coordinate or byte count shows up as a launch failure, not a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t a = vcp_smem_u32(bar);
     uint32_t done = 0;
@@ -59,6 +60,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (spin > (1u << 26)) __trap();
     }
 }
+// Every lane of the waiting warp probes: the hardware parks the whole warp on the barrier.  Letting one lane wait and the
+// others follow through __syncwarp() turned the wait into a divergent polling loop: me_refine 23 -> 49 ms per step (measured).
+// rounded-up average of four unsigned bytes, (a + b + 1) >> 1 per byte: five plain integer instructions
+// (the __vavgu4 intrinsic is emulated with about twice as many on sm_100a)
+__device__ __forceinline__ uint32_t vcp_avg4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) >> 1) & 0x7f7f7f7fu); }
 // generic-proxy accesses to shared memory before this point are ordered before later async-proxy (TMA) writes
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
