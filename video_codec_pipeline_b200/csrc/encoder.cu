@@ -601,6 +601,10 @@ int vcpenc_session_upload_device(vcpenc_session* s, const uint8_t* dframes, int 
 
 uint64_t vcpenc_session_launch_count(vcpenc_session* s) { return s ? s->launches : 0; }
 
+// timing experiments only (the output is garbage): VCPENC_DEBUG_SKIP = bit mask of kernels NOT launched,
+// 1 pre-pass, 2 refine, 4 p_recon, 8 deblock, 16 hpel, 32 CAVLC, 64 mbinfo/pad -- the marginal cost of a kernel inside the overlapped step
+static const int g_dbg_skip = [] { const char* e = getenv("VCPENC_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
+
 static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
     const VcpGeom& g = s->g;
     const VcpBufs& b = s->b;
@@ -623,7 +627,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
     const bool streamed = s->streamed && !s->profile;
     if (s->streamed && s->profile) CK(cudaStreamSynchronize(s->st_up));   // profiling was switched on after an asynchronous upload
     if (s->profile) {
-        Prof pr(s, VCPENC_K_ME_PRE);
+        Prof pr(s, VCPENC_K_ME_PRE, 2);
         vcp_launch_me_prepass(g, b, s->tm, N, gop, -1, s->st);
     } else {
         // picture by picture and group by group on its own stream: chain step t of a group only waits for
@@ -634,8 +638,8 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
         auto pre = [&](int k, int t) -> int {
             int gA, gB;
             group_gops(s, N, ng, k, &gA, &gB);
-            s->launches += 1;
-            vcp_launch_me_prepass(g, b, s->tm, N, gop, t, s->st_pre, gA, gB);
+            s->launches += 2;   // L1 + L0 kernels
+            if (!(g_dbg_skip & 1)) vcp_launch_me_prepass(g, b, s->tm, N, gop, t, s->st_pre, gA, gB);
             CK(cudaEventRecord(s->ev_pre_t[(size_t)k * s->pre_T + t], s->st_pre));
             return VCPENC_OK;
         };
@@ -690,9 +694,9 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 vcp_launch_i_recon(g, bt, sp, st);
             } else {
                 if (!s->profile) CK(cudaStreamWaitEvent(st, s->ev_pre_t[(size_t)k * s->pre_T + t], 0));
-                { Prof pr(s, VCPENC_K_ME_REFINE, 1, st); vcp_launch_me_refine(g, bt, s->tm, sp, st); }
-                { Prof pr(s, VCPENC_K_P_RECON, 2, st); vcp_launch_p_recon(g, bt, sp, st); vcp_launch_i_fix(g, bt, sp, st); }
-                { Prof pr(s, VCPENC_K_MBINFO, 1, st); vcp_launch_mbinfo(g, bt, sp, st); }
+                { Prof pr(s, VCPENC_K_ME_REFINE, 1, st); if (!(g_dbg_skip & 2)) vcp_launch_me_refine(g, bt, s->tm, sp, st); }
+                { Prof pr(s, VCPENC_K_P_RECON, 2, st); if (!(g_dbg_skip & 4)) { vcp_launch_p_recon(g, bt, sp, st); vcp_launch_i_fix(g, bt, sp, st); } }
+                { Prof pr(s, VCPENC_K_MBINFO, 1, st); if (!(g_dbg_skip & 64)) vcp_launch_mbinfo(g, bt, sp, st); }
             }
             if (s->p.debug) {
                 for (int gi = gA; gi < gA + sp.ngop; gi++) {
@@ -729,20 +733,22 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                     if (!dbg_skip) vcp_launch_cabac_encode(g, bt, sb, t0, t + 1, sc);
                 }
             } else {
+                if (!(g_dbg_skip & 32)) {
                 { Prof pr(s, VCPENC_K_CAVLC_COUNT, 1, se); vcp_launch_cavlc_count(g, bt, sp, se); }
                 { Prof pr(s, VCPENC_K_CAVLC_SCAN, 1, se); vcp_launch_cavlc_scan(g, bt, sp, se); }
                 { Prof pr(s, VCPENC_K_CAVLC_WRITE, 2, se); vcp_launch_cavlc_write(g, bt, sp, se); vcp_launch_nal_pack(g, bt, sp, se); }
+                }
                 if (g.rc_abr) { Prof pr(s, VCPENC_K_RC, 1, se); vcp_launch_rc_update(g, bt, sp, se); }
             }
             if (!s->profile) CK(cudaEventRecord(s->ev_ent[k][par], se));
             if (g.hevc_sao) { Prof pr(s, VCPENC_K_DEBLOCK, 1, st); vcp_launch_hevc_sao_copy(g, bt, sp, st); }   // after the fork: only the picture changes
             else if (g.deblock_idc != 1) {
                 Prof pr(s, VCPENC_K_DEBLOCK, g.hevc ? 2 : 1, st);
-                if (g.hevc) vcp_launch_hevc_deblock(g, bt, sp, st); else vcp_launch_deblock(g, bt, sp, st);
+                if (g.hevc) vcp_launch_hevc_deblock(g, bt, sp, st); else if (!(g_dbg_skip & 8)) vcp_launch_deblock(g, bt, sp, st);
             }
-            { Prof pr(s, VCPENC_K_PAD, 1, st); vcp_launch_pad(g, bt, sp, st); }
+            { Prof pr(s, VCPENC_K_PAD, 1, st); if (!(g_dbg_skip & 64)) vcp_launch_pad(g, bt, sp, st); }
             // half-sample planes of this reconstruction for the next picture's search and prediction
-            if (t + 1 < gop && t + 1 < N && (!g.hevc || g.hevc_subpel)) { Prof pr(s, VCPENC_K_HPEL, 1, st); vcp_launch_hpel(g, bt, sp, st); }
+            if (t + 1 < gop && t + 1 < N && (!g.hevc || g.hevc_subpel)) { Prof pr(s, VCPENC_K_HPEL, 1, st); if (!(g_dbg_skip & 16)) vcp_launch_hpel(g, bt, sp, st); }
         }
     }
     if (!s->profile)

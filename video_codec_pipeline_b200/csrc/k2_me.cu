@@ -35,7 +35,8 @@ namespace {
 // K2a
 // ---------------------------------------------------------------------------------------------
 constexpr int PP_MBS = 16;                         // macroblocks per CTA (one row segment)
-constexpr int PP_THREADS = 512;                    // 16 warps: 12.5 carry L1 columns, 16 = one per macroblock in L0
+constexpr int PP_THREADS = 416;                    // 13 warps: 12.5 carry the L1 columns
+constexpr int PP0_WARPS = 4;                       // L0 kernel: macroblocks (warps) per CTA
 constexpr int PP_NDX = 2 * VCP_ME_R1 + 1;          // 25
 constexpr int PP_ITEMS = PP_MBS * PP_NDX;          // 400 (macroblock, dx) columns
 constexpr int PP_WIN_USED = 160;                   // bytes of a window row the columns read (the box brings 16 more for the shifts)
@@ -43,28 +44,30 @@ constexpr int PP_WIN_USED = 160;                   // bytes of a window row the 
 struct __align__(128) PrepassSmem {
     uint8_t win[4][VCP_L1_WIN_H][VCP_L1_WIN_W];    // copy k = the window shifted left by k bytes; copy 0 is where the box lands
     uint8_t hcur[8][VCP_L1_CUR_W];                 // the CTA's 16 half-res current blocks
-    uint8_t l0ref[PP_MBS][1024];                   // per macroblock: VCP_L0_REF_H rows of VCP_L0_REF_W bytes
-    uint8_t l0cur[PP_MBS][16][16];
     uint64_t bar_l1;
-    uint64_t bar_l0[PP_MBS];
     uint32_t best1[PP_MBS];
 };
-static_assert(sizeof(PrepassSmem) <= 100 * 1024, "two CTAs per SM");
+static_assert(sizeof(PrepassSmem) <= 48 * 1024, "static shared memory, three CTAs per SM");
+struct __align__(128) PrepassL0Warp {
+    uint8_t ref[1024];                             // VCP_L0_REF_H rows of VCP_L0_REF_W bytes
+    uint8_t cur[16][16];
+    uint64_t bar;
+};
 static_assert(VCP_L0_REF_H * VCP_L0_REF_W <= 1024, "L0 reference box");
 
 // grid z = frame (t < 0: every resident frame) or GOP (t >= 0: picture t of every GOP, so that the
 // pre-pass of later pictures runs beside the reconstruction chain of earlier ones)
-__global__ void __launch_bounds__(PP_THREADS, 2) me_prepass_kernel(VcpGeom g, VcpBufs b, int nframes, int gop, int t, int g0,
+// Two kernels, one TMA phase each (a single kernel waited twice per CTA at 2 CTAs per SM: 45 % of its warp samples sat in
+// the waits).  L1 leaves twice its best half-res vector in mvfp[], L0 replaces it by the full-res vector.
+__global__ void __launch_bounds__(PP_THREADS, 3) me_prepass_kernel(VcpGeom g, VcpBufs b, int nframes, int gop, int t, int g0,
                                                                     const __grid_constant__ VcpTmaps tm) {
-    extern __shared__ __align__(128) uint8_t pp_raw[];
-    PrepassSmem& S = *reinterpret_cast<PrepassSmem*>(pp_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    __shared__ PrepassSmem S;
+    const int tid = threadIdx.x;
     const int n = t < 0 ? (int)blockIdx.z : ((int)blockIdx.z + g0) * gop + t;
     if (n >= nframes || n % gop == 0) return;  // IDR: no search (uniform for the CTA)
     const int my = blockIdx.y, mx0 = blockIdx.x * PP_MBS;
     if (tid == 0) {
         mbar_init(&S.bar_l1, 1);
-        for (int i = 0; i < PP_MBS; i++) mbar_init(&S.bar_l0[i], 1);
         mbar_init_fence();
     }
     if (tid < PP_MBS) S.best1[tid] = 0xffffffffu;
@@ -130,26 +133,41 @@ __global__ void __launch_bounds__(PP_THREADS, 2) me_prepass_kernel(VcpGeom g, Vc
     }
     __syncthreads();
 
-    // ---- L0: warp = macroblock, +-2 around twice the L1 vector on the full-res originals ------------
-    const int mx = mx0 + warp;
+    if (tid < PP_MBS && mx0 + tid < g.mbw) {
+        const int bi = (int)(S.best1[tid] & 0xffff);
+        b.mvfp[(size_t)n * g.nmb + my * g.mbw + mx0 + tid] = make_short2((short)(2 * (bi % PP_NDX - VCP_ME_R1)), (short)(2 * (bi / PP_NDX - VCP_ME_R1)));
+    }
+}
+
+// L0: warp = macroblock, +-2 around twice the L1 vector on the full-res originals
+__global__ void __launch_bounds__(PP0_WARPS * 32) me_prepass_l0_kernel(VcpGeom g, VcpBufs b, int nframes, int gop, int t, int g0,
+                                                                        const __grid_constant__ VcpTmaps tm) {
+    __shared__ PrepassL0Warp sh[PP0_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = t < 0 ? (int)blockIdx.z : ((int)blockIdx.z + g0) * gop + t;
+    if (n >= nframes || n % gop == 0) return;
+    const int my = blockIdx.y, mx = blockIdx.x * PP0_WARPS + warp;
     if (mx >= g.mbw) return;
-    const int bi = (int)(S.best1[warp] & 0xffff);
-    const int cx = 2 * (bi % PP_NDX - VCP_ME_R1), cy = 2 * (bi / PP_NDX - VCP_ME_R1);
+    PrepassL0Warp& S = sh[warp];
+    if (lane == 0) { mbar_init(&S.bar, 1); mbar_init_fence(); }
+    __syncwarp();
+    const short2 l1 = b.mvfp[(size_t)n * g.nmb + my * g.mbw + mx];
+    const int cx = l1.x, cy = l1.y;
     const int xr = 16 * mx + cx - 2 + VCP_PAD;       // plane column of the region's first sample
     if (lane == 0) {
-        mbar_expect_tx(&S.bar_l0[warp], (uint32_t)(VCP_L0_REF_H * VCP_L0_REF_W + 256));
-        tma_load_3d(&S.l0ref[warp][0], &tm.y_ref, &S.bar_l0[warp], xr & ~15, 16 * my + cy - 2 + VCP_PAD, n - 1);
-        tma_load_3d(&S.l0cur[warp][0][0], &tm.y_cur, &S.bar_l0[warp], 16 * mx + VCP_PAD, 16 * my + VCP_PAD, n);
+        mbar_expect_tx(&S.bar, (uint32_t)(VCP_L0_REF_H * VCP_L0_REF_W + 256));
+        tma_load_3d(&S.ref[0], &tm.y_ref, &S.bar, xr & ~15, 16 * my + cy - 2 + VCP_PAD, n - 1);
+        tma_load_3d(&S.cur[0][0], &tm.y_cur, &S.bar, 16 * mx + VCP_PAD, 16 * my + VCP_PAD, n);
     }
-    mbar_wait(&S.bar_l0[warp], 0);
+    mbar_wait(&S.bar, 0);
     uint32_t acc[5] = {0, 0, 0, 0, 0};
     const int ox = lane % 5, rg = lane / 5;   // lanes 0..19: horizontal offset, group of four current rows
     if (lane < 20) {
         uint4 c[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) c[i] = *reinterpret_cast<const uint4*>(&S.l0cur[warp][4 * rg + i][0]);
+        for (int i = 0; i < 4; i++) c[i] = *reinterpret_cast<const uint4*>(&S.cur[4 * rg + i][0]);
         const int o = (xr & 15) + ox;                                // byte of this lane's first column inside a region row
-        const uint32_t* rp = reinterpret_cast<const uint32_t*>(&S.l0ref[warp][(4 * rg) * VCP_L0_REF_W]) + (o >> 2);
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(&S.ref[(4 * rg) * VCP_L0_REF_W]) + (o >> 2);
         const uint32_t sh = (uint32_t)(o & 3) * 8u;
 #pragma unroll
         for (int tt = 0; tt < 8; tt++) {
@@ -473,10 +491,10 @@ void vcp_launch_me_prepass(const VcpGeom& g, const VcpBufs& b, const VcpTmaps& t
     int nz = t < 0 ? nframes : (nframes - t + gop - 1) / gop;   // GOPs that own a picture t
     if (t >= 0) { if (g1 >= 0 && g1 < nz) nz = g1; nz -= g0; } else g0 = 0;
     if (nz <= 0) return;
-    // function attributes are per device: a process may drive several GPUs from different threads
-    cudaFuncSetAttribute(me_prepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrepassSmem));
     dim3 grid((g.mbw + PP_MBS - 1) / PP_MBS, g.mbh, nz);
-    me_prepass_kernel<<<grid, PP_THREADS, sizeof(PrepassSmem), st>>>(g, b, nframes, gop, t, g0, tm);
+    me_prepass_kernel<<<grid, PP_THREADS, 0, st>>>(g, b, nframes, gop, t, g0, tm);
+    dim3 grid0((g.mbw + PP0_WARPS - 1) / PP0_WARPS, g.mbh, nz);
+    me_prepass_l0_kernel<<<grid0, PP0_WARPS * 32, 0, st>>>(g, b, nframes, gop, t, g0, tm);
 }
 
 void vcp_launch_me_refine(const VcpGeom& g, const VcpBufs& b, const VcpTmaps& tm, const VcpStep& s, cudaStream_t st) {

@@ -73,45 +73,39 @@ struct __align__(16) DbTile {
     uint8_t bs[2][4][4];   // [dir][edge][segment]
 };
 
-// One luma line across an edge, in registers: v[0..7] = p3 p2 p1 p0 q0 q1 q2 q3.
-__device__ __forceinline__ void filt_luma_reg(int* v, int bS, int alpha, int beta, int tc0) {
+// One line across an edge, in registers: v[0..7] = p3 p2 p1 p0 q0 q1 q2 q3.  Luma and chroma lanes run the SAME
+// instruction stream (chroma = the luma filter with its p1 / q1 / three-tap branches switched off: 8.7.2.3 and 8.7.2.4 are
+// written that way), results are selected, nothing branches on sample values: the two plane types no longer serialise
+// inside the warp and the filter conditions cost no branch resolution on the wavefront's critical path.
+//   strong: warp-uniform, true when some lane of the warp has bS 4 (intra macroblock edges: rare in P pictures)
+__device__ __forceinline__ void filt_edge(int* v, int bS, bool chroma, int alpha, int beta, int tc0, bool strong) {
     const int p3 = v[0], p2 = v[1], p1 = v[2], p0 = v[3], q0 = v[4], q1 = v[5], q2 = v[6], q3 = v[7];
-    if (vcp_iabs(p0 - q0) >= alpha || vcp_iabs(p1 - p0) >= beta || vcp_iabs(q1 - q0) >= beta) return;
-    const int ap = vcp_iabs(p2 - p0), aq = vcp_iabs(q2 - q0);
-    if (bS < 4) {
-        const int tc = tc0 + (ap < beta) + (aq < beta);
-        const int d = vcp_clip3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
-        v[3] = vcp_clip255(p0 + d);
-        v[4] = vcp_clip255(q0 - d);
-        if (ap < beta) v[2] = p1 + vcp_clip3(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - 2 * p1) >> 1);
-        if (aq < beta) v[5] = q1 + vcp_clip3(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - 2 * q1) >> 1);
-    } else {
-        const bool small = vcp_iabs(p0 - q0) < ((alpha >> 2) + 2);
-        if (ap < beta && small) {
-            v[3] = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3;
-            v[2] = (p2 + p1 + p0 + q0 + 2) >> 2;
-            v[1] = (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3;
-        } else v[3] = (2 * p1 + p0 + q1 + 2) >> 2;
-        if (aq < beta && small) {
-            v[4] = (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3;
-            v[5] = (p0 + q0 + q1 + q2 + 2) >> 2;
-            v[6] = (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3;
-        } else v[4] = (2 * q1 + q0 + p1 + 2) >> 2;
+    const int dpq = vcp_iabs(p0 - q0);
+    const bool on = bS > 0 && dpq < alpha && vcp_iabs(p1 - p0) < beta && vcp_iabs(q1 - q0) < beta;
+    const bool apb = !chroma && vcp_iabs(p2 - p0) < beta, aqb = !chroma && vcp_iabs(q2 - q0) < beta;
+    // bS < 4
+    const int tc = tc0 + (chroma ? 1 : (int)apb + (int)aqb);
+    const int d = vcp_clip3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
+    const int avg = (p0 + q0 + 1) >> 1;
+    int n1 = apb ? p1 + vcp_clip3(-tc0, tc0, (p2 + avg - 2 * p1) >> 1) : p1;   // p1'
+    int n2 = p2;
+    int n3 = vcp_clip255(p0 + d);                                             // p0'
+    int n4 = vcp_clip255(q0 - d);                                             // q0'
+    int n5 = aqb ? q1 + vcp_clip3(-tc0, tc0, (q2 + avg - 2 * q1) >> 1) : q1;   // q1'
+    int n6 = q2;
+    if (strong) {
+        const bool s4 = bS == 4;
+        const bool small = dpq < ((alpha >> 2) + 2);
+        const bool ps = apb && small, qs = aqb && small;
+        const int sp0 = ps ? (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3 : (2 * p1 + p0 + q1 + 2) >> 2;
+        const int sp1 = ps ? (p2 + p1 + p0 + q0 + 2) >> 2 : p1;
+        const int sp2 = ps ? (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3 : p2;
+        const int sq0 = qs ? (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3 : (2 * q1 + q0 + p1 + 2) >> 2;
+        const int sq1 = qs ? (p0 + q0 + q1 + q2 + 2) >> 2 : q1;
+        const int sq2 = qs ? (2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3 : q2;
+        if (s4) { n1 = sp1; n2 = sp2; n3 = sp0; n4 = sq0; n5 = sq1; n6 = sq2; }
     }
-}
-// chroma: v[0..3] = p1 p0 q0 q1
-__device__ __forceinline__ void filt_chroma_reg(int* v, int bS, int alpha, int beta, int tc0) {
-    const int p1 = v[0], p0 = v[1], q0 = v[2], q1 = v[3];
-    if (vcp_iabs(p0 - q0) >= alpha || vcp_iabs(p1 - p0) >= beta || vcp_iabs(q1 - q0) >= beta) return;
-    if (bS < 4) {
-        const int tc = tc0 + 1;
-        const int d = vcp_clip3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
-        v[1] = vcp_clip255(p0 + d);
-        v[2] = vcp_clip255(q0 - d);
-    } else {
-        v[1] = (2 * p1 + p0 + q1 + 2) >> 2;
-        v[2] = (2 * q1 + q0 + p1 + 2) >> 2;
-    }
+    if (on) { v[1] = n2; v[2] = n1; v[3] = n3; v[4] = n4; v[5] = n5; v[6] = n6; }
 }
 
 // Everything one macroblock needs that does not depend on the row above, fetched one iteration
@@ -225,7 +219,11 @@ struct DbShared {
     volatile int* taken;          // [BH] ring slots the row has finished reading from the row above
 };
 
-__global__ void __launch_bounds__(512) deblock_kernel(VcpGeom g, VcpBufs b, VcpStep s, int BH, int nbands,
+// MAXT only steers the register allocation (512 threads are launched at most): 512 -> 126 registers, 768 -> 80, 1024 -> 64.
+// A CTA of 16 warps at 126 registers holds the SM's whole register file for the ~0.7 ms a picture band takes, at an issue
+// rate of 0.3 per cycle: nothing else can run beside it.  Fewer registers leave room for the other GOP groups' kernels.
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) deblock_kernel(VcpGeom g, VcpBufs b, VcpStep s, int BH, int nbands,
                                                         int* __restrict__ ticket, int* __restrict__ progress, unsigned spin_ns) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int my_ticket;
@@ -268,6 +266,7 @@ __global__ void __launch_bounds__(512) deblock_kernel(VcpGeom g, VcpBufs b, VcpS
     const DbLaneAddr la = db_lane_addr(g, b, Y, U, V, base, my, top_ok, lane);
     DbPrefetch f = db_prefetch(la, 0);
     int seen_up = 0;
+    uint32_t prev_nz = 0u;
     for (int mx = 0; mx < g.mbw; mx++) {
         // (1) own samples and boundary strengths -> tile
         const int mybs = db_strength(f, lane);
@@ -311,69 +310,58 @@ __global__ void __launch_bounds__(512) deblock_kernel(VcpGeom g, VcpBufs b, VcpS
         }
         __syncwarp();
         if (top_smem && lane == 0) sh.taken[warp] = mx + 1;   // slot mx may be recycled by the row above
+        const bool strong_any = __any_sync(0xffffffffu, mybs == 4);
         if (nzmask & 0x0000ffffu) {
-            // vertical edges, whole sample row in registers: lanes 0-15 luma rows, 16-31 chroma rows
-            if (lum) {
-                uint32_t* row = reinterpret_cast<uint32_t*>(&T.Y[lane + 4][0]);
-                int v[20];
+            // vertical edges, whole sample row in registers: lanes 0-15 luma rows (20 samples, edges at 4 8 12 16), lanes 16-31
+            // chroma rows (12 samples, edges at 4 and 8 = slots 0 and 1); one code path for both
+            const int pl = (lane - 16) >> 3, r = lane & 7;
+            uint32_t* row = lum ? reinterpret_cast<uint32_t*>(&T.Y[lane + 4][0]) : reinterpret_cast<uint32_t*>(&T.C[pl][r + 2][0]);
+            const uint8_t* bsr = lum ? &T.bs[0][0][lane >> 2] : &T.bs[0][0][r >> 1];   // luma: edge e at +4e; chroma: edge 2e at +8e
+            const int bstep = lum ? 4 : 8;
+            int v[20];
 #pragma unroll
-                for (int w = 0; w < 5; w++) {
-                    const uint32_t x = row[w];
-                    v[4 * w] = x & 255; v[4 * w + 1] = (x >> 8) & 255; v[4 * w + 2] = (x >> 16) & 255; v[4 * w + 3] = x >> 24;
-                }
-#pragma unroll
-                for (int ed = 0; ed < 4; ed++) {
-                    const int bS = T.bs[0][ed][lane >> 2];
-                    if (bS) filt_luma_reg(&v[4 * ed], bS, alpha, beta, bS < 4 ? tc[bS - 1] : 0);
-                }
-#pragma unroll
-                for (int w = 0; w < 5; w++) row[w] = pack4(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3]);
-            } else {
-                const int pl = (lane - 16) >> 3, r = lane & 7;
-                uint32_t* row = reinterpret_cast<uint32_t*>(&T.C[pl][r + 2][0]);
-                int v[12];
-#pragma unroll
-                for (int w = 0; w < 3; w++) {
-                    const uint32_t x = row[w];
-                    v[4 * w] = x & 255; v[4 * w + 1] = (x >> 8) & 255; v[4 * w + 2] = (x >> 16) & 255; v[4 * w + 3] = x >> 24;
-                }
-#pragma unroll
-                for (int ed = 0; ed < 4; ed += 2) {
-                    const int bS = T.bs[0][ed][r >> 1];
-                    if (bS) filt_chroma_reg(&v[2 + 2 * ed], bS, alpha, beta, bS < 4 ? tc[bS - 1] : 0);
-                }
-#pragma unroll
-                for (int w = 0; w < 3; w++) row[w] = pack4(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3]);
+            for (int w = 0; w < 5; w++) {
+                const uint32_t x = (lum || w < 3) ? row[w] : 0u;
+                v[4 * w] = x & 255; v[4 * w + 1] = (x >> 8) & 255; v[4 * w + 2] = (x >> 16) & 255; v[4 * w + 3] = x >> 24;
             }
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int bS = (lum || e < 2) ? bsr[bstep * e] : 0;
+                // an edge slot no lane filters (inter macroblocks without coefficients on either side) is skipped by the whole warp
+                if (__any_sync(0xffffffffu, bS > 0))
+                    filt_edge(&v[4 * e], bS, !lum, alpha, beta, bS == 1 ? tc[0] : (bS == 2 ? tc[1] : tc[2]), strong_any);
+            }
+#pragma unroll
+            for (int w = 0; w < 5; w++)
+                if (lum || w < 3) row[w] = pack4(v[4 * w], v[4 * w + 1], v[4 * w + 2], v[4 * w + 3]);
         }
         __syncwarp();
         if (nzmask & 0xffff0000u) {
-            // horizontal edges, whole sample column in registers: lanes 0-15 luma, 16-31 chroma columns
-            if (lum) {
-                uint8_t* col = &T.Y[0][lane + 4];
-                int v[20];
+            // horizontal edges, whole sample column in registers: lanes 0-15 luma columns (tile rows 0..19 = y -4..15), lanes
+            // 16-31 chroma columns (tile rows 0..9 = y -2..7, held in v[2..11] so that the edges sit where luma's do)
+            const int pl = (lane - 16) >> 3, cx = lane & 7;
+            uint8_t* col = lum ? &T.Y[0][lane + 4] : &T.C[pl][0][cx + 4];
+            const int pitch = lum ? 24 : 12;
+            const uint8_t* bsr = lum ? &T.bs[1][0][lane >> 2] : &T.bs[1][0][cx >> 1];
+            const int bstep = lum ? 4 : 8;
+            int v[20];
 #pragma unroll
-                for (int r = 0; r < 20; r++) v[r] = col[24 * r];
+            for (int r = 0; r < 20; r++) {
+                // chroma: v[r] = tile row r - 2 (rows above the tile do not exist: any value, never used by the chroma filter)
+                const int tr = lum ? r : (r < 2 ? 0 : (r < 12 ? r - 2 : 9));
+                v[r] = (lum || r < 12) ? col[pitch * tr] : 0;
+            }
 #pragma unroll
-                for (int ed = 0; ed < 4; ed++) {
-                    const int bS = T.bs[1][ed][lane >> 2];
-                    if (bS) filt_luma_reg(&v[4 * ed], bS, alpha, beta, bS < 4 ? tc[bS - 1] : 0);
-                }
+            for (int e = 0; e < 4; e++) {
+                const int bS = (lum || e < 2) ? bsr[bstep * e] : 0;
+                // an edge slot no lane filters (inter macroblocks without coefficients on either side) is skipped by the whole warp
+                if (__any_sync(0xffffffffu, bS > 0))
+                    filt_edge(&v[4 * e], bS, !lum, alpha, beta, bS == 1 ? tc[0] : (bS == 2 ? tc[1] : tc[2]), strong_any);
+            }
 #pragma unroll
-                for (int r = 1; r < 19; r++) col[24 * r] = (uint8_t)v[r];
-            } else {
-                const int pl = (lane - 16) >> 3, cx = lane & 7;
-                uint8_t* col = &T.C[pl][0][cx + 4];
-                int v[10];
-#pragma unroll
-                for (int r = 0; r < 10; r++) v[r] = col[12 * r];
-#pragma unroll
-                for (int ed = 0; ed < 4; ed += 2) {
-                    const int bS = T.bs[1][ed][cx >> 1];
-                    if (bS) filt_chroma_reg(&v[2 * ed], bS, alpha, beta, bS < 4 ? tc[bS - 1] : 0);
-                }
-#pragma unroll
-                for (int r = 1; r < 9; r++) col[12 * r] = (uint8_t)v[r];
+            for (int r = 1; r < 19; r++) {
+                if (lum) col[24 * r] = (uint8_t)v[r];
+                else if (r >= 3 && r <= 10) col[12 * (r - 2)] = (uint8_t)v[r];
             }
         }
         __syncwarp();
@@ -399,7 +387,11 @@ __global__ void __launch_bounds__(512) deblock_kernel(VcpGeom g, VcpBufs b, VcpS
         }
         // (5) write back.  Luma rows 0..15: x=-4..11 now (x=12..15 wait for the next vertical
         //     edge; on the last macroblock they go out too); top rows -3..-1: x=0..15.
-        {
+        //     Nothing to store when neither this macroblock nor the previous one (whose last four columns go out
+        //     now) filtered anything: the tile still holds what the picture holds.
+        const bool wb = (nzmask | prev_nz) != 0u;
+        prev_nz = nzmask;
+        if (wb) {
             const int r = lane >> 1, h = lane & 1;
             uint32_t* dst = reinterpret_cast<uint32_t*>(Y + (size_t)r * g.ys + 16 * mx - 4);
             const uint32_t* src = reinterpret_cast<const uint32_t*>(&T.Y[r + 4][0]);
@@ -411,7 +403,7 @@ __global__ void __launch_bounds__(512) deblock_kernel(VcpGeom g, VcpBufs b, VcpS
             *reinterpret_cast<uint32_t*>(Y + (ptrdiff_t)(r - 3) * g.ys + 16 * mx + 4 * w) =
                 *reinterpret_cast<const uint32_t*>(&T.Y[r + 1][4 + 4 * w]);
         }
-        {
+        if (wb) {
             const int pl = lane >> 4, r = (lane >> 1) & 7, h = lane & 1;
             uint32_t* dst = reinterpret_cast<uint32_t*>((pl ? V : U) + (size_t)r * g.cs + 8 * mx - 4);
             const uint32_t* src = reinterpret_cast<const uint32_t*>(&T.C[pl][r + 2][0]);
@@ -497,9 +489,12 @@ void vcp_launch_deblock(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cu
     int* sync = b.db_sync + (size_t)s.g0 * (g.mbh + 1);
     cudaMemsetAsync(sync, 0, (size_t)(s.ngop * g.mbh + 1) * sizeof(int), st);
     // function attributes are per device: a process may drive several GPUs from different threads
-    if (smem > 48 * 1024) cudaFuncSetAttribute(deblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     static const unsigned spin_ns = [] { const char* e = getenv("VCPENC_DB_SPIN_NS"); return e ? (unsigned)atoi(e) : 0u; }();
-    deblock_kernel<<<s.ngop * nbands, BH * 32, smem, st>>>(g, b, s, BH, nbands, sync, sync + 1 - (size_t)s.g0 * g.mbh, spin_ns);
+    static const int regs = [] { const char* e = getenv("VCPENC_DB_REGS"); return e ? atoi(e) : 80; }();   // measured: 126 -> 119.5, 80 -> 118.7, 64 (spills) -> 128.2 ms per 1080p step
+    int* progress = sync + 1 - (size_t)s.g0 * g.mbh;
+    if (regs >= 120) deblock_kernel<512><<<s.ngop * nbands, BH * 32, smem, st>>>(g, b, s, BH, nbands, sync, progress, spin_ns);
+    else if (regs >= 72) deblock_kernel<768><<<s.ngop * nbands, BH * 32, smem, st>>>(g, b, s, BH, nbands, sync, progress, spin_ns);
+    else deblock_kernel<1024><<<s.ngop * nbands, BH * 32, smem, st>>>(g, b, s, BH, nbands, sync, progress, spin_ns);
 }
 
 void vcp_launch_pad(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
