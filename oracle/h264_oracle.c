@@ -565,8 +565,10 @@ static void me_refine_mb(Enc* e, const Frame* ref, int mx, int my, int qp, int16
     uint32_t bcost = best >> 4;
     e->mbs[i].type = VCP_MB_P16;
     if (bcost < VCP_SUBPEL_SKIP_COST) { mv[0] = (int16_t)bx; mv[1] = (int16_t)by; return; }
-    /* half-pel then quarter-pel: 8 neighbours each, raster order, strict improvement */
-    for (int step = 2; step >= 1; step--) {
+    /* half-pel then quarter-pel: 8 neighbours each, raster order, strict improvement.  -preset fast tiers (effort 0) stop
+     * at half samples (vcpenc_params.effort: 0 fast, 1 medium, 2 slow; the built-in presets are medium / slow) */
+    const int last_step = e->p.effort == 0 ? 2 : 1;
+    for (int step = 2; step >= last_step; step--) {
         uint32_t sb = (bcost << 4) | 0; /* centre keeps priority (index 0) */
         int k = 1, cx = bx, cy = by;
         for (int dy = -1; dy <= 1; dy++)

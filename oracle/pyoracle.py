@@ -41,6 +41,7 @@ def make_params(width, height, fps=30, gop=60, qp_i=24, qp_p=26, slices=1, deblo
     p.qp_i, p.qp_p = qp_i, qp_p
     p.slices = slices
     p.deblock_idc = deblock_idc
+    p.effort = 1            # vcpenc_default_params: medium (0 = the fast tiers: no quarter-sample step)
     for k, v in kw.items():
         setattr(p, k, v)
     return p

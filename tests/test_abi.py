@@ -59,6 +59,8 @@ def test_parse_reference_presets(built):
     assert p.bitrate == 15_000_000 and p.maxrate == 20_000_000 and p.bufsize == 30_000_000 and p.effort == 2
     p = api.parse_args(PRESETS["h265-cpu"].split())
     assert p.codec == 1
+    # -preset tiers: custom presets (config.yaml:14-23) may name the fast ones
+    assert [api.parse_args(("-c:v libx264 -preset %s" % t).split()).effort for t in ("veryfast", "p2", "medium", "p5", "slow", "p7")] == [0, 0, 1, 1, 2, 2]
     with pytest.raises(api.VcpencError) as e:
         api.parse_args(PRESETS["copy"].split())
     assert e.value.code == 8  # NOTENCODE: the Go side hands the task to a stock ffmpeg

@@ -576,3 +576,20 @@ def test_transcode_drop_in(built, tmp_path):
     with pytest.raises(api.VcpencError) as e:
         api.transcode(str(y4m), str(out3), "-c:v libx264 -crf 23", cancel=flag)
     assert e.value.code == 6 and not out3.exists()
+
+
+def test_effort_tier_fast_equals_oracle(built):
+    """`-preset` fast tiers (effort 0): the refine stops at half samples; kernels and oracle agree byte for byte"""
+    from oracle import pyoracle
+    w, h, n = 320, 192, 7
+    clip = synth.make_hard_clip(w, h, n, seed=5, noise=1)
+    for entropy in (0, 1):
+        ref = pyoracle.encode(pyoracle.make_params(w, h, gop=7, qp_i=24, qp_p=26, slices=2, effort=0, entropy=entropy), clip, want_dump=True)
+        p = api.default_params(w, h, gop=7, qp_i=24, qp_p=26, slices=2, effort=0, entropy=entropy, debug=1)
+        with api.Session(p, n) as s:
+            s.upload(clip)
+            s.encode()
+            got = s.download(want_recon=True)
+            dbg = s.debug_mbs()
+        assert np.array_equal(dbg["mv_final"], ref["dump"]["mv_final"]) and not (dbg["mv_final"] & 1).any()
+        assert got["stream"].tobytes() == ref["stream"] and np.array_equal(got["recon"], ref["recon"])

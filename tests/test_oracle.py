@@ -478,3 +478,23 @@ def test_hevc_tables_match_decoder_rodata():
         # last_sig_coeff prefix (18), coded_sub_block (4), sig_coeff (42), greater1 (24), greater2 (6) are contiguous runs
         for a, b in ((18, 36), (54, 58), (58, 100), (100, 124), (124, 130)):
             assert data.find(bytes(row[a:b])) >= 0, (a, b)
+
+
+def test_oracle_effort_tiers():
+    """`-preset` tiers (vcpenc_params.effort): the fast tiers stop the motion refine at half samples.  On a clip that
+    pans by quarter samples the medium tier needs clearly fewer bits; both streams decode to their reconstruction."""
+    w, h, n = 176, 144, 6
+    clip = synth.make_hard_clip(w, h, n, seed=5, noise=0)          # (1.25, 0.75) samples per frame
+    sizes = {}
+    for effort in (0, 1, 2):
+        r = pyoracle.encode(pyoracle.make_params(w, h, gop=6, qp_i=24, qp_p=26, effort=effort), clip, want_dump=True)
+        sizes[effort] = len(r["stream"])
+        mv = r["dump"]["mv_final"][1:]
+        if effort == 0:
+            assert not (mv & 1).any(), "fast tier: vectors stay on half-sample positions"
+        else:
+            assert (mv & 1).any()
+        if arbiter.available():
+            dec = arbiter.decode_annexb(r["stream"])
+            assert all(np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i]) for i in range(n))
+    assert sizes[1] == sizes[2] and sizes[1] < 0.97 * sizes[0], sizes   # IDR included: the P pictures alone differ more

@@ -136,6 +136,7 @@ int check_params(const vcpenc_params& p, char* err, size_t errlen) {
     if (p.hevc_intra_modes) { set_err(err, errlen, "HEVC intra modes beyond DC are implemented in the oracle only (device path: next round)"); return VCPENC_E_UNSUPPORTED; }
     if (p.hevc_sao < 0 || p.hevc_sao > 1) { set_err(err, errlen, "bad hevc_sao %d", p.hevc_sao); return VCPENC_E_ARGS; }
     if (p.entropy < 0 || p.entropy > 1) { set_err(err, errlen, "bad entropy coder %d", p.entropy); return VCPENC_E_ARGS; }
+    if (p.effort < 0 || p.effort > 2) { set_err(err, errlen, "bad effort tier %d", p.effort); return VCPENC_E_ARGS; }
     if (p.width < 16 || p.height < 16 || (p.width & 1) || (p.height & 1)) { set_err(err, errlen, "unsupported picture size %dx%d", p.width, p.height); return VCPENC_E_ARGS; }
     if (p.gop < 1 || p.slices < 0 || p.slices > (p.height + 15) / 16) { set_err(err, errlen, "bad gop/slices"); return VCPENC_E_ARGS; }
     if (p.qp_i < 0 || p.qp_i > 51 || p.qp_p < 0 || p.qp_p > 51) { set_err(err, errlen, "qp out of range"); return VCPENC_E_ARGS; }
@@ -351,6 +352,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     g.hevc = pp->codec == VCPENC_CODEC_HEVC;
     g.hevc_subpel = g.hevc && pp->hevc_subpel;
     g.hevc_sao = g.hevc && pp->hevc_sao;
+    g.effort = pp->effort;
     g.rc_abr = pp->rc_mode == VCPENC_RC_ABR;
     g.rc_bitrate = pp->bitrate; g.fps_num = pp->fps_num; g.fps_den = pp->fps_den;
     g.rc_qp0 = g.rc_abr ? vcp_rc_initial_qp(pp->bitrate, pp->fps_num, pp->fps_den, pp->width, pp->height) : 0;

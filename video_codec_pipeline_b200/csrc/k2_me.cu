@@ -412,8 +412,9 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
             ox = __shfl_sync(0xffffffffu, bk ? cq : 0, bk);
             oy = __shfl_sync(0xffffffffu, bk ? cr : 0, bk);
         }
-        // ---- quarter-sample step (H.264 only: HEVC quarter positions are not averages of half-sample planes) ----
-        if (!g.hevc) {
+        // ---- quarter-sample step (H.264 only: HEVC quarter positions are not averages of half-sample planes; not in
+        //      the fast -preset tiers) ----
+        if (!g.hevc && g.effort > 0) {
             // lane k (1..8): candidate k -> byte offsets of its two grid samples, and its vector cost
             // Every lane's first sample has the same misalignment (rows are 24 B, halves 8 B apart), so lane k can
             // turn its candidate's two byte offsets into (word offset, funnel shift) pairs once, packed as

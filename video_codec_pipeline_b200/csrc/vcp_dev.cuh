@@ -30,6 +30,7 @@ struct VcpGeom {
     int hevc;          // codec: 0 H.264, 1 HEVC (k6_hevc.cu; the motion search and the arithmetic coder are shared)
     int hevc_subpel;   // HEVC: half-sample luma motion from the 8-tap planes of k2_hpel.cu
     int hevc_sao;      // HEVC: sample adaptive offset (luma edge offsets)
+    int effort;        // -preset tier: 0 fast (motion refine stops at half samples), 1 medium, 2 slow (= medium so far)
     // rate control (VCPENC_RC_ABR): see vcp_algo.h
     int rc_abr, rc_qp0, rc_bitrate, fps_num, fps_den;
 };
