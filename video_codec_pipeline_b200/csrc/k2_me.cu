@@ -415,35 +415,47 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
         // ---- quarter-sample step (H.264 only: HEVC quarter positions are not averages of half-sample planes; not in
         //      the fast -preset tiers) ----
         if (!g.hevc && g.effort > 0) {
-            // lane k (1..8): candidate k -> byte offsets of its two grid samples, and its vector cost
-            // Every lane's first sample has the same misalignment (rows are 24 B, halves 8 B apart), so lane k can
-            // turn its candidate's two byte offsets into (word offset, funnel shift) pairs once, packed as
-            // word * 32 + shift; the SAD loop then only broadcasts them.
-            int pk1 = 0, pk2 = 0, cq = 0, cr = 0;
+            // The eight quarter positions around the best half position c are averages of samples of the 3 x 3 half-sample
+            // neighbourhood H[i][j] of c (i, j in -1..1): horizontal / vertical neighbours average H[0][0] with H[0][dx] /
+            // H[dy][0]; the diagonal ones average H[0][dx] with H[dy][0] when c's two half coordinates have the same parity
+            // (c is an integer or a j sample) and H[0][0] with H[dy][dx] otherwise (8.4.2.2.1: the pair "x odd, y even" +
+            // "x even, y odd").  Nine fetches instead of sixteen; lane m < 9 works out where H[m/3-1][m%3-1] lives (every
+            // lane's first sample has the same misalignment: rows are 24 B, halves 8 B apart) and broadcasts it packed as
+            // word * 32 + shift.
+            const int hx0 = ox >> 1, hy0 = oy >> 1;                      // c in half-sample units: -1, 0, 1
             const int lbr = lb & 3;
             const uint32_t* Wl = Ww + (lb >> 2);
+            int pk = 0;
             {
-                const int k = (lane - 1) & 7, q = k + (k > 3);
-                cq = ox + (q % 3 - 1); cr = oy + (q / 3 - 1);
-                const HpelPoints h = hpel_points(cq, cr);
-                const int a1 = lbr + (hpel_plane(h.x1, h.y1) * VCP_RF_WIN_H + (h.y1 >> 1)) * (4 * RF_ROWW) + (h.x1 >> 1);
-                const int a2 = lbr + (hpel_plane(h.x2, h.y2) * VCP_RF_WIN_H + (h.y2 >> 1)) * (4 * RF_ROWW) + (h.x2 >> 1);
-                pk1 = (a1 >> 2) * 32 + (a1 & 3) * 8;
-                pk2 = (a2 >> 2) * 32 + (a2 & 3) * 8;
+                const int m = lane < 9 ? lane : 0;
+                const int X = hx0 + m % 3 - 1, Y = hy0 + m / 3 - 1;
+                const int a = lbr + (hpel_plane(X, Y) * VCP_RF_WIN_H + (Y >> 1)) * (4 * RF_ROWW) + (X >> 1);
+                pk = (a >> 2) * 32 + (a & 3) * 8;
             }
+            uint2 H[9];
+#pragma unroll
+            for (int m = 0; m < 9; m++) {
+                const int p = __shfl_sync(0xffffffffu, pk, m);
+                const uint32_t* r = Wl + (p >> 5);
+                const uint32_t shb = (uint32_t)p & 31u;
+                const uint32_t w0 = r[0], w1 = r[1], w2 = r[2];
+                H[m] = make_uint2(__funnelshift_r(w0, w1, shb), __funnelshift_r(w1, w2, shb));
+            }
+            int cq, cr;
+            { const int k = (lane - 1) & 7, q = k + (k > 3); cq = ox + (q % 3 - 1); cr = oy + (q / 3 - 1); }
             mycost = lam * (vcp_se_len(4 * bvx + cq - pmx) + vcp_se_len(4 * bvy + cr - pmy));
             if (lane == 0) mycost = (int)bcost;
-            auto fetch8 = [&](int pk) {
-                const uint32_t* r = Wl + (pk >> 5);
-                const uint32_t shb = (uint32_t)pk & 31u;
-                const uint32_t w0 = r[0], w1 = r[1], w2 = r[2];
-                return make_uint2(__funnelshift_r(w0, w1, shb), __funnelshift_r(w1, w2, shb));
-            };
+            const bool same_par = ((hx0 ^ hy0) & 1) == 0;
 #pragma unroll
             for (int k = 1; k <= 8; k++) {
-                const uint2 p1 = fetch8(__shfl_sync(0xffffffffu, pk1, k));
-                const uint2 p2 = fetch8(__shfl_sync(0xffffffffu, pk2, k));
-                // quarter positions average two grid samples (a half position would average a sample with itself)
+                const int q = (k - 1) + (k - 1 > 3), dx = q % 3 - 1, dy = q / 3 - 1;   // compile-time
+                uint2 p1, p2;
+                if (dy == 0) { p1 = H[4]; p2 = H[4 + dx]; }
+                else if (dx == 0) { p1 = H[4]; p2 = H[4 + 3 * dy]; }
+                else {
+                    p1 = same_par ? H[4 + dx] : H[4];
+                    p2 = same_par ? H[4 + 3 * dy] : H[4 + 3 * dy + dx];
+                }
                 const int sad = warp_sum((int)sad4(vcp_avg4(p1.y, p2.y), c8.y, sad4(vcp_avg4(p1.x, p2.x), c8.x, 0)));
                 if (lane == k) mycost += sad;
             }
