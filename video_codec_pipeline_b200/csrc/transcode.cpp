@@ -418,10 +418,11 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
 
     const size_t sfb = src->fbytes();
     const size_t fb = std::max(fbytes(p.width, p.height), sfb);
-    // chunk: whole GOPs, at most ~6 GiB of raw frames per pass and buffer (34 closed GOPs of 1080p: what fills the
-    // GOP-group chains of one GPU; measured with 3 GiB chunks: 17 GOPs per encode, 0.30 s of GPU time per 1 920 frames)
+    // chunk: whole GOPs, at most ~3 GiB of raw frames per pass and buffer (17 closed GOPs of 1080p).  Measured on a 1 920
+    // picture y4m with two worker threads (profiles/r02_notes.md): 1.5 GiB 6 584 fps, 2 GiB 7 606, 3 GiB 7 691, 6 GiB 6 346 --
+    // larger chunks fill the GOP-group chains better but leave the reader nothing to overlap with.
     const int ndev = task_gpus();
-    size_t chunk_bytes = ((size_t)6 << 30) * (size_t)ndev;
+    size_t chunk_bytes = ((size_t)3 << 30) * (size_t)ndev;
     if (const char* e = getenv("VCPENC_CHUNK_BYTES")) { const long long v = atoll(e); if (v > 0) chunk_bytes = (size_t)v; }   // tests: force many chunks
     int chunk = (int)std::max<size_t>(1, chunk_bytes / fb);
     // short clips: do not page-lock more host memory than the input can fill.  The picture count is exact for raw /
