@@ -1533,15 +1533,20 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
     int ri = 0, idr_count = p->first_gop;
     /* rate control state of the current GOP (vcp_algo.h) */
     const int abr = p->rc_mode == VCPENC_RC_ABR;
-    const int rc_qp0 = abr ? vcp_rc_initial_qp(p->bitrate, p->fps_num, p->fps_den, p->width, p->height) : 0;
+    const int vbv = vcp_rc_has_vbv(p->maxrate, p->bufsize, p->fps_num, p->fps_den);
+    const int rc_fb = abr || vbv;   /* per-picture QP feedback on */
+    const int rc_qp0 = abr ? vcp_rc_initial_qp(vcp_rc_eff_bitrate(p->bitrate, p->maxrate), p->fps_num, p->fps_den, p->width, p->height) : 0;
     unsigned long long rc_cum = 0;
+    long long rc_full = 0;
     int rc_qp_next[2] = {0, 0}; /* QP decided for pictures t+1, t+2 */
     for (int n = 0; n < nframes; n++) {
         int t = n % p->gop, idr = t == 0;
         int qp = idr ? p->qp_i : p->qp_p;
-        if (abr) {
-            if (idr) { rc_cum = 0; rc_qp_next[0] = rc_qp_next[1] = rc_qp0; qp = rc_qp0 - VCP_RC_QP_I_OFFSET; if (qp < 0) qp = 0; }
-            else { qp = rc_qp_next[0]; rc_qp_next[0] = rc_qp_next[1]; }
+        if (rc_fb) {
+            if (idr) {
+                rc_qp_next[0] = rc_qp_next[1] = abr ? rc_qp0 : p->qp_p;
+                if (abr) { qp = rc_qp0 - VCP_RC_QP_I_OFFSET; if (qp < 0) qp = 0; }
+            } else { qp = rc_qp_next[0]; rc_qp_next[0] = rc_qp_next[1]; }
         }
         /* K1 */
         { Frame tf = e->prev_orig; e->prev_orig = e->cur; e->cur = tf; Half th = e->hprev; e->hprev = e->hcur; e->hcur = th; }
@@ -1610,14 +1615,14 @@ int orc_encode(const vcpenc_params* p, const uint8_t* frames, int nframes, uint8
              * count scaled by VCP_CABAC_BITS_PER_BIN_Q4/16 instead of the final bits */
             frame_bits += p->entropy ? (nb * VCP_CABAC_BITS_PER_BIN_Q4) >> 4 : (unsigned long long)b.pos * 8;
         }
-        if (abr) {
+        if (rc_fb) {
             /* feedback lands two pictures later (entropy coding runs beside the recon chain) */
             int gop_len = p->gop;
             int g0 = n - t;
             if (g0 + gop_len > nframes) gop_len = nframes - g0;
-            unsigned long long budget = (unsigned long long)p->bitrate * (unsigned)p->fps_den / (unsigned)p->fps_num * (unsigned)gop_len;
-            rc_cum += frame_bits;
-            rc_qp_next[1] = vcp_rc_next_qp(rc_qp0, qp, rc_qp_next[0], idr, frame_bits, rc_cum, t, gop_len, budget);
+            rc_qp_next[1] = vcp_rc_picture(abr, rc_qp0, p->qp_p, abr ? vcp_rc_gop_budget(p->bitrate, p->maxrate, p->fps_num, p->fps_den, gop_len) : 0,
+                                           vbv ? vcp_vbv_rate(p->maxrate, p->fps_num, p->fps_den) : 0, vbv ? p->bufsize : 0,
+                                           qp, rc_qp_next[0], idr, frame_bits, t, gop_len, &rc_cum, &rc_full);
         }
         if (idr) idr_count++;
         if (info) { info[n].offset = au0; info[n].size = (uint32_t)(o - au0); info[n].is_idr = (uint8_t)idr; info[n].qp = (uint8_t)qp; }

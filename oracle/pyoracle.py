@@ -49,7 +49,8 @@ def make_params(width, height, fps=30, gop=60, qp_i=24, qp_p=26, slices=1, deblo
 
 def build(force=False):
     if force or not os.path.exists(LIB_PATH) or \
-            os.path.getmtime(LIB_PATH) < max(os.path.getmtime(os.path.join(HERE, f)) for f in ("h264_oracle.c", "hevc_oracle.inc.c")):
+            os.path.getmtime(LIB_PATH) < max(os.path.getmtime(os.path.join(HERE, f)) for f in
+                                             ("h264_oracle.c", "hevc_oracle.inc.c", "../video_codec_pipeline_b200/csrc/vcp_algo.h")):
         subprocess.check_call(["make", "-C", HERE, "-s"] + (["-B"] if force else []))
     return LIB_PATH
 

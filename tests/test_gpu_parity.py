@@ -158,6 +158,25 @@ def test_bitrate_mode_equals_oracle(built):
         assert np.array_equal(got["recon"], ref["recon"])
 
 
+def test_vbv_equals_oracle(built):
+    """-maxrate / -bufsize: the per-GOP buffer model runs in rc_update_kernel (vcp_algo.h: vcp_rc_picture, shared with the
+    oracle); per-picture QPs, bytes and reconstruction must agree in constant-QP mode (CAVLC, High CABAC, HEVC) and
+    together with -b:v, and the cap must actually move the QPs."""
+    w, h, n, fps, gop = 320, 192, 60, 24, 24
+    clip = synth.make_hard_clip(w, h, n, seed=5)
+    from oracle import pyoracle
+    for kw in (dict(entropy=0), dict(entropy=1, transform8x8=1, slices=2), dict(entropy=0, rc_mode=1, bitrate=900_000)):
+        got = _same_as_oracle(w, h, clip, fps=fps, gop=gop, qp_i=21, qp_p=24, maxrate=300_000, bufsize=300_000, **kw)
+        qps = [x[3] for x in got["info"]]
+        assert len(set(qps[1:gop])) > 2, (kw, qps)
+    kw = dict(codec=1, entropy=1, slices=2, fps=fps, gop=gop, qp_i=24, qp_p=27, maxrate=300_000, bufsize=300_000)
+    ref = pyoracle.encode_hevc(pyoracle.make_params(w, h, **kw), clip)
+    got = api.encode_frames(api.default_params(w, h, **kw), clip, want_recon=True)
+    assert [x[3] for x in got["info"]] == [x[3] for x in ref["info"]]
+    assert got["stream"].tobytes() == ref["stream"] and np.array_equal(got["recon"], ref["recon"])
+    assert len({x[3] for x in ref["info"][1:gop]}) > 2
+
+
 @pytest.mark.parametrize("fmt", [1, 2, 3, 4, 5])
 def test_k1_input_formats_equal_oracle(built, fmt):
     """K1 front stages (nv12 / rgb24 / yuv444p / yuv422p / bgr24, with and without scaling)."""

@@ -253,6 +253,59 @@ def test_oracle_bitrate_mode():
     assert 0.6 * 1_600_000 < sizes[1_600_000] < 1.5 * 1_600_000
 
 
+def _vbv_min_fullness(bits, rate, buf, start):
+    """Decoder buffer over the whole stream: +rate per picture interval, capped at buf, minus the picture."""
+    f, lo = start, float("inf")
+    for b in bits:
+        f = min(buf, f + rate) - b
+        lo = min(lo, f)
+    return lo
+
+
+def test_oracle_vbv_maxrate_bufsize():
+    """-maxrate / -bufsize (the h264-nvenc-hq preset, /root/reference/internal/config/config.go:46): every GOP steers its own
+    buffer model (vcp_algo.h: vcp_rc_vbv_qp); the concatenated stream must not underflow a buffer that starts at
+    FFmpeg's 0.9 B, where the same clip at the plain constant QP does."""
+    w, h, n, fps, gop = 320, 192, 72, 24, 24
+    clip = synth.make_hard_clip(w, h, n, seed=5)
+    for ent in (0, 1):
+        kw = dict(fps=fps, gop=gop, qp_i=21, qp_p=24, entropy=ent)
+        free = pyoracle.encode(pyoracle.make_params(w, h, **kw), clip)
+        bits0 = [x[1] * 8 for x in free["info"]]
+        natural = sum(bits0) / n * fps
+        maxrate = int(0.7 * natural)
+        bufsize = maxrate                                          # one second
+        r = pyoracle.encode(pyoracle.make_params(w, h, maxrate=maxrate, bufsize=bufsize, **kw), clip)
+        bits = [x[1] * 8 for x in r["info"]]
+        qps = [x[3] for x in r["info"]]
+        assert _vbv_min_fullness(bits0, maxrate / fps, bufsize, 0.9 * bufsize) < 0      # the cap binds on this clip
+        assert _vbv_min_fullness(bits, maxrate / fps, bufsize, 0.9 * bufsize) >= 0
+        assert sum(bits) / n * fps < 1.15 * maxrate
+        assert qps[0] == 21 and qps[1] == 24 and max(qps) > 24 and min(q for i, q in enumerate(qps) if i % gop) >= 24
+        assert qps[gop] == 21 and qps[gop + 1] == 24               # every GOP starts from the nominal QPs
+        if arbiter.available():
+            dec = arbiter.decode_annexb(r["stream"])
+            for i in range(n):
+                assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i])
+        # a VBV needs both numbers (like libx264): -maxrate alone changes nothing in constant-QP mode
+        alone = pyoracle.encode(pyoracle.make_params(w, h, maxrate=maxrate, **kw), clip[:gop])
+        assert alone["stream"] == pyoracle.encode(pyoracle.make_params(w, h, **kw), clip[:gop])["stream"]
+    # -b:v above -maxrate: the GOP budget follows -maxrate
+    kw = dict(fps=fps, gop=gop, rc_mode=1, bitrate=900_000)
+    capped = pyoracle.encode(pyoracle.make_params(w, h, maxrate=300_000, bufsize=600_000, **kw), clip)
+    plain = pyoracle.encode(pyoracle.make_params(w, h, **kw), clip)
+    rate = len(capped["stream"]) * 8 / (n / fps)
+    assert rate < 1.3 * 300_000 < len(plain["stream"]) * 8 / (n / fps)
+    # the h264-nvenc-hq numbers scaled to this picture size: -b:v 15M -maxrate 20M -bufsize 30M at 1080p30 never binds
+    scale = (w * h) / (1920 * 1080)
+    hq = dict(fps=30, gop=gop, rc_mode=1, bitrate=int(15e6 * scale))
+    a = pyoracle.encode(pyoracle.make_params(w, h, maxrate=int(20e6 * scale), bufsize=int(30e6 * scale), **hq), clip)
+    b = pyoracle.encode(pyoracle.make_params(w, h, **hq), clip)
+    assert a["stream"] == b["stream"]
+    bits = [x[1] * 8 for x in a["info"]]
+    assert _vbv_min_fullness(bits, 20e6 * scale / 30, 30e6 * scale, 0.9 * 30e6 * scale) > 0
+
+
 # ---- K1: other input formats and scaling (vcp_algo.h: vcp_rgb_*, vcp_scale_pos, vcp_bilerp) ----
 def _k1_inputs(clip, w, h):
     """The same yuv420p content re-expressed in formats whose conversion back is lossless."""

@@ -144,6 +144,7 @@ int check_params(const vcpenc_params& p, char* err, size_t errlen) {
     if (p.in_width < 0 || p.in_height < 0 || (p.in_width > 0) != (p.in_height > 0)) { set_err(err, errlen, "bad input size %dx%d", p.in_width, p.in_height); return VCPENC_E_ARGS; }
     if (p.deblock_idc < 0 || p.deblock_idc > 2) { set_err(err, errlen, "bad deblock_idc"); return VCPENC_E_ARGS; }
     if (p.rc_mode == VCPENC_RC_ABR && (p.bitrate <= 0 || p.fps_num <= 0 || p.fps_den <= 0)) { set_err(err, errlen, "bitrate mode needs -b:v and a frame rate"); return VCPENC_E_ARGS; }
+    if (p.maxrate < 0 || p.bufsize < 0) { set_err(err, errlen, "bad -maxrate / -bufsize"); return VCPENC_E_ARGS; }
     return VCPENC_OK;
 }
 
@@ -355,7 +356,14 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     g.effort = pp->effort;
     g.rc_abr = pp->rc_mode == VCPENC_RC_ABR;
     g.rc_bitrate = pp->bitrate; g.fps_num = pp->fps_num; g.fps_den = pp->fps_den;
-    g.rc_qp0 = g.rc_abr ? vcp_rc_initial_qp(pp->bitrate, pp->fps_num, pp->fps_den, pp->width, pp->height) : 0;
+    g.rc_qp0 = g.rc_abr ? vcp_rc_initial_qp(vcp_rc_eff_bitrate(pp->bitrate, pp->maxrate), pp->fps_num, pp->fps_den, pp->width, pp->height) : 0;
+    {
+        const bool vbv = vcp_rc_has_vbv(pp->maxrate, pp->bufsize, pp->fps_num, pp->fps_den) != 0;
+        g.rc_fb = g.rc_abr || vbv;
+        g.rc_maxrate = pp->maxrate; g.rc_qp_nom = pp->qp_p;
+        g.rc_vbv_rate = vbv ? vcp_vbv_rate(pp->maxrate, pp->fps_num, pp->fps_den) : 0;
+        g.rc_vbv_buf = vbv ? pp->bufsize : 0;
+    }
     s->ngop_max = (max_frames + pp->gop - 1) / pp->gop;
     s->ring = pp->debug ? std::min(pp->gop, max_frames) : std::min(2, std::min(pp->gop, max_frames));
     if (s->ring < 1) s->ring = 1;
@@ -388,7 +396,9 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
         // H.264 hides two latency-bound wavefronts (deblocking, IDR intra) behind other groups' work: 4 groups.
         // The HEVC chain has no wavefront after the IDR picture, so fewer, larger launches win (measured 14.6k /
         // 13.8k / 12.0k fps with 2 / 4 / 8 groups).
-        int ng = e ? atoi(e) : (pp->codec == VCPENC_CODEC_HEVC ? 2 : 4);
+        // H.264 with CABAC: the coder batches already fill the gaps; measured 1080p High 11.9k / 11.9k / 11.5k fps with
+        // 2 / 3 / 4 groups (e2e 9.9k / 9.6k / 9.2k), 4K High 3.18k / 3.20k with 2 / 4.
+        int ng = e ? atoi(e) : (pp->codec == VCPENC_CODEC_HEVC || pp->entropy ? 2 : 4);
         s->ngroups = std::max(1, std::min(ng, (int)vcpenc_session::kMaxGroups));
         const char* e2 = getenv("VCPENC_BINS_PER_MB");
         if (e2 && atoi(e2) > 0) s->bins_per_mb = std::min(atoi(e2), 65536);
@@ -446,6 +456,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     TRY(dev_alloc(s, &b.frame_bits, N, err, errlen));
     TRY(dev_alloc(s, &b.error_flag, (size_t)1, err, errlen));
     TRY(dev_alloc(s, &b.rc_cum, G, err, errlen));
+    TRY(dev_alloc(s, &b.rc_full, G, err, errlen));
     TRY(dev_alloc(s, &b.db_sync, G * (g.mbh + 1) + 1, err, errlen));
     TRY(dev_alloc(s, &b.icount, G * g.slices, err, errlen));
     CKS(cudaMemset(b.icount, 0, G * g.slices * sizeof(int)));
@@ -714,8 +725,8 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 CK(cudaStreamWaitEvent(se, s->ev_rec[k][par], 0));
             }
             if (g.cabac) {
-                { Prof pr(s, VCPENC_K_CABAC_BINS, g.rc_abr ? 3 : 2, se); if (g.hevc) vcp_launch_hevc_bins(g, bt, sp, se); else vcp_launch_cabac_bins(g, bt, sp, se); }
-                if (g.rc_abr) { Prof pr(s, VCPENC_K_RC, 1, se); vcp_launch_rc_update(g, bt, sp, se); }
+                { Prof pr(s, VCPENC_K_CABAC_BINS, g.rc_fb ? 3 : 2, se); if (g.hevc) vcp_launch_hevc_bins(g, bt, sp, se); else vcp_launch_cabac_bins(g, bt, sp, se); }
+                if (g.rc_fb) { Prof pr(s, VCPENC_K_RC, 1, se); vcp_launch_rc_update(g, bt, sp, se); }
                 // The arithmetic coder takes the bins in batches on its own streams: one lane per slice, long-running but
                 // only a few warps wide.  The IDR pictures are a batch of their own on a stream of their own: their
                 // slices carry ten times the bins of a P slice, and a later batch queued behind them on the same stream
@@ -740,7 +751,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
                 { Prof pr(s, VCPENC_K_CAVLC_SCAN, 1, se); vcp_launch_cavlc_scan(g, bt, sp, se); }
                 { Prof pr(s, VCPENC_K_CAVLC_WRITE, 2, se); vcp_launch_cavlc_write(g, bt, sp, se); vcp_launch_nal_pack(g, bt, sp, se); }
                 }
-                if (g.rc_abr) { Prof pr(s, VCPENC_K_RC, 1, se); vcp_launch_rc_update(g, bt, sp, se); }
+                if (g.rc_fb) { Prof pr(s, VCPENC_K_RC, 1, se); vcp_launch_rc_update(g, bt, sp, se); }
             }
             if (!s->profile) CK(cudaEventRecord(s->ev_ent[k][par], se));
             if (g.hevc_sao) { Prof pr(s, VCPENC_K_DEBLOCK, 1, st); vcp_launch_hevc_sao_copy(g, bt, sp, st); }   // after the fork: only the picture changes
@@ -822,7 +833,7 @@ int vcpenc_session_download(vcpenc_session* s, uint8_t* out, size_t out_cap, siz
     CK(cudaMemcpyAsync(s->h_out, s->b.out, (size_t)used, cudaMemcpyDeviceToHost, s->st));
     CK(cudaMemcpyAsync(idx.data(), s->b.out_index, idx.size() * sizeof(uint2), cudaMemcpyDeviceToHost, s->st));
     CK(cudaMemcpyAsync(idx_hi.data(), s->b.out_index_hi, idx_hi.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->st));
-    if (s->g.rc_abr) CK(cudaMemcpyAsync(s->h_qp.data(), s->b.qp, (size_t)N, cudaMemcpyDeviceToHost, s->st));
+    if (s->g.rc_fb) CK(cudaMemcpyAsync(s->h_qp.data(), s->b.qp, (size_t)N, cudaMemcpyDeviceToHost, s->st));
     CK(cudaStreamSynchronize(s->st));
     static const uint8_t sc[4] = {0, 0, 0, 1};
     size_t o = 0;

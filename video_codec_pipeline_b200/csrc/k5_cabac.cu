@@ -856,14 +856,14 @@ void vcp_launch_cabac_bins(const VcpGeom& g, const VcpBufs& b, const VcpStep& s,
     cabac_bins_kernel<<<grid, CB_WARPS * 32, 0, st>>>(g, b, s);
     static const int dbg_skip = [] { const char* e = getenv("VCPENC_DEBUG_SKIP_CODER"); return e ? atoi(e) : 0; }();   // timing experiments only
     if (dbg_skip < 2) cabac_gather_kernel<<<s.ngop * g.slices, GA_THREADS, 0, st>>>(g, b, s);
-    if (g.rc_abr) cabac_rc_bits_kernel<<<(s.ngop + 63) / 64, 64, 0, st>>>(g, b, s);
+    if (g.rc_fb) cabac_rc_bits_kernel<<<(s.ngop + 63) / 64, 64, 0, st>>>(g, b, s);
 }
 
 void vcp_launch_hevc_bins(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
     dim3 grid((g.nmb + CB_WARPS - 1) / CB_WARPS, s.ngop);
     hevc_bins_kernel<<<grid, CB_WARPS * 32, 0, st>>>(g, b, s);
     cabac_gather_kernel<<<s.ngop * g.slices, GA_THREADS, 0, st>>>(g, b, s);
-    if (g.rc_abr) cabac_rc_bits_kernel<<<(s.ngop + 63) / 64, 64, 0, st>>>(g, b, s);
+    if (g.rc_fb) cabac_rc_bits_kernel<<<(s.ngop + 63) / 64, 64, 0, st>>>(g, b, s);
 }
 
 void vcp_launch_cabac_encode(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, int t0, int t1, cudaStream_t st) {

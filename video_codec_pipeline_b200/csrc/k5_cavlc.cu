@@ -333,19 +333,22 @@ __global__ void rc_update_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
     const int n = vcp_frame_of(s, gi);
     int gop_len = s.gop;
     if (gi * s.gop + gop_len > s.nframes) gop_len = s.nframes - gi * s.gop;
-    const unsigned long long cum = (s.t == 0 ? 0ull : b.rc_cum[gi]) + b.frame_bits[n];
+    // the QP of picture t+2 (vcp_algo.h); the state is advanced for every picture
+    unsigned long long cum = b.rc_cum[gi];
+    long long full = b.rc_full[gi];
+    const int q = vcp_rc_picture(g.rc_abr, g.rc_qp0, g.rc_qp_nom,
+                                 g.rc_abr ? vcp_rc_gop_budget(g.rc_bitrate, g.rc_maxrate, g.fps_num, g.fps_den, gop_len) : 0ull,
+                                 g.rc_vbv_rate, g.rc_vbv_buf, b.qp[n], s.t + 1 < gop_len ? b.qp[n + 1] : b.qp[n], s.t == 0,
+                                 b.frame_bits[n], s.t, gop_len, &cum, &full);
     b.rc_cum[gi] = cum;
-    if (s.t + 2 < gop_len) {
-        const unsigned long long budget =
-            (unsigned long long)g.rc_bitrate * (unsigned)g.fps_den / (unsigned)g.fps_num * (unsigned)gop_len;
-        b.qp[n + 2] = (uint8_t)vcp_rc_next_qp(g.rc_qp0, b.qp[n], b.qp[n + 1], s.t == 0, b.frame_bits[n], cum, s.t, gop_len, budget);
-    }
+    b.rc_full[gi] = full;
+    if (s.t + 2 < gop_len) b.qp[n + 2] = (uint8_t)q;
 }
 
 }  // namespace
 
 void vcp_launch_rc_update(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cudaStream_t st) {
-    if (!g.rc_abr) return;
+    if (!g.rc_fb) return;
     rc_update_kernel<<<(s.ngop + 63) / 64, 64, 0, st>>>(g, b, s);
 }
 

@@ -367,11 +367,10 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
     int rc = vcpenc_parse_args(argc, argv, &p, err, errlen);
     if (rc) return rc;
     if (vcpenc_device_count() <= 0) { set_err(err, errlen, "no CUDA device available (libvcpenc has no CPU fallback)"); return VCPENC_E_NODEVICE; }
-    if ((p.maxrate > 0 || p.bufsize > 0) && !getenv("VCPENC_QUIET")) {
-        // a warning, as ffmpeg prints at -loglevel warning: the h264-nvenc-hq preset's cap (internal/config/config.go:46) is parsed, not modelled
+    if ((p.maxrate > 0) != (p.bufsize > 0) && !getenv("VCPENC_QUIET")) {
+        // like libx264: a VBV needs both numbers; -maxrate alone still caps the GOP budget of -b:v
         static std::atomic<bool> once{false};
-        if (!once.exchange(true))
-            fprintf(stderr, "[vcpenc] warning: -maxrate / -bufsize are not enforced (no VBV model yet); -b:v is met per GOP (budget = bitrate x GOP duration)\n");
+        if (!once.exchange(true)) fprintf(stderr, "[vcpenc] warning: VBV needs both -maxrate and -bufsize; the buffer model is off\n");
     }
 
     const std::string in = input, outp = output;
@@ -414,7 +413,7 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
     if (p.slices == 0) p.slices = vcp_auto_slices((p.height + 15) / 16, p.entropy);
     if (p.slices > (p.height + 15) / 16) p.slices = (p.height + 15) / 16;
     vcpenc_params pkey = p;            // session key: what the kernels see (not the muxer's / front end's settings)
-    pkey.faststart = 0; pkey.audio_bitrate = 0; pkey.drop_audio = 0; pkey.maxrate = 0; pkey.bufsize = 0;
+    pkey.faststart = 0; pkey.audio_bitrate = 0; pkey.drop_audio = 0;
 
     const size_t sfb = src->fbytes();
     const size_t fb = std::max(fbytes(p.width, p.height), sfb);

@@ -211,4 +211,76 @@ VCP_HD int vcp_rc_next_qp(int qp0, int qp_t, int qp_t1, int idr_t, unsigned long
     return q < 10 ? 10 : (q > 51 ? 51 : q);
 }
 
+// ---- VBV (-maxrate R -bufsize B), integer only ----------------------------------------------------
+// Decoder buffer model: fullness F gains R/fps bits per picture interval, is capped at B, and loses the bits of a
+// picture when it is decoded.  GOPs are encoded in parallel, so each GOP runs its own model from an ASSUMED start level
+// of B/2 and is steered to end at least that full; F is monotone in its start value, so a stream whose first GOP really
+// starts at B/2 or above (FFmpeg's default initial occupancy is 0.9 B) keeps every GOP at or above its model.
+// Steering, two pictures ahead like the bitrate control: the QP chosen for picture t+2 is raised (by at most VCP_VBV_STEP
+// over picture t+1) until the predicted fullness after picture t+2 stays above a floor that rises from B/10 at the GOP
+// start to B/2 at its end.  The prediction prices pictures t+1 and t+2 from the bits of picture t with bits ~ 2^(-QP/6).
+// An IDR picture that alone exceeds B/2 underflows the model (there is no second pass to re-encode it).
+#define VCP_VBV_START_DIV 2
+#define VCP_VBV_FLOOR_DIV 10
+#define VCP_VBV_STEP 6
+// bits * 2^(-dq/6): the same picture coded dq QP steps higher (lower when dq < 0)
+VCP_HD unsigned long long vcp_rc_scale_bits(unsigned long long bits, int dq) {
+    const unsigned f[6] = {65536, 58386, 52016, 46341, 41285, 36781};   // 65536 * 2^(-k/6)
+    int sh = 0;
+    if (dq < -48) dq = -48;
+    if (dq > 48) dq = 48;
+    while (dq < 0) { dq += 6; sh--; }
+    while (dq >= 6) { dq -= 6; sh++; }
+    if (bits > (1ull << 40)) bits = 1ull << 40;
+    const unsigned long long v = (bits * f[dq]) >> 16;
+    return sh >= 0 ? v >> sh : v << -sh;
+}
+VCP_HD long long vcp_vbv_advance(long long fullness, long long rate, long long buf, unsigned long long bits) {
+    fullness += rate;
+    if (fullness > buf) fullness = buf;
+    return fullness - (long long)bits;
+}
+VCP_HD long long vcp_vbv_rate(int maxrate, int fps_num, int fps_den) {
+    return (long long)((unsigned long long)maxrate * (unsigned)fps_den / (unsigned)(fps_num > 0 ? fps_num : 1));
+}
+// fullness: the model after picture t has been removed
+VCP_HD int vcp_rc_vbv_qp(int q, int qp_t, int qp_t1, int idr_t, unsigned long long bits_t, long long fullness,
+                         long long rate, long long buf, int t, int L) {
+    const unsigned long long bits_eq = idr_t ? bits_t / VCP_RC_I_WEIGHT : bits_t;
+    const int base = idr_t ? qp_t + VCP_RC_QP_I_OFFSET : qp_t;
+    const long long f1 = vcp_vbv_advance(fullness, rate, buf, vcp_rc_scale_bits(bits_eq, qp_t1 - base));
+    const long long lo = buf / VCP_VBV_FLOOR_DIV, hi = buf / VCP_VBV_START_DIV;
+    const long long need = lo + (hi - lo) * (t + 3) / (L > 0 ? L : 1);
+    const int qmax = qp_t1 + VCP_VBV_STEP > 51 ? 51 : qp_t1 + VCP_VBV_STEP;
+    while (q < qmax && vcp_vbv_advance(f1, rate, buf, vcp_rc_scale_bits(bits_eq, q - base)) < need) q++;
+    return q;
+}
+// the rate -b:v control aims for: -b:v, capped by -maxrate
+VCP_HD int vcp_rc_eff_bitrate(int bitrate, int maxrate) { return maxrate > 0 && maxrate < bitrate ? maxrate : bitrate; }
+// budget of a GOP of L pictures
+VCP_HD unsigned long long vcp_rc_gop_budget(int bitrate, int maxrate, int fps_num, int fps_den, int L) {
+    const int r = vcp_rc_eff_bitrate(bitrate, maxrate);
+    return (unsigned long long)r * (unsigned)fps_den / (unsigned)(fps_num > 0 ? fps_num : 1) * (unsigned)L;
+}
+// One call per coded picture t of a GOP of L pictures, when its bits are known: returns the QP of picture t+2 and
+// advances the GOP's state (*cum: bits spent, *fullness: VBV model).  abr: -b:v control (vcp_rc_next_qp) from qp0;
+// otherwise constant QP qp_nom for P pictures, to which the QP returns VCP_RC_STEP per picture after a VBV excursion.
+// vbv_buf = 0: no VBV.
+VCP_HD int vcp_rc_picture(int abr, int qp0, int qp_nom, unsigned long long gop_budget, long long vbv_rate, long long vbv_buf,
+                          int qp_t, int qp_t1, int idr_t, unsigned long long bits_t, int t, int L,
+                          unsigned long long* cum, long long* fullness) {
+    if (t == 0) { *cum = 0; *fullness = vbv_buf / VCP_VBV_START_DIV; }
+    *cum += bits_t;
+    int q;
+    if (abr) q = vcp_rc_next_qp(qp0, qp_t, qp_t1, idr_t, bits_t, *cum, t, L, gop_budget);
+    else q = qp_t1 - VCP_RC_STEP > qp_nom ? qp_t1 - VCP_RC_STEP : qp_nom;
+    if (vbv_buf > 0) {
+        *fullness = vcp_vbv_advance(*fullness, vbv_rate, vbv_buf, bits_t);
+        q = vcp_rc_vbv_qp(q, qp_t, qp_t1, idr_t, bits_t, *fullness, vbv_rate, vbv_buf, t, L);
+    }
+    return q;
+}
+// does this parameter set run the per-picture feedback?  (VBV needs both -maxrate and -bufsize, like libx264)
+VCP_HD int vcp_rc_has_vbv(int maxrate, int bufsize, int fps_num, int fps_den) { return maxrate > 0 && bufsize > 0 && fps_num > 0 && fps_den > 0; }
+
 #endif  // VCP_ALGO_H

@@ -31,8 +31,11 @@ struct VcpGeom {
     int hevc_subpel;   // HEVC: half-sample luma motion from the 8-tap planes of k2_hpel.cu
     int hevc_sao;      // HEVC: sample adaptive offset (luma edge offsets)
     int effort;        // -preset tier: 0 fast (motion refine stops at half samples), 1 medium, 2 slow (= medium so far)
-    // rate control (VCPENC_RC_ABR): see vcp_algo.h
+    // rate control (VCPENC_RC_ABR and / or the VBV model of -maxrate / -bufsize): see vcp_algo.h
     int rc_abr, rc_qp0, rc_bitrate, fps_num, fps_den;
+    int rc_fb;                         // per-picture QP feedback on: rc_abr or VBV
+    int rc_maxrate, rc_qp_nom;         // -maxrate; the P-picture QP of constant-QP mode
+    long long rc_vbv_rate, rc_vbv_buf; // bits per picture interval, buffer size (0: no VBV)
 };
 
 __host__ __device__ __forceinline__ int vcp_slice_first_row(int s, int slices, int mbh) {
@@ -91,6 +94,7 @@ struct VcpBufs {
     uint32_t* frame_bits;  // [nframes] coded bits per frame (for rate control)
     int* error_flag;
     unsigned long long* rc_cum;  // [ngop_max] bits spent so far in the GOP
+    long long* rc_full;          // [ngop_max] VBV model of the GOP
     int* db_sync;          // deblocking: [0] row ticket, [1 + gop*mbh + row] progress
     // CABAC (k5_cabac.cu): bins of every resident picture, per-macroblock descriptors, slice RBSPs
     uint16_t* bins;                  // arena, bump-allocated per macroblock
