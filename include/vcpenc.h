@@ -70,7 +70,9 @@ typedef struct vcpenc_params {
     int32_t rc_mode;           /* VCPENC_RC_*                                       */
     int32_t qp_i, qp_p;        /* CQP values / ABR starting point                   */
     int32_t bitrate;           /* bits per second for ABR (-b:v)                    */
-    int32_t maxrate, bufsize;  /* -maxrate / -bufsize (bits, bits)                  */
+    int32_t maxrate, bufsize;  /* -maxrate / -bufsize (bits/s, bits): both > 0 switch
+                                  the per-GOP VBV model on (vcp_algo.h); -maxrate
+                                  alone only caps the -b:v target                   */
     int32_t slices;            /* slices per picture (-slices)                      */
     int32_t deblock_idc;       /* disable_deblocking_filter_idc: 0 on, 1 off, 2 on
                                   but not across slice edges                        */
