@@ -58,10 +58,11 @@ class Workload:
     """One encoder configuration + clip.  `entropy`/`slices`/... follow vcpenc_params."""
 
     def __init__(self, name, w=1920, h=1080, fps=30, entropy=0, slices=-1, t8x8=0, codec=0, content="std", gops=32,
-                 seed=1080, qp_i=QP_I, qp_p=QP_P, hevc_sao=0, label=None):
+                 seed=1080, qp_i=QP_I, qp_p=QP_P, hevc_sao=0, hevc_subpel=2, label=None):
         self.name, self.w, self.h, self.fps = name, w, h, fps
         self.codec, self.content, self.gops, self.seed = codec, content, gops, seed
         self.qp_i, self.qp_p, self.hevc_sao = qp_i, qp_p, hevc_sao
+        self.hevc_subpel = hevc_subpel if codec else 0
         if codec:
             entropy, t8x8 = 1, 0
         self.entropy, self.t8x8 = entropy, t8x8
@@ -71,8 +72,8 @@ class Workload:
         res = "4K" if w >= 3840 else "%dp" % h
         if codec:
             self.metric = "%s HEVC encode fps (GOP=60, Main profile, I+P)" % res
-            tools = "HEVC Main, GOP=60, CABAC, %d slice%s, I+P, half-sample motion, deblock%s" % (
-                self.slices, "" if self.slices == 1 else "s", ", SAO" if hevc_sao else "")
+            tools = "HEVC Main, GOP=60, CABAC, %d slice%s, I+P, %s-sample motion, deblock%s" % (
+                self.slices, "" if self.slices == 1 else "s", ("full", "half", "quarter")[self.hevc_subpel], ", SAO" if hevc_sao else "")
         else:
             coder = "CABAC" if entropy else "CAVLC"
             self.metric = "%s H.264 encode fps (GOP=60, %s%s, I+P)" % (res, "High profile, " if t8x8 else "", coder)
@@ -84,12 +85,12 @@ class Workload:
     def params(self, api, first_gop=0, **kw):
         return api.default_params(self.w, self.h, fps=self.fps, gop=GOP, qp_i=self.qp_i, qp_p=self.qp_p, slices=self.slices,
                                   first_gop=first_gop, entropy=self.entropy, transform8x8=self.t8x8, codec=self.codec,
-                                  hevc_subpel=1 if self.codec else 0, hevc_sao=self.hevc_sao if self.codec else 0, **kw)
+                                  hevc_subpel=self.hevc_subpel, hevc_sao=self.hevc_sao if self.codec else 0, **kw)
 
     def oracle_params(self, pyoracle, first_gop=0):
         return pyoracle.make_params(self.w, self.h, fps=self.fps, gop=GOP, qp_i=self.qp_i, qp_p=self.qp_p, entropy=self.entropy,
                                     slices=self.slices, transform8x8=self.t8x8, codec=self.codec, first_gop=first_gop,
-                                    hevc_subpel=1 if self.codec else 0, hevc_sao=self.hevc_sao if self.codec else 0)
+                                    hevc_subpel=self.hevc_subpel, hevc_sao=self.hevc_sao if self.codec else 0)
 
     def make_frames(self, gops=None):
         """`gops` closed GOPs.  Two distinct GOPs are synthesised (numpy is slow at these sizes) and cycled;
@@ -117,8 +118,8 @@ def headline_workload(args):
     if args.codec == "hevc":
         if args.workload == "4k":
             return Workload("hevc4k", 3840, 2160, 60, codec=1, gops=args.gops or 16, seed=2160, slices=args.slices, hevc_sao=args.hevc_sao,
-                            label="configs[3] (one GPU's GOP shard)")
-        return Workload("hevc1080", codec=1, gops=args.gops or 32, slices=args.slices, hevc_sao=args.hevc_sao, label="configs[3] at 1080p")
+                            hevc_subpel=args.hevc_subpel, label="configs[3] (one GPU's GOP shard)")
+        return Workload("hevc1080", codec=1, gops=args.gops or 32, slices=args.slices, hevc_sao=args.hevc_sao, hevc_subpel=args.hevc_subpel, label="configs[3] at 1080p")
     if args.workload == "4k":
         ent = 1 if args.entropy < 0 else args.entropy
         return Workload("4k", 3840, 2160, 60, entropy=ent, t8x8=1 if ent else 0, gops=args.gops or 16, seed=2160, slices=args.slices,
@@ -642,6 +643,7 @@ def main():
     ap.add_argument("--workload", default="1080p", choices=["1080p", "4k"], help="default: BASELINE.json configs[1]")
     ap.add_argument("--codec", default="h264", choices=["h264", "hevc"], help="hevc: BASELINE.json configs[3] (use with --workload 4k)")
     ap.add_argument("--content", default="std", choices=["std", "hard"], help="hard: fractional full-frame pan + noise")
+    ap.add_argument("--hevc-subpel", type=int, default=2, help="HEVC motion precision: 0 full, 1 half, 2 quarter samples (what the h265 presets parse to)")
     ap.add_argument("--hevc-sao", action="store_true", help="HEVC: sample adaptive offset on (default off: its first kernel is slow)")
     ap.add_argument("--entropy", type=int, default=-1, help="0 CAVLC, 1 CABAC (default: what the workload names)")
     ap.add_argument("--t8x8", type=int, default=0, help="1: High profile 8x8 transform (1080p workload)")
@@ -759,7 +761,7 @@ def main():
                                                              label="h264-cpu as parsed on hard content"), "prev"),
             ("configs[2] 4K60 High CABAC shard", Workload("4k", 3840, 2160, 60, entropy=1, t8x8=1, gops=16, seed=2160,
                                                           label="configs[2] (one GPU's GOP shard, High profile)"), None),
-            ("configs[3] 4K60 HEVC shard (h265-cpu as parsed)", Workload("hevc4k", 3840, 2160, 60, codec=1, gops=16, seed=2160, qp_i=ph.qp_i, qp_p=ph.qp_p,
+            ("configs[3] 4K60 HEVC shard (h265-cpu as parsed)", Workload("hevc4k", 3840, 2160, 60, codec=1, gops=16, seed=2160, qp_i=ph.qp_i, qp_p=ph.qp_p, hevc_subpel=ph.hevc_subpel,
                                                                          label="configs[3] (one GPU's GOP shard), h265-cpu (config.go:50) as parsed"), "prev"),
         ]
         prev = None

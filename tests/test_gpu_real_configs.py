@@ -99,7 +99,7 @@ def test_hevc_1080p_gop60(built):
     """the h265-* presets' path at 1080p, GOP 60, two GOPs"""
     w, h, gop = 1920, 1080, 60
     clip = np.concatenate([synth.make_clip(w, h, gop, seed=1080, start=0), synth.make_clip(w, h, gop, seed=1081, start=gop)])
-    _check(w, h, clip, gop, dict(codec=1, qp_i=26, qp_p=29, slices=4, hevc_subpel=1))
+    _check(w, h, clip, gop, dict(codec=1, qp_i=26, qp_p=29, slices=4, hevc_subpel=2))
 
 
 @pytest.mark.timeout(900)

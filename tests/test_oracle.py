@@ -444,8 +444,9 @@ def test_hevc_oracle_half_sample_motion():
 
 
 def test_hevc_oracle_quarter_sample_motion():
-    """params.hevc_subpel = 2 (oracle only): the 7/8-tap quarter-sample filters.  Decoder-exact, and each precision
-    step pays off on a clip that moves by quarter samples."""
+    """params.hevc_subpel = 2 / 3: the 7/8-tap quarter-sample filters (candidates ranked by the half-sample proxy / by the
+    exact prediction).  Decoder-exact, each precision step pays off on a clip that moves by quarter samples, and the
+    proxy ranking finds what the exact ranking finds."""
     if not arbiter.available():
         pytest.skip("bundled FFmpeg decoder not present")
     w, h, n = 320, 192, 5
@@ -457,7 +458,7 @@ def test_hevc_oracle_quarter_sample_motion():
     clip = np.stack([np.concatenate([np.clip(np.rint(big[i:i + 4 * h:4, 3 * i:3 * i + 4 * w:4]), 0, 255).astype(np.uint8).ravel(),
                                      np.full(w * h // 2, 128, np.uint8)]) for i in range(n)])
     size = {}
-    for sub in (0, 1, 2):
+    for sub in (0, 1, 2, 3):
         r = pyoracle.encode_hevc(pyoracle.make_params(w, h, codec=1, gop=n, qp_i=26, qp_p=28, hevc_subpel=sub, slices=2), clip)
         dec = arbiter.decode_annexb_hevc(r["stream"])
         assert len(dec) == n
@@ -465,6 +466,7 @@ def test_hevc_oracle_quarter_sample_motion():
             assert np.array_equal(np.concatenate([pl.ravel() for pl in dec[i]]), r["recon"][i]), (sub, i)
         size[sub] = len(r["stream"])
     assert size[2] < size[1] < size[0]
+    assert abs(size[2] - size[3]) < 0.01 * size[3]
 
 
 def test_hevc_oracle_sample_adaptive_offset():

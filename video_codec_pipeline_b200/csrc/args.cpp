@@ -57,7 +57,7 @@ extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_param
     p->transform8x8 = -1;   // likewise: High profile tools unless -profile:v baseline / main
     bool have_codec = false, have_crf = false, have_qp = false;
     int crf = 23;
-    int sao = -1, subpel = 1;   // HEVC tools from -x265-params
+    int sao = -1, subpel = -1;   // HEVC tools from -x265-params (-1: not given)
     for (int i = 0; i < argc; i++) {
         const std::string t = argv[i];
         auto need = [&](const char** v) -> bool {
@@ -109,7 +109,10 @@ extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_param
             const std::string xs = std::string(":") + v + ":";
             if (xs.find(":sao=1:") != std::string::npos || xs.find(":sao:") != std::string::npos) sao = 1;
             if (xs.find(":sao=0:") != std::string::npos || xs.find(":no-sao:") != std::string::npos || xs.find(":no-sao=1:") != std::string::npos) sao = 0;
-            if (xs.find(":subme=0:") != std::string::npos) subpel = 0;
+            {   // subme=N: 0 full samples only, 1 half samples, 2..4 quarter samples (candidates ranked by the half-sample proxy), 5.. ranked exactly
+                const size_t at = xs.find(":subme=");
+                if (at != std::string::npos) { const int lv = atoi(xs.c_str() + at + 7); subpel = lv <= 0 ? 0 : lv == 1 ? 1 : lv < 5 ? 2 : 3; }
+            }
         } else if (t == "-an") {
             p->drop_audio = 1;
         } else if (t == "-sn" || t == "-dn" || t == "-y" || t == "-hide_banner" || t == "-nostdin") {
@@ -193,9 +196,10 @@ extern "C" int vcpenc_parse_args(int argc, const char* const* argv, vcpenc_param
     if (p->entropy < 0) p->entropy = 1;   // x264 and NVENC both default to CABAC
     if (p->transform8x8 < 0) p->transform8x8 = 1;   // ... and to High profile
     if (p->codec == VCPENC_CODEC_HEVC) {
-        // libx265 / hevc_nvenc search sub-sample positions: half samples here.  SAO is implemented and bit-exact but
-        // its first kernel costs ~45 us per 1080p picture (profiles/r01_notes.md), so it is opt-in: -x265-params sao=1
-        p->hevc_subpel = subpel;
+        // libx265 / hevc_nvenc search sub-sample positions: quarter samples here too, half samples in the fast -preset
+        // tiers (like the H.264 refine).  SAO is implemented and bit-exact but its first kernel costs ~45 us per 1080p
+        // picture (profiles/r01_notes.md), so it is opt-in: -x265-params sao=1
+        p->hevc_subpel = subpel >= 0 ? subpel : (p->effort == 0 ? 1 : 2);
         p->hevc_sao = sao > 0 ? 1 : 0;
     }
     if (have_crf && !have_qp) {

@@ -131,8 +131,7 @@ int dev_alloc(vcpenc_session* s, T** p, size_t count, char* err, size_t errlen) 
 
 int check_params(const vcpenc_params& p, char* err, size_t errlen) {
     if (p.codec != VCPENC_CODEC_H264 && p.codec != VCPENC_CODEC_HEVC) { set_err(err, errlen, "unknown codec %d", p.codec); return VCPENC_E_ARGS; }
-    if (p.hevc_subpel == 2) { set_err(err, errlen, "HEVC quarter-sample motion is implemented in the oracle only (device path: half samples)"); return VCPENC_E_UNSUPPORTED; }
-    if (p.hevc_subpel < 0 || p.hevc_subpel > 2) { set_err(err, errlen, "bad hevc_subpel %d", p.hevc_subpel); return VCPENC_E_ARGS; }
+    if (p.hevc_subpel < 0 || p.hevc_subpel > 3) { set_err(err, errlen, "bad hevc_subpel %d", p.hevc_subpel); return VCPENC_E_ARGS; }
     if (p.hevc_intra_modes) { set_err(err, errlen, "HEVC intra modes beyond DC are implemented in the oracle only (device path: next round)"); return VCPENC_E_UNSUPPORTED; }
     if (p.hevc_sao < 0 || p.hevc_sao > 1) { set_err(err, errlen, "bad hevc_sao %d", p.hevc_sao); return VCPENC_E_ARGS; }
     if (p.entropy < 0 || p.entropy > 1) { set_err(err, errlen, "bad entropy coder %d", p.entropy); return VCPENC_E_ARGS; }
@@ -351,7 +350,7 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
     g.hoff = VCP_PAD1 * g.hs + VCP_PAD1;
     g.slices = pp->slices; g.deblock_idc = pp->deblock_idc; g.cabac = pp->entropy; g.t8x8 = pp->transform8x8 ? 1 : 0;
     g.hevc = pp->codec == VCPENC_CODEC_HEVC;
-    g.hevc_subpel = g.hevc && pp->hevc_subpel;
+    g.hevc_subpel = g.hevc ? pp->hevc_subpel : 0;
     g.hevc_sao = g.hevc && pp->hevc_sao;
     g.effort = pp->effort;
     g.rc_abr = pp->rc_mode == VCPENC_RC_ABR;
@@ -492,10 +491,11 @@ int vcpenc_session_create(const vcpenc_params* pp, int device, int max_frames, v
         const uint64_t rd[4] = {(uint64_t)g.ys, yrows, VCP_REC_PLANES, G * s->ring}, rst[3] = {(uint64_t)g.ys, g.ysize, VCP_REC_PLANES * g.ysize};
         const uint32_t b_hwin[3] = {VCP_L1_WIN_W, VCP_L1_WIN_H, 1}, b_hcur[3] = {VCP_L1_CUR_W, 8, 1};
         const uint32_t b_yref[3] = {VCP_L0_REF_W, VCP_L0_REF_H, 1}, b_ycur[3] = {16, 16, 1};
-        const uint32_t b_rec4[4] = {VCP_RF_WIN_W, VCP_RF_WIN_H, 4, 1}, b_rec1[4] = {VCP_RF_WIN_W, VCP_RF_WIN_H, 1, 1};
+        const uint32_t b_rec4[4] = {VCP_RF_WIN_W, VCP_RF_WIN_H, 4, 1}, b_rec1[4] = {VCP_RF_WIN_W, VCP_RF_WIN_H, 1, 1}, b_rec1q[4] = {VCP_RFQ_WIN_W, VCP_RFQ_WIN_H, 1, 1};
         int bad = vcp_make_tmap(&s->tm.h_win, b.src_h, 3, hd, hst, b_hwin) | vcp_make_tmap(&s->tm.h_cur, b.src_h, 3, hd, hst, b_hcur) |
                   vcp_make_tmap(&s->tm.y_ref, b.src_y, 3, yd, yst, b_yref) | vcp_make_tmap(&s->tm.y_cur, b.src_y, 3, yd, yst, b_ycur) |
-                  vcp_make_tmap(&s->tm.rec4, b.rec_y, 4, rd, rst, b_rec4) | vcp_make_tmap(&s->tm.rec1, b.rec_y, 4, rd, rst, b_rec1);
+                  vcp_make_tmap(&s->tm.rec4, b.rec_y, 4, rd, rst, b_rec4) | vcp_make_tmap(&s->tm.rec1, b.rec_y, 4, rd, rst, b_rec1) |
+                  vcp_make_tmap(&s->tm.rec1q, b.rec_y, 4, rd, rst, b_rec1q);
         if (bad) { set_err(err, errlen, "cuTensorMapEncodeTiled failed (%d): the motion search needs TMA (sm_90+ driver)", bad); vcpenc_session_destroy(s); return VCPENC_E_CUDA; }
     }
     if (pp->debug) {

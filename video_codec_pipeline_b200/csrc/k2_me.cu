@@ -28,6 +28,7 @@
 #include "vcp_dev.cuh"
 #include "vcp_luma_interp.cuh"
 #include "vcp_tma.cuh"
+#include "vcp_hevc_qpel.cuh"
 
 namespace {
 
@@ -235,7 +236,10 @@ struct __align__(128) RefineWarp {
     uint32_t landp[256];
     uint32_t w[4][VCP_RF_WIN_H][RF_ROWW];
     uint64_t bar;
+    uint64_t barq;            // HEVC quarter-sample step: the 24 x 24 window of integer samples has landed in landz / landp
 };
+static_assert(VCP_RFQ_WIN_H * VCP_RFQ_WIN_W <= 2 * 256 * 4, "the quarter-sample window lands in landz + landp");
+static_assert(HQ_WROWS * HQ_WPITCH <= 4 * RF_LANDPLANE, "the row-pass output of the quarter-sample step reuses the landing planes");
 static_assert(RF_LANDPLANE <= 256, "landing buffers");
 
 // landing buffer -> working copy, planes [p0, p1), dropping the window's misalignment `mis` (0..15):
@@ -267,6 +271,9 @@ __device__ __forceinline__ int rf_sad_land(const uint32_t* L, int row, int hx, i
     return warp_sum((int)sad4(__funnelshift_r(a1, a2, sh), c8.y, sad4(__funnelshift_r(a0, a1, sh), c8.x, 0)));
 }
 
+// HQ: HEVC quarter-sample candidates ranked by their exact prediction (hevc_subpel = 3): a kernel of its own, so that the
+// H.264 / proxy-ranked build keeps its registers
+template <bool HQ>
 __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, VcpBufs b, VcpStep s, const __grid_constant__ VcpTmaps tm) {
     __shared__ RefineWarp sh[RF_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -274,7 +281,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
     const int gi = blockIdx.y + s.g0;
     if (mbi >= g.nmb) return;
     RefineWarp& S = sh[warp];
-    if (lane == 0) { mbar_init(&S.bar, 1); mbar_init_fence(); }
+    if (lane == 0) { mbar_init(&S.bar, 1); if (HQ) mbar_init(&S.barq, 1); mbar_init_fence(); }
     __syncwarp();
     const int n = vcp_frame_of(s, gi);
     const int mx = mbi % g.mbw, my = mbi / g.mbw;
@@ -357,6 +364,16 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
     }
 
     int ox = 0, oy = 0;
+    if (HQ) {
+        // the integer samples -4 .. 19 around the block at its best full-sample vector, for the quarter-sample step: the
+        // zero-vector / predictor landing buffers have been read (rf_sad_land above) and take the box
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            mbar_expect_tx(&S.barq, VCP_RFQ_WIN_H * VCP_RFQ_WIN_W);
+            tma_load_4d(&S.landz[0], &tm.rec1q, &S.barq, (x0 + bvx - 2) & ~15, y0 + bvy - 2, 0, slot);
+        }
+    }
     if (sub) {   // HEVC: full samples only, or (hevc_subpel) the half-sample step alone
         int bdx, bdy;   // best full-pel position relative to the vector the working copy is centred on
         if (kb >= 9) {
@@ -412,9 +429,12 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
             ox = __shfl_sync(0xffffffffu, bk ? cq : 0, bk);
             oy = __shfl_sync(0xffffffffu, bk ? cr : 0, bk);
         }
-        // ---- quarter-sample step (H.264 only: HEVC quarter positions are not averages of half-sample planes; not in
-        //      the fast -preset tiers) ----
-        if (!g.hevc && g.effort > 0) {
+        // ---- quarter-sample step (H.264: not in the fast -preset tiers.  HEVC with hevc_subpel = 2: its quarter positions
+        //      are NOT averages of half-sample planes, but the averages rank the eight candidates as well as the exact
+        //      7/8-tap predictions do (oracle: hevc_luma_proxy; measured on quarter-sample pans 53 591 vs 53 577 bytes), and
+        //      hevc_p_recon codes the exact prediction of whichever vector wins.  hevc_subpel = 3 ranks by the exact
+        //      prediction: me_refine_kernel<true>, below) ----
+        if (g.hevc ? g.hevc_subpel == 2 : g.effort > 0) {
             // The eight quarter positions around the best half position c are averages of samples of the 3 x 3 half-sample
             // neighbourhood H[i][j] of c (i, j in -1..1): horizontal / vertical neighbours average H[0][0] with H[0][dx] /
             // H[dy][0]; the diagonal ones average H[0][dx] with H[dy][0] when c's two half coordinates have the same parity
@@ -466,6 +486,41 @@ __global__ void __launch_bounds__(RF_WARPS * 32) me_refine_kernel(VcpGeom g, Vcp
             oy = __shfl_sync(0xffffffffu, bk ? cr : oy, bk);
         }
     }
+    if (HQ) {
+        // ---- HEVC quarter-sample step, exact (hevc_subpel = 3; oracle: hevc_refine_cu, step 1): the 8 neighbours of the best
+        //      half-sample position, each predicted exactly as the decoder will (vcp_hevc_qpel.cuh).  Candidates in one
+        //      column of the 3 x 3 ring share their row pass.
+        mbar_wait(&S.barq, 0);
+        __syncwarp();                                   // every lane is done with the half-sample planes: W takes their place
+        uint32_t* W = &S.land[0][0][0];
+        const uint32_t* win = &S.landz[0];
+        const int misq = (x0 + bvx - 2) & 15;
+        int cq, cr;
+        { const int k = (lane - 1) & 7, q = k + (k > 3); cq = ox + (q % 3 - 1); cr = oy + (q / 3 - 1); }
+        mycost = lam * (vcp_se_len(4 * bvx + cq - pmx) + vcp_se_len(4 * bvy + cr - pmy));
+        if (lane == 0) mycost = (int)bcost;
+#pragma unroll 1
+        for (int dxi = 0; dxi < 3; dxi++) {
+            const int qx = ox + dxi - 1;
+            hq_hpass(win, VCP_RFQ_WIN_W / 4, misq + (qx >> 2) + 1, qx & 3, W, lane);
+            __syncwarp();
+#pragma unroll 1
+            for (int dyi = 0; dyi < 3; dyi++) {
+                if (dxi == 1 && dyi == 1) continue;
+                const int qy = oy + dyi - 1;
+                const uint2 p8 = hq_vpass(W, row + (qy >> 2) + 1, lane & 1, qy & 3);
+                const int sad = warp_sum((int)sad4(p8.y, c8.y, sad4(p8.x, c8.x, 0)));
+                const int q = dyi * 3 + dxi, k = q < 4 ? q + 1 : q;
+                if (lane == k) mycost += sad;
+            }
+            __syncwarp();
+        }
+        best = warp_min(lane < 9 ? (((uint32_t)mycost << 4) | (uint32_t)lane) : 0xffffffffu);
+        bcost = best >> 4;
+        const int bk = (int)(best & 15);
+        ox = __shfl_sync(0xffffffffu, bk ? cq : ox, bk);
+        oy = __shfl_sync(0xffffffffu, bk ? cr : oy, bk);
+    }
     // intra or inter?  Intra16x16 estimated on the ORIGINAL picture (best of V / H / DC from original
     // neighbours): no reconstruction needed, so the decision stays macroblock-parallel (oracle:
     // intra_estimate, vcp_intra_wins).  Intra macroblocks are coded by i_fix_kernel after the inter ones.
@@ -512,5 +567,6 @@ void vcp_launch_me_prepass(const VcpGeom& g, const VcpBufs& b, const VcpTmaps& t
 
 void vcp_launch_me_refine(const VcpGeom& g, const VcpBufs& b, const VcpTmaps& tm, const VcpStep& s, cudaStream_t st) {
     dim3 grid((g.nmb + RF_WARPS - 1) / RF_WARPS, s.ngop);
-    me_refine_kernel<<<grid, RF_WARPS * 32, 0, st>>>(g, b, s, tm);
+    if (g.hevc && g.hevc_subpel >= 3) me_refine_kernel<true><<<grid, RF_WARPS * 32, 0, st>>>(g, b, s, tm);
+    else me_refine_kernel<false><<<grid, RF_WARPS * 32, 0, st>>>(g, b, s, tm);
 }

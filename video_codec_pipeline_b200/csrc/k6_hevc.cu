@@ -26,6 +26,7 @@
 // luma [z*64 + y*8 + x], Cb [256 + z*16 + y*4 + x], Cr [320 + z*16 + y*4 + x].
 #include "vcp_dev.cuh"
 #include "vcp_luma_interp.cuh"
+#include "vcp_hevc_qpel.cuh"
 
 #define VCP_TAB static __device__ const
 #include "hevc_tables.h"
@@ -40,6 +41,7 @@ struct __align__(16) HvScratch {
     int t[4][HV_T_STRIDE];
     int16_t lv[384];
 };
+static_assert(sizeof(int) * 4 * HV_T_STRIDE + sizeof(int16_t) * 384 >= sizeof(uint32_t) * HQ_WROWS * HQ_WPITCH, "the row-pass output aliases t + lv");
 
 __device__ __forceinline__ int hevc_chroma_qp(int qp) { return qp < 30 ? qp : qp > 43 ? qp - 6 : hevc_qpc_tab[qp - 30]; }
 
@@ -252,6 +254,7 @@ constexpr int HP_WARPS = 4;
 
 __global__ void __launch_bounds__(HP_WARPS * 32) hevc_p_recon_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
     __shared__ HvScratch scr[HP_WARPS];
+    __shared__ __align__(16) uint32_t qwin_all[HP_WARPS][HQ_WIN][8];   // quarter-sample vectors: the integer samples -3 .. 20 around the block (24 bytes per row used)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mbi = blockIdx.x * HP_WARPS + warp;
     const int gi = blockIdx.y + s.g0;
@@ -268,6 +271,21 @@ __global__ void __launch_bounds__(HP_WARPS * 32) hevc_p_recon_kernel(VcpGeom g, 
     {
         const int row = lane >> 1, hx = (lane & 1) * 8;
         const uint8_t* r0 = vcp_rec_luma(b, g, rslot) + g.yoff + (ptrdiff_t)(16 * my + row) * g.ys + 16 * mx + hx;
+        if ((mv.x | mv.y) & 1) {
+            // quarter-sample vector (hevc_subpel = 2): interpolate from the integer samples (vcp_hevc_qpel.cuh), window
+            // origin at the first tap of sample (0, 0)
+            if (lane < HQ_WIN) {
+                const uint8_t* wr = vcp_rec_luma(b, g, rslot) + g.yoff + (ptrdiff_t)(16 * my + (mv.y >> 2) - 3 + lane) * g.ys + 16 * mx + (mv.x >> 2) - 3;
+                const uint2 a = ld8_unaligned(wr), c = ld8_unaligned(wr + 8), e = ld8_unaligned(wr + 16);
+                *reinterpret_cast<uint4*>(&qwin_all[warp][lane][0]) = make_uint4(a.x, a.y, c.x, c.y);
+                *reinterpret_cast<uint4*>(&qwin_all[warp][lane][4]) = make_uint4(e.x, e.y, 0u, 0u);
+            }
+            __syncwarp();
+            uint32_t* W = reinterpret_cast<uint32_t*>(&S.t[0][0]);
+            hq_hpass(&qwin_all[warp][0][0], 8, 0, mv.x & 3, W, lane);
+            __syncwarp();
+            *reinterpret_cast<uint2*>(&S.pred[row][hx]) = hq_vpass(W, row, lane & 1, mv.y & 3);
+        } else
         // half-sample vectors (hevc_subpel) read the 8-tap planes of the reference; full-sample ones the picture itself
         *reinterpret_cast<uint2*>(&S.pred[row][hx]) = g.hevc_subpel ? hpel_fetch8(r0, mv.x, mv.y, g.ys, g.ysize)
                                                                     : ld8_unaligned(r0 + (ptrdiff_t)(mv.y >> 2) * g.ys + (mv.x >> 2));

@@ -24,6 +24,8 @@
 #define VCP_L0_REF_H 20       // 16 + 4 candidate rows
 #define VCP_RF_WIN_W 48       // refine: x = -2 .. 17 around the vector + up to 15 bytes of misalignment
 #define VCP_RF_WIN_H 20       // y = -2 .. 17
+#define VCP_RFQ_WIN_W 48      // HEVC quarter-sample step: x = -4 .. 19 around the best full-sample vector + misalignment
+#define VCP_RFQ_WIN_H 24      // y = -4 .. 19
 
 struct VcpTmaps {
     CUtensorMap h_win;    // src_h  (x, row, frame)          box {VCP_L1_WIN_W, VCP_L1_WIN_H, 1}
@@ -32,6 +34,7 @@ struct VcpTmaps {
     CUtensorMap y_cur;    // src_y                            box {16, 16, 1}
     CUtensorMap rec4;     // rec_y  (x, row, plane, slot)    box {VCP_RF_WIN_W, VCP_RF_WIN_H, 4, 1}
     CUtensorMap rec1;     // rec_y                            box {VCP_RF_WIN_W, VCP_RF_WIN_H, 1, 1}
+    CUtensorMap rec1q;    // rec_y                            box {VCP_RFQ_WIN_W, VCP_RFQ_WIN_H, 1, 1}
 };
 
 // host: encode a tiled u8 map (rank 3 or 4), no swizzle, no interleave; returns 0 on success
