@@ -193,6 +193,12 @@ int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes,
  * memory, vcpenc_host_alloc, for a truly asynchronous copy) must stay valid until that encode returns. */
 int vcpenc_session_upload_async(vcpenc_session* s, const uint8_t* frames, int nframes, char* err,
                                 size_t errlen);
+/* vcpenc_session_upload_async for a buffer that is STILL BEING FILLED (a reader thread delivering a file): the copy of a
+ * group of GOPs is queued as soon as *ready (pictures complete in `frames`, written by the producer with release
+ * semantics) covers it, so the host-to-device transfer hides inside the read.  Returns when every copy is queued, or
+ * VCPENC_E_CANCELLED when *finished becomes non-zero before `nframes` pictures exist (upload again with what there is). */
+int vcpenc_session_upload_gated(vcpenc_session* s, const uint8_t* frames, int nframes, const volatile long* ready,
+                                const volatile int* finished, char* err, size_t errlen);
 /* same, but the raw frames are already in device memory (`dframes` is a device pointer):
  * runs K1 only.  `ms` (optional) receives the CUDA-event time on the launching stream. */
 int vcpenc_session_upload_device(vcpenc_session* s, const uint8_t* dframes, int nframes, float* ms,

@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -546,7 +548,10 @@ static void group_gops(const vcpenc_session* s, int N, int ng, int k, int* gA, i
     *gA = (int)((long long)ngop_total * k / ng); *gB = (int)((long long)ngop_total * (k + 1) / ng);
 }
 
-static int upload_host(vcpenc_session* s, const uint8_t* frames, int nframes, bool wait, char* err, size_t errlen) {
+// ready / finished (both or neither): the caller is still filling `frames`; piece k is queued once *ready pictures exist,
+// and the call gives up with VCPENC_E_CANCELLED when *finished is set before that (the producer stopped short)
+static int upload_host(vcpenc_session* s, const uint8_t* frames, int nframes, bool wait, char* err, size_t errlen,
+                       const volatile long* ready = nullptr, const volatile int* finished = nullptr) {
     if (!s || !frames || nframes < 1 || nframes > s->max_frames) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
     CK(cudaSetDevice(s->device));
     const size_t fb = s->in_fb;
@@ -565,6 +570,17 @@ static int upload_host(vcpenc_session* s, const uint8_t* frames, int nframes, bo
         group_gops(s, nframes, ng, k, &gA, &gB);
         const int n0 = gA * s->p.gop, n1 = std::min(nframes, gB * s->p.gop);
         if (n1 <= n0) { CK(cudaEventRecord(s->ev_piece[k], s->st_up)); continue; }
+        if (ready) {
+            while (*ready < n1) {
+                if (finished && *finished && *ready < n1) {
+                    s->nframes = 0;     // nothing usable was declared: the caller uploads again
+                    set_err(err, errlen, "input ended after %ld of %d pictures", (long)*ready, nframes);
+                    return VCPENC_E_CANCELLED;
+                }
+                std::this_thread::sleep_for(std::chrono::microseconds(50));
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
         CK(cudaMemcpyAsync(s->raw_dev + (size_t)n0 * fb, frames + (size_t)n0 * fb, (size_t)(n1 - n0) * fb, cudaMemcpyHostToDevice, s->st_copy));
         CK(cudaEventRecord(s->staging_ready[k & 1], s->st_copy));
         CK(cudaStreamWaitEvent(s->st_up, s->staging_ready[k & 1], 0));
@@ -589,6 +605,13 @@ int vcpenc_session_upload(vcpenc_session* s, const uint8_t* frames, int nframes,
 // host memory for a truly asynchronous copy) must stay valid until that encode returns.
 int vcpenc_session_upload_async(vcpenc_session* s, const uint8_t* frames, int nframes, char* err, size_t errlen) {
     return upload_host(s, frames, nframes, false, err, errlen);
+}
+
+// vcpenc_session_upload_async for a buffer that is still being filled: see include/vcpenc.h
+int vcpenc_session_upload_gated(vcpenc_session* s, const uint8_t* frames, int nframes, const volatile long* ready,
+                                const volatile int* finished, char* err, size_t errlen) {
+    if (!ready || !finished) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
+    return upload_host(s, frames, nframes, false, err, errlen, ready, finished);
 }
 
 int vcpenc_session_upload_device(vcpenc_session* s, const uint8_t* dframes, int nframes, float* ms, char* err, size_t errlen) {

@@ -26,6 +26,7 @@ struct FrameSource {
     AudioTrack audio;
     std::mutex audio_mu;   // guards audio.data / audio.sizes (the reader thread appends, the muxing thread drains)
     long est_frames = 0;
+    long exact_frames = 0;   // raw / y4m files: the number of pictures, known up front (0: unknown) -- lets the caller upload while it reads
     // end of input reached: flush the audio encoder (call once, after the last read())
     virtual int finish_audio(char*, size_t) { return 0; }
 };

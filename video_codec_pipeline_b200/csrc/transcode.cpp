@@ -118,7 +118,10 @@ struct Y4mSource : FrameSource {
         if (width <= 0 || height <= 0) { set_err(err, errlen, "bad y4m header"); return VCPENC_E_FORMAT; }
         data0 = (uint64_t)ftello(f);
         struct stat sb;
-        if (stat(path, &sb) == 0 && sb.st_size > 0) est_frames = (long)((size_t)sb.st_size / (fbytes() + 6)) + 1;
+        if (stat(path, &sb) == 0 && sb.st_size > 0) {
+            est_frames = (long)((size_t)sb.st_size / (fbytes() + 6)) + 1;
+            if (S_ISREG(sb.st_mode) && (uint64_t)sb.st_size > data0) exact_frames = (long)(((uint64_t)sb.st_size - data0) / (fbytes() + 6));   // bare FRAME markers assumed; a short chunk falls back
+        }
         return VCPENC_OK;
     }
     int read(uint8_t* dst, int max, char* err, size_t errlen) override {
@@ -155,7 +158,10 @@ struct RawSource : FrameSource {
         f = fopen(path, "rb");
         if (!f) { set_err(err, errlen, "cannot open %s", path); return VCPENC_E_IO; }
         struct stat sb;
-        if (stat(path, &sb) == 0 && sb.st_size > 0) est_frames = (long)((size_t)sb.st_size / fbytes()) + 1;
+        if (stat(path, &sb) == 0 && sb.st_size > 0) {
+            est_frames = (long)((size_t)sb.st_size / fbytes()) + 1;
+            if (S_ISREG(sb.st_mode)) exact_frames = (long)((size_t)sb.st_size / fbytes());
+        }
         return VCPENC_OK;
     }
     int read(uint8_t* dst, int max, char*, size_t) override {
@@ -463,6 +469,9 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
     std::condition_variable cv;
     int filled[2] = {-1, -1};          // frames in buffer i; -1: free for the reader
     bool last[2] = {false, false};     // buffer i holds the end of the input
+    // upload-while-reading (inputs whose picture count is known): pictures of buffer i read so far / the reader is done with it
+    volatile long progress[2] = {0, 0};
+    volatile int finished[2] = {0, 0};
     int read_rc = 0; char read_err[256] = {0};
     std::atomic<int> stop{0};          // VCPENC_E_CANCELLED / VCPENC_E_TIMEOUT once a stop condition is seen
     bool quit = false;
@@ -487,8 +496,12 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
                 const int k = src->read(fbuf[i] + (size_t)n * sfb, want, read_err, sizeof read_err);
                 if (k < 0) { rcr = -k; break; }
                 n += k;
+                std::atomic_thread_fence(std::memory_order_release);
+                progress[i] = n;
                 if (k < want) eof = true;
             }
+            std::atomic_thread_fence(std::memory_order_release);
+            finished[i] = 1;
             if (eof && !rcr) { const int ra = src->finish_audio(read_err, sizeof read_err); if (ra) rcr = ra; }
             std::lock_guard<std::mutex> lk(mu);
             filled[i] = n; last[i] = eof || rcr || stop.load(); read_rc = rcr;
@@ -522,9 +535,44 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
 
     long total = 0;
     int gop_index = 0;
+    // shards of a chunk of n pictures: closed GOPs, contiguous ranges per device; sessions on first use
+    auto prepare = [&](int n) -> int {
+        const int ngops = (n + p.gop - 1) / p.gop;
+        const int used = std::min(ndev, ngops);
+        for (int d = 0; d < ndev; d++) {
+            Shard& sh = shards[d];
+            const int ga = d < used ? (int)((long long)ngops * d / used) : 0, gb = d < used ? (int)((long long)ngops * (d + 1) / used) : 0;
+            sh.f0 = ga * p.gop; sh.n = std::min(n, gb * p.gop) - sh.f0; sh.g0 = gop_index + ga; sh.rc = 0; sh.len = 0;
+            if (sh.n <= 0) { sh.n = 0; continue; }
+            if (!sh.ses) {
+                pkey.first_gop = 0;
+                const int want = std::min((chunk / p.gop + used - 1) / used * p.gop, std::max(sh.n, 1));
+                const int rcs = acquire_session(pkey, sh.device, std::max(want, sh.n), &sh.ses, err, errlen);
+                if (rcs) return rcs;
+            }
+            sh.need_bits((size_t)sh.n * fb / 4 + (1 << 20));
+            if (sh.info.size() < (size_t)sh.n) sh.info.resize((size_t)sh.n);
+        }
+        return 0;
+    };
     for (int bi = 0;; bi = (bi + 1) % nbuf) {
-        int n;
-        bool is_last;
+        int n = 0;
+        bool is_last = false;
+        // Upload while reading: with the picture count known (raw / y4m files) and one device, the copies of this chunk
+        // are queued GOP group by GOP group as the reader delivers them, so the H2D transfer hides inside the file read
+        // and the encode below starts with its input (almost) resident.  A chunk that comes up short is uploaded again.
+        bool early = false;
+        if (ndev == 1 && src->exact_frames > total && !getenv("VCPENC_NO_EARLY_UPLOAD")) {
+            const int n_exp = (int)std::min<long>((long)chunk, src->exact_frames - total);
+            rc = prepare(n_exp);
+            if (rc) return fail(rc);
+            t_create += lap(tl);
+            Shard& sh = shards[0];
+            vcpenc_session_set_first_gop(sh.ses, sh.g0);
+            const int rg = vcpenc_session_upload_gated(sh.ses, fbuf[bi], n_exp, &progress[bi], &finished[bi], sh.err, sizeof sh.err);
+            if (rg == VCPENC_OK) early = true;
+            else if (rg != VCPENC_E_CANCELLED) { set_err(err, errlen, "%s", sh.err); return fail(rg); }
+        }
         {
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return filled[bi] >= 0; });
@@ -534,29 +582,16 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
         if (int sr = stop_reason()) { stop_message(sr); return fail(sr); }
         if (read_rc) { set_err(err, errlen, "%s", read_err); return fail(read_rc); }
         if (n > 0) {
-            // closed GOPs of this chunk, contiguous ranges per device
+            if (early && n != shards[0].n) early = false;   // the chunk came up short (or long): upload it again as it is
             const int ngops = (n + p.gop - 1) / p.gop;
             const int used = std::min(ndev, ngops);
-            for (int d = 0; d < ndev; d++) {
-                Shard& sh = shards[d];
-                const int ga = d < used ? (int)((long long)ngops * d / used) : 0, gb = d < used ? (int)((long long)ngops * (d + 1) / used) : 0;
-                sh.f0 = ga * p.gop; sh.n = std::min(n, gb * p.gop) - sh.f0; sh.g0 = gop_index + ga; sh.rc = 0; sh.len = 0;
-                if (sh.n <= 0) { sh.n = 0; continue; }
-                if (!sh.ses) {
-                    pkey.first_gop = 0;
-                    const int want = std::min((chunk / p.gop + used - 1) / used * p.gop, std::max(sh.n, 1));
-                    rc = acquire_session(pkey, sh.device, std::max(want, sh.n), &sh.ses, err, errlen);
-                    if (rc) return fail(rc);
-                }
-                sh.need_bits((size_t)sh.n * fb / 4 + (1 << 20));
-                if (sh.info.size() < (size_t)sh.n) sh.info.resize((size_t)sh.n);
-            }
+            if (!early) { rc = prepare(n); if (rc) return fail(rc); }
             t_create += lap(tl);
             auto run = [&](Shard& sh) {
                 if (!sh.n) return;
                 vcpenc_session_set_first_gop(sh.ses, sh.g0);          // idr_pic_id parity continues across ranges and chunks
                 // streamed: the pinned chunk buffer outlives the encode, whose GOP groups start as their frames land
-                sh.rc = vcpenc_session_upload_async(sh.ses, fbuf[bi] + (size_t)sh.f0 * sfb, sh.n, sh.err, sizeof sh.err);
+                if (!early) sh.rc = vcpenc_session_upload_async(sh.ses, fbuf[bi] + (size_t)sh.f0 * sfb, sh.n, sh.err, sizeof sh.err);
                 if (!sh.rc) sh.rc = vcpenc_session_encode(sh.ses, nullptr, sh.err, sizeof sh.err);
                 if (!sh.rc) {
                     sh.rc = vcpenc_session_download(sh.ses, sh.bits.get(), sh.bits_cap, &sh.len, sh.info.data(), nullptr, sh.err, sizeof sh.err);
@@ -576,7 +611,7 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
             t_gpu += lap(tl);
         }
         // the buffer is free again: the reader fills it while this chunk is written out
-        { std::lock_guard<std::mutex> lk(mu); filled[bi] = -1; cv.notify_all(); }
+        { std::lock_guard<std::mutex> lk(mu); filled[bi] = -1; progress[bi] = 0; finished[bi] = 0; cv.notify_all(); }
         if (int sr = stop_reason()) { stop_message(sr); return fail(sr); }
         if (n > 0) {
             if (!writer_open) {
