@@ -490,7 +490,14 @@ void vcp_launch_deblock(const VcpGeom& g, const VcpBufs& b, const VcpStep& s, cu
     cudaMemsetAsync(sync, 0, (size_t)(s.ngop * g.mbh + 1) * sizeof(int), st);
     // function attributes are per device: a process may drive several GPUs from different threads
     static const unsigned spin_ns = [] { const char* e = getenv("VCPENC_DB_SPIN_NS"); return e ? (unsigned)atoi(e) : 0u; }();
-    static const int regs = [] { const char* e = getenv("VCPENC_DB_REGS"); return e ? atoi(e) : 80; }();   // measured: 126 -> 119.5, 80 -> 118.7, 64 (spills) -> 128.2 ms per 1080p step
+    // Register build by how crowded the machine is.  While every band CTA of the batch (all GOP groups' launches together)
+    // can have an SM of its own, the 126-register build is faster (1080p step, 80 vs 126 registers: 10 GOPs 68.4 / 57.0 ms,
+    // 16: 80.3 / 70.0, 24: 98.5 / 91.3); beyond that the CTAs hold registers the throughput kernels of the other groups
+    // need, and 80 wins (32 GOPs: 118.3 / 120.2; 64 registers spill: 128.2).
+    static const int forced = [] { const char* e = getenv("VCPENC_DB_REGS"); return e ? atoi(e) : 0; }();
+    static const int nsm = [] { int dev = 0, n = 148; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n > 0 ? n : 148; }();
+    const int total_gops = (s.nframes + s.gop - 1) / s.gop;
+    const int regs = forced ? forced : (total_gops * nbands <= nsm ? 126 : 80);
     int* progress = sync + 1 - (size_t)s.g0 * g.mbh;
     if (regs >= 120) deblock_kernel<512><<<s.ngop * nbands, BH * 32, smem, st>>>(g, b, s, BH, nbands, sync, progress, spin_ns);
     else if (regs >= 72) deblock_kernel<768><<<s.ngop * nbands, BH * 32, smem, st>>>(g, b, s, BH, nbands, sync, progress, spin_ns);
