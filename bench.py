@@ -569,6 +569,38 @@ def e2e_transcode(cx: Ctx, wl: Workload, frames2: np.ndarray, tokens: str, clips
             out[label] = {"frames_per_task": n, "tasks": 2 * reps, "fps": round(2 * reps * n / dt, 1), "seconds": round(dt, 3),
                           "mp4_bytes": os.path.getsize(dsts[0]), "verify": ok, "file_read_ceiling_fps": read_fps,
                           "of_read_ceiling": round(2 * reps * n / dt / read_fps, 3) if read_fps else None}
+            if gops <= 8 and ok:
+                # what the producer really forwards (cmd/producer.go:485-488): a CONTAINER file.  The mp4 just written goes
+                # back in: demux + CPU decode (libavcodec, frame threads) in the reader thread, encode on the GPU.
+                src2 = os.path.join(base, "vcp_bench_%d_%s_in.mp4" % (os.getpid(), label))
+                os.replace(dsts[0], src2)
+                try:
+                    def task2(i, reps2):
+                        try:
+                            api.set_thread_device(cx.local_rank)
+                            for _ in range(reps2):
+                                api.transcode(src2, dsts[i], tokens)
+                        except Exception as ex:  # noqa: BLE001
+                            errs.append(ex)
+                    for r2 in (1, 2):                       # warm-up round, timed round
+                        t0 = time.perf_counter()
+                        ths = [threading.Thread(target=task2, args=(i, r2)) for i in range(2)]
+                        for t in ths:
+                            t.start()
+                        for t in ths:
+                            t.join()
+                        dt2 = time.perf_counter() - t0
+                    if errs:
+                        raise errs[0]
+                    api.verify(dsts[0])
+                    out[label + "_mp4_in"] = {"input": "the H.264 mp4 of the leg above (%d bytes)" % os.path.getsize(src2), "frames_per_task": n, "tasks": 4,
+                                              "fps": round(4 * n / dt2, 1), "seconds": round(dt2, 3), "verify": True,
+                                              "note": "bound by the CPU decode of the input (libavcodec h264, frame threads), not by the encoder"}
+                except Exception as ex:  # noqa: BLE001
+                    out[label + "_mp4_in"] = {"error": str(ex)[:200]}
+                finally:
+                    if os.path.exists(src2):
+                        os.remove(src2)
         except Exception as ex:  # noqa: BLE001
             out[label] = {"error": str(ex)[:200]}
         finally:
