@@ -197,6 +197,55 @@ def test_transcode_foreign_containers_and_codecs(built, tmp_path):
 
 
 @pytest.mark.timeout(300)
+def test_transcode_uploads_while_reading(built, tmp_path, monkeypatch):
+    """raw / y4m inputs: the copies of a chunk are queued while the reader still delivers it (vcpenc_session_upload_gated).
+    Same file as with the path switched off; a y4m whose FRAME markers carry parameters (the picture count computed from
+    the file size is then too high: the chunk comes up short) and a file cut in the middle of a picture fall back to the
+    plain upload and still give the right pictures; headerless raw input (.yuv, -s WxH) takes the same path."""
+    w, h, n = 320, 192, 47
+    clip = synth.make_clip(w, h, n, seed=33)
+    hdr = b"YUV4MPEG2 W%d H%d F30:1 Ip A1:1 C420\n" % (w, h)
+    bare = str(tmp_path / "bare.y4m")
+    with open(bare, "wb") as f:
+        f.write(hdr)
+        for fr in clip:
+            f.write(b"FRAME\n" + fr.tobytes())
+    marked = str(tmp_path / "marked.y4m")
+    with open(marked, "wb") as f:
+        f.write(hdr)
+        for fr in clip:
+            f.write(b"FRAME Ip\n" + fr.tobytes())
+    cut = str(tmp_path / "cut.y4m")
+    with open(cut, "wb") as f:
+        f.write(open(bare, "rb").read()[:len(hdr) + 30 * (6 + clip.shape[1]) + 1000])      # 30 whole pictures + a stump
+    raw = str(tmp_path / "in.yuv")
+    clip.tofile(raw)
+    args = H264_CPU + " -g 6"
+    outs = {}
+    for chunk in (None, 6 * 2 * clip.shape[1]):          # one chunk; chunks of two GOPs
+        if chunk:
+            monkeypatch.setenv("VCPENC_CHUNK_BYTES", str(chunk))
+        for name, src, a in (("bare", bare, args), ("marked", marked, args), ("raw", raw, "-s %dx%d -r 30 " % (w, h) + args)):
+            out = str(tmp_path / ("%s_%s.mp4" % (name, chunk)))
+            api.transcode(src, out, a)
+            outs[(name, chunk)] = open(out, "rb").read()
+        monkeypatch.setenv("VCPENC_NO_EARLY_UPLOAD", "1")
+        off = str(tmp_path / ("off_%s.mp4" % chunk))
+        api.transcode(bare, off, args)
+        monkeypatch.delenv("VCPENC_NO_EARLY_UPLOAD")
+        assert outs[("bare", chunk)] == open(off, "rb").read()
+        assert outs[("marked", chunk)] == outs[("bare", chunk)] == outs[("raw", chunk)]
+        out = str(tmp_path / ("cut_%s.mp4" % chunk))
+        api.transcode(cut, out, args)
+        if arbiter.available():
+            assert len(arbiter.decode_file(out)) == 30
+    assert outs[("bare", None)] == outs[("bare", 6 * 2 * clip.shape[1])]
+    if arbiter.available():
+        dec = arbiter.decode_file(str(tmp_path / "bare_None.mp4"))
+        assert len(dec) == n and arbiter.psnr(dec[n - 1][0], synth.split_planes(clip[n - 1], w, h)[0]) > 32
+
+
+@pytest.mark.timeout(300)
 def test_transcode_many_chunks_cancel_and_timeout(built, tmp_path, monkeypatch):
     """the double-buffered reader: a clip forced into many small chunks gives the same file as one chunk; a cancel flag
     set beforehand and an expired deadline stop the task with the reference's error classes and leave no output"""
