@@ -199,6 +199,11 @@ int vcpenc_session_upload_async(vcpenc_session* s, const uint8_t* frames, int nf
  * VCPENC_E_CANCELLED when *finished becomes non-zero before `nframes` pictures exist (upload again with what there is). */
 int vcpenc_session_upload_gated(vcpenc_session* s, const uint8_t* frames, int nframes, const volatile long* ready,
                                 const volatile int* finished, char* err, size_t errlen);
+/* vcpenc_session_upload_gated and vcpenc_session_encode in one call: the encode of a group of GOPs is queued right behind
+ * its copy, so the first groups are being encoded while the producer still delivers the last ones.  Returns when the
+ * bitstream is complete on the device (download next), or VCPENC_E_CANCELLED as above (nothing was encoded). */
+int vcpenc_session_encode_gated(vcpenc_session* s, const uint8_t* frames, int nframes, const volatile long* ready,
+                                const volatile int* finished, char* err, size_t errlen);
 /* same, but the raw frames are already in device memory (`dframes` is a device pointer):
  * runs K1 only.  `ms` (optional) receives the CUDA-event time on the launching stream. */
 int vcpenc_session_upload_device(vcpenc_session* s, const uint8_t* dframes, int nframes, float* ms,

@@ -548,10 +548,14 @@ static void group_gops(const vcpenc_session* s, int N, int ng, int k, int* gA, i
     *gA = (int)((long long)ngop_total * k / ng); *gB = (int)((long long)ngop_total * (k + 1) / ng);
 }
 
+static int run_encode(vcpenc_session* s, char* err, size_t errlen, int konly = -1, int phase = 3);
+
 // ready / finished (both or neither): the caller is still filling `frames`; piece k is queued once *ready pictures exist,
-// and the call gives up with VCPENC_E_CANCELLED when *finished is set before that (the producer stopped short)
+// and the call gives up with VCPENC_E_CANCELLED when *finished is set before that (the producer stopped short).
+// fused: the encode of GOP group k is queued right behind its piece (vcpenc_session_encode_gated), so that the first
+// groups are being encoded while the producer still delivers the last ones.
 static int upload_host(vcpenc_session* s, const uint8_t* frames, int nframes, bool wait, char* err, size_t errlen,
-                       const volatile long* ready = nullptr, const volatile int* finished = nullptr) {
+                       const volatile long* ready = nullptr, const volatile int* finished = nullptr, bool fused = false) {
     if (!s || !frames || nframes < 1 || nframes > s->max_frames) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
     CK(cudaSetDevice(s->device));
     const size_t fb = s->in_fb;
@@ -565,28 +569,42 @@ static int upload_host(vcpenc_session* s, const uint8_t* frames, int nframes, bo
     // copies); K1 trails the copies piece by piece.  Pieces = the GOP groups of the encode, so that a
     // streamed upload (wait = false) lets group k start its chain as soon as ITS frames have landed.
     const int ng = s->profile ? 1 : group_count(s, nframes);
+    if (fused) {
+        if (s->profile || !ready) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
+        s->streamed = true;
+        const int rc = run_encode(s, err, errlen, -2, 1);
+        if (rc) return rc;
+    }
     for (int k = 0; k < ng; k++) {
         int gA, gB;
         group_gops(s, nframes, ng, k, &gA, &gB);
         const int n0 = gA * s->p.gop, n1 = std::min(nframes, gB * s->p.gop);
         if (n1 <= n0) { CK(cudaEventRecord(s->ev_piece[k], s->st_up)); continue; }
         if (ready) {
-            while (*ready < n1) {
-                if (finished && *finished && *ready < n1) {
-                    s->nframes = 0;     // nothing usable was declared: the caller uploads again
-                    set_err(err, errlen, "input ended after %ld of %d pictures", (long)*ready, nframes);
-                    return VCPENC_E_CANCELLED;
+            // gated: GOP by GOP, so that the copy trails the producer by one GOP, not by one piece
+            for (int a = n0; a < n1; a += s->p.gop) {
+                const int e = std::min(n1, a + s->p.gop);
+                while (*ready < e) {
+                    if (finished && *finished && *ready < e) {
+                        if (fused) { run_encode(s, err, errlen, -2, 2); cudaStreamSynchronize(s->st); }   // drain what was queued
+                        s->nframes = 0;     // nothing usable was declared: the caller uploads again
+                        set_err(err, errlen, "input ended after %ld of %d pictures", (long)*ready, nframes);
+                        return VCPENC_E_CANCELLED;
+                    }
+                    std::this_thread::sleep_for(std::chrono::microseconds(50));
                 }
-                std::this_thread::sleep_for(std::chrono::microseconds(50));
+                std::atomic_thread_fence(std::memory_order_acquire);
+                CK(cudaMemcpyAsync(s->raw_dev + (size_t)a * fb, frames + (size_t)a * fb, (size_t)(e - a) * fb, cudaMemcpyHostToDevice, s->st_copy));
             }
-            std::atomic_thread_fence(std::memory_order_acquire);
-        }
+        } else
         CK(cudaMemcpyAsync(s->raw_dev + (size_t)n0 * fb, frames + (size_t)n0 * fb, (size_t)(n1 - n0) * fb, cudaMemcpyHostToDevice, s->st_copy));
         CK(cudaEventRecord(s->staging_ready[k & 1], s->st_copy));
         CK(cudaStreamWaitEvent(s->st_up, s->staging_ready[k & 1], 0));
         k1_chain(s, s->raw_dev + (size_t)n0 * fb, n0, n1 - n0, s->st_up);
         CK(cudaEventRecord(s->ev_piece[k], s->st_up));
+        if (fused) { const int rc = run_encode(s, err, errlen, k, 0); if (rc) return rc; }
     }
+    if (fused) { const int rc = run_encode(s, err, errlen, -2, 2); if (rc) return rc; }
     CK(cudaGetLastError());
     s->streamed = !wait && !s->profile;
     if (!s->streamed) {
@@ -641,25 +659,32 @@ uint64_t vcpenc_session_launch_count(vcpenc_session* s) { return s ? s->launches
 // 1 pre-pass, 2 refine, 4 p_recon, 8 deblock, 16 hpel, 32 CAVLC, 64 mbinfo/pad -- the marginal cost of a kernel inside the overlapped step
 static const int g_dbg_skip = [] { const char* e = getenv("VCPENC_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
 
-static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
+// The whole encode of the resident pictures, queued on the session's streams (nothing here waits for the device).
+// konly / phase: the gated encode (vcpenc_session_encode_gated) issues it in pieces -- phase bit 0 = the prologue
+// (cursors reset, fork from the session stream), bit 1 = the epilogue (every stream joined back), konly = k: the
+// pre-pass and the chain of GOP group k alone, -2: no group.  The default is everything at once.
+static int run_encode(vcpenc_session* s, char* err, size_t errlen, int konly, int phase) {
     const VcpGeom& g = s->g;
     const VcpBufs& b = s->b;
     const int N = s->nframes, gop = s->p.gop;
-    CK(cudaMemsetAsync(b.out_cursor, 0, sizeof(unsigned long long), s->st));
-    CK(cudaMemsetAsync(b.error_flag, 0, sizeof(int), s->st));
-    CK(cudaMemsetAsync(b.frame_bits, 0, (size_t)N * sizeof(uint32_t), s->st));
-    if (g.cabac) {
-        CK(cudaMemsetAsync(b.bins_cursor, 0, sizeof(unsigned long long), s->st));
-        CK(cudaMemsetAsync(b.crbsp_cursor, 0, sizeof(unsigned long long), s->st));
-        CK(cudaMemsetAsync(b.sbins_cursor, 0, sizeof(unsigned long long), s->st));
-        CK(cudaMemsetAsync(b.slice_bins, 0, (size_t)N * g.slices * sizeof(uint32_t), s->st));
-        CK(cudaMemsetAsync(b.out_index, 0, (size_t)N * g.slices * sizeof(uint2), s->st));
+    if (phase & 1) {
+        CK(cudaMemsetAsync(b.out_cursor, 0, sizeof(unsigned long long), s->st));
+        CK(cudaMemsetAsync(b.error_flag, 0, sizeof(int), s->st));
+        CK(cudaMemsetAsync(b.frame_bits, 0, (size_t)N * sizeof(uint32_t), s->st));
+        if (g.cabac) {
+            CK(cudaMemsetAsync(b.bins_cursor, 0, sizeof(unsigned long long), s->st));
+            CK(cudaMemsetAsync(b.crbsp_cursor, 0, sizeof(unsigned long long), s->st));
+            CK(cudaMemsetAsync(b.sbins_cursor, 0, sizeof(unsigned long long), s->st));
+            CK(cudaMemsetAsync(b.slice_bins, 0, (size_t)N * g.slices * sizeof(uint32_t), s->st));
+            CK(cudaMemsetAsync(b.out_index, 0, (size_t)N * g.slices * sizeof(uint2), s->st));
+        }
     }
     const int T = std::min(gop, N);
     // GOP groups advance on their own streams: the latency-bound wavefront kernels (intra
     // recon, deblocking) of one group overlap the throughput-bound kernels of the others.
     // Per-kernel profiling wants clean timings, so it runs everything on one stream.
     const int ng = s->profile ? 1 : group_count(s, N);
+    const int kA = konly == -1 ? 0 : (konly < 0 ? 0 : konly), kB = konly == -1 ? ng : (konly < 0 ? 0 : konly + 1);   // groups issued by this call
     const bool streamed = s->streamed && !s->profile;
     if (s->streamed && s->profile) CK(cudaStreamSynchronize(s->st_up));   // profiling was switched on after an asynchronous upload
     if (s->profile) {
@@ -669,8 +694,10 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
         // picture by picture and group by group on its own stream: chain step t of a group only waits for
         // the vectors of picture t of its GOPs.  Resident input: pictures outermost (every group gets its
         // first vectors early).  Streamed input: groups outermost, each behind the arrival of its frames.
-        CK(cudaEventRecord(s->ev_pre, s->st));
-        CK(cudaStreamWaitEvent(s->st_pre, s->ev_pre, 0));
+        if (phase & 1) {
+            CK(cudaEventRecord(s->ev_pre, s->st));
+            CK(cudaStreamWaitEvent(s->st_pre, s->ev_pre, 0));
+        }
         auto pre = [&](int k, int t) -> int {
             int gA, gB;
             group_gops(s, N, ng, k, &gA, &gB);
@@ -680,24 +707,24 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
             return VCPENC_OK;
         };
         if (streamed) {
-            for (int k = 0; k < ng; k++) {
+            for (int k = kA; k < kB; k++) {
                 CK(cudaStreamWaitEvent(s->st_pre, s->ev_piece[k], 0));
                 for (int t = 1; t < T; t++) { const int rc = pre(k, t); if (rc) return rc; }
             }
         } else {
             for (int t = 1; t < T; t++)
-                for (int k = 0; k < ng; k++) { const int rc = pre(k, t); if (rc) return rc; }
+                for (int k = kA; k < kB; k++) { const int rc = pre(k, t); if (rc) return rc; }
         }
     }
-    CK(cudaEventRecord(s->ev_pre, s->st));
-    for (int k = 0; k < ng; k++) {
+    if (phase & 1) CK(cudaEventRecord(s->ev_pre, s->st));   // (the session stream has not moved since the prologue)
+    for (int k = kA; k < kB; k++) {
         CK(cudaStreamWaitEvent(s->gst[k], s->ev_pre, 0));
         if (streamed) CK(cudaStreamWaitEvent(s->gst[k], s->ev_piece[k], 0));
     }
     for (int t = 0; t < gop && t < N; t++) {
         const int par = t & 1;
         const VcpBufs& bt = s->bpar[par];     // macroblock records of this step
-        for (int k = 0; k < ng; k++) {
+        for (int k = kA; k < kB; k++) {
             cudaStream_t st = s->profile ? s->st : s->gst[k];
             cudaStream_t se = s->profile ? s->st : s->est[k];   // entropy stream
             VcpStep sp;
@@ -787,7 +814,7 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
             if (t + 1 < gop && t + 1 < N && (!g.hevc || g.hevc_subpel)) { Prof pr(s, VCPENC_K_HPEL, 1, st); if (!(g_dbg_skip & 16)) vcp_launch_hpel(g, bt, sp, st); }
         }
     }
-    if (!s->profile)
+    if (!s->profile && (phase & 2))
         for (int k = 0; k < ng; k++) {
             CK(cudaEventRecord(s->gev[k], s->gst[k]));
             CK(cudaStreamWaitEvent(s->st, s->gev[k], 0));
@@ -802,16 +829,18 @@ static int run_encode(vcpenc_session* s, char* err, size_t errlen) {
     return VCPENC_OK;
 }
 
-int vcpenc_session_encode(vcpenc_session* s, float* ms, char* err, size_t errlen) {
-    if (!s || s->nframes < 1) { set_err(err, errlen, "no frames uploaded"); return VCPENC_E_ARGS; }
-    CK(cudaSetDevice(s->device));
+// issued: the first pass is already queued on the session's streams (vcpenc_session_encode_gated)
+static int encode_and_wait(vcpenc_session* s, float* ms, bool issued, char* err, size_t errlen) {
     int flag = 0;
     for (int attempt = 0;; attempt++) {
-        CK(cudaEventRecord(s->ev0, s->st));
+        int rc = 0;
         const auto h0 = std::chrono::steady_clock::now();
-        int rc = run_encode(s, err, errlen);
-        if (rc) return rc;
-        CK(cudaEventRecord(s->ev1, s->st));
+        if (!(issued && attempt == 0)) {
+            CK(cudaEventRecord(s->ev0, s->st));
+            rc = run_encode(s, err, errlen);
+            if (rc) return rc;
+            CK(cudaEventRecord(s->ev1, s->st));
+        } else ms = nullptr;
         const auto h1 = std::chrono::steady_clock::now();
         CK(cudaStreamSynchronize(s->st));
         if (getenv("VCPENC_TRACE_ENCODE")) {
@@ -834,6 +863,21 @@ int vcpenc_session_encode(vcpenc_session* s, float* ms, char* err, size_t errlen
     if (flag) { set_err(err, errlen, "bitstream buffer overflow on device (flag %d)", flag); return VCPENC_E_OVERFLOW; }
     s->encoded = true;
     return VCPENC_OK;
+}
+
+int vcpenc_session_encode(vcpenc_session* s, float* ms, char* err, size_t errlen) {
+    if (!s || s->nframes < 1) { set_err(err, errlen, "no frames uploaded"); return VCPENC_E_ARGS; }
+    CK(cudaSetDevice(s->device));
+    return encode_and_wait(s, ms, false, err, errlen);
+}
+
+// upload_gated + encode in one call: see include/vcpenc.h
+int vcpenc_session_encode_gated(vcpenc_session* s, const uint8_t* frames, int nframes, const volatile long* ready,
+                                const volatile int* finished, char* err, size_t errlen) {
+    if (!ready || !finished) { set_err(err, errlen, "bad arguments"); return VCPENC_E_ARGS; }
+    const int rc = upload_host(s, frames, nframes, false, err, errlen, ready, finished, true);
+    if (rc) return rc;
+    return encode_and_wait(s, nullptr, true, err, errlen);
 }
 
 int vcpenc_session_download(vcpenc_session* s, uint8_t* out, size_t out_cap, size_t* out_len,

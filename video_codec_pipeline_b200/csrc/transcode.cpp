@@ -558,9 +558,10 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
     for (int bi = 0;; bi = (bi + 1) % nbuf) {
         int n = 0;
         bool is_last = false;
-        // Upload while reading: with the picture count known (raw / y4m files) and one device, the copies of this chunk
-        // are queued GOP group by GOP group as the reader delivers them, so the H2D transfer hides inside the file read
-        // and the encode below starts with its input (almost) resident.  A chunk that comes up short is uploaded again.
+        // Upload and encode while reading: with the picture count known (raw / y4m files) and one device, the copies of this
+        // chunk are queued GOP by GOP as the reader delivers them and the encode of every GOP group right behind its
+        // copies, so the H2D transfer hides inside the file read and the first groups are done when the last one arrives.
+        // A chunk that comes up short is uploaded and encoded again as it is.
         bool early = false;
         if (ndev == 1 && src->exact_frames > total && !getenv("VCPENC_NO_EARLY_UPLOAD")) {
             const int n_exp = (int)std::min<long>((long)chunk, src->exact_frames - total);
@@ -569,7 +570,7 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
             t_create += lap(tl);
             Shard& sh = shards[0];
             vcpenc_session_set_first_gop(sh.ses, sh.g0);
-            const int rg = vcpenc_session_upload_gated(sh.ses, fbuf[bi], n_exp, &progress[bi], &finished[bi], sh.err, sizeof sh.err);
+            const int rg = vcpenc_session_encode_gated(sh.ses, fbuf[bi], n_exp, &progress[bi], &finished[bi], sh.err, sizeof sh.err);
             if (rg == VCPENC_OK) early = true;
             else if (rg != VCPENC_E_CANCELLED) { set_err(err, errlen, "%s", sh.err); return fail(rg); }
         }
@@ -591,8 +592,10 @@ extern "C" int vcpenc_transcode(const char* input, const char* output, int argc,
                 if (!sh.n) return;
                 vcpenc_session_set_first_gop(sh.ses, sh.g0);          // idr_pic_id parity continues across ranges and chunks
                 // streamed: the pinned chunk buffer outlives the encode, whose GOP groups start as their frames land
-                if (!early) sh.rc = vcpenc_session_upload_async(sh.ses, fbuf[bi] + (size_t)sh.f0 * sfb, sh.n, sh.err, sizeof sh.err);
-                if (!sh.rc) sh.rc = vcpenc_session_encode(sh.ses, nullptr, sh.err, sizeof sh.err);
+                if (!early) {
+                    sh.rc = vcpenc_session_upload_async(sh.ses, fbuf[bi] + (size_t)sh.f0 * sfb, sh.n, sh.err, sizeof sh.err);
+                    if (!sh.rc) sh.rc = vcpenc_session_encode(sh.ses, nullptr, sh.err, sizeof sh.err);
+                }
                 if (!sh.rc) {
                     sh.rc = vcpenc_session_download(sh.ses, sh.bits.get(), sh.bits_cap, &sh.len, sh.info.data(), nullptr, sh.err, sizeof sh.err);
                     if (sh.rc == VCPENC_E_OVERFLOW) {
