@@ -81,7 +81,8 @@ typedef struct vcpenc_params {
     int32_t in_width, in_height; /* size of the frames handed in (0 = same as out)  */
     int32_t faststart;         /* -movflags +faststart: moov before mdat            */
     int32_t effort;            /* from -preset: 0 fast tiers (ultrafast..fast, p1..p3): the motion refine stops at half
-                                  samples; 1 medium (medium, p4, p5; the default); 2 slow (slow.., p6, p7): as medium so far */
+                                  samples and inter macroblocks are not decimated; 1 medium (medium, p4, p5; the default);
+                                  2 slow (slow.., p6, p7): as medium so far */
     int32_t debug;             /* 1: keep every reconstructed picture and per-MB
                                   decisions resident for the parity taps            */
     int32_t first_gop;         /* index of the first GOP handed in (sharded encodes):

@@ -695,48 +695,75 @@ static void encode_p_mb(Enc* e, const Frame* ref, Frame* rec, int mx, int my, in
     const uint8_t* src = e->cur.y + (size_t)(16 * my) * e->cur.ys + 16 * mx;
     uint8_t* dst = rec->y + (size_t)(16 * my) * rec->ys + 16 * mx;
     mb->t8x8 = 0;
+    /* Coefficient decimation (vcp_algo.h: vcp_decimate_*): an 8x8 luma group of an inter macroblock that holds only a
+     * few isolated +-1 levels costs more bits than the distortion it removes -- such groups, or the whole macroblock,
+     * are coded as zero (not in the fast -preset tiers, effort 0).  The scores walk the levels in scan order. */
+    int score[4];
     if (e->p.transform8x8 && prefer_8x8(src, e->cur.ys, pred)) {
         /* High profile: the four 8x8 luma blocks of an inter macroblock */
+        int16_t lv8[4][64];
         for (int k = 0; k < 4; k++) {
-            int bx = (k & 1) * 8, by = (k >> 1) * 8, d[64], w[64], c[64], r[64];
-            int16_t lv8[64];
+            int bx = (k & 1) * 8, by = (k >> 1) * 8, d[64], w[64];
             for (int y = 0; y < 8; y++)
                 for (int x = 0; x < 8; x++)
                     d[y * 8 + x] = src[(by + y) * e->cur.ys + bx + x] - pred[(by + y) * 16 + bx + x];
             fdct8(d, w);
-            int nz = quant8x8(w, qp, 0, lv8);
+            quant8x8(w, qp, 0, lv8[k]);
+            uint64_t mask = 0; int big = 0;
+            for (int i = 0; i < 64; i++) { if (lv8[k][i]) mask |= 1ull << i; if (lv8[k][i] > 1 || lv8[k][i] < -1) big = 1; }
+            score[k] = vcp_decimate_score(mask, big, 1);
+        }
+        const int tot = score[0] + score[1] + score[2] + score[3];
+        for (int k = 0; k < 4; k++) {
+            int bx = (k & 1) * 8, by = (k >> 1) * 8, c[64], r[64];
+            if (e->p.effort > 0 && vcp_decimate_zero(score[k], tot)) memset(lv8[k], 0, sizeof lv8[k]);
+            int nz = 0;
+            for (int i = 0; i < 64; i++) nz += lv8[k][i] != 0;
             if (nz) mb->cbp |= (uint8_t)(1 << k);
             int cnt4[4] = {0, 0, 0, 0};
             for (int i = 0; i < 64; i++) {
-                if (e->p.entropy) mb->lv[VCP_LV_LUMA + k * 64 + i] = lv8[i];
-                else mb->lv[VCP_LV_LUMA + (k * 4 + (i & 3)) * 16 + (i >> 2)] = lv8[i];
-                cnt4[i & 3] += lv8[i] != 0;
+                if (e->p.entropy) mb->lv[VCP_LV_LUMA + k * 64 + i] = lv8[k][i];
+                else mb->lv[VCP_LV_LUMA + (k * 4 + (i & 3)) * 16 + (i >> 2)] = lv8[k][i];
+                cnt4[i & 3] += lv8[k][i] != 0;
             }
             for (int j = 0; j < 4; j++)   /* luma4x4BlkIdx 4k+j */
                 mb->nnz_y[vcp_blk_y[4 * k + j] * 4 + vcp_blk_x[4 * k + j]] = (uint8_t)(e->p.entropy ? nz : cnt4[j]);
-            dequant8x8(lv8, qp, c);
+            dequant8x8(lv8[k], qp, c);
             idct8(c, r);
             for (int y = 0; y < 8; y++)
                 for (int x = 0; x < 8; x++)
                     dst[(by + y) * rec->ys + bx + x] = (uint8_t)vcp_clip255(pred[(by + y) * 16 + bx + x] + r[y * 8 + x]);
         }
         mb->t8x8 = (mb->cbp & 15) != 0;   /* the flag is only transmitted (else inferred 0) with coded luma */
-    } else
-    for (int b = 0; b < 16; b++) {
-        int bx = vcp_blk_x[b] * 4, by = vcp_blk_y[b] * 4, d[16], w[16], c[16], r[16];
-        for (int y = 0; y < 4; y++)
-            for (int x = 0; x < 4; x++)
-                d[y * 4 + x] = src[(by + y) * e->cur.ys + bx + x] - pred[(by + y) * 16 + bx + x];
-        fdct4(d, w);
-        int16_t* lv = mb->lv + VCP_LV_LUMA + b * 16;
-        int nz = quant4x4(w, qp, 0, 0, lv);
-        mb->nnz_y[vcp_blk_y[b] * 4 + vcp_blk_x[b]] = (uint8_t)nz;
-        if (nz) mb->cbp |= (uint8_t)(1 << (b >> 2));
-        dequant4x4(lv, qp, 0, c);
-        idct4(c, r);
-        for (int y = 0; y < 4; y++)
-            for (int x = 0; x < 4; x++)
-                dst[(by + y) * rec->ys + bx + x] = (uint8_t)vcp_clip255(pred[(by + y) * 16 + bx + x] + r[y * 4 + x]);
+    } else {
+        score[0] = score[1] = score[2] = score[3] = 0;
+        for (int b = 0; b < 16; b++) {
+            int bx = vcp_blk_x[b] * 4, by = vcp_blk_y[b] * 4, d[16], w[16];
+            for (int y = 0; y < 4; y++)
+                for (int x = 0; x < 4; x++)
+                    d[y * 4 + x] = src[(by + y) * e->cur.ys + bx + x] - pred[(by + y) * 16 + bx + x];
+            fdct4(d, w);
+            int16_t* lv = mb->lv + VCP_LV_LUMA + b * 16;
+            quant4x4(w, qp, 0, 0, lv);
+            uint64_t mask = 0; int big = 0;
+            for (int i = 0; i < 16; i++) { if (lv[i]) mask |= 1ull << i; if (lv[i] > 1 || lv[i] < -1) big = 1; }
+            score[b >> 2] += vcp_decimate_score(mask, big, 0);
+        }
+        const int tot = score[0] + score[1] + score[2] + score[3];
+        for (int b = 0; b < 16; b++) {
+            int bx = vcp_blk_x[b] * 4, by = vcp_blk_y[b] * 4, c[16], r[16];
+            int16_t* lv = mb->lv + VCP_LV_LUMA + b * 16;
+            if (e->p.effort > 0 && vcp_decimate_zero(score[b >> 2], tot)) memset(lv, 0, 16 * sizeof(int16_t));
+            int nz = 0;
+            for (int i = 0; i < 16; i++) nz += lv[i] != 0;
+            mb->nnz_y[vcp_blk_y[b] * 4 + vcp_blk_x[b]] = (uint8_t)nz;
+            if (nz) mb->cbp |= (uint8_t)(1 << (b >> 2));
+            dequant4x4(lv, qp, 0, c);
+            idct4(c, r);
+            for (int y = 0; y < 4; y++)
+                for (int x = 0; x < 4; x++)
+                    dst[(by + y) * rec->ys + bx + x] = (uint8_t)vcp_clip255(pred[(by + y) * 16 + bx + x] + r[y * 4 + x]);
+        }
     }
     encode_chroma(e, mb, rec, mx, my, qp, 0, pu, pv);
 }
@@ -1657,6 +1684,7 @@ int orc_ue_bits(unsigned k, uint8_t* out) { BW b; bw_init(&b, out, 8); bw_ue(&b,
 int orc_se_bits(int v, uint8_t* out) { BW b; bw_init(&b, out, 8); bw_se(&b, v); int n = (int)bw_bits(&b); if (b.nbits) bw_put(&b, 8 - b.nbits, 0); return n; }
 int orc_luma_qpel(const uint8_t* plane, int stride, int ix, int iy, int fx, int fy) { return luma_qpel(plane, stride, ix, iy, fx, fy); }
 int orc_lambda(int qp) { return vcp_lambda(qp); }
+int orc_decimate_score(unsigned long long mask, int big, int is8x8) { return vcp_decimate_score(mask, big, is8x8); }
 void orc_fdct8(const int* d, int* w) { fdct8(d, w); }
 void orc_roundtrip8(const int* d, int qp, int* r) {
     int w[64], c[64]; int16_t lv[64];

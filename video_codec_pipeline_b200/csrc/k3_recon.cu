@@ -126,11 +126,30 @@ __device__ __forceinline__ uint32_t luma8x8_transform(const VcpGeom& g, const Vc
 #pragma unroll
         for (int r = 0; r < 8; r++) in[r] = T[8 * r + ((q + r) & 7)];
         fdct8_1d(in, w);
+        // quantise; then the decimation rule (vcp_algo.h: vcp_decimate_score over the block's levels in scan order, the
+        // macroblock total over the four blocks) decides whether the block is coded at all
+        int lq[8];
+        unsigned long long m = 0ull;
+        bool bigl = false;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int i = 8 * r + q;
+            const int l = vcp_quant1(w[r], TT.mf[rem][TT.cls[i]], f, qbits);
+            lq[r] = l;
+            if (l) m |= 1ull << TT.izz[i];
+            bigl |= l > 1 || l < -1;
+        }
+        m |= __shfl_xor_sync(0xffffffffu, m, 1); m |= __shfl_xor_sync(0xffffffffu, m, 2); m |= __shfl_xor_sync(0xffffffffu, m, 4);
+        const int big = (__ballot_sync(0xffffffffu, bigl) >> (8 * k)) & 0xff;
+        const int sc = vcp_decimate_score(m, big, 1);
+        int tot = sc + __shfl_xor_sync(0xffffffffu, sc, 8);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+        const bool drop = g.effort > 0 && vcp_decimate_zero(sc, tot) != 0;
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             const int i = 8 * r + q;
             const int cls = TT.cls[i], zz = TT.izz[i];
-            const int l = vcp_quant1(w[r], TT.mf[rem][cls], f, qbits);
+            const int l = drop ? 0 : lq[r];
             nz += l != 0;
             cnt4 += (l != 0) << (8 * (zz & 3));
             lvp[g.cabac ? k * 64 + zz : (k * 4 + (zz & 3)) * 16 + (zz >> 2)] = (int16_t)l;
@@ -187,7 +206,7 @@ __device__ __forceinline__ void store_block_recon(uint8_t* dst, int stride, cons
 // intra16: luma DC goes through the 4x4 Hadamard (dcbuf = 16 ints of shared scratch).
 __device__ __forceinline__ void mb_transform(const VcpGeom& g, const VcpBufs& b, int n, int slot, int gi, int mbi,
                                              int mx, int my, int qp, bool intra16, const uint32_t predw[4],
-                                             int* dcbuf, int lane, uint32_t& cbp_out, bool luma_off = false) {
+                                             int* dcbuf, int lane, uint32_t& cbp_out, bool luma_off = false, bool decimate = false) {
     const int qpc = vcp_chroma_qp[vcp_clip3(0, 51, qp)];
     const bool is_luma = lane < 16 && !luma_off, is_chroma = lane >= 16 && lane < 24;
     const int pl = (lane - 16) >> 2, cb = lane & 3;
@@ -224,6 +243,25 @@ __device__ __forceinline__ void mb_transform(const VcpGeom& g, const VcpBufs& b,
     }
     const bool ac_only = is_chroma || (is_luma && intra16);
     if (is_luma || is_chroma) nz = vcp_quant_dequant4x4(w, is_luma ? qp : qpc, intra16, ac_only ? 1 : 0, lv, c);
+    if (decimate) {   // inter macroblocks (warp-uniform): vcp_algo.h, vcp_decimate_score
+        int sc = 0;
+        if (is_luma) {
+            unsigned long long m = 0ull;
+            bool big = false;
+#pragma unroll
+            for (int i = 0; i < 16; i++) { if (lv[i]) m |= 1ull << i; big |= lv[i] > 1 || lv[i] < -1; }
+            sc = vcp_decimate_score(m, big, 0);
+        }
+        int g8 = sc + __shfl_xor_sync(0xffffffffu, sc, 1);
+        g8 += __shfl_xor_sync(0xffffffffu, g8, 2);                 // the four blocks of this lane's 8x8 group
+        int tot = g8 + __shfl_xor_sync(0xffffffffu, g8, 4);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 8);               // lanes 0..15: the macroblock
+        if (is_luma && vcp_decimate_zero(g8, tot)) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) { lv[i] = 0; c[i] = 0; }
+            nz = 0;
+        }
+    }
 
     // chroma DC (lanes 16..23; all lanes execute the shuffles)
     {
@@ -310,7 +348,7 @@ __device__ __forceinline__ void mb_transform(const VcpGeom& g, const VcpBufs& b,
 // ---- P macroblocks ---------------------------------------------------------------------------
 constexpr int PR_WARPS = 4;
 
-__global__ void __launch_bounds__(PR_WARPS * 32) p_recon_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
+__global__ void __launch_bounds__(PR_WARPS * 32, 8) p_recon_kernel(VcpGeom g, VcpBufs b, VcpStep s) {
     __shared__ McScratch scr[PR_WARPS];
     __shared__ uint8_t cpred[PR_WARPS][2][8][8];
     __shared__ T8Tables t8t;
@@ -386,7 +424,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32) p_recon_kernel(VcpGeom g, VcpBu
         cbp = (cbp & ~15u) | cbpl;
         use8 = cbpl != 0;   // transform_size_8x8_flag is only transmitted (else inferred 0) with coded luma
     } else {
-        mb_transform(g, b, n, slot, gi, mbi, mx, my, qp, false, predw, nullptr, lane, cbp);
+        mb_transform(g, b, n, slot, gi, mbi, mx, my, qp, false, predw, nullptr, lane, cbp, false, g.effort > 0);
     }
     if (lane == 0) {
         b.cbp[(size_t)gi * g.nmb + mbi] = (uint8_t)cbp;
